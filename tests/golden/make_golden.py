@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference in the build container.
+
+Usage (build container only -- /root/reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Recipe: put the reference's flat-import directory on sys.path, stub the
+missing `h5py` module, import `models`, `inference`, `train` unchanged.  Noise is injected by
+temporarily replacing `torch.randn` / `torch.randn_like` (the reference draws from the global
+RNG).  Weights/inputs come from tests/golden/weights.py (numpy PCG64) so the tests
+can regenerate them anywhere.  Nothing from the reference is copied into the repo: only its
+numerical outputs are stored.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from weights import make_state_dict, synthetic_chirps, gaussian  # noqa: E402
+
+REF = "/root/reference/src/snr_denoising"
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    import models as ref_models          # noqa
+    import inference as ref_inf          # noqa
+    import train as ref_train            # noqa
+    return ref_models, ref_inf, ref_train
+
+
+class NoiseInjector:
+    """Replace torch.randn / torch.randn_like by a queue of pre-drawn tensors."""
+
+    def __init__(self, draws):
+        self.draws = list(draws)
+        self.k = 0
+
+    def _next(self, shape):
+        z = self.draws[self.k]
+        self.k += 1
+        assert tuple(z.shape) == tuple(shape), (z.shape, shape)
+        return z.clone()
+
+    def __enter__(self):
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+        torch.randn = lambda *s, **kw: self._next(s[0] if len(s) == 1 and not isinstance(s[0], int) else s)
+        torch.randn_like = lambda x, **kw: self._next(x.shape)
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randn_like = self._randn, self._randn_like
+
+
+def sub(x: torch.Tensor) -> np.ndarray:
+    """Strided subsample that keeps fixtures small: every 4th channel, every 4th position."""
+    return x.detach()[:, ::4, ::4].contiguous().numpy()
+
+
+def build_model(M, in_ch, cond_in_ch, seed=0, base_ch=64):
+    model = M.UNet1D(in_ch=in_ch, base_ch=base_ch, cond_in_ch=cond_in_ch, use_selfcond=True)
+    sd = make_state_dict(in_ch=in_ch, cond_in_ch=cond_in_ch, base_ch=base_ch, seed=seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return model, sd
+
+
+def gen_schedule(M, I, out):
+    d = {}
+    diff = M.CustomDiffusion(T=1000)
+    d["betas"] = diff.betas.numpy()
+    d["alpha_bar"] = diff.alpha_bar.numpy()
+    d50 = M.CustomDiffusion(T=50)
+    d["alpha_bar_T50"] = d50.alpha_bar.numpy()
+    for (T, steps, st) in [(1000, 1000, None), (1000, 50, None), (1000, 10, 289), (1000, 7, 529), (1000, 200, 100),
+                           (1000, 1, None), (50, 50, None), (1000, 3, 0)]:
+        ts = I._build_t_schedule(T, steps, torch.device("cpu"), st)
+        d[f"sched_{T}_{steps}_{st}"] = ts.numpy()
+    tt = torch.tensor([0, 1, 24, 55, 289, 529, 998, 999])
+    d["temb_t"] = tt.numpy()
+    d["temb_128"] = M.TimeEmbedding(128, 999.0)(tt).numpy()
+    d["temb_33"] = M.TimeEmbedding(33, 49.0)(tt).numpy()
+    w = []
+    for mode in ["const", "tophat", "gauss"]:
+        for i in [0, 3, 5, 9]:
+            w.append(I._cfg_weight(i, 10, mode, 1.5, 0.5, 0.3))
+    d["cfg_w"] = np.array(w, dtype=np.float64)
+    d["t_for_snr"] = np.array([I.t_for_target_snr(diff, s) for s in [0.9, 2.0, 10.0, 20.0]])
+    d["snr_tab"] = I.snr_from_alpha_bar(diff.alpha_bar)
+    np.savez_compressed(os.path.join(out, "schedule.npz"), **d)
+
+
+def gen_forward(M, out):
+    for tag, in_ch, cc, L, B in [("c3_L256", 3, 1, 256, 2), ("c7_L256", 7, 5, 256, 2), ("c3_L500", 3, 1, 500, 1),
+                                 ("c7_L1024", 7, 5, 1024, 1)]:
+        model, _ = build_model(M, in_ch, cc, seed=0)
+        x = gaussian((B, in_ch, L), seed=100 + L + in_ch)
+        if cc == 5:   # metadata channels are tiled scalars (dataloader.py:219-222)
+            x[:, 2:6, :] = x[:, 2:6, :1].clone()
+        t = torch.tensor([24, 999][:B] if B == 2 else [529])
+        rec = {}
+        hooks = []
+
+        def mk(name):
+            def h(mod, inp, outp):
+                rec[name + ".in"] = sub(inp[0])
+                rec[name + ".raw"] = sub(outp)
+            return h
+        for i in range(3):
+            hooks.append(model.encoders[i][0].register_forward_hook(mk(f"enc{i}")))
+            hooks.append(model.decoders[i][0].register_forward_hook(mk(f"dec{i}")))
+        hooks.append(model.mid[0].register_forward_hook(mk("mid")))
+        hooks.append(model.final.register_forward_hook(mk("final")))
+        with torch.no_grad():
+            eps = model(x, t)
+        for h in hooks:
+            h.remove()
+        rec["eps"] = eps.numpy()
+        rec["t"] = t.numpy()
+        np.savez_compressed(os.path.join(out, f"forward_{tag}.npz"), **rec)
+
+
+CHAIN_CASES = {
+    # tag: kwargs
+    "ddim10_s289": dict(steps=10, eta=0.0, start_t=289, init_mode="noise", dc_weight=0.0, cfg_scale=1.0),
+    "ddpm12_full": dict(steps=12, eta=1.0, start_t=None, init_mode="noise", dc_weight=0.0, cfg_scale=1.0),
+    "ddpm_all_s40": dict(steps=41, eta=1.0, start_t=40, init_mode="scaled-noise", dc_weight=0.0, cfg_scale=1.0),
+    "cfg15_dc": dict(steps=10, eta=0.5, start_t=529, init_mode="y-blend", dc_weight=0.05, cfg_scale=1.5),
+    "cfg_tophat": dict(steps=8, eta=0.0, start_t=289, init_mode="noise", dc_weight=0.0, cfg_scale=2.0,
+                       cfg_mode="tophat", cfg_center=0.5, cfg_width=0.5),
+    "uonly": dict(steps=6, eta=1.0, start_t=289, init_mode="noise", dc_weight=0.0, cfg_scale=0.0,
+                  cfg_u_only_thresh=0.0),
+    "x0pred": dict(steps=6, eta=0.3, start_t=289, init_mode="noise", dc_weight=0.0, cfg_scale=1.0,
+                   pred_type="x0", eps_scale=0.9, cond_scale=1.1),
+}
+
+
+def gen_chains(M, I, out):
+    L = 256
+    for in_ch, cc in [(3, 1), (7, 5)]:
+        model, _ = build_model(M, in_ch, cc, seed=1)
+        diff = M.CustomDiffusion(T=1000)
+        data = synthetic_chirps(2, L, snr=10.0, seed=77)
+        y = data["y_norm"]
+        if cc == 5:
+            meta = gaussian((2, 4, 1), seed=5).expand(2, 4, L).contiguous() * 0.3
+            cond = torch.cat([y, meta], dim=1)
+        else:
+            cond = y
+        for tag, kw in CHAIN_CASES.items():
+            if cc == 5 and tag not in ("cfg15_dc", "ddim10_s289"):
+                continue
+            full = dict(T=1000, device=torch.device("cpu"), length=L, debug=False, x0_std_est=0.14,
+                        cond_scale=1.0, eps_scale=1.0, pred_type="eps", in_ch=in_ch, cond_in_ch=cc,
+                        use_selfcond=True, cfg_mode="const", cfg_center=0.5, cfg_width=0.3,
+                        cfg_u_only_thresh=0.0)
+            full.update(kw)
+            outs, xin, eh = [], [], []
+            for b in range(2):   # the reference sampler is batch-1 only
+                draws = [gaussian((1, 1, L), seed=9000 + 100 * b + k) for k in range(64)]
+                calls_x, calls_o = [], []
+                orig_forward = model.forward
+
+                def spy(xx, tt, _f=orig_forward):
+                    o = _f(xx, tt)
+                    calls_x.append(xx[:, :1].clone())
+                    calls_o.append(o.clone())
+                    return o
+                model.forward = spy
+                with NoiseInjector(draws) as inj:
+                    xr = I.ddim_sample(model, diff, cond[b:b + 1], **full)
+                    n_draws = inj.k
+                model.forward = orig_forward
+                outs.append(xr)
+                xin.append(torch.cat(calls_x, 0))
+                eh.append(torch.cat(calls_o, 0))
+            np.savez_compressed(os.path.join(out, f"chain_c{in_ch}_{tag}.npz"),
+                                x_final=torch.cat(outs, 0).numpy(),
+                                fwd_x=torch.stack(xin, 0).numpy(),      # [B, n_forward_calls, 1, L]
+                                fwd_out=torch.stack(eh, 0).numpy(),
+                                n_draws=np.array(n_draws))
+
+
+def gen_train(M, TR, out):
+    import torch.optim as optim
+    L, B = 256, 4
+    for in_ch, cc in [(7, 5), (3, 1)]:
+        model, sd0 = build_model(M, in_ch, cc, seed=2)
+        model.train()
+        diff = M.CustomDiffusion(T=1000)
+        data = synthetic_chirps(B, L, snr=12.0, seed=31)
+        clean, y = data["clean_norm"], data["y_norm"]
+        mask = torch.ones(B, 1, L)
+        mask[1, :, :37] = 0.0                        # left-padded sample (dataloader.py:248-268)
+        if cc == 5:
+            meta = gaussian((B, 4, 1), seed=6).expand(B, 4, L).contiguous() * 0.3
+            cond = torch.cat([y, meta], dim=1)
+        else:
+            cond = y
+        t = torch.tensor([500, 731, 999, 612])
+        eps = gaussian((B, 1, L), seed=41)
+        drop = torch.tensor([0.0, 1.0, 0.0, 0.0]).view(B, 1, 1)
+        for sc in (False, True):
+            m = deepcopy(model)
+            ema = deepcopy(m)
+            opt = optim.AdamW(m.parameters(), lr=2e-4, weight_decay=1e-4)
+            sched = TR.make_warmup_cosine_scheduler(opt, warmup_steps=10, total_steps=100, min_lr_scale=0.1)
+            rec = {}
+            for step in range(2):
+                clean_c = clean.clamp(-10, 10)
+                y_c = y.clamp(-10, 10)
+                with NoiseInjector([eps]):
+                    x_t, e = diff.q_sample(clean_c, t)
+                x_t = x_t.clamp(-10, 10)
+                if cc == 5:
+                    cond_used = torch.cat([y_c * (1.0 - drop), cond[:, 1:]], dim=1)
+                else:
+                    cond_used = cond * (1.0 - drop)
+                if sc:
+                    x0_sc = TR._predict_x0_norm(m, diff, x_t, cond_used, t)
+                else:
+                    x0_sc = torch.zeros_like(x_t)
+                eps_hat = m(torch.cat([x_t, cond_used, x0_sc], dim=1), t)
+                el = TR._element_loss(eps_hat, e, mask, "huber", 0.5)
+                loss = (el.sum(dim=[1, 2]) / mask.sum(dim=[1, 2]).clamp_min(1.0)).mean()
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                if step == 0:
+                    rec["loss"] = loss.detach().numpy()
+                    rec["eps_hat"] = eps_hat.detach().numpy()
+                    for k, p in m.named_parameters():
+                        g = p.grad.detach()
+                        rec["gnorm/" + k] = np.array(float(g.norm()))
+                        if g.numel() <= 4096:
+                            rec["grad/" + k] = g.numpy().copy()
+                        else:
+                            rec["grad/" + k] = g.reshape(-1)[::97].numpy().copy()
+                gn = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+                rec[f"grad_norm{step}"] = np.array(float(gn))
+                rec[f"lr{step}"] = np.array(opt.param_groups[0]["lr"])
+                opt.step()
+                sched.step()
+                TR.update_ema(ema, m, 0.999)
+                rec[f"loss{step}"] = loss.detach().numpy()
+            for k, p in m.named_parameters():
+                if p.numel() <= 4096:
+                    rec["p2/" + k] = p.detach().numpy().copy()
+                    rec["ema2/" + k] = dict(ema.named_parameters())[k].detach().numpy().copy()
+                else:
+                    rec["p2/" + k] = p.detach().reshape(-1)[::97].numpy().copy()
+                    rec["ema2/" + k] = dict(ema.named_parameters())[k].detach().reshape(-1)[::97].numpy().copy()
+            np.savez_compressed(os.path.join(out, f"train_c{in_ch}_sc{int(sc)}.npz"), **rec)
+    lam = [TR.make_warmup_cosine_scheduler(optim.SGD([torch.zeros(1, requires_grad=True)], lr=1.0), 10, 100, 0.1)
+           .lr_lambdas[0](s) for s in [0, 5, 9, 10, 50, 99, 100, 150]]
+    np.savez_compressed(os.path.join(out, "lr_lambda.npz"), lam=np.array(lam))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=HERE)
+    args = ap.parse_args()
+    torch.set_num_threads(8)
+    M, I, TR = import_reference()
+    gen_schedule(M, I, args.out)
+    gen_forward(M, args.out)
+    gen_chains(M, I, args.out)
+    gen_train(M, TR, args.out)
+    tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
+    print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

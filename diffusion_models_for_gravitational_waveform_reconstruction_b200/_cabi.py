@@ -1,0 +1,90 @@
+"""ctypes binding of include/gwb200.h.  There is no fallback: if the library is missing or a call fails we raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "libgwb200.so")
+_lib: Optional[C.CDLL] = None
+
+GW_F32, GW_BF16 = 0, 1
+
+
+class StepParams(C.Structure):
+    _fields_ = [("mode", C.c_int), ("cfg_both", C.c_int), ("selfcond", C.c_int), ("pred_x0", C.c_int),
+                ("eps_scale", C.c_float), ("dc_weight", C.c_float), ("y_dc", C.c_void_p),
+                ("seed", C.c_ulonglong), ("sample0", C.c_long)]
+
+
+class ConvTcShape(C.Structure):
+    _fields_ = [("n_src", C.c_int), ("pair", C.c_int), ("B", C.c_int), ("L", C.c_int), ("C0", C.c_int),
+                ("L0", C.c_int), ("C1", C.c_int), ("Cout", C.c_int)]
+
+
+_P, _I, _L, _F, _U64 = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_ulonglong
+
+_SIGS = {
+    "gw_version": ([], _I),
+    "gw_last_error": ([], C.c_char_p),
+    "gw_device_info": ([C.POINTER(_I)] * 3, _I),
+    "gw_film_vectors": ([_P, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _P], _I),
+    "gw_cond_pyramid": ([_P, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_P), _P], _I),
+    "gw_conv_in": ([_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P], _I),
+    "gw_conv3_simt": ([_P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P], _I),
+    "gw_gn_apply": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _I, _P], _I),
+    "gw_final_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, C.POINTER(StepParams), _P, _P, _P, _P, _P, _P], _I),
+    "gw_step_advance": ([_P, _I, _P], _I),
+    "gw_q_sample": ([_P, _P, _P, _P, _P, _I, _U64, _L, C.c_uint, _F, _P, _I, _I, _I, _P], _I),
+    "gw_conv_tc_packed_elems": ([C.POINTER(ConvTcShape)], _L),
+    "gw_conv_tc_pack": ([C.POINTER(ConvTcShape), _P, _P, _P], _I),
+    "gw_conv_tc_n_part": ([C.POINTER(ConvTcShape)], _I),
+    "gw_conv_tc": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _I, _P], _I),
+}
+# entry points added by backward.cu / optim.cu register themselves here (see _cabi_train.py)
+_EXTRA_SIGS = {}
+
+
+def exported_symbols():
+    return list(_SIGS) + list(_EXTRA_SIGS)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load libgwb200.so (built in-tree by build.py).  Raises if absent: the CUDA path is the only path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(_LIB_PATH)
+    for name, (args, res) in {**_SIGS, **_EXTRA_SIGS}.items():
+        fn = getattr(lib, name)       # AttributeError here = header/library mismatch
+        fn.argtypes = args
+        fn.restype = res
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().gw_last_error().decode()
+        raise RuntimeError(f"gwb200 {what} failed ({rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream

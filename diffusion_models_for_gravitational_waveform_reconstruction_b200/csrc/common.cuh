@@ -1,0 +1,148 @@
+// Shared device/host helpers for the gwb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#define GW_OK 0
+#define GW_ERR_ARG -1
+#define GW_ERR_CUDA -2
+#define GW_ERR_UNSUPPORTED -3
+
+// ---------------------------------------------------------------- error plumbing
+void gw_set_error(const char* fmt, ...);
+
+#define GW_REQUIRE(cond, ...)                                  \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            gw_set_error(__VA_ARGS__);                         \
+            return GW_ERR_ARG;                                 \
+        }                                                      \
+    } while (0)
+
+#define GW_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            gw_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return GW_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define GW_LAUNCH_CHECK()                                                               \
+    do {                                                                                \
+        cudaError_t _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess) {                                                        \
+            gw_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return GW_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+// dtype codes of the C-ABI
+#define GW_F32 0
+#define GW_BF16 1
+
+static inline int gw_cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- 8-wide vector load/store
+// Activations are channels-last; a thread always owns 8 consecutive channels.
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+    uint4 r;
+    r.x = pack_bf16x2(v[0], v[1]);
+    r.y = pack_bf16x2(v[2], v[3]);
+    r.z = pack_bf16x2(v[4], v[5]);
+    r.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = r;
+}
+// value as it will be read back from storage (stats must describe the stored data)
+__device__ __forceinline__ float round_to(float x, const float*) { return x; }
+__device__ __forceinline__ float round_to(float x, const bf16*) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+
+// ---------------------------------------------------------------- activations
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_f(float x) {
+    if (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+    return 1.0f / (1.0f + expf(-x));
+}
+template <bool FAST>
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f<FAST>(x); }
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Philox4x32-10 counter RNG + Box-Muller; key = seed, counter = (sample, step, chunk, 0).
+struct Philox {
+    __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+        uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __device__ static inline void gen(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&out)[4]) {
+        uint32_t c[4] = {c0, c1, c2, c3};
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+    // 4 standard normals for (sample, step, chunk): positions 4*chunk .. 4*chunk+3
+    __device__ static inline void normal4(uint64_t seed, uint32_t sample, uint32_t step, uint32_t chunk, float (&z)[4]) {
+        uint32_t r[4];
+        gen(seed, chunk, step, sample, 0x6a09e667u, r);
+        const float k = 2.3283064365386963e-10f;  // 2^-32
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            float u1 = ((float)r[2 * i] + 0.5f) * k;   // (0,1)
+            float u2 = ((float)r[2 * i + 1] + 0.5f) * k;
+            u1 = fminf(fmaxf(u1, 1.0e-10f), 1.0f);
+            float rad = sqrtf(-2.0f * logf(u1));
+            float s, c;
+            sincosf(6.283185307179586f * u2, &s, &c);
+            z[2 * i] = rad * c;
+            z[2 * i + 1] = rad * s;
+        }
+    }
+};

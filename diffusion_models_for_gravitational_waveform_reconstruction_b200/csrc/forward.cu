@@ -1,0 +1,740 @@
+// Forward-path kernels other than the tcgen05 conv: FiLM vectors, conditioning pyramid, first conv,
+// exact-mode SIMT conv, fused GroupNorm-apply/SiLU/cond/FiLM/pool, fused head conv + DDIM/DDPM step, q_sample.
+// Reference call sites are cited in include/gwb200.h.
+#include "common.cuh"
+#include "../../include/gwb200.h"
+
+// ------------------------------------------------------------------------------------------------
+// error text
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "ok";
+void gw_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* gw_last_error(void) { return g_err; }
+extern "C" int gw_version(void) { return 100; }
+extern "C" int gw_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    GW_CUDA(cudaGetDevice(&dev));
+    GW_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+    GW_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    GW_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FiLM vectors: one CTA per timestep value
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t, int time_dim, float inv_max_time_den,
+                                                   float freq_coef, const float* __restrict__ w1,
+                                                   const float* __restrict__ b1, const float* __restrict__ w2,
+                                                   const float* __restrict__ b2, int base, int F, float* __restrict__ out) {
+    extern __shared__ float sm[];
+    float* emb = sm;              // [time_dim]
+    float* act = sm + time_dim;   // [base]
+    const int n = blockIdx.x;
+    const float ts = (float)t[n] / inv_max_time_den;
+    const int half = time_dim / 2;
+    for (int i = threadIdx.x; i < time_dim; i += blockDim.x) {
+        float v = 0.0f;
+        if (i < 2 * half) {
+            const int j = i < half ? i : i - half;
+            const float freq = expf((float)j * freq_coef);
+            const float a = ts * freq;
+            v = i < half ? sinf(a) : cosf(a);
+        }
+        emb[i] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < base; j += blockDim.x) {
+        float acc = 0.0f;
+        const float* wr = w1 + (size_t)j * time_dim;
+        for (int i = 0; i < time_dim; ++i) acc = fmaf(wr[i], emb[i], acc);
+        acc += b1[j];
+        const float ctx = silu_f<false>(acc);   // time_mlp's SiLU
+        act[j] = silu_f<false>(ctx);            // tproj's leading SiLU
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float acc = 0.0f;
+        const float* wr = w2 + (size_t)f * base;
+        for (int j = 0; j < base; ++j) acc = fmaf(wr[j], act[j], acc);
+        out[(size_t)n * F + f] = acc + b2[f];
+    }
+}
+
+extern "C" int gw_film_vectors(const int64_t* t, int n, int time_dim, float max_time, const float* w1, const float* b1,
+                               const float* w2, const float* b2, int base, int F, float* out, void* stream) {
+    GW_REQUIRE(n > 0 && time_dim > 0 && base > 0 && F > 0, "gw_film_vectors: bad sizes");
+    const int half = time_dim / 2;
+    const float den = max_time > 1.0f ? max_time : 1.0f;                       // models.py:21
+    const float coef = (float)(-(log(10000.0) / (double)(half - 1 > 1 ? half - 1 : 1)));   // models.py:25
+    size_t smem = (size_t)(time_dim + base) * sizeof(float);
+    film_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(t, time_dim, den, coef, w1, b1, w2, b2, base, F, out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conditioning pyramid
+// ------------------------------------------------------------------------------------------------
+struct PyrArgs {
+    float* out[GW_MAX_LEVELS];
+    int len[GW_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) cond_pyramid_kernel(const float* __restrict__ x, int B, int Cx, int L, int Cc,
+                                                           PyrArgs a) {
+    const int lvl = blockIdx.y;
+    const int Lo = a.len[lvl];
+    const long total = (long)B * Lo * Cc;
+    const float scale = (float)L / (float)Lo;     // area_pixel_compute_scale (align_corners=False, size given)
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cc);
+        const long r = i / Cc;
+        const int l = (int)(r % Lo);
+        const int b = (int)(r / Lo);
+        float src = scale * ((float)l + 0.5f) - 0.5f;
+        if (src < 0.0f) src = 0.0f;
+        int i0 = (int)src;
+        if (i0 > L - 1) i0 = L - 1;
+        const int i1 = i0 + (i0 < L - 1 ? 1 : 0);
+        const float l1 = src - (float)i0;
+        const float l0 = 1.0f - l1;
+        const float* xp = x + ((size_t)b * Cx + 1 + c) * L;
+        a.out[lvl][i] = l0 * xp[i0] + l1 * xp[i1];
+    }
+}
+
+extern "C" int gw_cond_pyramid(const float* x, int B, int Cx, int L, int Cc, int n_levels, const int* level_len,
+                               float* const* level_out, void* stream) {
+    GW_REQUIRE(n_levels > 0 && n_levels <= GW_MAX_LEVELS, "gw_cond_pyramid: n_levels %d", n_levels);
+    GW_REQUIRE(Cc > 0 && 1 + Cc <= Cx, "gw_cond_pyramid: Cc %d Cx %d", Cc, Cx);
+    PyrArgs a;
+    for (int i = 0; i < n_levels; ++i) {
+        a.out[i] = level_out[i];
+        a.len[i] = level_len[i];
+    }
+    long total = (long)B * L * Cc;
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 16) gx = 148 * 16;
+    cond_pyramid_kernel<<<dim3(gx, n_levels), 256, 0, (cudaStream_t)stream>>>(x, B, Cx, L, Cc, a);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic per-tile GroupNorm partials: red[256][2] in smem -> part[(tile, g)]
+// each thread contributed (s1, s2) for group `g_of_thread`; groups in this tile = n_groups starting at g0.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_stats_reduce(float s1, float s2, int g_local, int n_groups, float* red,
+                                                  float* part_tile /* [8][2] */, int g0) {
+    // red layout: [thread][3] = (s1, s2, group)
+    red[threadIdx.x * 3 + 0] = s1;
+    red[threadIdx.x * 3 + 1] = s2;
+    red[threadIdx.x * 3 + 2] = __int_as_float(g_local);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < n_groups; g += (blockDim.x >> 5)) {
+        float a1 = 0.0f, a2 = 0.0f;
+        for (int i = lane; i < (int)blockDim.x; i += 32) {
+            if (__float_as_int(red[i * 3 + 2]) == g) {
+                a1 += red[i * 3 + 0];
+                a2 += red[i * 3 + 1];
+            }
+        }
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) {
+            part_tile[(g0 + g) * 2 + 0] = a1;
+            part_tile[(g0 + g) * 2 + 1] = a2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// first conv (K1): NCL fp32 input -> channels-last raw + stats.  128 positions x C channels per CTA.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ xa, const float* __restrict__ xb,
+                                                      const int* __restrict__ step_ptr, int Cx, int L,
+                                                      const float* __restrict__ w, const float* __restrict__ bias, int C,
+                                                      T* __restrict__ raw, float* __restrict__ part, int n_part) {
+    constexpr int TP = 128;
+    extern __shared__ float sm[];
+    float* xs = sm;                              // [Cx][TP + 2]
+    float* ws = xs + Cx * (TP + 2);              // [Cx*3][C]
+    float* bs = ws + Cx * 3 * C;                 // [C]
+    float* wst = bs + C;                         // [n_iter*8 warps][2]
+    const int b = blockIdx.y, tile = blockIdx.x, l0 = tile * TP;
+    const float* x = (step_ptr != nullptr && (*step_ptr & 1)) ? xb : xa;
+    for (int i = threadIdx.x; i < Cx * (TP + 2); i += blockDim.x) {
+        const int c = i / (TP + 2), p = i % (TP + 2);
+        const int l = l0 + p - 1;
+        xs[i] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < Cx * 3 * C; i += blockDim.x) {
+        const int co = i % C, ck = i / C;        // ck = ci*3 + k
+        ws[i] = w[(size_t)co * Cx * 3 + ck];
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
+    __syncthreads();
+    const int n_oct = C / 8;
+    const int n_iter = n_oct * TP / 256;         // = C/16
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // one (octet, position) item per thread per iteration; a warp shares the octet -> weight reads broadcast
+    for (int it = 0; it < n_iter; ++it) {
+        const int item = it * 256 + threadIdx.x;
+        const int pos = item % TP, oct = item / TP;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bs[oct * 8 + j];
+        for (int ck = 0; ck < Cx * 3; ++ck) {
+            const int ci = ck / 3, k = ck - ci * 3;
+            const float xv = xs[ci * (TP + 2) + pos + k];
+            const float4 wa = *reinterpret_cast<const float4*>(ws + ck * C + oct * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(ws + ck * C + oct * 8 + 4);
+            acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]);
+            acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
+            acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]);
+            acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+        }
+        const int l = l0 + pos;
+        float s1 = 0.0f, s2 = 0.0f;
+        if (l < L) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[j] = round_to(acc[j], raw);
+                s1 += acc[j];
+                s2 += acc[j] * acc[j];
+            }
+            st8(raw + ((size_t)b * L + l) * C + oct * 8, acc);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            wst[(it * 8 + warp) * 2 + 0] = s1;
+            wst[(it * 8 + warp) * 2 + 1] = s2;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        // slot (it, warp) covers octet (it*256 + warp*32)/TP; group = octet*8 / (C/8)
+        const int g = threadIdx.x, cg = C / 8;
+        float a1 = 0.0f, a2 = 0.0f;
+        for (int s = 0; s < n_iter * 8; ++s) {
+            const int oct = ((s >> 3) * 256 + (s & 7) * 32) / TP;
+            if ((oct * 8) / cg == g) {
+                a1 += wst[s * 2 + 0];
+                a2 += wst[s * 2 + 1];
+            }
+        }
+        float* pt = part + ((size_t)b * n_part + tile) * 16;
+        pt[g * 2 + 0] = a1;
+        pt[g * 2 + 1] = a2;
+    }
+}
+
+extern "C" int gw_conv_in(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
+                          const float* bias, int C, void* raw, int dtype, float* part, void* stream) {
+    GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_conv_in: C=%d must be a multiple of 64 and <= 256", C);
+    GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_conv_in: Cx=%d", Cx);
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv_in: dtype %d", dtype);
+    constexpr int TP = 128;
+    const int n_part = gw_cdiv(L, TP);
+    size_t smem = (size_t)(Cx * (TP + 2) + Cx * 3 * C + C + (C / 16) * 8 * 2) * sizeof(float);
+    dim3 grid(n_part, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32) {
+        GW_CUDA(cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_in_kernel<float><<<grid, 256, smem, st>>>(x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, C, (float*)raw, part, n_part);
+    } else {
+        GW_CUDA(cudaFuncSetAttribute(conv_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_in_kernel<bf16><<<grid, 256, smem, st>>>(x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, C, (bf16*)raw, part, n_part);
+    }
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact-mode SIMT conv (K2-K7 in fp32): 64 positions x 64 couts per CTA, K chunks of 16 channels x 3 taps.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv3_simt_kernel(const T* __restrict__ src0, int C0, int L0, int up0,
+                                                         const T* __restrict__ src1, int C1, int L,
+                                                         const float* __restrict__ w3, const float* __restrict__ bias,
+                                                         int Cout, T* __restrict__ raw, float* __restrict__ part,
+                                                         int n_part) {
+    constexpr int TP = 64, TN = 64, KC = 16;
+    __shared__ __align__(16) float xs[(TP + 2) * KC];
+    __shared__ __align__(16) float ws[3 * KC * TN];
+    __shared__ float red[256 * 3];
+    const int b = blockIdx.z, n0 = blockIdx.y * TN, tile = blockIdx.x, l0 = tile * TP;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int Cin = C0 + C1;
+    float acc[4][4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[p][n] = 0.0f;
+
+    for (int c0 = 0; c0 < Cin; c0 += KC) {
+        // input tile: rows l0-1 .. l0+TP, channels c0..c0+15 (two octets per row)
+        for (int i = threadIdx.x; i < (TP + 2) * 2; i += blockDim.x) {
+            const int row = i >> 1, oct = i & 1;
+            const int l = l0 + row - 1;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+            if (l >= 0 && l < L) {
+                if (c0 < C0) {
+                    const int ls = up0 ? (l >> 1) : l;
+                    if (ls < L0) ld8(src0 + ((size_t)b * L0 + ls) * C0 + c0 + oct * 8, v);
+                } else {
+                    ld8(src1 + ((size_t)b * L + l) * C1 + (c0 - C0) + oct * 8, v);
+                }
+            }
+            float* d = xs + row * KC + oct * 8;
+            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        // weights: ws[k][ci][n] = w[n0+n][c0+ci][k]  (reference layout [Cout, Cin, 3]: 48 contiguous floats per n)
+        for (int i = threadIdx.x; i < 3 * KC * TN; i += blockDim.x) {
+            const int n = i / (3 * KC), j = i % (3 * KC);
+            const int ci = j / 3, k = j - ci * 3;
+            ws[(k * KC + ci) * TN + n] = w3[((size_t)(n0 + n) * Cin + c0 + ci) * 3 + k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll 4
+            for (int ci = 0; ci < KC; ++ci) {
+                const float4 wv = *reinterpret_cast<const float4*>(ws + (k * KC + ci) * TN + tx * 4);
+                float a[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) a[p] = xs[(ty * 4 + p + k) * KC + ci];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    acc[p][0] = fmaf(a[p], wv.x, acc[p][0]);
+                    acc[p][1] = fmaf(a[p], wv.y, acc[p][1]);
+                    acc[p][2] = fmaf(a[p], wv.z, acc[p][2]);
+                    acc[p][3] = fmaf(a[p], wv.w, acc[p][3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
+    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int l = l0 + ty * 4 + p;
+        if (l < L) {
+            float o[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                o[n] = round_to(acc[p][n] + bb[n], raw);
+                s1 += o[n];
+                s2 += o[n] * o[n];
+            }
+            T* dst = raw + ((size_t)b * L + l) * Cout + n0 + tx * 4;
+            if (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+                uint2 pk;
+                pk.x = pack_bf16x2(o[0], o[1]);
+                pk.y = pack_bf16x2(o[2], o[3]);
+                *reinterpret_cast<uint2*>(dst) = pk;
+            }
+        }
+    }
+    const int cg = Cout / 8;
+    const int n_groups = TN / cg > 0 ? TN / cg : 1;   // groups covered by this cout tile (cg <= 64)
+    tile_stats_reduce(s1, s2, (tx * 4) / cg, n_groups, red, part + ((size_t)b * n_part + tile) * 16, n0 / cg);
+}
+
+extern "C" int gw_conv3_simt(const void* src0, int C0, int L0, int up0, const void* src1, int C1, int B, int L,
+                             const float* w3, const float* bias, int Cout, void* raw, int dtype, float* part,
+                             void* stream) {
+    GW_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "gw_conv3_simt: channels C0=%d C1=%d", C0, C1);
+    GW_REQUIRE(Cout % 64 == 0 && Cout <= 512, "gw_conv3_simt: Cout=%d", Cout);
+    GW_REQUIRE((src1 != nullptr) == (C1 > 0), "gw_conv3_simt: src1/C1 mismatch");
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv3_simt: dtype %d", dtype);
+    const int n_part = gw_cdiv(L, 64);
+    dim3 grid(n_part, Cout / 64, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32)
+        conv3_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)src0, C0, L0, up0, (const float*)src1, C1, L, w3, bias,
+                                                        Cout, (float*)raw, part, n_part);
+    else
+        conv3_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src0, C0, L0, up0, (const bf16*)src1, C1, L, w3, bias,
+                                                       Cout, (bf16*)raw, part, n_part);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused GroupNorm-apply + SiLU + cond 1x1 conv + FiLM (+ pooled output)
+// ------------------------------------------------------------------------------------------------
+#define GN_MAX_CC 8
+// CC = compile-time number of conditioning channels (0, 1, 5) or -1 for the generic (<= GN_MAX_CC) path.
+// A thread owns one channel octet for the whole CTA so all per-channel coefficients live in registers.
+template <typename T, bool FAST, int CC>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ part,
+                                                       int n_part, int L, int C, const float* __restrict__ gn_w,
+                                                       const float* __restrict__ gn_b, const float* __restrict__ cond,
+                                                       int Cc_rt, const float* __restrict__ wc, const float* __restrict__ bc,
+                                                       const float* __restrict__ film, int film_off, long film_b_stride,
+                                                       long film_step_stride, const int* __restrict__ step_ptr,
+                                                       T* __restrict__ out, T* __restrict__ pooled,
+                                                       float* __restrict__ stats_out, int rows_per_cta) {
+    constexpr int NC = CC >= 0 ? CC : GN_MAX_CC;
+    const int Cc = CC >= 0 ? CC : Cc_rt;
+    __shared__ float s_mean[8], s_rstd[8];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = C / 8;
+    if (warp < 8) {
+        double a1 = 0.0, a2 = 0.0;
+        const float* pp = part + (size_t)b * n_part * 16 + warp * 2;
+        for (int i = lane; i < n_part; i += 32) {
+            a1 += (double)pp[(size_t)i * 16];
+            a2 += (double)pp[(size_t)i * 16 + 1];
+        }
+        a1 = warp_sum_d(a1);
+        a2 = warp_sum_d(a2);
+        if (lane == 0) {
+            const double n = (double)cg * (double)L;
+            const double mean = a1 / n;
+            double var = a2 / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+            s_mean[warp] = (float)mean;
+            s_rstd[warp] = rstd;
+            if (stats_out != nullptr && blockIdx.x == 0) {
+                stats_out[((size_t)b * 8 + warp) * 2 + 0] = (float)mean;
+                stats_out[((size_t)b * 8 + warp) * 2 + 1] = rstd;
+            }
+        }
+    }
+    __syncthreads();
+    const int n_oct = C / 8;                    // divides 256 (C in {64,128,256,512,...})
+    const int oct = threadIdx.x % n_oct;
+    const int pr0 = threadIdx.x / n_oct, pr_stride = blockDim.x / n_oct;
+    const int step = step_ptr != nullptr ? *step_ptr : 0;
+    const float* fr = film + (size_t)step * film_step_stride + (size_t)b * film_b_stride + film_off;
+    // out = silu(A*x + Bn) * G + E + sum_j W[j] * cond[j]   with G = 1+gamma, E = bc*G + beta, W = wc*G
+    float cA[8], cB[8], cG[8], cE[8], cW[8][NC > 0 ? NC : 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = oct * 8 + i;
+        const int g = c / cg;
+        const float a = s_rstd[g] * gn_w[c];
+        cA[i] = a;
+        cB[i] = gn_b[c] - s_mean[g] * a;
+        cG[i] = 1.0f + fr[c];
+        cE[i] = fr[C + c];
+        if (NC > 0) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) cW[i][j] = (j < Cc) ? wc[c * Cc + j] : 0.0f;
+        }
+    }
+    const float* cbp = bc;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const bool do_pool = pooled != nullptr;
+    const int Lp = L / 2;
+    const int n_pairs = rows_per_cta / 2;
+    for (int pr = pr0; pr < n_pairs; pr += pr_stride) {
+        const int la = r0 + 2 * pr;
+        if (la >= L) break;
+        float o[2][8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = la + h;
+            if (l < L) {
+                float x[8];
+                ld8(raw + ((size_t)b * L + l) * C + oct * 8, x);
+                float cv[NC > 0 ? NC : 1];
+                if (NC > 0) {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) cv[j] = (j < Cc) ? cond[((size_t)b * L + l) * Cc + j] : 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float v = silu_f<FAST>(fmaf(x[i], cA[i], cB[i]));
+                    if (NC > 0) {
+                        float cb = cbp[oct * 8 + i];      // L1-resident; keeps 8 registers free
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) cb = fmaf(cW[i][j], cv[j], cb);
+                        v += cb;                          // h = silu(gn) + cond_bias   (models.py:205)
+                    }
+                    o[h][i] = fmaf(v, cG[i], cE[i]);      // h*(1+gamma)+beta            (models.py:173)
+                }
+                st8(out + ((size_t)b * L + l) * C + oct * 8, o[h]);
+            }
+        }
+        if (do_pool && la + 1 < L) {
+            float p[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) p[i] = 0.5f * (o[0][i] + o[1][i]);
+            st8(pooled + ((size_t)b * Lp + (la >> 1)) * C + oct * 8, p);
+        }
+    }
+}
+
+template <typename T, bool FAST>
+static int gn_apply_launch(dim3 grid, cudaStream_t st, const void* raw, const float* part, int n_part, int L, int C,
+                           const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc,
+                           const float* bc, const float* film, int film_off, long fbs, long fss, const int* step_ptr,
+                           void* out, void* pooled, float* stats_out, int rows) {
+#define GN_GO(CCV)                                                                                                     \
+    gn_apply_kernel<T, FAST, CCV><<<grid, 256, 0, st>>>((const T*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
+                                                        film, film_off, fbs, fss, step_ptr, (T*)out, (T*)pooled,        \
+                                                        stats_out, rows)
+    if (Cc == 0) GN_GO(0);
+    else if (Cc == 1) GN_GO(1);
+    else if (Cc == 5) GN_GO(5);
+    else GN_GO(-1);
+#undef GN_GO
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+extern "C" int gw_gn_apply(const void* raw, const float* part, int n_part, int B, int L, int C, const float* gn_w,
+                           const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
+                           const float* film, int film_off, long film_b_stride, long film_step_stride,
+                           const int* step_ptr, void* out, void* pooled, float* stats_out, int dtype, void* stream) {
+    GW_REQUIRE(C % 64 == 0 && C <= 2048 && (256 % (C / 8) == 0 || (C / 8) % 256 == 0) && C / 8 <= 256,
+               "gw_gn_apply: C=%d", C);
+    GW_REQUIRE(Cc >= 0 && Cc <= GN_MAX_CC, "gw_gn_apply: Cc=%d (max %d)", Cc, GN_MAX_CC);
+    GW_REQUIRE((cond != nullptr) == (Cc > 0), "gw_gn_apply: cond/Cc mismatch");
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_gn_apply: dtype %d", dtype);
+    // >= 8 row pairs per thread so the per-thread coefficient setup is amortised
+    int rows = 2 * 8 * 256 / (C / 8);
+    if (rows > L) rows = (L + 1) & ~1;
+    if (rows < 2) rows = 2;
+    dim3 grid(gw_cdiv(L, rows), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32)
+        return gn_apply_launch<float, false>(grid, st, raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film, film_off,
+                                             film_b_stride, film_step_stride, step_ptr, out, pooled, stats_out, rows);
+    return gn_apply_launch<bf16, true>(grid, st, raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film, film_off,
+                                       film_b_stride, film_step_stride, step_ptr, out, pooled, stats_out, rows);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head conv (C+1 -> 1, k=3) fused with CFG combine + DDIM/DDPM update
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+    int mode, cfg_both, selfcond, pred_x0;
+    float eps_scale, dc_weight;
+    const float* y_dc;
+    unsigned long long seed;
+    long sample0;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h, const float* __restrict__ net_a,
+                                                         const float* __restrict__ net_b, int B, int Cx, int L, int C,
+                                                         const float* __restrict__ wf, const float* __restrict__ bf,
+                                                         StepArgs p, const float* __restrict__ coef,
+                                                         const int* __restrict__ step_ptr, const float* __restrict__ noise,
+                                                         float* __restrict__ eps_out, float* __restrict__ x0_out) {
+    constexpr int TP = 128;
+    extern __shared__ float sm[];
+    float* sw = sm;                       // [3][C] tap-major head weights for the h channels
+    float* pd = sw + 3 * C;               // [2 halves][3][TP+2] per-row partial dots
+    const int b = blockIdx.y, l0 = blockIdx.x * TP;
+    const int step = step_ptr != nullptr ? *step_ptr : 0;
+    const float* net_in = (step & 1) ? net_b : net_a;
+    float* net_out = const_cast<float*>((step & 1) ? net_a : net_b);
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+        const int k = i / C, c = i % C;
+        sw[i] = wf[c * 3 + k];
+    }
+    __syncthreads();
+    const int n_half = (p.mode == 1 && p.cfg_both) ? 2 : 1;
+    const int n_oct = C / 8;                 // threads per row
+    const int rows_per_pass = blockDim.x / n_oct;
+    for (int hf = 0; hf < n_half; ++hf) {
+        const int bb = b + hf * B;
+        for (int rb = 0; rb < TP + 2; rb += rows_per_pass) {      // uniform trip count: shuffles need the full warp
+            const int r = rb + threadIdx.x / n_oct;
+            const int oct = threadIdx.x % n_oct;
+            const int l = l0 + r - 1;
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+            if (r < TP + 2 && l >= 0 && l < L) {
+                float v[8];
+                ld8(h + ((size_t)bb * L + l) * C + oct * 8, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = oct * 8 + i;
+                    d0 = fmaf(v[i], sw[c], d0);
+                    d1 = fmaf(v[i], sw[C + c], d1);
+                    d2 = fmaf(v[i], sw[2 * C + c], d2);
+                }
+            }
+            // reduce over the n_oct lanes of this row (n_oct is a power of two <= 32)
+            for (int o = n_oct >> 1; o > 0; o >>= 1) {
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if (oct == 0 && r < TP + 2) {
+                float* q = pd + hf * 3 * (TP + 2);
+                q[r] = d0;
+                q[(TP + 2) + r] = d1;
+                q[2 * (TP + 2) + r] = d2;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= TP) return;
+    const int l = l0 + threadIdx.x;
+    if (l >= L) return;
+    const float wx0 = wf[C * 3 + 0], wx1 = wf[C * 3 + 1], wx2 = wf[C * 3 + 2], bias = bf[0];
+    float outv[2] = {0.0f, 0.0f};
+    float xt_c = 0.0f;
+    for (int hf = 0; hf < n_half; ++hf) {
+        const int bb = b + hf * B;
+        const float* xr = net_in + (size_t)bb * Cx * L;     // channel 0 = x_t
+        const float xm = l > 0 ? xr[l - 1] : 0.0f, xc = xr[l], xp = l + 1 < L ? xr[l + 1] : 0.0f;
+        const float* q = pd + hf * 3 * (TP + 2);
+        const int r = threadIdx.x + 1;
+        float acc = q[r - 1] + q[(TP + 2) + r] + q[2 * (TP + 2) + r + 1];
+        acc += fmaf(xm, wx0, fmaf(xc, wx1, xp * wx2));
+        outv[hf] = acc + bias;
+        if (hf == 0) xt_c = xc;
+    }
+    if (p.mode == 0) {
+        eps_out[(size_t)b * L + l] = outv[0];
+        return;
+    }
+    const float* cf = coef + (size_t)step * 16;
+    const float c_s1mab = cf[0], c_sab = cf[1], c_sabp = cf[2], c_dir = cf[3], c_sig = cf[4], c_w = cf[5];
+    const int use = (int)cf[6], last = (int)cf[7], draw = (int)cf[8];
+    const float c_s1mab_cl = cf[9];
+    float o;
+    if (use == 0) o = outv[0];
+    else if (use == 1) o = p.cfg_both ? outv[1] : outv[0];
+    else o = __fadd_rn(outv[1], __fmul_rn(c_w, __fsub_rn(outv[0], outv[1])));       // inference.py:460
+    float eps, x0;
+    if (!p.pred_x0) {
+        eps = __fmul_rn(p.eps_scale, o);
+        x0 = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_s1mab, eps)), c_sab);          // inference.py:465-466 (no FMA contraction)
+    } else {
+        x0 = o;
+        eps = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_sab, x0)), c_s1mab_cl);       // inference.py:468-469
+    }
+    if (p.dc_weight > 0.0f)
+        x0 = __fadd_rn(__fmul_rn(1.0f - p.dc_weight, x0), __fmul_rn(p.dc_weight, p.y_dc[(size_t)b * L + l]));   // inference.py:472
+    float xn;
+    if (last) {
+        xn = x0;
+    } else {
+        float nz = 0.0f;
+        if (c_sig > 0.0f) {
+            float z;
+            if (noise != nullptr) {
+                z = noise[((size_t)draw * B + b) * L + l];
+            } else {
+                float z4[4];
+                Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)(l >> 2), z4);
+                z = z4[l & 3];
+            }
+            nz = __fmul_rn(c_sig, z);
+        }
+        xn = __fadd_rn(__fadd_rn(__fmul_rn(c_sabp, x0), __fmul_rn(c_dir, eps)), nz);   // inference.py:481-484
+    }
+    for (int hf = 0; hf < n_half; ++hf) {
+        float* orow = net_out + (size_t)(b + hf * B) * Cx * L;
+        orow[l] = xn;
+        if (p.selfcond) orow[(size_t)(Cx - 1) * L + l] = x0;
+    }
+    if (eps_out != nullptr) eps_out[(size_t)b * L + l] = eps;
+    if (x0_out != nullptr) x0_out[(size_t)b * L + l] = x0;
+}
+
+extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const float* net_b, int B, int Cx, int L,
+                             int C, const float* wf, const float* bf, const gw_step_params* p, const float* coef,
+                             const int* step_ptr, const float* noise, float* eps_out, float* x0_out, void* stream) {
+    GW_REQUIRE(p != nullptr, "gw_final_step: params");
+    GW_REQUIRE(C % 64 == 0 && C <= 256 && ((C / 8) & (C / 8 - 1)) == 0, "gw_final_step: C=%d", C);
+    GW_REQUIRE(p->mode == 0 || (coef != nullptr && net_b != nullptr), "gw_final_step: step mode needs coef and net_b");
+    GW_REQUIRE(p->mode == 1 || eps_out != nullptr, "gw_final_step: forward mode needs eps_out");
+    GW_REQUIRE(!(p->dc_weight > 0.0f) || p->y_dc != nullptr, "gw_final_step: dc_weight needs y_dc");
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_final_step: dtype %d", dtype);
+    StepArgs a;
+    a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
+    a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    constexpr int TP = 128;
+    size_t smem = (size_t)(3 * C + 2 * 3 * (TP + 2)) * sizeof(float);
+    dim3 grid(gw_cdiv(L, TP), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32)
+        final_step_kernel<float><<<grid, 256, smem, st>>>((const float*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
+                                                          coef, step_ptr, noise, eps_out, x0_out);
+    else
+        final_step_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
+                                                         coef, step_ptr, noise, eps_out, x0_out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+__global__ void step_advance_kernel(int* p, int set_value) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *p = set_value >= 0 ? set_value : *p + 1;
+}
+extern "C" int gw_step_advance(int* step_ptr, int set_value, void* stream) {
+    step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_ptr, set_value);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// q_sample
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ x0, const int64_t* __restrict__ t,
+                                                       const float* __restrict__ sab, const float* __restrict__ s1mab,
+                                                       float* __restrict__ eps, int philox, unsigned long long seed,
+                                                       long sample0, unsigned step, float clampv, float* __restrict__ net,
+                                                       int Cx, int L) {
+    const int b = blockIdx.y;
+    const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (l4 >= L) return;
+    const long tt = t[b];
+    const float a = sab[tt], m = s1mab[tt];
+    float z[4];
+    if (philox) {
+        Philox::normal4(seed, (uint32_t)(sample0 + b), step, (uint32_t)(l4 >> 2), z);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int l = l4 + i;
+        if (l >= L) break;
+        float e;
+        if (philox) {
+            e = z[i];
+            eps[(size_t)b * L + l] = e;
+        } else {
+            e = eps[(size_t)b * L + l];
+        }
+        float v = a * x0[(size_t)b * L + l] + m * e;
+        if (clampv > 0.0f) v = fminf(fmaxf(v, -clampv), clampv);
+        net[(size_t)b * Cx * L + l] = v;
+    }
+}
+
+extern "C" int gw_q_sample(const float* x0, const int64_t* t, const float* sqrt_ab, const float* sqrt_1mab, float* eps,
+                           int philox, unsigned long long seed, long sample0, unsigned step, float clampv, float* net,
+                           int B, int Cx, int L, void* stream) {
+    GW_REQUIRE(B > 0 && L > 0 && Cx > 0, "gw_q_sample: sizes");
+    dim3 grid(gw_cdiv(gw_cdiv(L, 4), 256), B);
+    q_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, t, sqrt_ab, sqrt_1mab, eps, philox, seed, sample0, step, clampv,
+                                                            net, Cx, L);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}

@@ -1,0 +1,480 @@
+"""Host-side orchestration of the sm_100a kernels for UNet1D.forward and the DDIM/DDPM chain.
+
+Everything numerical happens in libgwb200.so (csrc/*.cu) through the C-ABI; torch provides device memory,
+streams and CUDA-graph capture only.  Layer structure follows models.py:195-231 of the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import GW_BF16, GW_F32, ConvTcShape, StepParams, check, ptr
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class ModelSpec:
+    in_ch: int = 1
+    base_ch: int = 64
+    time_dim: int = 128
+    depth: int = 3
+    kernel: int = 3
+    max_time: float = 999.0
+    cond_in_ch: int = 0
+    use_selfcond: bool = False
+
+    @property
+    def chs(self) -> List[int]:
+        return [self.base_ch * (2 ** i) for i in range(self.depth)]
+
+    @property
+    def layer_channels(self) -> List[int]:
+        """enc0..encD-1, mid, dec0..decD-1"""
+        c = self.chs
+        return c + [c[-1]] + list(reversed(c))
+
+    @property
+    def film_dim(self) -> int:
+        return 2 * sum(self.layer_channels)
+
+    def film_offsets(self) -> List[int]:
+        offs, o = [], 0
+        for c in self.layer_channels:
+            offs.append(o)
+            o += 2 * c
+        return offs
+
+    def level_lengths(self, L: int) -> List[int]:
+        out = [L]
+        for _ in range(self.depth):
+            out.append(out[-1] // 2)
+        return out
+
+    def layer_names(self) -> List[str]:
+        d = self.depth
+        return [f"encoders.{i}" for i in range(d)] + ["mid"] + [f"decoders.{i}" for i in range(d)]
+
+    def cond_names(self) -> List[str]:
+        d = self.depth
+        return [f"cond_enc.{i}" for i in range(d)] + ["cond_mid"] + [f"cond_dec.{i}" for i in range(d)]
+
+    def tproj_names(self) -> List[str]:
+        d = self.depth
+        return [f"tproj_enc.{i}.1" for i in range(d)] + ["tproj_mid.1"] + [f"tproj_dec.{i}.1" for i in range(d)]
+
+    def conv_flops(self, L: int) -> float:
+        """Algorithmic FLOPs of one forward of one sample (2*Cin*Cout*K*L over every Conv1d)."""
+        Ls = self.level_lengths(L)
+        fl, cin = 0.0, self.in_ch
+        for i, c in enumerate(self.chs):
+            fl += 2.0 * cin * c * self.kernel * Ls[i] + 2.0 * self.cond_in_ch * c * Ls[i]
+            cin = c
+        fl += 2.0 * cin * cin * self.kernel * Ls[-1] + 2.0 * self.cond_in_ch * cin * Ls[-1]
+        prev = cin
+        for i, c in enumerate(reversed(self.chs)):
+            Li = Ls[self.depth - 1 - i]
+            fl += 2.0 * (prev + c) * c * self.kernel * Li + 2.0 * self.cond_in_ch * c * Li
+            prev = c
+        return fl + 2.0 * (prev + 1) * self.kernel * L
+
+
+class _Workspace:
+    """Activation buffers for one (batch, length).  Channels-last [B, L_lvl, C] in the engine's storage dtype."""
+
+    def __init__(self, spec: ModelSpec, B: int, L: int, tdtype: torch.dtype, device, keep_raw: bool):
+        self.B, self.L = B, L
+        d = spec.depth
+        Ls = spec.level_lengths(L)
+        self.Ls = Ls
+        chs = spec.chs
+        e = lambda *s: torch.empty(*s, device=device, dtype=tdtype)
+        lay_len = [Ls[i] for i in range(d)] + [Ls[d]] + [Ls[d - 1 - i] for i in range(d)]
+        lay_ch = spec.layer_channels
+        self.lay_len = lay_len
+        if keep_raw:
+            self.raw = [e(B, lay_len[i], lay_ch[i]) for i in range(2 * d + 1)]
+        else:
+            big = e(B * max(lay_len[i] * lay_ch[i] for i in range(2 * d + 1)))
+            self.raw = [big[: B * lay_len[i] * lay_ch[i]].view(B, lay_len[i], lay_ch[i]) for i in range(2 * d + 1)]
+        self.out = [e(B, lay_len[i], lay_ch[i]) for i in range(2 * d + 1)]
+        self.pooled = [e(B, Ls[i + 1], chs[i]) for i in range(d)]
+        n_part_max = (L + 63) // 64 + 2
+        self.part = torch.empty(B, n_part_max, 8, 2, device=device, dtype=torch.float32)
+        self.stats = [torch.empty(B, 8, 2, device=device, dtype=torch.float32) for _ in range(2 * d + 1)] if keep_raw else None
+        self.cond = [torch.empty(B, Ls[j], max(spec.cond_in_ch, 1), device=device, dtype=torch.float32)
+                     for j in range(d + 1)] if spec.cond_in_ch > 0 else None
+
+
+class UNetEngine:
+    """Runs the denoiser forward on the GPU.  `params` maps reference state_dict keys to CUDA fp32 tensors
+    (the engine keeps references, not copies, so in-place optimiser updates are seen after `refresh()`)."""
+
+    def __init__(self, params: Dict[str, Tensor], spec: ModelSpec, dtype: str = "bf16", conv_impl: str = "auto",
+                 tc_variant: int = 0):
+        self.lib = _cabi.load()
+        self.spec = spec
+        assert dtype in ("bf16", "fp32")
+        self.dtype = dtype
+        self.gw_dtype = GW_BF16 if dtype == "bf16" else GW_F32
+        self.tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        if conv_impl == "auto":
+            conv_impl = "tc" if dtype == "bf16" else "simt"
+        if conv_impl == "tc" and dtype != "bf16":
+            raise ValueError("the tcgen05 conv path stores bf16 activations; use dtype='bf16'")
+        self.conv_impl = conv_impl
+        self.tc_variant = tc_variant
+        if spec.base_ch % 64 != 0:
+            raise NotImplementedError("gwb200 kernels need base_ch % 64 == 0 (reference default is 64)")
+        if spec.kernel != 3:
+            raise NotImplementedError("gwb200 kernels implement the reference default kernel=3")
+        self.p = params
+        dev = params["final.weight"].device
+        if dev.type != "cuda":
+            raise RuntimeError("UNetEngine needs CUDA tensors: there is no CPU fallback for this path")
+        self.device = dev
+        self._ws: Dict[tuple, _Workspace] = {}
+        self._packed: Dict[tuple, Tensor] = {}
+        self.launches = 0
+        self.refresh()
+
+    # ------------------------------------------------------------------ weights
+    def refresh(self) -> None:
+        """Re-derive kernel-side weight layouts from the current parameter values."""
+        sp, p = self.spec, self.p
+        self.film_w2 = torch.cat([p[n + ".weight"] for n in sp.tproj_names()], dim=0).contiguous()
+        self.film_b2 = torch.cat([p[n + ".bias"] for n in sp.tproj_names()], dim=0).contiguous()
+        self.wf = p["final.weight"].reshape(-1).contiguous()      # [(C+1)*3], index c*3+k
+        for key in list(self._packed):
+            self._pack_tc(key)
+
+    def _shape(self, li: int, B: int, L: int, L0: int) -> ConvTcShape:
+        sp = self.spec
+        d = sp.depth
+        lc = sp.layer_channels
+        if li <= d:
+            return ConvTcShape(1, 0, B, L, lc[li - 1], L, 0, lc[li])
+        i = li - d - 1
+        return ConvTcShape(2, 1, B, L, lc[li - 1], L0, sp.chs[d - 1 - i], lc[li])
+
+    def _pack_tc(self, key) -> Tensor:
+        li, L, L0 = key
+        shp = self._shape(li, 1, L, L0)
+        n = self.lib.gw_conv_tc_packed_elems(C.byref(shp))
+        if n < 0:
+            raise RuntimeError("gw_conv_tc_packed_elems: " + self.lib.gw_last_error().decode())
+        buf = self._packed.get(key)
+        if buf is None or buf.numel() != n:
+            buf = torch.empty(n, device=self.device, dtype=torch.bfloat16)
+            self._packed[key] = buf
+        w = self.p[self.spec.layer_names()[li] + ".0.weight"]
+        check(self.lib.gw_conv_tc_pack(C.byref(shp), ptr(w), ptr(buf), _cabi.stream_ptr()), "conv_tc_pack")
+        return buf
+
+    def tc_supported(self, li: int, L: int, L0: int) -> bool:
+        sp = self.spec
+        if self.conv_impl != "tc" or li == 0:
+            return False
+        lc = sp.layer_channels
+        cout = lc[li]
+        if cout > 256 or (cout & (cout - 1)) != 0:
+            return False
+        if li > sp.depth and (L % 2 != 0 or L0 * 2 != L):
+            return False
+        shp = self._shape(li, 1, L, L0)
+        return self.lib.gw_conv_tc_packed_elems(C.byref(shp)) > 0
+
+    # ------------------------------------------------------------------ workspace
+    def workspace(self, B: int, L: int, keep_raw: bool = False) -> _Workspace:
+        key = (B, L, keep_raw)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = _Workspace(self.spec, B, L, self.tdtype, self.device, keep_raw)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ kernels
+    def film_vectors(self, t: Tensor) -> Tensor:
+        sp = self.spec
+        t = t.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty(t.numel(), sp.film_dim, device=self.device, dtype=torch.float32)
+        check(self.lib.gw_film_vectors(ptr(t), t.numel(), sp.time_dim, sp.max_time, ptr(self.p["time_mlp.1.weight"]),
+                                       ptr(self.p["time_mlp.1.bias"]), ptr(self.film_w2), ptr(self.film_b2),
+                                       sp.base_ch, sp.film_dim, ptr(out), _cabi.stream_ptr()), "film_vectors")
+        self.launches += 1
+        return out
+
+    def cond_pyramid(self, ws: _Workspace, net: Tensor) -> None:
+        sp = self.spec
+        if sp.cond_in_ch == 0:
+            return
+        B, Cx, L = net.shape
+        n = sp.depth + 1
+        lens = (C.c_int * n)(*ws.Ls)
+        outs = (C.c_void_p * n)(*[ptr(c) for c in ws.cond])
+        check(self.lib.gw_cond_pyramid(ptr(net), B, Cx, L, sp.cond_in_ch, n, lens, outs, _cabi.stream_ptr()), "cond_pyramid")
+        self.launches += 1
+
+    def _conv(self, li: int, src0: Tensor, src1: Optional[Tensor], raw: Tensor, part: Tensor) -> int:
+        """Conv of layer li (>=1).  Returns n_part."""
+        sp = self.spec
+        B, L, Cout = raw.shape
+        L0, C0 = src0.shape[1], src0.shape[2]
+        up = src1 is not None
+        name = sp.layer_names()[li]
+        st = _cabi.stream_ptr()
+        if self.tc_supported(li, L, L0):
+            key = (li, L, L0)
+            packed = self._packed.get(key)
+            if packed is None:
+                packed = self._pack_tc(key)
+                self.launches += 1
+            shp = self._shape(li, B, L, L0)
+            check(self.lib.gw_conv_tc(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),
+                                      ptr(raw), ptr(part), self.tc_variant, st), f"conv_tc[{name}]")
+            self.launches += 1
+            return self.lib.gw_conv_tc_n_part(C.byref(shp))
+        C1 = src1.shape[2] if up else 0
+        check(self.lib.gw_conv3_simt(ptr(src0), C0, L0, 1 if up else 0, ptr(src1), C1, B, L,
+                                     ptr(self.p[name + ".0.weight"]), ptr(self.p[name + ".0.bias"]), Cout, ptr(raw),
+                                     self.gw_dtype, ptr(part), st), f"conv3_simt[{name}]")
+        self.launches += 1
+        return (L + 63) // 64
+
+    def _gn(self, li: int, ws: _Workspace, n_part: int, film: Tensor, film_b_stride: int, film_step_stride: int,
+            step_ptr: Optional[Tensor], pooled: Optional[Tensor], lvl: int) -> None:
+        sp = self.spec
+        name = sp.layer_names()[li]
+        raw, out = ws.raw[li], ws.out[li]
+        B, L, Cc_ = raw.shape
+        Cc = sp.cond_in_ch
+        cname = sp.cond_names()[li]
+        check(self.lib.gw_gn_apply(ptr(raw), ptr(ws.part), n_part, B, L, Cc_, ptr(self.p[name + ".1.weight"]),
+                                   ptr(self.p[name + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                   ptr(self.p[cname + ".weight"]) if Cc > 0 else None,
+                                   ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film), sp.film_offsets()[li],
+                                   film_b_stride, film_step_stride, ptr(step_ptr), ptr(out), ptr(pooled),
+                                   ptr(ws.stats[li]) if ws.stats is not None else None, self.gw_dtype,
+                                   _cabi.stream_ptr()), f"gn_apply[{name}]")
+        self.launches += 1
+
+    def body(self, ws: _Workspace, net_a: Tensor, net_b: Optional[Tensor], step_ptr: Optional[Tensor], film: Tensor,
+             film_b_stride: int, film_step_stride: int) -> Tensor:
+        """conv_in .. decoders[-1] FiLM; returns the last activation [B, L, base_ch].  The cond pyramid must be current."""
+        sp = self.spec
+        d = sp.depth
+        B, Cx, L = net_a.shape
+        st = _cabi.stream_ptr()
+        check(self.lib.gw_conv_in(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),
+                                  ptr(self.p["encoders.0.0.bias"]), sp.base_ch, ptr(ws.raw[0]), self.gw_dtype,
+                                  ptr(ws.part), st), "conv_in")
+        self.launches += 1
+        self._gn(0, ws, (L + 127) // 128, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[0], 0)
+        for i in range(1, d):
+            n_part = self._conv(i, ws.pooled[i - 1], None, ws.raw[i], ws.part)
+            self._gn(i, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[i], i)
+        n_part = self._conv(d, ws.pooled[d - 1], None, ws.raw[d], ws.part)
+        self._gn(d, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, None, d)
+        h = ws.out[d]
+        for i in range(d):
+            li = d + 1 + i
+            n_part = self._conv(li, h, ws.out[d - 1 - i], ws.raw[li], ws.part)
+            self._gn(li, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, None, d - 1 - i)
+            h = ws.out[li]
+        return h
+
+    def head(self, h: Tensor, net_a: Tensor, net_b: Optional[Tensor], params: StepParams, coef: Optional[Tensor],
+             step_ptr: Optional[Tensor], noise: Optional[Tensor], eps_out: Optional[Tensor], x0_out: Optional[Tensor],
+             B: int) -> None:
+        _, Cx, L = net_a.shape
+        check(self.lib.gw_final_step(ptr(h), self.gw_dtype, ptr(net_a), ptr(net_b), B, Cx, L, self.spec.base_ch,
+                                     ptr(self.wf), ptr(self.p["final.bias"]), C.byref(params), ptr(coef), ptr(step_ptr),
+                                     ptr(noise), ptr(eps_out), ptr(x0_out), _cabi.stream_ptr()), "final_step")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ public: plain forward
+    @torch.no_grad()
+    def forward(self, x: Tensor, t: Tensor, keep_raw: bool = False) -> Tensor:
+        """UNet1D.forward (models.py:195-231): x [B, C, L] fp32, t [B] -> eps_hat [B, 1, L] fp32."""
+        sp = self.spec
+        if x.device.type != "cuda":
+            raise RuntimeError("gwb200: CUDA tensors only (no CPU fallback)")
+        B, Cx, L = x.shape
+        if Cx != sp.in_ch:
+            raise ValueError(f"expected {sp.in_ch} input channels, got {Cx}")
+        if L < 2 ** sp.depth:
+            raise ValueError("sequence too short for the U-Net depth")
+        x = x.contiguous().float()
+        ws = self.workspace(B, L, keep_raw)
+        film = self.film_vectors(t.reshape(-1).expand(B) if t.numel() == 1 else t)
+        self.cond_pyramid(ws, x)
+        h = self.body(ws, x, None, None, film, sp.film_dim, 0)
+        eps = torch.empty(B, 1, L, device=self.device, dtype=torch.float32)
+        prm = StepParams(0, 0, 0, 0, 1.0, 0.0, None, 0, 0)
+        self.head(h, x, None, prm, None, None, None, eps, None, B)
+        return eps
+
+
+# ======================================================================================================
+# sampler
+# ======================================================================================================
+def build_t_schedule(T: int, steps: int, start_t: Optional[int]) -> List[int]:
+    """inference.py:217-228, on the host (pure integers; fp32 linspace + round like the reference)."""
+    if start_t is None:
+        start_t = T - 1
+    start_t = int(max(0, min(start_t, T - 1)))
+    steps = int(max(1, min(steps, start_t + 1)))
+    ts = torch.linspace(start_t, 0, steps).round().long()
+    ts = torch.unique_consecutive(ts)
+    out = [int(v) for v in ts]
+    if out[0] != start_t:
+        out = [start_t] + out
+    if out[-1] != 0:
+        out = out + [0]
+    return out
+
+
+def cfg_weight(i: int, N: int, mode: str, wmax: float, center: float, width: float) -> float:
+    """inference.py:230-244."""
+    s = 1.0 if N <= 1 else i / (N - 1)
+    mode = mode.lower()
+    if mode == "const":
+        return float(wmax)
+    if mode == "tophat":
+        lo, hi = center - width * 0.5, center + width * 0.5
+        return float(wmax) if (lo <= s <= hi) else 1.0
+    if mode == "gauss":
+        sig = max(width, 1e-9)
+        return float(wmax) * math.exp(-0.5 * ((s - center) / sig) ** 2)
+    raise ValueError(f"unknown cfg-mode: {mode}")
+
+
+class SamplerPlan:
+    """One DDIM/DDPM chain configuration bound to (B, L): device tables + a captured CUDA graph."""
+
+    def __init__(self, eng: UNetEngine, alpha_bar: Tensor, B: int, L: int, *, T: int, steps: int, eta: float,
+                 start_t: Optional[int], dc_weight: float, eps_scale: float, pred_type: str, cfg_scale: float,
+                 cfg_mode: str, cfg_center: float, cfg_width: float, cfg_u_only_thresh: float, seed: int = 0,
+                 sample0: int = 0):
+        self.eng, self.B, self.L = eng, B, L
+        sp = eng.spec
+        dev = eng.device
+        sched = build_t_schedule(T, steps, start_t)
+        N = len(sched)
+        self.sched, self.N = sched, N
+        ab = alpha_bar.detach().float().cpu().clamp(1e-12, 1.0)           # inference.py:399
+        coef = torch.zeros(N, 16, dtype=torch.float32)
+        uses = []
+        draw = 1                                                        # draw 0 initialises x_T
+        for i, t_now in enumerate(sched):
+            ab_t = ab[t_now]
+            ab_prev = ab[sched[i + 1]] if i + 1 < N else torch.tensor(1.0)
+            w = cfg_weight(i, N, cfg_mode, cfg_scale, cfg_center, cfg_width)
+            if w <= cfg_u_only_thresh:
+                use = 1
+            elif abs(w - 1.0) <= 1e-6:
+                use = 0
+            else:
+                use = 2
+            uses.append(use)
+            sig = eta * torch.sqrt((1 - ab_prev) / (1 - ab_t) * (1 - ab_t / ab_prev))       # inference.py:481
+            dirc = torch.sqrt(torch.clamp(1 - ab_prev - sig ** 2, min=0.0))                 # inference.py:482
+            last = 1.0 if t_now == 0 else 0.0
+            sigv = float(sig) if (not last and float(sig) > 0 and math.isfinite(float(sig))) else 0.0
+            coef[i, 0] = torch.sqrt(1 - ab_t)
+            coef[i, 1] = torch.sqrt(ab_t)
+            coef[i, 2] = torch.sqrt(ab_prev)
+            coef[i, 3] = dirc if math.isfinite(float(dirc)) else 0.0
+            coef[i, 4] = sigv
+            coef[i, 5] = w
+            coef[i, 6] = float(use)
+            coef[i, 7] = last
+            coef[i, 8] = float(draw if sigv > 0 else 0)
+            coef[i, 9] = torch.sqrt(torch.clamp(1 - ab_t, min=1e-12))
+            if sigv > 0:
+                draw += 1
+        self.n_draws = draw
+        self.ab_start = float(ab[sched[0]])
+        self.cfg_both = any(u != 0 for u in uses)       # an unconditional batch is needed at some step
+        self.Bn = B * (2 if self.cfg_both else 1)
+        self.coef = coef.to(dev)
+        self.film = eng.film_vectors(torch.tensor(sched, dtype=torch.int64, device=dev))
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        Cx = sp.in_ch
+        self.net = [torch.zeros(self.Bn, Cx, L, device=dev, dtype=torch.float32) for _ in range(2)]
+        self.ws = eng.workspace(self.Bn, L)
+        self.y_dc = torch.zeros(B, L, device=dev, dtype=torch.float32) if dc_weight > 0 else None
+        self.params = StepParams(1, 1 if self.cfg_both else 0, 1 if sp.use_selfcond else 0, 1 if pred_type != "eps" else 0,
+                                 float(eps_scale), float(dc_weight), ptr(self.y_dc), int(seed) & (2 ** 64 - 1), int(sample0))
+        self.noise: Optional[Tensor] = None
+        self.trace_eps: Optional[Tensor] = None
+        self.trace_x0: Optional[Tensor] = None
+        self._graph = None
+        self._graph_steps = 0
+
+    # one reverse step = 16 kernels
+    def enqueue_step(self) -> None:
+        eng = self.eng
+        h = eng.body(self.ws, self.net[0], self.net[1], self.step, self.film, 0, eng.spec.film_dim)
+        eng.head(h, self.net[0], self.net[1], self.params, self.coef, self.step, self.noise, self.trace_eps, self.trace_x0, self.B)
+        check(eng.lib.gw_step_advance(ptr(self.step), -1, _cabi.stream_ptr()), "step_advance")
+        eng.launches += 1
+
+    def load_inputs(self, x_init: Tensor, cond_on: Tensor, cond_off: Optional[Tensor], y_dc: Optional[Tensor]) -> None:
+        """x_init [B,1,L]; cond_on/off [B,Cc,L] (already cond-scaled / zeroed as inference.py:434-446)."""
+        sp, B = self.eng.spec, self.B
+        for net in self.net:
+            net.zero_()
+            net[:B, 0:1] = x_init
+            if sp.cond_in_ch > 0:
+                net[:B, 1:1 + sp.cond_in_ch] = cond_on
+            if self.cfg_both:
+                net[B:, 0:1] = x_init
+                if sp.cond_in_ch > 0 and cond_off is not None:
+                    net[B:, 1:1 + sp.cond_in_ch] = cond_off
+        if self.y_dc is not None:
+            self.y_dc.copy_(y_dc.reshape(B, self.L))
+        self.step.zero_()
+        self.eng.cond_pyramid(self.ws, self.net[0])
+
+    def capture(self, steps_per_graph: int) -> None:
+        """Capture `steps_per_graph` reverse steps in one CUDA graph (N for the whole chain)."""
+        if self._graph is not None and self._graph_steps == steps_per_graph:
+            return
+        # warm-up outside capture (lazy packing, cudaFuncSetAttribute) on a side stream, as torch requires
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        saved = [n.clone() for n in self.net]
+        with torch.cuda.stream(s):
+            self.enqueue_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for n, sv in zip(self.net, saved):
+            n.copy_(sv)
+        self.step.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(steps_per_graph):
+                self.enqueue_step()
+        self._graph, self._graph_steps = g, steps_per_graph
+        self.step.zero_()
+
+    def run(self, use_graph: bool = True, steps_per_graph: Optional[int] = None) -> Tensor:
+        """Run the N-step chain from the loaded inputs; returns x_0 estimate [B,1,L] (a view of the ping-pong buffer)."""
+        N = self.N
+        if use_graph:
+            spg = steps_per_graph or N
+            if N % spg != 0:
+                spg = 1
+            self.capture(spg)
+            for _ in range(N // spg):
+                self._graph.replay()
+        else:
+            for _ in range(N):
+                self.enqueue_step()
+        return self.net[N & 1][: self.B, 0:1]

@@ -1,0 +1,224 @@
+"""Drop-in mirror of the reference sampler entry points (src/snr_denoising/inference.py:209-244, 317-514).
+
+`ddim_sample` keeps the reference signature and argument meaning; additive behaviour only:
+  * `cond_stack` may be [B, cond_in_ch, L] (the reference is hard-wired to B=1);
+  * `noise=` injects the draws the reference would take from the global RNG ([n_draws, B, 1, L], draw 0 = x_T,
+    draw k = k-th stochastic step), `seed=`/`sample0=` select the on-device Philox stream instead;
+  * `use_graph=` runs the whole chain as one CUDA graph, `compute_dtype=` picks fp32-exact or bf16/tcgen05 kernels.
+Deployment-CLI pieces of the reference file (HDF5 IO, whitening, plotting; inference.py:59-205, 247-314, 517-903) are
+outside the hot path and are not re-implemented here.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .engine import SamplerPlan, build_t_schedule, cfg_weight
+from .models import CustomDiffusion, UNet1D
+
+__all__ = ["snr_from_alpha_bar", "t_for_target_snr", "_build_t_schedule", "_cfg_weight", "_reduce_to_one_channel",
+           "one_step_proxy_like_test_infer", "ddim_sample", "make_sampler_plan"]
+
+
+def snr_from_alpha_bar(alpha_bar: torch.Tensor) -> np.ndarray:
+    ab = alpha_bar.detach().cpu().numpy().clip(1e-12, 1 - 1e-12)
+    return np.sqrt(ab / (1.0 - ab))
+
+
+def t_for_target_snr(diffusion: CustomDiffusion, target_snr: float) -> int:
+    return int(np.argmin(np.abs(snr_from_alpha_bar(diffusion.alpha_bar) - float(target_snr))))
+
+
+def _build_t_schedule(T: int, steps: int, device, start_t: Optional[int]) -> torch.Tensor:
+    return torch.tensor(build_t_schedule(T, steps, start_t), dtype=torch.long, device=device)
+
+
+def _cfg_weight(i: int, N: int, mode: str, wmax: float, center: float, width: float) -> float:
+    return cfg_weight(i, N, mode, wmax, center, width)
+
+
+def _reduce_to_one_channel(x: torch.Tensor) -> torch.Tensor:
+    return x[:, :1, :] if (x.ndim == 3 and x.size(1) > 1) else x
+
+
+_PLANS: Dict[Tuple, SamplerPlan] = {}
+
+
+def make_sampler_plan(model: UNet1D, diffusion: CustomDiffusion, B: int, L: int, *, T: int, steps: int, eta: float,
+                      start_t: Optional[int] = None, dc_weight: float = 0.0, eps_scale: float = 1.0,
+                      pred_type: str = "eps", cfg_scale: float = 1.0, cfg_mode: str = "const", cfg_center: float = 0.5,
+                      cfg_width: float = 0.3, cfg_u_only_thresh: float = 0.0, seed: int = 0, sample0: int = 0,
+                      compute_dtype: Optional[str] = None, conv_impl: str = "auto", cache: bool = True) -> SamplerPlan:
+    eng = model.engine(compute_dtype, conv_impl)
+    key = (id(eng), B, L, T, steps, float(eta), start_t, float(dc_weight), float(eps_scale), pred_type, float(cfg_scale),
+           cfg_mode, float(cfg_center), float(cfg_width), float(cfg_u_only_thresh))
+    plan = _PLANS.get(key) if cache else None
+    if plan is None:
+        plan = SamplerPlan(eng, diffusion.alpha_bar, B, L, T=T, steps=steps, eta=eta, start_t=start_t, dc_weight=dc_weight,
+                           eps_scale=eps_scale, pred_type=pred_type, cfg_scale=cfg_scale, cfg_mode=cfg_mode,
+                           cfg_center=cfg_center, cfg_width=cfg_width, cfg_u_only_thresh=cfg_u_only_thresh, seed=seed,
+                           sample0=sample0)
+        if cache:
+            if len(_PLANS) > 16:
+                _PLANS.clear()
+            _PLANS[key] = plan
+    plan.params.seed = int(seed) & (2 ** 64 - 1)
+    plan.params.sample0 = int(sample0)
+    return plan
+
+
+@torch.no_grad()
+def ddim_sample(model, diffusion, cond_stack: torch.Tensor,
+                T: int, steps: int, eta: float,
+                device, length: int, debug: bool,
+                start_t: Optional[int], init_mode: str, x0_std_est: float,
+                dc_weight: float, cond_scale: float, eps_scale: float, pred_type: str,
+                in_ch: int, cond_in_ch: int, use_selfcond: bool, cfg_scale: float,
+                cfg_mode: str, cfg_center: float, cfg_width: float, cfg_u_only_thresh: float,
+                oracle_init: bool = False, clean_norm_311: Optional[torch.Tensor] = None,
+                log_jsonl_path: Optional[str] = None, log_interval: int = 0,
+                xcorr_window_samp: int = 0, delta_t: float = 1.0,
+                amp: bool = False, drop_y_only: bool = True, *,
+                noise: Optional[torch.Tensor] = None, seed: Optional[int] = None, sample0: int = 0,
+                use_graph: bool = True, compute_dtype: Optional[str] = None, conv_impl: str = "auto",
+                return_trace: bool = False) -> torch.Tensor:
+    """eta-parameterised DDIM sampler (eta=0 deterministic, eta=1 with all steps = DDPM ancestral); inference.py:374-514."""
+    if init_mode not in ("noise", "scaled-noise", "y-blend"):
+        raise ValueError(f"unknown init_mode: {init_mode}")
+    cfg_weight(0, 2, cfg_mode, cfg_scale, cfg_center, cfg_width)           # raises ValueError on an unknown cfg-mode
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("gwb200 ddim_sample runs on CUDA (sm_100a) only: no CPU fallback")
+    cond_stack = cond_stack.to(dev).float()
+    if cond_stack.ndim == 2:
+        cond_stack = cond_stack.unsqueeze(0)
+    B, _, L = cond_stack.shape
+    if length != L:
+        raise ValueError(f"length={length} does not match cond_stack length {L}")
+    if model.in_ch != in_ch or model.cond_in_ch != cond_in_ch or bool(model.use_selfcond) != bool(use_selfcond):
+        raise ValueError("in_ch / cond_in_ch / use_selfcond do not match the model")
+    if compute_dtype is None and amp:
+        compute_dtype = "bf16"            # reference AMP is fp16 autocast (inference.py:444); bf16 is the B200 analogue
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    plan = make_sampler_plan(model, diffusion, B, L, T=T, steps=steps, eta=eta, start_t=start_t, dc_weight=dc_weight,
+                             eps_scale=eps_scale, pred_type=pred_type, cfg_scale=cfg_scale, cfg_mode=cfg_mode,
+                             cfg_center=cfg_center, cfg_width=cfg_width, cfg_u_only_thresh=cfg_u_only_thresh, seed=seed,
+                             sample0=sample0, compute_dtype=compute_dtype, conv_impl=conv_impl)
+    y_chan = cond_stack[:, :1, :]
+    meta = cond_stack[:, 1:, :] if cond_stack.size(1) > 1 else None
+    ab_start = torch.tensor(plan.ab_start, device=dev)
+
+    def draw0():
+        if noise is not None:
+            return noise[0].to(dev).float().reshape(B, 1, L)
+        g = torch.Generator(device=dev)
+        g.manual_seed(int(seed) & (2 ** 63 - 1))
+        return torch.randn(B, 1, L, device=dev, generator=g)
+
+    if oracle_init and (clean_norm_311 is not None):                        # inference.py:403-406
+        t0 = torch.full((B,), plan.sched[0], dtype=torch.long, device=dev)
+        x_t, _ = diffusion.q_sample(clean_norm_311.to(dev).float().reshape(B, 1, L), t0, noise=draw0())
+        if debug:
+            print(f"[debug] oracle-init enabled (t0={plan.sched[0]})")
+    elif init_mode == "noise":
+        x_t = draw0()
+    elif init_mode == "scaled-noise":
+        x_t = torch.sqrt(ab_start * (x0_std_est ** 2) + (1 - ab_start)) * draw0()
+    else:
+        x_t = torch.sqrt(ab_start) * y_chan + torch.sqrt(1 - ab_start) * draw0()
+
+    y_used = cond_scale * y_chan                                           # inference.py:434-435
+    cond_on = torch.cat([y_used, meta], dim=1) if meta is not None else y_used
+    if drop_y_only and meta is not None:                                    # inference.py:446
+        cond_off = torch.cat([torch.zeros_like(y_used), meta], dim=1)
+    else:
+        cond_off = torch.zeros_like(cond_on)
+
+    want_noise = None
+    if noise is not None:
+        if noise.shape[0] < plan.n_draws:
+            raise ValueError(f"noise has {noise.shape[0]} draws, the chain needs {plan.n_draws}")
+        want_noise = noise[: plan.n_draws].to(dev).float().reshape(plan.n_draws, B, L).contiguous()
+    trace = return_trace or bool(log_jsonl_path) or debug
+    rebuild = False
+    if (want_noise is None) != (plan.noise is None) or (want_noise is not None and plan.noise.shape != want_noise.shape):
+        plan.noise = None if want_noise is None else torch.empty_like(want_noise)
+        rebuild = True
+    if want_noise is not None:
+        plan.noise.copy_(want_noise)
+    if trace and plan.trace_eps is None:
+        plan.trace_eps = torch.empty(B, L, device=dev)
+        plan.trace_x0 = torch.empty(B, L, device=dev)
+        rebuild = True
+    if rebuild:
+        plan._graph = None
+    plan.load_inputs(x_t, cond_on, cond_off, y_chan if dc_weight > 0 else None)
+
+    if debug:
+        print(f"[debug] init_mode={init_mode}, x0_std_est={x0_std_est:.3f}, ab_start={plan.ab_start:.6f}")
+        print(f"[debug] schedule length={plan.N}, first={plan.sched[0]}, last={plan.sched[-1]}")
+
+    if trace:
+        # per-step host visibility (debug prints / JSONL / parity traces): run step by step
+        if log_jsonl_path:
+            os.makedirs(os.path.dirname(log_jsonl_path) or ".", exist_ok=True)
+        steps_out = []
+        for i in range(plan.N):
+            x_in = plan.net[i & 1][:B, 0:1].clone() if return_trace else None
+            plan.enqueue_step()
+            x_now = plan.net[(i + 1) & 1][:B, 0:1]
+            if return_trace:
+                steps_out.append({"t": plan.sched[i], "x_in": x_in, "eps": plan.trace_eps.clone().view(B, 1, L),
+                                  "x0": plan.trace_x0.clone().view(B, 1, L), "x_out": x_now.clone()})
+            if debug and (i % max(1, plan.N // 5) == 0 or plan.sched[i] == 0):
+                print(f"x_t (t={plan.sched[i]}): mean={x_now.mean().item():.3e} std={x_now.std().item():.3e}")
+            if log_jsonl_path and ((i % max(1, log_interval) == 0) or (i == plan.N - 1)):
+                with open(log_jsonl_path, "a") as fh:
+                    fh.write(json.dumps({"phase": "ddim_step", "i": i, "t": plan.sched[i],
+                                         "i_norm": float(0.0 if plan.N <= 1 else i / (plan.N - 1)),
+                                         "alpha_bar": float(diffusion.alpha_bar[plan.sched[i]]),
+                                         "cfg_mode": cfg_mode, "cfg_w_t": float(plan.coef[i, 5]),
+                                         "cfg_scale": float(cfg_scale)}) + "\n")
+        out = plan.net[plan.N & 1][:B, 0:1].clone()
+        return (out, steps_out) if return_trace else out
+    return plan.run(use_graph=use_graph).clone()
+
+
+@torch.no_grad()
+def one_step_proxy_like_test_infer(model, diffusion, clean_norm: torch.Tensor, cond_stack: torch.Tensor,
+                                   sigma_scalar: float, target_snr: float, device, in_ch: int, cond_in_ch: int,
+                                   use_selfcond: bool, cfg_scale: float, drop_y_only: bool, cond_scale: float = 1.0,
+                                   eps_scale: float = 1.0, pred_type: str = "eps", amp: bool = False,
+                                   noise: Optional[torch.Tensor] = None):
+    """Single-forward x0 estimate at the t matching `target_snr` (inference.py:317-371)."""
+    dev = torch.device(device)
+    t_pick = t_for_target_snr(diffusion, target_snr)
+    B = clean_norm.shape[0]
+    t = torch.full((B,), t_pick, dtype=torch.long, device=dev)
+    x_t, _ = diffusion.q_sample(clean_norm.to(dev), t, noise=noise)
+    sc = torch.zeros_like(x_t)
+    y = cond_scale * cond_stack[:, :1, :].to(dev)
+    meta = cond_stack[:, 1:, :].to(dev) if cond_stack.size(1) > 1 else None
+    c_on = torch.cat([y, meta], dim=1) if meta is not None else y
+
+    def net_in(c):
+        return torch.cat([x_t, c, sc], dim=1) if use_selfcond else torch.cat([x_t, c], dim=1)
+
+    eng = model.engine("bf16" if amp else None)
+    out = eng.forward(net_in(c_on), t)
+    if cfg_scale != 1.0:
+        c_off = torch.cat([torch.zeros_like(y), meta], dim=1) if (drop_y_only and meta is not None) else torch.zeros_like(c_on)
+        out_u = eng.forward(net_in(c_off), t)
+        out = out_u + cfg_scale * (out - out_u)
+    out = _reduce_to_one_channel(out)
+    ab_t = diffusion.alpha_bar[t_pick].to(dev)
+    if pred_type == "eps":
+        x0 = (x_t - torch.sqrt(1 - ab_t) * (eps_scale * out)) / torch.sqrt(ab_t)
+    else:
+        x0 = out
+    return x0 * torch.tensor(sigma_scalar, device=dev).view(1, 1, 1)

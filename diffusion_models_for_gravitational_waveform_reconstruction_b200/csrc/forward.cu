@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     constexpr int TP = 128;
     extern __shared__ float sm[];
     float* xs = sm;                              // [Cx][TP + 2]
-    float* ws = xs + Cx * (TP + 2);              // [Cx*3][C]
+    float* ws = xs + ((Cx * (TP + 2) + 3) & ~3); // [Cx*3][C], 16-byte aligned for float4 reads
     float* bs = ws + Cx * 3 * C;                 // [C]
     float* wst = bs + C;                         // [n_iter*8 warps][2]
     const int b = blockIdx.y, tile = blockIdx.x, l0 = tile * TP;
@@ -245,7 +245,7 @@ extern "C" int gw_conv_in(const float* x, const float* x_alt, const int* step_pt
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv_in: dtype %d", dtype);
     constexpr int TP = 128;
     const int n_part = gw_cdiv(L, TP);
-    size_t smem = (size_t)(Cx * (TP + 2) + Cx * 3 * C + C + (C / 16) * 8 * 2) * sizeof(float);
+    size_t smem = (size_t)(((Cx * (TP + 2) + 3) & ~3) + Cx * 3 * C + C + (C / 16) * 8 * 2) * sizeof(float);
     dim3 grid(n_part, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32) {

@@ -30,6 +30,11 @@ struct TcSeg {
     int16_t ci0;      // first reference input channel of this chunk (packing only)
     uint8_t mask[2];  // taps summed into the weights of phase 0 / phase 1 (packing only)
     int32_t wk;       // K offset of this segment in the packed weight matrix
+    // v2 kernel: segments that read the same 64-channel column share one A tile of 130 rows (row0-1 .. row0+128)
+    uint8_t a_new;    // load a new A tile before this segment
+    uint8_t a_last;   // release the A tile after this segment
+    int8_t load_shift;  // row shift of that TMA load
+    int8_t desc_row;    // row (0..2) inside the A tile where this segment's MMA operand starts
 };
 
 struct TcParams {
@@ -42,6 +47,11 @@ struct TcParams {
     int cout;      // channels of the conv output
     int stages;
     int k_total;   // packed K extent (max n_seg * 64)
+    // v2 kernel
+    int m_super;   // ceil(m_tiles / 2)
+    int total_tiles;
+    int sa, sb, nbuf, n_acc;   // A ring slots, B ring slots, store staging buffers per warp, accumulator stages
+    int use_base_off;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -344,8 +354,268 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ kernel v2
+// Persistent CTAs (one per SM).  A work item is a SUPER-TILE of 2 x 128 rows x bn columns of one sample: every weight
+// tile fetched from L2 feeds two accumulators (the L2->SM fabric, ~42 B/clk/SM, is what bounds the v1 kernel), and the
+// three taps of a 64-channel chunk read ONE 130-row A tile through row-shifted UMMA descriptors (halo mode).
+// warp 0: TMA producer | warp 1: MMA issuer | warps 2..9: epilogue (two warps per TMEM lane quarter, half the columns each).
+#define TC2_A_SLOT 17408          // 130 rows x 128 B rounded up to 1 KB
+#define TC2_A_BYTES 16640         // bytes one A box really transfers
+#define TC2_MT 2
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int CG_LOG2>
+__global__ void __launch_bounds__(320, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out,
+                const __grid_constant__ TcParams P, const float* __restrict__ bias, float* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int SA = P.sa, SB = P.sb, NBUF = P.nbuf, NACC = P.n_acc;
+    const uint32_t b_bytes = (uint32_t)P.bn * TC_BLOCK_K * 2;
+    const uint32_t sA = base;                                           // [SA][MT][A_SLOT]
+    const uint32_t sB = sA + (uint32_t)SA * TC2_MT * TC2_A_SLOT;        // [SB][b_bytes]
+    const uint32_t sStage = sB + (uint32_t)SB * b_bytes;                // [8 warps][NBUF][4096]
+    const uint32_t sMisc = sStage + 8u * NBUF * 4096u;
+    uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc);                 // a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * 28);
+    float* s_bias = reinterpret_cast<float*>(misc + 256);               // [2][bn]  (per n_tile)
+    float* s_stat = s_bias + 512;                                       // [2 parity][MT][8 warps][8 groups][2]
+    auto a_full = [&](int i) { return smem_u32(bars + i); };
+    auto a_empty = [&](int i) { return smem_u32(bars + SA + i); };
+    auto b_full = [&](int i) { return smem_u32(bars + 2 * SA + i); };
+    auto b_empty = [&](int i) { return smem_u32(bars + 2 * SA + SB + i); };
+    auto acc_full = [&](int i) { return smem_u32(bars + 2 * SA + 2 * SB + i); };
+    auto acc_empty = [&](int i) { return smem_u32(bars + 2 * SA + 2 * SB + 2 + i); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < NACC * TC2_MT * P.bn) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_a1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm_out) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 1); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    for (int i = threadIdx.x; i < P.n_tiles * P.bn; i += blockDim.x) s_bias[i] = bias[i % P.cout];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t ia = 0, pa = 0, ib = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % P.n_tiles;
+                const int r = tile / P.n_tiles;
+                const int ms = r % P.m_super, b = r / P.m_super;
+                const int row0 = ms * (TC2_MT * TC_BLOCK_M);
+                const int n_seg = P.n_seg[n_tile];
+                for (int s = 0; s < n_seg; ++s) {
+                    const TcSeg sg = P.seg[n_tile][s];
+                    if (sg.a_new) {
+                        mbar_wait(a_empty(ia), pa ^ 1);
+                        mbar_expect_tx(a_full(ia), TC2_MT * TC2_A_BYTES);
+#pragma unroll
+                        for (int mt = 0; mt < TC2_MT; ++mt)
+                            tma_load_3d(sA + (ia * TC2_MT + mt) * TC2_A_SLOT, sg.src ? &tm_a1 : &tm_a0, a_full(ia), sg.col,
+                                        row0 + mt * TC_BLOCK_M + sg.load_shift, b);
+                        if (++ia == (uint32_t)SA) { ia = 0; pa ^= 1; }
+                    }
+                    mbar_wait(b_empty(ib), pb ^ 1);
+                    mbar_expect_tx(b_full(ib), (uint32_t)sg.n_cnt * TC_BLOCK_K * 2);
+                    const int wrow = n_tile * P.bn + sg.n_off;
+                    for (int j = 0; j < sg.n_cnt; j += 64)
+                        tma_load_2d(sB + ib * b_bytes + (uint32_t)j * 128, &tm_w, b_full(ib), sg.wk, wrow + j);
+                    if (++ib == (uint32_t)SB) { ib = 0; pb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t ia = 0, pa = 0, ib = 0, pb = 0, cur_a = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+                const int n_tile = tile % P.n_tiles;
+                const int n_seg = P.n_seg[n_tile];
+                const int as = it % NACC;
+                mbar_wait(acc_empty(as), (((uint32_t)(it / NACC)) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t acc0 = tmem_base + (uint32_t)(as * TC2_MT * P.bn);
+                for (int s = 0; s < n_seg; ++s) {
+                    const TcSeg sg = P.seg[n_tile][s];
+                    if (sg.a_new) {
+                        cur_a = ia;
+                        mbar_wait(a_full(ia), pa);
+                        if (++ia == (uint32_t)SA) { ia = 0; pa ^= 1; }
+                    }
+                    mbar_wait(b_full(ib), pb);
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc(TC_BLOCK_M, (uint32_t)sg.n_cnt);
+                    const uint32_t b0 = sB + ib * b_bytes;
+#pragma unroll
+                    for (int mt = 0; mt < TC2_MT; ++mt) {
+                        const uint32_t a0 = sA + (cur_a * TC2_MT + mt) * TC2_A_SLOT + (uint32_t)sg.desc_row * 128u;
+                        const uint32_t bo = P.use_base_off ? ((a0 >> 7) & 7u) : 0u;
+#pragma unroll
+                        for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+                            const uint64_t ad = make_sw128_desc(a0 + k * 32, bo);
+                            const uint64_t bd = make_sw128_desc(b0 + k * 32, 0);
+                            umma_bf16(acc0 + (uint32_t)(mt * P.bn + sg.n_off), ad, bd, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(b_empty(ib));
+                    if (sg.a_last) umma_commit(a_empty(cur_a));
+                    if (++ib == (uint32_t)SB) { ib = 0; pb ^= 1; }
+                }
+                umma_commit(acc_full(as));
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9) =====================
+        const int e = warp - 2;
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int ch = e >> 2;                        // which half of the columns
+        const int cols_per_warp = P.bn >> 1;
+        const uint32_t stg0 = sStage + (uint32_t)e * NBUF * 4096u;
+        const int cg = P.cout >> 3;
+        const int n_part = P.m_tiles * P.n_tiles;
+        int buf = 0, stores = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+            const int n_tile = tile % P.n_tiles;
+            const int r = tile / P.n_tiles;
+            const int ms = r % P.m_super, b = r / P.m_super;
+            const int as = it % NACC;
+            float* my_stat = s_stat + (((it & 1) * TC2_MT) * 8 + e) * 16;      // + mt * 8 * 16
+            if (lane < 16) {
+                my_stat[lane] = 0.0f;
+                my_stat[8 * 16 + lane] = 0.0f;
+            }
+            __syncwarp();
+            mbar_wait(acc_full(as), ((uint32_t)(it / NACC)) & 1u);
+            tc_fence_after();
+            for (int mt = 0; mt < TC2_MT; ++mt) {
+                const int m_tile = ms * TC2_MT + mt;
+                if (m_tile >= P.m_tiles) break;
+                const int row_base = m_tile * TC_BLOCK_M + q * 32;
+                const bool row_ok = row_base + lane < P.rows;
+                float* st_mt = my_stat + mt * 8 * 16;
+                const uint32_t acc = tmem_base + (uint32_t)((as * TC2_MT + mt) * P.bn) + ((uint32_t)(q * 32) << 16);
+                for (int c0 = ch * cols_per_warp; c0 < (ch + 1) * cols_per_warp; c0 += 64) {
+                    const uint32_t stg = stg0 + buf * 4096;
+                    if (stores >= NBUF) {              // the staging buffer must have been read by its previous store
+                        if (lane == 0) {
+                            if (NBUF == 2) tma_wait_read<1>(); else tma_wait_read<0>();
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int cc = c0 + hh * 32;
+                        uint32_t v[32];
+                        tmem_ld32(acc + (uint32_t)cc, v);
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float x = __uint_as_float(v[i]) + s_bias[n_tile * P.bn + cc + i];
+                            f[i] = __bfloat162float(__float2bfloat16_rn(x));
+                        }
+                        constexpr int NG = 32 >> CG_LOG2 ? 32 >> CG_LOG2 : 1;
+                        constexpr int GW = 32 / NG;
+                        const int ch0 = (n_tile * P.bn + cc) % P.cout;
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            float s1 = 0.0f, s2 = 0.0f;
+                            if (row_ok) {
+#pragma unroll
+                                for (int i = 0; i < GW; ++i) {
+                                    const float x = f[g * GW + i];
+                                    s1 += x;
+                                    s2 += x * x;
+                                }
+                            }
+                            s1 = warp_sum(s1);
+                            s2 = warp_sum(s2);
+                            if (lane == 0) {
+                                const int grp = (ch0 + g * GW) / cg;
+                                st_mt[grp * 2 + 0] += s1;
+                                st_mt[grp * 2 + 1] += s2;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int chunk = (hh * 4 + j) ^ (lane & 7);
+                            const uint32_t dst = stg + (uint32_t)lane * 128 + (uint32_t)chunk * 16;
+                            const uint32_t p0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+                            const uint32_t p1 = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+                            const uint32_t p2 = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+                            const uint32_t p3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                                         : "memory");
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tm_out, stg, n_tile * P.bn + c0, row_base, b);
+                        tma_commit();
+                    }
+                    ++stores;
+                    if (NBUF == 2) buf ^= 1;
+                }
+            }
+            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp, publish the stats
+            tc_fence_before();
+            named_bar_sync(1, 256);
+            if (e == 0 && lane == 0) mbar_arrive(acc_empty(as));
+            const int tid = threadIdx.x - 64;
+            if (tid < TC2_MT * 8) {
+                const int mt = tid >> 3, g = tid & 7;
+                const int m_tile = ms * TC2_MT + mt;
+                if (m_tile < P.m_tiles) {
+                    const float* sp = s_stat + (((it & 1) * TC2_MT + mt) * 8) * 16 + g * 2;
+                    float a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        a1 += sp[w * 16 + 0];
+                        a2 += sp[w * 16 + 1];
+                    }
+                    float* pt = part + ((size_t)b * n_part + (m_tile * P.n_tiles + n_tile)) * 16;
+                    pt[g * 2 + 0] = a1;
+                    pt[g * 2 + 1] = a2;
+                }
+            }
+        }
+        if (lane == 0) tma_wait_all<0>();
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
-static int build_params(const gw_conv_tc_shape* s, TcParams* P) {
+static int build_params(const gw_conv_tc_shape* s, TcParams* P, bool halo = false) {
     memset(P, 0, sizeof(*P));
     GW_REQUIRE(s->Cout % 64 == 0 && s->Cout <= 256, "conv_tc: Cout=%d must be 64/128/192/256", s->Cout);
     GW_REQUIRE(s->C0 % 64 == 0 && s->C0 > 0 && s->C1 % 64 == 0, "conv_tc: C0=%d C1=%d must be multiples of 64", s->C0, s->C1);
@@ -385,9 +655,9 @@ static int build_params(const gw_conv_tc_shape* s, TcParams* P) {
         for (int c = 0; c < s->C1 / 64; ++c) {        // skip half, pair view [lo = skip[2m] | hi = skip[2m+1]]
             const int ci = s->C0 + c * 64;
             cand[nc++] = {1, 0, c * 64, ci, 0b010, 0b001};              // S[m].lo : W1 | W0
+            cand[nc++] = {1, +1, c * 64, ci, 0, 0b100};                 // S[m+1].lo : -  | W2
             cand[nc++] = {1, 0, s->C1 + c * 64, ci, 0b100, 0b010};      // S[m].hi : W2 | W1
             cand[nc++] = {1, -1, s->C1 + c * 64, ci, 0b001, 0};         // S[m-1].hi : W0 | -
-            cand[nc++] = {1, +1, c * 64, ci, 0, 0b100};                 // S[m+1].lo : -  | W2
         }
         for (int t = 0; t < P->n_tiles; ++t) {
             int n = 0;
@@ -415,6 +685,21 @@ static int build_params(const gw_conv_tc_shape* s, TcParams* P) {
     P->m_tiles = gw_cdiv(P->rows, TC_BLOCK_M);
     int mx = P->n_seg[0] > P->n_seg[1] ? P->n_seg[0] : P->n_seg[1];
     P->k_total = mx * 64;
+    // v2: group consecutive segments on the same (src, col) around one halo A tile
+    for (int t = 0; t < P->n_tiles; ++t) {
+        for (int i = 0; i < P->n_seg[t]; ++i) {
+            TcSeg& g = P->seg[t][i];
+            const bool first = i == 0 || P->seg[t][i - 1].src != g.src || P->seg[t][i - 1].col != g.col;
+            const bool last = i + 1 == P->n_seg[t] || P->seg[t][i + 1].src != g.src || P->seg[t][i + 1].col != g.col;
+            if (halo) {
+                g.a_new = first; g.a_last = last; g.load_shift = -1; g.desc_row = (int8_t)(g.shift + 1);
+            } else {
+                g.a_new = 1; g.a_last = 1; g.load_shift = (int8_t)g.shift; g.desc_row = 0;
+            }
+        }
+    }
+    P->m_super = gw_cdiv(P->m_tiles, 2);
+    P->total_tiles = s->B * P->m_super * P->n_tiles;
     return GW_OK;
 }
 
@@ -506,24 +791,59 @@ static int make_map2(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, 
     return GW_OK;
 }
 
+static int sm_count_cached() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
+// variant bits: 1 = v1 kernel sized for two CTAs/SM; 2 = v2 persistent super-tile kernel; 4 = (v2) halo-shared A tiles;
+//               8 = (v2 halo) set the descriptor base_offset field from the start address
 extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed,
                           const float* bias, void* raw, float* part, int variant, void* stream) {
     TcParams P;
-    int rc = build_params(s, &P);
+    const bool v2 = (variant & 2) != 0;
+    int rc = build_params(s, &P, v2 && (variant & 4));
     if (rc != GW_OK) return rc;
     GW_REQUIRE(src0 != nullptr && packed != nullptr && raw != nullptr && part != nullptr && bias != nullptr, "conv_tc: null pointer");
     GW_REQUIRE((s->n_src == 2) == (src1 != nullptr), "conv_tc: src1 / n_src mismatch");
+    GW_REQUIRE(!v2 || P.bn >= 128, "conv_tc v2 needs bn >= 128");
+    const uint32_t a_box_rows = v2 ? 130 : TC_BLOCK_M;
     CUtensorMap ta0, ta1, tw, to;
-    if ((rc = make_map3(&ta0, src0, (uint64_t)s->C0, (uint64_t)s->L0, (uint64_t)s->B, 64, TC_BLOCK_M)) != GW_OK) return rc;
+    if ((rc = make_map3(&ta0, src0, (uint64_t)s->C0, (uint64_t)s->L0, (uint64_t)s->B, 64, a_box_rows)) != GW_OK) return rc;
     if (s->pair) {
-        if ((rc = make_map3(&ta1, src1, (uint64_t)2 * s->C1, (uint64_t)P.rows, (uint64_t)s->B, 64, TC_BLOCK_M)) != GW_OK) return rc;
+        if ((rc = make_map3(&ta1, src1, (uint64_t)2 * s->C1, (uint64_t)P.rows, (uint64_t)s->B, 64, a_box_rows)) != GW_OK) return rc;
         if ((rc = make_map3(&to, raw, (uint64_t)2 * s->Cout, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
     } else {
         ta1 = ta0;
         if ((rc = make_map3(&to, raw, (uint64_t)s->Cout, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
     }
     if ((rc = make_map2(&tw, packed, (uint64_t)P.k_total, (uint64_t)P.n_tiles * P.bn, 64, 64)) != GW_OK) return rc;
-
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cg = s->Cout / 8;
+    if (v2) {
+        P.use_base_off = (variant & 8) ? 1 : 0;
+        P.sa = 2;
+        if (P.bn > 128) { P.sb = 3; P.nbuf = 1; P.n_acc = 1; }
+        else { P.sb = 4; P.nbuf = 2; P.n_acc = 2; }
+        const int smem = 1024 + P.sa * TC2_MT * TC2_A_SLOT + P.sb * P.bn * 128 + 8 * P.nbuf * 4096 + 256 + 2048 + 2048 + 64;
+        GW_REQUIRE(smem <= 232448, "conv_tc v2: smem %d too large", smem);
+        int grid = P.total_tiles < sm_count_cached() ? P.total_tiles : sm_count_cached();
+#define TC2_GO(LG)                                                                                                  \
+    do {                                                                                                            \
+        GW_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
+        conv_tc2_kernel<LG><<<grid, 320, smem, st>>>(ta0, ta1, tw, to, P, bias, part);                               \
+    } while (0)
+        if (cg == 8) TC2_GO(3);
+        else if (cg == 16) TC2_GO(4);
+        else TC2_GO(5);
+#undef TC2_GO
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
     const int stage_bytes = TC_BLOCK_M * TC_BLOCK_K * 2 + P.bn * TC_BLOCK_K * 2;
     const int fixed = 1024 /*align slack*/ + 4 * 2 * 4096 /*store staging*/ + 256 + 256 * 4 + 64 * 4 + 64;
     int max_seg = P.n_seg[0] > P.n_seg[1] ? P.n_seg[0] : P.n_seg[1];
@@ -536,8 +856,6 @@ extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const voi
     P.stages = stages;
     const int smem = fixed + stages * stage_bytes;
     dim3 grid(P.m_tiles * s->B, P.n_tiles);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int cg = s->Cout / 8;
 #define TC_GO(LG)                                                                                                   \
     do {                                                                                                            \
         GW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \

@@ -192,15 +192,21 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = bs[oct * 8 + j];
-        for (int ck = 0; ck < Cx * 3; ++ck) {
-            const int ci = ck / 3, k = ck - ci * 3;
-            const float xv = xs[ci * (TP + 2) + pos + k];
-            const float4 wa = *reinterpret_cast<const float4*>(ws + ck * C + oct * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(ws + ck * C + oct * 8 + 4);
-            acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]);
-            acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
-            acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]);
-            acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+        const float* xp = xs + pos;
+        const float* wp = ws + oct * 8;
+        for (int ci = 0; ci < Cx; ++ci) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float xv = xp[k];
+                const float4 wa = *reinterpret_cast<const float4*>(wp);
+                const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+                acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]);
+                acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
+                acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]);
+                acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+                wp += C;
+            }
+            xp += TP + 2;
         }
         const int l = l0 + pos;
         float s1 = 0.0f, s2 = 0.0f;
@@ -381,18 +387,46 @@ extern "C" int gw_conv3_simt(const void* src0, int C0, int L0, int up0, const vo
 // fused GroupNorm-apply + SiLU + cond 1x1 conv + FiLM (+ pooled output)
 // ------------------------------------------------------------------------------------------------
 #define GN_MAX_CC 8
+// 4-channel vectors: 16 B (fp32) or 8 B (bf16) per lane, a warp always touches whole 128 B lines
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld4(const bf16* p, float (&v)[4]) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
+    uint2 r;
+    r.x = pack_bf16x2(v[0], v[1]);
+    r.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+// FAST silu: x*sigmoid(x) = h + h*tanh(h), h = x/2; one MUFU op (tanh.approx, rel. error ~2^-11 << bf16 epsilon)
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 // CC = compile-time number of conditioning channels (0, 1, 5) or -1 for the generic (<= GN_MAX_CC) path.
-// A thread owns one channel octet for the whole CTA so all per-channel coefficients live in registers.
+// A thread owns one channel quad for the whole CTA (coefficients live in registers) and walks row PAIRS so the
+// avg_pool1d(2,2) output is formed from fp32 values; UN pairs are in flight per iteration to cover HBM latency.
 template <typename T, bool FAST, int CC>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ part,
-                                                       int n_part, int L, int C, const float* __restrict__ gn_w,
-                                                       const float* __restrict__ gn_b, const float* __restrict__ cond,
-                                                       int Cc_rt, const float* __restrict__ wc, const float* __restrict__ bc,
-                                                       const float* __restrict__ film, int film_off, long film_b_stride,
-                                                       long film_step_stride, const int* __restrict__ step_ptr,
-                                                       T* __restrict__ out, T* __restrict__ pooled,
-                                                       float* __restrict__ stats_out, int rows_per_cta) {
+__global__ void __launch_bounds__(256, FAST ? ((CC == 0 || CC == 1) ? 3 : 2) : 2)
+gn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ part, int n_part, int L, int C,
+                const float* __restrict__ gn_w, const float* __restrict__ gn_b, const float* __restrict__ cond, int Cc_rt,
+                const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ film, int film_off,
+                long film_b_stride, long film_step_stride, const int* __restrict__ step_ptr, T* __restrict__ out,
+                T* __restrict__ pooled, float* __restrict__ stats_out, int rows_per_cta) {
     constexpr int NC = CC >= 0 ? CC : GN_MAX_CC;
+    constexpr int NCA = NC > 0 ? NC : 1;
+    constexpr int UN = (FAST && (CC == 0 || CC == 1)) ? 4 : 2;
     const int Cc = CC >= 0 ? CC : Cc_rt;
     __shared__ float s_mean[8], s_rstd[8];
     const int b = blockIdx.y;
@@ -422,66 +456,94 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ raw
         }
     }
     __syncthreads();
-    const int n_oct = C / 8;                    // divides 256 (C in {64,128,256,512,...})
-    const int oct = threadIdx.x % n_oct;
-    const int pr0 = threadIdx.x / n_oct, pr_stride = blockDim.x / n_oct;
+    const int n_quad = C / 4;                   // 16..512; host guarantees it divides or is a multiple of 256
     const int step = step_ptr != nullptr ? *step_ptr : 0;
     const float* fr = film + (size_t)step * film_step_stride + (size_t)b * film_b_stride + film_off;
-    // out = silu(A*x + Bn) * G + E + sum_j W[j] * cond[j]   with G = 1+gamma, E = bc*G + beta, W = wc*G
-    float cA[8], cB[8], cG[8], cE[8], cW[8][NC > 0 ? NC : 1];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = oct * 8 + i;
-        const int g = c / cg;
-        const float a = s_rstd[g] * gn_w[c];
-        cA[i] = a;
-        cB[i] = gn_b[c] - s_mean[g] * a;
-        cG[i] = 1.0f + fr[c];
-        cE[i] = fr[C + c];
-        if (NC > 0) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) cW[i][j] = (j < Cc) ? wc[c * Cc + j] : 0.0f;
-        }
-    }
-    const float* cbp = bc;
     const int r0 = blockIdx.x * rows_per_cta;
     const bool do_pool = pooled != nullptr;
     const int Lp = L / 2;
     const int n_pairs = rows_per_cta / 2;
-    for (int pr = pr0; pr < n_pairs; pr += pr_stride) {
-        const int la = r0 + 2 * pr;
-        if (la >= L) break;
-        float o[2][8];
+    const int pr_stride = n_quad >= 256 ? 1 : 256 / n_quad;
+    for (int quad = threadIdx.x % n_quad; quad < n_quad; quad += 256) {
+        const int pr0 = n_quad >= 256 ? 0 : threadIdx.x / n_quad;
+        // h = silu(A*x + Bn) + (bc + sum_j wc[j]*cond[j]);  out = h*G + E   (models.py:165-166, 205, 173)
+        // FAST folds the second line into the first: out = silu(.)*G + (E + bc*G) + sum_j (wc[j]*G)*cond[j]
+        float cA[4], cB[4], cG[4], cE[4], cC[4], cW[4][NCA];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int l = la + h;
-            if (l < L) {
-                float x[8];
-                ld8(raw + ((size_t)b * L + l) * C + oct * 8, x);
-                float cv[NC > 0 ? NC : 1];
-                if (NC > 0) {
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            const int g = c / cg;
+            const float a = s_rstd[g] * gn_w[c];
+            cA[i] = a;
+            cB[i] = gn_b[c] - s_mean[g] * a;
+            cG[i] = 1.0f + fr[c];
+            cE[i] = fr[C + c];
+            cC[i] = NC > 0 ? bc[c] : 0.0f;
 #pragma unroll
-                    for (int j = 0; j < NC; ++j) cv[j] = (j < Cc) ? cond[((size_t)b * L + l) * Cc + j] : 0.0f;
-                }
+            for (int j = 0; j < NCA; ++j) cW[i][j] = (NC > 0 && j < Cc) ? wc[c * Cc + j] : 0.0f;
+            if (FAST) {
+                cE[i] = fmaf(cC[i], cG[i], cE[i]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float v = silu_f<FAST>(fmaf(x[i], cA[i], cB[i]));
-                    if (NC > 0) {
-                        float cb = cbp[oct * 8 + i];      // L1-resident; keeps 8 registers free
-#pragma unroll
-                        for (int j = 0; j < NC; ++j) cb = fmaf(cW[i][j], cv[j], cb);
-                        v += cb;                          // h = silu(gn) + cond_bias   (models.py:205)
-                    }
-                    o[h][i] = fmaf(v, cG[i], cE[i]);      // h*(1+gamma)+beta            (models.py:173)
-                }
-                st8(out + ((size_t)b * L + l) * C + oct * 8, o[h]);
+                for (int j = 0; j < NCA; ++j) cW[i][j] *= cG[i];
             }
         }
-        if (do_pool && la + 1 < L) {
-            float p[8];
+        const T* rbase = raw + (size_t)b * L * C + quad * 4;
+        T* obase = out + (size_t)b * L * C + quad * 4;
+        const float* cbase = cond + (size_t)b * L * Cc;
+        for (int pr = pr0; pr < n_pairs; pr += pr_stride * UN) {
+            float x[UN][2][4];
+            float cv[UN][2][NCA];
+            // all loads first (addresses clamped into the sample so they need no predicate)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) p[i] = 0.5f * (o[0][i] + o[1][i]);
-            st8(pooled + ((size_t)b * Lp + (la >> 1)) * C + oct * 8, p);
+            for (int u = 0; u < UN; ++u) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int l = r0 + 2 * (pr + u * pr_stride) + h;
+                    l = l < L ? l : L - 1;
+                    ld4(rbase + (size_t)l * C, x[u][h]);
+                    if (NC > 0) {
+#pragma unroll
+                        for (int j = 0; j < NCA; ++j) cv[u][h][j] = (j < Cc) ? cbase[(size_t)l * Cc + j] : 0.0f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int l0 = r0 + 2 * (pr + u * pr_stride);
+                const bool pair_ok = (pr + u * pr_stride) < n_pairs;
+                float o[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float z = fmaf(x[u][h][i], cA[i], cB[i]);
+                        if (FAST) {
+                            float v = fmaf(silu_tanh(z), cG[i], cE[i]);
+                            if (NC > 0) {
+#pragma unroll
+                                for (int j = 0; j < NCA; ++j) v = fmaf(cW[i][j], cv[u][h][j], v);
+                            }
+                            o[h][i] = v;
+                        } else {
+                            float v = silu_f<false>(z);
+                            if (NC > 0) {
+                                float cb = cC[i];
+#pragma unroll
+                                for (int j = 0; j < NCA; ++j) cb = fmaf(cW[i][j], cv[u][h][j], cb);
+                                v += cb;
+                            }
+                            o[h][i] = fmaf(v, cG[i], cE[i]);
+                        }
+                    }
+                    if (pair_ok && l0 + h < L) st4(obase + (size_t)(l0 + h) * C, o[h]);
+                }
+                if (do_pool && pair_ok && l0 + 1 < L) {
+                    float pv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pv[i] = 0.5f * (o[0][i] + o[1][i]);
+                    st4(pooled + ((size_t)b * Lp + (l0 >> 1)) * C + quad * 4, pv);
+                }
+            }
         }
     }
 }
@@ -508,13 +570,12 @@ extern "C" int gw_gn_apply(const void* raw, const float* part, int n_part, int B
                            const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
                            const float* film, int film_off, long film_b_stride, long film_step_stride,
                            const int* step_ptr, void* out, void* pooled, float* stats_out, int dtype, void* stream) {
-    GW_REQUIRE(C % 64 == 0 && C <= 2048 && (256 % (C / 8) == 0 || (C / 8) % 256 == 0) && C / 8 <= 256,
-               "gw_gn_apply: C=%d", C);
+    GW_REQUIRE(C % 64 == 0 && C <= 4096 && (256 % (C / 4) == 0 || (C / 4) % 256 == 0), "gw_gn_apply: C=%d", C);
     GW_REQUIRE(Cc >= 0 && Cc <= GN_MAX_CC, "gw_gn_apply: Cc=%d (max %d)", Cc, GN_MAX_CC);
     GW_REQUIRE((cond != nullptr) == (Cc > 0), "gw_gn_apply: cond/Cc mismatch");
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_gn_apply: dtype %d", dtype);
     // >= 8 row pairs per thread so the per-thread coefficient setup is amortised
-    int rows = 2 * 8 * 256 / (C / 8);
+    int rows = C / 4 >= 256 ? 32 : 2 * 16 * (256 / (C / 4));     // 16 row pairs per thread
     if (rows > L) rows = (L + 1) & ~1;
     if (rows < 2) rows = 2;
     dim3 grid(gw_cdiv(L, rows), B);
@@ -560,35 +621,52 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
     const int n_half = (p.mode == 1 && p.cfg_both) ? 2 : 1;
     const int n_oct = C / 8;                 // threads per row
     const int rows_per_pass = blockDim.x / n_oct;
+    float w0[8], w1[8], w2[8];               // this thread's channel octet of the three taps
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = (threadIdx.x % n_oct) * 8 + i;
+        w0[i] = sw[c];
+        w1[i] = sw[C + c];
+        w2[i] = sw[2 * C + c];
+    }
     for (int hf = 0; hf < n_half; ++hf) {
         const int bb = b + hf * B;
-        for (int rb = 0; rb < TP + 2; rb += rows_per_pass) {      // uniform trip count: shuffles need the full warp
-            const int r = rb + threadIdx.x / n_oct;
-            const int oct = threadIdx.x % n_oct;
-            const int l = l0 + r - 1;
-            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-            if (r < TP + 2 && l >= 0 && l < L) {
-                float v[8];
-                ld8(h + ((size_t)bb * L + l) * C + oct * 8, v);
+        // rows r = rb + tid/n_oct for rb = 0, rpp, 2*rpp ... : issue every load first (clamped address), then reduce
+        constexpr int MAXP = 5;                                   // ceil(130 / 32) passes when C = 64; fewer rows/pass for wider C
+        const int oct = threadIdx.x % n_oct;
+        for (int rb0 = 0; rb0 < TP + 2; rb0 += rows_per_pass * MAXP) {
+            float v[MAXP][8];
+#pragma unroll
+            for (int ps = 0; ps < MAXP; ++ps) {
+                const int r = rb0 + ps * rows_per_pass + threadIdx.x / n_oct;
+                int l = l0 + r - 1;
+                l = l < 0 ? 0 : (l >= L ? L - 1 : l);
+                ld8(h + ((size_t)bb * L + l) * C + oct * 8, v[ps]);
+            }
+#pragma unroll
+            for (int ps = 0; ps < MAXP; ++ps) {
+                const int r = rb0 + ps * rows_per_pass + threadIdx.x / n_oct;
+                const int l = l0 + r - 1;
+                const bool ok = r < TP + 2 && l >= 0 && l < L;
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int c = oct * 8 + i;
-                    d0 = fmaf(v[i], sw[c], d0);
-                    d1 = fmaf(v[i], sw[C + c], d1);
-                    d2 = fmaf(v[i], sw[2 * C + c], d2);
+                    d0 = fmaf(v[ps][i], w0[i], d0);
+                    d1 = fmaf(v[ps][i], w1[i], d1);
+                    d2 = fmaf(v[ps][i], w2[i], d2);
                 }
-            }
-            // reduce over the n_oct lanes of this row (n_oct is a power of two <= 32)
-            for (int o = n_oct >> 1; o > 0; o >>= 1) {
-                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-            }
-            if (oct == 0 && r < TP + 2) {
-                float* q = pd + hf * 3 * (TP + 2);
-                q[r] = d0;
-                q[(TP + 2) + r] = d1;
-                q[2 * (TP + 2) + r] = d2;
+                if (!ok) { d0 = 0.0f; d1 = 0.0f; d2 = 0.0f; }
+                for (int o = n_oct >> 1; o > 0; o >>= 1) {
+                    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+                    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                }
+                if (oct == 0 && r < TP + 2) {
+                    float* q = pd + hf * 3 * (TP + 2);
+                    q[r] = d0;
+                    q[(TP + 2) + r] = d1;
+                    q[2 * (TP + 2) + r] = d2;
+                }
             }
         }
     }

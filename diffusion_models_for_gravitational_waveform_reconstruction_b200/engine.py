@@ -116,7 +116,7 @@ class UNetEngine:
     (the engine keeps references, not copies, so in-place optimiser updates are seen after `refresh()`)."""
 
     def __init__(self, params: Dict[str, Tensor], spec: ModelSpec, dtype: str = "bf16", conv_impl: str = "auto",
-                 tc_variant: int = 0):
+                 tc_variant: int = 6):
         self.lib = _cabi.load()
         self.spec = spec
         assert dtype in ("bf16", "fp32")

@@ -31,7 +31,7 @@ _SIGS = {
     "gw_version": ([], _I),
     "gw_last_error": ([], C.c_char_p),
     "gw_device_info": ([C.POINTER(_I)] * 3, _I),
-    "gw_film_vectors": ([_P, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _P], _I),
+    "gw_film_vectors": ([_P, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _P, _P], _I),
     "gw_cond_pyramid": ([_P, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_P), _P], _I),
     "gw_conv_in": ([_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P], _I),
     "gw_conv3_simt": ([_P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P], _I),
@@ -44,7 +44,26 @@ _SIGS = {
     "gw_conv_tc_n_part": ([C.POINTER(ConvTcShape)], _I),
     "gw_conv_tc": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _I, _P], _I),
 }
-# entry points added by backward.cu / optim.cu register themselves here (see _cabi_train.py)
+# training step: backward.cu / optim.cu
+_SIGS.update({
+    "gw_reduce_rows": ([_P, _I, _L, _F, _P, _I, _P], _I),
+    "gw_loss": ([_P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P], _I),
+    "gw_final_bwd": ([_P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
+    "gw_gn_bwd_scratch_elems": ([_I, _I, _I, _I], _L),
+    "gw_gn_bwd": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P, _P,
+                   _P, _P], _I),
+    "gw_weight_dgrad": ([_P, _I, _I, _P, _P], _I),
+    "gw_split_cat_grad": ([_P, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
+    "gw_wgrad3_simt": ([_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _L, _P, _P], _I),
+    "gw_wgrad_in": ([_P, _I, _I, _I, _P, _I, _I, _P, _L, _P, _P], _I),
+    "gw_film_bwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
+    "gw_train_draws": ([_U64, _P, _L, _I, _I, _I, _F, _P, _P, _P], _I),
+    "gw_train_pack": ([_P, _P, _I, _P, _P, _P, _P, _P, _I, _U64, _L, _P, _F, _I, _I, _P, _I, _I, _I, _P], _I),
+    "gw_selfcond_x0": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "gw_opt_scratch_doubles": ([], _I),
+    "gw_grad_sumsq": ([_P, _L, _P, _P], _I),
+    "gw_adamw_ema": ([_P, _P, _P, _P, _P, _L, _P, _P, _P, _F, _F, _F, _P, _P], _I),
+})
 _EXTRA_SIGS = {}
 
 

@@ -1,0 +1,792 @@
+// Backward-path kernels of the training step (train.py:408-439 of the reference = autograd through
+// UNet1D.forward + the masked Huber/MSE loss).  Everything here is CUDA-core fp32 math on channels-last
+// activations; the tcgen05 dgrad / wgrad GEMMs live in conv_tc.cu / wgrad_tc.cu.
+//
+// Notation for one conv block (models.py:160-173, 188-193), per sample b, position l, channel c (group g):
+//   z   = conv(in) + bias                       ("raw", saved by the forward)
+//   xh  = (z - mean[b,g]) * rstd[b,g]
+//   n   = xh * gn_w[c] + gn_b[c]
+//   a   = n * sigmoid(n)
+//   h   = a + bc[c] + sum_j wc[c,j] * cond[b,l,j]
+//   o   = h * (1 + gamma[b,c]) + beta[b,c]      ("out"; encoders also emit pooled = avg of row pairs)
+// Given do = dL/do:  dbeta = sum_l do, dgamma = sum_l do*h, dh = do*(1+gamma), dn = dh * silu'(n),
+//   d gn_w = sum dn*xh, d gn_b = sum dn, dxh = dn*gn_w,
+//   dz = rstd * (dxh - mean_g(dxh) - xh * mean_g(dxh*xh))      (biased variance, models.py:154-158)
+// All reductions are two-level and deterministic: per-CTA partials in caller-provided scratch, then a
+// fixed-order second pass (no floating-point atomics anywhere).
+#include "common.cuh"
+#include "../../include/gwb200.h"
+
+#define BW_MAX_CC 8
+
+// ------------------------------------------------------------------------------------------------
+// generic column sums: dst[c] (+)= scale * sum_r src[r, c]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ src, int n_rows, long n_cols, long pitch,
+                                                          float scale, float* __restrict__ dst, int accumulate) {
+    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int r = 0;
+    for (; r + 3 < n_rows; r += 4) {
+        a0 += src[(size_t)r * pitch + c];
+        a1 += src[(size_t)(r + 1) * pitch + c];
+        a2 += src[(size_t)(r + 2) * pitch + c];
+        a3 += src[(size_t)(r + 3) * pitch + c];
+    }
+    for (; r < n_rows; ++r) a0 += src[(size_t)r * pitch + c];
+    const float s = scale * ((a0 + a1) + (a2 + a3));
+    dst[c] = accumulate ? dst[c] + s : s;
+}
+
+static int reduce_rows(const float* src, int n_rows, long n_cols, long pitch, float scale, float* dst, int accumulate,
+                       cudaStream_t st) {
+    reduce_rows_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(src, n_rows, n_cols, pitch, scale, dst, accumulate);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+extern "C" int gw_reduce_rows(const float* src, int n_rows, long n_cols, float scale, float* dst, int accumulate, void* stream) {
+    GW_REQUIRE(n_rows > 0 && n_cols > 0, "gw_reduce_rows: sizes");
+    return reduce_rows(src, n_rows, n_cols, n_cols, scale, dst, accumulate, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss forward + dL/d eps_hat  (train.py:53-58, 411-421)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ eps_hat, const float* __restrict__ eps,
+                                                   const float* __restrict__ mask, const float* __restrict__ wt, int B, int L,
+                                                   int loss_type, float beta, float grad_scale, float* __restrict__ per_sample,
+                                                   float* __restrict__ d_eps) {
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    const float* eh = eps_hat + (size_t)b * L;
+    const float* e = eps + (size_t)b * L;
+    const float* m = mask ? mask + (size_t)b * L : nullptr;
+    float sm = 0.0f, sl = 0.0f;
+    for (int l = threadIdx.x; l < L; l += 256) {
+        const float mk = m ? m[l] : 1.0f;
+        const float d = eh[l] - e[l];
+        float el;
+        if (loss_type == 0) {
+            const float ad = fabsf(d);
+            el = ad < beta ? 0.5f * d * d / beta : ad - 0.5f * beta;      // F.smooth_l1_loss(beta)
+        } else {
+            el = d * d;
+        }
+        sm += mk;
+        sl += el * mk;
+    }
+    const float tm = block_sum_256(sm, red);
+    const float tl = block_sum_256(sl, red);
+    const float denom = fmaxf(tm, 1.0f);                                    // mask.sum().clamp_min(1) (train.py:419)
+    const float w = wt ? wt[b] : 1.0f;
+    if (threadIdx.x == 0) per_sample[b] = w * tl / denom;
+    const float k = grad_scale * w / (denom * (float)B);
+    for (int l = threadIdx.x; l < L; l += 256) {
+        const float mk = m ? m[l] : 1.0f;
+        const float d = eh[l] - e[l];
+        float g;
+        if (loss_type == 0) g = fabsf(d) < beta ? d / beta : (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f));
+        else g = 2.0f * d;
+        d_eps[(size_t)b * L + l] = k * mk * g;
+    }
+}
+
+extern "C" int gw_loss(const float* eps_hat, const float* eps, const float* mask, const float* wt, int B, int L, int loss_type,
+                       float beta, float grad_scale, float* per_sample, float* loss, float* d_eps, void* stream) {
+    GW_REQUIRE(B > 0 && L > 0 && (loss_type == 0 || loss_type == 1), "gw_loss: arguments");
+    GW_REQUIRE(loss_type == 1 || beta > 0.0f, "gw_loss: huber beta must be > 0");
+    loss_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(eps_hat, eps, mask, wt, B, L, loss_type, beta, grad_scale, per_sample, d_eps);
+    GW_LAUNCH_CHECK();
+    return reduce_rows(per_sample, B, 1, 1, 1.0f / (float)B, loss, 0, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head conv backward (models.py:230): d_h, and per-CTA partials of d final.weight / d final.bias
+//   eps[l] = bias + sum_k sum_c wf[c,k] * hcat[l+k-1, c]   =>   d_hcat[l,c] = sum_k wf[c,k] * d_eps[l-k+1]
+// partial layout per CTA: [(C+1)*3 + 1]  (weight grads in the reference's [c][k] order, then the bias grad)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict__ d_eps, const T* __restrict__ h,
+                                                        const float* __restrict__ net, int Cx, int L, int C,
+                                                        const float* __restrict__ wf, T* __restrict__ d_h,
+                                                        float* __restrict__ partial, int rows_per_cta) {
+    extern __shared__ float sm[];
+    const int n_oct = C / 8;
+    const int n_tr = 256 / n_oct;                 // thread rows
+    float* red = sm;                              // [n_tr][C*3]
+    const int b = blockIdx.y, r0 = blockIdx.x * rows_per_cta;
+    const int oct = threadIdx.x % n_oct, tr = threadIdx.x / n_oct;
+    float w[8][3], dw[8][3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            w[i][k] = wf[(oct * 8 + i) * 3 + k];
+            dw[i][k] = 0.0f;
+        }
+    const float* de = d_eps + (size_t)b * L;
+    const int r_end = min(r0 + rows_per_cta, L);
+    for (int r = r0 + tr; r < r_end; r += n_tr) {
+        const float e_m = r > 0 ? de[r - 1] : 0.0f, e_c = de[r], e_p = r + 1 < L ? de[r + 1] : 0.0f;
+        float hv[8], o[8];
+        ld8(h + ((size_t)b * L + r) * C + oct * 8, hv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            o[i] = fmaf(w[i][0], e_p, fmaf(w[i][1], e_c, w[i][2] * e_m));
+            dw[i][0] = fmaf(hv[i], e_p, dw[i][0]);
+            dw[i][1] = fmaf(hv[i], e_c, dw[i][1]);
+            dw[i][2] = fmaf(hv[i], e_m, dw[i][2]);
+        }
+        st8(d_h + ((size_t)b * L + r) * C + oct * 8, o);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) red[(size_t)tr * C * 3 + (oct * 8 + i) * 3 + k] = dw[i][k];
+    __syncthreads();
+    float* pt = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((C + 1) * 3 + 1);
+    for (int i = threadIdx.x; i < C * 3; i += 256) {
+        float a = 0.0f;
+        for (int t = 0; t < n_tr; ++t) a += red[(size_t)t * C * 3 + i];
+        pt[i] = a;
+    }
+    // x_t channel (index C of hcat) and the bias: warp 0
+    if (threadIdx.x < 32) {
+        const float* xr = net + (size_t)b * Cx * L;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, ab = 0.0f;
+        for (int r = r0 + threadIdx.x; r < r_end; r += 32) {
+            const float e_m = r > 0 ? de[r - 1] : 0.0f, e_c = de[r], e_p = r + 1 < L ? de[r + 1] : 0.0f;
+            const float x = xr[r];
+            a0 = fmaf(x, e_p, a0);
+            a1 = fmaf(x, e_c, a1);
+            a2 = fmaf(x, e_m, a2);
+            ab += e_c;
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); ab = warp_sum(ab);
+        if (threadIdx.x == 0) {
+            pt[C * 3 + 0] = a0; pt[C * 3 + 1] = a1; pt[C * 3 + 2] = a2; pt[C * 3 + 3] = ab;
+        }
+    }
+}
+
+extern "C" int gw_final_bwd(const float* d_eps, const void* h, int dtype, const float* net, int B, int Cx, int L, int C,
+                            const float* wf, void* d_h, float* scratch, float* d_wf, float* d_bf, void* stream) {
+    GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_final_bwd: C=%d", C);
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_final_bwd: dtype %d", dtype);
+    const int rows = 512;
+    dim3 grid(gw_cdiv(L, rows), B);
+    const int n_tr = 256 / (C / 8);
+    const size_t smem = (size_t)n_tr * C * 3 * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32) {
+        GW_CUDA(cudaFuncSetAttribute(final_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        final_bwd_kernel<float><<<grid, 256, smem, st>>>(d_eps, (const float*)h, net, Cx, L, C, wf, (float*)d_h, scratch, rows);
+    } else {
+        GW_CUDA(cudaFuncSetAttribute(final_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        final_bwd_kernel<bf16><<<grid, 256, smem, st>>>(d_eps, (const bf16*)h, net, Cx, L, C, wf, (bf16*)d_h, scratch, rows);
+    }
+    GW_LAUNCH_CHECK();
+    const int n_cta = grid.x * grid.y, nv = (C + 1) * 3 + 1;
+    int rc = reduce_rows(scratch, n_cta, nv - 1, nv, 1.0f, d_wf, 1, st);
+    if (rc != GW_OK) return rc;
+    return reduce_rows(scratch + nv - 1, n_cta, 1, nv, 1.0f, d_bf, 1, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm/SiLU/cond/FiLM backward.  Thread mapping as in gn_apply_kernel (forward.cu): a thread owns one
+// channel quad for the whole CTA and walks rows r0+tr, r0+tr+n_tr, ...
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld4f(const float* p, float (&v)[4]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld4f(const bf16* p, float (&v)[4]) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ void st4f(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4f(bf16* p, const float (&v)[4]) {
+    uint2 r;
+    r.x = pack_bf16x2(v[0], v[1]);
+    r.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
+struct GnBwdArgs {
+    const void* raw;        // [B, L, C] conv output saved by the forward
+    const float* stats;     // [B, 8, 2] (mean, rstd) saved by gw_gn_apply
+    const float* gn_w;      // [C]
+    const float* gn_b;      // [C]
+    const float* cond;      // [B, L, Cc] fp32 or NULL
+    const float* wc;        // [C, Cc]
+    const float* bc;        // [C]
+    const float* film;      // row of sample b: film + b*film_b_stride + film_off; gamma at [0,C), beta at [C,2C)
+    long film_b_stride;
+    int film_off;
+    const void* do_a;       // [B, L, C] gradient wrt out, or NULL
+    const void* do_pool;    // [B, L/2, C] gradient wrt the pooled output (encoders), or NULL
+    int L, C, Cc;
+    int rows_per_cta;
+};
+
+// per-thread constants of one channel quad
+template <int NCA>
+struct QuadCoef {
+    float A[4], Bn[4], G[4], cC[4], cW[4][NCA], gw[4];
+    float mean, rstd;
+};
+
+template <int NC, int NCA>
+__device__ __forceinline__ void load_quad(const GnBwdArgs& a, int b, int quad, int Cc, QuadCoef<NCA>& q) {
+    const int cg = a.C / 8;
+    const int g = (quad * 4) / cg;
+    q.mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+    q.rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+    const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = quad * 4 + i;
+        q.gw[i] = a.gn_w[c];
+        q.A[i] = q.rstd * q.gw[i];
+        q.Bn[i] = a.gn_b[c] - q.mean * q.A[i];
+        q.G[i] = 1.0f + fr[c];
+        q.cC[i] = NC > 0 ? a.bc[c] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < NCA; ++j) q.cW[i][j] = (NC > 0 && j < Cc) ? a.wc[c * Cc + j] : 0.0f;
+    }
+}
+
+// number of per-(b, c) sums the stats pass produces
+#define GN_NV(cc) (4 + (cc))
+
+template <typename T, bool FAST, int CC>
+__global__ void __launch_bounds__(256) gn_bwd_stats_kernel(GnBwdArgs a, float* __restrict__ partial) {
+    constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
+    constexpr int NCA = NC > 0 ? NC : 1;
+    constexpr int NV = 4 + NC;
+    extern __shared__ float red[];                      // [n_tr][C * NV]
+    const int Cc = CC >= 0 ? CC : a.Cc;
+    const int b = blockIdx.y, C = a.C, L = a.L;
+    const int n_quad = C / 4, n_tr = 256 / n_quad;
+    const int quad = threadIdx.x % n_quad, tr = threadIdx.x / n_quad;
+    QuadCoef<NCA> q;
+    load_quad<NC, NCA>(a, b, quad, Cc, q);
+    float acc[4][NV];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[i][v] = 0.0f;
+    const T* raw = (const T*)a.raw + (size_t)b * L * C + quad * 4;
+    const T* doa = a.do_a ? (const T*)a.do_a + (size_t)b * L * C + quad * 4 : nullptr;
+    const int Lp = L / 2;
+    const T* dop = a.do_pool ? (const T*)a.do_pool + (size_t)b * Lp * C + quad * 4 : nullptr;
+    const float* cbase = a.cond + (size_t)b * L * Cc;
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r_end = min(r0 + a.rows_per_cta, L);
+    for (int r = r0 + tr; r < r_end; r += n_tr) {
+        float x[4], d[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cv[NCA];
+        ld4f(raw + (size_t)r * C, x);
+        if (doa) ld4f(doa + (size_t)r * C, d);
+        if (dop && (r >> 1) < Lp) {
+            float p[4];
+            ld4f(dop + (size_t)(r >> 1) * C, p);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = fmaf(0.5f, p[i], d[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < NCA; ++j) cv[j] = (NC > 0 && j < Cc) ? cbase[(size_t)r * Cc + j] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float z = fmaf(x[i], q.A[i], q.Bn[i]);
+            const float s = sigmoid_f<FAST>(z);
+            float h = z * s;
+            if (NC > 0) {
+                float cb = q.cC[i];
+#pragma unroll
+                for (int j = 0; j < NCA; ++j) cb = fmaf(q.cW[i][j], cv[j], cb);
+                h += cb;
+            }
+            const float dn = d[i] * q.G[i] * (s * fmaf(z, 1.0f - s, 1.0f));
+            const float xh = (x[i] - q.mean) * q.rstd;
+            acc[i][0] += d[i];
+            acc[i][1] = fmaf(d[i], h, acc[i][1]);
+            acc[i][2] += dn;
+            acc[i][3] = fmaf(dn, xh, acc[i][3]);
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[i][4 + j] = fmaf(d[i], cv[j], acc[i][4 + j]);
+        }
+    }
+    const int nvr = 4 + Cc;                              // values really stored per channel
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (v < nvr) red[((size_t)tr * C + quad * 4 + i) * nvr + v] = acc[i][v];
+    __syncthreads();
+    float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nvr;
+    for (int i = threadIdx.x; i < C * nvr; i += 256) {
+        float s = 0.0f;
+        for (int t = 0; t < n_tr; ++t) s += red[(size_t)t * C * nvr + i];
+        pt[i] = s;
+    }
+}
+
+// grid B: reduce the row-CTA partials of one sample, emit dfilm and the group means needed by the apply pass
+__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ partial, int n_rc, int C, int nvr, int L,
+                                                              const float* __restrict__ gn_w, float* __restrict__ redb,
+                                                              float* __restrict__ dfilm, long dfilm_b_stride, int film_off,
+                                                              float* __restrict__ gstat) {
+    extern __shared__ float sv[];                        // [C][nvr]
+    const int b = blockIdx.x;
+    const float* pb = partial + (size_t)b * n_rc * C * nvr;
+    for (int i = threadIdx.x; i < C * nvr; i += 256) {
+        float s = 0.0f;
+        for (int r = 0; r < n_rc; ++r) s += pb[(size_t)r * C * nvr + i];
+        sv[i] = s;
+        redb[(size_t)b * C * nvr + i] = s;
+    }
+    __syncthreads();
+    float* df = dfilm + (size_t)b * dfilm_b_stride + film_off;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        df[c] = sv[c * nvr + 1];                          // d gamma = sum do*h
+        df[C + c] = sv[c * nvr + 0];                      // d beta  = sum do
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = C / 8;
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int c = warp * cg + lane; c < (warp + 1) * cg; c += 32) {
+        s1 = fmaf(gn_w[c], sv[c * nvr + 2], s1);
+        s2 = fmaf(gn_w[c], sv[c * nvr + 3], s2);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        const float n = (float)cg * (float)L;
+        gstat[((size_t)b * 8 + warp) * 2 + 0] = s1 / n;
+        gstat[((size_t)b * 8 + warp) * 2 + 1] = s2 / n;
+    }
+}
+
+// grid ceil(C/32): parameter gradients that sum over the batch
+__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restrict__ redb, int B, int C, int nvr,
+                                                           const float* __restrict__ film, long film_b_stride, int film_off,
+                                                           float* __restrict__ d_gn_w, float* __restrict__ d_gn_b,
+                                                           float* __restrict__ d_wc, float* __restrict__ d_bc) {
+    __shared__ float red[8][32][3 + BW_MAX_CC];
+    const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int Cc = nvr - 4;
+    float a[3 + BW_MAX_CC];
+#pragma unroll
+    for (int v = 0; v < 3 + BW_MAX_CC; ++v) a[v] = 0.0f;
+    if (c < C) {
+        for (int b = bl; b < B; b += 8) {
+            const float* p = redb + ((size_t)b * C + c) * nvr;
+            const float G = 1.0f + film[(size_t)b * film_b_stride + film_off + c];
+            a[0] += p[3];                                 // d gn_w
+            a[1] += p[2];                                 // d gn_b
+            a[2] = fmaf(G, p[0], a[2]);                   // d bc
+#pragma unroll
+            for (int j = 0; j < BW_MAX_CC; ++j)
+                if (j < Cc) a[3 + j] = fmaf(G, p[4 + j], a[3 + j]);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 3 + BW_MAX_CC; ++v) red[bl][cl][v] = a[v];
+    __syncthreads();
+    if (bl == 0 && c < C) {
+        float s[3 + BW_MAX_CC];
+#pragma unroll
+        for (int v = 0; v < 3 + BW_MAX_CC; ++v) {
+            s[v] = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) s[v] += red[t][cl][v];
+        }
+        d_gn_w[c] += s[0];
+        d_gn_b[c] += s[1];
+        if (Cc > 0) {
+            d_bc[c] += s[2];
+            for (int j = 0; j < Cc; ++j) d_wc[c * Cc + j] += s[3 + j];
+        }
+    }
+}
+
+template <typename T, bool FAST, int CC>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, const float* __restrict__ gstat, T* __restrict__ d_raw,
+                                                           float* __restrict__ partial_bias) {
+    constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
+    constexpr int NCA = NC > 0 ? NC : 1;
+    extern __shared__ float red[];                      // [n_tr][C]
+    const int Cc = CC >= 0 ? CC : a.Cc;
+    const int b = blockIdx.y, C = a.C, L = a.L;
+    const int n_quad = C / 4, n_tr = 256 / n_quad;
+    const int quad = threadIdx.x % n_quad, tr = threadIdx.x / n_quad;
+    QuadCoef<NCA> q;
+    load_quad<NC, NCA>(a, b, quad, Cc, q);
+    const int g = (quad * 4) / (C / 8);
+    const float m1 = gstat[((size_t)b * 8 + g) * 2 + 0], m2 = gstat[((size_t)b * 8 + g) * 2 + 1];
+    float sb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const T* raw = (const T*)a.raw + (size_t)b * L * C + quad * 4;
+    const T* doa = a.do_a ? (const T*)a.do_a + (size_t)b * L * C + quad * 4 : nullptr;
+    const int Lp = L / 2;
+    const T* dop = a.do_pool ? (const T*)a.do_pool + (size_t)b * Lp * C + quad * 4 : nullptr;
+    T* out = d_raw + (size_t)b * L * C + quad * 4;
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r_end = min(r0 + a.rows_per_cta, L);
+    for (int r = r0 + tr; r < r_end; r += n_tr) {
+        float x[4], d[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dz[4];
+        ld4f(raw + (size_t)r * C, x);
+        if (doa) ld4f(doa + (size_t)r * C, d);
+        if (dop && (r >> 1) < Lp) {
+            float p[4];
+            ld4f(dop + (size_t)(r >> 1) * C, p);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = fmaf(0.5f, p[i], d[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float z = fmaf(x[i], q.A[i], q.Bn[i]);
+            const float s = sigmoid_f<FAST>(z);
+            const float dn = d[i] * q.G[i] * (s * fmaf(z, 1.0f - s, 1.0f));
+            const float xh = (x[i] - q.mean) * q.rstd;
+            const float v = q.rstd * (fmaf(dn, q.gw[i], -m1) - xh * m2);
+            dz[i] = round_to(v, d_raw);
+            sb[i] += dz[i];
+        }
+        st4f(out + (size_t)r * C, dz);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[(size_t)tr * C + quad * 4 + i] = sb[i];
+    __syncthreads();
+    float* pt = partial_bias + ((size_t)b * gridDim.x + blockIdx.x) * C;
+    for (int i = threadIdx.x; i < C; i += 256) {
+        float s = 0.0f;
+        for (int t = 0; t < n_tr; ++t) s += red[(size_t)t * C + i];
+        pt[i] = s;
+    }
+}
+
+static int gn_rows_per_cta(int L, int C) {
+    const int n_tr = 256 / (C / 4);
+    int rows = 16 * n_tr;
+    if (rows > L) rows = L;
+    return rows < 1 ? 1 : rows;
+}
+
+extern "C" long gw_gn_bwd_scratch_elems(int B, int L, int C, int Cc) {
+    const int rows = gn_rows_per_cta(L, C), n_rc = gw_cdiv(L, rows), nvr = 4 + Cc;
+    // [partials | per-sample reduced | group means]
+    return (long)B * n_rc * C * nvr + (long)B * C * nvr + (long)B * 16;
+}
+
+template <typename T, bool FAST>
+static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+                      float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, cudaStream_t st) {
+    const int C = a.C, L = a.L, Cc = a.Cc, nvr = 4 + Cc;
+    const int n_rc = gw_cdiv(L, a.rows_per_cta), n_tr = 256 / (C / 4);
+    float* partial = scratch;
+    float* redb = partial + (size_t)B * n_rc * C * nvr;
+    float* gstat = redb + (size_t)B * C * nvr;
+    dim3 grid(n_rc, B);
+    const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
+#define GNB_GO(CCV)                                                                                                       \
+    do {                                                                                                                  \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_kernel<T, FAST, CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
+        gn_bwd_stats_kernel<T, FAST, CCV><<<grid, 256, sm1, st>>>(a, partial);                                            \
+    } while (0)
+    if (Cc == 0) GNB_GO(0);
+    else if (Cc == 1) GNB_GO(1);
+    else if (Cc == 5) GNB_GO(5);
+    else GNB_GO(-1);
+#undef GNB_GO
+    GW_LAUNCH_CHECK();
+    gn_bwd_finalize_kernel<<<B, 256, (size_t)C * nvr * sizeof(float), st>>>(partial, n_rc, C, nvr, L, a.gn_w, redb, dfilm,
+                                                                            dfilm_b_stride, a.film_off, gstat);
+    GW_LAUNCH_CHECK();
+    gn_bwd_param_kernel<<<gw_cdiv(C, 32), 256, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+                                                       d_wc, d_bc);
+    GW_LAUNCH_CHECK();
+    // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
+#define GNA_GO(CCV) gn_bwd_apply_kernel<T, FAST, CCV><<<grid, 256, sm2, st>>>(a, gstat, (T*)d_raw, partial)
+    if (Cc == 0) GNA_GO(0);
+    else if (Cc == 1) GNA_GO(1);
+    else if (Cc == 5) GNA_GO(5);
+    else GNA_GO(-1);
+#undef GNA_GO
+    GW_LAUNCH_CHECK();
+    return reduce_rows(partial, B * n_rc, C, C, 1.0f, d_conv_bias, 1, st);
+}
+
+// d_raw [B, L, C] (dtype); parameter gradients are ACCUMULATED into d_gn_w, d_gn_b [C], d_wc [C, Cc], d_bc [C],
+// d_conv_bias [C]; dfilm row b gets (d gamma | d beta) of this layer at film_off (overwritten).
+extern "C" int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
+                         const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+                         long film_b_stride, const void* do_a, const void* do_pool, int dtype, float* scratch, float* dfilm,
+                         long dfilm_b_stride, void* d_raw, float* d_gn_w, float* d_gn_b, float* d_wc, float* d_bc,
+                         float* d_conv_bias, void* stream) {
+    GW_REQUIRE(C % 64 == 0 && C <= 1024 && 256 % (C / 4) == 0, "gw_gn_bwd: C=%d", C);
+    GW_REQUIRE(Cc >= 0 && Cc <= BW_MAX_CC, "gw_gn_bwd: Cc=%d", Cc);
+    GW_REQUIRE((cond != nullptr) == (Cc > 0), "gw_gn_bwd: cond/Cc mismatch");
+    GW_REQUIRE(do_a != nullptr || do_pool != nullptr, "gw_gn_bwd: no incoming gradient");
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_gn_bwd: dtype %d", dtype);
+    GnBwdArgs a;
+    a.raw = raw; a.stats = stats; a.gn_w = gn_w; a.gn_b = gn_b; a.cond = cond; a.wc = wc; a.bc = bc; a.film = film;
+    a.film_b_stride = film_b_stride; a.film_off = film_off; a.do_a = do_a; a.do_pool = do_pool; a.L = L; a.C = C; a.Cc = Cc;
+    a.rows_per_cta = gn_rows_per_cta(L, C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32)
+        return gn_bwd_run<float, false>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, st);
+    return gn_bwd_run<bf16, true>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact-mode conv backward helpers
+// ------------------------------------------------------------------------------------------------
+// dgrad of Conv1d(k=3, pad=1) is the same conv with w'[ci][co][k] = w[co][ci][2-k]  (run through gw_conv3_simt)
+__global__ void __launch_bounds__(256) weight_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ wt) {
+    const long n = (long)Cout * Cin * 3;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % 3);
+        const long r = i / 3;
+        const int co = (int)(r % Cout), ci = (int)(r / Cout);
+        wt[i] = w[((size_t)co * Cin + ci) * 3 + (2 - k)];
+    }
+}
+extern "C" int gw_weight_dgrad(const float* w, int Cout, int Cin, float* wt, void* stream) {
+    GW_REQUIRE(Cout > 0 && Cin > 0, "gw_weight_dgrad: sizes");
+    const long n = (long)Cout * Cin * 3;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    weight_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, wt);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// gradient of cat[nearest-upsample x2 (h), skip] (models.py:217-221): d_h[m] = d_cat[2m, :C0] + d_cat[2m+1, :C0],
+// d_skip = d_cat[:, C0:].  d_cat [B, L, C0+C1]; d_h [B, L0, C0]; d_skip [B, L, C1].
+template <typename T>
+__global__ void __launch_bounds__(256) split_cat_grad_kernel(const T* __restrict__ d_cat, int L, int C0, int L0, int C1,
+                                                             T* __restrict__ d_h, T* __restrict__ d_skip) {
+    const int b = blockIdx.y;
+    const int Ct = C0 + C1;
+    const int q0 = C0 / 4, q1 = C1 / 4;
+    const long n_h = (long)L0 * q0, n_s = (long)L * q1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_h + n_s; i += (long)gridDim.x * blockDim.x) {
+        if (i < n_h) {
+            const int m = (int)(i / q0), q = (int)(i % q0);
+            float a[4] = {0.0f, 0.0f, 0.0f, 0.0f}, c[4];
+            if (2 * m < L) ld4f(d_cat + ((size_t)b * L + 2 * m) * Ct + q * 4, a);
+            if (2 * m + 1 < L) {
+                ld4f(d_cat + ((size_t)b * L + 2 * m + 1) * Ct + q * 4, c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a[j] += c[j];
+            }
+            st4f(d_h + ((size_t)b * L0 + m) * C0 + q * 4, a);
+        } else {
+            const long k = i - n_h;
+            const int l = (int)(k / q1), q = (int)(k % q1);
+            float a[4];
+            ld4f(d_cat + ((size_t)b * L + l) * Ct + C0 + q * 4, a);
+            st4f(d_skip + ((size_t)b * L + l) * C1 + q * 4, a);
+        }
+    }
+}
+extern "C" int gw_split_cat_grad(const void* d_cat, int B, int L, int C0, int L0, int C1, void* d_h, void* d_skip, int dtype,
+                                 void* stream) {
+    GW_REQUIRE(C0 % 4 == 0 && C1 % 4 == 0 && C0 > 0 && C1 > 0, "gw_split_cat_grad: channels");
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_split_cat_grad: dtype %d", dtype);
+    const long n = (long)L0 * (C0 / 4) + (long)L * (C1 / 4);
+    int gx = (int)((n + 255) / 256);
+    if (gx > 1024) gx = 1024;
+    dim3 grid(gx, B);
+    if (dtype == GW_F32)
+        split_cat_grad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)d_cat, L, C0, L0, C1, (float*)d_h, (float*)d_skip);
+    else
+        split_cat_grad_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)d_cat, L, C0, L0, C1, (bf16*)d_h, (bf16*)d_skip);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// wgrad of Conv1d(k=3, pad=1) over the virtual concat [nearest-upsample(src0) | src1], CUDA-core fp32:
+//   dW[co][ci][k] = sum_{b,l} d_raw[b,l,co] * in[b, l+k-1, ci]
+// CTA = 64 couts x 64 cins x 3 taps over a strided share of (sample, 32-position chunk) work items; the split-K
+// partials [n_split][Cout][Cin][3] land in scratch and are summed in fixed order into dW.
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad3_simt_kernel(const T* __restrict__ src0, int C0, int L0, int up0,
+                                                          const T* __restrict__ src1, int C1, const T* __restrict__ d_raw, int B,
+                                                          int L, int Cout, float* __restrict__ partial) {
+    constexpr int KP = 32;
+    __shared__ __align__(16) float dy[KP][64];
+    __shared__ __align__(16) float xs[KP + 2][64];
+    const int Cin = C0 + C1;
+    const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, split = blockIdx.z, n_split = gridDim.z;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[i][j][k] = 0.0f;
+    const int n_chunk = (L + KP - 1) / KP;
+    const long total = (long)B * n_chunk;
+    const bool from0 = ci0 < C0;
+    for (long w = split; w < total; w += n_split) {
+        const int b = (int)(w / n_chunk), l0 = (int)(w % n_chunk) * KP;
+        {
+            const int row = threadIdx.x >> 3, oct = threadIdx.x & 7;
+            const int l = l0 + row;
+            float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (l < L) ld8(d_raw + ((size_t)b * L + l) * Cout + co0 + oct * 8, v);
+            *reinterpret_cast<float4*>(&dy[row][oct * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(&dy[row][oct * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        for (int i = threadIdx.x; i < (KP + 2) * 8; i += 256) {
+            const int row = i >> 3, oct = i & 7;
+            const int l = l0 + row - 1;
+            float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            if (l >= 0 && l < L) {
+                if (from0) {
+                    const int ls = up0 ? (l >> 1) : l;
+                    if (ls < L0) ld8(src0 + ((size_t)b * L0 + ls) * C0 + ci0 + oct * 8, v);
+                } else {
+                    ld8(src1 + ((size_t)b * L + l) * C1 + (ci0 - C0) + oct * 8, v);
+                }
+            }
+            *reinterpret_cast<float4*>(&xs[row][oct * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(&xs[row][oct * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = 0; p < KP; ++p) {
+            const float4 d4 = *reinterpret_cast<const float4*>(&dy[p][ty * 4]);
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 x4 = *reinterpret_cast<const float4*>(&xs[p + k][tx * 4]);
+                const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j][k] = fmaf(d[i], x[j], acc[i][j][k]);
+            }
+        }
+        __syncthreads();
+    }
+    float* pt = partial + (size_t)split * Cout * Cin * 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                pt[((size_t)(co0 + ty * 4 + i) * Cin + ci0 + tx * 4 + j) * 3 + k] = acc[i][j][k];
+}
+
+extern "C" int gw_wgrad3_simt(const void* src0, int C0, int L0, int up0, const void* src1, int C1, const void* d_raw, int B,
+                              int L, int Cout, int dtype, float* scratch, long scratch_elems, float* dW, void* stream) {
+    GW_REQUIRE(C0 % 64 == 0 && C1 % 64 == 0 && C0 > 0 && Cout % 64 == 0, "gw_wgrad3_simt: channels C0=%d C1=%d Cout=%d", C0, C1, Cout);
+    GW_REQUIRE((src1 != nullptr) == (C1 > 0), "gw_wgrad3_simt: src1/C1 mismatch");
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_wgrad3_simt: dtype %d", dtype);
+    const int Cin = C0 + C1;
+    const long per = (long)Cout * Cin * 3;
+    const long total = (long)B * gw_cdiv(L, 32);
+    const int tiles = (Cin / 64) * (Cout / 64);
+    long n_split = (148L * 4 + tiles - 1) / tiles;
+    if (n_split > total) n_split = total;
+    if (n_split > scratch_elems / per) n_split = scratch_elems / per;
+    if (n_split > 65535) n_split = 65535;
+    GW_REQUIRE(n_split >= 1, "gw_wgrad3_simt: scratch too small (%ld < %ld)", scratch_elems, per);
+    dim3 grid(Cin / 64, Cout / 64, (unsigned)n_split);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32)
+        wgrad3_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)src0, C0, L0, up0, (const float*)src1, C1, (const float*)d_raw, B, L, Cout, scratch);
+    else
+        wgrad3_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src0, C0, L0, up0, (const bf16*)src1, C1, (const bf16*)d_raw, B, L, Cout, scratch);
+    GW_LAUNCH_CHECK();
+    return reduce_rows(scratch, (int)n_split, per, per, 1.0f, dW, 1, st);
+}
+
+// wgrad of the first conv (models.py:204): dW[co][ci][k] = sum d_raw[b,l,co] * x[b,ci,l+k-1], x fp32 [B, Cx, L]
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_in_kernel(const float* __restrict__ x, int Cx, int L, const T* __restrict__ d_raw,
+                                                       int C, float* __restrict__ partial, int rows_per_cta) {
+    extern __shared__ float sm[];
+    float* xs = sm;                               // [Cx][rows + 2]
+    const int n_tr = 256 / C;                     // C = 64 -> 4 thread rows
+    const int pitch = rows_per_cta + 2;
+    float* red = xs + Cx * pitch;                 // [n_tr][C][Cx*3]
+    const int b = blockIdx.y, r0 = blockIdx.x * rows_per_cta;
+    for (int i = threadIdx.x; i < Cx * pitch; i += 256) {
+        const int c = i / pitch, p = i % pitch;
+        const int l = r0 + p - 1;
+        xs[i] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+    }
+    __syncthreads();
+    const int co = threadIdx.x % C, tr = threadIdx.x / C;
+    float acc[16 * 3];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) acc[i] = 0.0f;
+    const int r_end = min(rows_per_cta, L - r0);
+    for (int r = tr; r < r_end; r += n_tr) {
+        const float d = to_f(d_raw[((size_t)b * L + r0 + r) * C + co]);
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) {
+            if (ci < Cx) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[ci * 3 + k] = fmaf(d, xs[ci * pitch + r + k], acc[ci * 3 + k]);
+            }
+        }
+    }
+    const int nv = Cx * 3;
+#pragma unroll
+    for (int i = 0; i < 48; ++i)
+        if (i < nv) red[((size_t)tr * C + co) * nv + i] = acc[i];
+    __syncthreads();
+    float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nv;
+    for (int i = threadIdx.x; i < C * nv; i += 256) {
+        float s = 0.0f;
+        for (int t = 0; t < n_tr; ++t) s += red[(size_t)t * C * nv + i];
+        pt[i] = s;
+    }
+}
+
+extern "C" int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_raw, int C, int dtype, float* scratch,
+                           long scratch_elems, float* dW, void* stream) {
+    GW_REQUIRE(C > 0 && 256 % C == 0 && C >= 32, "gw_wgrad_in: C=%d must divide 256", C);
+    GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_wgrad_in: Cx=%d", Cx);
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_wgrad_in: dtype %d", dtype);
+    int rows = 1024;
+    if (rows > L) rows = L;
+    const int n_rc = gw_cdiv(L, rows), nv = Cx * 3;
+    GW_REQUIRE((long)B * n_rc * C * nv <= scratch_elems, "gw_wgrad_in: scratch too small");
+    const int n_tr = 256 / C;
+    const size_t smem = ((size_t)Cx * (rows + 2) + (size_t)n_tr * C * nv) * sizeof(float);
+    dim3 grid(n_rc, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32) {
+        GW_CUDA(cudaFuncSetAttribute(wgrad_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_in_kernel<float><<<grid, 256, smem, st>>>(x, Cx, L, (const float*)d_raw, C, scratch, rows);
+    } else {
+        GW_CUDA(cudaFuncSetAttribute(wgrad_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wgrad_in_kernel<bf16><<<grid, 256, smem, st>>>(x, Cx, L, (const bf16*)d_raw, C, scratch, rows);
+    }
+    GW_LAUNCH_CHECK();
+    return reduce_rows(scratch, B * n_rc, (long)C * nv, (long)C * nv, 1.0f, dW, 1, st);
+}

@@ -31,7 +31,8 @@ extern "C" int gw_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t, int time_dim, float inv_max_time_den,
                                                    float freq_coef, const float* __restrict__ w1,
                                                    const float* __restrict__ b1, const float* __restrict__ w2,
-                                                   const float* __restrict__ b2, int base, int F, float* __restrict__ out) {
+                                                   const float* __restrict__ b2, int base, int F, float* __restrict__ out,
+                                                   float* __restrict__ aux) {
     extern __shared__ float sm[];
     float* emb = sm;              // [time_dim]
     float* act = sm + time_dim;   // [base]
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t
             v = i < half ? sinf(a) : cosf(a);
         }
         emb[i] = v;
+        if (aux != nullptr) aux[(size_t)n * (time_dim + 3 * base) + i] = v;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < base; j += blockDim.x) {
@@ -56,6 +58,12 @@ __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t
         acc += b1[j];
         const float ctx = silu_f<false>(acc);   // time_mlp's SiLU
         act[j] = silu_f<false>(ctx);            // tproj's leading SiLU
+        if (aux != nullptr) {                   // saved for gw_film_bwd: [emb | pre | ctx | act]
+            float* ax = aux + (size_t)n * (time_dim + 3 * base) + time_dim;
+            ax[j] = acc;
+            ax[base + j] = ctx;
+            ax[2 * base + j] = act[j];
+        }
     }
     __syncthreads();
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
@@ -67,13 +75,13 @@ __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t
 }
 
 extern "C" int gw_film_vectors(const int64_t* t, int n, int time_dim, float max_time, const float* w1, const float* b1,
-                               const float* w2, const float* b2, int base, int F, float* out, void* stream) {
+                               const float* w2, const float* b2, int base, int F, float* out, float* aux, void* stream) {
     GW_REQUIRE(n > 0 && time_dim > 0 && base > 0 && F > 0, "gw_film_vectors: bad sizes");
     const int half = time_dim / 2;
     const float den = max_time > 1.0f ? max_time : 1.0f;                       // models.py:21
     const float coef = (float)(-(log(10000.0) / (double)(half - 1 > 1 ? half - 1 : 1)));   // models.py:25
     size_t smem = (size_t)(time_dim + base) * sizeof(float);
-    film_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(t, time_dim, den, coef, w1, b1, w2, b2, base, F, out);
+    film_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(t, time_dim, den, coef, w1, b1, w2, b2, base, F, out, aux);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -333,8 +341,11 @@ __global__ void __launch_bounds__(256) conv3_simt_kernel(const T* __restrict__ s
         }
         __syncthreads();
     }
-    const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
-    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    float bb[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (bias != nullptr) {
+        const float4 bv = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
+        bb[0] = bv.x; bb[1] = bv.y; bb[2] = bv.z; bb[3] = bv.w;
+    }
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -358,6 +369,7 @@ __global__ void __launch_bounds__(256) conv3_simt_kernel(const T* __restrict__ s
             }
         }
     }
+    if (part == nullptr) return;                      // dgrad use: no GroupNorm statistics wanted
     const int cg = Cout / 8;
     const int n_groups = TN / cg > 0 ? TN / cg : 1;   // groups covered by this cout tile (cg <= 64)
     tile_stats_reduce(s1, s2, (tx * 4) / cg, n_groups, red, part + ((size_t)b * n_part + tile) * 16, n0 / cg);

@@ -1,0 +1,270 @@
+// Training-step kernels around the network: input packing (q_sample + CFG dropout + clamp, train.py:349-407),
+// self-conditioning estimate (train.py:40-51), time-MLP / tproj backward (models.py:105-109, 137-142),
+// and the fused clip_grad_norm_ + AdamW + EMA update (train.py:445-455, 73-81) over flat parameter buffers.
+#include "common.cuh"
+#include "../../include/gwb200.h"
+
+// ------------------------------------------------------------------------------------------------
+// per-sample draws: t ~ U{t_min..T-1} (train.py:376) and the CFG-dropout coin (train.py:386), Philox keyed on the
+// GLOBAL sample index so a W-rank run draws what the 1-rank run draws.
+// ------------------------------------------------------------------------------------------------
+__global__ void train_draws_kernel(unsigned long long seed, const int* __restrict__ step_ptr, long sample0, int B, int t_min,
+                                   int T, float p_uncond, int64_t* __restrict__ t_out, float* __restrict__ drop_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t step = (uint32_t)(step_ptr ? *step_ptr : 0);
+    uint32_t r[4];
+    Philox::gen(seed, 0xfffffff0u, step, (uint32_t)(sample0 + b), 0x3c6ef372u, r);
+    const int span = T - t_min;
+    t_out[b] = (int64_t)t_min + (int64_t)(((unsigned long long)r[0] * (unsigned long long)span) >> 32);
+    const float u = ((float)(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    drop_out[b] = u < p_uncond ? 1.0f : 0.0f;
+}
+extern "C" int gw_train_draws(unsigned long long seed, const int* step_ptr, long sample0, int B, int t_min, int T,
+                              float p_uncond, int64_t* t_out, float* drop_out, void* stream) {
+    GW_REQUIRE(B > 0 && T > t_min && t_min >= 0, "gw_train_draws: B=%d t_min=%d T=%d", B, t_min, T);
+    train_draws_kernel<<<gw_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(seed, step_ptr, sample0, B, t_min, T, p_uncond, t_out, drop_out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// network-input packing: net[b] = [ clamp(q_sample(clamp(clean), t, eps)) | clamp(y)*(1-drop), meta... | 0 ]
+// (train.py:350-352, 379-398, 404-407).  cond [B, Cc, L] (channel 0 = y); eps read (philox == 0) or generated.
+// drop_all != 0 zeroes every conditioning channel for dropped samples (dropout_y_only = False or no metadata);
+// clamp_y != 0 clamps the y channel (the reference only does so on the y-only dropout branch, train.py:387).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) train_pack_kernel(const float* __restrict__ clean, const float* __restrict__ cond, int Cc,
+                                                         const int64_t* __restrict__ t, const float* __restrict__ drop,
+                                                         const float* __restrict__ sab, const float* __restrict__ s1mab,
+                                                         float* __restrict__ eps, int philox, unsigned long long seed,
+                                                         long sample0, const int* __restrict__ step_ptr, float clampv,
+                                                         int clamp_y, int drop_all, float* __restrict__ net, int Cx, int L) {
+    const int b = blockIdx.y;
+    const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (l4 >= L) return;
+    const long tt = t[b];
+    const float a = sab[tt], m = s1mab[tt];
+    const float keep = drop ? 1.0f - drop[b] : 1.0f;
+    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (philox) Philox::normal4(seed, (uint32_t)(sample0 + b), (uint32_t)(step_ptr ? *step_ptr : 0), (uint32_t)(l4 >> 2), z);
+    float* nb = net + (size_t)b * Cx * L;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int l = l4 + i;
+        if (l >= L) break;
+        float e;
+        if (philox) {
+            e = z[i];
+            eps[(size_t)b * L + l] = e;
+        } else {
+            e = eps[(size_t)b * L + l];
+        }
+        float x0 = clean[(size_t)b * L + l];
+        if (clampv > 0.0f) x0 = fminf(fmaxf(x0, -clampv), clampv);
+        float v = a * x0 + m * e;
+        if (clampv > 0.0f) v = fminf(fmaxf(v, -clampv), clampv);
+        nb[l] = v;
+        for (int c = 0; c < Cc; ++c) {
+            float cv = cond[((size_t)b * Cc + c) * L + l];
+            if (c == 0) {
+                if (clampv > 0.0f && clamp_y) cv = fminf(fmaxf(cv, -clampv), clampv);   // train.py:387 uses the clamped y_norm, :398 cond_stack
+                cv *= keep;
+            } else if (drop_all) {
+                cv *= keep;
+            }
+            nb[(size_t)(1 + c) * L + l] = cv;
+        }
+        for (int c = 1 + Cc; c < Cx; ++c) nb[(size_t)c * L + l] = 0.0f;
+    }
+}
+extern "C" int gw_train_pack(const float* clean, const float* cond, int Cc, const int64_t* t, const float* drop,
+                             const float* sqrt_ab, const float* sqrt_1mab, float* eps, int philox, unsigned long long seed,
+                             long sample0, const int* step_ptr, float clampv, int clamp_y, int drop_all, float* net, int B, int Cx,
+                             int L, void* stream) {
+    GW_REQUIRE(B > 0 && L > 0 && Cx >= 1 + Cc && Cc >= 0, "gw_train_pack: sizes B=%d L=%d Cx=%d Cc=%d", B, L, Cx, Cc);
+    dim3 grid(gw_cdiv(gw_cdiv(L, 4), 256), B);
+    train_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(clean, cond, Cc, t, drop, sqrt_ab, sqrt_1mab, eps, philox, seed, sample0,
+                                                              step_ptr, clampv, clamp_y, drop_all, net, Cx, L);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// self-conditioning estimate x0_hat = (x_t - sqrt(1-ab_t) eps_hat) / sqrt(ab_t) written to the last input channel
+// (train.py:40-51, 404-407).  ab = alpha_bar table (NOT clamped, as in train.py:49).
+__global__ void __launch_bounds__(256) selfcond_kernel(float* __restrict__ net, const float* __restrict__ eps_hat,
+                                                       const int64_t* __restrict__ t, const float* __restrict__ ab, int Cx, int L) {
+    const int b = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const float a = ab[t[b]];
+    float* nb = net + (size_t)b * Cx * L;
+    nb[(size_t)(Cx - 1) * L + l] = __fdiv_rn(__fsub_rn(nb[l], __fmul_rn(sqrtf(1.0f - a), eps_hat[(size_t)b * L + l])), sqrtf(a));
+}
+extern "C" int gw_selfcond_x0(float* net, const float* eps_hat, const int64_t* t, const float* alpha_bar, int B, int Cx, int L,
+                              void* stream) {
+    GW_REQUIRE(B > 0 && L > 0 && Cx >= 2, "gw_selfcond_x0: sizes");
+    selfcond_kernel<<<dim3(gw_cdiv(L, 256), B), 256, 0, (cudaStream_t)stream>>>(net, eps_hat, t, alpha_bar, Cx, L);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// time-MLP / tproj backward.  aux rows (written by gw_film_vectors): [emb(time_dim) | pre(base) | ctx(base) | act(base)]
+//   film = W2 act + b2, act = silu(ctx), ctx = silu(pre), pre = W1 emb + b1
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dsilu(float x) {
+    const float s = 1.0f / (1.0f + expf(-x));
+    return s * (1.0f + x * (1.0f - s));
+}
+// grid F/4, block (64, 4): dW2[f, j] += sum_b dfilm[b,f] act[b,j]; db2[f] += sum_b dfilm[b,f]
+__global__ void film_bwd_w2_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux, int B, int td, int base, int F,
+                                   float* __restrict__ dW2, float* __restrict__ db2) {
+    const int f = blockIdx.x * blockDim.y + threadIdx.y;
+    if (f >= F) return;
+    const int na = td + 3 * base;
+    float bsum = 0.0f;
+    for (int j = threadIdx.x; j < base; j += blockDim.x) {
+        float acc = 0.0f;
+        bsum = 0.0f;
+        for (int b = 0; b < B; ++b) {
+            const float d = dfilm[(size_t)b * F + f];
+            acc = fmaf(d, aux[(size_t)b * na + td + 2 * base + j], acc);
+            bsum += d;
+        }
+        dW2[(size_t)f * base + j] += acc;
+    }
+    if (threadIdx.x == 0) db2[f] += bsum;
+}
+// grid B, block 256: dpre[b, j] = (sum_f dfilm[b,f] W2[f,j]) * silu'(ctx) * silu'(pre)
+__global__ void __launch_bounds__(256) film_bwd_act_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux,
+                                                           const float* __restrict__ w2, int td, int base, int F,
+                                                           float* __restrict__ dpre) {
+    extern __shared__ float sm[];           // [4][base]
+    const int b = blockIdx.x;
+    const int j = threadIdx.x % base, part = threadIdx.x / base, n_part = blockDim.x / base;
+    float acc = 0.0f;
+    for (int f = part; f < F; f += n_part) acc = fmaf(dfilm[(size_t)b * F + f], w2[(size_t)f * base + j], acc);
+    sm[part * base + j] = acc;
+    __syncthreads();
+    if (part == 0) {
+        float s = 0.0f;
+        for (int p = 0; p < n_part; ++p) s += sm[p * base + j];
+        const float* ax = aux + (size_t)b * (td + 3 * base) + td;
+        dpre[(size_t)b * base + j] = s * dsilu(ax[base + j]) * dsilu(ax[j]);
+    }
+}
+// grid base, block td: dW1[j, i] += sum_b dpre[b,j] emb[b,i]; db1[j] += sum_b dpre[b,j]
+__global__ void film_bwd_w1_kernel(const float* __restrict__ dpre, const float* __restrict__ aux, int B, int td, int base,
+                                   float* __restrict__ dW1, float* __restrict__ db1) {
+    const int j = blockIdx.x, i = threadIdx.x;
+    const int na = td + 3 * base;
+    float acc = 0.0f, bs = 0.0f;
+    for (int b = 0; b < B; ++b) {
+        const float d = dpre[(size_t)b * base + j];
+        acc = fmaf(d, aux[(size_t)b * na + i], acc);
+        bs += d;
+    }
+    dW1[(size_t)j * td + i] += acc;
+    if (i == 0) db1[j] += bs;
+}
+extern "C" int gw_film_bwd(const float* dfilm, const float* aux, const float* w2, int B, int time_dim, int base, int F,
+                           float* scratch, float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+    GW_REQUIRE(B > 0 && base > 0 && base <= 256 && 256 % base == 0 && time_dim > 0 && time_dim <= 1024, "gw_film_bwd: sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    film_bwd_w2_kernel<<<gw_cdiv(F, 4), dim3(64, 4), 0, st>>>(dfilm, aux, B, time_dim, base, F, dW2, db2);
+    GW_LAUNCH_CHECK();
+    film_bwd_act_kernel<<<B, 256, (size_t)256 * sizeof(float), st>>>(dfilm, aux, w2, time_dim, base, F, scratch);
+    GW_LAUNCH_CHECK();
+    film_bwd_w1_kernel<<<base, time_dim, 0, st>>>(scratch, aux, B, time_dim, base, dW1, db1);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// clip_grad_norm_ + AdamW + EMA over flat buffers
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, double* __restrict__ partial) {
+    __shared__ double red[8];
+    double a = 0.0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double v = (double)g[i];
+        a += v * v;
+    }
+    a = warp_sum_d(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        partial[blockIdx.x] = s;
+    }
+}
+
+// hyper (device, fp32[8]): 0 lr, 1 bias_correction1, 2 sqrt(bias_correction2), 3 ema_decay (<0: no EMA), 4 weight_decay,
+//                          5 max_norm (<=0: no clipping), 6 grad_scale (1/world applied before the norm), 7 unused
+// info (device, fp32[4]) out: 0 total grad norm (after grad_scale), 1 clip coefficient, 2 1 if the step was applied
+__global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, float* __restrict__ ema, long n,
+                                                        const double* __restrict__ partial, int n_partial,
+                                                        const float* __restrict__ hyper, const float* __restrict__ loss,
+                                                        float beta1, float beta2, float eps, float* __restrict__ info) {
+    __shared__ float s_coef;
+    __shared__ int s_ok;
+    if (threadIdx.x < 32) {
+        double a = 0.0;
+        for (int i = threadIdx.x; i < n_partial; i += 32) a += partial[i];
+        a = warp_sum_d(a);
+        if (threadIdx.x == 0) {
+            const float gs = hyper[6];
+            const float norm = (float)sqrt(a) * gs;
+            const float max_norm = hyper[5];
+            float coef = 1.0f;
+            if (max_norm > 0.0f) coef = fminf(max_norm / (norm + 1e-6f), 1.0f);    // torch clip_grad_norm_
+            const bool ok = isfinite(norm) && (loss == nullptr || isfinite(loss[0]));   // train.py:424-427 skips the batch
+            s_coef = coef * gs;
+            s_ok = ok ? 1 : 0;
+            if (blockIdx.x == 0) {
+                info[0] = norm;
+                info[1] = coef;
+                info[2] = ok ? 1.0f : 0.0f;
+            }
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    const float coef = s_coef;
+    const float lr = hyper[0], bc1 = hyper[1], bc2s = hyper[2], decay = hyper[3], wd = hyper[4];
+    const float step_size = lr / bc1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        float pi = p[i] * (1.0f - lr * wd);                        // torch.optim.AdamW (decoupled decay first)
+        const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);      // exp_avg.lerp_(grad, 1-beta1)
+        const float vi = v[i] * beta2 + (1.0f - beta2) * gi * gi;
+        const float denom = sqrtf(vi) / bc2s + eps;
+        pi -= step_size * (mi / denom);
+        p[i] = pi;
+        m[i] = mi;
+        v[i] = vi;
+        if (ema != nullptr && decay >= 0.0f) ema[i] = ema[i] * decay + pi * (1.0f - decay);     // train.py:78
+    }
+}
+
+#define OPT_PARTIALS 296
+extern "C" int gw_opt_scratch_doubles(void) { return OPT_PARTIALS; }
+extern "C" int gw_grad_sumsq(const float* g, long n, double* partial, void* stream) {
+    GW_REQUIRE(n > 0, "gw_grad_sumsq: n");
+    sumsq_kernel<<<OPT_PARTIALS, 256, 0, (cudaStream_t)stream>>>(g, n, partial);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+extern "C" int gw_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, long n, const double* partial,
+                            const float* hyper, const float* loss, float beta1, float beta2, float eps, float* info,
+                            void* stream) {
+    GW_REQUIRE(n > 0 && hyper != nullptr && info != nullptr && partial != nullptr, "gw_adamw_ema: arguments");
+    int grid = (int)((n + 1023) / 1024);
+    if (grid > 148 * 4) grid = 148 * 4;
+    adamw_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, partial, OPT_PARTIALS, hyper, loss, beta1, beta2, eps, info);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}

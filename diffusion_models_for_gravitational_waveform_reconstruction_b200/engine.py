@@ -84,6 +84,40 @@ class ModelSpec:
         return fl + 2.0 * (prev + 1) * self.kernel * L
 
 
+class ParamLayout:
+    """Canonical flat ordering of the 60 parameter tensors: every tproj weight first (so the concatenated FiLM
+    projection [film_dim, base_ch] is one contiguous block), then every tproj bias, then the rest in state_dict order.
+    Offsets are multiples of 4 floats so every view is 16-byte aligned; the padding stays zero in all flat buffers."""
+
+    def __init__(self, spec: ModelSpec, shapes: Dict[str, tuple]):
+        tw = [n + ".weight" for n in spec.tproj_names()]
+        tb = [n + ".bias" for n in spec.tproj_names()]
+        rest = [k for k in shapes if k not in tw and k not in tb]
+        self.names = tw + tb + rest
+        self.shapes = {k: tuple(shapes[k]) for k in self.names}
+        self.offsets: Dict[str, int] = {}
+        o = 0
+        for k in self.names:
+            self.offsets[k] = o
+            n = 1
+            for d_ in self.shapes[k]:
+                n *= d_
+            # the tproj blocks must stay gap-free (their sizes are multiples of 4 already)
+            o += (n + 3) // 4 * 4
+        self.total = o
+        self.w2 = (self.offsets[tw[0]], spec.film_dim * spec.base_ch)
+        self.b2 = (self.offsets[tb[0]], spec.film_dim)
+
+    def views(self, flat: Tensor) -> Dict[str, Tensor]:
+        out = {}
+        for k in self.names:
+            n = 1
+            for d_ in self.shapes[k]:
+                n *= d_
+            out[k] = flat[self.offsets[k]: self.offsets[k] + n].view(self.shapes[k])
+        return out
+
+
 class _Workspace:
     """Activation buffers for one (batch, length).  Channels-last [B, L_lvl, C] in the engine's storage dtype."""
 
@@ -141,17 +175,31 @@ class UNetEngine:
         self._ws: Dict[tuple, _Workspace] = {}
         self._packed: Dict[tuple, Tensor] = {}
         self.launches = 0
+        self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
+        self.layout: Optional[ParamLayout] = None
         self.refresh()
 
     # ------------------------------------------------------------------ weights
     def refresh(self) -> None:
         """Re-derive kernel-side weight layouts from the current parameter values."""
         sp, p = self.spec, self.p
-        self.film_w2 = torch.cat([p[n + ".weight"] for n in sp.tproj_names()], dim=0).contiguous()
-        self.film_b2 = torch.cat([p[n + ".bias"] for n in sp.tproj_names()], dim=0).contiguous()
-        self.wf = p["final.weight"].reshape(-1).contiguous()      # [(C+1)*3], index c*3+k
+        if self.flat is not None:
+            lo = self.layout
+            self.film_w2 = self.flat[lo.w2[0]: lo.w2[0] + lo.w2[1]]
+            self.film_b2 = self.flat[lo.b2[0]: lo.b2[0] + lo.b2[1]]
+        else:
+            self.film_w2 = torch.cat([p[n + ".weight"] for n in sp.tproj_names()], dim=0).contiguous()
+            self.film_b2 = torch.cat([p[n + ".bias"] for n in sp.tproj_names()], dim=0).contiguous()
+        self.wf = p["final.weight"].reshape(-1)                   # [(C+1)*3], index c*3+k
         for key in list(self._packed):
             self._pack_tc(key)
+
+    def bind_flat(self, flat: Tensor, layout: ParamLayout) -> None:
+        """Use `flat` (fp32, ParamLayout order) as the parameter storage: in-place optimiser updates of the flat buffer
+        are seen by every kernel without copies (only the packed bf16 conv weights need `refresh()`)."""
+        self.flat, self.layout = flat, layout
+        self.p = layout.views(flat)
+        self.refresh()
 
     def _shape(self, li: int, B: int, L: int, L0: int) -> ConvTcShape:
         sp = self.spec
@@ -199,13 +247,15 @@ class UNetEngine:
         return ws
 
     # ------------------------------------------------------------------ kernels
-    def film_vectors(self, t: Tensor) -> Tensor:
+    def film_vectors(self, t: Tensor, out: Optional[Tensor] = None, aux: Optional[Tensor] = None) -> Tensor:
+        """FiLM rows [n, film_dim] for integer timesteps t; `aux` [n, time_dim + 3*base_ch] keeps the MLP activations."""
         sp = self.spec
         t = t.to(device=self.device, dtype=torch.int64).contiguous()
-        out = torch.empty(t.numel(), sp.film_dim, device=self.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(t.numel(), sp.film_dim, device=self.device, dtype=torch.float32)
         check(self.lib.gw_film_vectors(ptr(t), t.numel(), sp.time_dim, sp.max_time, ptr(self.p["time_mlp.1.weight"]),
                                        ptr(self.p["time_mlp.1.bias"]), ptr(self.film_w2), ptr(self.film_b2),
-                                       sp.base_ch, sp.film_dim, ptr(out), _cabi.stream_ptr()), "film_vectors")
+                                       sp.base_ch, sp.film_dim, ptr(out), ptr(aux), _cabi.stream_ptr()), "film_vectors")
         self.launches += 1
         return out
 

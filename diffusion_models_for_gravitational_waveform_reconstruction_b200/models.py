@@ -164,6 +164,7 @@ class UNet1D(nn.Module):
             self.cond_mid = _Empty()
             self.cond_dec = nn.ModuleList([_Empty() for _ in chs])
         self._engines: Dict[tuple, UNetEngine] = {}
+        self._bwd: Dict[int, object] = {}
         self._versions = None
 
     # ------------------------------------------------------------------
@@ -187,8 +188,21 @@ class UNet1D(nn.Module):
             self._engines[key] = eng
         return eng
 
+    def _backward_engine(self, compute_dtype: Optional[str] = None, conv_impl: str = "auto"):
+        """BackwardEngine (train.py) for the autograd path; gradients come back in ParamLayout order."""
+        from .engine import ParamLayout
+        from .train import BackwardEngine
+        eng = self.engine(compute_dtype, conv_impl)
+        bw = self._bwd.get(id(eng))
+        if bw is None:
+            layout = ParamLayout(self.spec, {k: tuple(p.shape) for k, p in self.named_parameters()})
+            bw = BackwardEngine(eng, layout)
+            self._bwd = {id(eng): bw}
+        return bw
+
     def _apply(self, fn, *a, **kw):
         self._engines = {}
+        self._bwd = {}
         self._versions = None
         return super()._apply(fn, *a, **kw)
 

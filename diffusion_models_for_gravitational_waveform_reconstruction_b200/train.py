@@ -1,0 +1,587 @@
+"""Drop-in mirror of the reference training hot path (src/snr_denoising/train.py:40-172, 320-456) on the sm_100a kernels.
+
+Three layers, from the reference-facing one down:
+  * the reference helper names (`_predict_x0_norm`, `_element_loss`, `update_ema`, `make_warmup_cosine_scheduler`,
+    `_match_batch`, `_sample_timesteps_stratified`) and `train_diffusion(args)`;
+  * `unet_autograd_forward`: `UNet1D.forward` under autograd -- `loss.backward()` in a reference-style loop runs the
+    hand-written backward kernels and fills `param.grad`;
+  * `FusedTrainStep`: the whole per-batch body (q_sample, CFG dropout, optional self-conditioning forward, forward,
+    masked Huber/MSE loss, backward, global-norm clip, AdamW, EMA) as one kernel sequence over flat parameter / gradient /
+    optimiser buffers, CUDA-graph captured, with one NCCL all-reduce of the flat gradient bucket when world_size > 1.
+Everything numerical is in libgwb200.so; torch supplies memory, streams, graphs and `torch.distributed`.
+Dataset / HDF5 / logging parts of the reference file (train.py:17-27, 93-130, 202-217, 467-630) are outside the hot path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import StepParams, check, ptr
+from .engine import ModelSpec, ParamLayout, UNetEngine, _Workspace
+
+Tensor = torch.Tensor
+
+__all__ = ["BackwardEngine", "FusedTrainStep", "unet_autograd_forward", "_predict_x0_norm", "_element_loss", "update_ema",
+           "make_warmup_cosine_scheduler", "warmup_cosine_lambda", "_match_batch", "_sample_timesteps_stratified",
+           "train_diffusion"]
+
+
+# ======================================================================================================
+# backward engine
+# ======================================================================================================
+class _GradWorkspace:
+    """Activation-gradient buffers for one (B, L): sized once, reused by every layer (see BackwardEngine.backward)."""
+
+    def __init__(self, spec: ModelSpec, ws: _Workspace, tdtype, device, lib, simt: bool):
+        B = ws.B
+        d = spec.depth
+        lc = spec.layer_channels
+        per = [ws.lay_len[i] * lc[i] for i in range(2 * d + 1)]
+        mx = max(per)
+        e = lambda n: torch.empty(B * n, device=device, dtype=tdtype)
+        self.d_raw = e(mx)
+        self.d_h = [e(mx), e(mx)]
+        self.d_skip = [e(per[i]) for i in range(d)]
+        self.d_pool = [e(mx), e(mx)]
+        cat_max = max(ws.lay_len[d + 1 + i] * (lc[d + i] + spec.chs[d - 1 - i]) for i in range(d))
+        self.d_cat = e(cat_max) if simt else None
+        n_scr = max(lib.gw_gn_bwd_scratch_elems(B, ws.lay_len[i], lc[i], spec.cond_in_ch) for i in range(2 * d + 1))
+        n_scr = max(n_scr, B * ((ws.L + 511) // 512) * ((lc[-1] + 1) * 3 + 1), B * spec.base_ch,
+                    B * ((ws.L + 1023) // 1024) * lc[0] * spec.in_ch * 3)
+        wmax = max(lc[i] * ((lc[i - 1] + (spec.chs[2 * d - i] if i > d else 0)) * 3) for i in range(1, 2 * d + 1))
+        self.wg_elems = max(16 * wmax, 8 << 20) if simt else 0            # split-K partials of the SIMT wgrad
+        self.scratch = torch.empty(max(n_scr, self.wg_elems), device=device, dtype=torch.float32)
+        self.dfilm = torch.zeros(B, spec.film_dim, device=device, dtype=torch.float32)
+        self.aux = torch.empty(B, spec.time_dim + 3 * spec.base_ch, device=device, dtype=torch.float32)
+        self.film = torch.empty(B, spec.film_dim, device=device, dtype=torch.float32)
+
+
+class BackwardEngine:
+    """Forward-with-saved-activations and backward of UNet1D on top of `UNetEngine`.
+
+    Gradients are ACCUMULATED into `flat_grad` (fp32, `ParamLayout` order; the caller zeroes it once per step)."""
+
+    def __init__(self, eng: UNetEngine, layout: ParamLayout):
+        self.eng = eng
+        self.lib = eng.lib
+        self.layout = layout
+        self._gws: Dict[tuple, _GradWorkspace] = {}
+        self._wt: Dict[int, Tensor] = {}
+
+    def grad_workspace(self, ws: _Workspace) -> _GradWorkspace:
+        key = (ws.B, ws.L)
+        g = self._gws.get(key)
+        if g is None:
+            g = _GradWorkspace(self.eng.spec, ws, self.eng.tdtype, self.eng.device, self.lib, simt=True)
+            self._gws[key] = g
+        return g
+
+    # ------------------------------------------------------------------ forward (training mode)
+    def forward(self, net: Tensor, t: Tensor, eps_out: Optional[Tensor] = None) -> Tensor:
+        """UNet1D.forward keeping raw conv outputs, GroupNorm statistics and the time-MLP activations for `backward`."""
+        eng, sp = self.eng, self.eng.spec
+        B, Cx, L = net.shape
+        ws = eng.workspace(B, L, True)
+        g = self.grad_workspace(ws)
+        eng.film_vectors(t, out=g.film, aux=g.aux)
+        eng.cond_pyramid(ws, net)
+        h = eng.body(ws, net, None, None, g.film, sp.film_dim, 0)
+        if eps_out is None:
+            eps_out = torch.empty(B, 1, L, device=eng.device, dtype=torch.float32)
+        eng.head(h, net, None, StepParams(0, 0, 0, 0, 1.0, 0.0, None, 0, 0), None, None, None, eps_out, None, B)
+        return eps_out
+
+    # ------------------------------------------------------------------ backward
+    def _conv_bwd(self, li: int, ws: _Workspace, g: _GradWorkspace, grads: Dict[str, Tensor], d_in0: Tensor,
+                  d_in1: Optional[Tensor]) -> None:
+        """wgrad + dgrad of conv `li` (>= 1) given g.d_raw.  d_in0 receives the gradient wrt src0 (the pooled tensor, or h
+        before the nearest upsample), d_in1 the gradient wrt the skip (decoders)."""
+        eng, sp, lib = self.eng, self.eng.spec, self.lib
+        d = sp.depth
+        name = sp.layer_names()[li]
+        B, L, Cout = ws.raw[li].shape
+        st = _cabi.stream_ptr()
+        if li <= d:
+            src0, src1, up = ws.pooled[li - 1], None, 0
+        else:
+            src0, src1, up = ws.out[li - 1], ws.out[2 * d - li], 1
+        C0, L0 = src0.shape[2], src0.shape[1]
+        C1 = src1.shape[2] if src1 is not None else 0
+        check(lib.gw_wgrad3_simt(ptr(src0), C0, L0, up, ptr(src1), C1, ptr(g.d_raw), B, L, Cout, eng.gw_dtype,
+                                 ptr(g.scratch), g.wg_elems, ptr(grads[name + ".0.weight"]), st), f"wgrad3_simt[{name}]")
+        eng.launches += 2
+        # dgrad = the same conv with flipped / transposed weights (conv_transpose of a stride-1 'same' conv)
+        w = eng.p[name + ".0.weight"]
+        wt = self._wt.get(li)
+        if wt is None:
+            wt = torch.empty(w.numel(), device=eng.device, dtype=torch.float32)
+            self._wt[li] = wt
+        check(lib.gw_weight_dgrad(ptr(w), Cout, C0 + C1, ptr(wt), st), "weight_dgrad")
+        dst = d_in0 if src1 is None else g.d_cat
+        check(lib.gw_conv3_simt(ptr(g.d_raw), Cout, L, 0, None, 0, B, L, ptr(wt), None, C0 + C1, ptr(dst), eng.gw_dtype, None,
+                                st), f"dgrad_simt[{name}]")
+        eng.launches += 2
+        if src1 is not None:
+            check(lib.gw_split_cat_grad(ptr(g.d_cat), B, L, C0, L0, C1, ptr(d_in0), ptr(d_in1), eng.gw_dtype, st), "split_cat_grad")
+            eng.launches += 1
+
+    def backward(self, net: Tensor, d_eps: Tensor, flat_grad: Tensor) -> None:
+        """Backward of the forward last run by `forward(net, t)`.  d_eps [B, L] fp32 = dLoss/d eps_hat."""
+        eng, sp, lib = self.eng, self.eng.spec, self.lib
+        d = sp.depth
+        lc = sp.layer_channels
+        B, Cx, L = net.shape
+        ws = eng.workspace(B, L, True)
+        g = self.grad_workspace(ws)
+        st = _cabi.stream_ptr()
+        grads = self.layout.views(flat_grad)
+        names, cnames, foffs = sp.layer_names(), sp.cond_names(), sp.film_offsets()
+        Cc = sp.cond_in_ch
+        nl = 2 * d + 1
+
+        def gn_bwd(li: int, do_a: Optional[Tensor], do_pool: Optional[Tensor]) -> None:
+            n = names[li]
+            lvl = li if li <= d else 2 * d - li
+            _, Ll, Cl = ws.raw[li].shape
+            check(lib.gw_gn_bwd(ptr(ws.raw[li]), ptr(ws.stats[li]), B, Ll, Cl, ptr(eng.p[n + ".1.weight"]),
+                                ptr(eng.p[n + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                ptr(eng.p[cnames[li] + ".weight"]) if Cc > 0 else None,
+                                ptr(eng.p[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(g.film), foffs[li], sp.film_dim,
+                                ptr(do_a), ptr(do_pool), eng.gw_dtype, ptr(g.scratch), ptr(g.dfilm), sp.film_dim, ptr(g.d_raw),
+                                ptr(grads[n + ".1.weight"]), ptr(grads[n + ".1.bias"]),
+                                ptr(grads[cnames[li] + ".weight"]) if Cc > 0 else None,
+                                ptr(grads[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(grads[n + ".0.bias"]), st),
+                  f"gn_bwd[{n}]")
+            eng.launches += 5
+
+        check(lib.gw_final_bwd(ptr(d_eps), ptr(ws.out[nl - 1]), eng.gw_dtype, ptr(net), B, Cx, L, lc[-1], ptr(eng.wf),
+                               ptr(g.d_h[0]), ptr(g.scratch), ptr(grads["final.weight"]), ptr(grads["final.bias"]), st), "final_bwd")
+        eng.launches += 3
+        cur = 0
+        for li in range(nl - 1, d, -1):                       # decoders, last first
+            gn_bwd(li, g.d_h[cur], None)
+            self._conv_bwd(li, ws, g, grads, g.d_h[cur ^ 1], g.d_skip[2 * d - li])
+            cur ^= 1
+        gn_bwd(d, g.d_h[cur], None)                           # mid
+        pc = 0
+        self._conv_bwd(d, ws, g, grads, g.d_pool[pc], None)
+        for li in range(d - 1, 0, -1):                        # encoders d-1 .. 1: skip gradient + avg_pool gradient
+            gn_bwd(li, g.d_skip[li], g.d_pool[pc])
+            self._conv_bwd(li, ws, g, grads, g.d_pool[pc ^ 1], None)
+            pc ^= 1
+        gn_bwd(0, g.d_skip[0], g.d_pool[pc])
+        check(lib.gw_wgrad_in(ptr(net), B, Cx, L, ptr(g.d_raw), lc[0], eng.gw_dtype, ptr(g.scratch), g.scratch.numel(),
+                              ptr(grads["encoders.0.0.weight"]), st), "wgrad_in")
+        eng.launches += 2
+        lo = self.layout
+        check(lib.gw_film_bwd(ptr(g.dfilm), ptr(g.aux), ptr(eng.film_w2), B, sp.time_dim, sp.base_ch, sp.film_dim, ptr(g.scratch),
+                              ptr(grads["time_mlp.1.weight"]), ptr(grads["time_mlp.1.bias"]),
+                              flat_grad.data_ptr() + 4 * lo.w2[0], flat_grad.data_ptr() + 4 * lo.b2[0], st), "film_bwd")
+        eng.launches += 3
+
+
+# ======================================================================================================
+# autograd bridge: reference-style loops (`loss.backward()`, torch optimisers) on the CUDA kernels
+# ======================================================================================================
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, cd, x, t, *params):
+        bwd = model._backward_engine(cd)
+        net = x.detach().contiguous().float()
+        eps = bwd.forward(net, t.reshape(-1).expand(net.shape[0]) if t.numel() == 1 else t)
+        ctx.bwd, ctx.net, ctx.n_params = bwd, net, len(params)
+        ctx.names = [k for k, _ in model.named_parameters()]
+        return eps
+
+    @staticmethod
+    def backward(ctx, d_eps):
+        bwd = ctx.bwd
+        flat = torch.zeros(bwd.layout.total, device=d_eps.device, dtype=torch.float32)
+        B, _, L = ctx.net.shape
+        bwd.backward(ctx.net, d_eps.contiguous().float().reshape(B, L), flat)
+        views = bwd.layout.views(flat)
+        return (None, None, None, None) + tuple(views[k] for k in ctx.names)
+
+
+def unet_autograd_forward(model, x: Tensor, t: Tensor, compute_dtype: str) -> Tensor:
+    params = [p for _, p in model.named_parameters()]
+    return _UNetFunction.apply(model, compute_dtype, x, t, *params)
+
+
+# ======================================================================================================
+# reference helper API (train.py:40-172)
+# ======================================================================================================
+@torch.no_grad()
+def _predict_x0_norm(model, diffusion, x_t: Tensor, cond_stack: Tensor, t: Tensor) -> Tensor:
+    """train.py:40-51: one-step x0 estimate with a zero self-conditioning channel."""
+    t = t.long()
+    net_in = torch.cat([x_t, cond_stack, torch.zeros_like(x_t)], dim=1).contiguous()
+    eps_hat = model(net_in, t)
+    lib = _cabi.load()
+    B, Cx, L = net_in.shape
+    ab = diffusion.alpha_bar.to(x_t.device).float().contiguous()
+    check(lib.gw_selfcond_x0(ptr(net_in), ptr(eps_hat.contiguous()), ptr(t.contiguous()), ptr(ab), B, Cx, L, _cabi.stream_ptr()),
+          "selfcond_x0")
+    return net_in[:, Cx - 1:Cx].clone()
+
+
+def _element_loss(eps_hat: Tensor, eps: Tensor, mask: Tensor, loss_type: str, huber_beta: float) -> Tensor:
+    """train.py:53-58 (elementwise; kept as torch ops for reference-style loops -- the fused step uses gw_loss)."""
+    if loss_type == "huber":
+        el = torch.nn.functional.smooth_l1_loss(eps_hat, eps, reduction="none", beta=huber_beta)
+    else:
+        el = (eps_hat - eps) ** 2
+    return el * mask
+
+
+@torch.no_grad()
+def update_ema(ema_model, model, decay: float) -> None:
+    """train.py:73-81."""
+    ema_params = dict(ema_model.named_parameters())
+    for k, p in model.named_parameters():
+        ema_params[k].data.mul_(decay).add_(p.data, alpha=(1.0 - decay))
+    for eb, mb in zip(ema_model.buffers(), model.buffers()):
+        eb.copy_(mb)
+
+
+def warmup_cosine_lambda(step: int, warmup_steps: int, total_steps: int, min_lr_scale: float = 0.1) -> float:
+    """train.py:85-90."""
+    if step < warmup_steps:
+        return max(1e-8, float(step + 1) / max(1, warmup_steps))
+    progress = (step - warmup_steps) / max(1, (total_steps - warmup_steps))
+    progress = min(max(progress, 0.0), 1.0)
+    return min_lr_scale + 0.5 * (1 - min_lr_scale) * (1 + math.cos(math.pi * progress))
+
+
+def make_warmup_cosine_scheduler(optimizer, warmup_steps: int, total_steps: int, min_lr_scale: float = 0.1):
+    """train.py:84-91."""
+    return torch.optim.lr_scheduler.LambdaLR(
+        optimizer, lambda step: warmup_cosine_lambda(step, warmup_steps, total_steps, min_lr_scale))
+
+
+def _match_batch(a: Tensor, target_bsz: int) -> Tensor:
+    """train.py:133-144."""
+    if a.shape[0] == target_bsz or a.shape[0] == 0:
+        return a
+    if target_bsz % a.shape[0] == 0:
+        return a.repeat_interleave(target_bsz // a.shape[0], dim=0)
+    rep = (target_bsz + a.shape[0] - 1) // a.shape[0]
+    return a.repeat_interleave(rep, dim=0)[:target_bsz]
+
+
+def _sample_timesteps_stratified(bsz: int, t_min: int, t_max: int, device, bins: int = 0) -> Tensor:
+    """train.py:147-172; the bucket edges are computed on the host (no per-bucket `.item()` syncs)."""
+    b = int(bins) if bins and bins > 0 else int(bsz)
+    b = max(1, min(b, bsz))
+    edges = torch.linspace(t_min, t_max + 1, b + 1).long().tolist()
+    q, r = divmod(bsz, b)
+    lo = torch.tensor([edges[i] for i in range(b) for _ in range(q + 1 if i < r else q)], device=device)
+    hi = torch.tensor([max(edges[i + 1] - 1, edges[i]) for i in range(b) for _ in range(q + 1 if i < r else q)], device=device)
+    t = lo + (torch.rand(lo.numel(), device=device) * (hi - lo + 1).float()).long().clamp_(max=hi - lo)
+    return t[torch.randperm(bsz, device=device)].long()
+
+
+# ======================================================================================================
+# fused training step
+# ======================================================================================================
+class FusedTrainStep:
+    """The per-batch body of `train_diffusion` (train.py:320-456) over flat buffers.
+
+    model parameters are re-pointed at views of `self.flat_p` (ParamLayout order), so `model.state_dict()` always shows
+    the live weights.  `self.flat_ema` holds the EMA copy (`ema_state_dict()`), `self.flat_m` / `self.flat_v` AdamW state.
+    """
+
+    def __init__(self, model, diffusion, B: int, L: int, *, lr: float = 2e-4, weight_decay: float = 1e-4,
+                 betas=(0.9, 0.999), eps: float = 1e-8, clip_grad: float = 1.0, ema_decay: Optional[float] = 0.999,
+                 loss: str = "huber", huber_beta: float = 0.5, loss_weight_power: float = 0.0, clamp_inputs: float = 10.0,
+                 p_uncond: float = 0.2, dropout_y_only: bool = True, t_min: int = 500, warmup_steps: int = 0,
+                 total_steps: int = 0, min_lr_scale: float = 0.1, cosine_decay: bool = False, seed: int = 0,
+                 compute_dtype: Optional[str] = None, conv_impl: str = "auto", process_group=None, sample0: int = 0):
+        import torch.distributed as dist
+        self.model, self.diffusion = model, diffusion
+        self.B, self.L = B, L
+        sp: ModelSpec = model.spec
+        self.spec = sp
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("gwb200 FusedTrainStep runs on CUDA (sm_100a) only: no CPU fallback")
+        self.device = dev
+        self.lib = _cabi.load()
+        cd = compute_dtype or model.compute_dtype
+        # ---- flat buffers; the module's parameters become views
+        shapes = {k: tuple(p.shape) for k, p in model.named_parameters()}
+        self.layout = ParamLayout(sp, shapes)
+        n = self.layout.total
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        views = self.layout.views(self.flat_p)
+        with torch.no_grad():
+            for k, p in model.named_parameters():
+                views[k].copy_(p.data)
+                p.data = views[k]
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_ema = self.flat_p.clone() if ema_decay is not None else None
+        self.eng = UNetEngine(views, sp, dtype=cd, conv_impl=conv_impl)
+        self.eng.bind_flat(self.flat_p, self.layout)
+        self.bwd = BackwardEngine(self.eng, self.layout)
+        # ---- hyper-parameters
+        self.lr, self.wd, self.betas, self.eps = float(lr), float(weight_decay), betas, float(eps)
+        self.clip_grad = float(clip_grad)
+        self.ema_decay = ema_decay
+        self.loss_type = 0 if loss == "huber" else 1
+        self.huber_beta, self.lwp = float(huber_beta), float(loss_weight_power)
+        self.clamp, self.p_uncond, self.dropout_y_only = float(clamp_inputs), float(p_uncond), bool(dropout_y_only)
+        self.t_min, self.T = int(t_min), int(diffusion.T)
+        self.warmup_steps, self.total_steps, self.min_lr_scale = int(warmup_steps), int(total_steps), float(min_lr_scale)
+        self.use_sched = warmup_steps > 0 or cosine_decay
+        self.seed, self.sample0 = int(seed) & (2 ** 64 - 1), int(sample0)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        # ---- step state
+        Cx, Cc = sp.in_ch, sp.cond_in_ch
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.net = torch.zeros(B, Cx, L, **f32)
+        self.clean = torch.zeros(B, L, **f32)
+        self.cond = torch.zeros(B, max(Cc, 1), L, **f32)
+        self.mask = torch.ones(B, L, **f32)
+        self.eps_buf = torch.zeros(B, L, **f32)
+        self.eps_hat = torch.zeros(B, 1, L, **f32)
+        self.d_eps = torch.zeros(B, L, **f32)
+        self.t = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.drop = torch.zeros(B, **f32)
+        self.wt = torch.ones(B, **f32) if self.lwp != 0.0 else None
+        self.per_sample = torch.zeros(B, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.info = torch.zeros(4, **f32)
+        self.hyper = torch.zeros(8, **f32)
+        self.hyper_host = torch.zeros(64, 8, dtype=torch.float32).pin_memory()     # ring: the host may run ahead of the stream
+        self._hyper_ev: List[Optional[torch.cuda.Event]] = [None] * 64
+        self.partial = torch.zeros(self.lib.gw_opt_scratch_doubles(), device=dev, dtype=torch.float64)
+        self.step_ctr = torch.zeros(1, device=dev, dtype=torch.int32)
+        ab = diffusion.alpha_bar.to(dev).float().contiguous()
+        self.ab, self.sab, self.s1mab = ab, ab.sqrt().contiguous(), (1 - ab).sqrt().contiguous()
+        self.steps_done = 0
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+
+    # ------------------------------------------------------------------ pieces
+    def state_dict_ema(self) -> Dict[str, Tensor]:
+        return {k: v.clone() for k, v in self.layout.views(self.flat_ema).items()} if self.flat_ema is not None else {}
+
+    def load_batch(self, clean_norm: Tensor, cond_stack: Tensor, mask: Optional[Tensor] = None) -> None:
+        """clean_norm [B,1,L], cond_stack [B,Cc,L] (sigma-normalised, train.py:336-347), mask [B,1,L]; async H2D if pinned."""
+        B, L = self.B, self.L
+        self.clean.copy_(clean_norm.reshape(B, L), non_blocking=True)
+        if self.spec.cond_in_ch > 0:
+            self.cond.copy_(cond_stack.reshape(B, self.spec.cond_in_ch, L), non_blocking=True)
+        if mask is not None:
+            self.mask.copy_(mask.reshape(B, L), non_blocking=True)
+
+    def _set_hyper(self) -> None:
+        step = self.steps_done + 1
+        lr = self.lr * (warmup_cosine_lambda(self.steps_done, self.warmup_steps, self.total_steps, self.min_lr_scale)
+                        if self.use_sched else 1.0)
+        slot = self.steps_done % self.hyper_host.shape[0]
+        if self._hyper_ev[slot] is not None:
+            self._hyper_ev[slot].synchronize()                # the copy that last used this pinned row has completed
+        h = self.hyper_host[slot]
+        h[0] = lr
+        h[1] = 1.0 - self.betas[0] ** step
+        h[2] = math.sqrt(1.0 - self.betas[1] ** step)
+        h[3] = self.ema_decay if self.ema_decay is not None else -1.0
+        h[4] = self.wd
+        h[5] = self.clip_grad
+        h[6] = 1.0 / self.world
+        self.hyper.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_ev[slot] = ev
+        self.last_lr = lr
+
+    def _enqueue(self, selfcond: bool, draws: bool, philox: bool) -> None:
+        """All kernels of one step on the current stream (capturable: no host reads, no allocation)."""
+        lib, eng, sp = self.lib, self.eng, self.spec
+        B, L, Cx, Cc = self.B, self.L, sp.in_ch, sp.cond_in_ch
+        st = _cabi.stream_ptr()
+        if draws:
+            check(lib.gw_train_draws(self.seed, ptr(self.step_ctr), self.sample0, B, self.t_min, self.T, self.p_uncond,
+                                     ptr(self.t), ptr(self.drop), st), "train_draws")
+            eng.launches += 1
+        use_drop = self.p_uncond > 0.0
+        y_only = self.dropout_y_only and Cc > 1
+        check(lib.gw_train_pack(ptr(self.clean), ptr(self.cond) if Cc > 0 else None, Cc, ptr(self.t),
+                                ptr(self.drop) if use_drop else None, ptr(self.sab), ptr(self.s1mab), ptr(self.eps_buf),
+                                1 if philox else 0, self.seed, self.sample0, ptr(self.step_ctr), self.clamp,
+                                1 if (use_drop and y_only) else 0, 0 if y_only else 1, ptr(self.net), B, Cx, L, st), "train_pack")
+        eng.launches += 1
+        if selfcond and sp.use_selfcond:                      # train.py:401-403: extra no-grad forward, zero self-cond
+            self.bwd.forward(self.net, self.t, self.eps_hat)
+            check(lib.gw_selfcond_x0(ptr(self.net), ptr(self.eps_hat), ptr(self.t), ptr(self.ab), B, Cx, L, st), "selfcond_x0")
+            eng.launches += 1
+        self.bwd.forward(self.net, self.t, self.eps_hat)
+        if self.wt is not None:
+            torch.pow(1.0 - self.ab[self.t], self.lwp, out=self.wt)
+        check(lib.gw_loss(ptr(self.eps_hat), ptr(self.eps_buf), ptr(self.mask), ptr(self.wt), B, L, self.loss_type,
+                          self.huber_beta, 1.0, ptr(self.per_sample), ptr(self.loss), ptr(self.d_eps), st), "loss")
+        eng.launches += 2
+        self.flat_g.zero_()
+        self.bwd.backward(self.net, self.d_eps, self.flat_g)
+
+    def _enqueue_update(self) -> None:
+        lib, st = self.lib, _cabi.stream_ptr()
+        n = self.layout.total
+        check(lib.gw_grad_sumsq(ptr(self.flat_g), n, ptr(self.partial), st), "grad_sumsq")
+        check(lib.gw_adamw_ema(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v), ptr(self.flat_ema), n,
+                               ptr(self.partial), ptr(self.hyper), ptr(self.loss), self.betas[0], self.betas[1], self.eps,
+                               ptr(self.info), st), "adamw_ema")
+        self.eng.refresh()                                    # re-pack the bf16 conv weights from the updated fp32 master
+        check(lib.gw_step_advance(ptr(self.step_ctr), -1, st), "step_advance")
+        self.eng.launches += 3
+
+    def _allreduce(self) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)    # the 1/world scale is applied in gw_adamw_ema
+
+    # ------------------------------------------------------------------ public
+    def step(self, *, selfcond: bool = False, t: Optional[Tensor] = None, eps: Optional[Tensor] = None,
+             drop: Optional[Tensor] = None, use_graph: bool = True) -> None:
+        """One optimisation step on the batch last given to `load_batch`.
+
+        `t` / `eps` / `drop` inject the draws the reference takes from the global RNG (parity tests); left None they come
+        from the on-device Philox streams keyed on (seed, global sample index, step).  `selfcond` is the per-batch coin of
+        train.py:401 (drawn by the caller from a host RNG so that no device->host sync is needed)."""
+        draws = t is None
+        philox = eps is None
+        if t is not None:
+            self.t.copy_(t.reshape(-1).long(), non_blocking=True)
+        if eps is not None:
+            self.eps_buf.copy_(eps.reshape(self.B, self.L), non_blocking=True)
+        if drop is not None:
+            self.drop.copy_(drop.reshape(-1).float(), non_blocking=True)
+        elif not draws:
+            self.drop.zero_()
+        self._set_hyper()
+        if not use_graph:
+            self._enqueue(selfcond, draws, philox)
+            self._allreduce()
+            self._enqueue_update()
+        else:
+            key = (bool(selfcond), draws, philox, self.p_uncond, self.t_min)
+            gs = self._graphs.get(key)
+            if gs is None:
+                gs = self._capture(key)
+            gs[0].replay()
+            self._allreduce()
+            gs[1].replay()
+        self.steps_done += 1
+
+    def _capture(self, key):
+        """Two graphs per step flavour: [pack .. backward] and [norm .. AdamW/EMA .. re-pack]; the NCCL all-reduce of the
+        flat gradient bucket runs between them on the same stream."""
+        selfcond, draws, philox = key[:3]
+        saved = [b.clone() for b in (self.flat_p, self.flat_m, self.flat_v, self.step_ctr)]
+        saved_ema = self.flat_ema.clone() if self.flat_ema is not None else None
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                            # warm-up: lazy packing, cudaFuncSetAttribute
+            self._enqueue(selfcond, draws, philox)
+            self._enqueue_update()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for b, sv in zip((self.flat_p, self.flat_m, self.flat_v, self.step_ctr), saved):
+            b.copy_(sv)
+        if saved_ema is not None:
+            self.flat_ema.copy_(saved_ema)
+        self.eng.refresh()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self._enqueue(selfcond, draws, philox)
+        with torch.cuda.graph(g2):
+            self._enqueue_update()
+        self._graphs[key] = (g1, g2)
+        return self._graphs[key]
+
+
+# ======================================================================================================
+# train_diffusion (train.py:174-630): host loop around FusedTrainStep
+# ======================================================================================================
+def train_diffusion(args, loader=None):
+    """Reference entry point.  `loader` yields (clean, noisy, sigma, mask[, meta]) batches as `dataloader.pad_collate`
+    does (dataloader.py:248-268); the HDF5 reader itself is outside this path, so a loader must be supplied."""
+    import random
+    from copy import deepcopy
+    from .models import CustomDiffusion, UNet1D
+    if loader is None:
+        raise RuntimeError("gwb200 train_diffusion: pass a batch iterable (the HDF5 dataloader is outside the hot path)")
+    if getattr(args, "seed", None) is not None:
+        random.seed(args.seed)
+        torch.manual_seed(args.seed)
+    device = torch.device(args.device)
+    peek = next(iter(loader))
+    C_meta = int(peek[4].shape[1]) if len(peek) == 5 else 0
+    cond_in_ch = 1 + C_meta
+    in_ch = 1 + cond_in_ch + 1
+    L = int(peek[0].shape[-1])
+    K = max(1, int(getattr(args, "t_multi", 1)))
+    B = int(peek[0].shape[0]) * K
+    model = UNet1D(in_ch=in_ch, base_ch=args.base_ch, time_dim=args.time_dim, depth=args.depth,
+                   t_embed_max_time=max(0, args.T - 1), cond_in_ch=cond_in_ch, use_selfcond=True,
+                   compute_dtype="bf16" if getattr(args, "amp", False) else "fp32").to(device)
+    diffusion = CustomDiffusion(T=args.T, device=device)
+    if getattr(args, "init_from", None):
+        ckpt = torch.load(args.init_from, map_location=device)
+        model.load_state_dict(ckpt.get("model_ema_state", ckpt.get("model_state")), strict=True)
+    total_steps = len(loader) * args.epochs
+    stepper = None
+    rng = random.Random(getattr(args, "seed", 0) or 0)
+    history = []
+    for epoch in range(1, args.epochs + 1):
+        forced = epoch <= getattr(args, "force_cond_epochs", 0)
+        p_uncond = 0.0 if forced else args.p_uncond
+        p_selfcond = 0.0 if forced else args.p_selfcond
+        t_min = int(max(0, min(args.T - 1, int(args.t_min_frac * args.T))))
+        for batch in loader:
+            clean_raw, noisy_raw, sigma, mask = batch[:4]
+            meta = batch[4].to(device).float() if len(batch) == 5 else None
+            sig = sigma.to(device).view(-1, 1, 1).float()
+            clean_norm = clean_raw.to(device).float() / sig
+            y_norm = noisy_raw.to(device).float() / sig
+            if meta is not None and meta.size(-1) != y_norm.size(-1):
+                meta = torch.nn.functional.interpolate(meta, size=y_norm.size(-1), mode="linear", align_corners=False)
+            cond_stack = torch.cat([y_norm, meta], dim=1) if meta is not None else y_norm
+            mask = mask.to(device).float()
+            if K > 1:
+                clean_norm, cond_stack, mask = (a.repeat_interleave(K, dim=0) for a in (clean_norm, cond_stack, mask))
+            if stepper is None or stepper.B != clean_norm.shape[0] or stepper.L != clean_norm.shape[-1]:
+                prev = stepper
+                stepper = FusedTrainStep(model, diffusion, clean_norm.shape[0], clean_norm.shape[-1], lr=args.lr,
+                                         weight_decay=args.weight_decay, clip_grad=args.clip_grad,
+                                         ema_decay=args.ema_decay if args.ema else None, loss=args.loss,
+                                         huber_beta=args.huber_beta, loss_weight_power=args.loss_weight_power,
+                                         clamp_inputs=args.clamp_inputs, p_uncond=p_uncond,
+                                         dropout_y_only=args.dropout_y_only, t_min=t_min, warmup_steps=args.warmup_steps,
+                                         total_steps=total_steps, min_lr_scale=args.min_lr_scale,
+                                         cosine_decay=args.cosine_decay, seed=getattr(args, "seed", 0) or 0)
+                if prev is not None:                           # ragged last batch: carry the optimiser state over
+                    for a, b in ((stepper.flat_m, prev.flat_m), (stepper.flat_v, prev.flat_v), (stepper.flat_ema, prev.flat_ema)):
+                        if a is not None and b is not None:
+                            a.copy_(b)
+                    stepper.steps_done = prev.steps_done
+            stepper.p_uncond, stepper.t_min = p_uncond, t_min
+            stepper.load_batch(clean_norm, cond_stack, mask)
+            t_inj = None
+            if getattr(args, "t_cover", "rand") == "strat":
+                t_inj = _sample_timesteps_stratified(stepper.B, t_min, args.T - 1, device, bins=getattr(args, "t_bins", 0))
+            stepper.step(selfcond=(p_selfcond > 0.0 and rng.random() < p_selfcond), t=t_inj,
+                         drop=(torch.rand(stepper.B, device=device) < p_uncond).float() if t_inj is not None else None)
+            history.append(stepper.loss.clone())              # device scalar; read back once per epoch below
+        history = [float(h) if isinstance(h, Tensor) else h for h in history]
+    return {"model": model, "stepper": stepper, "losses": history,
+            "checkpoint": {"model_state": model.state_dict(), "epoch": args.epochs,
+                           "model_ema_state": stepper.state_dict_ema() if stepper is not None else {},
+                           "args": {**vars(args), "in_ch": in_ch, "cond_in_ch": cond_in_ch, "meta_enabled": C_meta > 0,
+                                    "meta_channels": C_meta, "conditioning": "y+meta" if C_meta > 0 else "y"}}}

@@ -34,9 +34,10 @@ int gw_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---- time conditioning: TimeEmbedding + time_mlp + all tproj_* (models.py:19-31, 105-109, 137-142, 197).
  * t: int64 [n]; w1 [base, time_dim], b1 [base]; w2 [F, base], b2 [F] = the 2*depth+1 tproj Linear layers
- * concatenated in order enc0..encD-1, mid, dec0..decD-1; out fp32 [n, F] rows of (gamma|beta) blocks. */
+ * concatenated in order enc0..encD-1, mid, dec0..decD-1; out fp32 [n, F] rows of (gamma|beta) blocks.
+ * aux (optional, training): fp32 [n, time_dim + 3*base] rows of [emb | pre | ctx | act] kept for gw_film_bwd. */
 int gw_film_vectors(const int64_t* t, int n, int time_dim, float max_time, const float* w1, const float* b1,
-                    const float* w2, const float* b2, int base, int F, float* out, void* stream);
+                    const float* w2, const float* b2, int base, int F, float* out, float* aux, void* stream);
 
 /* ---- conditioning pyramid: F.interpolate(cond, size=L_j, mode="linear", align_corners=False) for every
  * level j (models.py:188-193), written channels-last fp32 [B, L_j, Cc].
@@ -53,7 +54,8 @@ int gw_conv_in(const float* x, const float* x_alt, const int* step_ptr, int B, i
 
 /* ---- generic Conv1d(k=3, pad=1) on channels-last activations, CUDA-core fp32 math (exact mode, any L).
  * Input is the virtual concat [nearest-upsample x2 (src0) | src1] (models.py:217-222); src1 may be NULL and
- * `up0` = 0 for encoder/mid convs.  src0 [B, L0, C0], src1 [B, L, C1]; w3 = the reference weight [Cout, C0+C1, 3] fp32; raw [B, L, Cout]; part [B, ceil(L/64), 8, 2]. */
+ * `up0` = 0 for encoder/mid convs.  src0 [B, L0, C0], src1 [B, L, C1]; w3 = the reference weight [Cout, C0+C1, 3] fp32;
+ * raw [B, L, Cout]; part [B, ceil(L/64), 8, 2].  bias and part may be NULL (dgrad use: see gw_weight_dgrad). */
 int gw_conv3_simt(const void* src0, int C0, int L0, int up0, const void* src1, int C1, int B, int L,
                   const float* w3, const float* bias, int Cout, void* raw, int dtype, float* part, void* stream);
 
@@ -125,6 +127,80 @@ int gw_conv_tc_pack(const gw_conv_tc_shape* s, const float* w, void* packed, voi
 int gw_conv_tc_n_part(const gw_conv_tc_shape* s);
 int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
                void* raw, float* part, int variant, void* stream);
+
+/* =====================================================================================================
+ * Training step (train.py:320-456): loss, backward of every block, optimiser.  Parameter gradients are always
+ * ACCUMULATED (+=) into fp32 buffers laid out like the reference parameters; the caller zeroes the flat gradient
+ * buffer once per step.  `scratch` arguments are caller-owned fp32 device workspaces.
+ * ===================================================================================================== */
+
+/* dst[c] (+)= scale * sum_r src[r, c]  -- fixed-order second level of every two-level reduction here */
+int gw_reduce_rows(const float* src, int n_rows, long n_cols, float scale, float* dst, int accumulate, void* stream);
+
+/* masked Huber (loss_type 0, F.smooth_l1_loss beta) / MSE (1) loss of train.py:53-58, 411-421:
+ * per_sample[b] = wt[b] * sum_l el*mask / max(sum_l mask, 1); loss[0] = mean_b per_sample;
+ * d_eps[b,l] = grad_scale * dloss/d eps_hat[b,l].  mask / wt (= (1-alpha_bar_t)^p, train.py:414-417) may be NULL. */
+int gw_loss(const float* eps_hat, const float* eps, const float* mask, const float* wt, int B, int L, int loss_type,
+            float beta, float grad_scale, float* per_sample, float* loss, float* d_eps, void* stream);
+
+/* backward of the head conv final(cat[h, x_t]) (models.py:230): d_h [B, L, C] (dtype); d_wf [(C+1)*3], d_bf [1] accumulated.
+ * scratch >= B * ceil(L/512) * ((C+1)*3 + 1) floats. */
+int gw_final_bwd(const float* d_eps, const void* h, int dtype, const float* net, int B, int Cx, int L, int C,
+                 const float* wf, void* d_h, float* scratch, float* d_wf, float* d_bf, void* stream);
+
+/* backward of GroupNorm -> SiLU -> +cond 1x1 conv -> FiLM (-> avg_pool) of one block (models.py:165-173, 188-193, 208).
+ * Incoming gradient = do_a [B, L, C] (wrt the block output; NULL if none) + avg_pool backward of do_pool [B, L/2, C]
+ * (NULL if none).  stats = (mean, rstd) [B, 8, 2] saved by gw_gn_apply.  Writes d_raw [B, L, C] (gradient wrt the conv
+ * output), dfilm[b, film_off + (0..C | C..2C)] = (d gamma | d beta); accumulates d_gn_w, d_gn_b, d_bc, d_conv_bias [C],
+ * d_wc [C, Cc].  scratch >= gw_gn_bwd_scratch_elems(B, L, C, Cc) floats. */
+long gw_gn_bwd_scratch_elems(int B, int L, int C, int Cc);
+int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
+              const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+              long film_b_stride, const void* do_a, const void* do_pool, int dtype, float* scratch, float* dfilm,
+              long dfilm_b_stride, void* d_raw, float* d_gn_w, float* d_gn_b, float* d_wc, float* d_bc,
+              float* d_conv_bias, void* stream);
+
+/* exact-mode conv backward.  gw_weight_dgrad: wt[ci][co][k] = w[co][ci][2-k], so that dgrad = gw_conv3_simt(d_raw, wt).
+ * gw_split_cat_grad: gradient of cat[nearest-upsample x2 (h), skip]: d_h [B, L0, C0] (pair sums), d_skip [B, L, C1].
+ * gw_wgrad3_simt: dW[co][ci][k] += sum_{b,l} d_raw[b,l,co] * cat[up(src0), src1][b, l+k-1, ci] (split-K partials in scratch).
+ * gw_wgrad_in: the same for the first conv, whose input is the fp32 [B, Cx, L] network input. */
+int gw_weight_dgrad(const float* w, int Cout, int Cin, float* wt, void* stream);
+int gw_split_cat_grad(const void* d_cat, int B, int L, int C0, int L0, int C1, void* d_h, void* d_skip, int dtype,
+                      void* stream);
+int gw_wgrad3_simt(const void* src0, int C0, int L0, int up0, const void* src1, int C1, const void* d_raw, int B,
+                   int L, int Cout, int dtype, float* scratch, long scratch_elems, float* dW, void* stream);
+int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_raw, int C, int dtype, float* scratch,
+                long scratch_elems, float* dW, void* stream);
+
+/* time_mlp / tproj_* backward (models.py:105-109, 137-142): dfilm [B, F] (written by gw_gn_bwd), aux from
+ * gw_film_vectors; accumulates dW1 [base, time_dim], db1 [base], dW2 [F, base], db2 [F]; scratch >= B*base floats. */
+int gw_film_bwd(const float* dfilm, const float* aux, const float* w2, int B, int time_dim, int base, int F,
+                float* scratch, float* dW1, float* db1, float* dW2, float* db2, void* stream);
+
+/* per-sample training draws, Philox keyed on the global sample index: t ~ U{t_min..T-1} (train.py:376) and the
+ * CFG-dropout coin (train.py:386).  step_ptr: device step counter (NULL = 0). */
+int gw_train_draws(unsigned long long seed, const int* step_ptr, long sample0, int B, int t_min, int T,
+                   float p_uncond, int64_t* t_out, float* drop_out, void* stream);
+/* network-input packing (train.py:350-352, 379-398, 404-407): q_sample with clamp into channel 0, conditioning
+ * channels with CFG dropout, zero self-conditioning channel.  clean [B, L]; cond [B, Cc, L]; eps [B, L] read
+ * (philox == 0) or generated; drop [B] or NULL. */
+int gw_train_pack(const float* clean, const float* cond, int Cc, const int64_t* t, const float* drop,
+                  const float* sqrt_ab, const float* sqrt_1mab, float* eps, int philox, unsigned long long seed,
+                  long sample0, const int* step_ptr, float clampv, int clamp_y, int drop_all, float* net, int B, int Cx,
+                  int L, void* stream);
+/* self-conditioning estimate (train.py:40-51): net[b, Cx-1, :] = (x_t - sqrt(1-ab_t) eps_hat) / sqrt(ab_t) */
+int gw_selfcond_x0(float* net, const float* eps_hat, const int64_t* t, const float* alpha_bar, int B, int Cx, int L,
+                   void* stream);
+
+/* clip_grad_norm_ + AdamW + EMA (train.py:445-455, 73-81) over flat fp32 buffers of n elements.
+ * gw_grad_sumsq writes gw_opt_scratch_doubles() partial sums; gw_adamw_ema finishes the norm, clips, updates.
+ * hyper (device fp32[8]): lr, 1-beta1^t, sqrt(1-beta2^t), ema_decay (<0 none), weight_decay, max_norm (<=0 none),
+ * grad_scale (1/world), unused.  info (device fp32[4]) out: grad norm, clip coefficient, applied flag.
+ * The update is skipped when the norm or *loss is not finite (train.py:424-427). */
+int gw_opt_scratch_doubles(void);
+int gw_grad_sumsq(const float* g, long n, double* partial, void* stream);
+int gw_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, long n, const double* partial,
+                 const float* hyper, const float* loss, float beta1, float beta2, float eps, float* info, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,13 +13,14 @@ Dataset / HDF5 / logging parts of the reference file (train.py:17-27, 93-130, 20
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Dict, List, Optional
 
 import torch
 
 from . import _cabi
-from ._cabi import StepParams, check, ptr
+from ._cabi import ConvTcShape, StepParams, check, ptr
 from .engine import ModelSpec, ParamLayout, UNetEngine, _Workspace
 
 Tensor = torch.Tensor
@@ -52,7 +53,13 @@ class _GradWorkspace:
         n_scr = max(n_scr, B * ((ws.L + 511) // 512) * ((lc[-1] + 1) * 3 + 1), B * spec.base_ch,
                     B * ((ws.L + 1023) // 1024) * lc[0] * spec.in_ch * 3)
         wmax = max(lc[i] * ((lc[i - 1] + (spec.chs[2 * d - i] if i > d else 0)) * 3) for i in range(1, 2 * d + 1))
-        self.wg_elems = max(16 * wmax, 8 << 20) if simt else 0            # split-K partials of the SIMT wgrad
+        self.wg_elems = max(16 * wmax, 8 << 20)                           # split-K partials of the SIMT / tcgen05 wgrad
+        for i in range(1, 2 * d + 1):
+            cin_parts = [(0, lc[i - 1])] if i <= d else [(1, lc[i - 1]), (0, spec.chs[2 * d - i])]
+            for mode, cx in cin_parts:
+                if mode == 1 and ws.lay_len[i] % 2:
+                    continue
+                self.wg_elems = max(self.wg_elems, lib.gw_wgrad_tc_scratch_elems(mode, B, ws.lay_len[i], lc[i], cx))
         self.scratch = torch.empty(max(n_scr, self.wg_elems), device=device, dtype=torch.float32)
         self.dfilm = torch.zeros(B, spec.film_dim, device=device, dtype=torch.float32)
         self.aux = torch.empty(B, spec.time_dim + 3 * spec.base_ch, device=device, dtype=torch.float32)
@@ -70,6 +77,11 @@ class BackwardEngine:
         self.layout = layout
         self._gws: Dict[tuple, _GradWorkspace] = {}
         self._wt: Dict[int, Tensor] = {}
+        self._dg_packed: Dict[tuple, Tensor] = {}
+        # conv backward kernels: tcgen05 GEMMs when the engine runs the tcgen05 forward, CUDA-core fp32 otherwise
+        self.dgrad_impl = "tc" if eng.conv_impl == "tc" else "simt"
+        self.wgrad_impl = "tc" if eng.conv_impl == "tc" else "simt"
+        self.wgrad_variant = 0
 
     def grad_workspace(self, ws: _Workspace) -> _GradWorkspace:
         key = (ws.B, ws.L)
@@ -110,9 +122,23 @@ class BackwardEngine:
             src0, src1, up = ws.out[li - 1], ws.out[2 * d - li], 1
         C0, L0 = src0.shape[2], src0.shape[1]
         C1 = src1.shape[2] if src1 is not None else 0
-        check(lib.gw_wgrad3_simt(ptr(src0), C0, L0, up, ptr(src1), C1, ptr(g.d_raw), B, L, Cout, eng.gw_dtype,
-                                 ptr(g.scratch), g.wg_elems, ptr(grads[name + ".0.weight"]), st), f"wgrad3_simt[{name}]")
-        eng.launches += 2
+        tc_ok = eng.dtype == "bf16" and (src1 is None or (L % 2 == 0 and L0 * 2 == L)) and Cout <= 256 and C0 <= 256 and C1 <= 256
+        dW = grads[name + ".0.weight"]
+        if self.wgrad_impl == "tc" and tc_ok:
+            if src1 is None:
+                check(lib.gw_wgrad_tc(0, ptr(g.d_raw), ptr(src0), B, L, Cout, C0, C0, 0, ptr(g.scratch), g.scratch.numel(), ptr(dW),
+                                      self.wgrad_variant, st), f"wgrad_tc[{name}]")
+                eng.launches += 2
+            else:
+                check(lib.gw_wgrad_tc(1, ptr(g.d_raw), ptr(src0), B, L, Cout, C0, C0 + C1, 0, ptr(g.scratch), g.scratch.numel(),
+                                      ptr(dW), self.wgrad_variant, st), f"wgrad_tc[{name}.up]")
+                check(lib.gw_wgrad_tc(0, ptr(g.d_raw), ptr(src1), B, L, Cout, C1, C0 + C1, C0, ptr(g.scratch), g.scratch.numel(),
+                                      ptr(dW), self.wgrad_variant, st), f"wgrad_tc[{name}.skip]")
+                eng.launches += 4
+        else:
+            check(lib.gw_wgrad3_simt(ptr(src0), C0, L0, up, ptr(src1), C1, ptr(g.d_raw), B, L, Cout, eng.gw_dtype,
+                                     ptr(g.scratch), g.wg_elems, ptr(dW), st), f"wgrad3_simt[{name}]")
+            eng.launches += 2
         # dgrad = the same conv with flipped / transposed weights (conv_transpose of a stride-1 'same' conv)
         w = eng.p[name + ".0.weight"]
         wt = self._wt.get(li)
@@ -120,6 +146,30 @@ class BackwardEngine:
             wt = torch.empty(w.numel(), device=eng.device, dtype=torch.float32)
             self._wt[li] = wt
         check(lib.gw_weight_dgrad(ptr(w), Cout, C0 + C1, ptr(wt), st), "weight_dgrad")
+        if self.dgrad_impl == "tc" and tc_ok:
+            # (shape, first row of the dgrad weight matrix, destination): plain conv for pooled / skip inputs, pair-sum
+            # mode through the nearest upsample
+            if src1 is None:
+                parts = [(ConvTcShape(1, 0, B, L, Cout, L, 0, C0), 0, d_in0)]
+            else:
+                parts = [(ConvTcShape(1, 2, B, L // 2, Cout, L, 0, C0), 0, d_in0),
+                         (ConvTcShape(1, 0, B, L, Cout, L, 0, C1), C0, d_in1)]
+            for pi, (shp, row0, dst) in enumerate(parts):
+                key = (li, pi, L)
+                packed = self._dg_packed.get(key)
+                if packed is None:
+                    n = lib.gw_conv_tc_packed_elems(C.byref(shp))
+                    if n <= 0:
+                        raise RuntimeError("gw_conv_tc_packed_elems(dgrad): " + lib.gw_last_error().decode())
+                    packed = torch.empty(n, device=eng.device, dtype=torch.bfloat16)
+                    self._dg_packed[key] = packed
+                check(lib.gw_conv_tc_pack(C.byref(shp), wt.data_ptr() + 4 * row0 * Cout * 3, ptr(packed), st), "conv_tc_pack(dgrad)")
+                variant = eng.tc_variant if shp.Cout >= 128 else 0
+                check(lib.gw_conv_tc(C.byref(shp), ptr(g.d_raw), None, ptr(packed), None, ptr(dst), None, variant, st),
+                      f"dgrad_tc[{name}.{pi}]")
+                eng.launches += 2
+            eng.launches += 1
+            return
         dst = d_in0 if src1 is None else g.d_cat
         check(lib.gw_conv3_simt(ptr(g.d_raw), Cout, L, 0, None, 0, B, L, ptr(wt), None, C0 + C1, ptr(dst), eng.gw_dtype, None,
                                 st), f"dgrad_simt[{name}]")

@@ -112,7 +112,9 @@ int gw_q_sample(const float* x0, const int64_t* t, const float* sqrt_ab, const f
 /* ---- tcgen05 / TMA implicit-GEMM Conv1d(k=3) on bf16 channels-last activations (K2-K7).  See conv_tc.cu. */
 typedef struct {
     int n_src;               /* 1 or 2 */
-    int pair;                /* 1: decoder conv evaluated in pair space (nearest-upsample folded into the weights) */
+    int pair;                /* 1: decoder conv evaluated in pair space (nearest-upsample folded into the weights);
+                              * 2: dgrad through the nearest upsample: src0 = d_raw [B, L0 = 2L, C0], output d_h [B, L, Cout]
+                              *    = sum of the gradients of the two upsampled positions (weights from gw_weight_dgrad) */
     int B, L;                /* output length L (positions) */
     int C0, L0;              /* src0 channels / length (L0 = L/2 when pair) */
     int C1;                  /* src1 channels (skip), 0 if none */
@@ -123,7 +125,8 @@ typedef struct {
 long gw_conv_tc_packed_elems(const gw_conv_tc_shape* s);
 /* pack fp32 reference weights [Cout, Cin, 3] into the kernel's bf16 segment-major layout (device -> device) */
 int gw_conv_tc_pack(const gw_conv_tc_shape* s, const float* w, void* packed, void* stream);
-/* run: src0/src1/raw bf16; bias fp32 [Cout]; part fp32 [B, n_part, 8, 2], n_part = gw_conv_tc_n_part(s) */
+/* run: src0/src1/raw bf16; bias fp32 [Cout] or NULL; part fp32 [B, n_part, 8, 2], n_part = gw_conv_tc_n_part(s), or NULL
+ * (no GroupNorm statistics: dgrad use) */
 int gw_conv_tc_n_part(const gw_conv_tc_shape* s);
 int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
                void* raw, float* part, int variant, void* stream);
@@ -171,6 +174,14 @@ int gw_wgrad3_simt(const void* src0, int C0, int L0, int up0, const void* src1, 
                    int L, int Cout, int dtype, float* scratch, long scratch_elems, float* dW, void* stream);
 int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_raw, int C, int dtype, float* scratch,
                 long scratch_elems, float* dW, void* stream);
+
+/* tcgen05 / TMA weight gradient (see wgrad_tc.cu).  mode 0: x [B, L, Cx] is a plain conv input (pooled tensor or skip);
+ * mode 1: x [B, L/2, Cx] is h before the nearest upsample.  d_raw [B, L, Cout] bf16.  ACCUMULATES into the input-channel
+ * block [ci_off, ci_off+Cx) of dW fp32 [Cout][Cin_total][3].  scratch >= gw_wgrad_tc_scratch_elems(...) floats.
+ * variant bit 0: one TMA box per tap instead of row-shifted descriptors. */
+long gw_wgrad_tc_scratch_elems(int mode, int B, int L, int Cout, int Cx);
+int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, int L, int Cout, int Cx, int Cin_total, int ci_off,
+                float* scratch, long scratch_elems, float* dW, int variant, void* stream);
 
 /* time_mlp / tproj_* backward (models.py:105-109, 137-142): dfilm [B, F] (written by gw_gn_bwd), aux from
  * gw_film_vectors; accumulates dW1 [base, time_dim], db1 [base], dW2 [F, base], db2 [F]; scratch >= B*base floats. */

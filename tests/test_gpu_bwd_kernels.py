@@ -1,0 +1,44 @@
+"""tcgen05 backward GEMMs (dgrad through conv_tc, wgrad_tc) against the CUDA-core fp32 kernels on the same bf16 tensors.
+
+Both families read identical bf16 activations / gradients; they differ by bf16 weights (dgrad) and accumulation order, so
+per-tensor rel-L2 <= 1e-2 (north_star bf16 bound)."""
+import pytest
+import torch
+
+from weights import gaussian, make_state_dict, synthetic_chirps
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _run(in_ch, cc, B, L, dgrad, wgrad, wvariant=0):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import FusedTrainStep
+    sd = make_state_dict(in_ch, cc, seed=4)
+    m = UNet1D(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True, compute_dtype="bf16")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    st = FusedTrainStep(m, CustomDiffusion(T=1000, device="cuda"), B, L, compute_dtype="bf16", seed=5)
+    st.bwd.dgrad_impl, st.bwd.wgrad_impl, st.bwd.wgrad_variant = dgrad, wgrad, wvariant
+    d = synthetic_chirps(B, L, seed=9)
+    cond = d["y_norm"] if cc == 1 else torch.cat([d["y_norm"], 0.2 * gaussian((B, 4, 1), 3).expand(B, 4, L)], 1)
+    st.load_batch(d["clean_norm"].cuda(), cond.contiguous().cuda(), None)
+    st.step(use_graph=False)
+    torch.cuda.synchronize()
+    return st, {k: v.clone() for k, v in st.layout.views(st.flat_g).items()}
+
+
+@pytest.mark.parametrize("in_ch,cc,B,L", [(3, 1, 3, 1024), (7, 5, 2, 4096), (3, 1, 5, 192)])
+def test_tc_backward_matches_simt(in_ch, cc, B, L):
+    _, ref = _run(in_ch, cc, B, L, "simt", "simt")
+    for dg, wg, wv, what in [("simt", "tc", 1, "wgrad_tc (one box per tap)"), ("simt", "tc", 0, "wgrad_tc (shifted descriptors)"),
+                             ("tc", "simt", 0, "dgrad_tc"), ("tc", "tc", 0, "both")]:
+        _, got = _run(in_ch, cc, B, L, dg, wg, wv)
+        tot = float(torch.cat([v.reshape(-1) for v in ref.values()]).norm())
+        for k in ref:
+            err = float((got[k].double() - ref[k].double()).norm())
+            assert err <= 1e-2 * max(float(ref[k].norm()), 1e-2 * tot), (what, k, err, float(ref[k].norm()))

@@ -417,6 +417,47 @@ class FusedTrainStep:
         self.steps_done = 0
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
 
+    # ------------------------------------------------------------------ host -> device staging
+    def prefetch(self, clean_norm: Tensor, cond_stack: Tensor, mask: Optional[Tensor] = None) -> None:
+        """Start the H2D copy of the NEXT batch (pinned host tensors) on a side stream into one of two staging sets, so
+        it overlaps the step in flight (the reference gets the same overlap from DataLoader pin_memory + non_blocking,
+        train.py:184-198, 323-332).  `step(prefetched=True)` consumes it."""
+        if not hasattr(self, "_stage"):
+            self._stage = [{"clean": torch.empty_like(self.clean), "cond": torch.empty_like(self.cond),
+                            "mask": torch.empty_like(self.mask)} for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream()
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._free = [torch.cuda.Event(), torch.cuda.Event()]
+            for ev in self._free:
+                ev.record()
+            self._pf, self._cs = 0, 0
+        slot = self._pf
+        self._pf ^= 1
+        B, L = self.B, self.L
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._free[slot])
+            sset = self._stage[slot]
+            sset["clean"].copy_(clean_norm.reshape(B, L), non_blocking=True)
+            if self.spec.cond_in_ch > 0:
+                sset["cond"].copy_(cond_stack.reshape(B, self.spec.cond_in_ch, L), non_blocking=True)
+            sset["has_mask"] = mask is not None
+            if mask is not None:
+                sset["mask"].copy_(mask.reshape(B, L), non_blocking=True)
+            self._ready[slot].record()
+
+    def _consume_prefetched(self) -> None:
+        slot = self._cs
+        self._cs ^= 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[slot])
+        sset = self._stage[slot]
+        self.clean.copy_(sset["clean"])
+        if self.spec.cond_in_ch > 0:
+            self.cond.copy_(sset["cond"])
+        if sset["has_mask"]:
+            self.mask.copy_(sset["mask"])
+        self._free[slot].record(cur)
+
     # ------------------------------------------------------------------ pieces
     def state_dict_ema(self) -> Dict[str, Tensor]:
         return {k: v.clone() for k, v in self.layout.views(self.flat_ema).items()} if self.flat_ema is not None else {}
@@ -493,12 +534,12 @@ class FusedTrainStep:
 
     def _allreduce(self) -> None:
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)    # the 1/world scale is applied in gw_adamw_ema
+            from .parallel import allreduce_flat_
+            allreduce_flat_(self.flat_g, self.pg)             # the 1/world scale is applied in gw_adamw_ema
 
     # ------------------------------------------------------------------ public
     def step(self, *, selfcond: bool = False, t: Optional[Tensor] = None, eps: Optional[Tensor] = None,
-             drop: Optional[Tensor] = None, use_graph: bool = True) -> None:
+             drop: Optional[Tensor] = None, use_graph: bool = True, prefetched: bool = False) -> None:
         """One optimisation step on the batch last given to `load_batch`.
 
         `t` / `eps` / `drop` inject the draws the reference takes from the global RNG (parity tests); left None they come
@@ -506,6 +547,8 @@ class FusedTrainStep:
         train.py:401 (drawn by the caller from a host RNG so that no device->host sync is needed)."""
         draws = t is None
         philox = eps is None
+        if prefetched:
+            self._consume_prefetched()
         if t is not None:
             self.t.copy_(t.reshape(-1).long(), non_blocking=True)
         if eps is not None:

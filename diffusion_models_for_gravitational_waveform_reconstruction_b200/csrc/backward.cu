@@ -20,30 +20,52 @@
 #define BW_MAX_CC 8
 
 // ------------------------------------------------------------------------------------------------
-// generic column sums: dst[c] (+)= scale * sum_r src[r, c]
+// generic column sums: dst[c] (+)= scale * sum_r src[r, c], fixed summation order (deterministic).
+// Block = 32 columns x 32 row lanes.  Tall inputs are reduced in two stages; stage 1 folds each chunk of 128 rows IN PLACE
+// into the chunk's first row (the partial buffers are scratch), stage 2 folds those rows into dst.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ src, int n_rows, long n_cols, long pitch,
-                                                          float scale, float* __restrict__ dst, int accumulate) {
-    const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cols) return;
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    int r = 0;
-    for (; r + 3 < n_rows; r += 4) {
-        a0 += src[(size_t)r * pitch + c];
-        a1 += src[(size_t)(r + 1) * pitch + c];
-        a2 += src[(size_t)(r + 2) * pitch + c];
-        a3 += src[(size_t)(r + 3) * pitch + c];
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(float* __restrict__ src, int n_rows, long n_cols, long pitch, int chunk,
+                                                           float scale, float* __restrict__ dst, int accumulate, int final_stage) {
+    __shared__ float red[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long c = (long)blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * chunk;
+    const int r1 = min(r0 + chunk, n_rows);
+    float a = 0.0f;
+    if (c < n_cols) {
+#pragma unroll 4
+        for (int r = r0 + ty; r < r1; r += 32) a += src[(size_t)r * pitch + c];
     }
-    for (; r < n_rows; ++r) a0 += src[(size_t)r * pitch + c];
-    const float s = scale * ((a0 + a1) + (a2 + a3));
-    dst[c] = accumulate ? dst[c] + s : s;
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < n_cols) {
+        float s = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) s += red[t][tx];
+        if (final_stage) dst[c] = accumulate ? dst[c] + scale * s : scale * s;
+        else src[(size_t)r0 * pitch + c] = s;
+    }
 }
 
-static int reduce_rows(const float* src, int n_rows, long n_cols, long pitch, float scale, float* dst, int accumulate,
+static int reduce_rows(const float* src_c, int n_rows, long n_cols, long pitch, float scale, float* dst, int accumulate,
                        cudaStream_t st) {
-    reduce_rows_kernel<<<(unsigned)((n_cols + 255) / 256), 256, 0, st>>>(src, n_rows, n_cols, pitch, scale, dst, accumulate);
+    float* src = const_cast<float*>(src_c);
+    const unsigned gx = (unsigned)((n_cols + 31) / 32);
+    if (n_rows <= 256) {
+        reduce_rows_kernel<<<dim3(gx, 1), 1024, 0, st>>>(src, n_rows, n_cols, pitch, n_rows, scale, dst, accumulate, 1);
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
+    const int chunk = 128;
+    const int n_chunks = gw_cdiv(n_rows, chunk);
+    reduce_rows_kernel<<<dim3(gx, n_chunks), 1024, 0, st>>>(src, n_rows, n_cols, pitch, chunk, 1.0f, nullptr, 0, 0);
     GW_LAUNCH_CHECK();
-    return GW_OK;
+    if (n_chunks <= 256) {
+        reduce_rows_kernel<<<dim3(gx, 1), 1024, 0, st>>>(src, n_chunks, n_cols, pitch * chunk, n_chunks, scale, dst, accumulate, 1);
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
+    return reduce_rows(src, n_chunks, n_cols, pitch * chunk, scale, dst, accumulate, st);
 }
 
 extern "C" int gw_reduce_rows(const float* src, int n_rows, long n_cols, float scale, float* dst, int accumulate, void* stream) {
@@ -105,13 +127,23 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ eps
     }
 }
 
+__global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+    __shared__ float red[8];
+    float a = 0.0f;
+    for (int i = threadIdx.x; i < n; i += 256) a += v[i];
+    const float t = block_sum_256(a, red);
+    if (threadIdx.x == 0) out[0] = t / (float)n;
+}
+
 extern "C" int gw_loss(const float* eps_hat, const float* eps, const float* mask, const float* wt, int B, int L, int loss_type,
                        float beta, float grad_scale, float* per_sample, float* loss, float* d_eps, void* stream) {
     GW_REQUIRE(B > 0 && L > 0 && (loss_type == 0 || loss_type == 1), "gw_loss: arguments");
     GW_REQUIRE(loss_type == 1 || beta > 0.0f, "gw_loss: huber beta must be > 0");
     loss_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(eps_hat, eps, mask, wt, B, L, loss_type, beta, grad_scale, per_sample, d_eps);
     GW_LAUNCH_CHECK();
-    return reduce_rows(per_sample, B, 1, 1, 1.0f / (float)B, loss, 0, (cudaStream_t)stream);
+    mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(per_sample, B, loss);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -140,18 +172,32 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
         }
     const float* de = d_eps + (size_t)b * L;
     const int r_end = min(r0 + rows_per_cta, L);
-    for (int r = r0 + tr; r < r_end; r += n_tr) {
-        const float e_m = r > 0 ? de[r - 1] : 0.0f, e_c = de[r], e_p = r + 1 < L ? de[r + 1] : 0.0f;
-        float hv[8], o[8];
-        ld8(h + ((size_t)b * L + r) * C + oct * 8, hv);
+    constexpr int UN = 4;
+    for (int r = r0 + tr; r < r_end; r += n_tr * UN) {
+        float hv[UN][8], em[UN], ec[UN], ep[UN];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            o[i] = fmaf(w[i][0], e_p, fmaf(w[i][1], e_c, w[i][2] * e_m));
-            dw[i][0] = fmaf(hv[i], e_p, dw[i][0]);
-            dw[i][1] = fmaf(hv[i], e_c, dw[i][1]);
-            dw[i][2] = fmaf(hv[i], e_m, dw[i][2]);
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            const int rc = rr < r_end ? rr : r;
+            ld8(h + ((size_t)b * L + rc) * C + oct * 8, hv[u]);
+            em[u] = rc > 0 ? de[rc - 1] : 0.0f;
+            ec[u] = de[rc];
+            ep[u] = rc + 1 < L ? de[rc + 1] : 0.0f;
         }
-        st8(d_h + ((size_t)b * L + r) * C + oct * 8, o);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            if (rr >= r_end) break;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                o[i] = fmaf(w[i][0], ep[u], fmaf(w[i][1], ec[u], w[i][2] * em[u]));
+                dw[i][0] = fmaf(hv[u][i], ep[u], dw[i][0]);
+                dw[i][1] = fmaf(hv[u][i], ec[u], dw[i][1]);
+                dw[i][2] = fmaf(hv[u][i], em[u], dw[i][2]);
+            }
+            st8(d_h + ((size_t)b * L + rr) * C + oct * 8, o);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -229,6 +275,17 @@ __device__ __forceinline__ void st4f(bf16* p, const float (&v)[4]) {
     *reinterpret_cast<uint2*>(p) = r;
 }
 
+// sigmoid for the backward kernels: exact expf in fp32 mode, one MUFU (tanh.approx) in bf16 mode
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_bw(float x) {
+    if (FAST) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+        return fmaf(0.5f, t, 0.5f);
+    }
+    return 1.0f / (1.0f + expf(-x));
+}
+
 struct GnBwdArgs {
     const void* raw;        // [B, L, C] conv output saved by the forward
     const float* stats;     // [B, 8, 2] (mean, rstd) saved by gw_gn_apply
@@ -277,17 +334,32 @@ __device__ __forceinline__ void load_quad(const GnBwdArgs& a, int b, int quad, i
 #define GN_NV(cc) (4 + (cc))
 
 template <typename T, bool FAST, int CC>
-__global__ void __launch_bounds__(256) gn_bwd_stats_kernel(GnBwdArgs a, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(GnBwdArgs a, float* __restrict__ partial) {
     constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     constexpr int NV = 4 + NC;
-    extern __shared__ float red[];                      // [n_tr][C * NV]
+    extern __shared__ float red[];                      // [n_tr][C * nvr]
     const int Cc = CC >= 0 ? CC : a.Cc;
     const int b = blockIdx.y, C = a.C, L = a.L;
     const int n_quad = C / 4, n_tr = 256 / n_quad;
     const int quad = threadIdx.x % n_quad, tr = threadIdx.x / n_quad;
-    QuadCoef<NCA> q;
-    load_quad<NC, NCA>(a, b, quad, Cc, q);
+    // per-thread constants: z = x*A + Bn, xh = x*rstd + xo, G = 1 + gamma
+    float cA[4], cBn[4], cG[4], rstd, xo;
+    {
+        const int cg = C / 8, g = (quad * 4) / cg;
+        const float mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+        rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+        xo = -mean * rstd;
+        const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            cA[i] = rstd * a.gn_w[c];
+            cBn[i] = a.gn_b[c] - mean * cA[i];
+            cG[i] = 1.0f + fr[c];
+        }
+    }
+    // per (b, c): 0 sum do, 1 sum do*silu(n), 2 sum dn, 3 sum dn*xh, 4+j sum do*cond_j
     float acc[4][NV];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -300,37 +372,39 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(GnBwdArgs a, float* _
     const float* cbase = a.cond + (size_t)b * L * Cc;
     const int r0 = blockIdx.x * a.rows_per_cta;
     const int r_end = min(r0 + a.rows_per_cta, L);
-    for (int r = r0 + tr; r < r_end; r += n_tr) {
-        float x[4], d[4] = {0.0f, 0.0f, 0.0f, 0.0f}, cv[NCA];
-        ld4f(raw + (size_t)r * C, x);
-        if (doa) ld4f(doa + (size_t)r * C, d);
-        if (dop && (r >> 1) < Lp) {
-            float p[4];
-            ld4f(dop + (size_t)(r >> 1) * C, p);
+    constexpr int UN = 4;                               // rows in flight per thread: every load is issued before any math
+    for (int r = r0 + tr; r < r_end; r += n_tr * UN) {
+        float x[UN][4], d[UN][4], pl[UN][4], cv[UN][NCA];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = fmaf(0.5f, p[i], d[i]);
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            const int rc = rr < r_end ? rr : r;         // clamped address; the result of a clamped row is discarded
+            ld4f(raw + (size_t)rc * C, x[u]);
+            if (doa) ld4f(doa + (size_t)rc * C, d[u]);
+            if (dop) ld4f(dop + (size_t)min(rc >> 1, Lp - 1) * C, pl[u]);
+#pragma unroll
+            for (int j = 0; j < NCA; ++j) cv[u][j] = (NC > 0 && j < Cc) ? cbase[(size_t)rc * Cc + j] : 0.0f;
         }
 #pragma unroll
-        for (int j = 0; j < NCA; ++j) cv[j] = (NC > 0 && j < Cc) ? cbase[(size_t)r * Cc + j] : 0.0f;
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            if (rr >= r_end) break;
+            const bool pool_ok = dop != nullptr && (rr >> 1) < Lp;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float z = fmaf(x[i], q.A[i], q.Bn[i]);
-            const float s = sigmoid_f<FAST>(z);
-            float h = z * s;
-            if (NC > 0) {
-                float cb = q.cC[i];
+            for (int i = 0; i < 4; ++i) {
+                float dv = doa ? d[u][i] : 0.0f;
+                if (pool_ok) dv = fmaf(0.5f, pl[u][i], dv);
+                const float z = fmaf(x[u][i], cA[i], cBn[i]);
+                const float sg = sigmoid_bw<FAST>(z);
+                const float dn = dv * cG[i] * (sg * fmaf(z, 1.0f - sg, 1.0f));
+                const float xh = fmaf(x[u][i], rstd, xo);
+                acc[i][0] += dv;
+                acc[i][1] = fmaf(dv, z * sg, acc[i][1]);
+                acc[i][2] += dn;
+                acc[i][3] = fmaf(dn, xh, acc[i][3]);
 #pragma unroll
-                for (int j = 0; j < NCA; ++j) cb = fmaf(q.cW[i][j], cv[j], cb);
-                h += cb;
+                for (int j = 0; j < NC; ++j) acc[i][4 + j] = fmaf(dv, cv[u][j], acc[i][4 + j]);
             }
-            const float dn = d[i] * q.G[i] * (s * fmaf(z, 1.0f - s, 1.0f));
-            const float xh = (x[i] - q.mean) * q.rstd;
-            acc[i][0] += d[i];
-            acc[i][1] = fmaf(d[i], h, acc[i][1]);
-            acc[i][2] += dn;
-            acc[i][3] = fmaf(dn, xh, acc[i][3]);
-#pragma unroll
-            for (int j = 0; j < NC; ++j) acc[i][4 + j] = fmaf(d[i], cv[j], acc[i][4 + j]);
         }
     }
     const int nvr = 4 + Cc;                              // values really stored per channel
@@ -342,15 +416,16 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(GnBwdArgs a, float* _
     __syncthreads();
     float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nvr;
     for (int i = threadIdx.x; i < C * nvr; i += 256) {
-        float s = 0.0f;
-        for (int t = 0; t < n_tr; ++t) s += red[(size_t)t * C * nvr + i];
-        pt[i] = s;
+        float sacc = 0.0f;
+        for (int t = 0; t < n_tr; ++t) sacc += red[(size_t)t * C * nvr + i];
+        pt[i] = sacc;
     }
 }
 
 // grid B: reduce the row-CTA partials of one sample, emit dfilm and the group means needed by the apply pass
 __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ partial, int n_rc, int C, int nvr, int L,
-                                                              const float* __restrict__ gn_w, float* __restrict__ redb,
+                                                              const float* __restrict__ gn_w, const float* __restrict__ wc,
+                                                              const float* __restrict__ bc, float* __restrict__ redb,
                                                               float* __restrict__ dfilm, long dfilm_b_stride, int film_off,
                                                               float* __restrict__ gstat) {
     extern __shared__ float sv[];                        // [C][nvr]
@@ -364,8 +439,14 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __res
     }
     __syncthreads();
     float* df = dfilm + (size_t)b * dfilm_b_stride + film_off;
+    const int Cc = nvr - 4;
     for (int c = threadIdx.x; c < C; c += 256) {
-        df[c] = sv[c * nvr + 1];                          // d gamma = sum do*h
+        float dg = sv[c * nvr + 1];                       // sum do*silu(n)
+        if (Cc > 0) {                                     // + sum do*(bc + sum_j wc_j cond_j): h = silu(n) + cond bias
+            dg = fmaf(bc[c], sv[c * nvr + 0], dg);
+            for (int j = 0; j < Cc; ++j) dg = fmaf(wc[c * Cc + j], sv[c * nvr + 4 + j], dg);
+        }
+        df[c] = dg;                                       // d gamma = sum do*h
         df[C + c] = sv[c * nvr + 0];                      // d beta  = sum do
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = C / 8;
@@ -383,12 +464,12 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __res
     }
 }
 
-// grid ceil(C/32): parameter gradients that sum over the batch
-__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restrict__ redb, int B, int C, int nvr,
-                                                           const float* __restrict__ film, long film_b_stride, int film_off,
-                                                           float* __restrict__ d_gn_w, float* __restrict__ d_gn_b,
-                                                           float* __restrict__ d_wc, float* __restrict__ d_bc) {
-    __shared__ float red[8][32][3 + BW_MAX_CC];
+// grid ceil(C/32), block 1024 = 32 channels x 32 batch lanes: parameter gradients that sum over the batch
+__global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restrict__ redb, int B, int C, int nvr,
+                                                            const float* __restrict__ film, long film_b_stride, int film_off,
+                                                            float* __restrict__ d_gn_w, float* __restrict__ d_gn_b,
+                                                            float* __restrict__ d_wc, float* __restrict__ d_bc) {
+    __shared__ float red[32][32][3 + BW_MAX_CC + 1];
     const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     const int Cc = nvr - 4;
@@ -396,7 +477,8 @@ __global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restri
 #pragma unroll
     for (int v = 0; v < 3 + BW_MAX_CC; ++v) a[v] = 0.0f;
     if (c < C) {
-        for (int b = bl; b < B; b += 8) {
+#pragma unroll 4
+        for (int b = bl; b < B; b += 32) {
             const float* p = redb + ((size_t)b * C + c) * nvr;
             const float G = 1.0f + film[(size_t)b * film_b_stride + film_off + c];
             a[0] += p[3];                                 // d gn_w
@@ -410,19 +492,16 @@ __global__ void __launch_bounds__(256) gn_bwd_param_kernel(const float* __restri
 #pragma unroll
     for (int v = 0; v < 3 + BW_MAX_CC; ++v) red[bl][cl][v] = a[v];
     __syncthreads();
-    if (bl == 0 && c < C) {
-        float s[3 + BW_MAX_CC];
+    // thread (v = bl, channel = cl) folds the 32 batch lanes of value v in fixed order
+    if (bl < 3 + Cc && c < C) {
+        float sv = 0.0f;
 #pragma unroll
-        for (int v = 0; v < 3 + BW_MAX_CC; ++v) {
-            s[v] = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 8; ++t) s[v] += red[t][cl][v];
-        }
-        d_gn_w[c] += s[0];
-        d_gn_b[c] += s[1];
-        if (Cc > 0) {
-            d_bc[c] += s[2];
-            for (int j = 0; j < Cc; ++j) d_wc[c * Cc + j] += s[3 + j];
+        for (int t = 0; t < 32; ++t) sv += red[t][cl][bl];
+        if (bl == 0) d_gn_w[c] += sv;
+        else if (bl == 1) d_gn_b[c] += sv;
+        else if (Cc > 0) {
+            if (bl == 2) d_bc[c] += sv;
+            else d_wc[c * Cc + (bl - 3)] += sv;
         }
     }
 }
@@ -449,27 +528,37 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, const fl
     T* out = d_raw + (size_t)b * L * C + quad * 4;
     const int r0 = blockIdx.x * a.rows_per_cta;
     const int r_end = min(r0 + a.rows_per_cta, L);
-    for (int r = r0 + tr; r < r_end; r += n_tr) {
-        float x[4], d[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dz[4];
-        ld4f(raw + (size_t)r * C, x);
-        if (doa) ld4f(doa + (size_t)r * C, d);
-        if (dop && (r >> 1) < Lp) {
-            float p[4];
-            ld4f(dop + (size_t)(r >> 1) * C, p);
+    constexpr int UN = 4;
+    for (int r = r0 + tr; r < r_end; r += n_tr * UN) {
+        float x[UN][4], d[UN][4], pl[UN][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = fmaf(0.5f, p[i], d[i]);
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            const int rc = rr < r_end ? rr : r;
+            ld4f(raw + (size_t)rc * C, x[u]);
+            if (doa) ld4f(doa + (size_t)rc * C, d[u]);
+            if (dop) ld4f(dop + (size_t)min(rc >> 1, Lp - 1) * C, pl[u]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float z = fmaf(x[i], q.A[i], q.Bn[i]);
-            const float s = sigmoid_f<FAST>(z);
-            const float dn = d[i] * q.G[i] * (s * fmaf(z, 1.0f - s, 1.0f));
-            const float xh = (x[i] - q.mean) * q.rstd;
-            const float v = q.rstd * (fmaf(dn, q.gw[i], -m1) - xh * m2);
-            dz[i] = round_to(v, d_raw);
-            sb[i] += dz[i];
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            if (rr >= r_end) break;
+            const bool pool_ok = dop != nullptr && (rr >> 1) < Lp;
+            float dz[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float dv = doa ? d[u][i] : 0.0f;
+                if (pool_ok) dv = fmaf(0.5f, pl[u][i], dv);
+                const float z = fmaf(x[u][i], q.A[i], q.Bn[i]);
+                const float s = sigmoid_bw<FAST>(z);
+                const float dn = dv * q.G[i] * (s * fmaf(z, 1.0f - s, 1.0f));
+                const float xh = (x[u][i] - q.mean) * q.rstd;
+                const float v = q.rstd * (fmaf(dn, q.gw[i], -m1) - xh * m2);
+                dz[i] = round_to(v, d_raw);
+                sb[i] += dz[i];
+            }
+            st4f(out + (size_t)rr * C, dz);
         }
-        st4f(out + (size_t)r * C, dz);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) red[(size_t)tr * C + quad * 4 + i] = sb[i];
@@ -484,7 +573,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, const fl
 
 static int gn_rows_per_cta(int L, int C) {
     const int n_tr = 256 / (C / 4);
-    int rows = 16 * n_tr;
+    int rows = 32 * n_tr;
     if (rows > L) rows = L;
     return rows < 1 ? 1 : rows;
 }
@@ -516,10 +605,10 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     else GNB_GO(-1);
 #undef GNB_GO
     GW_LAUNCH_CHECK();
-    gn_bwd_finalize_kernel<<<B, 256, (size_t)C * nvr * sizeof(float), st>>>(partial, n_rc, C, nvr, L, a.gn_w, redb, dfilm,
+    gn_bwd_finalize_kernel<<<B, 256, (size_t)C * nvr * sizeof(float), st>>>(partial, n_rc, C, nvr, L, a.gn_w, a.wc, a.bc, redb, dfilm,
                                                                             dfilm_b_stride, a.film_off, gstat);
     GW_LAUNCH_CHECK();
-    gn_bwd_param_kernel<<<gw_cdiv(C, 32), 256, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+    gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
                                                        d_wc, d_bc);
     GW_LAUNCH_CHECK();
     // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
@@ -723,15 +812,25 @@ extern "C" int gw_wgrad3_simt(const void* src0, int C0, int L0, int up0, const v
     return reduce_rows(scratch, (int)n_split, per, per, 1.0f, dW, 1, st);
 }
 
-// wgrad of the first conv (models.py:204): dW[co][ci][k] = sum d_raw[b,l,co] * x[b,ci,l+k-1], x fp32 [B, Cx, L]
-template <typename T>
+// wgrad of the first conv (models.py:204): dW[co][ci][k] = sum d_raw[b,l,co] * x[b,ci,l+k-1], x fp32 [B, Cx, L].
+// A thread owns one channel PAIR and walks groups of 4 consecutive rows: the 6 input samples a group needs are two
+// vector smem loads per input channel, reused by 4 rows x 3 taps x 2 channels of FMAs.
+__device__ __forceinline__ void ld2f(const float* p, float (&v)[2]) {
+    const float2 a = *reinterpret_cast<const float2*>(p);
+    v[0] = a.x; v[1] = a.y;
+}
+__device__ __forceinline__ void ld2f(const bf16* p, float (&v)[2]) {
+    const uint32_t r = *reinterpret_cast<const uint32_t*>(p);
+    v[0] = __uint_as_float(r << 16); v[1] = __uint_as_float(r & 0xffff0000u);
+}
+template <typename T, int CXM>
 __global__ void __launch_bounds__(256) wgrad_in_kernel(const float* __restrict__ x, int Cx, int L, const T* __restrict__ d_raw,
                                                        int C, float* __restrict__ partial, int rows_per_cta) {
-    extern __shared__ float sm[];
-    float* xs = sm;                               // [Cx][rows + 2]
-    const int n_tr = 256 / C;                     // C = 64 -> 4 thread rows
-    const int pitch = rows_per_cta + 2;
+    extern __shared__ __align__(16) float sm[];
+    const int pitch = rows_per_cta + 8;           // multiple of 4: xs[ci][j] = x[r0 - 1 + j], float4-aligned at j % 4 == 0
+    float* xs = sm;                               // [Cx][pitch]
     float* red = xs + Cx * pitch;                 // [n_tr][C][Cx*3]
+    const int n_cp = C / 2, n_tr = 256 / n_cp;
     const int b = blockIdx.y, r0 = blockIdx.x * rows_per_cta;
     for (int i = threadIdx.x; i < Cx * pitch; i += 256) {
         const int c = i / pitch, p = i % pitch;
@@ -739,54 +838,75 @@ __global__ void __launch_bounds__(256) wgrad_in_kernel(const float* __restrict__
         xs[i] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
     }
     __syncthreads();
-    const int co = threadIdx.x % C, tr = threadIdx.x / C;
-    float acc[16 * 3];
+    const int cp = threadIdx.x % n_cp, tr = threadIdx.x / n_cp;
+    float acc[2][CXM * 3];
 #pragma unroll
-    for (int i = 0; i < 48; ++i) acc[i] = 0.0f;
+    for (int i = 0; i < CXM * 3; ++i) { acc[0][i] = 0.0f; acc[1][i] = 0.0f; }
     const int r_end = min(rows_per_cta, L - r0);
-    for (int r = tr; r < r_end; r += n_tr) {
-        const float d = to_f(d_raw[((size_t)b * L + r0 + r) * C + co]);
+    const T* dp = d_raw + ((size_t)b * L + r0) * C + cp * 2;
+    for (int g = tr * 4; g < r_end; g += n_tr * 4) {
+        float d[4][2];
 #pragma unroll
-        for (int ci = 0; ci < 16; ++ci) {
+        for (int u = 0; u < 4; ++u) {
+            if (g + u < r_end) ld2f(dp + (size_t)(g + u) * C, d[u]);
+            else { d[u][0] = 0.0f; d[u][1] = 0.0f; }
+        }
+#pragma unroll
+        for (int ci = 0; ci < CXM; ++ci) {
             if (ci < Cx) {
+                const float4 xa = *reinterpret_cast<const float4*>(xs + ci * pitch + g);
+                const float2 xb = *reinterpret_cast<const float2*>(xs + ci * pitch + g + 4);
+                const float xv[6] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y};
 #pragma unroll
-                for (int k = 0; k < 3; ++k) acc[ci * 3 + k] = fmaf(d, xs[ci * pitch + r + k], acc[ci * 3 + k]);
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        acc[0][ci * 3 + k] = fmaf(d[u][0], xv[u + k], acc[0][ci * 3 + k]);
+                        acc[1][ci * 3 + k] = fmaf(d[u][1], xv[u + k], acc[1][ci * 3 + k]);
+                    }
             }
         }
     }
     const int nv = Cx * 3;
 #pragma unroll
-    for (int i = 0; i < 48; ++i)
-        if (i < nv) red[((size_t)tr * C + co) * nv + i] = acc[i];
+    for (int i = 0; i < CXM * 3; ++i)
+        if (i < nv) {
+            red[((size_t)tr * C + cp * 2) * nv + i] = acc[0][i];
+            red[((size_t)tr * C + cp * 2 + 1) * nv + i] = acc[1][i];
+        }
     __syncthreads();
     float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nv;
     for (int i = threadIdx.x; i < C * nv; i += 256) {
-        float s = 0.0f;
-        for (int t = 0; t < n_tr; ++t) s += red[(size_t)t * C * nv + i];
-        pt[i] = s;
+        float sacc = 0.0f;
+        for (int t = 0; t < n_tr; ++t) sacc += red[(size_t)t * C * nv + i];
+        pt[i] = sacc;
     }
 }
 
 extern "C" int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_raw, int C, int dtype, float* scratch,
                            long scratch_elems, float* dW, void* stream) {
-    GW_REQUIRE(C > 0 && 256 % C == 0 && C >= 32, "gw_wgrad_in: C=%d must divide 256", C);
+    GW_REQUIRE(C >= 64 && C <= 512 && 512 % C == 0, "gw_wgrad_in: C=%d", C);
     GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_wgrad_in: Cx=%d", Cx);
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_wgrad_in: dtype %d", dtype);
     int rows = 1024;
-    if (rows > L) rows = L;
+    if (rows > L) rows = (L + 3) & ~3;
     const int n_rc = gw_cdiv(L, rows), nv = Cx * 3;
     GW_REQUIRE((long)B * n_rc * C * nv <= scratch_elems, "gw_wgrad_in: scratch too small");
-    const int n_tr = 256 / C;
-    const size_t smem = ((size_t)Cx * (rows + 2) + (size_t)n_tr * C * nv) * sizeof(float);
+    const int n_tr = 256 / (C / 2);
+    const size_t smem = ((size_t)Cx * (rows + 8) + (size_t)n_tr * C * nv) * sizeof(float);
     dim3 grid(n_rc, B);
     cudaStream_t st = (cudaStream_t)stream;
+#define WIN_GO(TT, CXM)                                                                                               \
+    do {                                                                                                              \
+        GW_CUDA(cudaFuncSetAttribute(wgrad_in_kernel<TT, CXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        wgrad_in_kernel<TT, CXM><<<grid, 256, smem, st>>>(x, Cx, L, (const TT*)d_raw, C, scratch, rows);                \
+    } while (0)
     if (dtype == GW_F32) {
-        GW_CUDA(cudaFuncSetAttribute(wgrad_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wgrad_in_kernel<float><<<grid, 256, smem, st>>>(x, Cx, L, (const float*)d_raw, C, scratch, rows);
+        if (Cx <= 4) WIN_GO(float, 4); else if (Cx <= 8) WIN_GO(float, 8); else WIN_GO(float, 16);
     } else {
-        GW_CUDA(cudaFuncSetAttribute(wgrad_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wgrad_in_kernel<bf16><<<grid, 256, smem, st>>>(x, Cx, L, (const bf16*)d_raw, C, scratch, rows);
+        if (Cx <= 4) WIN_GO(bf16, 4); else if (Cx <= 8) WIN_GO(bf16, 8); else WIN_GO(bf16, 16);
     }
+#undef WIN_GO
     GW_LAUNCH_CHECK();
     return reduce_rows(scratch, B * n_rc, (long)C * nv, (long)C * nv, 1.0f, dW, 1, st);
 }

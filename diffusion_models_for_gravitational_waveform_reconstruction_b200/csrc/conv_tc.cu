@@ -544,27 +544,40 @@ static int build_params(const gw_conv_tc_shape* s, TcParams* P, bool halo = fals
         }
         P->n_seg[0] = n;
     } else {
-        GW_REQUIRE(s->n_src == 2 && s->C1 > 0 && s->L % 2 == 0 && s->L0 == s->L / 2,
-                   "conv_tc: pair conv needs L even, L0 = L/2 and a skip source");
+        // pair space: row m stands for output positions (2m, 2m+1), N = (phase, cout).
+        //   pair == 1: decoder conv over cat[nearest-upsample(src0), src1];
+        //   pair == 3: plain conv of ONE source evaluated in pair space (fills a 128-column tile when Cout = 64)
+        if (s->pair == 1)
+            GW_REQUIRE(s->n_src == 2 && s->C1 > 0 && s->L % 2 == 0 && s->L0 == s->L / 2,
+                       "conv_tc: pair conv needs L even, L0 = L/2 and a skip source");
+        else
+            GW_REQUIRE(s->pair == 3 && s->n_src == 1 && s->C1 == 0 && s->L % 2 == 0 && s->L0 == s->L && 2 * s->Cout <= 256,
+                       "conv_tc: pair-space plain conv needs one source, L even, Cout <= 128");
         P->rows = s->L / 2;
         const int ntot = 2 * s->Cout;
         P->n_tiles = ntot > 256 ? 2 : 1;
         P->bn = ntot / P->n_tiles;
         // candidate segments: (src, shift, col, ci0, mask phase0, mask phase1); the first one covers both phases
         struct Cand { int src, shift, col, ci0, m0, m1; };
-        Cand cand[64];
+        Cand cand[96];
         int nc = 0;
-        for (int c = 0; c < s->C0 / 64; ++c) {        // upsampled half: h[m-1], h[m], h[m+1]
-            cand[nc++] = {0, 0, c * 64, c * 64, 0b110, 0b011};
-            cand[nc++] = {0, -1, c * 64, c * 64, 0b001, 0};
-            cand[nc++] = {0, +1, c * 64, c * 64, 0, 0b100};
+        if (s->pair == 1) {
+            for (int c = 0; c < s->C0 / 64; ++c) {    // upsampled half: h[m-1], h[m], h[m+1]
+                cand[nc++] = {0, 0, c * 64, c * 64, 0b110, 0b011};
+                cand[nc++] = {0, -1, c * 64, c * 64, 0b001, 0};
+                cand[nc++] = {0, +1, c * 64, c * 64, 0, 0b100};
+            }
         }
-        for (int c = 0; c < s->C1 / 64; ++c) {        // skip half, pair view [lo = skip[2m] | hi = skip[2m+1]]
-            const int ci = s->C0 + c * 64;
-            cand[nc++] = {1, 0, c * 64, ci, 0b010, 0b001};              // S[m].lo : W1 | W0
-            cand[nc++] = {1, +1, c * 64, ci, 0, 0b100};                 // S[m+1].lo : -  | W2
-            cand[nc++] = {1, 0, s->C1 + c * 64, ci, 0b100, 0b010};      // S[m].hi : W2 | W1
-            cand[nc++] = {1, -1, s->C1 + c * 64, ci, 0b001, 0};         // S[m-1].hi : W0 | -
+        // pair view [lo = x[2m] | hi = x[2m+1]] of the skip (pair == 1, src1) or of the only source (pair == 3, src0)
+        const int psrc = s->pair == 1 ? 1 : 0;
+        const int pC = s->pair == 1 ? s->C1 : s->C0;
+        const int pci0 = s->pair == 1 ? s->C0 : 0;
+        for (int c = 0; c < pC / 64; ++c) {
+            const int ci = pci0 + c * 64;
+            cand[nc++] = {psrc, 0, c * 64, ci, 0b010, 0b001};           // S[m].lo : W1 | W0
+            cand[nc++] = {psrc, +1, c * 64, ci, 0, 0b100};              // S[m+1].lo : -  | W2
+            cand[nc++] = {psrc, 0, pC + c * 64, ci, 0b100, 0b010};      // S[m].hi : W2 | W1
+            cand[nc++] = {psrc, -1, pC + c * 64, ci, 0b001, 0};         // S[m-1].hi : W0 | -
         }
         for (int t = 0; t < P->n_tiles; ++t) {
             int n = 0;
@@ -720,7 +733,7 @@ extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const voi
     GW_REQUIRE(!v2 || P.bn >= 128, "conv_tc v2 needs bn >= 128");
     const uint32_t a_box_rows = v2 ? 130 : TC_BLOCK_M;
     CUtensorMap ta0, ta1, tw, to;
-    if (s->pair == 2) {
+    if (s->pair == 2 || s->pair == 3) {
         if ((rc = make_map3(&ta0, src0, (uint64_t)2 * s->C0, (uint64_t)P.rows, (uint64_t)s->B, 64, a_box_rows)) != GW_OK) return rc;
     } else {
         if ((rc = make_map3(&ta0, src0, (uint64_t)s->C0, (uint64_t)s->L0, (uint64_t)s->B, 64, a_box_rows)) != GW_OK) return rc;
@@ -730,7 +743,8 @@ extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const voi
         if ((rc = make_map3(&to, raw, (uint64_t)2 * s->Cout, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
     } else {
         ta1 = ta0;
-        if ((rc = make_map3(&to, raw, (uint64_t)s->Cout, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
+        const uint64_t oc = s->pair == 3 ? 2 * (uint64_t)s->Cout : (uint64_t)s->Cout;
+        if ((rc = make_map3(&to, raw, oc, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
     }
     if ((rc = make_map2(&tw, packed, (uint64_t)P.k_total, (uint64_t)P.n_tiles * P.bn, 64, 64)) != GW_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;

@@ -26,62 +26,93 @@ extern "C" int gw_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// FiLM vectors: one CTA per timestep value
+// FiLM vectors: one CTA per FILM_NB timestep values, so every weight row is read once per FILM_NB samples
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t, int time_dim, float inv_max_time_den,
+#define FILM_NB 4
+__global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t, int n, int time_dim, float inv_max_time_den,
                                                    float freq_coef, const float* __restrict__ w1,
                                                    const float* __restrict__ b1, const float* __restrict__ w2,
                                                    const float* __restrict__ b2, int base, int F, float* __restrict__ out,
                                                    float* __restrict__ aux) {
-    extern __shared__ float sm[];
-    float* emb = sm;              // [time_dim]
-    float* act = sm + time_dim;   // [base]
-    const int n = blockIdx.x;
-    const float ts = (float)t[n] / inv_max_time_den;
+    extern __shared__ __align__(16) float sm[];
+    float* emb = sm;                         // [NB][time_dim]
+    float* act = sm + FILM_NB * time_dim;    // [NB][base]
+    const int n0 = blockIdx.x * FILM_NB;
     const int half = time_dim / 2;
-    for (int i = threadIdx.x; i < time_dim; i += blockDim.x) {
+    const int na = time_dim + 3 * base;
+    for (int idx = threadIdx.x; idx < FILM_NB * time_dim; idx += blockDim.x) {
+        const int s = idx / time_dim, i = idx % time_dim;
         float v = 0.0f;
-        if (i < 2 * half) {
+        if (n0 + s < n && i < 2 * half) {
+            const float ts = (float)t[n0 + s] / inv_max_time_den;
             const int j = i < half ? i : i - half;
-            const float freq = expf((float)j * freq_coef);
-            const float a = ts * freq;
+            const float a = ts * expf((float)j * freq_coef);
             v = i < half ? sinf(a) : cosf(a);
         }
-        emb[i] = v;
-        if (aux != nullptr) aux[(size_t)n * (time_dim + 3 * base) + i] = v;
+        emb[idx] = v;
+        if (aux != nullptr && n0 + s < n) aux[(size_t)(n0 + s) * na + i] = v;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < base; j += blockDim.x) {
-        float acc = 0.0f;
+    // time_mlp Linear: one warp per output row (coalesced weight reads), FILM_NB dot products at once
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < base; j += 8) {
+        float acc[FILM_NB];
+#pragma unroll
+        for (int s = 0; s < FILM_NB; ++s) acc[s] = 0.0f;
         const float* wr = w1 + (size_t)j * time_dim;
-        for (int i = 0; i < time_dim; ++i) acc = fmaf(wr[i], emb[i], acc);
-        acc += b1[j];
-        const float ctx = silu_f<false>(acc);   // time_mlp's SiLU
-        act[j] = silu_f<false>(ctx);            // tproj's leading SiLU
-        if (aux != nullptr) {                   // saved for gw_film_bwd: [emb | pre | ctx | act]
-            float* ax = aux + (size_t)n * (time_dim + 3 * base) + time_dim;
-            ax[j] = acc;
-            ax[base + j] = ctx;
-            ax[2 * base + j] = act[j];
+        for (int i = lane; i < time_dim; i += 32) {
+            const float w = wr[i];
+#pragma unroll
+            for (int s = 0; s < FILM_NB; ++s) acc[s] = fmaf(w, emb[s * time_dim + i], acc[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < FILM_NB; ++s) acc[s] = warp_sum(acc[s]);
+        if (lane < FILM_NB) {
+            float pre = acc[0];
+#pragma unroll
+            for (int s = 1; s < FILM_NB; ++s) pre = lane == s ? acc[s] : pre;
+            pre += b1[j];
+            const float ctx = silu_f<false>(pre);     // time_mlp's SiLU
+            const float a2 = silu_f<false>(ctx);      // tproj's leading SiLU
+            act[lane * base + j] = a2;
+            if (aux != nullptr && n0 + lane < n) {    // saved for gw_film_bwd: [emb | pre | ctx | act]
+                float* ax = aux + (size_t)(n0 + lane) * na + time_dim;
+                ax[j] = pre;
+                ax[base + j] = ctx;
+                ax[2 * base + j] = a2;
+            }
         }
     }
     __syncthreads();
+    // tproj Linears: one thread per output, its weight row streamed as float4
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        float acc = 0.0f;
-        const float* wr = w2 + (size_t)f * base;
-        for (int j = 0; j < base; ++j) acc = fmaf(wr[j], act[j], acc);
-        out[(size_t)n * F + f] = acc + b2[f];
+        float acc[FILM_NB];
+#pragma unroll
+        for (int s = 0; s < FILM_NB; ++s) acc[s] = 0.0f;
+        const float4* wr = reinterpret_cast<const float4*>(w2 + (size_t)f * base);
+        for (int j4 = 0; j4 < base / 4; ++j4) {
+            const float4 w = wr[j4];
+#pragma unroll
+            for (int s = 0; s < FILM_NB; ++s) {
+                const float4 a = *reinterpret_cast<const float4*>(act + s * base + j4 * 4);
+                acc[s] = fmaf(w.x, a.x, fmaf(w.y, a.y, fmaf(w.z, a.z, fmaf(w.w, a.w, acc[s]))));
+            }
+        }
+        const float bb = b2[f];
+#pragma unroll
+        for (int s = 0; s < FILM_NB; ++s)
+            if (n0 + s < n) out[(size_t)(n0 + s) * F + f] = acc[s] + bb;
     }
 }
 
 extern "C" int gw_film_vectors(const int64_t* t, int n, int time_dim, float max_time, const float* w1, const float* b1,
                                const float* w2, const float* b2, int base, int F, float* out, float* aux, void* stream) {
-    GW_REQUIRE(n > 0 && time_dim > 0 && base > 0 && F > 0, "gw_film_vectors: bad sizes");
+    GW_REQUIRE(n > 0 && time_dim > 0 && base > 0 && F > 0 && base % 4 == 0, "gw_film_vectors: bad sizes (base must be a multiple of 4)");
     const int half = time_dim / 2;
     const float den = max_time > 1.0f ? max_time : 1.0f;                       // models.py:21
     const float coef = (float)(-(log(10000.0) / (double)(half - 1 > 1 ? half - 1 : 1)));   // models.py:25
-    size_t smem = (size_t)(time_dim + base) * sizeof(float);
-    film_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(t, time_dim, den, coef, w1, b1, w2, b2, base, F, out, aux);
+    size_t smem = (size_t)FILM_NB * (time_dim + base) * sizeof(float);
+    film_kernel<<<gw_cdiv(n, FILM_NB), 256, smem, (cudaStream_t)stream>>>(t, n, time_dim, den, coef, w1, b1, w2, b2, base, F, out, aux);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -98,13 +129,12 @@ __global__ void __launch_bounds__(256) cond_pyramid_kernel(const float* __restri
                                                            PyrArgs a) {
     const int lvl = blockIdx.y;
     const int Lo = a.len[lvl];
-    const long total = (long)B * Lo * Cc;
+    const long total = (long)B * Lo;
     const float scale = (float)L / (float)Lo;     // area_pixel_compute_scale (align_corners=False, size given)
+    // one thread per (b, l): reads are coalesced along l for every channel, the Cc outputs of a row are contiguous
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cc);
-        const long r = i / Cc;
-        const int l = (int)(r % Lo);
-        const int b = (int)(r / Lo);
+        const int l = (int)(i % Lo);
+        const int b = (int)(i / Lo);
         float src = scale * ((float)l + 0.5f) - 0.5f;
         if (src < 0.0f) src = 0.0f;
         int i0 = (int)src;
@@ -112,8 +142,9 @@ __global__ void __launch_bounds__(256) cond_pyramid_kernel(const float* __restri
         const int i1 = i0 + (i0 < L - 1 ? 1 : 0);
         const float l1 = src - (float)i0;
         const float l0 = 1.0f - l1;
-        const float* xp = x + ((size_t)b * Cx + 1 + c) * L;
-        a.out[lvl][i] = l0 * xp[i0] + l1 * xp[i1];
+        const float* xp = x + ((size_t)b * Cx + 1) * L;
+        float* op = a.out[lvl] + (size_t)i * Cc;
+        for (int c = 0; c < Cc; ++c) op[c] = l0 * xp[(size_t)c * L + i0] + l1 * xp[(size_t)c * L + i1];
     }
 }
 
@@ -126,7 +157,7 @@ extern "C" int gw_cond_pyramid(const float* x, int B, int Cx, int L, int Cc, int
         a.out[i] = level_out[i];
         a.len[i] = level_len[i];
     }
-    long total = (long)B * L * Cc;
+    long total = (long)B * L;
     int gx = (int)((total + 255) / 256);
     if (gx > 148 * 16) gx = 148 * 16;
     cond_pyramid_kernel<<<dim3(gx, n_levels), 256, 0, (cudaStream_t)stream>>>(x, B, Cx, L, Cc, a);
@@ -165,24 +196,27 @@ __device__ __forceinline__ void tile_stats_reduce(float s1, float s2, int g_loca
 
 // ------------------------------------------------------------------------------------------------
 // first conv (K1): NCL fp32 input -> channels-last raw + stats.  128 positions x C channels per CTA.
+// A thread owns one channel octet for 4 CONSECUTIVE positions: the 6 input samples they need are two vector smem
+// loads per input channel and every weight vector is reused by 4 positions (96 FMA per 8 shared-memory loads).
+// Lane = (octet, position group) so a warp's store of one position offset covers whole 128-byte rows.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ xa, const float* __restrict__ xb,
                                                       const int* __restrict__ step_ptr, int Cx, int L,
                                                       const float* __restrict__ w, const float* __restrict__ bias, int C,
                                                       T* __restrict__ raw, float* __restrict__ part, int n_part) {
-    constexpr int TP = 128;
-    extern __shared__ float sm[];
-    float* xs = sm;                              // [Cx][TP + 2]
-    float* ws = xs + ((Cx * (TP + 2) + 3) & ~3); // [Cx*3][C], 16-byte aligned for float4 reads
+    constexpr int TP = 128, XP = 136;            // XP: row pitch of xs (multiple of 4 -> float4-aligned groups)
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l0 - 1 + j]
+    float* ws = xs + Cx * XP;                    // [Cx*3][C]
     float* bs = ws + Cx * 3 * C;                 // [C]
-    float* wst = bs + C;                         // [n_iter*8 warps][2]
+    float* wst = bs + C;                         // [C/8 octets][8 warps][2]
     const int b = blockIdx.y, tile = blockIdx.x, l0 = tile * TP;
     const float* x = (step_ptr != nullptr && (*step_ptr & 1)) ? xb : xa;
-    for (int i = threadIdx.x; i < Cx * (TP + 2); i += blockDim.x) {
-        const int c = i / (TP + 2), p = i % (TP + 2);
+    for (int i = threadIdx.x; i < Cx * XP; i += blockDim.x) {
+        const int c = i / XP, p = i % XP;
         const int l = l0 + p - 1;
-        xs[i] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+        xs[i] = (p < TP + 2 && l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
     }
     for (int i = threadIdx.x; i < Cx * 3 * C; i += blockDim.x) {
         const int co = i % C, ck = i / C;        // ck = ci*3 + k
@@ -190,62 +224,65 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     }
     for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
     __syncthreads();
-    const int n_oct = C / 8;
-    const int n_iter = n_oct * TP / 256;         // = C/16
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // one (octet, position) item per thread per iteration; a warp shares the octet -> weight reads broadcast
+    const int pg = warp * 4 + (lane >> 3);       // position group: positions 4*pg .. 4*pg+3 of the tile
+    const int n_iter = C / 64;                   // 8 octets per pass
     for (int it = 0; it < n_iter; ++it) {
-        const int item = it * 256 + threadIdx.x;
-        const int pos = item % TP, oct = item / TP;
-        float acc[8];
+        const int oct = it * 8 + (lane & 7);
+        float acc[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = bs[oct * 8 + j];
-        const float* xp = xs + pos;
-        const float* wp = ws + oct * 8;
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[u][j] = bs[oct * 8 + j];
         for (int ci = 0; ci < Cx; ++ci) {
+            const float4 xa4 = *reinterpret_cast<const float4*>(xs + ci * XP + pg * 4);
+            const float2 xb2 = *reinterpret_cast<const float2*>(xs + ci * XP + pg * 4 + 4);
+            const float xv[6] = {xa4.x, xa4.y, xa4.z, xa4.w, xb2.x, xb2.y};
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float xv = xp[k];
+                const float* wp = ws + (ci * 3 + k) * C + oct * 8;
                 const float4 wa = *reinterpret_cast<const float4*>(wp);
                 const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
-                acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]);
-                acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
-                acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]);
-                acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
-                wp += C;
-            }
-            xp += TP + 2;
-        }
-        const int l = l0 + pos;
-        float s1 = 0.0f, s2 = 0.0f;
-        if (l < L) {
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[j] = round_to(acc[j], raw);
-                s1 += acc[j];
-                s2 += acc[j] * acc[j];
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(xv[u + k], wv[j], acc[u][j]);
             }
-            st8(raw + ((size_t)b * L + l) * C + oct * 8, acc);
         }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-            wst[(it * 8 + warp) * 2 + 0] = s1;
-            wst[(it * 8 + warp) * 2 + 1] = s2;
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int l = l0 + pg * 4 + u;
+            if (l < L) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[u][j] = round_to(acc[u][j], raw);
+                    s1 += acc[u][j];
+                    s2 += acc[u][j] * acc[u][j];
+                }
+                st8(raw + ((size_t)b * L + l) * C + oct * 8, acc[u]);
+            }
+        }
+        // fold the 4 position groups of the warp that share an octet (lanes differing in bits 3, 4)
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+        if (lane < 8) {
+            wst[(oct * 8 + warp) * 2 + 0] = s1;
+            wst[(oct * 8 + warp) * 2 + 1] = s2;
         }
     }
     __syncthreads();
     if (threadIdx.x < 8) {
-        // slot (it, warp) covers octet (it*256 + warp*32)/TP; group = octet*8 / (C/8)
-        const int g = threadIdx.x, cg = C / 8;
+        const int g = threadIdx.x, opg = C / 64;     // octets per GroupNorm group (C/8 channels per group)
         float a1 = 0.0f, a2 = 0.0f;
-        for (int s = 0; s < n_iter * 8; ++s) {
-            const int oct = ((s >> 3) * 256 + (s & 7) * 32) / TP;
-            if ((oct * 8) / cg == g) {
-                a1 += wst[s * 2 + 0];
-                a2 += wst[s * 2 + 1];
+        for (int o = g * opg; o < (g + 1) * opg; ++o)
+            for (int wi = 0; wi < 8; ++wi) {
+                a1 += wst[(o * 8 + wi) * 2 + 0];
+                a2 += wst[(o * 8 + wi) * 2 + 1];
             }
-        }
         float* pt = part + ((size_t)b * n_part + tile) * 16;
         pt[g * 2 + 0] = a1;
         pt[g * 2 + 1] = a2;
@@ -257,9 +294,9 @@ extern "C" int gw_conv_in(const float* x, const float* x_alt, const int* step_pt
     GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_conv_in: C=%d must be a multiple of 64 and <= 256", C);
     GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_conv_in: Cx=%d", Cx);
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv_in: dtype %d", dtype);
-    constexpr int TP = 128;
+    constexpr int TP = 128, XP = 136;
     const int n_part = gw_cdiv(L, TP);
-    size_t smem = (size_t)(((Cx * (TP + 2) + 3) & ~3) + Cx * 3 * C + C + (C / 16) * 8 * 2) * sizeof(float);
+    size_t smem = (size_t)(Cx * XP + Cx * 3 * C + C + (C / 8) * 8 * 2) * sizeof(float);
     dim3 grid(n_part, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32) {

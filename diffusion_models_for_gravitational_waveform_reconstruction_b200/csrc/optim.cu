@@ -117,33 +117,50 @@ __device__ __forceinline__ float dsilu(float x) {
     const float s = 1.0f / (1.0f + expf(-x));
     return s * (1.0f + x * (1.0f - s));
 }
-// grid F/4, block (64, 4): dW2[f, j] += sum_b dfilm[b,f] act[b,j]; db2[f] += sum_b dfilm[b,f]
-__global__ void film_bwd_w2_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux, int B, int td, int base, int F,
-                                   float* __restrict__ dW2, float* __restrict__ db2) {
-    const int f = blockIdx.x * blockDim.y + threadIdx.y;
-    if (f >= F) return;
+// grid F/4, block (base, 4, BL): thread (j, f, bl) sums the batch lane bl, bl+BL, ...; lanes are folded in fixed order
+#define FILM_BL 4
+__global__ void __launch_bounds__(1024) film_bwd_w2_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux, int B,
+                                                           int td, int base, int F, float* __restrict__ dW2,
+                                                           float* __restrict__ db2) {
+    __shared__ float red[FILM_BL][4][64 + 1];
+    __shared__ float redb[FILM_BL][4];
+    const int j = threadIdx.x, fl = threadIdx.y, bl = threadIdx.z;
+    const int f = blockIdx.x * 4 + fl;
     const int na = td + 3 * base;
-    float bsum = 0.0f;
-    for (int j = threadIdx.x; j < base; j += blockDim.x) {
-        float acc = 0.0f;
-        bsum = 0.0f;
-        for (int b = 0; b < B; ++b) {
+    float acc = 0.0f, bsum = 0.0f;
+    if (f < F) {
+#pragma unroll 8
+        for (int b = bl; b < B; b += FILM_BL) {
             const float d = dfilm[(size_t)b * F + f];
             acc = fmaf(d, aux[(size_t)b * na + td + 2 * base + j], acc);
             bsum += d;
         }
-        dW2[(size_t)f * base + j] += acc;
     }
-    if (threadIdx.x == 0) db2[f] += bsum;
+    red[bl][fl][j] = acc;
+    if (j == 0) redb[bl][fl] = bsum;
+    __syncthreads();
+    if (bl == 0 && f < F) {
+        float a = 0.0f;
+#pragma unroll
+        for (int t = 0; t < FILM_BL; ++t) a += red[t][fl][j];
+        dW2[(size_t)f * base + j] += a;
+        if (j == 0) {
+            float bb = 0.0f;
+#pragma unroll
+            for (int t = 0; t < FILM_BL; ++t) bb += redb[t][fl];
+            db2[f] += bb;
+        }
+    }
 }
-// grid B, block 256: dpre[b, j] = (sum_f dfilm[b,f] W2[f,j]) * silu'(ctx) * silu'(pre)
-__global__ void __launch_bounds__(256) film_bwd_act_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux,
-                                                           const float* __restrict__ w2, int td, int base, int F,
-                                                           float* __restrict__ dpre) {
-    extern __shared__ float sm[];           // [4][base]
+// grid B, block 1024: dpre[b, j] = (sum_f dfilm[b,f] W2[f,j]) * silu'(ctx) * silu'(pre)
+__global__ void __launch_bounds__(1024) film_bwd_act_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux,
+                                                            const float* __restrict__ w2, int td, int base, int F,
+                                                            float* __restrict__ dpre) {
+    extern __shared__ float sm[];           // [n_part][base]
     const int b = blockIdx.x;
     const int j = threadIdx.x % base, part = threadIdx.x / base, n_part = blockDim.x / base;
     float acc = 0.0f;
+#pragma unroll 8
     for (int f = part; f < F; f += n_part) acc = fmaf(dfilm[(size_t)b * F + f], w2[(size_t)f * base + j], acc);
     sm[part * base + j] = acc;
     __syncthreads();
@@ -154,29 +171,44 @@ __global__ void __launch_bounds__(256) film_bwd_act_kernel(const float* __restri
         dpre[(size_t)b * base + j] = s * dsilu(ax[base + j]) * dsilu(ax[j]);
     }
 }
-// grid base, block td: dW1[j, i] += sum_b dpre[b,j] emb[b,i]; db1[j] += sum_b dpre[b,j]
-__global__ void film_bwd_w1_kernel(const float* __restrict__ dpre, const float* __restrict__ aux, int B, int td, int base,
-                                   float* __restrict__ dW1, float* __restrict__ db1) {
-    const int j = blockIdx.x, i = threadIdx.x;
+// grid base, block (td, 8): dW1[j, i] += sum_b dpre[b,j] emb[b,i]; db1[j] += sum_b dpre[b,j]
+__global__ void __launch_bounds__(1024) film_bwd_w1_kernel(const float* __restrict__ dpre, const float* __restrict__ aux, int B,
+                                                           int td, int base, float* __restrict__ dW1, float* __restrict__ db1) {
+    extern __shared__ float sm[];           // [8][td + 1]
+    const int j = blockIdx.x, i = threadIdx.x, bl = threadIdx.y;
     const int na = td + 3 * base;
     float acc = 0.0f, bs = 0.0f;
-    for (int b = 0; b < B; ++b) {
+#pragma unroll 8
+    for (int b = bl; b < B; b += 8) {
         const float d = dpre[(size_t)b * base + j];
         acc = fmaf(d, aux[(size_t)b * na + i], acc);
         bs += d;
     }
-    dW1[(size_t)j * td + i] += acc;
-    if (i == 0) db1[j] += bs;
+    sm[bl * (td + 1) + i] = acc;
+    if (i == 0) sm[8 * (td + 1) + bl] = bs;
+    __syncthreads();
+    if (bl == 0) {
+        float a = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) a += sm[t * (td + 1) + i];
+        dW1[(size_t)j * td + i] += a;
+        if (i == 0) {
+            float bb = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) bb += sm[8 * (td + 1) + t];
+            db1[j] += bb;
+        }
+    }
 }
 extern "C" int gw_film_bwd(const float* dfilm, const float* aux, const float* w2, int B, int time_dim, int base, int F,
                            float* scratch, float* dW1, float* db1, float* dW2, float* db2, void* stream) {
-    GW_REQUIRE(B > 0 && base > 0 && base <= 256 && 256 % base == 0 && time_dim > 0 && time_dim <= 1024, "gw_film_bwd: sizes");
+    GW_REQUIRE(B > 0 && base > 0 && base <= 64 && 1024 % base == 0 && time_dim > 0 && time_dim <= 128, "gw_film_bwd: sizes (base <= 64, time_dim <= 128)");
     cudaStream_t st = (cudaStream_t)stream;
-    film_bwd_w2_kernel<<<gw_cdiv(F, 4), dim3(64, 4), 0, st>>>(dfilm, aux, B, time_dim, base, F, dW2, db2);
+    film_bwd_w2_kernel<<<gw_cdiv(F, 4), dim3(base, 4, FILM_BL), 0, st>>>(dfilm, aux, B, time_dim, base, F, dW2, db2);
     GW_LAUNCH_CHECK();
-    film_bwd_act_kernel<<<B, 256, (size_t)256 * sizeof(float), st>>>(dfilm, aux, w2, time_dim, base, F, scratch);
+    film_bwd_act_kernel<<<B, 1024, (size_t)1024 * sizeof(float), st>>>(dfilm, aux, w2, time_dim, base, F, scratch);
     GW_LAUNCH_CHECK();
-    film_bwd_w1_kernel<<<base, time_dim, 0, st>>>(scratch, aux, B, time_dim, base, dW1, db1);
+    film_bwd_w1_kernel<<<base, dim3(time_dim, 8), (size_t)(8 * (time_dim + 1) + 8) * sizeof(float), st>>>(scratch, aux, B, time_dim, base, dW1, db1);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

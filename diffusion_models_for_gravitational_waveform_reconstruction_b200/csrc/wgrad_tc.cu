@@ -170,29 +170,40 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ combine
-// mode 0 (plain):   dW[m][ci_off + n][k] += sum_split G_{k-1}[m][n]                               (m < Cout)
-// mode 1 (up/pair): A is the pair view [rows = L/2][2*Cout] of d_raw (lo = position 2r, hi = 2r+1) and X = h:
+// stage 1: fold the split-K partials [n_split][cols] into row 0 in fixed order (32 columns x 32 split lanes per block);
+// stage 2: scatter the folded G_s[m][n] into dW[co][ci][k]:
+//   mode 0 (plain):   dW[m][ci_off + n][k] += G_{k-1}[m][n]                                        (m < Cout)
+//   mode 1 (up/pair): A is the pair view [rows = L/2][2*Cout] of d_raw (lo = position 2r, hi = 2r+1) and X = h:
 //     dW[co][ci_off + n][0] += G_-1[lo] + G_0[hi];  [1] += G_0[lo] + G_0[hi];  [2] += G_0[lo] + G_+1[hi]
-__global__ void __launch_bounds__(256) wgrad_combine_kernel(const float* __restrict__ partial, WgParams P, int mode, int Cout,
+__global__ void __launch_bounds__(1024) wgrad_fold_kernel(float* __restrict__ partial, int n_split, long cols) {
+    __shared__ float red[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long c = (long)blockIdx.x * 32 + tx;
+    float a = 0.0f;
+    if (c < cols) {
+#pragma unroll 4
+        for (int r = ty; r < n_split; r += 32) a += partial[(size_t)r * cols + c];
+    }
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float sacc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) sacc += red[t][tx];
+        partial[c] = sacc;
+    }
+}
+
+__global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ folded, WgParams P, int mode, int Cout,
                                                             int Cx, int Cin_total, int ci_off, float* __restrict__ dW) {
     const long n = (long)Cout * Cx;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int co = (int)(i / Cx), nn = (int)(i % Cx);
-    const int n_tiles = P.mt * P.nt;
     const int tn = nn / P.bn, cn = nn % P.bn;
     auto G = [&](int m, int tap) {
         const int tile = (m / 128) * P.nt + tn;
-        const float* p = partial + (((size_t)tile * 3 + tap) * 128 + (m % 128)) * P.bn + cn;
-        const size_t stride = (size_t)n_tiles * 3 * 128 * P.bn;
-        float a0 = 0.0f, a1 = 0.0f;
-        int s = 0;
-        for (; s + 1 < P.n_split; s += 2) {
-            a0 += p[(size_t)s * stride];
-            a1 += p[(size_t)(s + 1) * stride];
-        }
-        if (s < P.n_split) a0 += p[(size_t)s * stride];
-        return a0 + a1;
+        return folded[(((size_t)tile * 3 + tap) * 128 + (m % 128)) * P.bn + cn];
     };
     float* d = dW + ((size_t)co * Cin_total + ci_off + nn) * 3;
     if (mode == 0) {
@@ -293,8 +304,11 @@ extern "C" int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, in
     cudaStream_t st = (cudaStream_t)stream;
     wgrad_tc_kernel<<<P.mt * P.nt * P.n_split, 192, smem, st>>>(ta, tx, P, scratch, shifted);
     GW_LAUNCH_CHECK();
+    const long cols = (long)P.mt * P.nt * 3 * 128 * P.bn;
+    wgrad_fold_kernel<<<(unsigned)((cols + 31) / 32), 1024, 0, st>>>(scratch, P.n_split, cols);
+    GW_LAUNCH_CHECK();
     const long n = (long)Cout * Cx;
-    wgrad_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, P, mode, Cout, Cx, Cin_total, ci_off, dW);
+    wgrad_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, P, mode, Cout, Cx, Cin_total, ci_off, dW);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

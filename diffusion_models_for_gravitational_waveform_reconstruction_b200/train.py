@@ -149,11 +149,12 @@ class BackwardEngine:
         if self.dgrad_impl == "tc" and tc_ok:
             # (shape, first row of the dgrad weight matrix, destination): plain conv for pooled / skip inputs, pair-sum
             # mode through the nearest upsample
+            def plain(cout_):                 # 64 output channels: evaluate in pair space to fill a 128-column tile
+                return ConvTcShape(1, 3 if (cout_ == 64 and L % 2 == 0) else 0, B, L, Cout, L, 0, cout_)
             if src1 is None:
-                parts = [(ConvTcShape(1, 0, B, L, Cout, L, 0, C0), 0, d_in0)]
+                parts = [(plain(C0), 0, d_in0)]
             else:
-                parts = [(ConvTcShape(1, 2, B, L // 2, Cout, L, 0, C0), 0, d_in0),
-                         (ConvTcShape(1, 0, B, L, Cout, L, 0, C1), C0, d_in1)]
+                parts = [(ConvTcShape(1, 2, B, L // 2, Cout, L, 0, C0), 0, d_in0), (plain(C1), C0, d_in1)]
             for pi, (shp, row0, dst) in enumerate(parts):
                 key = (li, pi, L)
                 packed = self._dg_packed.get(key)
@@ -164,7 +165,7 @@ class BackwardEngine:
                     packed = torch.empty(n, device=eng.device, dtype=torch.bfloat16)
                     self._dg_packed[key] = packed
                 check(lib.gw_conv_tc_pack(C.byref(shp), wt.data_ptr() + 4 * row0 * Cout * 3, ptr(packed), st), "conv_tc_pack(dgrad)")
-                variant = eng.tc_variant if shp.Cout >= 128 else 0
+                variant = eng.tc_variant if (shp.Cout >= 128 or shp.pair == 3) else 0
                 check(lib.gw_conv_tc(C.byref(shp), ptr(g.d_raw), None, ptr(packed), None, ptr(dst), None, variant, st),
                       f"dgrad_tc[{name}.{pi}]")
                 eng.launches += 2

@@ -114,7 +114,9 @@ typedef struct {
     int n_src;               /* 1 or 2 */
     int pair;                /* 1: decoder conv evaluated in pair space (nearest-upsample folded into the weights);
                               * 2: dgrad through the nearest upsample: src0 = d_raw [B, L0 = 2L, C0], output d_h [B, L, Cout]
-                              *    = sum of the gradients of the two upsampled positions (weights from gw_weight_dgrad) */
+                              *    = sum of the gradients of the two upsampled positions (weights from gw_weight_dgrad);
+                              * 3: plain one-source conv evaluated in pair space (L even, Cout <= 128): same result as pair = 0,
+                              *    fills a 128-column MMA tile when Cout = 64 */
     int B, L;                /* output length L (positions) */
     int C0, L0;              /* src0 channels / length (L0 = L/2 when pair) */
     int C1;                  /* src1 channels (skip), 0 if none */
@@ -137,7 +139,8 @@ int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const void* src1, co
  * buffer once per step.  `scratch` arguments are caller-owned fp32 device workspaces.
  * ===================================================================================================== */
 
-/* dst[c] (+)= scale * sum_r src[r, c]  -- fixed-order second level of every two-level reduction here */
+/* dst[c] (+)= scale * sum_r src[r, c]  -- fixed-order second level of every two-level reduction here.
+ * src is scratch: inputs taller than 256 rows are folded in place first. */
 int gw_reduce_rows(const float* src, int n_rows, long n_cols, float scale, float* dst, int accumulate, void* stream);
 
 /* masked Huber (loss_type 0, F.smooth_l1_loss beta) / MSE (1) loss of train.py:53-58, 411-421:

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--selfcond", type=int, default=0)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
     cc = 1 if a.cin == 3 else 5
     model = UNet1D(in_ch=a.cin, cond_in_ch=cc, use_selfcond=True, compute_dtype=a.dtype)
@@ -67,6 +68,8 @@ def main():
     for k, v in by_name.items():
         print(f"{k:28s} {v:9.1f} us  {100 * v / tot:5.1f} %")
     print(f"sum of C-ABI calls: {tot:.1f} us per training step (B={a.B}, L={a.L}, cin={a.cin}, dtype={a.dtype}, selfcond={a.selfcond})")
+    if a.no_graph:
+        return
     # graph-replayed step
     st.lib = st.eng.lib = st.bwd.lib = tl._lib
     for _ in range(3):

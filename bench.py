@@ -480,9 +480,7 @@ def bench_train(args, world, rank, dev, barrier, pk):
     ms, ms_e2e = float(t[0]), float(t[1])
     total = world * B * args.steps
     value, e2e = total / (ms / 1e3), total / (ms_e2e / 1e3)
-    if rank != 0:
-        return None
-    # ---- per-family rooflines: eager steps with every C-ABI call timed
+    # ---- per-family rooflines: eager steps with every C-ABI call timed (every rank runs them: the step has a collective)
     tl = TimedLib(st.lib)
     st.lib = st.eng.lib = st.bwd.lib = tl
     n_prof = 4
@@ -496,6 +494,8 @@ def bench_train(args, world, rank, dev, barrier, pk):
     tl.on = False
     st.lib = st.eng.lib = st.bwd.lib = tl._lib
     launches_per_step = (st.eng.launches - l0) / (n_prof + 1)
+    if rank != 0:
+        return None
     fams, step_ms_eager, other, t_by = family_rooflines(tl.records, model.spec, B, L, pk, n_prof, train=True)
     frac_sc = sum(seq) / len(seq)
     flops_sample = 3.0 * model.spec.conv_flops(L) + frac_sc * model.spec.conv_flops(L)

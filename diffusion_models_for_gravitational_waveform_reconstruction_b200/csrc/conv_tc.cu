@@ -54,6 +54,112 @@ struct TcParams {
     int use_base_off;
 };
 
+// ------------------------------------------------------------------------------------------------ epilogue
+// packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100a): the epilogue is issue-bound, these halve its FP instruction count
+__device__ __forceinline__ unsigned long long pk2(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a);
+    hi = __uint_as_float(b);
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Sum V per-lane values over the 32 lanes with recursive halving (V-1 + 5-log2(V) shuffles instead of 5V): afterwards the
+// total of value j sits in every lane whose top log2(V) lane bits equal j.
+template <int V>
+__device__ __forceinline__ float warp_reduce_multi(float (&v)[V], int lane) {
+    static_assert(V == 4 || V == 8 || V == 16, "V");
+    int n = V;
+#pragma unroll
+    for (int m = 16; n > 1; m >>= 1) {
+        n >>= 1;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+            if (i < n) {
+                const float send = up ? v[i] : v[i + n];
+                const float keep = up ? v[i + n] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+    }
+    float t = v[0];
+    constexpr int REST = V == 16 ? 1 : (V == 8 ? 2 : 4);      // lane bits not consumed by the halving
+#pragma unroll
+    for (int m = REST; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    return t;
+}
+
+// One epilogue unit: 64 accumulator columns of this lane's row -> +bias -> bf16 -> 128-byte-swizzled staging rows, plus
+// (optionally) the GroupNorm partial sums of the fp32 values.  CG_LOG2 = log2(channels per group) in {3, 4, 5}.
+// stat: this warp's [8 groups][2] slots (smem) for the current M tile; grp0: group of the chunk's first column.
+template <int CG_LOG2>
+__device__ __forceinline__ void epi_chunk64(uint32_t taddr, const float* sbias, bool row_ok, bool do_stats, float* stat, int grp0,
+                                            uint32_t stg, int lane) {
+    constexpr int NG = 64 >> CG_LOG2;                         // groups inside the 64 columns: 8, 4, 2
+    constexpr int PG = (1 << CG_LOG2) / 2;                    // column PAIRS per group
+    unsigned long long a1[NG], a2[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) { a1[g] = 0ull; a2[g] = 0ull; }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(hh * 32), v);
+        unsigned long long x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(sbias + hh * 32 + 2 * i);
+            x[i] = fadd2(pk2(v[2 * i], v[2 * i + 1]), bb);
+            const int g = (hh * 16 + i) / PG;
+            a1[g] = fadd2(a1[g], x[i]);
+            a2[g] = ffma2(x[i], x[i], a2[g]);
+        }
+        // 32 columns = 4 chunks of 16 B; SW128: chunk c of row r lives at chunk (c ^ (r & 7))
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t pkd[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float lo, hi;
+                upk2(x[j * 4 + q], lo, hi);
+                pkd[q] = pack_bf16x2(lo, hi);
+            }
+            const int chunk = (hh * 4 + j) ^ (lane & 7);
+            const uint32_t dst = stg + (uint32_t)lane * 128 + (uint32_t)chunk * 16;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pkd[0]), "r"(pkd[1]), "r"(pkd[2]), "r"(pkd[3])
+                         : "memory");
+        }
+    }
+    if (do_stats) {
+        float sv[2 * NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            float lo, hi;
+            upk2(a1[g], lo, hi);
+            sv[2 * g] = row_ok ? lo + hi : 0.0f;
+            upk2(a2[g], lo, hi);
+            sv[2 * g + 1] = row_ok ? lo + hi : 0.0f;
+        }
+        const float tot = warp_reduce_multi<2 * NG>(sv, lane);
+        constexpr int LOW = 2 * NG == 16 ? 2 : (2 * NG == 8 ? 4 : 8);   // lanes sharing one value
+        if ((lane & (LOW - 1)) == 0) stat[grp0 * 2 + lane / LOW] += tot;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 // CG_LOG2: log2(channels per GroupNorm group) clipped to 5 (a 32-column chunk then lies inside one group)
 template <int CG_LOG2>
@@ -162,54 +268,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 if (lane == 0) tma_wait_read<1>();
                 __syncwarp();
             }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int cc = c0 + hh * 32;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = __uint_as_float(v[i]) + s_bias[cc + i];
-                    f[i] = __bfloat162float(__float2bfloat16_rn(x));
-                }
-                // GroupNorm partial sums of the values as stored
-                constexpr int NG = 32 >> CG_LOG2 ? 32 >> CG_LOG2 : 1;     // groups inside this 32-column chunk
-                constexpr int GW = 32 / NG;
-                const int ch0 = (n_tile * P.bn + cc) % P.cout;
-if (part != nullptr) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    float s1 = 0.0f, s2 = 0.0f;
-                    if (row_ok) {
-#pragma unroll
-                        for (int i = 0; i < GW; ++i) {
-                            const float x = f[g * GW + i];
-                            s1 += x;
-                            s2 += x * x;
-                        }
-                    }
-                    s1 = warp_sum(s1);
-                    s2 = warp_sum(s2);
-                    if (lane == 0) {
-                        const int grp = (ch0 + g * GW) / cg;
-                        my_stat[grp * 2 + 0] += s1;
-                        my_stat[grp * 2 + 1] += s2;
-                    }
-                }
-                }
-                // 32 columns = 4 chunks of 16 B; SW128: chunk c of row r lives at chunk (c ^ (r & 7))
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int chunk = (hh * 4 + j) ^ (lane & 7);
-                    const uint32_t dst = stg + (uint32_t)lane * 128 + (uint32_t)chunk * 16;
-                    const uint32_t p0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-                    const uint32_t p1 = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-                    const uint32_t p2 = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-                    const uint32_t p3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
-                                 : "memory");
-                }
+            {
+                const int ch0 = (n_tile * P.bn + c0) & (P.cout - 1);
+                epi_chunk64<CG_LOG2>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, s_bias + c0, row_ok, part != nullptr,
+                                     my_stat, ch0 >> CG_LOG2, stg, lane);
             }
             fence_proxy_async();
             __syncwarp();
@@ -410,52 +472,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                         }
                         __syncwarp();
                     }
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int cc = c0 + hh * 32;
-                        uint32_t v[32];
-                        tmem_ld32(acc + (uint32_t)cc, v);
-                        float f[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float x = __uint_as_float(v[i]) + s_bias[n_tile * P.bn + cc + i];
-                            f[i] = __bfloat162float(__float2bfloat16_rn(x));
-                        }
-                        constexpr int NG = 32 >> CG_LOG2 ? 32 >> CG_LOG2 : 1;
-                        constexpr int GW = 32 / NG;
-                        const int ch0 = (n_tile * P.bn + cc) % P.cout;
-if (part != nullptr) {
-#pragma unroll
-                        for (int g = 0; g < NG; ++g) {
-                            float s1 = 0.0f, s2 = 0.0f;
-                            if (row_ok) {
-#pragma unroll
-                                for (int i = 0; i < GW; ++i) {
-                                    const float x = f[g * GW + i];
-                                    s1 += x;
-                                    s2 += x * x;
-                                }
-                            }
-                            s1 = warp_sum(s1);
-                            s2 = warp_sum(s2);
-                            if (lane == 0) {
-                                const int grp = (ch0 + g * GW) / cg;
-                                st_mt[grp * 2 + 0] += s1;
-                                st_mt[grp * 2 + 1] += s2;
-                            }
-                        }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int chunk = (hh * 4 + j) ^ (lane & 7);
-                            const uint32_t dst = stg + (uint32_t)lane * 128 + (uint32_t)chunk * 16;
-                            const uint32_t p0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-                            const uint32_t p1 = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-                            const uint32_t p2 = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-                            const uint32_t p3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
-                                         : "memory");
-                        }
+                    {
+                        const int ch0 = (n_tile * P.bn + c0) & (P.cout - 1);
+                        epi_chunk64<CG_LOG2>(acc + (uint32_t)c0, s_bias + n_tile * P.bn + c0, row_ok, part != nullptr, st_mt,
+                                             ch0 >> CG_LOG2, stg, lane);
                     }
                     fence_proxy_async();
                     __syncwarp();

@@ -197,7 +197,9 @@ def one_step_proxy_like_test_infer(model, diffusion, clean_norm: torch.Tensor, c
                                    noise: Optional[torch.Tensor] = None):
     """Single-forward x0 estimate at the t matching `target_snr` (inference.py:317-371)."""
     dev = torch.device(device)
-    t_pick = t_for_target_snr(diffusion, target_snr)
+    ab_np = diffusion.alpha_bar.detach().cpu().numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t_pick = int(np.argmin(np.abs(np.sqrt(ab_np / (1 - ab_np)) - target_snr)))      # inference.py:329-331 (unclipped)
     B = clean_norm.shape[0]
     t = torch.full((B,), t_pick, dtype=torch.long, device=dev)
     x_t, _ = diffusion.q_sample(clean_norm.to(dev), t, noise=noise)

@@ -265,6 +265,37 @@ def gen_train(M, TR, out):
     np.savez_compressed(os.path.join(out, "lr_lambda.npz"), lam=np.array(lam))
 
 
+def gen_proxy_and_helpers(M, I, TR, out):
+    """one_step_proxy_like_test_infer (inference.py:317-371), _match_batch and _sample_timesteps_stratified
+    (train.py:133-172) outputs of the unmodified reference."""
+    L = 512
+    rec = {}
+    for in_ch, cc in [(3, 1), (7, 5)]:
+        model, _ = build_model(M, in_ch, cc, seed=3)
+        diff = M.CustomDiffusion(T=1000)
+        data = synthetic_chirps(1, L, snr=10.0, seed=88)
+        cond = data["y_norm"]
+        if cc == 5:
+            cond = torch.cat([cond, gaussian((1, 4, 1), seed=8).expand(1, 4, L).contiguous() * 0.3], dim=1)
+        z = gaussian((1, 1, L), seed=99)
+        for cfg, snr in [(1.0, 2.0), (1.5, 10.0)]:
+            with NoiseInjector([z]):
+                x0 = I.one_step_proxy_like_test_infer(model, diff, data["clean_norm"], cond, 1.7, snr, torch.device("cpu"),
+                                                      in_ch, cc, True, cfg, True, cond_scale=0.9, eps_scale=1.1)
+            rec[f"proxy_c{in_ch}_cfg{cfg}_snr{snr}"] = x0.numpy()
+    a = torch.arange(6).view(3, 2).float()
+    rec["match_3_to_6"] = TR._match_batch(a, 6).numpy()
+    rec["match_3_to_7"] = TR._match_batch(a, 7).numpy()
+    rec["match_3_to_3"] = TR._match_batch(a, 3).numpy()
+    torch.manual_seed(123)
+    ts = TR._sample_timesteps_stratified(64, 500, 999, torch.device("cpu"), bins=8)
+    rec["strat_sorted_64_8"] = np.sort(ts.numpy())           # the draw itself is RNG-order dependent; the strata are not
+    edges = torch.linspace(500, 1000, 9).long().numpy()
+    rec["strat_edges"] = edges
+    rec["strat_counts"] = np.histogram(ts.numpy(), bins=edges)[0]
+    np.savez_compressed(os.path.join(out, "proxy_helpers.npz"), **rec)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
@@ -275,6 +306,7 @@ def main():
     gen_forward(M, args.out)
     gen_chains(M, I, args.out)
     gen_train(M, TR, args.out)
+    gen_proxy_and_helpers(M, I, TR, args.out)
     tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
     print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
 

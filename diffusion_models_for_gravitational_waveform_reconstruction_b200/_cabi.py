@@ -38,6 +38,7 @@ _SIGS = {
     "gw_gn_apply": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _I, _P], _I),
     "gw_final_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, C.POINTER(StepParams), _P, _P, _P, _P, _P, _P], _I),
     "gw_step_advance": ([_P, _I, _P], _I),
+    "gw_philox_normal": ([_U64, _L, C.c_uint, _I, _I, _P, _P], _I),
     "gw_q_sample": ([_P, _P, _P, _P, _P, _I, _U64, _L, C.c_uint, _F, _P, _I, _I, _I, _P], _I),
     "gw_conv_tc_packed_elems": ([C.POINTER(ConvTcShape)], _L),
     "gw_conv_tc_pack": ([C.POINTER(ConvTcShape), _P, _P, _P], _I),

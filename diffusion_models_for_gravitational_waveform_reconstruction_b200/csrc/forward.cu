@@ -647,6 +647,11 @@ struct StepArgs {
     long sample0;
 };
 
+// CTA = 256 rows of h (254 output positions + the two halo rows), 256 threads.  Phase 1: every thread first issues the
+// loads its epilogue will need (x_t taps, y, noise), then streams its share of h rows (4 x 16 B in flight, twice) and
+// leaves the three per-row tap dots in smem.  Phase 2: thread i finishes position i (CFG combine, DDIM/DDPM update).
+#define FS_ROWS 256
+#define FS_TP (FS_ROWS - 2)
 template <typename T>
 __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h, const float* __restrict__ net_a,
                                                          const float* __restrict__ net_b, int B, int Cx, int L, int C,
@@ -654,55 +659,66 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
                                                          StepArgs p, const float* __restrict__ coef,
                                                          const int* __restrict__ step_ptr, const float* __restrict__ noise,
                                                          float* __restrict__ eps_out, float* __restrict__ x0_out) {
-    constexpr int TP = 128;
-    extern __shared__ float sm[];
-    float* sw = sm;                       // [3][C] tap-major head weights for the h channels
-    float* pd = sw + 3 * C;               // [2 halves][3][TP+2] per-row partial dots
-    const int b = blockIdx.y, l0 = blockIdx.x * TP;
+    __shared__ float pd[2][3][FS_ROWS];           // [half][tap][row] partial dots
+    const int b = blockIdx.y, l0 = blockIdx.x * FS_TP;
     const int step = step_ptr != nullptr ? *step_ptr : 0;
     const float* net_in = (step & 1) ? net_b : net_a;
     float* net_out = const_cast<float*>((step & 1) ? net_a : net_b);
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
-        const int k = i / C, c = i % C;
-        sw[i] = wf[c * 3 + k];
-    }
-    __syncthreads();
     const int n_half = (p.mode == 1 && p.cfg_both) ? 2 : 1;
+    // ---- epilogue operands, requested before the h stream so their latency is hidden
+    const int l = l0 + threadIdx.x;
+    const bool mine = threadIdx.x < FS_TP && l < L;
+    float xin[2][3] = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
+    float ydc = 0.0f, zin = 0.0f;
+    const float* cf = coef != nullptr ? coef + (size_t)step * 16 : nullptr;
+    float cfv[10] = {0.0f, 1.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+    if (mine) {
+        for (int hf = 0; hf < n_half; ++hf) {
+            const float* xr = net_in + (size_t)(b + hf * B) * Cx * L;     // channel 0 = x_t
+            xin[hf][0] = l > 0 ? xr[l - 1] : 0.0f;
+            xin[hf][1] = xr[l];
+            xin[hf][2] = l + 1 < L ? xr[l + 1] : 0.0f;
+        }
+        if (p.mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) cfv[i] = cf[i];
+            if (p.dc_weight > 0.0f) ydc = p.y_dc[(size_t)b * L + l];
+            if (noise != nullptr && cfv[4] > 0.0f && cfv[7] == 0.0f) zin = noise[((size_t)(int)cfv[8] * B + b) * L + l];
+        }
+    }
+    // ---- phase 1: tap dots of rows l0-1 .. l0+254
     const int n_oct = C / 8;                 // threads per row
-    const int rows_per_pass = blockDim.x / n_oct;
+    const int rpp = 256 / n_oct;             // rows per pass
+    const int oct = threadIdx.x % n_oct, tr = threadIdx.x / n_oct;
     float w0[8], w1[8], w2[8];               // this thread's channel octet of the three taps
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int c = (threadIdx.x % n_oct) * 8 + i;
-        w0[i] = sw[c];
-        w1[i] = sw[C + c];
-        w2[i] = sw[2 * C + c];
+        const int c = oct * 8 + i;
+        w0[i] = wf[c * 3 + 0];
+        w1[i] = wf[c * 3 + 1];
+        w2[i] = wf[c * 3 + 2];
     }
     for (int hf = 0; hf < n_half; ++hf) {
-        const int bb = b + hf * B;
-        // rows r = rb + tid/n_oct for rb = 0, rpp, 2*rpp ... : issue every load first (clamped address), then reduce
-        constexpr int MAXP = 5;                                   // ceil(130 / 32) passes when C = 64; fewer rows/pass for wider C
-        const int oct = threadIdx.x % n_oct;
-        for (int rb0 = 0; rb0 < TP + 2; rb0 += rows_per_pass * MAXP) {
-            float v[MAXP][8];
+        const T* hb = h + (size_t)(b + hf * B) * L * C + oct * 8;
+        for (int r0 = 0; r0 < FS_ROWS; r0 += rpp * 4) {
+            float v[4][8];
 #pragma unroll
-            for (int ps = 0; ps < MAXP; ++ps) {
-                const int r = rb0 + ps * rows_per_pass + threadIdx.x / n_oct;
-                int l = l0 + r - 1;
-                l = l < 0 ? 0 : (l >= L ? L - 1 : l);
-                ld8(h + ((size_t)bb * L + l) * C + oct * 8, v[ps]);
+            for (int u = 0; u < 4; ++u) {
+                int lr = l0 + r0 + u * rpp + tr - 1;
+                lr = lr < 0 ? 0 : (lr >= L ? L - 1 : lr);
+                ld8(hb + (size_t)lr * C, v[u]);
             }
 #pragma unroll
-            for (int ps = 0; ps < MAXP; ++ps) {
-                const int r = rb0 + ps * rows_per_pass + threadIdx.x / n_oct;
-                const int l = l0 + r - 1;
-                const bool ok = r < TP + 2 && l >= 0 && l < L;
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * rpp + tr;
+                const int lr = l0 + r - 1;
+                const bool ok = r < FS_ROWS && lr >= 0 && lr < L;
                 float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    d0 = fmaf(v[ps][i], w0[i], d0);
-                    d1 = fmaf(v[ps][i], w1[i], d1);
-                    d2 = fmaf(v[ps][i], w2[i], d2);
+                    d0 = fmaf(v[u][i], w0[i], d0);
+                    d1 = fmaf(v[u][i], w1[i], d1);
+                    d2 = fmaf(v[u][i], w2[i], d2);
                 }
                 if (!ok) { d0 = 0.0f; d1 = 0.0f; d2 = 0.0f; }
                 for (int o = n_oct >> 1; o > 0; o >>= 1) {
@@ -710,41 +726,33 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
                     d1 += __shfl_xor_sync(0xffffffffu, d1, o);
                     d2 += __shfl_xor_sync(0xffffffffu, d2, o);
                 }
-                if (oct == 0 && r < TP + 2) {
-                    float* q = pd + hf * 3 * (TP + 2);
-                    q[r] = d0;
-                    q[(TP + 2) + r] = d1;
-                    q[2 * (TP + 2) + r] = d2;
+                if (oct == 0 && r < FS_ROWS) {
+                    pd[hf][0][r] = d0;
+                    pd[hf][1][r] = d1;
+                    pd[hf][2][r] = d2;
                 }
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x >= TP) return;
-    const int l = l0 + threadIdx.x;
-    if (l >= L) return;
+    if (!mine) return;
+    // ---- phase 2
     const float wx0 = wf[C * 3 + 0], wx1 = wf[C * 3 + 1], wx2 = wf[C * 3 + 2], bias = bf[0];
     float outv[2] = {0.0f, 0.0f};
-    float xt_c = 0.0f;
+    const float xt_c = xin[0][1];
     for (int hf = 0; hf < n_half; ++hf) {
-        const int bb = b + hf * B;
-        const float* xr = net_in + (size_t)bb * Cx * L;     // channel 0 = x_t
-        const float xm = l > 0 ? xr[l - 1] : 0.0f, xc = xr[l], xp = l + 1 < L ? xr[l + 1] : 0.0f;
-        const float* q = pd + hf * 3 * (TP + 2);
         const int r = threadIdx.x + 1;
-        float acc = q[r - 1] + q[(TP + 2) + r] + q[2 * (TP + 2) + r + 1];
-        acc += fmaf(xm, wx0, fmaf(xc, wx1, xp * wx2));
+        float acc = pd[hf][0][r - 1] + pd[hf][1][r] + pd[hf][2][r + 1];
+        acc += fmaf(xin[hf][0], wx0, fmaf(xin[hf][1], wx1, xin[hf][2] * wx2));
         outv[hf] = acc + bias;
-        if (hf == 0) xt_c = xc;
     }
     if (p.mode == 0) {
         eps_out[(size_t)b * L + l] = outv[0];
         return;
     }
-    const float* cf = coef + (size_t)step * 16;
-    const float c_s1mab = cf[0], c_sab = cf[1], c_sabp = cf[2], c_dir = cf[3], c_sig = cf[4], c_w = cf[5];
-    const int use = (int)cf[6], last = (int)cf[7], draw = (int)cf[8];
-    const float c_s1mab_cl = cf[9];
+    const float c_s1mab = cfv[0], c_sab = cfv[1], c_sabp = cfv[2], c_dir = cfv[3], c_sig = cfv[4], c_w = cfv[5];
+    const int use = (int)cfv[6], last = (int)cfv[7];
+    const float c_s1mab_cl = cfv[9];
     float o;
     if (use == 0) o = outv[0];
     else if (use == 1) o = p.cfg_both ? outv[1] : outv[0];
@@ -758,17 +766,15 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
         eps = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_sab, x0)), c_s1mab_cl);       // inference.py:468-469
     }
     if (p.dc_weight > 0.0f)
-        x0 = __fadd_rn(__fmul_rn(1.0f - p.dc_weight, x0), __fmul_rn(p.dc_weight, p.y_dc[(size_t)b * L + l]));   // inference.py:472
+        x0 = __fadd_rn(__fmul_rn(1.0f - p.dc_weight, x0), __fmul_rn(p.dc_weight, ydc));   // inference.py:472
     float xn;
     if (last) {
         xn = x0;
     } else {
         float nz = 0.0f;
         if (c_sig > 0.0f) {
-            float z;
-            if (noise != nullptr) {
-                z = noise[((size_t)draw * B + b) * L + l];
-            } else {
+            float z = zin;
+            if (noise == nullptr) {
                 float z4[4];
                 Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)(l >> 2), z4);
                 z = z4[l & 3];
@@ -798,16 +804,14 @@ extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const
     StepArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
     a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
-    constexpr int TP = 128;
-    size_t smem = (size_t)(3 * C + 2 * 3 * (TP + 2)) * sizeof(float);
-    dim3 grid(gw_cdiv(L, TP), B);
+    dim3 grid(gw_cdiv(L, FS_TP), B);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32)
-        final_step_kernel<float><<<grid, 256, smem, st>>>((const float*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
-                                                          coef, step_ptr, noise, eps_out, x0_out);
+        final_step_kernel<float><<<grid, 256, 0, st>>>((const float*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
+                                                       coef, step_ptr, noise, eps_out, x0_out);
     else
-        final_step_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
-                                                         coef, step_ptr, noise, eps_out, x0_out);
+        final_step_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
+                                                      coef, step_ptr, noise, eps_out, x0_out);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -817,6 +821,27 @@ __global__ void step_advance_kernel(int* p, int set_value) {
 }
 extern "C" int gw_step_advance(int* step_ptr, int set_value, void* stream) {
     step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_ptr, set_value);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// standard normals from the Philox stream (seed, global sample index, step): x_T of a chain is step 0
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) philox_normal_kernel(unsigned long long seed, long sample0, unsigned step, int L,
+                                                            float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (l4 >= L) return;
+    float z[4];
+    Philox::normal4(seed, (uint32_t)(sample0 + b), step, (uint32_t)(l4 >> 2), z);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (l4 + i < L) out[(size_t)b * L + l4 + i] = z[i];
+}
+extern "C" int gw_philox_normal(unsigned long long seed, long sample0, unsigned step, int B, int L, float* out, void* stream) {
+    GW_REQUIRE(B > 0 && L > 0 && out != nullptr, "gw_philox_normal: sizes");
+    philox_normal_kernel<<<dim3(gw_cdiv(gw_cdiv(L, 4), 256), B), 256, 0, (cudaStream_t)stream>>>(seed, sample0, step, L, out);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

@@ -20,8 +20,18 @@ import torch
 from .engine import SamplerPlan, build_t_schedule, cfg_weight
 from .models import CustomDiffusion, UNet1D
 
-__all__ = ["snr_from_alpha_bar", "t_for_target_snr", "_build_t_schedule", "_cfg_weight", "_reduce_to_one_channel",
+__all__ = ["philox_normal", "snr_from_alpha_bar", "t_for_target_snr", "_build_t_schedule", "_cfg_weight", "_reduce_to_one_channel",
            "one_step_proxy_like_test_infer", "ddim_sample", "make_sampler_plan"]
+
+
+def philox_normal(B: int, L: int, seed: int, sample0: int = 0, step: int = 0, device="cuda") -> torch.Tensor:
+    """[B, 1, L] standard normals of the on-device Philox stream (seed, sample0 + b, step): what `ddim_sample` starts from
+    when no `noise=` is injected (step 0), independent of batch chunking and world size."""
+    from . import _cabi
+    out = torch.empty(B, 1, L, device=device, dtype=torch.float32)
+    _cabi.check(_cabi.load().gw_philox_normal(int(seed) & (2 ** 64 - 1), int(sample0), int(step), B, L, _cabi.ptr(out),
+                                              _cabi.stream_ptr()), "philox_normal")
+    return out
 
 
 def snr_from_alpha_bar(alpha_bar: torch.Tensor) -> np.ndarray:
@@ -116,9 +126,7 @@ def ddim_sample(model, diffusion, cond_stack: torch.Tensor,
     def draw0():
         if noise is not None:
             return noise[0].to(dev).float().reshape(B, 1, L)
-        g = torch.Generator(device=dev)
-        g.manual_seed(int(seed) & (2 ** 63 - 1))
-        return torch.randn(B, 1, L, device=dev, generator=g)
+        return philox_normal(B, L, seed, sample0, 0, dev)
 
     if oracle_init and (clean_norm_311 is not None):                        # inference.py:403-406
         t0 = torch.full((B,), plan.sched[0], dtype=torch.long, device=dev)

@@ -102,6 +102,10 @@ int gw_final_step(const void* h, int dtype, const float* net_a, const float* net
 /* ---- step counter for graph replay: *step_ptr += 1 (or = value when set >= 0). */
 int gw_step_advance(int* step_ptr, int set_value, void* stream);
 
+/* ---- standard normals of the Philox stream (seed, sample0 + b, step) -> out fp32 [B, L].  The sampler's x_T
+ * (torch.randn at inference.py:409-415) is step 0 of each sample's stream; step s+1 is the noise of reverse step s. */
+int gw_philox_normal(unsigned long long seed, long sample0, unsigned step, int B, int L, float* out, void* stream);
+
 /* ---- q_sample (models.py:52-59, K19) fused with the clamp of train.py:381-382 and with network-input packing:
  * x_t = clamp(sqrt(ab[t]) * x0 + sqrt(1-ab[t]) * eps).  x0 fp32 [B, L]; t int64 [B]; eps fp32 [B, L] is READ when
  * philox == 0 and WRITTEN (generated) when philox != 0; x_t goes to net[b, 0, :] (batch stride Cx*L). */

@@ -149,3 +149,35 @@ def test_full_size_properties():
         c = _sample(model, diff, y, kw, noise=noise, use_graph=False)
         assert torch.equal(a, c), dtype
         assert torch.isfinite(a).all()
+
+
+def test_snr_sweep_tool_small():
+    """BASELINE config 5 at toy scale: sharded DDIM sweep + overlap against the oracle on a subset."""
+    import argparse
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import snr_sweep
+    a = argparse.Namespace(n=12, chunk=8, length=1024, steps=6, eta=0.0, start_t=289, dtype="fp32", seed=77, check=3)
+    res = snr_sweep.run(a)
+    assert res["check"]["rel_l2_max"] <= 1e-4 and res["check"]["overlap_vs_oracle_min"] >= 0.999999
+    a.dtype = "bf16"
+    res = snr_sweep.run(a)
+    assert res["check"]["overlap_vs_oracle_min"] >= 0.999 and res["check"]["rel_l2_max"] <= 3e-2
+
+
+def test_long_segment_forward_L16384():
+    """BASELINE config 4 shape (16384-sample segments): forward parity in both modes."""
+    import oracle
+    from weights import make_state_dict, gaussian
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.engine import ModelSpec, UNetEngine
+    sd = make_state_dict(3, 1, seed=0)
+    cfg = oracle.ModelCfg(in_ch=3, cond_in_ch=1, use_selfcond=True)
+    x = gaussian((1, 3, 16384), seed=21)
+    t = torch.tensor([700])
+    with torch.no_grad():
+        ref = oracle.unet_forward(sd, cfg, x, t)
+    spec = ModelSpec(in_ch=3, cond_in_ch=1, use_selfcond=True)
+    for dtype, impl, tol in [("fp32", "simt", 1e-5), ("bf16", "tc", 1e-2)]:
+        eng = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype=dtype, conv_impl=impl)
+        out = eng.forward(x.cuda(), t.cuda()).cpu()
+        assert float((out - ref).norm() / ref.norm()) <= tol, dtype

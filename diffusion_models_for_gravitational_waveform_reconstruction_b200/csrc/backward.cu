@@ -571,6 +571,223 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, const fl
     }
 }
 
+// ---- bf16 fast paths of the two kernels above on packed fp32x2 math (same thread mapping, same partial layouts)
+__device__ __forceinline__ void bf16x4_to_pairs(const bf16* p, f32x2 (&v)[2]) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    v[0] = pk2(r.x << 16, r.x & 0xffff0000u);
+    v[1] = pk2(r.y << 16, r.y & 0xffff0000u);
+}
+// per pair: z, silu(z) and d silu/dz from one tanh.approx per element
+__device__ __forceinline__ void silu_pair(f32x2 x, f32x2 hA, f32x2 hB, f32x2& z, f32x2& act, f32x2& dact) {
+    const f32x2 one = pkf2(1.0f, 1.0f), half2 = pkf2(0.5f, 0.5f), neg1 = pkf2(-1.0f, -1.0f);
+    const f32x2 hh = ffma2(x, hA, hB);                   // z / 2
+    z = fadd2(hh, hh);
+    float h0, h1, t0, t1;
+    upk2(hh, h0, h1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+    const f32x2 sg = ffma2(pkf2(t0, t1), half2, half2);  // sigmoid(z)
+    act = fmul2(z, sg);
+    dact = fmul2(sg, ffma2(z, ffma2(sg, neg1, one), one));   // sg * (1 + z (1 - sg))
+}
+
+template <int CC>
+__global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, float* __restrict__ partial) {
+    constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
+    constexpr int NCA = NC > 0 ? NC : 1;
+    constexpr int NV = 4 + NC;
+    extern __shared__ float red[];                      // [n_tr][C * nvr]
+    const int Cc = CC >= 0 ? CC : a.Cc;
+    const int b = blockIdx.y, C = a.C, L = a.L;
+    const int n_quad = C / 4, n_tr = 256 / n_quad;
+    const int quad = threadIdx.x % n_quad, tr = threadIdx.x / n_quad;
+    f32x2 hA[2], hB[2], G[2], rs2, xo2;
+    {
+        const int cg = C / 8, g = (quad * 4) / cg;
+        const float mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+        const float rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+        rs2 = pkf2(rstd, rstd);
+        xo2 = pkf2(-mean * rstd, -mean * rstd);
+        const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+        float a_[4], b_[4], g_[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            const float aa = rstd * a.gn_w[c];
+            a_[i] = 0.5f * aa;
+            b_[i] = 0.5f * (a.gn_b[c] - mean * aa);
+            g_[i] = 1.0f + fr[c];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+            hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+            G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+        }
+    }
+    f32x2 acc[2][NV];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[h][v] = 0ull;
+    const bf16* raw = (const bf16*)a.raw + (size_t)b * L * C + quad * 4;
+    const bf16* doa = a.do_a ? (const bf16*)a.do_a + (size_t)b * L * C + quad * 4 : nullptr;
+    const int Lp = L / 2;
+    const bf16* dop = a.do_pool ? (const bf16*)a.do_pool + (size_t)b * Lp * C + quad * 4 : nullptr;
+    const float* cbase = a.cond + (size_t)b * L * Cc;
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r_end = min(r0 + a.rows_per_cta, L);
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    constexpr int UN = 4;
+    for (int r = r0 + tr; r < r_end; r += n_tr * UN) {
+        f32x2 x[UN][2], d[UN][2], pl[UN][2];
+        float cv[UN][NCA];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            const int rc = rr < r_end ? rr : r;
+            bf16x4_to_pairs(raw + (size_t)rc * C, x[u]);
+            if (doa) bf16x4_to_pairs(doa + (size_t)rc * C, d[u]);
+            if (dop) bf16x4_to_pairs(dop + (size_t)min(rc >> 1, Lp - 1) * C, pl[u]);
+#pragma unroll
+            for (int j = 0; j < NCA; ++j) cv[u][j] = (NC > 0 && j < Cc) ? cbase[(size_t)rc * Cc + j] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            if (rr >= r_end) break;
+            const bool pool_ok = dop != nullptr && (rr >> 1) < Lp;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                f32x2 dv = doa ? d[u][h] : 0ull;
+                if (pool_ok) dv = ffma2(pl[u][h], half2, dv);
+                f32x2 z, act, dact;
+                silu_pair(x[u][h], hA[h], hB[h], z, act, dact);
+                const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
+                const f32x2 xh = ffma2(x[u][h], rs2, xo2);
+                acc[h][0] = fadd2(acc[h][0], dv);
+                acc[h][1] = ffma2(dv, act, acc[h][1]);
+                acc[h][2] = fadd2(acc[h][2], dn);
+                acc[h][3] = ffma2(dn, xh, acc[h][3]);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) acc[h][4 + j] = ffma2(dv, pkf2(cv[u][j], cv[u][j]), acc[h][4 + j]);
+            }
+        }
+    }
+    const int nvr = 4 + Cc;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (v < nvr) {
+                float lo, hi;
+                upk2(acc[h][v], lo, hi);
+                red[((size_t)tr * C + quad * 4 + 2 * h) * nvr + v] = lo;
+                red[((size_t)tr * C + quad * 4 + 2 * h + 1) * nvr + v] = hi;
+            }
+    __syncthreads();
+    float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nvr;
+    for (int i = threadIdx.x; i < C * nvr; i += 256) {
+        float sacc = 0.0f;
+        for (int t = 0; t < n_tr; ++t) sacc += red[(size_t)t * C * nvr + i];
+        pt[i] = sacc;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, const float* __restrict__ gstat,
+                                                                   bf16* __restrict__ d_raw, float* __restrict__ partial_bias) {
+    extern __shared__ float red[];                      // [n_tr][C]
+    const int b = blockIdx.y, C = a.C, L = a.L;
+    const int n_quad = C / 4, n_tr = 256 / n_quad;
+    const int quad = threadIdx.x % n_quad, tr = threadIdx.x / n_quad;
+    f32x2 hA[2], hB[2], G[2], GW2[2], rs2, xo2, nm1, nm2;
+    {
+        const int cg = C / 8, g = (quad * 4) / cg;
+        const float mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+        const float rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+        const float m1 = gstat[((size_t)b * 8 + g) * 2 + 0], m2 = gstat[((size_t)b * 8 + g) * 2 + 1];
+        rs2 = pkf2(rstd, rstd);
+        xo2 = pkf2(-mean * rstd, -mean * rstd);
+        nm1 = pkf2(-m1, -m1);
+        nm2 = pkf2(-m2, -m2);
+        const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+        float a_[4], b_[4], g_[4], w_[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            w_[i] = a.gn_w[c];
+            const float aa = rstd * w_[i];
+            a_[i] = 0.5f * aa;
+            b_[i] = 0.5f * (a.gn_b[c] - mean * aa);
+            g_[i] = 1.0f + fr[c];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+            hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+            G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+            GW2[h] = pkf2(w_[2 * h], w_[2 * h + 1]);
+        }
+    }
+    f32x2 sb[2] = {0ull, 0ull};
+    const bf16* raw = (const bf16*)a.raw + (size_t)b * L * C + quad * 4;
+    const bf16* doa = a.do_a ? (const bf16*)a.do_a + (size_t)b * L * C + quad * 4 : nullptr;
+    const int Lp = L / 2;
+    const bf16* dop = a.do_pool ? (const bf16*)a.do_pool + (size_t)b * Lp * C + quad * 4 : nullptr;
+    bf16* out = d_raw + (size_t)b * L * C + quad * 4;
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int r_end = min(r0 + a.rows_per_cta, L);
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    constexpr int UN = 4;
+    for (int r = r0 + tr; r < r_end; r += n_tr * UN) {
+        f32x2 x[UN][2], d[UN][2], pl[UN][2];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            const int rc = rr < r_end ? rr : r;
+            bf16x4_to_pairs(raw + (size_t)rc * C, x[u]);
+            if (doa) bf16x4_to_pairs(doa + (size_t)rc * C, d[u]);
+            if (dop) bf16x4_to_pairs(dop + (size_t)min(rc >> 1, Lp - 1) * C, pl[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int rr = r + u * n_tr;
+            if (rr >= r_end) break;
+            const bool pool_ok = dop != nullptr && (rr >> 1) < Lp;
+            uint2 st;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                f32x2 dv = doa ? d[u][h] : 0ull;
+                if (pool_ok) dv = ffma2(pl[u][h], half2, dv);
+                f32x2 z, act, dact;
+                silu_pair(x[u][h], hA[h], hB[h], z, act, dact);
+                const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
+                const f32x2 xh = ffma2(x[u][h], rs2, xo2);
+                const f32x2 dz = fmul2(ffma2(xh, nm2, ffma2(dn, GW2[h], nm1)), rs2);
+                sb[h] = fadd2(sb[h], dz);
+                float lo, hi;
+                upk2(dz, lo, hi);
+                if (h == 0) st.x = pack_bf16x2(lo, hi); else st.y = pack_bf16x2(lo, hi);
+            }
+            *reinterpret_cast<uint2*>(out + (size_t)rr * C) = st;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float lo, hi;
+        upk2(sb[h], lo, hi);
+        red[(size_t)tr * C + quad * 4 + 2 * h] = lo;
+        red[(size_t)tr * C + quad * 4 + 2 * h + 1] = hi;
+    }
+    __syncthreads();
+    float* pt = partial_bias + ((size_t)b * gridDim.x + blockIdx.x) * C;
+    for (int i = threadIdx.x; i < C; i += 256) {
+        float sacc = 0.0f;
+        for (int t = 0; t < n_tr; ++t) sacc += red[(size_t)t * C + i];
+        pt[i] = sacc;
+    }
+}
+
 static int gn_rows_per_cta(int L, int C) {
     const int n_tr = 256 / (C / 4);
     int rows = 32 * n_tr;
@@ -596,8 +813,13 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
 #define GNB_GO(CCV)                                                                                                       \
     do {                                                                                                                  \
-        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_kernel<T, FAST, CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
-        gn_bwd_stats_kernel<T, FAST, CCV><<<grid, 256, sm1, st>>>(a, partial);                                            \
+        if (FAST) {                                                                                                       \
+            GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_bf16_kernel<CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
+            gn_bwd_stats_bf16_kernel<CCV><<<grid, 256, sm1, st>>>(a, partial);                                            \
+        } else {                                                                                                          \
+            GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_kernel<T, FAST, CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
+            gn_bwd_stats_kernel<T, FAST, CCV><<<grid, 256, sm1, st>>>(a, partial);                                        \
+        }                                                                                                                 \
     } while (0)
     if (Cc == 0) GNB_GO(0);
     else if (Cc == 1) GNB_GO(1);
@@ -613,7 +835,8 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     GW_LAUNCH_CHECK();
     // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
 #define GNA_GO(CCV) gn_bwd_apply_kernel<T, FAST, CCV><<<grid, 256, sm2, st>>>(a, gstat, (T*)d_raw, partial)
-    if (Cc == 0) GNA_GO(0);
+    if (FAST) gn_bwd_apply_bf16_kernel<<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
+    else if (Cc == 0) GNA_GO(0);
     else if (Cc == 1) GNA_GO(1);
     else if (Cc == 5) GNA_GO(5);
     else GNA_GO(-1);

@@ -87,6 +87,38 @@ __device__ __forceinline__ float round_to(float x, const bf16*) { return __bfloa
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
 
+// ---------------------------------------------------------------- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2, sm_100a)
+// Issue-bound elementwise / epilogue code halves its FP instruction count with these; a value is two floats in a b64.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ unsigned long long pk2(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a);
+    hi = __uint_as_float(b);
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pkf2(float lo, float hi) { return pk2(__float_as_uint(lo), __float_as_uint(hi)); }
+
 // ---------------------------------------------------------------- activations
 template <bool FAST>
 __device__ __forceinline__ float sigmoid_f(float x) {

@@ -55,29 +55,6 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue
-// packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100a): the epilogue is issue-bound, these halve its FP instruction count
-__device__ __forceinline__ unsigned long long pk2(uint32_t lo, uint32_t hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
-    uint32_t a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
-    lo = __uint_as_float(a);
-    hi = __uint_as_float(b);
-}
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 // Sum V per-lane values over the 32 lanes with recursive halving (V-1 + 5-log2(V) shuffles instead of 5V): afterwards the
 // total of value j sits in every lane whose top log2(V) lane bits equal j.
 template <int V>

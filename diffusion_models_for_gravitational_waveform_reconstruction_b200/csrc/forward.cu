@@ -597,6 +597,149 @@ gn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ part, int n
     }
 }
 
+// bf16 fast path of the kernel above on packed fp32x2 math (the scalar version is issue-bound at ~60 % of HBM speed):
+//   out = silu(A x + Bn) G + (E + bc G) + sum_j (wc_j G) cond_j,   silu(z) = h + h tanh(h), h = z/2 (one MUFU per element)
+template <int CC>
+__global__ void __launch_bounds__(256, (CC == 0 || CC == 1) ? 3 : 2)
+gn_apply_bf16_kernel(const bf16* __restrict__ raw, const float* __restrict__ part, int n_part, int L, int C,
+                     const float* __restrict__ gn_w, const float* __restrict__ gn_b, const float* __restrict__ cond, int Cc_rt,
+                     const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ film, int film_off,
+                     long film_b_stride, long film_step_stride, const int* __restrict__ step_ptr, bf16* __restrict__ out,
+                     bf16* __restrict__ pooled, float* __restrict__ stats_out, int rows_per_cta) {
+    constexpr int NC = CC >= 0 ? CC : GN_MAX_CC;
+    constexpr int NCA = NC > 0 ? NC : 1;
+    constexpr int UN = (CC == 0 || CC == 1) ? 4 : 2;
+    const int Cc = CC >= 0 ? CC : Cc_rt;
+    __shared__ float s_mean[8], s_rstd[8];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = C / 8;
+    if (warp < 8) {
+        double a1 = 0.0, a2 = 0.0;
+        const float* pp = part + (size_t)b * n_part * 16 + warp * 2;
+        for (int i = lane; i < n_part; i += 32) {
+            a1 += (double)pp[(size_t)i * 16];
+            a2 += (double)pp[(size_t)i * 16 + 1];
+        }
+        a1 = warp_sum_d(a1);
+        a2 = warp_sum_d(a2);
+        if (lane == 0) {
+            const double n = (double)cg * (double)L;
+            const double mean = a1 / n;
+            double var = a2 / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+            s_mean[warp] = (float)mean;
+            s_rstd[warp] = rstd;
+            if (stats_out != nullptr && blockIdx.x == 0) {
+                stats_out[((size_t)b * 8 + warp) * 2 + 0] = (float)mean;
+                stats_out[((size_t)b * 8 + warp) * 2 + 1] = rstd;
+            }
+        }
+    }
+    __syncthreads();
+    const int n_quad = C / 4;
+    const int step = step_ptr != nullptr ? *step_ptr : 0;
+    const float* fr = film + (size_t)step * film_step_stride + (size_t)b * film_b_stride + film_off;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const bool do_pool = pooled != nullptr;
+    const int Lp = L / 2;
+    const int n_pairs = rows_per_cta / 2;
+    const int pr_stride = n_quad >= 256 ? 1 : 256 / n_quad;
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    for (int quad = threadIdx.x % n_quad; quad < n_quad; quad += 256) {
+        const int pr0 = n_quad >= 256 ? 0 : threadIdx.x / n_quad;
+        f32x2 hA[2], hB[2], G[2], E[2], W[NCA][2];
+        {
+            float a_[4], b_[4], g_[4], e_[4], w_[NCA][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = quad * 4 + i;
+                const int g = c / cg;
+                const float a = s_rstd[g] * gn_w[c];
+                a_[i] = 0.5f * a;
+                b_[i] = 0.5f * (gn_b[c] - s_mean[g] * a);
+                g_[i] = 1.0f + fr[c];
+                e_[i] = fmaf(NC > 0 ? bc[c] : 0.0f, g_[i], fr[C + c]);
+#pragma unroll
+                for (int j = 0; j < NCA; ++j) w_[j][i] = (NC > 0 && j < Cc) ? wc[c * Cc + j] * g_[i] : 0.0f;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+                hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+                G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+                E[h] = pkf2(e_[2 * h], e_[2 * h + 1]);
+#pragma unroll
+                for (int j = 0; j < NCA; ++j) W[j][h] = pkf2(w_[j][2 * h], w_[j][2 * h + 1]);
+            }
+        }
+        const bf16* rbase = raw + (size_t)b * L * C + quad * 4;
+        bf16* obase = out + (size_t)b * L * C + quad * 4;
+        const float* cbase = cond + (size_t)b * L * Cc;
+        for (int pr = pr0; pr < n_pairs; pr += pr_stride * UN) {
+            uint2 x[UN][2];
+            float cv[UN][2][NCA];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int l = r0 + 2 * (pr + u * pr_stride) + h;
+                    l = l < L ? l : L - 1;
+                    x[u][h] = *reinterpret_cast<const uint2*>(rbase + (size_t)l * C);
+                    if (NC > 0) {
+#pragma unroll
+                        for (int j = 0; j < NCA; ++j) cv[u][h][j] = (j < Cc) ? cbase[(size_t)l * Cc + j] : 0.0f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int l0 = r0 + 2 * (pr + u * pr_stride);
+                const bool pair_ok = (pr + u * pr_stride) < n_pairs;
+                f32x2 o[2][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t w2[2] = {x[u][h].x, x[u][h].y};
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const f32x2 xv = pk2(w2[q] << 16, w2[q] & 0xffff0000u);
+                        const f32x2 hh = ffma2(xv, hA[q], hB[q]);
+                        float h0, h1, t0, t1;
+                        upk2(hh, h0, h1);
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                        asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                        f32x2 v = ffma2(ffma2(hh, pkf2(t0, t1), hh), G[q], E[q]);
+                        if (NC > 0) {
+#pragma unroll
+                            for (int j = 0; j < NCA; ++j) v = ffma2(W[j][q], pkf2(cv[u][h][j], cv[u][h][j]), v);
+                        }
+                        o[h][q] = v;
+                    }
+                    if (pair_ok && l0 + h < L) {
+                        float a0, a1, a2, a3;
+                        upk2(o[h][0], a0, a1);
+                        upk2(o[h][1], a2, a3);
+                        uint2 r;
+                        r.x = pack_bf16x2(a0, a1);
+                        r.y = pack_bf16x2(a2, a3);
+                        *reinterpret_cast<uint2*>(obase + (size_t)(l0 + h) * C) = r;
+                    }
+                }
+                if (do_pool && pair_ok && l0 + 1 < L) {
+                    float a0, a1, a2, a3;
+                    upk2(fmul2(fadd2(o[0][0], o[1][0]), half2), a0, a1);
+                    upk2(fmul2(fadd2(o[0][1], o[1][1]), half2), a2, a3);
+                    uint2 r;
+                    r.x = pack_bf16x2(a0, a1);
+                    r.y = pack_bf16x2(a2, a3);
+                    *reinterpret_cast<uint2*>(pooled + ((size_t)b * Lp + (l0 >> 1)) * C + quad * 4) = r;
+                }
+            }
+        }
+    }
+}
+
 template <typename T, bool FAST>
 static int gn_apply_launch(dim3 grid, cudaStream_t st, const void* raw, const float* part, int n_part, int L, int C,
                            const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc,
@@ -632,8 +775,17 @@ extern "C" int gw_gn_apply(const void* raw, const float* part, int n_part, int B
     if (dtype == GW_F32)
         return gn_apply_launch<float, false>(grid, st, raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film, film_off,
                                              film_b_stride, film_step_stride, step_ptr, out, pooled, stats_out, rows);
-    return gn_apply_launch<bf16, true>(grid, st, raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film, film_off,
-                                       film_b_stride, film_step_stride, step_ptr, out, pooled, stats_out, rows);
+#define GNB_GO(CCV)                                                                                                         \
+    gn_apply_bf16_kernel<CCV><<<grid, 256, 0, st>>>((const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film,   \
+                                                    film_off, film_b_stride, film_step_stride, step_ptr, (bf16*)out,            \
+                                                    (bf16*)pooled, stats_out, rows)
+    if (Cc == 0) GNB_GO(0);
+    else if (Cc == 1) GNB_GO(1);
+    else if (Cc == 5) GNB_GO(5);
+    else GNB_GO(-1);
+#undef GNB_GO
+    GW_LAUNCH_CHECK();
+    return GW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

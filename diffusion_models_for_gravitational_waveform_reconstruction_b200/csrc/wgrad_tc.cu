@@ -175,22 +175,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 //   mode 0 (plain):   dW[m][ci_off + n][k] += G_{k-1}[m][n]                                        (m < Cout)
 //   mode 1 (up/pair): A is the pair view [rows = L/2][2*Cout] of d_raw (lo = position 2r, hi = 2r+1) and X = h:
 //     dW[co][ci_off + n][0] += G_-1[lo] + G_0[hi];  [1] += G_0[lo] + G_0[hi];  [2] += G_0[lo] + G_+1[hi]
-__global__ void __launch_bounds__(1024) wgrad_fold_kernel(float* __restrict__ partial, int n_split, long cols) {
-    __shared__ float red[32][33];
+__global__ void __launch_bounds__(256) wgrad_fold_kernel(float* __restrict__ partial, int n_split, long cols) {
+    // block = 32 float4 columns x 8 split lanes; each lane streams its splits with 4 loads in flight
+    __shared__ float4 red[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long c = (long)blockIdx.x * 32 + tx;
-    float a = 0.0f;
-    if (c < cols) {
+    const long c4 = (long)blockIdx.x * 32 + tx;            // float4 column
+    const long n4 = cols / 4;
+    float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (c4 < n4) {
+        const float4* p = reinterpret_cast<const float4*>(partial) + c4;
 #pragma unroll 4
-        for (int r = ty; r < n_split; r += 32) a += partial[(size_t)r * cols + c];
+        for (int r = ty; r < n_split; r += 8) {
+            const float4 v = p[(size_t)r * n4];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
     }
     red[ty][tx] = a;
     __syncthreads();
-    if (ty == 0 && c < cols) {
-        float sacc = 0.0f;
+    if (ty == 0 && c4 < n4) {
+        float4 sacc = red[0][tx];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) sacc += red[t][tx];
-        partial[c] = sacc;
+        for (int t = 1; t < 8; ++t) {
+            const float4 v = red[t][tx];
+            sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+        }
+        reinterpret_cast<float4*>(partial)[c4] = sacc;
     }
 }
 
@@ -305,7 +314,7 @@ extern "C" int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, in
     wgrad_tc_kernel<<<P.mt * P.nt * P.n_split, 192, smem, st>>>(ta, tx, P, scratch, shifted);
     GW_LAUNCH_CHECK();
     const long cols = (long)P.mt * P.nt * 3 * 128 * P.bn;
-    wgrad_fold_kernel<<<(unsigned)((cols + 31) / 32), 1024, 0, st>>>(scratch, P.n_split, cols);
+    wgrad_fold_kernel<<<(unsigned)((cols / 4 + 31) / 32), 256, 0, st>>>(scratch, P.n_split, cols);
     GW_LAUNCH_CHECK();
     const long n = (long)Cout * Cx;
     wgrad_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, P, mode, Cout, Cx, Cin_total, ci_off, dW);

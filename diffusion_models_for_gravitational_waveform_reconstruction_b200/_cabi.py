@@ -51,8 +51,8 @@ _SIGS.update({
     "gw_loss": ([_P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P], _I),
     "gw_final_bwd": ([_P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     "gw_gn_bwd_scratch_elems": ([_I, _I, _I, _I], _L),
-    "gw_gn_bwd": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P, _P,
-                   _P, _P], _I),
+    "gw_gn_bwd": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P,
+                   _P, _P, _P], _I),
     "gw_weight_dgrad": ([_P, _I, _I, _P, _P], _I),
     "gw_split_cat_grad": ([_P, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     "gw_wgrad3_simt": ([_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _L, _P, _P], _I),

@@ -151,7 +151,7 @@ extern "C" int gw_loss(const float* eps_hat, const float* eps, const float* mask
 //   eps[l] = bias + sum_k sum_c wf[c,k] * hcat[l+k-1, c]   =>   d_hcat[l,c] = sum_k wf[c,k] * d_eps[l-k+1]
 // partial layout per CTA: [(C+1)*3 + 1]  (weight grads in the reference's [c][k] order, then the bias grad)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool WRITE_DH>
 __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict__ d_eps, const T* __restrict__ h,
                                                         const float* __restrict__ net, int Cx, int L, int C,
                                                         const float* __restrict__ wf, T* __restrict__ d_h,
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            w[i][k] = wf[(oct * 8 + i) * 3 + k];
+            w[i][k] = WRITE_DH ? wf[(oct * 8 + i) * 3 + k] : 0.0f;
             dw[i][k] = 0.0f;
         }
     const float* de = d_eps + (size_t)b * L;
@@ -191,12 +191,12 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
             float o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                o[i] = fmaf(w[i][0], ep[u], fmaf(w[i][1], ec[u], w[i][2] * em[u]));
+                if (WRITE_DH) o[i] = fmaf(w[i][0], ep[u], fmaf(w[i][1], ec[u], w[i][2] * em[u]));
                 dw[i][0] = fmaf(hv[u][i], ep[u], dw[i][0]);
                 dw[i][1] = fmaf(hv[u][i], ec[u], dw[i][1]);
                 dw[i][2] = fmaf(hv[u][i], em[u], dw[i][2]);
             }
-            st8(d_h + ((size_t)b * L + rr) * C + oct * 8, o);
+            if (WRITE_DH) st8(d_h + ((size_t)b * L + rr) * C + oct * 8, o);
         }
     }
 #pragma unroll
@@ -233,18 +233,22 @@ extern "C" int gw_final_bwd(const float* d_eps, const void* h, int dtype, const 
                             const float* wf, void* d_h, float* scratch, float* d_wf, float* d_bf, void* stream) {
     GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_final_bwd: C=%d", C);
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_final_bwd: dtype %d", dtype);
-    const int rows = 512;
+    const int rows = 1024;
     dim3 grid(gw_cdiv(L, rows), B);
     const int n_tr = 256 / (C / 8);
     const size_t smem = (size_t)n_tr * C * 3 * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+#define FB_GO(TT, WR)                                                                                                  \
+    do {                                                                                                               \
+        GW_CUDA(cudaFuncSetAttribute(final_bwd_kernel<TT, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        final_bwd_kernel<TT, WR><<<grid, 256, smem, st>>>(d_eps, (const TT*)h, net, Cx, L, C, wf, (TT*)d_h, scratch, rows); \
+    } while (0)
     if (dtype == GW_F32) {
-        GW_CUDA(cudaFuncSetAttribute(final_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        final_bwd_kernel<float><<<grid, 256, smem, st>>>(d_eps, (const float*)h, net, Cx, L, C, wf, (float*)d_h, scratch, rows);
+        if (d_h) FB_GO(float, true); else FB_GO(float, false);
     } else {
-        GW_CUDA(cudaFuncSetAttribute(final_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        final_bwd_kernel<bf16><<<grid, 256, smem, st>>>(d_eps, (const bf16*)h, net, Cx, L, C, wf, (bf16*)d_h, scratch, rows);
+        if (d_h) FB_GO(bf16, true); else FB_GO(bf16, false);
     }
+#undef FB_GO
     GW_LAUNCH_CHECK();
     const int n_cta = grid.x * grid.y, nv = (C + 1) * 3 + 1;
     int rc = reduce_rows(scratch, n_cta, nv - 1, nv, 1.0f, d_wf, 1, st);
@@ -299,6 +303,8 @@ struct GnBwdArgs {
     int film_off;
     const void* do_a;       // [B, L, C] gradient wrt out, or NULL
     const void* do_pool;    // [B, L/2, C] gradient wrt the pooled output (encoders), or NULL
+    const float* do_eps;    // [B, L] fp32: the block feeds the head conv; dout[l,c] = sum_k do_w[c,k] * do_eps[l-k+1] (or NULL)
+    const float* do_w;      // [C+1, 3] head weights (models.py:230)
     int L, C, Cc;
     int rows_per_cta;
 };
@@ -591,7 +597,7 @@ __device__ __forceinline__ void silu_pair(f32x2 x, f32x2 hA, f32x2 hB, f32x2& z,
     dact = fmul2(sg, ffma2(z, ffma2(sg, neg1, one), one));   // sg * (1 + z (1 - sg))
 }
 
-template <int CC>
+template <int CC, bool HEAD>
 __global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, float* __restrict__ partial) {
     constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
@@ -638,10 +644,19 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, 
     const int r0 = blockIdx.x * a.rows_per_cta;
     const int r_end = min(r0 + a.rows_per_cta, L);
     const f32x2 half2 = pkf2(0.5f, 0.5f);
-    constexpr int UN = 4;
+    const float* de = (HEAD && a.do_eps) ? a.do_eps + (size_t)b * L : nullptr;
+    f32x2 wk[3][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+    if (HEAD && de) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                wk[k][h] = pkf2(a.do_w[(quad * 4 + 2 * h) * 3 + k], a.do_w[(quad * 4 + 2 * h + 1) * 3 + k]);
+    }
+    constexpr int UN = HEAD ? 2 : 4;
     for (int r = r0 + tr; r < r_end; r += n_tr * UN) {
         f32x2 x[UN][2], d[UN][2], pl[UN][2];
-        float cv[UN][NCA];
+        float cv[UN][NCA], ev[UN][3];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const int rr = r + u * n_tr;
@@ -649,6 +664,11 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, 
             bf16x4_to_pairs(raw + (size_t)rc * C, x[u]);
             if (doa) bf16x4_to_pairs(doa + (size_t)rc * C, d[u]);
             if (dop) bf16x4_to_pairs(dop + (size_t)min(rc >> 1, Lp - 1) * C, pl[u]);
+            if (HEAD && de) {
+                ev[u][0] = rc + 1 < L ? de[rc + 1] : 0.0f;
+                ev[u][1] = de[rc];
+                ev[u][2] = rc > 0 ? de[rc - 1] : 0.0f;
+            }
 #pragma unroll
             for (int j = 0; j < NCA; ++j) cv[u][j] = (NC > 0 && j < Cc) ? cbase[(size_t)rc * Cc + j] : 0.0f;
         }
@@ -661,6 +681,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, 
             for (int h = 0; h < 2; ++h) {
                 f32x2 dv = doa ? d[u][h] : 0ull;
                 if (pool_ok) dv = ffma2(pl[u][h], half2, dv);
+                if (HEAD && de) {
+                    const f32x2 t = ffma2(wk[1][h], pkf2(ev[u][1], ev[u][1]), fmul2(wk[2][h], pkf2(ev[u][2], ev[u][2])));
+                    dv = fadd2(dv, ffma2(wk[0][h], pkf2(ev[u][0], ev[u][0]), t));
+                }
                 f32x2 z, act, dact;
                 silu_pair(x[u][h], hA[h], hB[h], z, act, dact);
                 const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
@@ -694,6 +718,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, 
     }
 }
 
+template <bool HEAD>
 __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, const float* __restrict__ gstat,
                                                                    bf16* __restrict__ d_raw, float* __restrict__ partial_bias) {
     extern __shared__ float red[];                      // [n_tr][C]
@@ -738,9 +763,19 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
     const int r0 = blockIdx.x * a.rows_per_cta;
     const int r_end = min(r0 + a.rows_per_cta, L);
     const f32x2 half2 = pkf2(0.5f, 0.5f);
-    constexpr int UN = 4;
+    const float* de = (HEAD && a.do_eps) ? a.do_eps + (size_t)b * L : nullptr;
+    f32x2 wk[3][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+    if (HEAD && de) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                wk[k][h] = pkf2(a.do_w[(quad * 4 + 2 * h) * 3 + k], a.do_w[(quad * 4 + 2 * h + 1) * 3 + k]);
+    }
+    constexpr int UN = HEAD ? 2 : 4;
     for (int r = r0 + tr; r < r_end; r += n_tr * UN) {
         f32x2 x[UN][2], d[UN][2], pl[UN][2];
+        float ev[UN][3];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const int rr = r + u * n_tr;
@@ -748,6 +783,11 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
             bf16x4_to_pairs(raw + (size_t)rc * C, x[u]);
             if (doa) bf16x4_to_pairs(doa + (size_t)rc * C, d[u]);
             if (dop) bf16x4_to_pairs(dop + (size_t)min(rc >> 1, Lp - 1) * C, pl[u]);
+            if (HEAD && de) {
+                ev[u][0] = rc + 1 < L ? de[rc + 1] : 0.0f;
+                ev[u][1] = de[rc];
+                ev[u][2] = rc > 0 ? de[rc - 1] : 0.0f;
+            }
         }
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
@@ -759,6 +799,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
             for (int h = 0; h < 2; ++h) {
                 f32x2 dv = doa ? d[u][h] : 0ull;
                 if (pool_ok) dv = ffma2(pl[u][h], half2, dv);
+                if (HEAD && de) {
+                    const f32x2 t = ffma2(wk[1][h], pkf2(ev[u][1], ev[u][1]), fmul2(wk[2][h], pkf2(ev[u][2], ev[u][2])));
+                    dv = fadd2(dv, ffma2(wk[0][h], pkf2(ev[u][0], ev[u][0]), t));
+                }
                 f32x2 z, act, dact;
                 silu_pair(x[u][h], hA[h], hB[h], z, act, dact);
                 const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
@@ -813,9 +857,12 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
 #define GNB_GO(CCV)                                                                                                       \
     do {                                                                                                                  \
-        if (FAST) {                                                                                                       \
-            GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_bf16_kernel<CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
-            gn_bwd_stats_bf16_kernel<CCV><<<grid, 256, sm1, st>>>(a, partial);                                            \
+        if (FAST && a.do_eps != nullptr) {                                                                                \
+            GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_bf16_kernel<CCV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
+            gn_bwd_stats_bf16_kernel<CCV, true><<<grid, 256, sm1, st>>>(a, partial);                                      \
+        } else if (FAST) {                                                                                                \
+            GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_bf16_kernel<CCV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
+            gn_bwd_stats_bf16_kernel<CCV, false><<<grid, 256, sm1, st>>>(a, partial);                                     \
         } else {                                                                                                          \
             GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_kernel<T, FAST, CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
             gn_bwd_stats_kernel<T, FAST, CCV><<<grid, 256, sm1, st>>>(a, partial);                                        \
@@ -835,7 +882,8 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     GW_LAUNCH_CHECK();
     // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
 #define GNA_GO(CCV) gn_bwd_apply_kernel<T, FAST, CCV><<<grid, 256, sm2, st>>>(a, gstat, (T*)d_raw, partial)
-    if (FAST) gn_bwd_apply_bf16_kernel<<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
+    if (FAST && a.do_eps != nullptr) gn_bwd_apply_bf16_kernel<true><<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
+    else if (FAST) gn_bwd_apply_bf16_kernel<false><<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
     else if (Cc == 0) GNA_GO(0);
     else if (Cc == 1) GNA_GO(1);
     else if (Cc == 5) GNA_GO(5);
@@ -849,17 +897,19 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
 // d_conv_bias [C]; dfilm row b gets (d gamma | d beta) of this layer at film_off (overwritten).
 extern "C" int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
                          const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
-                         long film_b_stride, const void* do_a, const void* do_pool, int dtype, float* scratch, float* dfilm,
-                         long dfilm_b_stride, void* d_raw, float* d_gn_w, float* d_gn_b, float* d_wc, float* d_bc,
-                         float* d_conv_bias, void* stream) {
+                         long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
+                         int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+                         float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* stream) {
     GW_REQUIRE(C % 64 == 0 && C <= 1024 && 256 % (C / 4) == 0, "gw_gn_bwd: C=%d", C);
     GW_REQUIRE(Cc >= 0 && Cc <= BW_MAX_CC, "gw_gn_bwd: Cc=%d", Cc);
     GW_REQUIRE((cond != nullptr) == (Cc > 0), "gw_gn_bwd: cond/Cc mismatch");
-    GW_REQUIRE(do_a != nullptr || do_pool != nullptr, "gw_gn_bwd: no incoming gradient");
+    GW_REQUIRE(do_a != nullptr || do_pool != nullptr || do_eps != nullptr, "gw_gn_bwd: no incoming gradient");
+    GW_REQUIRE(do_eps == nullptr || (dtype == GW_BF16 && do_w != nullptr), "gw_gn_bwd: the head-gradient source needs bf16 and do_w");
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_gn_bwd: dtype %d", dtype);
     GnBwdArgs a;
     a.raw = raw; a.stats = stats; a.gn_w = gn_w; a.gn_b = gn_b; a.cond = cond; a.wc = wc; a.bc = bc; a.film = film;
-    a.film_b_stride = film_b_stride; a.film_off = film_off; a.do_a = do_a; a.do_pool = do_pool; a.L = L; a.C = C; a.Cc = Cc;
+    a.film_b_stride = film_b_stride; a.film_off = film_off; a.do_a = do_a; a.do_pool = do_pool; a.do_eps = do_eps; a.do_w = do_w;
+    a.L = L; a.C = C; a.Cc = Cc;
     a.rows_per_cta = gn_rows_per_cta(L, C);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32)

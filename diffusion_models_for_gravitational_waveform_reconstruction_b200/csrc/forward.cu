@@ -200,92 +200,101 @@ __device__ __forceinline__ void tile_stats_reduce(float s1, float s2, int g_loca
 // loads per input channel and every weight vector is reused by 4 positions (96 FMA per 8 shared-memory loads).
 // Lane = (octet, position group) so a warp's store of one position offset covers whole 128-byte rows.
 // ------------------------------------------------------------------------------------------------
+#define CIN_NPB 4                                 // 128-position blocks per CTA (weights / bias staged once for all of them)
 template <typename T>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ xa, const float* __restrict__ xb,
                                                       const int* __restrict__ step_ptr, int Cx, int L,
                                                       const float* __restrict__ w, const float* __restrict__ bias, int C,
                                                       T* __restrict__ raw, float* __restrict__ part, int n_part) {
-    constexpr int TP = 128, XP = 136;            // XP: row pitch of xs (multiple of 4 -> float4-aligned groups)
+    constexpr int TP = 128, XP = CIN_NPB * TP + 8;   // XP: row pitch of xs (multiple of 4 -> float4-aligned groups)
     extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l0 - 1 + j]
+    float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l00 - 1 + j]
     float* ws = xs + Cx * XP;                    // [Cx*3][C]
     float* bs = ws + Cx * 3 * C;                 // [C]
     float* wst = bs + C;                         // [C/8 octets][8 warps][2]
-    const int b = blockIdx.y, tile = blockIdx.x, l0 = tile * TP;
+    const int b = blockIdx.y, l00 = blockIdx.x * (CIN_NPB * TP);
     const float* x = (step_ptr != nullptr && (*step_ptr & 1)) ? xb : xa;
     for (int i = threadIdx.x; i < Cx * XP; i += blockDim.x) {
         const int c = i / XP, p = i % XP;
-        const int l = l0 + p - 1;
-        xs[i] = (p < TP + 2 && l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+        const int l = l00 + p - 1;
+        xs[i] = (p < CIN_NPB * TP + 2 && l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
     }
+    // weights as [ck][half][octet][4]: the 8 octet lanes of a quarter-warp read 8 consecutive float4 (no bank conflicts)
     for (int i = threadIdx.x; i < Cx * 3 * C; i += blockDim.x) {
         const int co = i % C, ck = i / C;        // ck = ci*3 + k
-        ws[i] = w[(size_t)co * Cx * 3 + ck];
+        ws[ck * C + ((co >> 2) & 1) * (C / 2) + (co >> 3) * 4 + (co & 3)] = w[(size_t)co * Cx * 3 + ck];
     }
     for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pg = warp * 4 + (lane >> 3);       // position group: positions 4*pg .. 4*pg+3 of the tile
+    const int pg = warp * 4 + (lane >> 3);       // position group: positions 4*pg .. 4*pg+3 of a block
     const int n_iter = C / 64;                   // 8 octets per pass
-    for (int it = 0; it < n_iter; ++it) {
-        const int oct = it * 8 + (lane & 7);
-        float acc[4][8];
+    for (int blk = 0; blk < CIN_NPB; ++blk) {
+        const int l0 = l00 + blk * TP;
+        const int tile = blockIdx.x * CIN_NPB + blk;
+        if (l0 >= L) break;
+        for (int it = 0; it < n_iter; ++it) {
+            const int oct = it * 8 + (lane & 7);
+            float acc[4][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[u][j] = bs[oct * 8 + j];
-        for (int ci = 0; ci < Cx; ++ci) {
-            const float4 xa4 = *reinterpret_cast<const float4*>(xs + ci * XP + pg * 4);
-            const float2 xb2 = *reinterpret_cast<const float2*>(xs + ci * XP + pg * 4 + 4);
-            const float xv[6] = {xa4.x, xa4.y, xa4.z, xa4.w, xb2.x, xb2.y};
+                for (int j = 0; j < 8; ++j) acc[u][j] = bs[oct * 8 + j];
+            for (int ci = 0; ci < Cx; ++ci) {
+                const float* xr = xs + ci * XP + blk * TP + pg * 4;
+                const float4 xa4 = *reinterpret_cast<const float4*>(xr);
+                const float2 xb2 = *reinterpret_cast<const float2*>(xr + 4);
+                const float xv[6] = {xa4.x, xa4.y, xa4.z, xa4.w, xb2.x, xb2.y};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float* wp = ws + (ci * 3 + k) * C + oct * 8;
-                const float4 wa = *reinterpret_cast<const float4*>(wp);
-                const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                for (int k = 0; k < 3; ++k) {
+                    const float* wp = ws + (ci * 3 + k) * C + oct * 4;
+                    const float4 wa = *reinterpret_cast<const float4*>(wp);
+                    const float4 wb = *reinterpret_cast<const float4*>(wp + C / 2);
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                    for (int u = 0; u < 4; ++u)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(xv[u + k], wv[j], acc[u][j]);
-            }
-        }
-        float s1 = 0.0f, s2 = 0.0f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int l = l0 + pg * 4 + u;
-            if (l < L) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    acc[u][j] = round_to(acc[u][j], raw);
-                    s1 += acc[u][j];
-                    s2 += acc[u][j] * acc[u][j];
+                        for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(xv[u + k], wv[j], acc[u][j]);
                 }
-                st8(raw + ((size_t)b * L + l) * C + oct * 8, acc[u]);
+            }
+            float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int l = l0 + pg * 4 + u;
+                if (l < L) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc[u][j] = round_to(acc[u][j], raw);
+                        s1 += acc[u][j];
+                        s2 += acc[u][j] * acc[u][j];
+                    }
+                    st8(raw + ((size_t)b * L + l) * C + oct * 8, acc[u]);
+                }
+            }
+            // fold the 4 position groups of the warp that share an octet (lanes differing in bits 3, 4)
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+            if (lane < 8) {
+                wst[(oct * 8 + warp) * 2 + 0] = s1;
+                wst[(oct * 8 + warp) * 2 + 1] = s2;
             }
         }
-        // fold the 4 position groups of the warp that share an octet (lanes differing in bits 3, 4)
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-        if (lane < 8) {
-            wst[(oct * 8 + warp) * 2 + 0] = s1;
-            wst[(oct * 8 + warp) * 2 + 1] = s2;
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            const int g = threadIdx.x, opg = C / 64;     // octets per GroupNorm group (C/8 channels per group)
+            float a1 = 0.0f, a2 = 0.0f;
+            for (int o = g * opg; o < (g + 1) * opg; ++o)
+                for (int wi = 0; wi < 8; ++wi) {
+                    a1 += wst[(o * 8 + wi) * 2 + 0];
+                    a2 += wst[(o * 8 + wi) * 2 + 1];
+                }
+            float* pt = part + ((size_t)b * n_part + tile) * 16;
+            pt[g * 2 + 0] = a1;
+            pt[g * 2 + 1] = a2;
         }
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        const int g = threadIdx.x, opg = C / 64;     // octets per GroupNorm group (C/8 channels per group)
-        float a1 = 0.0f, a2 = 0.0f;
-        for (int o = g * opg; o < (g + 1) * opg; ++o)
-            for (int wi = 0; wi < 8; ++wi) {
-                a1 += wst[(o * 8 + wi) * 2 + 0];
-                a2 += wst[(o * 8 + wi) * 2 + 1];
-            }
-        float* pt = part + ((size_t)b * n_part + tile) * 16;
-        pt[g * 2 + 0] = a1;
-        pt[g * 2 + 1] = a2;
+        __syncthreads();
     }
 }
 
@@ -294,10 +303,10 @@ extern "C" int gw_conv_in(const float* x, const float* x_alt, const int* step_pt
     GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_conv_in: C=%d must be a multiple of 64 and <= 256", C);
     GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_conv_in: Cx=%d", Cx);
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv_in: dtype %d", dtype);
-    constexpr int TP = 128, XP = 136;
+    constexpr int TP = 128, XP = CIN_NPB * TP + 8;
     const int n_part = gw_cdiv(L, TP);
     size_t smem = (size_t)(Cx * XP + Cx * 3 * C + C + (C / 8) * 8 * 2) * sizeof(float);
-    dim3 grid(n_part, B);
+    dim3 grid(gw_cdiv(L, CIN_NPB * TP), B);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32) {
         GW_CUDA(cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

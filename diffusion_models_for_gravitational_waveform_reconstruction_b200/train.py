@@ -193,7 +193,7 @@ class BackwardEngine:
         Cc = sp.cond_in_ch
         nl = 2 * d + 1
 
-        def gn_bwd(li: int, do_a: Optional[Tensor], do_pool: Optional[Tensor]) -> None:
+        def gn_bwd(li: int, do_a: Optional[Tensor], do_pool: Optional[Tensor], do_eps: Optional[Tensor] = None) -> None:
             n = names[li]
             lvl = li if li <= d else 2 * d - li
             _, Ll, Cl = ws.raw[li].shape
@@ -201,19 +201,27 @@ class BackwardEngine:
                                 ptr(eng.p[n + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
                                 ptr(eng.p[cnames[li] + ".weight"]) if Cc > 0 else None,
                                 ptr(eng.p[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(g.film), foffs[li], sp.film_dim,
-                                ptr(do_a), ptr(do_pool), eng.gw_dtype, ptr(g.scratch), ptr(g.dfilm), sp.film_dim, ptr(g.d_raw),
+                                ptr(do_a), ptr(do_pool), ptr(do_eps), ptr(eng.wf) if do_eps is not None else None, eng.gw_dtype,
+                                ptr(g.scratch), ptr(g.dfilm), sp.film_dim, ptr(g.d_raw),
                                 ptr(grads[n + ".1.weight"]), ptr(grads[n + ".1.bias"]),
                                 ptr(grads[cnames[li] + ".weight"]) if Cc > 0 else None,
                                 ptr(grads[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(grads[n + ".0.bias"]), st),
                   f"gn_bwd[{n}]")
             eng.launches += 5
 
+        # bf16: the gradient wrt the last block's output is a 3-tap outer product of d_eps and final.weight, formed on the fly
+        # inside gw_gn_bwd (no d_h tensor); fp32-exact mode materialises it
+        fuse_head = eng.dtype == "bf16"
         check(lib.gw_final_bwd(ptr(d_eps), ptr(ws.out[nl - 1]), eng.gw_dtype, ptr(net), B, Cx, L, lc[-1], ptr(eng.wf),
-                               ptr(g.d_h[0]), ptr(g.scratch), ptr(grads["final.weight"]), ptr(grads["final.bias"]), st), "final_bwd")
+                               None if fuse_head else ptr(g.d_h[0]), ptr(g.scratch), ptr(grads["final.weight"]),
+                               ptr(grads["final.bias"]), st), "final_bwd")
         eng.launches += 3
         cur = 0
         for li in range(nl - 1, d, -1):                       # decoders, last first
-            gn_bwd(li, g.d_h[cur], None)
+            if li == nl - 1 and fuse_head:
+                gn_bwd(li, None, None, d_eps)
+            else:
+                gn_bwd(li, g.d_h[cur], None)
             self._conv_bwd(li, ws, g, grads, g.d_h[cur ^ 1], g.d_skip[2 * d - li])
             cur ^= 1
         gn_bwd(d, g.d_h[cur], None)                           # mid

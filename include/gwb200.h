@@ -153,22 +153,23 @@ int gw_reduce_rows(const float* src, int n_rows, long n_cols, float scale, float
 int gw_loss(const float* eps_hat, const float* eps, const float* mask, const float* wt, int B, int L, int loss_type,
             float beta, float grad_scale, float* per_sample, float* loss, float* d_eps, void* stream);
 
-/* backward of the head conv final(cat[h, x_t]) (models.py:230): d_h [B, L, C] (dtype); d_wf [(C+1)*3], d_bf [1] accumulated.
+/* backward of the head conv final(cat[h, x_t]) (models.py:230): d_h [B, L, C] (dtype) or NULL (then the last block's
+ * gw_gn_bwd forms it on the fly from do_eps / do_w); d_wf [(C+1)*3], d_bf [1] accumulated.
  * scratch >= B * ceil(L/512) * ((C+1)*3 + 1) floats. */
 int gw_final_bwd(const float* d_eps, const void* h, int dtype, const float* net, int B, int Cx, int L, int C,
                  const float* wf, void* d_h, float* scratch, float* d_wf, float* d_bf, void* stream);
 
 /* backward of GroupNorm -> SiLU -> +cond 1x1 conv -> FiLM (-> avg_pool) of one block (models.py:165-173, 188-193, 208).
  * Incoming gradient = do_a [B, L, C] (wrt the block output; NULL if none) + avg_pool backward of do_pool [B, L/2, C]
- * (NULL if none).  stats = (mean, rstd) [B, 8, 2] saved by gw_gn_apply.  Writes d_raw [B, L, C] (gradient wrt the conv
+ * (NULL if none) + (bf16 only) the head-conv gradient sum_k do_w[c,k] * do_eps[b, l-k+1] (do_eps fp32 [B, L], do_w = final.weight).  stats = (mean, rstd) [B, 8, 2] saved by gw_gn_apply.  Writes d_raw [B, L, C] (gradient wrt the conv
  * output), dfilm[b, film_off + (0..C | C..2C)] = (d gamma | d beta); accumulates d_gn_w, d_gn_b, d_bc, d_conv_bias [C],
  * d_wc [C, Cc].  scratch >= gw_gn_bwd_scratch_elems(B, L, C, Cc) floats. */
 long gw_gn_bwd_scratch_elems(int B, int L, int C, int Cc);
 int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
               const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
-              long film_b_stride, const void* do_a, const void* do_pool, int dtype, float* scratch, float* dfilm,
-              long dfilm_b_stride, void* d_raw, float* d_gn_w, float* d_gn_b, float* d_wc, float* d_bc,
-              float* d_conv_bias, void* stream);
+              long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
+              int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+              float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* stream);
 
 /* exact-mode conv backward.  gw_weight_dgrad: wt[ci][co][k] = w[co][ci][2-k], so that dgrad = gw_conv3_simt(d_raw, wt).
  * gw_split_cat_grad: gradient of cat[nearest-upsample x2 (h), skip]: d_h [B, L0, C0] (pair sums), d_skip [B, L, C1].

@@ -257,3 +257,26 @@ def test_one_step_proxy_matches_reference_golden(golden_dir):
             x0 = inf.one_step_proxy_like_test_infer(m, d, data["clean_norm"].cuda(), cond.cuda(), 1.7, snr, "cuda", in_ch, cc, True,
                                                     cfg, True, cond_scale=0.9, eps_scale=1.1, noise=z.cuda())
             assert rel_l2(x0, torch.from_numpy(g[f"proxy_c{in_ch}_cfg{cfg}_snr{snr}"])) <= 1e-5, (in_ch, cfg, snr)
+
+
+@pytest.mark.parametrize("L,cd,tol", [(250, "fp32", 5e-5), (250, "bf16", 5e-2), (1000, "bf16", 5e-2)])
+def test_backward_odd_lengths(L, cd, tol):
+    """Lengths not divisible by 8: pad/trim in the decoder (models.py:218-220, 227-229), avg_pool1d dropping the last sample,
+    a left-padded (ragged) sample mask -- the exact CUDA-core kernels take over where the tcgen05 fast path needs even lengths."""
+    in_ch, cc, B = 3, 1, 3
+    sd, clean, cond, mask, t, eps, drop = _case(in_ch, cc, B, L)
+    mask[2, :, : L // 3] = 0.0
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True)
+    ab = oracle.alpha_bar_from_betas(oracle.cosine_beta_schedule(1000))
+    loss_o, grads_o, _ = oracle.train_step(sd, cfg, ab, clean_norm=clean, cond_stack=cond, mask=mask, t=t, eps=eps, drop=drop,
+                                           selfcond=True)
+    m, st = _stepper(sd, in_ch, cc, B, L, cd)
+    st.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+    st.step(selfcond=True, t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=False)
+    torch.cuda.synchronize()
+    assert abs(float(st.loss) - float(loss_o)) <= max(tol, 2e-6) * abs(float(loss_o))
+    grads = st.layout.views(st.flat_g)
+    tot = float(torch.cat([g.reshape(-1) for g in grads_o.values()]).norm())
+    for k, go in grads_o.items():
+        err = float((grads[k].cpu().double() - go.double()).norm())
+        assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))

@@ -34,6 +34,7 @@ _SIGS = {
     "gw_film_vectors": ([_P, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _P, _P], _I),
     "gw_cond_pyramid": ([_P, _I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_P), _P], _I),
     "gw_conv_in": ([_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P], _I),
+    "gw_conv_in_block": ([_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _I, _P, _P], _I),
     "gw_conv3_simt": ([_P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P], _I),
     "gw_gn_apply": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _I, _P], _I),
     "gw_final_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, C.POINTER(StepParams), _P, _P, _P, _P, _P, _P], _I),

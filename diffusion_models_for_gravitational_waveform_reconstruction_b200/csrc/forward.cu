@@ -3,6 +3,7 @@
 // Reference call sites are cited in include/gwb200.h.
 #include "common.cuh"
 #include "../../include/gwb200.h"
+#include <string.h>
 
 // ------------------------------------------------------------------------------------------------
 // error text
@@ -201,32 +202,88 @@ __device__ __forceinline__ void tile_stats_reduce(float s1, float s2, int g_loca
 // Lane = (octet, position group) so a warp's store of one position offset covers whole 128-byte rows.
 // ------------------------------------------------------------------------------------------------
 #define CIN_NPB 4                                 // 128-position blocks per CTA (weights / bias staged once for all of them)
-template <typename T>
+#define CIN_MAX_CC 8
+// Arguments of the fused first block (MODE 2): GroupNorm-apply + SiLU + cond 1x1 conv + FiLM + pool on the recomputed conv
+struct ConvInApply {
+    const float* part_in;     // [B, n_part, 8, 2] partial sums written by the MODE 1 pass
+    const float* gn_w;
+    const float* gn_b;
+    const float* wc;          // [C, Cc]
+    const float* bc;          // [C]
+    const float* film;        // FiLM rows; this block's (gamma | beta) at film_off
+    long film_b_stride, film_step_stride;
+    int film_off, Cc;
+    void* out;                // [B, L, C]
+    void* pooled;             // [B, L/2, C] or NULL
+};
+
+// MODE 0: raw conv output + GroupNorm partial sums (training keeps raw for the backward pass)
+// MODE 1: partial sums only (nothing but 64 B per tile is written)
+// MODE 2: recompute the conv and apply the rest of the block -> out (+ pooled); the 134 MB raw tensor never exists.
+template <typename T, int MODE>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ xa, const float* __restrict__ xb,
                                                       const int* __restrict__ step_ptr, int Cx, int L,
                                                       const float* __restrict__ w, const float* __restrict__ bias, int C,
-                                                      T* __restrict__ raw, float* __restrict__ part, int n_part) {
+                                                      T* __restrict__ raw, float* __restrict__ part, int n_part, ConvInApply ap) {
     constexpr int TP = 128, XP = CIN_NPB * TP + 8;   // XP: row pitch of xs (multiple of 4 -> float4-aligned groups)
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l00 - 1 + j]
     float* ws = xs + Cx * XP;                    // [Cx*3][C]
     float* bs = ws + Cx * 3 * C;                 // [C]
     float* wst = bs + C;                         // [C/8 octets][8 warps][2]
+    float* cf = wst + (C / 8) * 8 * 2;           // MODE 2: [4 + Cc][C] coefficient rows (A, Bn, G, E', W'_j), split-octet layout
+    __shared__ float s_mean[8], s_rstd[8];
     const int b = blockIdx.y, l00 = blockIdx.x * (CIN_NPB * TP);
-    const float* x = (step_ptr != nullptr && (*step_ptr & 1)) ? xb : xa;
+    const int step = step_ptr != nullptr ? *step_ptr : 0;
+    const float* x = (step & 1) ? xb : xa;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < Cx * XP; i += blockDim.x) {
         const int c = i / XP, p = i % XP;
         const int l = l00 + p - 1;
         xs[i] = (p < CIN_NPB * TP + 2 && l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
     }
     // weights as [ck][half][octet][4]: the 8 octet lanes of a quarter-warp read 8 consecutive float4 (no bank conflicts)
+    auto split = [C](int co) { return ((co >> 2) & 1) * (C / 2) + (co >> 3) * 4 + (co & 3); };
     for (int i = threadIdx.x; i < Cx * 3 * C; i += blockDim.x) {
         const int co = i % C, ck = i / C;        // ck = ci*3 + k
-        ws[ck * C + ((co >> 2) & 1) * (C / 2) + (co >> 3) * 4 + (co & 3)] = w[(size_t)co * Cx * 3 + ck];
+        ws[ck * C + split(co)] = w[(size_t)co * Cx * 3 + ck];
     }
     for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
+    if (MODE == 2) {
+        // finish the GroupNorm statistics of this sample (biased variance, eps 1e-5; models.py:154-158)
+        const int cg = C / 8;
+        if (warp < 8) {
+            double a1 = 0.0, a2 = 0.0;
+            const float* pp = ap.part_in + (size_t)b * n_part * 16 + warp * 2;
+            for (int i = lane; i < n_part; i += 32) {
+                a1 += (double)pp[(size_t)i * 16];
+                a2 += (double)pp[(size_t)i * 16 + 1];
+            }
+            a1 = warp_sum_d(a1);
+            a2 = warp_sum_d(a2);
+            if (lane == 0) {
+                const double n = (double)cg * (double)L;
+                const double mean = a1 / n;
+                double var = a2 / n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_mean[warp] = (float)mean;
+                s_rstd[warp] = (float)(1.0 / sqrt(var + 1e-5));
+            }
+        }
+        __syncthreads();
+        const float* fr = ap.film + (size_t)step * ap.film_step_stride + (size_t)b * ap.film_b_stride + ap.film_off;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g = c / cg, sc = split(c);
+            const float a = s_rstd[g] * ap.gn_w[c];
+            const float G = 1.0f + fr[c];
+            cf[0 * C + sc] = a;
+            cf[1 * C + sc] = ap.gn_b[c] - s_mean[g] * a;
+            cf[2 * C + sc] = G;
+            cf[3 * C + sc] = ap.Cc > 0 ? fmaf(ap.bc[c], G, fr[C + c]) : fr[C + c];       // (h + bc) G + beta, folded
+            for (int j = 0; j < ap.Cc; ++j) cf[(4 + j) * C + sc] = ap.wc[c * ap.Cc + j] * G;
+        }
+    }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pg = warp * 4 + (lane >> 3);       // position group: positions 4*pg .. 4*pg+3 of a block
     const int n_iter = C / 64;                   // 8 octets per pass
     for (int blk = 0; blk < CIN_NPB; ++blk) {
@@ -236,6 +293,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
         for (int it = 0; it < n_iter; ++it) {
             const int oct = it * 8 + (lane & 7);
             float acc[4][8];
+            float cvv[MODE == 2 ? CIN_MAX_CC : 1][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -245,6 +303,15 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                 const float4 xa4 = *reinterpret_cast<const float4*>(xr);
                 const float2 xb2 = *reinterpret_cast<const float2*>(xr + 4);
                 const float xv[6] = {xa4.x, xa4.y, xa4.z, xa4.w, xb2.x, xb2.y};
+                if (MODE == 2) {
+                    // input channels 1 .. Cc ARE the conditioning channels at full resolution (models.py:188-193 at level 0)
+#pragma unroll
+                    for (int j = 0; j < CIN_MAX_CC; ++j)
+                        if (ci == 1 + j && j < ap.Cc) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) cvv[j][u] = xv[u + 1];
+                        }
+                }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const float* wp = ws + (ci * 3 + k) * C + oct * 4;
@@ -257,6 +324,65 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                         for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(xv[u + k], wv[j], acc[u][j]);
                 }
             }
+            if (MODE == 2) {
+                T* outp = (T*)ap.out;
+                T* poolp = (T*)ap.pooled;
+                float cA[8], cB[8], cG[8], cE[8];
+#pragma unroll
+                for (int hsel = 0; hsel < 2; ++hsel) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(cf + 0 * C + hsel * (C / 2) + oct * 4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(cf + 1 * C + hsel * (C / 2) + oct * 4);
+                    const float4 g4 = *reinterpret_cast<const float4*>(cf + 2 * C + hsel * (C / 2) + oct * 4);
+                    const float4 e4 = *reinterpret_cast<const float4*>(cf + 3 * C + hsel * (C / 2) + oct * 4);
+                    cA[hsel * 4 + 0] = a4.x; cA[hsel * 4 + 1] = a4.y; cA[hsel * 4 + 2] = a4.z; cA[hsel * 4 + 3] = a4.w;
+                    cB[hsel * 4 + 0] = b4.x; cB[hsel * 4 + 1] = b4.y; cB[hsel * 4 + 2] = b4.z; cB[hsel * 4 + 3] = b4.w;
+                    cG[hsel * 4 + 0] = g4.x; cG[hsel * 4 + 1] = g4.y; cG[hsel * 4 + 2] = g4.z; cG[hsel * 4 + 3] = g4.w;
+                    cE[hsel * 4 + 0] = e4.x; cE[hsel * 4 + 1] = e4.y; cE[hsel * 4 + 2] = e4.z; cE[hsel * 4 + 3] = e4.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float z = fmaf(acc[u][j], cA[j], cB[j]);
+                        const float sl = sizeof(T) == 2 ? silu_tanh(z) : silu_f<false>(z);
+                        acc[u][j] = fmaf(sl, cG[j], cE[j]);
+                    }
+                for (int jc = 0; jc < ap.Cc; ++jc) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(cf + (4 + jc) * C + oct * 4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(cf + (4 + jc) * C + C / 2 + oct * 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float cu[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                    for (int j = 0; j < CIN_MAX_CC; ++j)
+                        if (j == jc) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) cu[u] = cvv[j][u];
+                        }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(wv[j], cu[u], acc[u][j]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int l = l0 + pg * 4 + u;
+                    if (l < L) st8(outp + ((size_t)b * L + l) * C + oct * 8, acc[u]);
+                }
+                if (poolp != nullptr) {
+                    const int Lp = L / 2;
+#pragma unroll
+                    for (int u = 0; u < 4; u += 2) {
+                        const int l = l0 + pg * 4 + u;
+                        if (l + 1 < L) {
+                            float pv[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pv[j] = 0.5f * (acc[u][j] + acc[u + 1][j]);
+                            st8(poolp + ((size_t)b * Lp + (l >> 1)) * C + oct * 8, pv);
+                        }
+                    }
+                }
+                continue;
+            }
             float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -264,11 +390,11 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                 if (l < L) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        acc[u][j] = round_to(acc[u][j], raw);
+                        if (MODE == 0) acc[u][j] = round_to(acc[u][j], raw);
                         s1 += acc[u][j];
                         s2 += acc[u][j] * acc[u][j];
                     }
-                    st8(raw + ((size_t)b * L + l) * C + oct * 8, acc[u]);
+                    if (MODE == 0) st8(raw + ((size_t)b * L + l) * C + oct * 8, acc[u]);
                 }
             }
             // fold the 4 position groups of the warp that share an octet (lanes differing in bits 3, 4)
@@ -281,6 +407,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                 wst[(oct * 8 + warp) * 2 + 1] = s2;
             }
         }
+        if (MODE == 2) continue;
         __syncthreads();
         if (threadIdx.x < 8) {
             const int g = threadIdx.x, opg = C / 64;     // octets per GroupNorm group (C/8 channels per group)
@@ -298,25 +425,52 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     }
 }
 
+template <typename T, int MODE>
+static int conv_in_launch(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
+                          const float* bias, int C, void* raw, float* part, const ConvInApply& ap, cudaStream_t st) {
+    constexpr int TP = 128, XP = CIN_NPB * TP + 8;
+    const int n_part = gw_cdiv(L, TP);
+    size_t smem = (size_t)(Cx * XP + Cx * 3 * C + C + (C / 8) * 8 * 2 + (MODE == 2 ? (4 + CIN_MAX_CC) * C : 0)) * sizeof(float);
+    dim3 grid(gw_cdiv(L, CIN_NPB * TP), B);
+    GW_CUDA(cudaFuncSetAttribute(conv_in_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_in_kernel<T, MODE><<<grid, 256, smem, st>>>(x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, C, (T*)raw, part, n_part, ap);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
 extern "C" int gw_conv_in(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
                           const float* bias, int C, void* raw, int dtype, float* part, void* stream) {
     GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_conv_in: C=%d must be a multiple of 64 and <= 256", C);
     GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_conv_in: Cx=%d", Cx);
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv_in: dtype %d", dtype);
-    constexpr int TP = 128, XP = CIN_NPB * TP + 8;
-    const int n_part = gw_cdiv(L, TP);
-    size_t smem = (size_t)(Cx * XP + Cx * 3 * C + C + (C / 8) * 8 * 2) * sizeof(float);
-    dim3 grid(gw_cdiv(L, CIN_NPB * TP), B);
+    ConvInApply ap;
+    memset(&ap, 0, sizeof(ap));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == GW_F32) {
-        GW_CUDA(cudaFuncSetAttribute(conv_in_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_in_kernel<float><<<grid, 256, smem, st>>>(x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, C, (float*)raw, part, n_part);
-    } else {
-        GW_CUDA(cudaFuncSetAttribute(conv_in_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_in_kernel<bf16><<<grid, 256, smem, st>>>(x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, C, (bf16*)raw, part, n_part);
-    }
-    GW_LAUNCH_CHECK();
-    return GW_OK;
+    if (dtype == GW_F32) return conv_in_launch<float, 0>(x, x_alt, step_ptr, B, Cx, L, w, bias, C, raw, part, ap, st);
+    return conv_in_launch<bf16, 0>(x, x_alt, step_ptr, B, Cx, L, w, bias, C, raw, part, ap, st);
+}
+
+// Fused first block for inference (no raw tensor): pass 1 = GroupNorm partial sums of the conv output, pass 2 = recompute
+// the conv and apply GroupNorm + SiLU + cond 1x1 conv + FiLM (+ avg_pool) -> out [B, L, C], pooled [B, L/2, C] or NULL.
+// part: scratch fp32 [B, ceil(L/128), 8, 2].  The conditioning channels are x[:, 1:1+Cc] themselves (level-0 interpolation
+// is the identity), so no conditioning pyramid is read.
+extern "C" int gw_conv_in_block(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
+                                const float* bias, int C, const float* gn_w, const float* gn_b, int Cc, const float* wc,
+                                const float* bc, const float* film, int film_off, long film_b_stride, long film_step_stride,
+                                void* out, void* pooled, int dtype, float* part, void* stream) {
+    GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_conv_in_block: C=%d must be a multiple of 64 and <= 256", C);
+    GW_REQUIRE(Cx >= 1 && Cx <= 16 && Cc >= 0 && Cc <= CIN_MAX_CC && 1 + Cc <= Cx, "gw_conv_in_block: Cx=%d Cc=%d", Cx, Cc);
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv_in_block: dtype %d", dtype);
+    ConvInApply ap;
+    memset(&ap, 0, sizeof(ap));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dtype == GW_F32 ? conv_in_launch<float, 1>(x, x_alt, step_ptr, B, Cx, L, w, bias, C, nullptr, part, ap, st)
+                             : conv_in_launch<bf16, 1>(x, x_alt, step_ptr, B, Cx, L, w, bias, C, nullptr, part, ap, st);
+    if (rc != GW_OK) return rc;
+    ap.part_in = part; ap.gn_w = gn_w; ap.gn_b = gn_b; ap.wc = wc; ap.bc = bc; ap.film = film; ap.film_off = film_off;
+    ap.film_b_stride = film_b_stride; ap.film_step_stride = film_step_stride; ap.Cc = Cc; ap.out = out; ap.pooled = pooled;
+    return dtype == GW_F32 ? conv_in_launch<float, 2>(x, x_alt, step_ptr, B, Cx, L, w, bias, C, nullptr, nullptr, ap, st)
+                           : conv_in_launch<bf16, 2>(x, x_alt, step_ptr, B, Cx, L, w, bias, C, nullptr, nullptr, ap, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -463,13 +617,6 @@ __device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
     r.x = pack_bf16x2(v[0], v[1]);
     r.y = pack_bf16x2(v[2], v[3]);
     *reinterpret_cast<uint2*>(p) = r;
-}
-// FAST silu: x*sigmoid(x) = h + h*tanh(h), h = x/2; one MUFU op (tanh.approx, rel. error ~2^-11 << bf16 epsilon)
-__device__ __forceinline__ float silu_tanh(float x) {
-    const float h = 0.5f * x;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
 }
 
 // CC = compile-time number of conditioning channels (0, 1, 5) or -1 for the generic (<= GN_MAX_CC) path.

@@ -175,6 +175,10 @@ class UNetEngine:
         self._ws: Dict[tuple, _Workspace] = {}
         self._packed: Dict[tuple, Tensor] = {}
         self.launches = 0
+        # inference option: gw_conv_in_block (stats pass + recompute/apply pass, no raw tensor) instead of gw_conv_in +
+        # gw_gn_apply.  Measured on B200 at B=256, L=4096: 166 us vs 70 + 72 us -- the CUDA-core conv is issue-bound, so
+        # recomputing it costs more than the 268 MB of HBM traffic it saves; kept (parity-tested) but off by default.
+        self.fuse_first_block = False
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
         self.refresh()
@@ -320,11 +324,23 @@ class UNetEngine:
         d = sp.depth
         B, Cx, L = net_a.shape
         st = _cabi.stream_ptr()
-        check(self.lib.gw_conv_in(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),
-                                  ptr(self.p["encoders.0.0.bias"]), sp.base_ch, ptr(ws.raw[0]), self.gw_dtype,
-                                  ptr(ws.part), st), "conv_in")
-        self.launches += 1
-        self._gn(0, ws, (L + 127) // 128, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[0], 0)
+        if ws.stats is None and self.fuse_first_block:
+            # inference: the first block never materialises its raw conv output (stats pass + recompute/apply pass)
+            Cc = sp.cond_in_ch
+            check(self.lib.gw_conv_in_block(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),
+                                            ptr(self.p["encoders.0.0.bias"]), sp.base_ch, ptr(self.p["encoders.0.1.weight"]),
+                                            ptr(self.p["encoders.0.1.bias"]), Cc,
+                                            ptr(self.p["cond_enc.0.weight"]) if Cc > 0 else None,
+                                            ptr(self.p["cond_enc.0.bias"]) if Cc > 0 else None, ptr(film),
+                                            sp.film_offsets()[0], film_b_stride, film_step_stride, ptr(ws.out[0]),
+                                            ptr(ws.pooled[0]), self.gw_dtype, ptr(ws.part), st), "conv_in_block")
+            self.launches += 2
+        else:
+            check(self.lib.gw_conv_in(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),
+                                      ptr(self.p["encoders.0.0.bias"]), sp.base_ch, ptr(ws.raw[0]), self.gw_dtype,
+                                      ptr(ws.part), st), "conv_in")
+            self.launches += 1
+            self._gn(0, ws, (L + 127) // 128, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[0], 0)
         for i in range(1, d):
             n_part = self._conv(i, ws.pooled[i - 1], None, ws.raw[i], ws.part)
             self._gn(i, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[i], i)

@@ -52,6 +52,15 @@ int gw_cond_pyramid(const float* x, int B, int Cx, int L, int Cc, int n_levels, 
 int gw_conv_in(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
                const float* bias, int C, void* raw, int dtype, float* part, void* stream);
 
+/* ---- fused first block for inference (models.py:204-208 without the raw tensor): pass 1 accumulates the GroupNorm partial
+ * sums of the conv output, pass 2 recomputes the conv and applies GroupNorm + SiLU + cond 1x1 conv + FiLM (+ avg_pool).
+ * The conditioning channels are x[:, 1:1+Cc] themselves (level-0 interpolation is the identity).  film row selection as in
+ * gw_gn_apply.  out [B, L, C], pooled [B, L/2, C] or NULL (dtype); part: scratch fp32 [B, ceil(L/128), 8, 2]. */
+int gw_conv_in_block(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
+                     const float* bias, int C, const float* gn_w, const float* gn_b, int Cc, const float* wc,
+                     const float* bc, const float* film, int film_off, long film_b_stride, long film_step_stride,
+                     void* out, void* pooled, int dtype, float* part, void* stream);
+
 /* ---- generic Conv1d(k=3, pad=1) on channels-last activations, CUDA-core fp32 math (exact mode, any L).
  * Input is the virtual concat [nearest-upsample x2 (src0) | src1] (models.py:217-222); src1 may be NULL and
  * `up0` = 0 for encoder/mid convs.  src0 [B, L0, C0], src1 [B, L, C1]; w3 = the reference weight [Cout, C0+C1, 3] fp32;

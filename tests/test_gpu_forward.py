@@ -127,3 +127,26 @@ def test_q_sample_kernel():
     assert rel_l2(xt, ref) <= 1e-6
     xt2, e2 = d.q_sample(x0.cuda(), t.cuda())
     assert abs(float(e2.std()) - 1.0) < 0.1
+
+
+@pytest.mark.parametrize("in_ch,cc,L,B", [(3, 1, 1024, 2), (7, 5, 4096, 2), (3, 1, 500, 3), (7, 5, 250, 1)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_fused_first_block(in_ch, cc, L, B, dtype, tol):
+    """Inference path of the first block (gw_conv_in_block: stats pass + recompute/apply pass, no raw tensor)."""
+    import torch.nn.functional as F
+    sd = make_state_dict(in_ch, cc, seed=0)
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True)
+    x = gaussian((B, in_ch, L), seed=3 + L)
+    t = torch.tensor(([24, 999, 500] * B)[:B])
+    with torch.no_grad():
+        taps = oracle.unet_forward_taps(sd, cfg, x, t)
+    eng = _engine(sd, in_ch, cc, dtype, "auto")
+    eng.fuse_first_block = True
+    eps = eng.forward(x.cuda(), t.cuda())
+    ws = eng.workspace(B, L, False)
+    assert rel_l2(ws.out[0].float().transpose(1, 2), taps["enc0.out"]) <= tol
+    assert rel_l2(ws.pooled[0].float().transpose(1, 2), F.avg_pool1d(taps["enc0.out"], 2, 2)) <= tol
+    assert rel_l2(eps, taps["eps"]) <= tol
+    eng.fuse_first_block = False
+    eps2 = eng.forward(x.cuda(), t.cuda())
+    assert rel_l2(eps2, taps["eps"]) <= tol

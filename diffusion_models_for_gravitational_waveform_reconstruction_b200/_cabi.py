@@ -37,6 +37,7 @@ _SIGS = {
     "gw_conv_in_block": ([_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _I, _P, _P], _I),
     "gw_conv3_simt": ([_P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P], _I),
     "gw_gn_apply": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _I, _P], _I),
+    "gw_gn_apply_stream": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P], _I),
     "gw_final_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _P, _P, C.POINTER(StepParams), _P, _P, _P, _P, _P, _P], _I),
     "gw_step_advance": ([_P, _I, _P], _I),
     "gw_philox_normal": ([_U64, _L, C.c_uint, _I, _I, _P, _P], _I),

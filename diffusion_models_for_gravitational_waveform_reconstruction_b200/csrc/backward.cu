@@ -16,6 +16,7 @@
 // fixed-order second pass (no floating-point atomics anywhere).
 #include "common.cuh"
 #include "../../include/gwb200.h"
+#include <string.h>
 
 #define BW_MAX_CC 8
 
@@ -290,24 +291,7 @@ __device__ __forceinline__ float sigmoid_bw(float x) {
     return 1.0f / (1.0f + expf(-x));
 }
 
-struct GnBwdArgs {
-    const void* raw;        // [B, L, C] conv output saved by the forward
-    const float* stats;     // [B, 8, 2] (mean, rstd) saved by gw_gn_apply
-    const float* gn_w;      // [C]
-    const float* gn_b;      // [C]
-    const float* cond;      // [B, L, Cc] fp32 or NULL
-    const float* wc;        // [C, Cc]
-    const float* bc;        // [C]
-    const float* film;      // row of sample b: film + b*film_b_stride + film_off; gamma at [0,C), beta at [C,2C)
-    long film_b_stride;
-    int film_off;
-    const void* do_a;       // [B, L, C] gradient wrt out, or NULL
-    const void* do_pool;    // [B, L/2, C] gradient wrt the pooled output (encoders), or NULL
-    const float* do_eps;    // [B, L] fp32: the block feeds the head conv; dout[l,c] = sum_k do_w[c,k] * do_eps[l-k+1] (or NULL)
-    const float* do_w;      // [C+1, 3] head weights (models.py:230)
-    int L, C, Cc;
-    int rows_per_cta;
-};
+#include "gn_bwd.cuh"
 
 // per-thread constants of one channel quad
 template <int NCA>
@@ -832,6 +816,13 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
     }
 }
 
+int g_gn_bwd_stream = 1;
+extern "C" int gw_set_option(const char* name, int value) {
+    if (strcmp(name, "gn_bwd_stream") == 0) { g_gn_bwd_stream = value; return GW_OK; }
+    gw_set_error("gw_set_option: unknown option %s", name);
+    return GW_ERR_ARG;
+}
+
 static int gn_rows_per_cta(int L, int C) {
     const int n_tr = 256 / (C / 4);
     int rows = 32 * n_tr;
@@ -855,9 +846,15 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     float* gstat = redb + (size_t)B * C * nvr;
     dim3 grid(n_rc, B);
     const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
+    // bf16 with friendly shapes: HBM-streaming kernels (stream_gn.cu), same partial layouts
+    const bool stream_ok = FAST && g_gn_bwd_stream && L % 4 == 0 && (C == 64 || C == 128 || C == 256) &&
+                           a.rows_per_cta == gn_bwd_stream_rows(L, C);
 #define GNB_GO(CCV)                                                                                                       \
     do {                                                                                                                  \
-        if (FAST && a.do_eps != nullptr) {                                                                                \
+        if (FAST && stream_ok) {                                                                                          \
+            int rcs = gn_bwd_stats_stream(a, B, partial, st);                                                              \
+            if (rcs != GW_OK) return rcs;                                                                                 \
+        } else if (FAST && a.do_eps != nullptr) {                                                                         \
             GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_bf16_kernel<CCV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
             gn_bwd_stats_bf16_kernel<CCV, true><<<grid, 256, sm1, st>>>(a, partial);                                      \
         } else if (FAST) {                                                                                                \
@@ -882,7 +879,10 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     GW_LAUNCH_CHECK();
     // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
 #define GNA_GO(CCV) gn_bwd_apply_kernel<T, FAST, CCV><<<grid, 256, sm2, st>>>(a, gstat, (T*)d_raw, partial)
-    if (FAST && a.do_eps != nullptr) gn_bwd_apply_bf16_kernel<true><<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
+    if (FAST && stream_ok) {
+        int rcs = gn_bwd_apply_stream(a, B, gstat, d_raw, partial, st);
+        if (rcs != GW_OK) return rcs;
+    } else if (FAST && a.do_eps != nullptr) gn_bwd_apply_bf16_kernel<true><<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
     else if (FAST) gn_bwd_apply_bf16_kernel<false><<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
     else if (Cc == 0) GNA_GO(0);
     else if (Cc == 1) GNA_GO(1);

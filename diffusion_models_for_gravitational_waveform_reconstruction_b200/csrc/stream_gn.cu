@@ -1,0 +1,626 @@
+// HBM-streaming versions of the fused GroupNorm kernels for bf16 channels-last activations (sm_100a).
+//
+// The register-streaming kernels in forward.cu / backward.cu keep ~50 KB of loads in flight per SM and top out near 70 % of
+// the measured copy bandwidth.  Here the data path is decoupled from the register file: a CTA owns a contiguous row range
+// of one sample (channels-last => one contiguous byte range), an elected thread streams it through a 4-deep ring of 8 KB
+// shared-memory stages with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), all 256 threads compute from shared
+// memory, results are staged in shared memory and leave through bulk stores.  ~100 KB per SM are in flight regardless of
+// register pressure.
+#include "common.cuh"
+#include "../../include/gwb200.h"
+#include "tc_common.cuh"
+
+#define SG_STAGE_BYTES 8192          // one stage of raw rows: S rows x C channels x 2 B
+#define SG_DEPTH 4
+#define SG_MAX_CC 8
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: GroupNorm-apply + SiLU + cond 1x1 conv + FiLM (+ avg_pool), see gn_apply_kernel in forward.cu
+// ------------------------------------------------------------------------------------------------
+template <int CC>
+__global__ void __launch_bounds__(256)
+gn_apply_stream_kernel(const bf16* __restrict__ raw, const float* __restrict__ part, int n_part, int L, int C,
+                       const float* __restrict__ gn_w, const float* __restrict__ gn_b, const float* __restrict__ cond, int Cc_rt,
+                       const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ film, int film_off,
+                       long film_b_stride, long film_step_stride, const int* __restrict__ step_ptr, bf16* __restrict__ out,
+                       bf16* __restrict__ pooled, float* __restrict__ stats_out, int rows_per_cta) {
+    constexpr int NC = CC >= 0 ? CC : SG_MAX_CC;
+    constexpr int NCA = NC > 0 ? NC : 1;
+    const int Cc = CC >= 0 ? CC : Cc_rt;
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: in[D][8 KB] | out[2][8 KB] | pool[2][4 KB] | cond[D][S*Cc*4 rounded to 128] | barriers
+    const int S = SG_STAGE_BYTES / (C * 2);                       // rows per stage (64 / 32 / 16 for C = 64 / 128 / 256)
+    const uint32_t cond_stage = (uint32_t)((S * NCA * 4 + 127) & ~127);
+    uint8_t* s_in = smem;
+    uint8_t* s_out = s_in + SG_DEPTH * SG_STAGE_BYTES;
+    uint8_t* s_pool = s_out + 2 * SG_STAGE_BYTES;
+    uint8_t* s_cond = s_pool + 2 * (SG_STAGE_BYTES / 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_cond + SG_DEPTH * cond_stage);
+    __shared__ float s_mean[8], s_rstd[8];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = C / 8;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int rows_here = min(rows_per_cta, L - r0);
+    const int n_sub = (rows_here + S - 1) / S;
+    const bf16* rbase = raw + ((size_t)b * L + r0) * C;
+    const float* cbase = cond + ((size_t)b * L + r0) * Cc;
+
+    auto issue_load = [&](int i) {
+        const int st = i % SG_DEPTH;
+        const int rows_i = min(S, rows_here - i * S);
+        const uint32_t bar = smem_u32(bars + st);
+        const uint32_t nb = (uint32_t)rows_i * C * 2, ncb = (uint32_t)rows_i * Cc * 4;
+        mbar_expect_tx(bar, nb + (NC > 0 ? ncb : 0u));
+        bulk_load(smem_u32(s_in + st * SG_STAGE_BYTES), rbase + (size_t)i * S * C, nb, bar);
+        if (NC > 0) bulk_load(smem_u32(s_cond + st * cond_stage), cbase + (size_t)i * S * Cc, ncb, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SG_DEPTH; ++s) mbar_init(smem_u32(bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < SG_DEPTH && i < n_sub; ++i) issue_load(i);      // the stream starts before the statistics are ready
+    }
+    if (warp < 8) {
+        double a1 = 0.0, a2 = 0.0;
+        const float* pp = part + (size_t)b * n_part * 16 + warp * 2;
+        for (int i = lane; i < n_part; i += 32) {
+            a1 += (double)pp[(size_t)i * 16];
+            a2 += (double)pp[(size_t)i * 16 + 1];
+        }
+        a1 = warp_sum_d(a1);
+        a2 = warp_sum_d(a2);
+        if (lane == 0) {
+            const double n = (double)cg * (double)L;
+            const double mean = a1 / n;
+            double var = a2 / n - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+            s_mean[warp] = (float)mean;
+            s_rstd[warp] = rstd;
+            if (stats_out != nullptr && blockIdx.x == 0) {
+                stats_out[((size_t)b * 8 + warp) * 2 + 0] = (float)mean;
+                stats_out[((size_t)b * 8 + warp) * 2 + 1] = rstd;
+            }
+        }
+    }
+    __syncthreads();
+    const int n_quad = C / 4;                                         // 16 / 32 / 64: divides 256
+    const int quad = threadIdx.x % n_quad, pr0 = threadIdx.x / n_quad, pr_stride = 256 / n_quad;
+    const int step = step_ptr != nullptr ? *step_ptr : 0;
+    const float* fr = film + (size_t)step * film_step_stride + (size_t)b * film_b_stride + film_off;
+    f32x2 hA[2], hB[2], G[2], E[2], W[NCA][2];
+    {
+        float a_[4], b_[4], g_[4], e_[4], w_[NCA][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            const int g = c / cg;
+            const float a = s_rstd[g] * gn_w[c];
+            a_[i] = 0.5f * a;
+            b_[i] = 0.5f * (gn_b[c] - s_mean[g] * a);
+            g_[i] = 1.0f + fr[c];
+            e_[i] = fmaf(NC > 0 ? bc[c] : 0.0f, g_[i], fr[C + c]);
+#pragma unroll
+            for (int j = 0; j < NCA; ++j) w_[j][i] = (NC > 0 && j < Cc) ? wc[c * Cc + j] * g_[i] : 0.0f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+            hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+            G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+            E[h] = pkf2(e_[2 * h], e_[2 * h + 1]);
+#pragma unroll
+            for (int j = 0; j < NCA; ++j) W[j][h] = pkf2(w_[j][2 * h], w_[j][2 * h + 1]);
+        }
+    }
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    const bool do_pool = pooled != nullptr;
+    const int Lp = L / 2;
+    bf16* obase = out + ((size_t)b * L + r0) * C;
+    bf16* pbase = do_pool ? pooled + ((size_t)b * Lp + (r0 >> 1)) * C : nullptr;
+
+    for (int i = 0; i < n_sub; ++i) {
+        const int st = i % SG_DEPTH;
+        const int rows_i = min(S, rows_here - i * S);
+        mbar_wait(smem_u32(bars + st), (uint32_t)((i / SG_DEPTH) & 1));
+        const uint8_t* in = s_in + st * SG_STAGE_BYTES;
+        const float* cd = reinterpret_cast<const float*>(s_cond + st * cond_stage);
+        uint8_t* so = s_out + (i & 1) * SG_STAGE_BYTES;
+        uint8_t* sp = s_pool + (i & 1) * (SG_STAGE_BYTES / 2);
+        for (int pr = pr0; 2 * pr < rows_i; pr += pr_stride) {
+            f32x2 o[2][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = 2 * pr + h;                         // rows_i is even on this path
+                const uint2 xr = *reinterpret_cast<const uint2*>(in + ((size_t)r * C + quad * 4) * 2);
+                const uint32_t w2[2] = {xr.x, xr.y};
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const f32x2 xv = pk2(w2[q] << 16, w2[q] & 0xffff0000u);
+                    const f32x2 hh = ffma2(xv, hA[q], hB[q]);
+                    float h0, h1, t0, t1;
+                    upk2(hh, h0, h1);
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+                    f32x2 v = ffma2(ffma2(hh, pkf2(t0, t1), hh), G[q], E[q]);
+                    if (NC > 0) {
+#pragma unroll
+                        for (int j = 0; j < NCA; ++j) {
+                            const float cvj = j < Cc ? cd[r * Cc + j] : 0.0f;
+                            v = ffma2(W[j][q], pkf2(cvj, cvj), v);
+                        }
+                    }
+                    o[h][q] = v;
+                }
+                float a0, a1, a2, a3;
+                upk2(o[h][0], a0, a1);
+                upk2(o[h][1], a2, a3);
+                uint2 rr;
+                rr.x = pack_bf16x2(a0, a1);
+                rr.y = pack_bf16x2(a2, a3);
+                *reinterpret_cast<uint2*>(so + ((size_t)r * C + quad * 4) * 2) = rr;
+            }
+            if (do_pool) {
+                float a0, a1, a2, a3;
+                upk2(fmul2(fadd2(o[0][0], o[1][0]), half2), a0, a1);
+                upk2(fmul2(fadd2(o[0][1], o[1][1]), half2), a2, a3);
+                uint2 rr;
+                rr.x = pack_bf16x2(a0, a1);
+                rr.y = pack_bf16x2(a2, a3);
+                *reinterpret_cast<uint2*>(sp + ((size_t)pr * C + quad * 4) * 2) = rr;
+            }
+        }
+        fence_proxy_async();                                          // my smem writes -> visible to the bulk-store engine
+        if (threadIdx.x == 0) tma_wait_read<0>();                     // stores of iteration i-1 have drained staging[(i+1)&1]
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store(obase + (size_t)i * S * C, smem_u32(so), (uint32_t)rows_i * C * 2);
+            if (do_pool) bulk_store(pbase + (size_t)i * (S / 2) * C, smem_u32(sp), (uint32_t)(rows_i / 2) * C * 2);
+            tma_commit();
+            if (i + SG_DEPTH < n_sub) issue_load(i + SG_DEPTH);       // every thread is done reading stage st
+        }
+    }
+    if (threadIdx.x == 0) tma_wait_read<0>();
+}
+
+static int gn_stream_rows(int L, int C) {
+    const int S = SG_STAGE_BYTES / (C * 2);
+    int rows = 8 * S;                                   // 64 KB of raw rows per CTA
+    if (rows > L) rows = (L + S - 1) / S * S;
+    return rows;
+}
+
+// same contract as gw_gn_apply for dtype = GW_BF16; needs L % 4 == 0 and C in {64, 128, 256}
+extern "C" int gw_gn_apply_stream(const void* raw, const float* part, int n_part, int B, int L, int C, const float* gn_w,
+                                  const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
+                                  const float* film, int film_off, long film_b_stride, long film_step_stride,
+                                  const int* step_ptr, void* out, void* pooled, float* stats_out, void* stream) {
+    GW_REQUIRE(C == 64 || C == 128 || C == 256, "gw_gn_apply_stream: C=%d", C);
+    GW_REQUIRE(L % 4 == 0 && L >= 4, "gw_gn_apply_stream: L=%d must be a multiple of 4", L);
+    GW_REQUIRE(Cc >= 0 && Cc <= SG_MAX_CC, "gw_gn_apply_stream: Cc=%d", Cc);
+    GW_REQUIRE((cond != nullptr) == (Cc > 0), "gw_gn_apply_stream: cond/Cc mismatch");
+    const int rows = gn_stream_rows(L, C);
+    const int S = SG_STAGE_BYTES / (C * 2);
+    const int nca = Cc > 0 ? (Cc == 1 || Cc == 5 ? Cc : SG_MAX_CC) : 1;
+    const int cond_stage = (S * nca * 4 + 127) & ~127;
+    const size_t smem = (size_t)SG_DEPTH * SG_STAGE_BYTES + 2 * SG_STAGE_BYTES + SG_STAGE_BYTES + SG_DEPTH * cond_stage + 64;
+    dim3 grid(gw_cdiv(L, rows), B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SGA_GO(CCV)                                                                                                        \
+    do {                                                                                                                   \
+        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        gn_apply_stream_kernel<CCV><<<grid, 256, smem, st>>>((const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
+                                                             film, film_off, film_b_stride, film_step_stride, step_ptr,        \
+                                                             (bf16*)out, (bf16*)pooled, stats_out, rows);                      \
+    } while (0)
+    if (Cc == 0) SGA_GO(0);
+    else if (Cc == 1) SGA_GO(1);
+    else if (Cc == 5) SGA_GO(5);
+    else SGA_GO(-1);
+#undef SGA_GO
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ================================================================================================
+// backward: the two passes of gw_gn_bwd (backward.cu) as streaming kernels
+// ================================================================================================
+#include "gn_bwd.cuh"
+
+int gn_bwd_stream_rows(int L, int C) {
+    const int S = SG_STAGE_BYTES / (C * 2);
+    int rows = 8 * S;
+    if (rows > L) rows = L;
+    return rows < 1 ? 1 : rows;
+}
+
+__device__ __forceinline__ f32x2 bf2_lo(uint32_t w) { return pk2(w << 16, w & 0xffff0000u); }
+
+// z/2, sigmoid and silu derivative of a channel pair from one tanh.approx per element
+__device__ __forceinline__ void sg_silu_pair(f32x2 x, f32x2 hA, f32x2 hB, f32x2& z, f32x2& act, f32x2& dact) {
+    const f32x2 one = pkf2(1.0f, 1.0f), half2 = pkf2(0.5f, 0.5f), neg1 = pkf2(-1.0f, -1.0f);
+    const f32x2 hh = ffma2(x, hA, hB);
+    z = fadd2(hh, hh);
+    float h0, h1, t0, t1;
+    upk2(hh, h0, h1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+    const f32x2 sg = ffma2(pkf2(t0, t1), half2, half2);
+    act = fmul2(z, sg);
+    dact = fmul2(sg, ffma2(z, ffma2(sg, neg1, one), one));
+}
+
+// Stage layout (bytes): raw [S*C*2] | do_a [S*C*2] | do_pool [S/2*C*2] | cond [S*Cc*4 -> 128]
+struct SgBwdLayout {
+    uint32_t off_do, off_pool, off_cond, stage;
+};
+__host__ __device__ inline SgBwdLayout sg_bwd_layout(int C, int Cc, bool has_do, bool has_pool) {
+    const int S = SG_STAGE_BYTES / (C * 2);
+    SgBwdLayout l;
+    uint32_t o = SG_STAGE_BYTES;
+    l.off_do = o;
+    if (has_do) o += SG_STAGE_BYTES;
+    l.off_pool = o;
+    if (has_pool) o += SG_STAGE_BYTES / 2;
+    l.off_cond = o;
+    if (Cc > 0) o += (uint32_t)((S * Cc * 4 + 127) & ~127);
+    l.stage = o;
+    return l;
+}
+
+// common producer: one sub-chunk of rows [i*S, i*S + rows_i) of this CTA's range into stage i % depth
+struct SgBwdStream {
+    const GnBwdArgs* a;
+    int b, r0, rows_here, S, depth;
+    SgBwdLayout lay;
+    uint8_t* base;
+    uint64_t* bars;
+    __device__ void issue(int i, bool want_cond) const {
+        const int C = a->C, L = a->L, Cc = a->Cc;
+        const int st = i % depth;
+        const int rows_i = min(S, rows_here - i * S);
+        const uint32_t bar = smem_u32(bars + st);
+        const uint32_t nb = (uint32_t)rows_i * C * 2;
+        uint32_t total = nb;
+        if (a->do_a) total += nb;
+        if (a->do_pool) total += nb / 2;
+        if (want_cond && Cc > 0) total += (uint32_t)rows_i * Cc * 4;
+        mbar_expect_tx(bar, total);
+        uint8_t* sb = base + (size_t)st * lay.stage;
+        const size_t row = (size_t)b * L + r0 + (size_t)i * S;
+        bulk_load(smem_u32(sb), (const bf16*)a->raw + row * C, nb, bar);
+        if (a->do_a) bulk_load(smem_u32(sb + lay.off_do), (const bf16*)a->do_a + row * C, nb, bar);
+        if (a->do_pool)
+            bulk_load(smem_u32(sb + lay.off_pool), (const bf16*)a->do_pool + ((size_t)b * (L / 2) + ((r0 + i * S) >> 1)) * C, nb / 2, bar);
+        if (want_cond && Cc > 0) bulk_load(smem_u32(sb + lay.off_cond), a->cond + row * Cc, (uint32_t)rows_i * Cc * 4, bar);
+    }
+};
+
+template <int CC, bool HEAD>
+__global__ void __launch_bounds__(256) gn_bwd_stats_stream_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
+    constexpr int NC = CC >= 0 ? CC : SG_MAX_CC;
+    constexpr int NV = 4 + NC;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int Cc = CC >= 0 ? CC : a.Cc;
+    const int b = blockIdx.y, C = a.C, L = a.L;
+    const int S = SG_STAGE_BYTES / (C * 2);
+    SgBwdStream ps;
+    ps.a = &a; ps.b = b; ps.r0 = blockIdx.x * a.rows_per_cta; ps.rows_here = min(a.rows_per_cta, L - ps.r0); ps.S = S;
+    ps.depth = depth; ps.lay = sg_bwd_layout(C, Cc, a.do_a != nullptr, a.do_pool != nullptr); ps.base = smem;
+    ps.bars = reinterpret_cast<uint64_t*>(smem + (size_t)depth * ps.lay.stage);
+    const int n_sub = (ps.rows_here + S - 1) / S;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < depth; ++s) mbar_init(smem_u32(ps.bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < depth && i < n_sub; ++i) ps.issue(i, true);
+    }
+    const int n_quad = C / 4, n_tr = 256 / n_quad;
+    const int quad = threadIdx.x % n_quad, tr = threadIdx.x / n_quad;
+    f32x2 hA[2], hB[2], G[2], rs2, xo2;
+    {
+        const int cg = C / 8, g = (quad * 4) / cg;
+        const float mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+        const float rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+        rs2 = pkf2(rstd, rstd);
+        xo2 = pkf2(-mean * rstd, -mean * rstd);
+        const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+        float a_[4], b_[4], g_[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            const float aa = rstd * a.gn_w[c];
+            a_[i] = 0.5f * aa;
+            b_[i] = 0.5f * (a.gn_b[c] - mean * aa);
+            g_[i] = 1.0f + fr[c];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+            hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+            G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+        }
+    }
+    const float* de = (HEAD && a.do_eps) ? a.do_eps + (size_t)b * L : nullptr;
+    f32x2 wk[3][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+    if (HEAD && de) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                wk[k][h] = pkf2(a.do_w[(quad * 4 + 2 * h) * 3 + k], a.do_w[(quad * 4 + 2 * h + 1) * 3 + k]);
+    }
+    f32x2 acc[2][NV];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[h][v] = 0ull;
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    const bool has_do = a.do_a != nullptr, has_pool = a.do_pool != nullptr;
+    __syncthreads();
+    for (int i = 0; i < n_sub; ++i) {
+        const int st = i % depth;
+        const int rows_i = min(S, ps.rows_here - i * S);
+        mbar_wait(smem_u32(ps.bars + st), (uint32_t)((i / depth) & 1));
+        const uint8_t* sb = smem + (size_t)st * ps.lay.stage;
+        const float* cd = reinterpret_cast<const float*>(sb + ps.lay.off_cond);
+        for (int rb = tr; rb < rows_i; rb += 2 * n_tr) {
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {                            // two independent rows in flight per thread (ILP)
+            const int r = rb + uu * n_tr;
+            if (r >= rows_i) break;
+            const uint2 xr = *reinterpret_cast<const uint2*>(sb + ((size_t)r * C + quad * 4) * 2);
+            uint2 dr = make_uint2(0u, 0u), pl = make_uint2(0u, 0u);
+            if (has_do) dr = *reinterpret_cast<const uint2*>(sb + ps.lay.off_do + ((size_t)r * C + quad * 4) * 2);
+            if (has_pool) pl = *reinterpret_cast<const uint2*>(sb + ps.lay.off_pool + ((size_t)(r >> 1) * C + quad * 4) * 2);
+            float e3[3] = {0.0f, 0.0f, 0.0f};
+            if (HEAD && de) {
+                const int l = ps.r0 + i * S + r;
+                e3[0] = l + 1 < L ? de[l + 1] : 0.0f;
+                e3[1] = de[l];
+                e3[2] = l > 0 ? de[l - 1] : 0.0f;
+            }
+            const uint32_t xw[2] = {xr.x, xr.y}, dw[2] = {dr.x, dr.y}, pw[2] = {pl.x, pl.y};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                f32x2 dv = has_do ? bf2_lo(dw[h]) : 0ull;
+                if (has_pool) dv = ffma2(bf2_lo(pw[h]), half2, dv);
+                if (HEAD && de) {
+                    const f32x2 t = ffma2(wk[1][h], pkf2(e3[1], e3[1]), fmul2(wk[2][h], pkf2(e3[2], e3[2])));
+                    dv = fadd2(dv, ffma2(wk[0][h], pkf2(e3[0], e3[0]), t));
+                }
+                const f32x2 x = bf2_lo(xw[h]);
+                f32x2 z, act, dact;
+                sg_silu_pair(x, hA[h], hB[h], z, act, dact);
+                const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
+                const f32x2 xh = ffma2(x, rs2, xo2);
+                acc[h][0] = fadd2(acc[h][0], dv);
+                acc[h][1] = ffma2(dv, act, acc[h][1]);
+                acc[h][2] = fadd2(acc[h][2], dn);
+                acc[h][3] = ffma2(dn, xh, acc[h][3]);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const float cvj = j < Cc ? cd[r * Cc + j] : 0.0f;
+                    acc[h][4 + j] = ffma2(dv, pkf2(cvj, cvj), acc[h][4 + j]);
+                }
+            }
+          }
+        }
+        __syncthreads();                                              // every thread is done with stage st
+        if (threadIdx.x == 0 && i + depth < n_sub) ps.issue(i + depth, true);
+    }
+    // reduce the thread rows through shared memory (the stage ring is free now)
+    float* red = reinterpret_cast<float*>(smem);
+    const int nvr = 4 + Cc;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (v < nvr) {
+                float lo, hi;
+                upk2(acc[h][v], lo, hi);
+                red[((size_t)tr * C + quad * 4 + 2 * h) * nvr + v] = lo;
+                red[((size_t)tr * C + quad * 4 + 2 * h + 1) * nvr + v] = hi;
+            }
+    __syncthreads();
+    float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nvr;
+    for (int i = threadIdx.x; i < C * nvr; i += 256) {
+        float sacc = 0.0f;
+        for (int t = 0; t < n_tr; ++t) sacc += red[(size_t)t * C * nvr + i];
+        pt[i] = sacc;
+    }
+}
+
+template <bool HEAD>
+__global__ void __launch_bounds__(256) gn_bwd_apply_stream_kernel(GnBwdArgs a, const float* __restrict__ gstat,
+                                                                  bf16* __restrict__ d_raw, float* __restrict__ partial_bias,
+                                                                  int depth) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int b = blockIdx.y, C = a.C, L = a.L;
+    const int S = SG_STAGE_BYTES / (C * 2);
+    SgBwdStream ps;
+    ps.a = &a; ps.b = b; ps.r0 = blockIdx.x * a.rows_per_cta; ps.rows_here = min(a.rows_per_cta, L - ps.r0); ps.S = S;
+    ps.depth = depth; ps.lay = sg_bwd_layout(C, 0, a.do_a != nullptr, a.do_pool != nullptr); ps.base = smem;
+    uint8_t* s_out = smem + (size_t)depth * ps.lay.stage;             // [2][8 KB] output staging
+    ps.bars = reinterpret_cast<uint64_t*>(s_out + 2 * SG_STAGE_BYTES);
+    const int n_sub = (ps.rows_here + S - 1) / S;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < depth; ++s) mbar_init(smem_u32(ps.bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < depth && i < n_sub; ++i) ps.issue(i, false);
+    }
+    const int n_quad = C / 4, n_tr = 256 / n_quad;
+    const int quad = threadIdx.x % n_quad, tr = threadIdx.x / n_quad;
+    f32x2 hA[2], hB[2], G[2], GW2[2], rs2, xo2, nm1, nm2;
+    {
+        const int cg = C / 8, g = (quad * 4) / cg;
+        const float mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+        const float rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+        const float m1 = gstat[((size_t)b * 8 + g) * 2 + 0], m2 = gstat[((size_t)b * 8 + g) * 2 + 1];
+        rs2 = pkf2(rstd, rstd);
+        xo2 = pkf2(-mean * rstd, -mean * rstd);
+        nm1 = pkf2(-m1, -m1);
+        nm2 = pkf2(-m2, -m2);
+        const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+        float a_[4], b_[4], g_[4], w_[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            w_[i] = a.gn_w[c];
+            const float aa = rstd * w_[i];
+            a_[i] = 0.5f * aa;
+            b_[i] = 0.5f * (a.gn_b[c] - mean * aa);
+            g_[i] = 1.0f + fr[c];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+            hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+            G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+            GW2[h] = pkf2(w_[2 * h], w_[2 * h + 1]);
+        }
+    }
+    const float* de = (HEAD && a.do_eps) ? a.do_eps + (size_t)b * L : nullptr;
+    f32x2 wk[3][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+    if (HEAD && de) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                wk[k][h] = pkf2(a.do_w[(quad * 4 + 2 * h) * 3 + k], a.do_w[(quad * 4 + 2 * h + 1) * 3 + k]);
+    }
+    f32x2 sbs[2] = {0ull, 0ull};
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    const bool has_do = a.do_a != nullptr, has_pool = a.do_pool != nullptr;
+    bf16* obase = d_raw + ((size_t)b * L + ps.r0) * C;
+    __syncthreads();
+    for (int i = 0; i < n_sub; ++i) {
+        const int st = i % depth;
+        const int rows_i = min(S, ps.rows_here - i * S);
+        mbar_wait(smem_u32(ps.bars + st), (uint32_t)((i / depth) & 1));
+        const uint8_t* sb = smem + (size_t)st * ps.lay.stage;
+        uint8_t* so = s_out + (i & 1) * SG_STAGE_BYTES;
+        for (int rb = tr; rb < rows_i; rb += 2 * n_tr) {
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {                            // two independent rows in flight per thread (ILP)
+            const int r = rb + uu * n_tr;
+            if (r >= rows_i) break;
+            const uint2 xr = *reinterpret_cast<const uint2*>(sb + ((size_t)r * C + quad * 4) * 2);
+            uint2 dr = make_uint2(0u, 0u), pl = make_uint2(0u, 0u);
+            if (has_do) dr = *reinterpret_cast<const uint2*>(sb + ps.lay.off_do + ((size_t)r * C + quad * 4) * 2);
+            if (has_pool) pl = *reinterpret_cast<const uint2*>(sb + ps.lay.off_pool + ((size_t)(r >> 1) * C + quad * 4) * 2);
+            float e3[3] = {0.0f, 0.0f, 0.0f};
+            if (HEAD && de) {
+                const int l = ps.r0 + i * S + r;
+                e3[0] = l + 1 < L ? de[l + 1] : 0.0f;
+                e3[1] = de[l];
+                e3[2] = l > 0 ? de[l - 1] : 0.0f;
+            }
+            const uint32_t xw[2] = {xr.x, xr.y}, dw[2] = {dr.x, dr.y}, pw[2] = {pl.x, pl.y};
+            uint2 outw;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                f32x2 dv = has_do ? bf2_lo(dw[h]) : 0ull;
+                if (has_pool) dv = ffma2(bf2_lo(pw[h]), half2, dv);
+                if (HEAD && de) {
+                    const f32x2 t = ffma2(wk[1][h], pkf2(e3[1], e3[1]), fmul2(wk[2][h], pkf2(e3[2], e3[2])));
+                    dv = fadd2(dv, ffma2(wk[0][h], pkf2(e3[0], e3[0]), t));
+                }
+                const f32x2 x = bf2_lo(xw[h]);
+                f32x2 z, act, dact;
+                sg_silu_pair(x, hA[h], hB[h], z, act, dact);
+                const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
+                const f32x2 xh = ffma2(x, rs2, xo2);
+                const f32x2 dz = fmul2(ffma2(xh, nm2, ffma2(dn, GW2[h], nm1)), rs2);
+                sbs[h] = fadd2(sbs[h], dz);
+                float lo, hi;
+                upk2(dz, lo, hi);
+                if (h == 0) outw.x = pack_bf16x2(lo, hi); else outw.y = pack_bf16x2(lo, hi);
+            }
+            *reinterpret_cast<uint2*>(so + ((size_t)r * C + quad * 4) * 2) = outw;
+          }
+        }
+        fence_proxy_async();
+        if (threadIdx.x == 0) tma_wait_read<0>();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store(obase + (size_t)i * S * C, smem_u32(so), (uint32_t)rows_i * C * 2);
+            tma_commit();
+            if (i + depth < n_sub) ps.issue(i + depth, false);
+        }
+    }
+    if (threadIdx.x == 0) tma_wait_read<0>();
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem);                      // stage ring is free (loads done, stores read staging only)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float lo, hi;
+        upk2(sbs[h], lo, hi);
+        red[(size_t)tr * C + quad * 4 + 2 * h] = lo;
+        red[(size_t)tr * C + quad * 4 + 2 * h + 1] = hi;
+    }
+    __syncthreads();
+    float* pt = partial_bias + ((size_t)b * gridDim.x + blockIdx.x) * C;
+    for (int i = threadIdx.x; i < C; i += 256) {
+        float sacc = 0.0f;
+        for (int t = 0; t < n_tr; ++t) sacc += red[(size_t)t * C + i];
+        pt[i] = sacc;
+    }
+}
+
+int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t st) {
+    const int C = a.C, Cc = a.Cc;
+    const SgBwdLayout lay = sg_bwd_layout(C, Cc, a.do_a != nullptr, a.do_pool != nullptr);
+    const int n_tr = 256 / (C / 4), nvr = 4 + Cc;
+    const int depth = lay.stage > 20000 ? 3 : 4;
+    size_t smem = (size_t)depth * lay.stage + 64;
+    const size_t red_bytes = (size_t)n_tr * C * nvr * sizeof(float);
+    if (smem < red_bytes) smem = red_bytes;
+    dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
+    const bool head = a.do_eps != nullptr;
+#define SGS_GO(CCV, HD)                                                                                                     \
+    do {                                                                                                                    \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_stream_kernel<CCV, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gn_bwd_stats_stream_kernel<CCV, HD><<<grid, 256, smem, st>>>(a, partial, depth);                                     \
+    } while (0)
+#define SGS_CC(HD)                      \
+    do {                                \
+        if (Cc == 0) SGS_GO(0, HD);     \
+        else if (Cc == 1) SGS_GO(1, HD); \
+        else if (Cc == 5) SGS_GO(5, HD); \
+        else SGS_GO(-1, HD);            \
+    } while (0)
+    if (head) SGS_CC(true); else SGS_CC(false);
+#undef SGS_CC
+#undef SGS_GO
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_raw, float* partial_bias, cudaStream_t st) {
+    const int C = a.C;
+    const SgBwdLayout lay = sg_bwd_layout(C, 0, a.do_a != nullptr, a.do_pool != nullptr);
+    const int depth = lay.stage > 20000 ? 3 : 4;
+    const size_t smem = (size_t)depth * lay.stage + 2 * SG_STAGE_BYTES + 64;
+    dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
+    if (a.do_eps != nullptr) {
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gn_bwd_apply_stream_kernel<true><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
+    } else {
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gn_bwd_apply_stream_kernel<false><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
+    }
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}

@@ -179,6 +179,7 @@ class UNetEngine:
         # gw_gn_apply.  Measured on B200 at B=256, L=4096: 166 us vs 70 + 72 us -- the CUDA-core conv is issue-bound, so
         # recomputing it costs more than the 268 MB of HBM traffic it saves; kept (parity-tested) but off by default.
         self.fuse_first_block = False
+        self.stream_gn = True                       # bf16: bulk-copy streaming GroupNorm kernels (stream_gn.cu)
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
         self.refresh()
@@ -308,6 +309,16 @@ class UNetEngine:
         B, L, Cc_ = raw.shape
         Cc = sp.cond_in_ch
         cname = sp.cond_names()[li]
+        if self.stream_gn and self.dtype == "bf16" and L % 4 == 0 and Cc_ in (64, 128, 256):
+            check(self.lib.gw_gn_apply_stream(ptr(raw), ptr(ws.part), n_part, B, L, Cc_, ptr(self.p[name + ".1.weight"]),
+                                              ptr(self.p[name + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                              ptr(self.p[cname + ".weight"]) if Cc > 0 else None,
+                                              ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film),
+                                              sp.film_offsets()[li], film_b_stride, film_step_stride, ptr(step_ptr), ptr(out),
+                                              ptr(pooled), ptr(ws.stats[li]) if ws.stats is not None else None,
+                                              _cabi.stream_ptr()), f"gn_apply_stream[{name}]")
+            self.launches += 1
+            return
         check(self.lib.gw_gn_apply(ptr(raw), ptr(ws.part), n_part, B, L, Cc_, ptr(self.p[name + ".1.weight"]),
                                    ptr(self.p[name + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
                                    ptr(self.p[cname + ".weight"]) if Cc > 0 else None,

@@ -79,6 +79,14 @@ int gw_gn_apply(const void* raw, const float* part, int n_part, int B, int L, in
                 int film_off, long film_b_stride, long film_step_stride, const int* step_ptr, void* out,
                 void* pooled, float* stats_out, int dtype, void* stream);
 
+/* ---- the same operation as gw_gn_apply for bf16 tensors, HBM-streaming implementation (stream_gn.cu): contiguous row
+ * ranges go through a ring of shared-memory stages with 1-D bulk copies (cp.async.bulk) in and bulk stores out.
+ * Needs L % 4 == 0 and C in {64, 128, 256}. */
+int gw_gn_apply_stream(const void* raw, const float* part, int n_part, int B, int L, int C, const float* gn_w,
+                       const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc, const float* film,
+                       int film_off, long film_b_stride, long film_step_stride, const int* step_ptr, void* out,
+                       void* pooled, float* stats_out, void* stream);
+
 /* ---- head: final Conv1d(C+1 -> 1, k=3) on cat[h, x_t] (models.py:227-230, K8) optionally fused with classifier-free
  * guidance combine and the DDIM/DDPM update (inference.py:445-484, K20/K21).
  *

@@ -412,17 +412,18 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(GnBwdArgs a, float
     }
 }
 
-// grid B: reduce the row-CTA partials of one sample, emit dfilm and the group means needed by the apply pass
-__global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __restrict__ partial, int n_rc, int C, int nvr, int L,
-                                                              const float* __restrict__ gn_w, const float* __restrict__ wc,
-                                                              const float* __restrict__ bc, float* __restrict__ redb,
-                                                              float* __restrict__ dfilm, long dfilm_b_stride, int film_off,
-                                                              float* __restrict__ gstat) {
+// grid B, block 1024: reduce the row-CTA partials of one sample, emit dfilm and the group means needed by the apply pass
+__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ partial, int n_rc, int C, int nvr, int L,
+                                                               const float* __restrict__ gn_w, const float* __restrict__ wc,
+                                                               const float* __restrict__ bc, float* __restrict__ redb,
+                                                               float* __restrict__ dfilm, long dfilm_b_stride, int film_off,
+                                                               float* __restrict__ gstat) {
     extern __shared__ float sv[];                        // [C][nvr]
     const int b = blockIdx.x;
     const float* pb = partial + (size_t)b * n_rc * C * nvr;
-    for (int i = threadIdx.x; i < C * nvr; i += 256) {
+    for (int i = threadIdx.x; i < C * nvr; i += blockDim.x) {
         float s = 0.0f;
+#pragma unroll 8
         for (int r = 0; r < n_rc; ++r) s += pb[(size_t)r * C * nvr + i];
         sv[i] = s;
         redb[(size_t)b * C * nvr + i] = s;
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __res
     __syncthreads();
     float* df = dfilm + (size_t)b * dfilm_b_stride + film_off;
     const int Cc = nvr - 4;
-    for (int c = threadIdx.x; c < C; c += 256) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float dg = sv[c * nvr + 1];                       // sum do*silu(n)
         if (Cc > 0) {                                     // + sum do*(bc + sum_j wc_j cond_j): h = silu(n) + cond bias
             dg = fmaf(bc[c], sv[c * nvr + 0], dg);
@@ -440,17 +441,19 @@ __global__ void __launch_bounds__(256) gn_bwd_finalize_kernel(const float* __res
         df[C + c] = sv[c * nvr + 0];                      // d beta  = sum do
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = C / 8;
-    float s1 = 0.0f, s2 = 0.0f;
-    for (int c = warp * cg + lane; c < (warp + 1) * cg; c += 32) {
-        s1 = fmaf(gn_w[c], sv[c * nvr + 2], s1);
-        s2 = fmaf(gn_w[c], sv[c * nvr + 3], s2);
-    }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-        const float n = (float)cg * (float)L;
-        gstat[((size_t)b * 8 + warp) * 2 + 0] = s1 / n;
-        gstat[((size_t)b * 8 + warp) * 2 + 1] = s2 / n;
+    if (warp < 8) {
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int c = warp * cg + lane; c < (warp + 1) * cg; c += 32) {
+            s1 = fmaf(gn_w[c], sv[c * nvr + 2], s1);
+            s2 = fmaf(gn_w[c], sv[c * nvr + 3], s2);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            const float n = (float)cg * (float)L;
+            gstat[((size_t)b * 8 + warp) * 2 + 0] = s1 / n;
+            gstat[((size_t)b * 8 + warp) * 2 + 1] = s2 / n;
+        }
     }
 }
 
@@ -871,7 +874,7 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     else GNB_GO(-1);
 #undef GNB_GO
     GW_LAUNCH_CHECK();
-    gn_bwd_finalize_kernel<<<B, 256, (size_t)C * nvr * sizeof(float), st>>>(partial, n_rc, C, nvr, L, a.gn_w, a.wc, a.bc, redb, dfilm,
+    gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvr * sizeof(float), st>>>(partial, n_rc, C, nvr, L, a.gn_w, a.wc, a.bc, redb, dfilm,
                                                                             dfilm_b_stride, a.film_off, gstat);
     GW_LAUNCH_CHECK();
     gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,

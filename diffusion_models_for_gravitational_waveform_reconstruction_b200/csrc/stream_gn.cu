@@ -307,7 +307,7 @@ struct SgBwdStream {
 };
 
 template <int CC, bool HEAD>
-__global__ void __launch_bounds__(256) gn_bwd_stats_stream_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
+__global__ void __launch_bounds__(256, 3) gn_bwd_stats_stream_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
     constexpr int NC = CC >= 0 ? CC : SG_MAX_CC;
     constexpr int NV = 4 + NC;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_stream_kernel(GnBwdArgs a, f
 }
 
 template <bool HEAD>
-__global__ void __launch_bounds__(256) gn_bwd_apply_stream_kernel(GnBwdArgs a, const float* __restrict__ gstat,
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_stream_kernel(GnBwdArgs a, const float* __restrict__ gstat,
                                                                   bf16* __restrict__ d_raw, float* __restrict__ partial_bias,
                                                                   int depth) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -583,7 +583,7 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     const int C = a.C, Cc = a.Cc;
     const SgBwdLayout lay = sg_bwd_layout(C, Cc, a.do_a != nullptr, a.do_pool != nullptr);
     const int n_tr = 256 / (C / 4), nvr = 4 + Cc;
-    const int depth = lay.stage > 20000 ? 3 : 4;
+    const int depth = lay.stage > 20000 ? 3 : 4;        // <= 75 KB per CTA: three CTAs per SM
     size_t smem = (size_t)depth * lay.stage + 64;
     const size_t red_bytes = (size_t)n_tr * C * nvr * sizeof(float);
     if (smem < red_bytes) smem = red_bytes;
@@ -611,7 +611,7 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
 int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_raw, float* partial_bias, cudaStream_t st) {
     const int C = a.C;
     const SgBwdLayout lay = sg_bwd_layout(C, 0, a.do_a != nullptr, a.do_pool != nullptr);
-    const int depth = lay.stage > 20000 ? 3 : 4;
+    const int depth = lay.stage > 20000 ? 2 : 3;        // + 16 KB of output staging: <= 75 KB per CTA, three CTAs per SM
     const size_t smem = (size_t)depth * lay.stage + 2 * SG_STAGE_BYTES + 64;
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
     if (a.do_eps != nullptr) {

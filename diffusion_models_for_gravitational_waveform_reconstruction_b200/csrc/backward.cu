@@ -1088,6 +1088,10 @@ extern "C" int gw_wgrad3_simt(const void* src0, int C0, int L0, int up0, const v
     return reduce_rows(scratch, (int)n_split, per, per, 1.0f, dW, 1, st);
 }
 
+int wgrad_in_stream(const float* x, int B, int Cx, int L, const void* d_raw, float* scratch, long scratch_elems, int* n_rows,
+                    cudaStream_t st);
+extern int g_gn_bwd_stream;
+
 // wgrad of the first conv (models.py:204): dW[co][ci][k] = sum d_raw[b,l,co] * x[b,ci,l+k-1], x fp32 [B, Cx, L].
 // A thread owns one channel PAIR and walks groups of 4 consecutive rows: the 6 input samples a group needs are two
 // vector smem loads per input channel, reused by 4 rows x 3 taps x 2 channels of FMAs.
@@ -1164,6 +1168,12 @@ extern "C" int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_r
     GW_REQUIRE(C >= 64 && C <= 512 && 512 % C == 0, "gw_wgrad_in: C=%d", C);
     GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_wgrad_in: Cx=%d", Cx);
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_wgrad_in: dtype %d", dtype);
+    if (dtype == GW_BF16 && C == 64 && L % 4 == 0 && g_gn_bwd_stream) {       // HBM-streaming kernel (stream_gn.cu)
+        int n_rows = 0;
+        int rcs = wgrad_in_stream(x, B, Cx, L, d_raw, scratch, scratch_elems, &n_rows, (cudaStream_t)stream);
+        if (rcs != GW_OK) return rcs;
+        return reduce_rows(scratch, n_rows, (long)C * Cx * 3, (long)C * Cx * 3, 1.0f, dW, 1, (cudaStream_t)stream);
+    }
     int rows = 1024;
     if (rows > L) rows = (L + 3) & ~3;
     const int n_rc = gw_cdiv(L, rows), nv = Cx * 3;

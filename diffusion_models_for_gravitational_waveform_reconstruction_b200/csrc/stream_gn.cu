@@ -624,3 +624,118 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
+
+// ================================================================================================
+// wgrad of the first conv as a streaming kernel (see wgrad_in_kernel in backward.cu for the math):
+//   dW[co][ci][k] = sum_{b,l} d_raw[b,l,co] * x[b,ci,l+k-1]
+// d_raw rows go through the bulk-copy ring; the fp32 input rows of the CTA's range sit in shared memory for its lifetime.
+// ================================================================================================
+template <int CXM>
+__global__ void __launch_bounds__(256) wgrad_in_stream_kernel(const float* __restrict__ x, int Cx, int L,
+                                                              const bf16* __restrict__ d_raw, float* __restrict__ partial,
+                                                              int rows_per_cta) {
+    constexpr int C = 64, S = SG_STAGE_BYTES / (C * 2), D = SG_DEPTH;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* ring = smem;                                         // [D][8 KB]; reused for the final reduction
+    const int pitch = rows_per_cta + 8;
+    const int nv = Cx * 3;
+    const int ring_bytes = max(D * SG_STAGE_BYTES, 8 * C * nv * 4);
+    float* xs = reinterpret_cast<float*>(smem + ring_bytes);      // [Cx][pitch]: xs[ci][j] = x[ci][r0 - 1 + j]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + Cx * pitch);
+    const int b = blockIdx.y, r0 = blockIdx.x * rows_per_cta;
+    const int rows_here = min(rows_per_cta, L - r0);
+    const int n_sub = (rows_here + S - 1) / S;
+    const bf16* dbase = d_raw + ((size_t)b * L + r0) * C;
+    auto issue = [&](int i) {
+        const int st = i % D;
+        const int rows_i = min(S, rows_here - i * S);
+        const uint32_t bar = smem_u32(bars + st);
+        mbar_expect_tx(bar, (uint32_t)rows_i * C * 2);
+        bulk_load(smem_u32(ring + st * SG_STAGE_BYTES), dbase + (size_t)i * S * C, (uint32_t)rows_i * C * 2, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < D; ++s) mbar_init(smem_u32(bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < D && i < n_sub; ++i) issue(i);
+    }
+    for (int i = threadIdx.x; i < Cx * pitch; i += 256) {
+        const int c = i / pitch, p = i % pitch;
+        const int l = r0 + p - 1;
+        xs[i] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+    }
+    __syncthreads();
+    const int cp = threadIdx.x & 31, tr = threadIdx.x >> 5;      // channel pair, thread row (8)
+    float acc[2][CXM * 3];
+#pragma unroll
+    for (int i = 0; i < CXM * 3; ++i) { acc[0][i] = 0.0f; acc[1][i] = 0.0f; }
+    for (int i = 0; i < n_sub; ++i) {
+        const int st = i % D;
+        const int rows_i = min(S, rows_here - i * S);
+        mbar_wait(smem_u32(bars + st), (uint32_t)((i / D) & 1));
+        const uint8_t* sb = ring + st * SG_STAGE_BYTES;
+        for (int g = tr * 4; g < rows_i; g += 32) {             // groups of 4 consecutive rows
+            float d[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t w = (g + u < rows_i) ? *reinterpret_cast<const uint32_t*>(sb + ((size_t)(g + u) * C + cp * 2) * 2) : 0u;
+                d[u][0] = __uint_as_float(w << 16);
+                d[u][1] = __uint_as_float(w & 0xffff0000u);
+            }
+            const int j0 = i * S + g;                             // xs column of the group's first row, tap 0
+#pragma unroll
+            for (int ci = 0; ci < CXM; ++ci) {
+                if (ci < Cx) {
+                    const float4 xa = *reinterpret_cast<const float4*>(xs + ci * pitch + j0);
+                    const float2 xb = *reinterpret_cast<const float2*>(xs + ci * pitch + j0 + 4);
+                    const float xv[6] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            acc[0][ci * 3 + k] = fmaf(d[u][0], xv[u + k], acc[0][ci * 3 + k]);
+                            acc[1][ci * 3 + k] = fmaf(d[u][1], xv[u + k], acc[1][ci * 3 + k]);
+                        }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && i + D < n_sub) issue(i + D);
+    }
+    float* red = reinterpret_cast<float*>(ring);                  // [8][C][nv]
+#pragma unroll
+    for (int i = 0; i < CXM * 3; ++i)
+        if (i < nv) {
+            red[((size_t)tr * C + cp * 2) * nv + i] = acc[0][i];
+            red[((size_t)tr * C + cp * 2 + 1) * nv + i] = acc[1][i];
+        }
+    __syncthreads();
+    float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nv;
+    for (int i = threadIdx.x; i < C * nv; i += 256) {
+        float sacc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sacc += red[(size_t)t * C * nv + i];
+        pt[i] = sacc;
+    }
+}
+
+// launcher used by gw_wgrad_in (backward.cu) for bf16, C = 64, L % 4 == 0; returns the number of partial rows written
+int wgrad_in_stream(const float* x, int B, int Cx, int L, const void* d_raw, float* scratch, long scratch_elems, int* n_rows,
+                    cudaStream_t st) {
+    const int C = 64, rows = L < 512 ? ((L + 3) & ~3) : 512;
+    const int n_rc = gw_cdiv(L, rows), nv = Cx * 3;
+    GW_REQUIRE((long)B * n_rc * C * nv <= scratch_elems, "gw_wgrad_in: scratch too small");
+    const int ring = SG_DEPTH * SG_STAGE_BYTES > 8 * C * nv * 4 ? SG_DEPTH * SG_STAGE_BYTES : 8 * C * nv * 4;
+    const size_t smem = (size_t)ring + (size_t)Cx * (rows + 8) * 4 + 64;
+    dim3 grid(n_rc, B);
+#define WIS_GO(CXM)                                                                                                   \
+    do {                                                                                                              \
+        GW_CUDA(cudaFuncSetAttribute(wgrad_in_stream_kernel<CXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        wgrad_in_stream_kernel<CXM><<<grid, 256, smem, st>>>(x, Cx, L, (const bf16*)d_raw, scratch, rows);               \
+    } while (0)
+    if (Cx <= 4) WIS_GO(4); else if (Cx <= 8) WIS_GO(8); else WIS_GO(16);
+#undef WIS_GO
+    GW_LAUNCH_CHECK();
+    *n_rows = B * n_rc;
+    return GW_OK;
+}

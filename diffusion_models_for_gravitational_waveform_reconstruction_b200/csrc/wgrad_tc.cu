@@ -31,6 +31,8 @@ struct WgParams {
     int bn;          // 64 or 128
     int n_split;
     int stages;
+    int lo_tiles;    // mode 1 with Cout >= 128: M tiles [0, lo_tiles) hold only "lo" rows (position 2r) and need taps {-1, 0},
+                     // the rest only "hi" rows and need taps {0, +1}; 0 = every tile needs all three taps
 };
 
 // MN-major, 128-byte-swizzled operand: LBO [16,30) = byte distance between 64-element MN blocks, SBO [32,46) = between
@@ -73,6 +75,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int n_tiles = P.mt * P.nt;
     const int tile = blockIdx.x % n_tiles, split = blockIdx.x / n_tiles;
     const int m0 = (tile / P.nt) * 128, n0 = (tile % P.nt) * P.bn;
+    const int tap_lo = (P.lo_tiles > 0 && tile / P.nt >= P.lo_tiles) ? 1 : 0;
+    const int tap_hi = (P.lo_tiles > 0 && tile / P.nt < P.lo_tiles) ? 1 : 2;
     const long total = (long)P.B * P.n_chunk;
     const uint32_t tmem_cols = 512;                                // 3 x bn <= 384, power of two
 
@@ -121,6 +125,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t a0 = sA + stage * a_bytes, x0 = sX + stage * x_bytes;
 #pragma unroll
                 for (int tap = 0; tap < 3; ++tap) {
+                    if (tap < tap_lo || tap > tap_hi) continue;     // this tile's rows never use that tap (see WgParams::lo_tiles)
                     const uint32_t xt = shifted_desc ? x0 + (uint32_t)tap * 128u : x0 + (uint32_t)tap * nb * WG_X_BOX;
 #pragma unroll
                     for (int k = 0; k < WG_KR / 16; ++k) {
@@ -147,7 +152,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int tap = 0; tap < 3; ++tap) {
             for (int c0 = 0; c0 < P.bn; c0 += 32) {
                 uint32_t v[32];
-                if (any) {
+                if (any && tap >= tap_lo && tap <= tap_hi) {
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * P.bn + c0), v);
                 } else {
 #pragma unroll
@@ -277,6 +282,7 @@ static int wg_params(int mode, int B, int L, int Cout, int Cx, WgParams* P) {
     const long total = (long)B * P->n_chunk;
     if (ns > total) ns = total;
     P->n_split = (int)ns;
+    P->lo_tiles = (mode == 1 && Cout % 128 == 0) ? Cout / 128 : 0;
     return GW_OK;
 }
 

@@ -51,7 +51,7 @@ class _GradWorkspace:
         self.d_cat = e(cat_max) if simt else None
         n_scr = max(lib.gw_gn_bwd_scratch_elems(B, ws.lay_len[i], lc[i], spec.cond_in_ch) for i in range(2 * d + 1))
         n_scr = max(n_scr, B * ((ws.L + 511) // 512) * ((lc[-1] + 1) * 3 + 1), B * spec.base_ch,
-                    B * ((ws.L + 1023) // 1024) * lc[0] * spec.in_ch * 3)
+                    B * ((ws.L + 511) // 512) * lc[0] * spec.in_ch * 3)
         wmax = max(lc[i] * ((lc[i - 1] + (spec.chs[2 * d - i] if i > d else 0)) * 3) for i in range(1, 2 * d + 1))
         self.wg_elems = max(16 * wmax, 8 << 20)                           # split-K partials of the SIMT / tcgen05 wgrad
         for i in range(1, 2 * d + 1):

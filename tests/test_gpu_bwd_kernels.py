@@ -15,7 +15,7 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _run(in_ch, cc, B, L, dgrad, wgrad, wvariant=0):
+def _run(in_ch, cc, B, L, dgrad, wgrad, wvariant=0, fuse_head=False):
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
     from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import FusedTrainStep
     sd = make_state_dict(in_ch, cc, seed=4)
@@ -24,6 +24,7 @@ def _run(in_ch, cc, B, L, dgrad, wgrad, wvariant=0):
     m = m.cuda()
     st = FusedTrainStep(m, CustomDiffusion(T=1000, device="cuda"), B, L, compute_dtype="bf16", seed=5)
     st.bwd.dgrad_impl, st.bwd.wgrad_impl, st.bwd.wgrad_variant = dgrad, wgrad, wvariant
+    st.bwd.fuse_head = fuse_head
     d = synthetic_chirps(B, L, seed=9)
     cond = d["y_norm"] if cc == 1 else torch.cat([d["y_norm"], 0.2 * gaussian((B, 4, 1), 3).expand(B, 4, L)], 1)
     st.load_batch(d["clean_norm"].cuda(), cond.contiguous().cuda(), None)
@@ -36,8 +37,8 @@ def _run(in_ch, cc, B, L, dgrad, wgrad, wvariant=0):
 def test_tc_backward_matches_simt(in_ch, cc, B, L):
     _, ref = _run(in_ch, cc, B, L, "simt", "simt")
     for dg, wg, wv, what in [("simt", "tc", 1, "wgrad_tc (one box per tap)"), ("simt", "tc", 0, "wgrad_tc (shifted descriptors)"),
-                             ("tc", "simt", 0, "dgrad_tc"), ("tc", "tc", 0, "both")]:
-        _, got = _run(in_ch, cc, B, L, dg, wg, wv)
+                             ("tc", "simt", 0, "dgrad_tc"), ("tc", "tc", 0, "both"), ("tc", "tc", 2, "both + fused head gradient")]:
+        _, got = _run(in_ch, cc, B, L, dg, wg, wv & 1, fuse_head=bool(wv & 2))
         tot = float(torch.cat([v.reshape(-1) for v in ref.values()]).norm())
         for k in ref:
             err = float((got[k].double() - ref[k].double()).norm())

@@ -69,6 +69,8 @@ _SIGS.update({
     "gw_grad_sumsq": ([_P, _L, _P, _P], _I),
     "gw_adamw_ema": ([_P, _P, _P, _P, _P, _L, _P, _P, _P, _F, _F, _F, _P, _P], _I),
 })
+_SIGS["gw_score_batch"] = ([_P, _P, _P, _I, _I, C.c_double, C.c_double, _I, C.c_double, _P, _P], _I)
+_SIGS["gw_set_option"] = ([C.c_char_p, _I], _I)
 _EXTRA_SIGS = {}
 
 

@@ -29,6 +29,8 @@ extern "C" {
 #define GW_MAX_LEVELS 8
 
 int gw_version(void);
+/* runtime switches for A/B measurements: "gn_bwd_stream" (1 = HBM-streaming GroupNorm backward kernels, default) */
+int gw_set_option(const char* name, int value);
 const char* gw_last_error(void);
 int gw_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -237,6 +239,16 @@ int gw_opt_scratch_doubles(void);
 int gw_grad_sumsq(const float* g, long n, double* partial, void* stream);
 int gw_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, long n, const double* partial,
                  const float* hyper, const float* loss, float beta1, float beta2, float eps, float* info, void* stream);
+
+/* =====================================================================================================
+ * On-device scoring of reconstructions (inference.py:11-27, 247-279, 303-314; sweep_infer.py:8-13, 225-241).
+ * xhat, clean fp32 [B, L]; sigma fp32 [B] or NULL; out fp64 [B, 12]:
+ *   0 corr_last, 1 mae_last (tail window t >= t_max - secs), 2 nmae_sigma (last int(fs*secs) samples), 3 overlap,
+ *   4 best xcorr lag (|k| <= max_shift; <= 0 means L-1), 5 MAE / 6 NMAE_clean / 7 NMAE_sigma over [-80 ms, +40 ms] around the
+ *   clean peak after alignment, 8 peak index, 9 aligned length, 10 window count, 11 tail count.
+ * ===================================================================================================== */
+int gw_score_batch(const float* xhat, const float* clean, const float* sigma, int B, int L, double fs, double secs,
+                   int max_shift, double delta_t, double* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -296,6 +296,42 @@ def gen_proxy_and_helpers(M, I, TR, out):
     np.savez_compressed(os.path.join(out, "proxy_helpers.npz"), **rec)
 
 
+def gen_scores(I, out):
+    """Scores of the unmodified reference helpers (inference.py:11-27, 247-279 and the window MAE of :303-314,
+    sweep_infer.py:8-13, 232-237) on synthetic (clean, reconstruction) pairs."""
+    sys.path.insert(0, REF)
+    import sweep_infer as SW
+    L, B, fs = 2048, 6, 4096.0
+    d = synthetic_chirps(B, L, snr=12.0, seed=55)
+    clean = d["clean_norm"][:, 0].numpy()
+    rng = np.random.default_rng(9)
+    rec = {"sigma": (0.5 + rng.uniform(size=B)).astype(np.float32)}
+    xh = np.zeros_like(clean)
+    for b in range(B):
+        shift = int(rng.integers(-7, 8))
+        xh[b] = np.roll(clean[b], shift) * (0.8 + 0.05 * b) + 0.02 * rng.standard_normal(L).astype(np.float32)
+    rec["xhat"] = xh
+    cols = {k: [] for k in ["corr_last", "mae_last", "nmae_sigma", "best_lag_full", "best_lag_64", "xc_mae", "xc_nmae_clean",
+                            "xc_nmae_sigma", "objective"]}
+    for b in range(B):
+        m = I._score_last_window(xh[b], clean[b], fs, secs=0.2)
+        w = int(fs * 0.2)
+        nm = float(np.mean(np.abs(xh[b][L - w:] - clean[b][L - w:]))) / (float(rec["sigma"][b]) + 1e-12)
+        cols["corr_last"].append(m["corr_last"]); cols["mae_last"].append(m["mae_last"]); cols["nmae_sigma"].append(nm)
+        cols["best_lag_full"].append(I._best_lag_by_xcorr(clean[b], xh[b], 0))
+        cols["best_lag_64"].append(I._best_lag_by_xcorr(clean[b], xh[b], 64))
+        a_al, b_al, t_a = I._align_xcorr(clean[b], xh[b], 1.0 / fs, max_shift=64)
+        mask = (t_a >= -0.080) & (t_a <= 0.040)
+        mae = float(np.mean(np.abs(b_al[mask] - a_al[mask])))
+        cols["xc_mae"].append(mae)
+        cols["xc_nmae_clean"].append(mae / (float(np.mean(np.abs(a_al[mask]))) + 1e-12))
+        cols["xc_nmae_sigma"].append(mae / (float(rec["sigma"][b]) + 1e-12))
+        cols["objective"].append(SW._objective({"corr_last": m["corr_last"], "nmae_sigma": nm}, {"corr_last": m["corr_last"]}))
+    for k, v in cols.items():
+        rec[k] = np.array(v, dtype=np.float64)
+    np.savez_compressed(os.path.join(out, "scores.npz"), **rec)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
@@ -307,6 +343,7 @@ def main():
     gen_chains(M, I, args.out)
     gen_train(M, TR, args.out)
     gen_proxy_and_helpers(M, I, TR, args.out)
+    gen_scores(I, args.out)
     tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
     print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
 

@@ -49,6 +49,7 @@ def injections(start, count, L, seed):
 def run(a):
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import scoring
     from diffusion_models_for_gravitational_waveform_reconstruction_b200.parallel import shard_range
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -63,7 +64,7 @@ def run(a):
     model = model.to(dev).eval()
     diff = CustomDiffusion(T=1000, device=dev)
     start, count = shard_range(a.n, rank, world)
-    recon, clean, snr = [], [], []
+    recon, clean, snr, ov_dev, corr_dev = [], [], [], [], []
     torch.cuda.synchronize()
     t_data = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -78,21 +79,28 @@ def run(a):
         x0 = inf.ddim_sample(model, diff, y, 1000, a.steps, a.eta, dev, a.length, False, a.start_t, "noise", 0.14, 0.0, 1.0, 1.0,
                              "eps", 3, 1, True, 1.0, "const", 0.5, 0.3, 0.0, seed=a.seed, sample0=start + c0,
                              compute_dtype=a.dtype)
+        # scored on the device (gw_score_batch): overlap with the injected clean waveform, tail-window correlation
+        sc = scoring.score_batch(x0, d["clean_norm"].to(dev), 4096.0, sigma=d["sigma"].to(dev), secs=0.8, max_shift=1)
         e1.record()
         torch.cuda.synchronize()
         gpu_ms += e0.elapsed_time(e1)
+        ov_dev.append(sc["overlap"].cpu())
+        corr_dev.append(sc["corr_last"].cpu())
         recon.append(x0.cpu())
         clean.append(d["clean_norm"])
         snr.append(d["snr"])
     recon, clean, snr = torch.cat(recon), torch.cat(clean), torch.cat(snr)
+    ov_dev, corr_dev = torch.cat(ov_dev).float(), torch.cat(corr_dev).float()
     t = torch.tensor([gpu_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     res = None
     if rank == 0:
-        ov_clean = overlap(recon, clean)
+        ov_clean = ov_dev
+        assert float((overlap(recon, clean) - ov_dev).abs().max()) < 1e-5        # device scores == host recomputation
         res = {"n": a.n, "world": world, "steps": a.steps, "length": a.length, "dtype": a.dtype,
                "waveforms_per_s": a.n / (float(t[0]) / 1e3), "gpu_ms_max_rank": float(t[0]), "host_data_gen_s_rank0": t_data,
+               "tail_corr_vs_clean_mean": float(corr_dev.mean()),
                "overlap_vs_clean_by_snr": {f"{lo}-{lo + 5}": float(ov_clean[(snr >= lo) & (snr < lo + 5)].mean())
                                            for lo in range(5, 30, 5) if ((snr >= lo) & (snr < lo + 5)).any()}}
         if a.check > 0:

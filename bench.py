@@ -125,6 +125,16 @@ class TimedLib:
         return wrapped
 
 
+def measured_traffic(step_kind, kernel, B, L):
+    """Per-launch DRAM traffic of `kernel` from the committed ncu capture (profiles/r01g_traffic.json); only valid for the
+    shape it was captured at (B=256, L=4096), otherwise None."""
+    p = os.path.join(ROOT, "profiles", "r01g_traffic.json")
+    if not os.path.exists(p) or (B, L) != (256, 4096):
+        return None
+    d = json.load(open(p)).get(step_kind, {}).get(kernel)
+    return None if d is None else d["bytes_per_launch"]
+
+
 def make_inputs(B, L, cin, seed):
     from weights import synthetic_chirps
     d = synthetic_chirps(B, L, snr=10.0, seed=seed)
@@ -406,7 +416,9 @@ def bench_sampling(args, workload, B, steps, warmup, world, rank, dev, barrier, 
                "gpu_launches": launches_per_chain * steps, "clocks": clk,
                "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel (6 launches per reverse step, tcgen05+TMA implicit GEMM)",
                             "achieved": conv["achieved"], "peak": pk["bf16"], "unit": "TFLOP/s", "frac": conv["frac"],
-                            "traffic": None, "peak_source": pk["src"] + " burst (kernels timed one by one)",
+                            "traffic": measured_traffic("reverse_step", "conv_tc2_kernel", plan.Bn, L),
+                            "traffic_note": "bytes per launch, ncu capture profiles/r01g_traffic.json (B=256, L=4096, in_ch=3)",
+                            "peak_source": pk["src"] + " burst (kernels timed one by one)",
                             "share_of_step": conv["share_of_step"]},
                "kernels": fams,
                "chain": {"tflops_per_gpu": chain_tflops, "frac_of_sustained_bf16_peak": chain_tflops / pk["bf16_sustained"],
@@ -518,7 +530,9 @@ def bench_train(args, world, rank, dev, barrier, pk):
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel family (forward convs + dgrad, tcgen05+TMA implicit GEMM)",
-                         "achieved": conv["achieved"], "peak": pk["bf16"], "unit": "TFLOP/s", "frac": conv["frac"], "traffic": None,
+                         "achieved": conv["achieved"], "peak": pk["bf16"], "unit": "TFLOP/s", "frac": conv["frac"],
+                         "traffic": measured_traffic("train_step", "conv_tc2_kernel", B, L),
+                         "traffic_note": "bytes per launch, ncu capture profiles/r01g_traffic.json (B=256, L=4096, in_ch=7)",
                          "peak_source": pk["src"] + " burst (kernels timed one by one, eager)",
                          "share_of_step": conv["share_of_step"]},
             "kernels": fams,

@@ -8,16 +8,18 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libgwb200.so")
+LIB_FFT = os.path.join(PKG, "libgwb200_fft.so")
 SOURCES = ["forward.cu", "conv_tc.cu", "backward.cu", "optim.cu", "wgrad_tc.cu", "stream_gn.cu", "score.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(LIB_FFT):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG, "..", "include", "gwb200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG, "..", "include", "gwb200.h"),
+                                                              os.path.join(PKG, "..", "include", "gwb200_fft.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -49,6 +51,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    # whitening / sigma library: separate .so so that the core library has no cuFFT dependency
+    cmd = [nvcc, *flags, "-shared", "-o", LIB_FFT, os.path.join(CSRC, "whiten.cu"), "-lcufft", "-Xlinker",
+           "-rpath=/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"building {LIB_FFT} failed:\n{r.stdout}")
     return LIB
 
 

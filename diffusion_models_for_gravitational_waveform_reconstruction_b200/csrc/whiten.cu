@@ -1,0 +1,279 @@
+// GPU whitening / de-whitening and sigma estimation around the reverse chain.
+// Reference (numpy, one sample at a time, float64): inference.py:125-205 -- _pick_sigma / _mad_std, _whiten_pair_train_like,
+// _dewhiten_train_like, _whiten_pair_model, _dewhiten_model, _interp_psd_for_length; dataloader.py:110-151 uses the same
+// train-like recipe.  Here: batched fp64 cuFFT (D2Z / Z2D) with hand-written spectral kernels between the transforms.
+// Built as a separate library (libgwb200_fft.so) so that the core library carries no cuFFT dependency.
+#include "common.cuh"
+#include "../../include/gwb200_fft.h"
+#include <cufft.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+static thread_local char g_ferr[512] = "ok";
+void gw_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_ferr, sizeof(g_ferr), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* gwf_last_error(void) { return g_ferr; }
+
+#define GW_CUFFT(expr)                                                                      \
+    do {                                                                                    \
+        cufftResult _r = (expr);                                                            \
+        if (_r != CUFFT_SUCCESS) {                                                          \
+            gw_set_error("%s:%d %s -> cufft error %d", __FILE__, __LINE__, #expr, (int)_r); \
+            return GW_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------- plans (cached per shape)
+static std::mutex g_plan_mu;
+static std::map<std::tuple<int, int, int>, cufftHandle> g_plans;      // (kind 0 = D2Z / 1 = Z2D, L, B)
+static int get_plan(int kind, int L, int B, cufftHandle* out) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto key = std::make_tuple(kind, L, B);
+    auto it = g_plans.find(key);
+    if (it == g_plans.end()) {
+        cufftHandle h;
+        int n[1] = {L};
+        GW_CUFFT(cufftPlanMany(&h, 1, n, nullptr, 1, L, nullptr, 1, L / 2 + 1, kind == 0 ? CUFFT_D2Z : CUFFT_Z2D, B));
+        it = g_plans.emplace(key, h).first;
+    }
+    *out = it->second;
+    return GW_OK;
+}
+
+__device__ __forceinline__ double blk_sum_d(double v, double* red) {
+    v = warp_sum_d(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+// y (fp32) -> y64 - mean(y64) (or plain cast when demean == 0); one CTA per sample
+__global__ void __launch_bounds__(256) to_f64_kernel(const float* __restrict__ y, int L, int demean, double* __restrict__ out) {
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    double s = 0.0;
+    if (demean) {
+        for (int i = threadIdx.x; i < L; i += 256) s += (double)y[(size_t)b * L + i];
+        s = blk_sum_d(s, red) / (double)L;
+    }
+    for (int i = threadIdx.x; i < L; i += 256) out[(size_t)b * L + i] = (double)y[(size_t)b * L + i] - s;
+}
+
+// P = max(conv_same(|Y|^2, ones(9)/9), 1e-20)   (inference.py:141-146: np.convolve(P, kernel, mode="same") when P.size > 9)
+__global__ void __launch_bounds__(256) periodogram_kernel(const cufftDoubleComplex* __restrict__ Y, int F, double* __restrict__ P) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const cufftDoubleComplex* yb = Y + (size_t)b * F;
+    double acc = 0.0;
+    if (F > 9) {
+        // numpy accumulates the 9 products in index order of the full convolution: sum_j P[f + 4 - j] * k[j]
+        for (int j = 0; j < 9; ++j) {
+            const int i = f + 4 - j;
+            if (i >= 0 && i < F) acc += (yb[i].x * yb[i].x + yb[i].y * yb[i].y) * (1.0 / 9.0);
+        }
+    } else {
+        acc = yb[f].x * yb[f].x + yb[f].y * yb[f].y;
+    }
+    P[(size_t)b * F + f] = fmax(acc, 1e-20);
+}
+
+// Z = Y * g(P):  mode 0: 1/sqrt(P)   mode 1: 1/sqrt(P + 1e-12)   mode 2: sqrt(P + 1e-12)
+__global__ void __launch_bounds__(256) spectral_scale_kernel(const cufftDoubleComplex* __restrict__ Y, const double* __restrict__ P,
+                                                             long p_b_stride, int F, int mode, cufftDoubleComplex* __restrict__ Z) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const double p = P[(size_t)b * p_b_stride + f];
+    const cufftDoubleComplex y = Y[(size_t)b * F + f];
+    cufftDoubleComplex z;
+    if (mode == 2) {
+        const double g = sqrt(p + 1e-12);
+        z.x = y.x * g; z.y = y.y * g;
+    } else {
+        const double g = sqrt(mode == 0 ? p : p + 1e-12);
+        z.x = y.x / g; z.y = y.y / g;
+    }
+    Z[(size_t)b * F + f] = z;
+}
+
+// irfft normalisation (1/L) + optional cast to fp32
+__global__ void __launch_bounds__(256) finish_kernel(const double* __restrict__ t, long n, double scale, float* __restrict__ o32,
+                                                     double* __restrict__ o64) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const double v = t[i] * scale;
+        if (o32) o32[i] = (float)v;
+        if (o64) o64[i] = v;
+    }
+}
+
+extern "C" long gwf_workspace_bytes(int B, int L) {
+    const long F = L / 2 + 1;
+    return (long)B * L * 8 + 2 * (long)B * F * 16;            // time-domain fp64 buffer + two spectra
+}
+
+static int fft_forward(const float* y, int demean, int B, int L, double* tbuf, cufftDoubleComplex* Y, cudaStream_t st) {
+    to_f64_kernel<<<B, 256, 0, st>>>(y, L, demean, tbuf);
+    GW_LAUNCH_CHECK();
+    cufftHandle h;
+    int rc = get_plan(0, L, B, &h);
+    if (rc != GW_OK) return rc;
+    GW_CUFFT(cufftSetStream(h, st));
+    GW_CUFFT(cufftExecD2Z(h, tbuf, Y));
+    return GW_OK;
+}
+static int fft_inverse(cufftDoubleComplex* Z, int B, int L, double* tbuf, float* o32, double* o64, cudaStream_t st) {
+    cufftHandle h;
+    int rc = get_plan(1, L, B, &h);
+    if (rc != GW_OK) return rc;
+    GW_CUFFT(cufftSetStream(h, st));
+    GW_CUFFT(cufftExecZ2D(h, Z, tbuf));
+    const long n = (long)B * L;
+    int grid = (int)((n + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    finish_kernel<<<grid, 256, 0, st>>>(tbuf, n, 1.0 / (double)L, o32, o64);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// _whiten_pair_train_like (inference.py:137-153): y, x fp32 [B, L] (x may be NULL) -> y_w, x_w fp32 [B, L], P fp64 [B, L/2+1]
+extern "C" int gwf_whiten_train_like(const float* y, const float* x, int B, int L, float* y_w, float* x_w, double* P, void* work,
+                                     void* stream) {
+    GW_REQUIRE(B > 0 && L >= 2 && y && y_w && P && work, "gwf_whiten_train_like: arguments");
+    GW_REQUIRE((x == nullptr) == (x_w == nullptr), "gwf_whiten_train_like: x / x_w mismatch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = L / 2 + 1;
+    double* tbuf = (double*)work;
+    cufftDoubleComplex* Y = (cufftDoubleComplex*)(tbuf + (size_t)B * L);
+    cufftDoubleComplex* Z = Y + (size_t)B * F;
+    int rc = fft_forward(y, 1, B, L, tbuf, Y, st);
+    if (rc != GW_OK) return rc;
+    dim3 g(gw_cdiv(F, 256), B);
+    periodogram_kernel<<<g, 256, 0, st>>>(Y, F, P);
+    GW_LAUNCH_CHECK();
+    spectral_scale_kernel<<<g, 256, 0, st>>>(Y, P, F, F, 0, Z);
+    GW_LAUNCH_CHECK();
+    if ((rc = fft_inverse(Z, B, L, tbuf, y_w, nullptr, st)) != GW_OK) return rc;
+    if (x != nullptr) {
+        if ((rc = fft_forward(x, 1, B, L, tbuf, Y, st)) != GW_OK) return rc;
+        spectral_scale_kernel<<<g, 256, 0, st>>>(Y, P, F, F, 0, Z);
+        GW_LAUNCH_CHECK();
+        if ((rc = fft_inverse(Z, B, L, tbuf, x_w, nullptr, st)) != GW_OK) return rc;
+    }
+    return GW_OK;
+}
+
+// spectral multiply / divide by a given PSD: mode 1 = whiten with 1/sqrt(P + 1e-12) (_whiten_pair_model, inference.py:190-199, no
+// mean removal), mode 2 = de-whiten with sqrt(P + 1e-12) (_dewhiten_train_like / _dewhiten_model, inference.py:155-159, 201-203).
+// P fp64 [B, L/2+1] or one shared row (p_shared != 0).  Output fp32 (o32) and / or fp64 (o64).
+extern "C" int gwf_apply_psd(const float* sig, int B, int L, const double* P, int p_shared, int mode, float* o32, double* o64,
+                             void* work, void* stream) {
+    GW_REQUIRE(B > 0 && L >= 2 && sig && P && work && (o32 || o64) && (mode == 1 || mode == 2), "gwf_apply_psd: arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = L / 2 + 1;
+    double* tbuf = (double*)work;
+    cufftDoubleComplex* Y = (cufftDoubleComplex*)(tbuf + (size_t)B * L);
+    cufftDoubleComplex* Z = Y + (size_t)B * F;
+    int rc = fft_forward(sig, 0, B, L, tbuf, Y, st);
+    if (rc != GW_OK) return rc;
+    dim3 g(gw_cdiv(F, 256), B);
+    spectral_scale_kernel<<<g, 256, 0, st>>>(Y, P, p_shared ? 0 : F, F, mode, Z);
+    GW_LAUNCH_CHECK();
+    return fft_inverse(Z, B, L, tbuf, o32, o64, st);
+}
+
+// _interp_psd_for_length (inference.py:181-188): np.interp of a model PSD given on rfftfreq(2*(n_src-1), 1/fs) onto rfftfreq(L, 1/fs)
+__global__ void interp_psd_kernel(const double* __restrict__ Ps, int n_src, int L, double fs, double* __restrict__ out) {
+    const int F = L / 2 + 1;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    if (n_src == F) { out[f] = Ps[f]; return; }
+    const int Ls = n_src * 2 - 2;
+    const double df_s = 1.0 / ((double)Ls * (1.0 / fs)), df_t = 1.0 / ((double)L * (1.0 / fs));   // rfftfreq: k / (n*d)
+    const double x = (double)f * df_t;
+    // np.interp: left/right = end values; linear in between on the grid xp[k] = k * df_s
+    if (x <= 0.0) { out[f] = Ps[0]; return; }
+    const double xmax = (double)(n_src - 1) * df_s;
+    if (x >= xmax) { out[f] = Ps[n_src - 1]; return; }
+    int k = (int)(x / df_s);
+    if (k > n_src - 2) k = n_src - 2;
+    while (k > 0 && (double)k * df_s > x) --k;
+    while (k < n_src - 2 && (double)(k + 1) * df_s <= x) ++k;
+    const double x0 = (double)k * df_s, x1 = (double)(k + 1) * df_s;
+    const double slope = (Ps[k + 1] - Ps[k]) / (x1 - x0);
+    out[f] = slope * (x - x0) + Ps[k];
+}
+extern "C" int gwf_interp_psd(const double* P_src, int n_src, int L, double fs, double* out, void* stream) {
+    GW_REQUIRE(P_src && out && n_src >= 2 && L >= 2 && fs > 0.0, "gwf_interp_psd: arguments");
+    interp_psd_kernel<<<gw_cdiv(L / 2 + 1, 256), 256, 0, (cudaStream_t)stream>>>(P_src, n_src, L, fs, out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- sigma (_pick_sigma)
+// mode 0: np.std(y64) (population);  mode 1: 1.4826 * median(|y64 - median(y64)|) + 1e-24  (bitonic sort in shared memory)
+__device__ void bitonic_sort(double* v, int n) {        // n = power of two, all threads of the CTA participate
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool up = (i & k) == 0;
+                    const double a = v[i], c = v[p];
+                    if ((a > c) == up) { v[i] = c; v[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+__device__ double median_sorted(const double* v, int L) { return (L & 1) ? v[L / 2] : 0.5 * (v[L / 2 - 1] + v[L / 2]); }
+
+__global__ void __launch_bounds__(256) sigma_kernel(const float* __restrict__ y, int L, int n2, int mode, double* __restrict__ out) {
+    extern __shared__ double sv[];
+    __shared__ double red[8];
+    const int b = blockIdx.x;
+    const float* yb = y + (size_t)b * L;
+    if (mode == 0) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < L; i += 256) s += (double)yb[i];
+        const double mean = blk_sum_d(s, red) / (double)L;
+        double q = 0.0;
+        for (int i = threadIdx.x; i < L; i += 256) {
+            const double d = (double)yb[i] - mean;
+            q += d * d;
+        }
+        q = blk_sum_d(q, red);
+        if (threadIdx.x == 0) out[b] = sqrt(q / (double)L);
+        return;
+    }
+    for (int i = threadIdx.x; i < n2; i += 256) sv[i] = i < L ? (double)yb[i] : 1.0e300;
+    __syncthreads();
+    bitonic_sort(sv, n2);
+    const double med = median_sorted(sv, L);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n2; i += 256) sv[i] = i < L ? fabs((double)yb[i] - med) : 1.0e300;
+    __syncthreads();
+    bitonic_sort(sv, n2);
+    if (threadIdx.x == 0) out[b] = 1.4826 * median_sorted(sv, L) + 1e-24;
+}
+extern "C" int gwf_sigma(const float* y, int B, int L, int mode, double* out, void* stream) {
+    GW_REQUIRE(y && out && B > 0 && L > 0 && (mode == 0 || mode == 1), "gwf_sigma: arguments");
+    int n2 = 1;
+    while (n2 < L) n2 <<= 1;
+    const size_t smem = mode == 1 ? (size_t)n2 * sizeof(double) : 0;
+    GW_REQUIRE(smem <= 200 * 1024, "gwf_sigma: MAD needs L <= 16384 (L=%d)", L);
+    if (smem > 48 * 1024) GW_CUDA(cudaFuncSetAttribute(sigma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sigma_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(y, L, n2, mode, out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}

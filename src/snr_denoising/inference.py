@@ -7,6 +7,7 @@ if _ROOT not in _sys.path:
     _sys.path.insert(0, _ROOT)
 
 from diffusion_models_for_gravitational_waveform_reconstruction_b200.inference import (  # noqa: E402,F401
-    _build_t_schedule, _cfg_weight, _reduce_to_one_channel, ddim_sample, make_sampler_plan,
-    one_step_proxy_like_test_infer, snr_from_alpha_bar, t_for_target_snr)
+    _build_t_schedule, _cfg_weight, _dewhiten_model, _dewhiten_train_like, _interp_psd_for_length, _mad_std, _pick_sigma,
+    _reduce_to_one_channel, _whiten_pair_model, _whiten_pair_train_like, ddim_sample, make_sampler_plan,
+    one_step_proxy_like_test_infer, philox_normal, snr_from_alpha_bar, t_for_target_snr)
 from diffusion_models_for_gravitational_waveform_reconstruction_b200.models import CustomDiffusion, UNet1D  # noqa: E402,F401

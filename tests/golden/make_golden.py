@@ -332,6 +332,29 @@ def gen_scores(I, out):
     np.savez_compressed(os.path.join(out, "scores.npz"), **rec)
 
 
+def gen_whitening(I, out):
+    """Outputs of the unmodified reference whitening / sigma helpers (inference.py:36-38, 125-205) on coloured synthetic data."""
+    rng = np.random.default_rng(21)
+    fs = 4096.0
+    rec = {}
+    for L in (2048, 1000):
+        n = rng.standard_normal(L + 64)
+        col = np.convolve(n, np.hanning(33) / np.hanning(33).sum(), mode="valid")[:L]       # coloured noise
+        clean = synthetic_chirps(1, L, snr=8.0, seed=70 + L)["clean_norm"][0, 0].numpy().astype(np.float64) * 0.3
+        y = (col * 3.0 + clean + 0.7).astype(np.float32)
+        x = clean.astype(np.float32)
+        y_w, x_w, P = I._whiten_pair_train_like(y, x, fs)
+        back = I._dewhiten_train_like(y_w, P)
+        P_model = 1e-3 + np.abs(np.sin(np.linspace(0, 3, 513))) ** 2 + np.linspace(0, 1, 513)
+        ym, xm, Pm = I._whiten_pair_model(y, x, P_model, fs)
+        backm = I._dewhiten_model(ym, Pm)
+        rec.update({f"y_{L}": y, f"x_{L}": x, f"yw_{L}": y_w, f"xw_{L}": x_w, f"P_{L}": P, f"back_{L}": back,
+                    f"Pmodel_{L}": P_model, f"ym_{L}": ym, f"xm_{L}": xm, f"Pm_{L}": Pm, f"backm_{L}": backm,
+                    f"sig_std_{L}": np.array(I._pick_sigma(y, "std", 1.0)), f"sig_mad_{L}": np.array(I._pick_sigma(y, "mad", 1.0)),
+                    f"sig_fixed_{L}": np.array(I._pick_sigma(y, "fixed", 2.5))})
+    np.savez_compressed(os.path.join(out, "whitening.npz"), **rec)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
@@ -344,6 +367,7 @@ def main():
     gen_train(M, TR, args.out)
     gen_proxy_and_helpers(M, I, TR, args.out)
     gen_scores(I, args.out)
+    gen_whitening(I, args.out)
     tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
     print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
 

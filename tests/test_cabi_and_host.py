@@ -30,6 +30,17 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.gw_version() >= 100
 
 
+def test_fft_library_exports_every_declared_symbol(lib):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening
+    hdr = open(os.path.join(ROOT, "include", "gwb200_fft.h")).read()
+    names = set(re.findall(r"^\s*(?:int|long|const char\*)\s+(gwf_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert names == set(whitening.exported_symbols()) and len(names) == 6
+    flib = whitening.load()
+    for n in names:
+        assert hasattr(flib, n)
+    assert flib.gwf_workspace_bytes(2, 1024) == 2 * 1024 * 8 + 2 * 2 * 513 * 16
+
+
 def test_conv_tc_shape_helpers(lib):
     from diffusion_models_for_gravitational_waveform_reconstruction_b200._cabi import ConvTcShape
     # dec0 at L=1024: pair space, two phase tiles of 256 columns, 20 segments of 64

@@ -1,0 +1,56 @@
+"""GPU whitening / de-whitening / sigma against outputs of the unmodified reference helpers
+(tests/golden/whitening.npz, make_golden.py:gen_whitening).
+
+Tolerances: the whitened float32 outputs and the float64 PSD come from fp64 FFTs on both sides (pocketfft vs cuFFT): rel-L2
+<= 1e-6 (float32 rounding of the output dominates), PSD <= 1e-10.  De-whitening: numpy >= 2 transforms a float32 input in
+single precision (inference.py:157 gets the float32 y_w), cuFFT here runs in fp64: rel-L2 <= 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+@pytest.mark.parametrize("L", [2048, 1000])
+def test_whitening_matches_reference_golden(golden_dir, L):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening as W
+    g = np.load(os.path.join(golden_dir, "whitening.npz"))
+    y, x = g[f"y_{L}"], g[f"x_{L}"]
+    y_w, x_w, P = W._whiten_pair_train_like(y, x, 4096.0)
+    assert y_w.dtype == np.float32 and P.dtype == np.float64 and P.shape == (L // 2 + 1,)
+    assert rel(P, g[f"P_{L}"]) <= 1e-10
+    assert rel(y_w, g[f"yw_{L}"]) <= 1e-6 and rel(x_w, g[f"xw_{L}"]) <= 1e-6
+    assert W._whiten_pair_train_like(y, None, 4096.0)[1] is None
+    assert rel(W._dewhiten_train_like(g[f"yw_{L}"], g[f"P_{L}"]), g[f"back_{L}"]) <= 1e-5
+    ym, xm, Pm = W._whiten_pair_model(y, x, g[f"Pmodel_{L}"], 4096.0)
+    assert rel(Pm, g[f"Pm_{L}"]) <= 1e-12
+    assert rel(ym, g[f"ym_{L}"]) <= 1e-6 and rel(xm, g[f"xm_{L}"]) <= 1e-6
+    assert rel(W._dewhiten_model(g[f"ym_{L}"], g[f"Pm_{L}"]), g[f"backm_{L}"]) <= 1e-5
+    assert abs(W._pick_sigma(y, "std", 1.0) - float(g[f"sig_std_{L}"])) <= 1e-12 * float(g[f"sig_std_{L}"])
+    assert abs(W._pick_sigma(y, "mad", 1.0) - float(g[f"sig_mad_{L}"])) <= 1e-12 * float(g[f"sig_mad_{L}"])
+    assert W._pick_sigma(y, "fixed", 2.5) == float(g[f"sig_fixed_{L}"])
+    with pytest.raises(ValueError):
+        W._pick_sigma(y, "bogus", 1.0)
+
+
+def test_batched_whitening_equals_per_sample_and_round_trips(golden_dir):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening as W
+    g = np.load(os.path.join(golden_dir, "whitening.npz"))
+    y = torch.from_numpy(np.stack([g["y_2048"], g["y_2048"][::-1].copy(), 2.0 * g["y_2048"]])).cuda()
+    y_w, _, P = W.whiten_train_like(y)
+    assert rel(y_w[0].cpu().numpy(), g["yw_2048"]) <= 1e-6
+    # whiten -> de-whiten returns the mean-removed input (spectral floor aside)
+    back = W.apply_psd(y_w, P, dewhiten=True)
+    ref = (y.double() - y.double().mean(dim=1, keepdim=True)).cpu().numpy()
+    assert rel(back.cpu().numpy(), ref) <= 1e-5
+    s = W.sigma(y, "std")
+    assert torch.allclose(s, y.double().std(dim=1, unbiased=False), rtol=1e-12)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        W.whiten_train_like(torch.zeros(1, 64))

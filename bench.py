@@ -317,7 +317,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm: sampling
@@ -568,7 +568,7 @@ def run_ours(args):
             samp = bench_sampling(args, "ddpm1000", args.batch, 2, 3, world, rank, dev, barrier, pk, with_cpu=True)
         if rank == 0:
             line["sampling"] = samp
-            print(json.dumps(line))
+            emit(line)
     else:
         B = args.batch
         res = bench_sampling(args, args.workload, B, args.steps, max(args.warmup, 3), world, rank, dev, barrier, pk)
@@ -583,12 +583,30 @@ def run_ours(args):
                                "weights": "random-init (numpy PCG64 seed 0), final.* ~ N(0,0.05^2)"},
                     "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "roofline": res["roofline"],
                     "kernels": res["kernels"], "chain": res["chain"], "cpu_baseline": res.get("cpu_baseline")}
-            print(json.dumps(line))
+            emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else a library prints there (e.g. NCCL's
+    "NCCL version ..." banner) has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                     # stray prints of native libraries -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -473,6 +473,20 @@ class FusedTrainStep:
     def state_dict_ema(self) -> Dict[str, Tensor]:
         return {k: v.clone() for k, v in self.layout.views(self.flat_ema).items()} if self.flat_ema is not None else {}
 
+    def optimizer_state_dict(self) -> Dict:
+        """The flat AdamW moments in `torch.optim.AdamW.state_dict()` layout (parameters indexed in `model.parameters()` order),
+        which is what the reference stores under 'optimizer_state' (train.py:610)."""
+        m, v = self.layout.views(self.flat_m), self.layout.views(self.flat_v)
+        names = [k for k, _ in self.model.named_parameters()]
+        state = {i: {"step": torch.tensor(float(self.steps_done)), "exp_avg": m[k].clone(), "exp_avg_sq": v[k].clone()}
+                 for i, k in enumerate(names)}
+        group = {"lr": getattr(self, "last_lr", self.lr), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": list(range(len(names)))}
+        if self.use_sched:
+            group["initial_lr"] = self.lr
+        return {"state": state, "param_groups": [group]}
+
     def load_batch(self, clean_norm: Tensor, cond_stack: Tensor, mask: Optional[Tensor] = None) -> None:
         """clean_norm [B,1,L], cond_stack [B,Cc,L] (sigma-normalised, train.py:336-347), mask [B,1,L]; async H2D if pinned."""
         B, L = self.B, self.L
@@ -684,8 +698,21 @@ def train_diffusion(args, loader=None):
                          drop=(torch.rand(stepper.B, device=device) < p_uncond).float() if t_inj is not None else None)
             history.append(stepper.loss.clone())              # device scalar; read back once per epoch below
         history = [float(h) if isinstance(h, Tensor) else h for h in history]
-    return {"model": model, "stepper": stepper, "losses": history,
-            "checkpoint": {"model_state": model.state_dict(), "epoch": args.epochs,
-                           "model_ema_state": stepper.state_dict_ema() if stepper is not None else {},
-                           "args": {**vars(args), "in_ch": in_ch, "cond_in_ch": cond_in_ch, "meta_enabled": C_meta > 0,
-                                    "meta_channels": C_meta, "conditioning": "y+meta" if C_meta > 0 else "y"}}}
+    # checkpoint payload of train.py:606-630 (same keys; 'model_ema_state' only with --ema)
+    payload = {"model_state": {k: v.detach().clone() for k, v in model.state_dict().items()},
+               "optimizer_state": stepper.optimizer_state_dict() if stepper is not None else {},
+               "args": {**vars(args), "conditional": True, "in_ch": in_ch, "cond_in_ch": cond_in_ch, "meta_enabled": C_meta > 0,
+                        "meta_channels": C_meta,
+                        "conditioning": "concat[y + meta]+selfcond" if C_meta > 0 else "concat[y]+selfcond",
+                        "whiten": getattr(args, "whiten", False), "whiten_mode": getattr(args, "whiten_mode", "auto"),
+                        "sigma_mode": getattr(args, "sigma_mode", "std"), "dropout_y_only": bool(args.dropout_y_only),
+                        "meta_scale": getattr(args, "meta_scale", {"M": 80.0, "q": 10.0})},
+               "epoch": args.epochs}
+    if getattr(args, "ema", False) and stepper is not None:
+        payload["model_ema_state"] = stepper.state_dict_ema()
+    if getattr(args, "model_dir", None):                       # train.py:17-27, 607: <model_dir>/latest_model/model_diffusion.pth
+        import os
+        out_dir = os.path.join(args.model_dir, "latest_model")
+        os.makedirs(out_dir, exist_ok=True)
+        torch.save(payload, os.path.join(out_dir, "model_diffusion.pth"))
+    return {"model": model, "stepper": stepper, "losses": history, "checkpoint": payload}

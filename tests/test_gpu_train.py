@@ -207,7 +207,7 @@ def test_loss_kernel_mse_weight_and_mask():
         assert rel_l2(de, ehr.grad) <= 1e-6
 
 
-def test_train_diffusion_entry_point_runs_and_learns():
+def test_train_diffusion_entry_point_runs_and_learns(tmp_path):
     """train.train_diffusion(args, loader) with the reference's argparse names on a synthetic pad_collate-style loader."""
     import argparse
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import train as TR
@@ -224,15 +224,28 @@ def test_train_diffusion_entry_point_runs_and_learns():
                               weight_decay=1e-4, clip_grad=1.0, ema=True, ema_decay=0.9, loss="huber", huber_beta=0.5,
                               loss_weight_power=0.0, clamp_inputs=10.0, p_uncond=0.2, p_selfcond=0.5, dropout_y_only=True,
                               t_min_frac=0.5, warmup_steps=2, min_lr_scale=0.1, cosine_decay=True, force_cond_epochs=1,
-                              t_cover="rand", t_bins=0, t_multi=1, amp=False, init_from=None)
+                              t_cover="rand", t_bins=0, t_multi=1, amp=False, init_from=None, model_dir=str(tmp_path))
     out = TR.train_diffusion(args, loader)
     losses = out["losses"]
     assert len(losses) == 12 and all(np.isfinite(losses))
     assert np.mean(losses[-3:]) < np.mean(losses[:3])                    # the head starts at zero (models.py:132-134): it learns
     ck = out["checkpoint"]
-    assert set(ck) >= {"model_state", "model_ema_state", "args", "epoch"} and ck["args"]["in_ch"] == 7 and ck["args"]["cond_in_ch"] == 5
+    assert set(ck) == {"model_state", "optimizer_state", "model_ema_state", "args", "epoch"}          # train.py:608-628
+    assert ck["args"]["in_ch"] == 7 and ck["args"]["cond_in_ch"] == 5 and ck["args"]["meta_channels"] == 4
     assert len(ck["model_state"]) == 60 and len(ck["model_ema_state"]) == 60
     assert float((ck["model_state"]["final.weight"] - ck["model_ema_state"]["final.weight"]).abs().max()) > 0
+    # the file the reference's inference CLI reads (inference.py:614-650): rebuild from ckpt['args'], strict load of EMA weights
+    saved = torch.load(os.path.join(args.model_dir, "latest_model", "model_diffusion.pth"), map_location="cuda", weights_only=False)
+    a2 = saved["args"]
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import UNet1D
+    m2 = UNet1D(in_ch=a2["in_ch"], base_ch=a2["base_ch"], time_dim=a2["time_dim"], depth=a2["depth"],
+                t_embed_max_time=max(0, a2["T"] - 1), cond_in_ch=a2["cond_in_ch"],
+                use_selfcond=(a2["in_ch"] == 1 + a2["cond_in_ch"] + 1)).cuda()
+    m2.load_state_dict(saved["model_ema_state"], strict=True)
+    # and torch's own AdamW accepts the optimiser state
+    opt = torch.optim.AdamW(m2.parameters(), lr=1e-3)
+    opt.load_state_dict(saved["optimizer_state"])
+    assert len(opt.state_dict()["state"]) == 60 and float(opt.state_dict()["state"][0]["step"]) == 12.0
     # stratified timesteps + AMP (bf16 / tcgen05) flavour
     args.t_cover, args.t_bins, args.amp, args.epochs = "strat", 4, True, 1
     out2 = TR.train_diffusion(args, loader)

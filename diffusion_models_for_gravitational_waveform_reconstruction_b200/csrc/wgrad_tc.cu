@@ -53,7 +53,8 @@ __device__ __forceinline__ uint32_t make_idesc_mn(uint32_t m, uint32_t n) {
 
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_x,
-                const __grid_constant__ WgParams P, float* __restrict__ partial, int shifted_desc) {
+                const __grid_constant__ WgParams P, float* __restrict__ partial, int shifted_desc, float* __restrict__ dW_atomic,
+                int mode, int Cout, int Cin_total, int ci_off) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = P.stages;
@@ -148,6 +149,35 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             mbar_wait(acc_full, 0);
             tc_fence_after();
         }
+        if (dW_atomic != nullptr) {
+            // split-K by fp32 atomics straight into dW (red.global.add.f32): no partial buffer, no fold / scatter passes;
+            // the summation order over the CTAs is not fixed (run-to-run differences at the 1e-7 level)
+            const int m = m0 + q * 32 + lane;                        // row of the [M, N] product this lane owns
+            const int M = mode == 1 ? 2 * Cout : Cout;
+            for (int tap = tap_lo; tap <= tap_hi && any; ++tap) {
+                for (int c0 = 0; c0 < P.bn; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * P.bn + c0), v);
+                    if (m >= M) continue;
+                    const int co = mode == 1 ? m % Cout : m;
+                    const bool hi = mode == 1 && m >= Cout;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float g = __uint_as_float(v[i]);
+                        float* d = dW_atomic + ((size_t)co * Cin_total + ci_off + n0 + c0 + i) * 3;
+                        if (mode == 0) {
+                            atomicAdd(d + tap, g);
+                        } else if (!hi) {                            // lo rows (position 2r): G_-1 -> k0, G_0 -> k1 and k2
+                            if (tap == 0) atomicAdd(d + 0, g);
+                            else if (tap == 1) { atomicAdd(d + 1, g); atomicAdd(d + 2, g); }
+                        } else {                                     // hi rows (position 2r+1): G_0 -> k0 and k1, G_+1 -> k2
+                            if (tap == 1) { atomicAdd(d + 0, g); atomicAdd(d + 1, g); }
+                            else if (tap == 2) atomicAdd(d + 2, g);
+                        }
+                    }
+                }
+            }
+        } else {
         float* out = partial + ((size_t)(split * n_tiles + tile) * 3) * 128 * P.bn;
         for (int tap = 0; tap < 3; ++tap) {
             for (int c0 = 0; c0 < P.bn; c0 += 32) {
@@ -164,6 +194,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                                          __uint_as_float(v[4 * i + 3]));
             }
+        }
         }
     }
     tc_fence_before();
@@ -294,7 +325,8 @@ extern "C" long gw_wgrad_tc_scratch_elems(int mode, int B, int L, int Cout, int 
 
 // d_raw [B, L, Cout] bf16; x [B, Lx, Cx] bf16 with Lx = L (mode 0) or L/2 (mode 1: x is h before the nearest upsample);
 // dW fp32 [Cout][Cin_total][3], this call ACCUMULATES the block of input channels [ci_off, ci_off + Cx).
-// variant bit 0: do not use row-shifted descriptors (load one X box per tap instead).
+// variant bit 0: do not use row-shifted descriptors (load one X box per tap instead);
+// variant bit 1: split-K by fp32 atomics into dW instead of the deterministic partial-buffer + fold + scatter passes.
 extern "C" int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, int L, int Cout, int Cx, int Cin_total, int ci_off,
                            float* scratch, long scratch_elems, float* dW, int variant, void* stream) {
     WgParams P;
@@ -317,8 +349,11 @@ extern "C" int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, in
     const int smem = 1024 + stages * stage_bytes + 512;
     GW_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaStream_t st = (cudaStream_t)stream;
-    wgrad_tc_kernel<<<P.mt * P.nt * P.n_split, 192, smem, st>>>(ta, tx, P, scratch, shifted);
+    const bool atomic = (variant & 2) != 0;
+    wgrad_tc_kernel<<<P.mt * P.nt * P.n_split, 192, smem, st>>>(ta, tx, P, scratch, shifted, atomic ? dW : nullptr, mode, Cout,
+                                                                 Cin_total, ci_off);
     GW_LAUNCH_CHECK();
+    if (atomic) return GW_OK;
     const long cols = (long)P.mt * P.nt * 3 * 128 * P.bn;
     wgrad_fold_kernel<<<(unsigned)((cols / 4 + 31) / 32), 256, 0, st>>>(scratch, P.n_split, cols);
     GW_LAUNCH_CHECK();

@@ -205,7 +205,8 @@ int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_raw, int C, 
 /* tcgen05 / TMA weight gradient (see wgrad_tc.cu).  mode 0: x [B, L, Cx] is a plain conv input (pooled tensor or skip);
  * mode 1: x [B, L/2, Cx] is h before the nearest upsample.  d_raw [B, L, Cout] bf16.  ACCUMULATES into the input-channel
  * block [ci_off, ci_off+Cx) of dW fp32 [Cout][Cin_total][3].  scratch >= gw_wgrad_tc_scratch_elems(...) floats.
- * variant bit 0: one TMA box per tap instead of row-shifted descriptors. */
+ * variant bit 0: one TMA box per tap instead of row-shifted descriptors; bit 1: split-K by fp32 atomics straight into dW
+ * (no fold / scatter passes; summation order, hence the last bits, not reproducible run to run). */
 long gw_wgrad_tc_scratch_elems(int mode, int B, int L, int Cout, int Cx);
 int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, int L, int Cout, int Cx, int Cin_total, int ci_off,
                 float* scratch, long scratch_elems, float* dW, int variant, void* stream);

@@ -37,8 +37,9 @@ def _run(in_ch, cc, B, L, dgrad, wgrad, wvariant=0, fuse_head=False):
 def test_tc_backward_matches_simt(in_ch, cc, B, L):
     _, ref = _run(in_ch, cc, B, L, "simt", "simt")
     for dg, wg, wv, what in [("simt", "tc", 1, "wgrad_tc (one box per tap)"), ("simt", "tc", 0, "wgrad_tc (shifted descriptors)"),
-                             ("tc", "simt", 0, "dgrad_tc"), ("tc", "tc", 0, "both"), ("tc", "tc", 2, "both + fused head gradient")]:
-        _, got = _run(in_ch, cc, B, L, dg, wg, wv & 1, fuse_head=bool(wv & 2))
+                             ("tc", "simt", 0, "dgrad_tc"), ("tc", "tc", 0, "both"), ("tc", "tc", 2, "both + fused head gradient"),
+                             ("simt", "tc", 4, "wgrad_tc with atomic split-K")]:
+        _, got = _run(in_ch, cc, B, L, dg, wg, (wv & 1) | (2 if wv & 4 else 0), fuse_head=bool(wv & 2))
         tot = float(torch.cat([v.reshape(-1) for v in ref.values()]).norm())
         for k in ref:
             err = float((got[k].double() - ref[k].double()).norm())

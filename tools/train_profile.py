@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--selfcond", type=int, default=0)
     ap.add_argument("--json", default=None)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--wgrad-variant", type=int, default=-1)
     a = ap.parse_args()
     cc = 1 if a.cin == 3 else 5
     model = UNet1D(in_ch=a.cin, cond_in_ch=cc, use_selfcond=True, compute_dtype=a.dtype)
@@ -41,6 +42,8 @@ def main():
     cond = d["y_norm"]
     if cc == 5:
         cond = torch.cat([cond, torch.zeros(a.B, 4, a.L)], 1)
+    if a.wgrad_variant >= 0:
+        st.bwd.wgrad_variant = a.wgrad_variant
     st.load_batch(d["clean_norm"].cuda(), cond.cuda(), None)
     for _ in range(2):
         st.step(selfcond=bool(a.selfcond), use_graph=False)

@@ -751,9 +751,6 @@ extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const voi
         P.sa = 2;
         if (P.bn > 128) { P.sb = 3; P.nbuf = 1; P.n_acc = 1; }
         else { P.sb = 4; P.nbuf = 2; P.n_acc = 2; }
-        // experiment knobs: bit 16 = deeper A ring (memory-bound small-K layers), bit 32 = single store-staging buffer
-        if ((variant & 16) && P.bn <= 128) { P.sa = 3; P.sb = 3; }
-        if ((variant & 32) && P.bn <= 128) { P.nbuf = 1; P.sa = 3; P.sb = 4; }
         const int smem = 1024 + P.sa * TC2_MT * TC2_A_SLOT + P.sb * P.bn * 128 + 8 * P.nbuf * 4096 + 256 + 2048 + 2048 + 64;
         GW_REQUIRE(smem <= 232448, "conv_tc v2: smem %d too large", smem);
         int grid = P.total_tiles < sm_count_cached() ? P.total_tiles : sm_count_cached();

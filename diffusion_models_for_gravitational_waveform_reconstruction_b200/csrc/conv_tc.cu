@@ -373,6 +373,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
         // ===================== MMA issuer =====================
         if (lane == 0) {
             uint32_t ia = 0, pa = 0, ib = 0, pb = 0, cur_a = 0;
+            const uint64_t desc_hi = make_sw128_desc(0, 0);          // SBO, version, swizzle fields; address field empty
             int it = 0;
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
                 const int n_tile = tile % P.n_tiles;
@@ -390,18 +391,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant
                     }
                     mbar_wait(b_full(ib), pb);
                     tc_fence_after();
+                    // The single issuing thread is the pacing resource for N <= 128 (an MMA retires in 32-64 cycles), so the
+                    // per-MMA instruction count is kept minimal: descriptors are a constant high word plus (address >> 4),
+                    // and stepping K by 16 elements is "+2" in that field (smem addresses < 256 KB fit its 14 bits).
                     const uint32_t idesc = make_idesc(TC_BLOCK_M, (uint32_t)sg.n_cnt);
-                    const uint32_t b0 = sB + ib * b_bytes;
+                    const uint64_t bd0 = desc_hi | (uint64_t)((sB + ib * b_bytes) >> 4);
+                    const uint32_t acc_first = s > 0 ? 1u : 0u;
 #pragma unroll
                     for (int mt = 0; mt < TC2_MT; ++mt) {
                         const uint32_t a0 = sA + (cur_a * TC2_MT + mt) * TC2_A_SLOT + (uint32_t)sg.desc_row * 128u;
-                        const uint32_t bo = P.use_base_off ? ((a0 >> 7) & 7u) : 0u;
-#pragma unroll
-                        for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-                            const uint64_t ad = make_sw128_desc(a0 + k * 32, bo);
-                            const uint64_t bd = make_sw128_desc(b0 + k * 32, 0);
-                            umma_bf16(acc0 + (uint32_t)(mt * P.bn + sg.n_off), ad, bd, idesc, (s > 0 || k > 0) ? 1u : 0u);
-                        }
+                        uint64_t ad0 = desc_hi | (uint64_t)(a0 >> 4);
+                        if (P.use_base_off) ad0 |= (uint64_t)((a0 >> 7) & 7u) << 49;
+                        const uint32_t d = acc0 + (uint32_t)(mt * P.bn + sg.n_off);
+                        umma_bf16(d, ad0, bd0, idesc, acc_first);
+                        umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+                        umma_bf16(d, ad0 + 4, bd0 + 4, idesc, 1u);
+                        umma_bf16(d, ad0 + 6, bd0 + 6, idesc, 1u);
                     }
                     umma_commit(b_empty(ib));
                     if (sg.a_last) umma_commit(a_empty(cur_a));

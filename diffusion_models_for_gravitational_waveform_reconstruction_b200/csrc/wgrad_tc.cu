@@ -119,6 +119,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             const uint32_t idesc = make_idesc_mn(128, (uint32_t)P.bn);
+            const uint64_t a_hi = make_mn_sw128_desc(0, WG_A_BOX), x_hi = make_mn_sw128_desc(0, WG_X_BOX);
             bool first = true;
             for (long w = split; w < total; w += P.n_split) {
                 mbar_wait(full_bar(stage), phase);
@@ -128,12 +129,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 for (int tap = 0; tap < 3; ++tap) {
                     if (tap < tap_lo || tap > tap_hi) continue;     // this tile's rows never use that tap (see WgParams::lo_tiles)
                     const uint32_t xt = shifted_desc ? x0 + (uint32_t)tap * 128u : x0 + (uint32_t)tap * nb * WG_X_BOX;
-#pragma unroll
-                    for (int k = 0; k < WG_KR / 16; ++k) {
-                        const uint64_t ad = make_mn_sw128_desc(a0 + k * 2048, WG_A_BOX);
-                        const uint64_t xd = make_mn_sw128_desc(xt + k * 2048, WG_X_BOX);
-                        umma_bf16(tmem_base + (uint32_t)(tap * P.bn), ad, xd, idesc, (!first || k > 0) ? 1u : 0u);
-                    }
+                    // descriptors = constant high word | (address >> 4); a K step of 16 rows is +2048 B = +128 in that field
+                    const uint64_t ad0 = a_hi | (uint64_t)(a0 >> 4), xd0 = x_hi | (uint64_t)(xt >> 4);
+                    const uint32_t d = tmem_base + (uint32_t)(tap * P.bn);
+                    umma_bf16(d, ad0, xd0, idesc, first ? 0u : 1u);
+                    umma_bf16(d, ad0 + 128, xd0 + 128, idesc, 1u);
+                    umma_bf16(d, ad0 + 256, xd0 + 256, idesc, 1u);
+                    umma_bf16(d, ad0 + 384, xd0 + 384, idesc, 1u);
                 }
                 first = false;
                 umma_commit(empty_bar(stage));

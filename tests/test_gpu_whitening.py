@@ -54,3 +54,41 @@ def test_batched_whitening_equals_per_sample_and_round_trips(golden_dir):
     assert torch.allclose(s, y.double().std(dim=1, unbiased=False), rtol=1e-12)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         W.whiten_train_like(torch.zeros(1, 64))
+
+
+def test_reconstruct_batch_pipeline_equals_its_stages_and_the_oracle():
+    """pipeline.reconstruct_batch (inference.py:655-826 on the device) == whiten -> sigma -> oracle DDIM -> de-whiten by hand."""
+    import oracle
+    from weights import make_state_dict, synthetic_chirps
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import pipeline, whitening as W
+    B, L, fs = 3, 1024, 4096.0
+    d = synthetic_chirps(B, L, snr=10.0, seed=17)
+    y_raw = (d["y_norm"][:, 0] * 3e-3 + 1e-3).cuda()            # "strain-like" scale and a DC offset
+    clean_raw = (d["clean_norm"][:, 0] * 3e-3).cuda()
+    sd = make_state_dict(3, 1, seed=0)
+    m = UNet1D(in_ch=3, cond_in_ch=1, use_selfcond=True)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    diff = CustomDiffusion(T=1000, device="cuda")
+    r = pipeline.reconstruct_batch(m, diff, y_raw, fs=fs, clean_raw=clean_raw, whiten=True, whiten_mode="train", sigma_mode="std",
+                                   start_snr=2.0, steps=6, eta=0.0, seed=5, compute_dtype="fp32", score_secs=0.2)
+    assert r["whiten_kind"] == "train" and r["start_t"] == 289
+    # stage by stage
+    y_w, c_w, P = W.whiten_train_like(y_raw, clean_raw)
+    sig = W.sigma(y_w, "std")
+    assert torch.allclose(sig, r["sigma"], rtol=1e-12)
+    y_norm = (y_w / sig.float()[:, None])[:, None, :]
+    cfg = oracle.ModelCfg(in_ch=3, cond_in_ch=1, use_selfcond=True)
+    ab = oracle.alpha_bar_from_betas(oracle.cosine_beta_schedule(1000))
+    xT = inf.philox_normal(B, L, 5, 0, 0, "cuda").cpu()
+    ref = oracle.ddim_sample(sd, cfg, ab, y_norm.cpu(), T=1000, steps=6, eta=0.0, start_t=289, noise=[xT])
+    assert rel(r["x0_hat_norm"].cpu().numpy(), ref.numpy()) <= 1e-4
+    back = W.apply_psd((ref.cuda() * sig.float().view(B, 1, 1)).view(B, L), P, dewhiten=True)
+    assert rel(r["x0_hat_strain"].cpu().numpy(), back.cpu().numpy()) <= 1e-4
+    assert set(r["strain"]) >= {"corr_last", "mae_last", "nmae_sigma", "overlap"} and r["objective"].shape == (B,)
+    assert torch.isfinite(r["objective"]).all()
+    # raw (un-whitened) flavour and the bf16 engine
+    r2 = pipeline.reconstruct_batch(m, diff, y_raw, fs=fs, whiten=False, steps=4, start_t=200, seed=5, compute_dtype="bf16")
+    assert r2["whiten_kind"] == "raw" and r2["x0_hat_strain"].shape == (B, L) and torch.isfinite(r2["x0_hat_strain"]).all()

@@ -579,7 +579,7 @@ extern "C" int gw_conv3_simt(const void* src0, int C0, int L0, int up0, const vo
                              const float* w3, const float* bias, int Cout, void* raw, int dtype, float* part,
                              void* stream) {
     GW_REQUIRE(C0 % 16 == 0 && C1 % 16 == 0 && C0 > 0, "gw_conv3_simt: channels C0=%d C1=%d", C0, C1);
-    GW_REQUIRE(Cout % 64 == 0 && Cout <= 512, "gw_conv3_simt: Cout=%d", Cout);
+    GW_REQUIRE(Cout % 64 == 0 && Cout <= 4096, "gw_conv3_simt: Cout=%d", Cout);
     GW_REQUIRE((src1 != nullptr) == (C1 > 0), "gw_conv3_simt: src1/C1 mismatch");
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv3_simt: dtype %d", dtype);
     const int n_part = gw_cdiv(L, 64);

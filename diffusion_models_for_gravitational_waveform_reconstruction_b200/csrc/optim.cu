@@ -117,34 +117,40 @@ __device__ __forceinline__ float dsilu(float x) {
     const float s = 1.0f / (1.0f + expf(-x));
     return s * (1.0f + x * (1.0f - s));
 }
-// grid F/4, block (base, 4, BL): thread (j, f, bl) sums the batch lane bl, bl+BL, ...; lanes are folded in fixed order
+// grid F/4, block (64, 4, BL): thread (jl, f, bl) sums the batch lane bl, bl+BL, ... for columns j = jl, jl+64, ...; the
+// lanes are folded in fixed order
 #define FILM_BL 4
 __global__ void __launch_bounds__(1024) film_bwd_w2_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux, int B,
                                                            int td, int base, int F, float* __restrict__ dW2,
                                                            float* __restrict__ db2) {
-    __shared__ float red[FILM_BL][4][64 + 1];
+    extern __shared__ float red[];                   // [BL][4][base]
     __shared__ float redb[FILM_BL][4];
-    const int j = threadIdx.x, fl = threadIdx.y, bl = threadIdx.z;
+    const int jl = threadIdx.x, fl = threadIdx.y, bl = threadIdx.z;
     const int f = blockIdx.x * 4 + fl;
     const int na = td + 3 * base;
-    float acc = 0.0f, bsum = 0.0f;
-    if (f < F) {
-#pragma unroll 8
-        for (int b = bl; b < B; b += FILM_BL) {
-            const float d = dfilm[(size_t)b * F + f];
-            acc = fmaf(d, aux[(size_t)b * na + td + 2 * base + j], acc);
-            bsum += d;
-        }
+    float bsum = 0.0f;
+    if (f < F && jl == 0) {
+        for (int b = bl; b < B; b += FILM_BL) bsum += dfilm[(size_t)b * F + f];
     }
-    red[bl][fl][j] = acc;
-    if (j == 0) redb[bl][fl] = bsum;
+    for (int j = jl; j < base; j += 64) {
+        float acc = 0.0f;
+        if (f < F) {
+#pragma unroll 8
+            for (int b = bl; b < B; b += FILM_BL)
+                acc = fmaf(dfilm[(size_t)b * F + f], aux[(size_t)b * na + td + 2 * base + j], acc);
+        }
+        red[(bl * 4 + fl) * base + j] = acc;
+    }
+    if (jl == 0) redb[bl][fl] = bsum;
     __syncthreads();
     if (bl == 0 && f < F) {
-        float a = 0.0f;
+        for (int j = jl; j < base; j += 64) {
+            float a = 0.0f;
 #pragma unroll
-        for (int t = 0; t < FILM_BL; ++t) a += red[t][fl][j];
-        dW2[(size_t)f * base + j] += a;
-        if (j == 0) {
+            for (int t = 0; t < FILM_BL; ++t) a += red[(t * 4 + fl) * base + j];
+            dW2[(size_t)f * base + j] += a;
+        }
+        if (jl == 0) {
             float bb = 0.0f;
 #pragma unroll
             for (int t = 0; t < FILM_BL; ++t) bb += redb[t][fl];
@@ -171,44 +177,49 @@ __global__ void __launch_bounds__(1024) film_bwd_act_kernel(const float* __restr
         dpre[(size_t)b * base + j] = s * dsilu(ax[base + j]) * dsilu(ax[j]);
     }
 }
-// grid base, block (td, 8): dW1[j, i] += sum_b dpre[b,j] emb[b,i]; db1[j] += sum_b dpre[b,j]
+// grid base, block (128, 8): dW1[j, i] += sum_b dpre[b,j] emb[b,i] (i = il, il+128, ...); db1[j] += sum_b dpre[b,j]
 __global__ void __launch_bounds__(1024) film_bwd_w1_kernel(const float* __restrict__ dpre, const float* __restrict__ aux, int B,
                                                            int td, int base, float* __restrict__ dW1, float* __restrict__ db1) {
-    extern __shared__ float sm[];           // [8][td + 1]
-    const int j = blockIdx.x, i = threadIdx.x, bl = threadIdx.y;
+    extern __shared__ float sm[];           // [8][td] + [8]
+    const int j = blockIdx.x, il = threadIdx.x, bl = threadIdx.y;
     const int na = td + 3 * base;
-    float acc = 0.0f, bs = 0.0f;
+    float bs = 0.0f;
+    if (il == 0)
+        for (int b = bl; b < B; b += 8) bs += dpre[(size_t)b * base + j];
+    for (int i = il; i < td; i += 128) {
+        float acc = 0.0f;
 #pragma unroll 8
-    for (int b = bl; b < B; b += 8) {
-        const float d = dpre[(size_t)b * base + j];
-        acc = fmaf(d, aux[(size_t)b * na + i], acc);
-        bs += d;
+        for (int b = bl; b < B; b += 8) acc = fmaf(dpre[(size_t)b * base + j], aux[(size_t)b * na + i], acc);
+        sm[bl * td + i] = acc;
     }
-    sm[bl * (td + 1) + i] = acc;
-    if (i == 0) sm[8 * (td + 1) + bl] = bs;
+    if (il == 0) sm[8 * td + bl] = bs;
     __syncthreads();
     if (bl == 0) {
-        float a = 0.0f;
+        for (int i = il; i < td; i += 128) {
+            float a = 0.0f;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) a += sm[t * (td + 1) + i];
-        dW1[(size_t)j * td + i] += a;
-        if (i == 0) {
+            for (int t = 0; t < 8; ++t) a += sm[t * td + i];
+            dW1[(size_t)j * td + i] += a;
+        }
+        if (il == 0) {
             float bb = 0.0f;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) bb += sm[8 * (td + 1) + t];
+            for (int t = 0; t < 8; ++t) bb += sm[8 * td + t];
             db1[j] += bb;
         }
     }
 }
 extern "C" int gw_film_bwd(const float* dfilm, const float* aux, const float* w2, int B, int time_dim, int base, int F,
                            float* scratch, float* dW1, float* db1, float* dW2, float* db2, void* stream) {
-    GW_REQUIRE(B > 0 && base > 0 && base <= 64 && 1024 % base == 0 && time_dim > 0 && time_dim <= 128, "gw_film_bwd: sizes (base <= 64, time_dim <= 128)");
+    GW_REQUIRE(B > 0 && base > 0 && base <= 1024 && 1024 % base == 0 && time_dim > 0 && time_dim <= 4096,
+               "gw_film_bwd: sizes (base must divide 1024)");
     cudaStream_t st = (cudaStream_t)stream;
-    film_bwd_w2_kernel<<<gw_cdiv(F, 4), dim3(base, 4, FILM_BL), 0, st>>>(dfilm, aux, B, time_dim, base, F, dW2, db2);
+    film_bwd_w2_kernel<<<gw_cdiv(F, 4), dim3(64, 4, FILM_BL), (size_t)FILM_BL * 4 * base * sizeof(float), st>>>(dfilm, aux, B, time_dim,
+                                                                                                          base, F, dW2, db2);
     GW_LAUNCH_CHECK();
     film_bwd_act_kernel<<<B, 1024, (size_t)1024 * sizeof(float), st>>>(dfilm, aux, w2, time_dim, base, F, scratch);
     GW_LAUNCH_CHECK();
-    film_bwd_w1_kernel<<<base, dim3(time_dim, 8), (size_t)(8 * (time_dim + 1) + 8) * sizeof(float), st>>>(scratch, aux, B, time_dim, base, dW1, db1);
+    film_bwd_w1_kernel<<<base, dim3(128, 8), (size_t)(8 * time_dim + 8) * sizeof(float), st>>>(scratch, aux, B, time_dim, base, dW1, db1);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

@@ -293,3 +293,29 @@ def test_backward_odd_lengths(L, cd, tol):
     for k, go in grads_o.items():
         err = float((grads[k].cpu().double() - go.double()).norm())
         assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))
+
+
+@pytest.mark.parametrize("base_ch,depth,time_dim,cd,tol", [(128, 2, 64, "fp32", 5e-5), (128, 3, 128, "bf16", 6e-2), (64, 4, 128, "fp32", 5e-5)])
+def test_non_default_architectures(base_ch, depth, time_dim, cd, tol):
+    """UNet1D(base_ch, depth, time_dim) other than the CLI defaults (models.py:78-88): forward and one training step."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import FusedTrainStep
+    in_ch, cc, B, L = 3, 1, 2, 512
+    sd = make_state_dict(in_ch, cc, base_ch=base_ch, depth=depth, time_dim=time_dim, seed=3)
+    cfg = oracle.ModelCfg(in_ch=in_ch, base_ch=base_ch, time_dim=time_dim, depth=depth, cond_in_ch=cc, use_selfcond=True)
+    _, clean, cond, mask, t, eps, drop = _case(in_ch, cc, B, L)
+    ab = oracle.alpha_bar_from_betas(oracle.cosine_beta_schedule(1000))
+    loss_o, grads_o, eps_o = oracle.train_step(sd, cfg, ab, clean_norm=clean, cond_stack=cond, mask=mask, t=t, eps=eps, drop=drop)
+    m = UNet1D(in_ch=in_ch, base_ch=base_ch, time_dim=time_dim, depth=depth, cond_in_ch=cc, use_selfcond=True, compute_dtype=cd)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    st = FusedTrainStep(m, CustomDiffusion(T=1000, device="cuda"), B, L, compute_dtype=cd, p_uncond=0.2, warmup_steps=10, total_steps=100)
+    st.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+    st.step(t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=False)
+    torch.cuda.synchronize()
+    assert rel_l2(st.eps_hat, eps_o) <= (1e-5 if cd == "fp32" else 1.5e-2)
+    grads = st.layout.views(st.flat_g)
+    tot = float(torch.cat([g.reshape(-1) for g in grads_o.values()]).norm())
+    for k, go in grads_o.items():
+        err = float((grads[k].cpu().double() - go.double()).norm())
+        assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))

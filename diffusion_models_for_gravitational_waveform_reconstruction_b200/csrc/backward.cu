@@ -820,8 +820,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
 }
 
 int g_gn_bwd_stream = 1;
+extern int g_final_stream;
 extern "C" int gw_set_option(const char* name, int value) {
     if (strcmp(name, "gn_bwd_stream") == 0) { g_gn_bwd_stream = value; return GW_OK; }
+    if (strcmp(name, "final_stream") == 0) { g_final_stream = value; return GW_OK; }
     gw_set_error("gw_set_option: unknown option %s", name);
     return GW_ERR_ARG;
 }

@@ -1100,6 +1100,11 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
     if (x0_out != nullptr) x0_out[(size_t)b * L + l] = x0;
 }
 
+int final_step_stream(const void* h, const float* net_a, const float* net_b, int B, int Cx, int L, const float* wf, const float* bf,
+                      const gw_step_params* p, const float* coef, const int* step_ptr, const float* noise, float* eps_out,
+                      float* x0_out, cudaStream_t st);
+int g_final_stream = 1;
+
 extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const float* net_b, int B, int Cx, int L,
                              int C, const float* wf, const float* bf, const gw_step_params* p, const float* coef,
                              const int* step_ptr, const float* noise, float* eps_out, float* x0_out, void* stream) {
@@ -1112,8 +1117,10 @@ extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const
     StepArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
     a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
-    dim3 grid(gw_cdiv(L, FS_TP), B);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_BF16 && C == 64 && g_final_stream)       // HBM-streaming kernel (stream_gn.cu)
+        return final_step_stream(h, net_a, net_b, B, Cx, L, wf, bf, p, coef, step_ptr, noise, eps_out, x0_out, st);
+    dim3 grid(gw_cdiv(L, FS_TP), B);
     if (dtype == GW_F32)
         final_step_kernel<float><<<grid, 256, 0, st>>>((const float*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
                                                        coef, step_ptr, noise, eps_out, x0_out);

@@ -218,7 +218,8 @@ extern "C" int gw_gn_apply_stream(const void* raw, const float* part, int n_part
     cudaStream_t st = (cudaStream_t)stream;
 #define SGA_GO(CCV)                                                                                                        \
     do {                                                                                                                   \
-        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   \
         gn_apply_stream_kernel<CCV><<<grid, 256, smem, st>>>((const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
                                                              film, film_off, film_b_stride, film_step_stride, step_ptr,        \
                                                              (bf16*)out, (bf16*)pooled, stats_out, rows);                      \
@@ -592,6 +593,7 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
 #define SGS_GO(CCV, HD)                                                                                                     \
     do {                                                                                                                    \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_stream_kernel<CCV, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_stream_kernel<CCV, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
         gn_bwd_stats_stream_kernel<CCV, HD><<<grid, 256, smem, st>>>(a, partial, depth);                                     \
     } while (0)
 #define SGS_CC(HD)                      \
@@ -616,9 +618,11 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
     if (a.do_eps != nullptr) {
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         gn_bwd_apply_stream_kernel<true><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
     } else {
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         gn_bwd_apply_stream_kernel<false><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
     }
     GW_LAUNCH_CHECK();
@@ -731,11 +735,200 @@ int wgrad_in_stream(const float* x, int B, int Cx, int L, const void* d_raw, flo
 #define WIS_GO(CXM)                                                                                                   \
     do {                                                                                                              \
         GW_CUDA(cudaFuncSetAttribute(wgrad_in_stream_kernel<CXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GW_CUDA(cudaFuncSetAttribute(wgrad_in_stream_kernel<CXM>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
         wgrad_in_stream_kernel<CXM><<<grid, 256, smem, st>>>(x, Cx, L, (const bf16*)d_raw, scratch, rows);               \
     } while (0)
     if (Cx <= 4) WIS_GO(4); else if (Cx <= 8) WIS_GO(8); else WIS_GO(16);
 #undef WIS_GO
     GW_LAUNCH_CHECK();
     *n_rows = B * n_rc;
+    return GW_OK;
+}
+
+// ================================================================================================
+// head conv (C = 64 -> 1, k = 3) + CFG combine + DDIM/DDPM update as a streaming kernel (see final_step_kernel in forward.cu
+// for the math and the argument meaning).  A CTA owns FSS_TP output positions of one sample: the FSS_TP + 2 rows of h it
+// needs go through the bulk-copy ring, every row leaves three tap dots in shared memory, the update runs at the end.
+// ================================================================================================
+#define FSS_TP 508                    // positions per CTA (multiple of 4: Philox quads stay aligned); + 2 halo rows = 8 stages
+struct FssArgs {
+    int mode, cfg_both, selfcond, pred_x0;
+    float eps_scale, dc_weight;
+    const float* y_dc;
+    unsigned long long seed;
+    long sample0;
+};
+
+__global__ void __launch_bounds__(256) final_step_stream_kernel(const bf16* __restrict__ h, const float* __restrict__ net_a,
+                                                                const float* __restrict__ net_b, int B, int Cx, int L,
+                                                                const float* __restrict__ wf, const float* __restrict__ bf,
+                                                                FssArgs p, const float* __restrict__ coef,
+                                                                const int* __restrict__ step_ptr, const float* __restrict__ noise,
+                                                                float* __restrict__ eps_out, float* __restrict__ x0_out) {
+    constexpr int C = 64, S = 64, D = SG_DEPTH, ROWS = FSS_TP + 2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* ring = smem;                                           // [D][8 KB]
+    float* pd = reinterpret_cast<float*>(smem + D * SG_STAGE_BYTES);  // [2 halves][3 taps][ROWS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pd + 2 * 3 * ROWS);
+    const int b = blockIdx.y, l0 = blockIdx.x * FSS_TP;
+    const int step = step_ptr != nullptr ? *step_ptr : 0;
+    const float* net_in = (step & 1) ? net_b : net_a;
+    float* net_out = const_cast<float*>((step & 1) ? net_a : net_b);
+    const int n_half = (p.mode == 1 && p.cfg_both) ? 2 : 1;
+    // rows of h this CTA streams: [w0, w1) = [l0 - 1, l0 + FSS_TP + 1) clipped to the sample; local index r = row - (l0 - 1)
+    const int w0 = max(l0 - 1, 0), w1 = min(l0 + FSS_TP + 1, L);
+    const int n_rows = w1 - w0, n_sub = (n_rows + S - 1) / S;
+    const int r_off = w0 - (l0 - 1);                                // 1 for the first CTA of a sample, else 0
+    const int total = n_half * n_sub;
+    auto issue = [&](int i) {
+        const int hf = i / n_sub, j = i % n_sub;
+        const int rows_i = min(S, n_rows - j * S);
+        const uint32_t bar = smem_u32(bars + (i % D));
+        mbar_expect_tx(bar, (uint32_t)rows_i * C * 2);
+        bulk_load(smem_u32(ring + (i % D) * SG_STAGE_BYTES), h + ((size_t)(b + hf * B) * L + w0 + (size_t)j * S) * C,
+                  (uint32_t)rows_i * C * 2, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < D; ++s) mbar_init(smem_u32(bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < D && i < total; ++i) issue(i);
+    }
+    for (int i = threadIdx.x; i < 2 * 3 * ROWS; i += 256) pd[i] = 0.0f;      // rows outside the sample contribute zero
+    const int sx = threadIdx.x & 3, tr = threadIdx.x >> 2;          // 4 threads per row (16 channels each), 64 rows per pass
+    float w0v[16], w1v[16], w2v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = sx * 16 + i;
+        w0v[i] = wf[c * 3 + 0];
+        w1v[i] = wf[c * 3 + 1];
+        w2v[i] = wf[c * 3 + 2];
+    }
+    __syncthreads();
+    for (int i = 0; i < total; ++i) {
+        const int hf = i / n_sub, j = i % n_sub;
+        const int rows_i = min(S, n_rows - j * S);
+        mbar_wait(smem_u32(bars + (i % D)), (uint32_t)((i / D) & 1));
+        const uint8_t* sb = ring + (i % D) * SG_STAGE_BYTES;
+        {
+            const int r = tr;
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = 0.0f;
+            if (r < rows_i) {
+                float va[8], vb[8];
+                ld8(reinterpret_cast<const bf16*>(sb + ((size_t)r * C + sx * 16) * 2), va);
+                ld8(reinterpret_cast<const bf16*>(sb + ((size_t)r * C + sx * 16 + 8) * 2), vb);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { v[q] = va[q]; v[8 + q] = vb[q]; }
+            }
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                d0 = fmaf(v[q], w0v[q], d0);
+                d1 = fmaf(v[q], w1v[q], d1);
+                d2 = fmaf(v[q], w2v[q], d2);
+            }
+#pragma unroll
+            for (int o = 2; o > 0; o >>= 1) {
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+            }
+            if (sx == 0 && r < rows_i) {
+                const int rl = r_off + j * S + r;                   // local row index in [0, ROWS)
+                float* q = pd + hf * 3 * ROWS;
+                q[rl] = d0;
+                q[ROWS + rl] = d1;
+                q[2 * ROWS + rl] = d2;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && i + D < total) issue(i + D);
+    }
+    // ---- update: thread g finishes the 4 consecutive positions l0 + 4g .. l0 + 4g + 3 (one Philox call per quad)
+    const float wx0 = wf[C * 3 + 0], wx1 = wf[C * 3 + 1], wx2 = wf[C * 3 + 2], bias = bf[0];
+    const int g = threadIdx.x;
+    if (g * 4 >= FSS_TP || l0 + g * 4 >= L) return;
+    float cfv[10] = {0.0f, 1.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+    if (p.mode == 1) {
+        const float* cf = coef + (size_t)step * 16;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) cfv[i] = cf[i];
+    }
+    const float c_s1mab = cfv[0], c_sab = cfv[1], c_sabp = cfv[2], c_dir = cfv[3], c_sig = cfv[4], c_w = cfv[5];
+    const int use = (int)cfv[6], last = (int)cfv[7], draw = (int)cfv[8];
+    const float c_s1mab_cl = cfv[9];
+    const bool need_z = p.mode == 1 && !last && c_sig > 0.0f;
+    float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (need_z && noise == nullptr)
+        Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)((l0 + g * 4) >> 2), z4);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int pi = g * 4 + u, l = l0 + pi;
+        if (l >= L) break;
+        float outv0 = 0.0f, outv1 = 0.0f, xt_c = 0.0f;
+        for (int hf = 0; hf < n_half; ++hf) {
+            const float* xr = net_in + (size_t)(b + hf * B) * Cx * L;
+            const float xm = l > 0 ? xr[l - 1] : 0.0f, xc = xr[l], xp = l + 1 < L ? xr[l + 1] : 0.0f;
+            const float* q = pd + hf * 3 * ROWS;
+            const int r = pi + 1;
+            float acc = q[r - 1] + q[ROWS + r] + q[2 * ROWS + r + 1];
+            acc += fmaf(xm, wx0, fmaf(xc, wx1, xp * wx2));
+            if (hf == 0) { outv0 = acc + bias; xt_c = xc; } else { outv1 = acc + bias; }
+        }
+        if (p.mode == 0) {
+            eps_out[(size_t)b * L + l] = outv0;
+            continue;
+        }
+        float o;
+        if (use == 0) o = outv0;
+        else if (use == 1) o = p.cfg_both ? outv1 : outv0;
+        else o = __fadd_rn(outv1, __fmul_rn(c_w, __fsub_rn(outv0, outv1)));
+        float eps, x0;
+        if (!p.pred_x0) {
+            eps = __fmul_rn(p.eps_scale, o);
+            x0 = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_s1mab, eps)), c_sab);
+        } else {
+            x0 = o;
+            eps = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_sab, x0)), c_s1mab_cl);
+        }
+        if (p.dc_weight > 0.0f)
+            x0 = __fadd_rn(__fmul_rn(1.0f - p.dc_weight, x0), __fmul_rn(p.dc_weight, p.y_dc[(size_t)b * L + l]));
+        float xn;
+        if (last) {
+            xn = x0;
+        } else {
+            float nz = 0.0f;
+            if (c_sig > 0.0f) {
+                const float z = noise != nullptr ? noise[((size_t)draw * B + b) * L + l] : z4[u];
+                nz = __fmul_rn(c_sig, z);
+            }
+            xn = __fadd_rn(__fadd_rn(__fmul_rn(c_sabp, x0), __fmul_rn(c_dir, eps)), nz);
+        }
+        for (int hf = 0; hf < n_half; ++hf) {
+            float* orow = net_out + (size_t)(b + hf * B) * Cx * L;
+            orow[l] = xn;
+            if (p.selfcond) orow[(size_t)(Cx - 1) * L + l] = x0;
+        }
+        if (eps_out != nullptr) eps_out[(size_t)b * L + l] = eps;
+        if (x0_out != nullptr) x0_out[(size_t)b * L + l] = x0;
+    }
+}
+
+// called by gw_final_step (forward.cu) for bf16, C = 64
+int final_step_stream(const void* h, const float* net_a, const float* net_b, int B, int Cx, int L, const float* wf, const float* bf,
+                      const gw_step_params* p, const float* coef, const int* step_ptr, const float* noise, float* eps_out,
+                      float* x0_out, cudaStream_t st) {
+    FssArgs a;
+    a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
+    a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    const size_t smem = (size_t)SG_DEPTH * SG_STAGE_BYTES + (size_t)2 * 3 * (FSS_TP + 2) * 4 + 64;
+    GW_CUDA(cudaFuncSetAttribute(final_step_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(final_step_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    dim3 grid(gw_cdiv(L, FSS_TP), B);
+    final_step_stream_kernel<<<grid, 256, smem, st>>>((const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, wf, bf, a, coef, step_ptr,
+                                                      noise, eps_out, x0_out);
+    GW_LAUNCH_CHECK();
     return GW_OK;
 }

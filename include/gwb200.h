@@ -29,7 +29,8 @@ extern "C" {
 #define GW_MAX_LEVELS 8
 
 int gw_version(void);
-/* runtime switches for A/B measurements: "gn_bwd_stream" (1 = HBM-streaming GroupNorm backward kernels, default) */
+/* runtime switches for A/B measurements: "gn_bwd_stream" (1 = HBM-streaming GroupNorm backward kernels, default),
+ * "final_stream" (1 = HBM-streaming head + update kernel for bf16 / C = 64, default) */
 int gw_set_option(const char* name, int value);
 const char* gw_last_error(void);
 int gw_device_info(int* sm_count, int* cc_major, int* cc_minor);

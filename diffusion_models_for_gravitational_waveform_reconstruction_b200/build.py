@@ -28,6 +28,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("GW_NVCC_EXTRA", "").split()          # experiments only (e.g. -DCGN_ABLATE)
     objs = []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     procs = []

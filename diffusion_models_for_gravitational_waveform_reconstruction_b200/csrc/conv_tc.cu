@@ -84,7 +84,7 @@ __device__ __forceinline__ float warp_reduce_multi(float (&v)[V], int lane) {
 // One epilogue unit: 64 accumulator columns of this lane's row -> +bias -> bf16 -> 128-byte-swizzled staging rows, plus
 // (optionally) the GroupNorm partial sums of the fp32 values.  CG_LOG2 = log2(channels per group) in {3, 4, 5}.
 // stat: this warp's [8 groups][2] slots (smem) for the current M tile; grp0: group of the chunk's first column.
-template <int CG_LOG2>
+template <int CG_LOG2, bool STORE = true>
 __device__ __forceinline__ void epi_chunk64(uint32_t taddr, const float* sbias, bool row_ok, bool do_stats, float* stat, int grp0,
                                             uint32_t stg, int lane) {
     constexpr int NG = 64 >> CG_LOG2;                         // groups inside the 64 columns: 8, 4, 2
@@ -107,7 +107,7 @@ __device__ __forceinline__ void epi_chunk64(uint32_t taddr, const float* sbias, 
         }
         // 32 columns = 4 chunks of 16 B; SW128: chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < (STORE ? 4 : 0); ++j) {
             uint32_t pkd[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -795,3 +795,6 @@ extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const voi
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ fused conv + GroupNorm block
+#include "conv_gn.cuh"

@@ -143,6 +143,7 @@ class _Workspace:
         self.stats = [torch.empty(B, 8, 2, device=device, dtype=torch.float32) for _ in range(2 * d + 1)] if keep_raw else None
         self.cond = [torch.empty(B, Ls[j], max(spec.cond_in_ch, 1), device=device, dtype=torch.float32)
                      for j in range(d + 1)] if spec.cond_in_ch > 0 else None
+        self.sync: Optional[Tensor] = None          # gw_conv_gn exchange buffer (zeroed once, see UNetEngine._block)
 
 
 class UNetEngine:
@@ -180,6 +181,10 @@ class UNetEngine:
         # recomputing it costs more than the 268 MB of HBM traffic it saves; kept (parity-tested) but off by default.
         self.fuse_first_block = False
         self.stream_gn = True                       # bf16: bulk-copy streaming GroupNorm kernels (stream_gn.cu)
+        # bf16/tcgen05: conv + GroupNorm + SiLU + cond + FiLM (+ pool) of a block in ONE kernel (conv_gn.cuh) wherever the
+        # layer shape allows it; the conv output then never makes the HBM round trip between gw_conv_tc and gw_gn_apply
+        self.fuse_gn = True
+        self._fuse_ok: Dict[tuple, bool] = {}
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
         self.refresh()
@@ -248,6 +253,8 @@ class UNetEngine:
         ws = self._ws.get(key)
         if ws is None:
             ws = _Workspace(self.spec, B, L, self.tdtype, self.device, keep_raw)
+            if self.dtype == "bf16":
+                ws.sync = torch.zeros(self.lib.gw_conv_gn_sync_bytes(B), device=self.device, dtype=torch.uint8)
             self._ws[key] = ws
         return ws
 
@@ -328,6 +335,46 @@ class UNetEngine:
                                    _cabi.stream_ptr()), f"gn_apply[{name}]")
         self.launches += 1
 
+    def _block(self, li: int, ws: _Workspace, src0: Tensor, src1: Optional[Tensor], film: Tensor, film_b_stride: int,
+               film_step_stride: int, step_ptr: Optional[Tensor], pooled: Optional[Tensor], lvl: int) -> None:
+        """One conv block (models.py:160-173 + cond bias + FiLM (+ pool)) of layer li >= 1 into ws.out[li]."""
+        sp = self.spec
+        raw = ws.raw[li]
+        B, L, Cout = raw.shape
+        L0 = src0.shape[1]
+        Cc = sp.cond_in_ch
+        fused = False
+        if self.fuse_gn and self.dtype == "bf16" and self.tc_supported(li, L, L0):
+            fkey = (li, L, L0, pooled is not None)
+            fused = self._fuse_ok.get(fkey)
+            if fused is None:
+                shp1 = self._shape(li, 1, L, L0)
+                fused = self.lib.gw_conv_gn_group(C.byref(shp1), Cc, 1 if pooled is not None else 0) > 0
+                self._fuse_ok[fkey] = fused
+        if not fused:
+            n_part = self._conv(li, src0, src1, raw, ws.part)
+            self._gn(li, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, pooled, lvl)
+            return
+        if ws.sync is None:
+            ws.sync = torch.zeros(self.lib.gw_conv_gn_sync_bytes(B), device=self.device, dtype=torch.uint8)
+        key = (li, L, L0)
+        packed = self._packed.get(key)
+        if packed is None:
+            packed = self._pack_tc(key)
+            self.launches += 1
+        name, cname = sp.layer_names()[li], sp.cond_names()[li]
+        shp = self._shape(li, B, L, L0)
+        keep = ws.stats is not None
+        check(self.lib.gw_conv_gn(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),
+                                  ptr(self.p[name + ".1.weight"]), ptr(self.p[name + ".1.bias"]),
+                                  ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                  ptr(self.p[cname + ".weight"]) if Cc > 0 else None,
+                                  ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film), sp.film_offsets()[li],
+                                  film_b_stride, film_step_stride, ptr(step_ptr), ptr(ws.out[li]), ptr(pooled),
+                                  ptr(raw) if keep else None, ptr(ws.stats[li]) if keep else None, ptr(ws.sync),
+                                  _cabi.stream_ptr()), f"conv_gn[{name}]")
+        self.launches += 1
+
     def body(self, ws: _Workspace, net_a: Tensor, net_b: Optional[Tensor], step_ptr: Optional[Tensor], film: Tensor,
              film_b_stride: int, film_step_stride: int) -> Tensor:
         """conv_in .. decoders[-1] FiLM; returns the last activation [B, L, base_ch].  The cond pyramid must be current."""
@@ -353,15 +400,12 @@ class UNetEngine:
             self.launches += 1
             self._gn(0, ws, (L + 127) // 128, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[0], 0)
         for i in range(1, d):
-            n_part = self._conv(i, ws.pooled[i - 1], None, ws.raw[i], ws.part)
-            self._gn(i, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[i], i)
-        n_part = self._conv(d, ws.pooled[d - 1], None, ws.raw[d], ws.part)
-        self._gn(d, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, None, d)
+            self._block(i, ws, ws.pooled[i - 1], None, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[i], i)
+        self._block(d, ws, ws.pooled[d - 1], None, film, film_b_stride, film_step_stride, step_ptr, None, d)
         h = ws.out[d]
         for i in range(d):
             li = d + 1 + i
-            n_part = self._conv(li, h, ws.out[d - 1 - i], ws.raw[li], ws.part)
-            self._gn(li, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, None, d - 1 - i)
+            self._block(li, ws, h, ws.out[d - 1 - i], film, film_b_stride, film_step_stride, step_ptr, None, d - 1 - i)
             h = ws.out[li]
         return h
 

@@ -157,6 +157,22 @@ int gw_conv_tc_n_part(const gw_conv_tc_shape* s);
 int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
                void* raw, float* part, int variant, void* stream);
 
+/* ---- fused block: Conv1d(k=3) -> GroupNorm(8) -> SiLU -> + cond 1x1 conv -> FiLM (-> avg_pool1d(2)) in one tcgen05 kernel
+ * (models.py:160-173, 188-193, 205-208, 217-225; see conv_gn.cuh).  gw_conv_tc + gw_gn_apply without the raw round trip:
+ * a group of G CTAs keeps one sample's conv output in tensor memory and exchanges GroupNorm partial sums through `sync`.
+ *   s: pair 0 (encoder / mid conv) or 1 (decoder conv over cat[upsample(src0), src1]); packed from gw_conv_tc_pack;
+ *   cond [B, L, Cc] fp32 (gw_cond_pyramid level) or NULL when Cc == 0; film as in gw_gn_apply;
+ *   out [B, L, Cout] bf16; pooled [B, L/2, Cout] bf16 or NULL; raw [B, L, Cout] bf16 or NULL (training keeps the conv output
+ *   for gw_gn_bwd); stats_out [B, 8, 2] fp32 (mean, rstd) or NULL;
+ *   sync: gw_conv_gn_sync_bytes(B) bytes, zeroed ONCE by the caller, shared by all launches on one stream.
+ * gw_conv_gn_group returns G (0: this layer shape / length is not supported -> use gw_conv_tc + gw_gn_apply). */
+int gw_conv_gn_group(const gw_conv_tc_shape* s, int Cc, int pool);
+long gw_conv_gn_sync_bytes(int B);
+int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
+               const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
+               const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
+               void* out, void* pooled, void* raw, float* stats_out, void* sync, void* stream);
+
 /* =====================================================================================================
  * Training step (train.py:320-456): loss, backward of every block, optimiser.  Parameter gradients are always
  * ACCUMULATED (+=) into fp32 buffers laid out like the reference parameters; the caller zeroes the flat gradient

@@ -128,7 +128,7 @@ class TimedLib:
 def measured_traffic(step_kind, kernel, B, L):
     """Per-launch DRAM traffic of `kernel` from the committed ncu capture (profiles/r01g_traffic.json); only valid for the
     shape it was captured at (B=256, L=4096), otherwise None."""
-    p = os.path.join(ROOT, "profiles", "r01g_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01i_traffic.json")
     if not os.path.exists(p) or (B, L) != (256, 4096):
         return None
     d = json.load(open(p)).get(step_kind, {}).get(kernel)
@@ -192,9 +192,17 @@ def family_rooflines(records, spec, B, L, pk, n_steps, train):
         add("GroupNorm/SiLU/cond/FiLM backward", ["gw_gn_bwd"], "hbm", gn_bwd_bytes,
             "bf16: 2 passes over (raw, dout[, dpool/2]) + d_raw write per block")
     else:
+        # inference: one kernel per block does the conv AND the GroupNorm/SiLU/cond/FiLM/pool epilogue (conv_gn.cuh); its
+        # roofline counts the conv FLOPs only, against the time of the whole fused kernel
+        add("fused conv block (tcgen05 implicit GEMM + GroupNorm/SiLU/cond/FiLM/pool epilogue)", ["gw_conv_gn"], "tensor",
+            conv_fl, "2*Cin*Cout*3*L*B per conv (the fused elementwise work is not counted)")
         add("conv fwd (tcgen05 implicit GEMM)", ["gw_conv_tc"], "tensor", conv_fl, "2*Cin*Cout*3*L*B per conv")
-    add("GroupNorm/SiLU/cond/FiLM/pool forward", ["gw_gn_apply"], "hbm", gn_fwd_bytes * n_fwd,
-        "bf16: raw read + out write (+ pooled write) per block")
+    gn_keys = [k for k in ("gw_gn_apply", "gw_gn_apply_stream") if k in t_by]
+    n_gn = sum(1 for n, _, _ in records if n in gn_keys) / max(1, n_steps)
+    gn_share = min(1.0, n_gn / (len(tab) * n_fwd)) if n_fwd else 0.0        # inference: only the first block is unfused
+    gn_work = gn_fwd_bytes * n_fwd if gn_share >= 0.999 else (2.5 * act[0] * 2) * n_gn
+    add("GroupNorm/SiLU/cond/FiLM/pool forward", gn_keys, "hbm", gn_work,
+        "bf16: raw read + out write (+ pooled write) per unfused block")
     other = step_ms - sum(f["ms_per_step"] for f in fams)
     return fams, step_ms, other, t_by
 
@@ -365,7 +373,7 @@ def bench_sampling(args, workload, B, steps, warmup, world, rank, dev, barrier, 
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
-    launches_per_chain = plan.N * (2 * (2 * model.spec.depth + 1) + 2) + 1
+    launches_per_chain = None                         # counted from the profiled steps below
 
     def chain_e2e():
         cond = y_host.to(dev, non_blocking=True)
@@ -403,6 +411,7 @@ def bench_sampling(args, workload, B, steps, warmup, world, rank, dev, barrier, 
         torch.cuda.synchronize()
         tl.on = False
         eng.lib = tl._lib
+        launches_per_chain = plan.N * (len(tl.records) // 4) + 1
         fams, step_ms_eager, other, _ = family_rooflines(tl.records, model.spec, plan.Bn, L, pk, 4, train=False)
         step_ms = ms / steps / plan.N
         flops_wf = model.spec.conv_flops(L) * plan.N
@@ -414,10 +423,14 @@ def bench_sampling(args, workload, B, steps, warmup, world, rank, dev, barrier, 
                "e2e": {"value": e2e, "unit": "waveforms/s", "h2d_bytes_per_step": int(y_host.numel() * 4),
                        "d2h_bytes_per_step": int(out_host.numel() * 4)},
                "gpu_launches": launches_per_chain * steps, "clocks": clk,
-               "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel (6 launches per reverse step, tcgen05+TMA implicit GEMM)",
+               "roofline": {"bound": "tensor",
+                            "kernel": "conv_gn_kernel (6 launches per reverse step: tcgen05+TMA implicit GEMM with the "
+                                      "GroupNorm/SiLU/cond/FiLM/pool epilogue fused in)"
+                            if conv["entry_points"] == ["gw_conv_gn"] else "conv_tc2_kernel (tcgen05+TMA implicit GEMM)",
                             "achieved": conv["achieved"], "peak": pk["bf16"], "unit": "TFLOP/s", "frac": conv["frac"],
-                            "traffic": measured_traffic("reverse_step", "conv_tc2_kernel", plan.Bn, L),
-                            "traffic_note": "bytes per launch, ncu capture profiles/r01g_traffic.json (B=256, L=4096, in_ch=3)",
+                            "traffic": measured_traffic("reverse_step", "conv_gn_kernel" if conv["entry_points"] == ["gw_conv_gn"]
+                                                        else "conv_tc2_kernel", plan.Bn, L),
+                            "traffic_note": "bytes per launch, ncu capture profiles/r01i_traffic.json (B=256, L=4096, in_ch=3)",
                             "peak_source": pk["src"] + " burst (kernels timed one by one)",
                             "share_of_step": conv["share_of_step"]},
                "kernels": fams,

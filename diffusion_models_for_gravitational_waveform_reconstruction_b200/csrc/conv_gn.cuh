@@ -20,6 +20,11 @@
 #define CGN_NCA_MAX 8
 #define CGN_EPI_GROUPS 2       // epilogue warpgroups (8 warps each) working on alternate samples
 #define CGN_THREADS (64 + CGN_EPI_GROUPS * 256)
+// 1: the 16 epilogue warps form ONE group (every warp owns one 32x64 chunk of every sample); 0: two groups of 8 warps on
+// alternate samples (two chunks per warp)
+#ifndef CGN_ONE_GROUP
+#define CGN_ONE_GROUP 0
+#endif
 
 struct GnFuseArgs {
     const float* gn_w;
@@ -71,6 +76,20 @@ __device__ __forceinline__ void gn_cols16(uint32_t taddr, int kb, const ulonglon
                                           uint32_t stgp, int lane, int dm = 0) {
     const unsigned long long half2 = pkf2(0.5f, 0.5f);
     const int tq = lane & 3, tr = lane >> 2;
+    // coefficient loads first: the TMEM load below is an asm volatile with a memory clobber, nothing moves across it, and the
+    // LDS -> FFMA2 latency would otherwise sit exposed at the head of every block
+    ulonglong2 c_ab2[2], c_ge2[2];
+    unsigned long long wv2[2][NCA];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int pi = 4 * (2 * kb + kk) + tq;
+        c_ab2[kk] = ab[pi];
+        c_ge2[kk] = ge[pi];
+        if (HAS_COND) {
+#pragma unroll
+            for (int jj = 0; jj < NCA; ++jj) wv2[kk][jj] = w[pi * NCA + jj];
+        }
+    }
     uint32_t v[16];
 #ifdef CGN_ABLATE
     if (dm & 32) {
@@ -82,14 +101,11 @@ __device__ __forceinline__ void gn_cols16(uint32_t taddr, int kb, const ulonglon
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
         const int k = 2 * kb + kk;
-        const int pi = 4 * k + tq;
-        const ulonglong2 c_ab = ab[pi];
-        const ulonglong2 c_ge = ge[pi];
+        const ulonglong2 c_ab = c_ab2[kk];
+        const ulonglong2 c_ge = c_ge2[kk];
         unsigned long long wv[NCA];
-        if (HAS_COND) {
 #pragma unroll
-            for (int jj = 0; jj < NCA; ++jj) wv[jj] = w[pi * NCA + jj];
-        }
+        for (int jj = 0; jj < NCA; ++jj) wv[jj] = HAS_COND ? wv2[kk][jj] : 0ull;
         unsigned long long o[4];
         uint32_t r[4];
 #pragma unroll
@@ -226,7 +242,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * 28);
     float* s_bias = reinterpret_cast<float*>(misc + 256);               // [256]
     // per epilogue warpgroup: s_stat [8 warps][8 groups][2] | s_x [G][16] | s_abf, s_gef [128 column pairs][4] | s_wf [128][NCA][2]
-    constexpr int GRP_FLOATS = 128 + CGN_MAX_G * 16 + 512 + 512 + 256 * NCA;
+    constexpr int GRP_FLOATS = 256 + CGN_MAX_G * 16 + 512 + 512 + 256 * NCA;
     float* s_grp0 = s_bias + 256;
     auto a_full = [&](int i) { return smem_u32(bars + i); };
     auto a_empty = [&](int i) { return smem_u32(bars + SA + i); };
@@ -332,14 +348,17 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
-        const int eg = (warp - 2) >> 3;               // epilogue warpgroup: samples it = eg, eg + GROUPS, ... of this CTA
-        const int e = (warp - 2) & 7;
+        constexpr bool ONE = CGN_ONE_GROUP != 0;
+        constexpr int NT = ONE ? 512 : 256;           // threads of one epilogue group
+        const int eg = ONE ? 0 : (warp - 2) >> 3;     // epilogue warpgroup: samples it = eg, eg + GROUPS, ... of this CTA
+        const int e = ONE ? (warp - 2) : ((warp - 2) & 7);
         const int q = warp & 3;                       // TMEM lane quarter
-        const int ch = e >> 2;                        // which half of the columns
-        const int tid = (threadIdx.x - 64) & 255;
+        const int ch = (e >> 2) & 1;                  // which half of the columns
+        const int kc_lo = ONE ? (e >> 3) : 0, kc_hi = ONE ? (e >> 3) + 1 : 2;     // my chunk(s) of the two per (quarter, half)
+        const int tid = (threadIdx.x - 64) & (NT - 1);
         const int bar_id = 1 + eg;
         float* s_stat = s_grp0 + eg * GRP_FLOATS;
-        float* s_x = s_stat + 128;
+        float* s_x = s_stat + 256;
         float* s_abf = s_x + CGN_MAX_G * 16;
         float* s_gef = s_abf + 512;
         float* s_wf = s_gef + 512;
@@ -389,7 +408,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 __syncwarp();
             }
         };
-        constexpr int ITS = CGN_EPI_GROUPS;
+        constexpr int ITS = ONE ? 1 : CGN_EPI_GROUPS;
         for (int it = eg, b = grp + eg * F.n_groups; b < F.B; it += ITS, b += ITS * F.n_groups) {
             const int as = it & 1;
             if (tid == 0) CGN_STAMP(0);
@@ -406,12 +425,15 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             }
             if (lane < 16) my_stat[lane] = 0.0f;
             __syncwarp();
-            mbar_wait(acc_full(as), ((uint32_t)(it >> 1)) & 1u);
+            // one warp polls the accumulator barrier, the other seven block on a hardware barrier: eight spinning warps were
+            // ~20 % of all issued instructions, taken from the other warpgroup's arithmetic
+            if (e == 0) mbar_wait(acc_full(as), ((uint32_t)(it >> 1)) & 1u);
+            named_bar_sync(bar_id, NT);
             tc_fence_after();
             if (tid == 0) CGN_STAMP(1);
             // ---- pass 1: GroupNorm partial sums of (acc + bias) (+ the raw tensor for the backward pass)
 #pragma unroll 1
-            for (int kc = 0; kc < 2; ++kc) {
+            for (int kc = kc_lo; kc < kc_hi; ++kc) {
                 const int mt = MT == 2 ? kc : 0;
                 const int c0 = ch * cols_per_warp + (MT == 2 ? 0 : kc * 64);
                 const int m_tile = ms * MT + mt;
@@ -434,21 +456,21 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 }
                 stat_reduce<CG_LOG2>(sv, my_stat, ((n_tile * P.bn + c0) & (P.cout - 1)) >> CG_LOG2, lane);
             }
-            named_bar_sync(bar_id, 256);
+            named_bar_sync(bar_id, NT);
             if (tid == 0) CGN_STAMP(2);
             // cond values of my fragment rows (row-group m: row 8m + lane/4 of this warp's 32 rows) in my output phase, for the
             // first pass-2 chunk: issued now, so the loads complete while the statistics travel
             float cd[4][NCA];
-            load_cond(b, 0, cd);
+            load_cond(b, (ONE && MT == 2) ? kc_lo : 0, cd);
             // ---- exchange: publish this CTA's 16 sums, collect the G x 16 sums of the group
             if (tid < 16) {
                 float v = 0.0f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) v += s_stat[w * 16 + tid];
+                for (int w = 0; w < NT / 32; ++w) v += s_stat[w * 16 + tid];
                 st_relaxed_u64(F.xchg + ((size_t)b * CGN_MAX_G + j_cta) * 16 + tid,
                                ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v));
             }
-            for (int i = tid; i < G * 16; i += 256) {
+            for (int i = tid; i < G * 16; i += NT) {
                 const unsigned long long* src = F.xchg + ((size_t)b * CGN_MAX_G + (i >> 4)) * 16 + (i & 15);
                 unsigned long long pk = ld_relaxed_u64(src);
                 if ((unsigned int)(pk >> 32) != epoch) {
@@ -460,7 +482,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 }
                 s_x[i] = __uint_as_float((unsigned int)pk);
             }
-            named_bar_sync(bar_id, 256);
+            named_bar_sync(bar_id, NT);
             if (tid == 0) CGN_STAMP(3);
             // ---- statistics -> affine coefficients of my column (conv bias folded in; h = half of the GroupNorm output)
             if (has_col) {
@@ -485,11 +507,11 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     F.stats_out[((size_t)b * 8 + my_g) * 2 + 1] = rstd;
                 }
             }
-            named_bar_sync(bar_id, 256);
+            named_bar_sync(bar_id, NT);
             if (tid == 0) CGN_STAMP(4);
             // ---- pass 2: normalise / activate / modulate out of TMEM
 #pragma unroll 1
-            for (int kc = 0; kc < 2; ++kc) {
+            for (int kc = kc_lo; kc < kc_hi; ++kc) {
                 const int mt = MT == 2 ? kc : 0;
                 const int c0 = ch * cols_per_warp + (MT == 2 ? 0 : kc * 64);
                 const int m_tile = ms * MT + mt;
@@ -498,7 +520,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 const uint32_t acc = tmem_base + (uint32_t)(as * 256 + mt * P.bn + c0) + ((uint32_t)(q * 32) << 16);
                 const uint32_t stg = stg0 + buf * 4096, stgp = stgp0 + buf * 2048;
                 float cdn[4][NCA];
-                if (MT == 2 && kc == 0) load_cond(b, 1, cdn);      // the second tile's rows, needed one chunk later
+                if (!ONE && MT == 2 && kc == 0) load_cond(b, 1, cdn);      // the second tile's rows, needed one chunk later
                 stage_wait();
                 const ulonglong2* ab = reinterpret_cast<const ulonglong2*>(s_abf) + (c0 >> 1);
                 const ulonglong2* ge = reinterpret_cast<const ulonglong2*>(s_gef) + (c0 >> 1);
@@ -516,13 +538,19 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 if (F.dbg_mode & 8) continue;
 #endif
                 if (lane == 0) {
+#ifdef CGN_ABLATE
+                    if (!(F.dbg_mode & 128))
+#endif
                     tma_store_3d(&tm_out, stg, n_tile * P.bn + c0, row_base, b);
+#ifdef CGN_ABLATE
+                    if (!(F.dbg_mode & 64))
+#endif
                     if (POOL) tma_store_3d(&tm_pool, stgp, n_tile * P.bn + c0, row_base >> 1, b);
                     tma_commit();
                 }
                 ++stores;
                 if (NBUF == 2) buf ^= 1;
-                if (MT == 2 && kc == 0) {
+                if (!ONE && MT == 2 && kc == 0) {
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
 #pragma unroll
@@ -532,7 +560,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             }
             // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
             tc_fence_before();
-            named_bar_sync(bar_id, 256);
+            named_bar_sync(bar_id, NT);
             if (e == 0 && lane == 0) mbar_arrive(acc_empty(as));
             if (tid == 0) CGN_STAMP(5);
         }
@@ -585,7 +613,7 @@ static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
     pl->n_groups = sms / pl->G;
     if (pl->n_groups > s->B) pl->n_groups = s->B;
     const int nca = (Cc == 1 || Cc == 5) ? Cc : CGN_NCA_MAX;
-    const int misc = 256 + 1024 + CGN_EPI_GROUPS * (512 + CGN_MAX_G * 64 + 2048 + 2048 + 1024 * nca) + 64;
+    const int misc = 256 + 1024 + CGN_EPI_GROUPS * (1024 + CGN_MAX_G * 64 + 2048 + 2048 + 1024 * nca) + 64;
     // ring / staging depths: prefer deep rings, shrink until the CTA fits
     const int ew = 8 * CGN_EPI_GROUPS;
     const int cand[6][3] = {{2, 4, 2}, {2, 3, 2}, {2, 4, 1}, {2, 3, 1}, {2, 2, 1}, {1, 2, 1}};

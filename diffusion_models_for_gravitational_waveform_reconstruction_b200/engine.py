@@ -184,6 +184,10 @@ class UNetEngine:
         # bf16/tcgen05: conv + GroupNorm + SiLU + cond + FiLM (+ pool) of a block in ONE kernel (conv_gn.cuh) wherever the
         # layer shape allows it; the conv output then never makes the HBM round trip between gw_conv_tc and gw_gn_apply
         self.fuse_gn = True
+        # training (keep_raw) forwards also have to write the conv output for the backward pass and carry five cond channels;
+        # measured on B200 the fused kernel then loses its edge (962 us vs ~900 us of conv + GroupNorm launches per step at
+        # B=256, L=4096, in_ch=7), so it stays an inference default; parity-tested for both
+        self.fuse_gn_train = False
         self._fuse_ok: Dict[tuple, bool] = {}
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
@@ -344,7 +348,8 @@ class UNetEngine:
         L0 = src0.shape[1]
         Cc = sp.cond_in_ch
         fused = False
-        if self.fuse_gn and self.dtype == "bf16" and self.tc_supported(li, L, L0):
+        if (self.fuse_gn and (ws.stats is None or self.fuse_gn_train) and self.dtype == "bf16"
+                and self.tc_supported(li, L, L0)):
             fkey = (li, L, L0, pooled is not None)
             fused = self._fuse_ok.get(fkey)
             if fused is None:

@@ -163,6 +163,7 @@ def test_fused_conv_gn_block(in_ch, cc, L, B, keep_raw):
     x = gaussian((B, in_ch, L), seed=3 + L)
     t = torch.tensor(([24, 999, 500, 3, 250] * B)[:B])
     fused, plain = _engine(sd, in_ch, cc, "bf16", "tc"), _engine(sd, in_ch, cc, "bf16", "tc")
+    fused.fuse_gn_train = True
     plain.fuse_gn = False
     # three forwards through the same workspace: the exchange epoch must advance between launches
     for _ in range(3):

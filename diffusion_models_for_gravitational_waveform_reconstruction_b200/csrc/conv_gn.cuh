@@ -15,6 +15,7 @@
 // All CTAs of a group spin on each other's packets, so the whole grid must be co-resident: grid = G x n_groups <= #SMs and
 // one CTA per SM (the shared-memory footprint guarantees it).
 #pragma once
+#include "xchg.cuh"
 
 #define CGN_MAX_G 32
 #define CGN_NCA_MAX 8
@@ -47,14 +48,6 @@ struct GnFuseArgs {
         if (F.dbg != nullptr && it < 16) F.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (k)] = clock64();    \
     } while (0)
 
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 static __device__ __noinline__ void xchg_timeout(int b, int src) {
     printf("gwb200 conv_gn kernel: statistics exchange timed out (block %d sample %d source %d)\n", blockIdx.x, b, src);
     __trap();

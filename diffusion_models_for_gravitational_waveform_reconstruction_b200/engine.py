@@ -387,7 +387,19 @@ class UNetEngine:
         d = sp.depth
         B, Cx, L = net_a.shape
         st = _cabi.stream_ptr()
-        if ws.stats is None and self.fuse_first_block:
+        Cc0 = sp.cond_in_ch
+        if (ws.stats is None and self.fuse_gn and self.dtype == "bf16" and ws.sync is not None
+                and self.lib.gw_conv_in_gn_group(Cx, L, sp.base_ch, Cc0) > 0):
+            # inference: conv + GroupNorm + SiLU + cond + FiLM + pool of the first block in one kernel (conv_in_gn.cu)
+            check(self.lib.gw_conv_in_gn(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),
+                                         ptr(self.p["encoders.0.0.bias"]), sp.base_ch, ptr(self.p["encoders.0.1.weight"]),
+                                         ptr(self.p["encoders.0.1.bias"]), Cc0,
+                                         ptr(self.p["cond_enc.0.weight"]) if Cc0 > 0 else None,
+                                         ptr(self.p["cond_enc.0.bias"]) if Cc0 > 0 else None, ptr(film),
+                                         sp.film_offsets()[0], film_b_stride, film_step_stride, ptr(ws.out[0]),
+                                         ptr(ws.pooled[0]), ptr(ws.sync), st), "conv_in_gn")
+            self.launches += 1
+        elif ws.stats is None and self.fuse_first_block:
             # inference: the first block never materialises its raw conv output (stats pass + recompute/apply pass)
             Cc = sp.cond_in_ch
             check(self.lib.gw_conv_in_block(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),

@@ -173,6 +173,17 @@ int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const void* src1, co
                const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
                void* out, void* pooled, void* raw, float* stats_out, void* sync, void* stream);
 
+/* ---- fused FIRST block for inference: Conv1d(C_in -> 64, k=3) -> GroupNorm -> SiLU -> + cond 1x1 conv -> FiLM (-> pool) in
+ * one kernel (models.py:160-173, 188-193, 204-208; conv_in_gn.cu).  gw_conv_in + gw_gn_apply without the raw tensor: G = L/256
+ * CTAs share a sample, keep their conv rows in shared memory and exchange GroupNorm sums through `sync` (the buffer of
+ * gw_conv_gn).  x / x_alt / step_ptr as in gw_conv_in; the conditioning channels are x[:, 1:1+Cc] themselves.  bf16 outputs.
+ * gw_conv_in_gn_group returns G, or 0 when the shape is not supported (C != 64, odd L, L > 16384). */
+int gw_conv_in_gn_group(int Cx, int L, int C, int Cc);
+int gw_conv_in_gn(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
+                  const float* bias, int C, const float* gn_w, const float* gn_b, int Cc, const float* wc, const float* bc,
+                  const float* film, int film_off, long film_b_stride, long film_step_stride, void* out, void* pooled,
+                  void* sync, void* stream);
+
 /* =====================================================================================================
  * Training step (train.py:320-456): loss, backward of every block, optimiser.  Parameter gradients are always
  * ACCUMULATED (+=) into fp32 buffers laid out like the reference parameters; the caller zeroes the flat gradient

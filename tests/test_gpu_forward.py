@@ -185,3 +185,30 @@ def test_fused_conv_gn_block(in_ch, cc, L, B, keep_raw):
         with torch.no_grad():
             ref = oracle.unet_forward(sd, cfg, x, t)
         assert rel_l2(eps_f, ref) <= BF16_TOL
+
+
+@pytest.mark.parametrize("in_ch,cc,L,B", [(3, 1, 1000, 3), (7, 5, 2050, 2), (3, 1, 9000, 2), (1, 0, 768, 2)])
+def test_fused_first_block_partial_tiles(in_ch, cc, L, B):
+    """gw_conv_in_gn on lengths that leave a partial CTA slice (256 rows up to L = 8192, 512 beyond) and without
+    conditioning; the deeper blocks of these lengths take the unfused kernels."""
+    sd = make_state_dict(in_ch, cc, seed=0)
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=(in_ch > 1))
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.engine import ModelSpec, UNetEngine
+    spec = ModelSpec(in_ch=in_ch, cond_in_ch=cc, use_selfcond=(in_ch > 1))
+    fused = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype="bf16", conv_impl="tc")
+    plain = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype="bf16", conv_impl="tc")
+    plain.fuse_gn = False
+    x = gaussian((B, in_ch, L), seed=5 + L)
+    t = torch.tensor(([700, 12, 333] * B)[:B])
+    assert fused.lib.gw_conv_in_gn_group(in_ch, L, 64, cc) > 0
+    for _ in range(2):
+        eps_f = fused.forward(x.cuda(), t.cuda())
+    eps_p = plain.forward(x.cuda(), t.cuda())
+    wf, wp = fused.workspace(B, L, False), plain.workspace(B, L, False)
+    assert rel_l2(wf.out[0].float(), wp.out[0].float()) <= 2e-3
+    assert rel_l2(wf.pooled[0].float(), wp.pooled[0].float()) <= 2e-3
+    assert rel_l2(eps_f, eps_p) <= BF16_TOL
+    if B * L <= 3 * 4096:
+        with torch.no_grad():
+            ref = oracle.unet_forward(sd, cfg, x, t)
+        assert rel_l2(eps_f, ref) <= BF16_TOL

@@ -61,6 +61,10 @@ _SIGS.update({
     "gw_gn_bwd_scratch_elems": ([_I, _I, _I, _I], _L),
     "gw_gn_bwd": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P,
                    _P, _P, _P], _I),
+    "gw_gn_bwd2": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P,
+                    _P, _P, _P, _P], _I),
+    "gw_gn_bwd_sync_bytes": ([_I], _L),
+    "gw_gn_bwd_fused_group": ([_I, _I, _I, _I, _I], _I),
     "gw_weight_dgrad": ([_P, _I, _I, _P, _P], _I),
     "gw_split_cat_grad": ([_P, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     "gw_wgrad3_simt": ([_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _L, _P, _P], _I),

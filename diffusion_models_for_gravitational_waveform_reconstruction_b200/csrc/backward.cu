@@ -292,6 +292,7 @@ __device__ __forceinline__ float sigmoid_bw(float x) {
 }
 
 #include "gn_bwd.cuh"
+#include "xchg.cuh"
 
 // per-thread constants of one channel quad
 template <int NCA>
@@ -821,8 +822,15 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
 
 int g_gn_bwd_stream = 1;
 extern int g_final_stream;
+extern int g_gn_bwd_fused, g_gn_bwd_fused_slice;
+int g_gn_bwd_chunk = 0;
+extern int g_gn_bwd_stats_fast;
 extern "C" int gw_set_option(const char* name, int value) {
     if (strcmp(name, "gn_bwd_stream") == 0) { g_gn_bwd_stream = value; return GW_OK; }
+    if (strcmp(name, "gn_bwd_stats_fast") == 0) { g_gn_bwd_stats_fast = value; return GW_OK; }
+    if (strcmp(name, "gn_bwd_chunk") == 0) { g_gn_bwd_chunk = value; return GW_OK; }
+    if (strcmp(name, "gn_bwd_fused") == 0) { g_gn_bwd_fused = value; return GW_OK; }
+    if (strcmp(name, "gn_bwd_fused_slice") == 0) { g_gn_bwd_fused_slice = value; return GW_OK; }
     if (strcmp(name, "final_stream") == 0) { g_final_stream = value; return GW_OK; }
     gw_set_error("gw_set_option: unknown option %s", name);
     return GW_ERR_ARG;
@@ -838,13 +846,42 @@ static int gn_rows_per_cta(int L, int C) {
 extern "C" long gw_gn_bwd_scratch_elems(int B, int L, int C, int Cc) {
     const int rows = gn_rows_per_cta(L, C), n_rc = gw_cdiv(L, rows), nvr = 4 + Cc;
     // [partials | per-sample reduced | group means]
-    return (long)B * n_rc * C * nvr + (long)B * C * nvr + (long)B * 16;
+    const long two_pass = (long)B * n_rc * C * nvr + (long)B * C * nvr + (long)B * 16;
+    // one-pass kernel (gn_bwd_fused.cu): up to XCHG_MAX_G row CTAs per sample, plus the conv-bias partials
+    const long one_pass = (long)B * XCHG_MAX_G * C * nvr + (long)B * C * nvr + (long)B * 16 + (long)B * XCHG_MAX_G * C;
+    return two_pass > one_pass ? two_pass : one_pass;
+}
+extern "C" long gw_gn_bwd_sync_bytes(int B) { return 64 + (long)B * XCHG_MAX_G * 16 * 8; }
+// CTAs per sample the one-pass kernel would use for this layer (0: the two-pass kernels run)
+extern "C" int gw_gn_bwd_fused_group(int L, int C, int Cc, int has_do, int has_pool) {
+    return gn_bwd_fused_group(L, C, Cc, has_do != 0, has_pool != 0);
 }
 
 template <typename T, bool FAST>
 static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
-                      float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, cudaStream_t st) {
+                      float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* sync, cudaStream_t st) {
     const int C = a.C, L = a.L, Cc = a.Cc, nvr = 4 + Cc;
+    if (FAST && sync != nullptr && a.do_eps == nullptr) {
+        // one-pass kernel: operands read once, d_raw formed out of shared memory (gn_bwd_fused.cu)
+        const int G = gn_bwd_fused_group(L, C, Cc, a.do_a != nullptr, a.do_pool != nullptr);
+        if (G > 0) {
+            float* partial = scratch;
+            float* redb = partial + (size_t)B * G * C * nvr;
+            float* gstat = redb + (size_t)B * C * nvr;
+            float* biasp = gstat + (size_t)B * 16;
+            const int rcf = gn_bwd_fused(a, B, partial, biasp, d_raw, sync, st);
+            if (rcf == GW_OK) {
+                gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvr * sizeof(float), st>>>(partial, G, C, nvr, L, a.gn_w, a.wc, a.bc, redb,
+                                                                                        dfilm, dfilm_b_stride, a.film_off, gstat);
+                GW_LAUNCH_CHECK();
+                gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w,
+                                                                   d_gn_b, d_wc, d_bc);
+                GW_LAUNCH_CHECK();
+                return reduce_rows(biasp, B * G, C, C, 1.0f, d_conv_bias, 1, st);
+            }
+            if (rcf != GW_ERR_UNSUPPORTED) return rcf;
+        }
+    }
     const int n_rc = gw_cdiv(L, a.rows_per_cta), n_tr = 256 / (C / 4);
     float* partial = scratch;
     float* redb = partial + (size_t)B * n_rc * C * nvr;
@@ -854,6 +891,35 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     // bf16 with friendly shapes: HBM-streaming kernels (stream_gn.cu), same partial layouts
     const bool stream_ok = FAST && g_gn_bwd_stream && L % 4 == 0 && (C == 64 || C == 128 || C == 256) &&
                            a.rows_per_cta == gn_bwd_stream_rows(L, C);
+    if (FAST && stream_ok && g_gn_bwd_chunk > 0 && a.do_eps == nullptr && B > g_gn_bwd_chunk) {
+        // experiment: sub-batches small enough that the second pass finds its operands in the L2
+        const size_t esz = 2;
+        for (int b0 = 0; b0 < B; b0 += g_gn_bwd_chunk) {
+            const int Bc = B - b0 < g_gn_bwd_chunk ? B - b0 : g_gn_bwd_chunk;
+            GnBwdArgs c = a;
+            c.raw = (const char*)a.raw + (size_t)b0 * L * C * esz;
+            c.stats = a.stats + (size_t)b0 * 16;
+            if (a.cond) c.cond = a.cond + (size_t)b0 * L * Cc;
+            c.film = a.film + (size_t)b0 * a.film_b_stride;
+            if (a.do_a) c.do_a = (const char*)a.do_a + (size_t)b0 * L * C * esz;
+            if (a.do_pool) c.do_pool = (const char*)a.do_pool + (size_t)b0 * (L / 2) * C * esz;
+            float* pc = partial + (size_t)b0 * n_rc * C * nvr;
+            int rcs = gn_bwd_stats_stream(c, Bc, pc, st);
+            if (rcs != GW_OK) return rcs;
+            gn_bwd_finalize_kernel<<<Bc, 1024, (size_t)C * nvr * sizeof(float), st>>>(
+                pc, n_rc, C, nvr, L, a.gn_w, a.wc, a.bc, redb + (size_t)b0 * C * nvr, dfilm + (size_t)b0 * dfilm_b_stride,
+                dfilm_b_stride, a.film_off, gstat + (size_t)b0 * 16);
+            GW_LAUNCH_CHECK();
+            rcs = gn_bwd_apply_stream(c, Bc, gstat + (size_t)b0 * 16, (char*)d_raw + (size_t)b0 * L * C * esz, pc, st);
+            if (rcs != GW_OK) return rcs;
+            rcs = reduce_rows(pc, Bc * n_rc, C, C, 1.0f, d_conv_bias, 1, st);
+            if (rcs != GW_OK) return rcs;
+        }
+        gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+                                                           d_wc, d_bc);
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
 #define GNB_GO(CCV)                                                                                                       \
     do {                                                                                                                  \
         if (FAST && stream_ok) {                                                                                          \
@@ -900,11 +966,13 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
 
 // d_raw [B, L, C] (dtype); parameter gradients are ACCUMULATED into d_gn_w, d_gn_b [C], d_wc [C, Cc], d_bc [C],
 // d_conv_bias [C]; dfilm row b gets (d gamma | d beta) of this layer at film_off (overwritten).
-extern "C" int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
-                         const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
-                         long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
-                         int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
-                         float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* stream) {
+// gw_gn_bwd2: sync_buf (gw_gn_bwd_sync_bytes(B) bytes, zeroed once by the caller, kept across calls) enables the one-pass
+// bf16 kernel where the layer shape allows it; NULL = two-pass kernels.
+extern "C" int gw_gn_bwd2(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
+                          const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+                          long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
+                          int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+                          float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* sync_buf, void* stream) {
     GW_REQUIRE(C % 64 == 0 && C <= 1024 && 256 % (C / 4) == 0, "gw_gn_bwd: C=%d", C);
     GW_REQUIRE(Cc >= 0 && Cc <= BW_MAX_CC, "gw_gn_bwd: Cc=%d", Cc);
     GW_REQUIRE((cond != nullptr) == (Cc > 0), "gw_gn_bwd: cond/Cc mismatch");
@@ -918,8 +986,16 @@ extern "C" int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int 
     a.rows_per_cta = gn_rows_per_cta(L, C);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32)
-        return gn_bwd_run<float, false>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, st);
-    return gn_bwd_run<bf16, true>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, st);
+        return gn_bwd_run<float, false>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, nullptr, st);
+    return gn_bwd_run<bf16, true>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, sync_buf, st);
+}
+extern "C" int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
+                         const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+                         long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
+                         int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+                         float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* stream) {
+    return gw_gn_bwd2(raw, stats, B, L, C, gn_w, gn_b, cond, Cc, wc, bc, film, film_off, film_b_stride, do_a, do_pool, do_eps, do_w,
+                      dtype, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -21,7 +21,29 @@ struct GnBwdArgs {
     int rows_per_cta;
 };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ f32x2 bf2_lo(uint32_t w) { return pk2(w << 16, w & 0xffff0000u); }
+
+// z/2, sigmoid and silu derivative of a channel pair from one tanh.approx per element
+__device__ __forceinline__ void sg_silu_pair(f32x2 x, f32x2 hA, f32x2 hB, f32x2& z, f32x2& act, f32x2& dact) {
+    const f32x2 one = pkf2(1.0f, 1.0f), half2 = pkf2(0.5f, 0.5f), neg1 = pkf2(-1.0f, -1.0f);
+    const f32x2 hh = ffma2(x, hA, hB);
+    z = fadd2(hh, hh);
+    float h0, h1, t0, t1;
+    upk2(hh, h0, h1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+    const f32x2 sg = ffma2(pkf2(t0, t1), half2, half2);
+    act = fmul2(z, sg);
+    dact = fmul2(sg, ffma2(z, ffma2(sg, neg1, one), one));
+}
+#endif
+
 // HBM-streaming bf16 implementations (stream_gn.cu); same partial layouts as the register-streaming kernels
 int gn_bwd_stream_rows(int L, int C);
 int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t st);
 int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_raw, float* partial_bias, cudaStream_t st);
+
+// one-pass implementation (gn_bwd_fused.cu): a group of CTAs keeps a sample's operands in shared memory
+int gn_bwd_fused_group(int L, int C, int Cc, bool has_do, bool has_pool);
+int gn_bwd_fused(const GnBwdArgs& a, int B, float* partial, float* partial_bias, void* d_raw, void* sync, cudaStream_t st);

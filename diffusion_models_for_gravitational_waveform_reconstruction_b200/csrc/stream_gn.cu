@@ -14,15 +14,6 @@
 #define SG_DEPTH 4
 #define SG_MAX_CC 8
 
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward: GroupNorm-apply + SiLU + cond 1x1 conv + FiLM (+ avg_pool), see gn_apply_kernel in forward.cu
 // ------------------------------------------------------------------------------------------------
@@ -238,27 +229,12 @@ extern "C" int gw_gn_apply_stream(const void* raw, const float* part, int n_part
 // ================================================================================================
 #include "gn_bwd.cuh"
 
+int g_gn_bwd_stats_fast = 1;
 int gn_bwd_stream_rows(int L, int C) {
     const int S = SG_STAGE_BYTES / (C * 2);
     int rows = 8 * S;
     if (rows > L) rows = L;
     return rows < 1 ? 1 : rows;
-}
-
-__device__ __forceinline__ f32x2 bf2_lo(uint32_t w) { return pk2(w << 16, w & 0xffff0000u); }
-
-// z/2, sigmoid and silu derivative of a channel pair from one tanh.approx per element
-__device__ __forceinline__ void sg_silu_pair(f32x2 x, f32x2 hA, f32x2 hB, f32x2& z, f32x2& act, f32x2& dact) {
-    const f32x2 one = pkf2(1.0f, 1.0f), half2 = pkf2(0.5f, 0.5f), neg1 = pkf2(-1.0f, -1.0f);
-    const f32x2 hh = ffma2(x, hA, hB);
-    z = fadd2(hh, hh);
-    float h0, h1, t0, t1;
-    upk2(hh, h0, h1);
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
-    const f32x2 sg = ffma2(pkf2(t0, t1), half2, half2);
-    act = fmul2(z, sg);
-    dact = fmul2(sg, ffma2(z, ffma2(sg, neg1, one), one));
 }
 
 // Stage layout (bytes): raw [S*C*2] | do_a [S*C*2] | do_pool [S/2*C*2] | cond [S*Cc*4 -> 128]
@@ -442,6 +418,137 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_stream_kernel(GnBwdArgs a
     }
 }
 
+// Same sums with every stride a compile-time constant (C, cond channels, which gradients come in): the generic kernel above
+// spends ~250 warp instructions per (row, 4 channels) of which ~85 are arithmetic and is ISSUE-bound at 61 % issue utilisation,
+// 2.8 TB/s (profiles/r01j_ncu_gn_bwd_stats.md).  Here a full stage is 4 rows per thread at immediate offsets.
+template <int C, int CC, bool POOL>
+__global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
+    constexpr int S = SG_STAGE_BYTES / (C * 2);                       // rows per stage
+    constexpr int NQ = C / 4, NTR = 256 / NQ, RPT = S / NTR;          // channel quads, row lanes, rows per thread and stage
+    constexpr int NV = 4 + CC;
+    constexpr uint32_t OFF_DO = SG_STAGE_BYTES, OFF_POOL = 2 * SG_STAGE_BYTES;
+    constexpr uint32_t OFF_COND = OFF_POOL + (POOL ? SG_STAGE_BYTES / 2 : 0);
+    static_assert(RPT * NTR == S && NTR % 2 == 0, "stage geometry");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int b = blockIdx.y, L = a.L;
+    SgBwdStream ps;
+    ps.a = &a; ps.b = b; ps.r0 = blockIdx.x * a.rows_per_cta; ps.rows_here = min(a.rows_per_cta, L - ps.r0); ps.S = S;
+    ps.depth = depth; ps.lay = sg_bwd_layout(C, CC, true, POOL); ps.base = smem;
+    ps.bars = reinterpret_cast<uint64_t*>(smem + (size_t)depth * ps.lay.stage);
+    const uint32_t stage_bytes = ps.lay.stage;
+    const int n_sub = (ps.rows_here + S - 1) / S;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < depth; ++s) mbar_init(smem_u32(ps.bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < depth && i < n_sub; ++i) ps.issue(i, true);
+    }
+    const int quad = threadIdx.x % NQ, tr = threadIdx.x / NQ;
+    f32x2 hA[2], hB[2], G[2], rs2, xo2;
+    {
+        constexpr int cg = C / 8;
+        const int g = (quad * 4) / cg;
+        const float mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+        const float rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+        rs2 = pkf2(rstd, rstd);
+        xo2 = pkf2(-mean * rstd, -mean * rstd);
+        const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+        float a_[4], b_[4], g_[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            const float aa = rstd * a.gn_w[c];
+            a_[i] = 0.5f * aa;
+            b_[i] = 0.5f * (a.gn_b[c] - mean * aa);
+            g_[i] = 1.0f + fr[c];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+            hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+            G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+        }
+    }
+    f32x2 acc[2][NV];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[h][v] = 0ull;
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    // one (row, channel quad): x, incoming gradient, cond values -> the 4 + CC running sums
+    auto row = [&](uint2 xr, uint2 dr, uint2 pl, const float* cdr) {
+        float cv[CC > 0 ? CC : 1];
+#pragma unroll
+        for (int j = 0; j < CC; ++j) cv[j] = cdr[j];
+        const uint32_t xw[2] = {xr.x, xr.y}, dw[2] = {dr.x, dr.y}, pw[2] = {pl.x, pl.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            f32x2 dv = bf2_lo(dw[h]);
+            if (POOL) dv = ffma2(bf2_lo(pw[h]), half2, dv);
+            const f32x2 x = bf2_lo(xw[h]);
+            f32x2 z, act, dact;
+            sg_silu_pair(x, hA[h], hB[h], z, act, dact);
+            const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
+            const f32x2 xh = ffma2(x, rs2, xo2);
+            acc[h][0] = fadd2(acc[h][0], dv);
+            acc[h][1] = ffma2(dv, act, acc[h][1]);
+            acc[h][2] = fadd2(acc[h][2], dn);
+            acc[h][3] = ffma2(dn, xh, acc[h][3]);
+#pragma unroll
+            for (int j = 0; j < CC; ++j) acc[h][4 + j] = ffma2(dv, pkf2(cv[j], cv[j]), acc[h][4 + j]);
+        }
+    };
+    const uint32_t t_off = (uint32_t)(tr * C + quad * 4) * 2;          // my quad in row tr of a stage
+    const uint32_t p_off = OFF_POOL + (uint32_t)((tr >> 1) * C + quad * 4) * 2;
+    __syncthreads();
+    for (int i = 0; i < n_sub; ++i) {
+        const int st = i % depth;
+        const int rows_i = min(S, ps.rows_here - i * S);
+        mbar_wait(smem_u32(ps.bars + st), (uint32_t)((i / depth) & 1));
+        const uint8_t* sb = smem + (size_t)st * stage_bytes;
+        const float* cd = reinterpret_cast<const float*>(sb + OFF_COND) + tr * CC;
+        if (rows_i == S) {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const uint2 xr = *reinterpret_cast<const uint2*>(sb + t_off + k * NTR * C * 2);
+                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + t_off + k * NTR * C * 2);
+                uint2 pl = make_uint2(0u, 0u);
+                if (POOL) pl = *reinterpret_cast<const uint2*>(sb + p_off + k * (NTR / 2) * C * 2);
+                row(xr, dr, pl, cd + k * NTR * CC);
+            }
+        } else {
+            for (int r = tr; r < rows_i; r += NTR) {
+                const uint2 xr = *reinterpret_cast<const uint2*>(sb + ((size_t)r * C + quad * 4) * 2);
+                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + ((size_t)r * C + quad * 4) * 2);
+                uint2 pl = make_uint2(0u, 0u);
+                if (POOL) pl = *reinterpret_cast<const uint2*>(sb + OFF_POOL + ((size_t)(r >> 1) * C + quad * 4) * 2);
+                row(xr, dr, pl, reinterpret_cast<const float*>(sb + OFF_COND) + r * CC);
+            }
+        }
+        __syncthreads();                                              // every thread is done with stage st
+        if (threadIdx.x == 0 && i + depth < n_sub) ps.issue(i + depth, true);
+    }
+    // reduce the thread rows through shared memory (the stage ring is free now)
+    float* red = reinterpret_cast<float*>(smem);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float lo, hi;
+            upk2(acc[h][v], lo, hi);
+            red[((size_t)tr * C + quad * 4 + 2 * h) * NV + v] = lo;
+            red[((size_t)tr * C + quad * 4 + 2 * h + 1) * NV + v] = hi;
+        }
+    __syncthreads();
+    float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * NV;
+    for (int i = threadIdx.x; i < C * NV; i += 256) {
+        float sacc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < NTR; ++t) sacc += red[(size_t)t * C * NV + i];
+        pt[i] = sacc;
+    }
+}
+
 template <bool HEAD>
 __global__ void __launch_bounds__(256, 3) gn_bwd_apply_stream_kernel(GnBwdArgs a, const float* __restrict__ gstat,
                                                                   bf16* __restrict__ d_raw, float* __restrict__ partial_bias,
@@ -590,6 +697,27 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     if (smem < red_bytes) smem = red_bytes;
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
     const bool head = a.do_eps != nullptr;
+    if (g_gn_bwd_stats_fast && !head && a.do_a != nullptr && (Cc == 1 || Cc == 5)) {
+        const bool pool = a.do_pool != nullptr;
+#define SGF_GO(CV, CCV, PL)                                                                                                 \
+    do {                                                                                                                    \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<CV, CCV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<CV, CCV, PL>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
+        gn_bwd_stats_fast_kernel<CV, CCV, PL><<<grid, 256, smem, st>>>(a, partial, depth);                                   \
+    } while (0)
+#define SGF_C(CCV, PL)                        \
+    do {                                      \
+        if (C == 64) SGF_GO(64, CCV, PL);     \
+        else if (C == 128) SGF_GO(128, CCV, PL); \
+        else SGF_GO(256, CCV, PL);            \
+    } while (0)
+        if (Cc == 1) { if (pool) SGF_C(1, true); else SGF_C(1, false); }
+        else { if (pool) SGF_C(5, true); else SGF_C(5, false); }
+#undef SGF_C
+#undef SGF_GO
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
 #define SGS_GO(CCV, HD)                                                                                                     \
     do {                                                                                                                    \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_stream_kernel<CCV, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -64,6 +64,8 @@ class _GradWorkspace:
         self.dfilm = torch.zeros(B, spec.film_dim, device=device, dtype=torch.float32)
         self.aux = torch.empty(B, spec.time_dim + 3 * spec.base_ch, device=device, dtype=torch.float32)
         self.film = torch.empty(B, spec.film_dim, device=device, dtype=torch.float32)
+        # exchange buffer of the one-pass GroupNorm backward (gn_bwd_fused.cu): zeroed once, epochs advance per launch
+        self.sync = torch.zeros(lib.gw_gn_bwd_sync_bytes(B), device=device, dtype=torch.uint8)
 
 
 class BackwardEngine:
@@ -83,6 +85,8 @@ class BackwardEngine:
         self.wgrad_impl = "tc" if eng.conv_impl == "tc" else "simt"
         self.wgrad_variant = 0
         self.fuse_head = False
+        # bf16: one-pass GroupNorm backward (gn_bwd_fused.cu) wherever a sample fits the shared memory of <= 32 CTAs
+        self.fuse_gn_bwd = True
 
     def grad_workspace(self, ws: _Workspace) -> _GradWorkspace:
         key = (ws.B, ws.L)
@@ -198,7 +202,7 @@ class BackwardEngine:
             n = names[li]
             lvl = li if li <= d else 2 * d - li
             _, Ll, Cl = ws.raw[li].shape
-            check(lib.gw_gn_bwd(ptr(ws.raw[li]), ptr(ws.stats[li]), B, Ll, Cl, ptr(eng.p[n + ".1.weight"]),
+            check(lib.gw_gn_bwd2(ptr(ws.raw[li]), ptr(ws.stats[li]), B, Ll, Cl, ptr(eng.p[n + ".1.weight"]),
                                 ptr(eng.p[n + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
                                 ptr(eng.p[cnames[li] + ".weight"]) if Cc > 0 else None,
                                 ptr(eng.p[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(g.film), foffs[li], sp.film_dim,
@@ -206,7 +210,8 @@ class BackwardEngine:
                                 ptr(g.scratch), ptr(g.dfilm), sp.film_dim, ptr(g.d_raw),
                                 ptr(grads[n + ".1.weight"]), ptr(grads[n + ".1.bias"]),
                                 ptr(grads[cnames[li] + ".weight"]) if Cc > 0 else None,
-                                ptr(grads[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(grads[n + ".0.bias"]), st),
+                                ptr(grads[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(grads[n + ".0.bias"]),
+                                ptr(g.sync) if self.fuse_gn_bwd else None, st),
                   f"gn_bwd[{n}]")
             eng.launches += 5
 

@@ -217,6 +217,17 @@ int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const fl
               long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
               int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
               float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* stream);
+/* gw_gn_bwd2 = gw_gn_bwd + `sync` (gw_gn_bwd_sync_bytes(B) bytes, zeroed ONCE by the caller, kept across launches on one
+ * stream; may be the gw_conv_gn buffer).  With a non-NULL sync, bf16 layers whose sample fits the shared memory of <= 32 CTAs
+ * (gw_gn_bwd_fused_group(L, C, Cc, has_do, has_pool) > 0) run the ONE-PASS kernel (gn_bwd_fused.cu): operands are read once, the
+ * CTAs of a sample exchange the GroupNorm group sums through `sync`, d_raw is formed out of shared memory.  Same outputs. */
+long gw_gn_bwd_sync_bytes(int B);
+int gw_gn_bwd_fused_group(int L, int C, int Cc, int has_do, int has_pool);
+int gw_gn_bwd2(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
+               const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+               long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
+               int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+               float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* sync, void* stream);
 
 /* exact-mode conv backward.  gw_weight_dgrad: wt[ci][co][k] = w[co][ci][2-k], so that dgrad = gw_conv3_simt(d_raw, wt).
  * gw_split_cat_grad: gradient of cat[nearest-upsample x2 (h), skip]: d_h [B, L0, C0] (pair sums), d_skip [B, L, C1].

@@ -44,3 +44,52 @@ def test_tc_backward_matches_simt(in_ch, cc, B, L):
         for k in ref:
             err = float((got[k].double() - ref[k].double()).norm())
             assert err <= 1e-2 * max(float(ref[k].norm()), 1e-2 * tot), (what, k, err, float(ref[k].norm()))
+
+
+def _run_gn(in_ch, cc, B, L, fused, slice_bytes=None):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import _cabi
+    lib = _cabi.load()
+    if slice_bytes is not None:
+        assert lib.gw_set_option(b"gn_bwd_fused_slice", slice_bytes) == 0
+    try:
+        from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
+        from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import FusedTrainStep
+        sd = make_state_dict(in_ch, cc, seed=4)
+        m = UNet1D(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True, compute_dtype="bf16")
+        m.load_state_dict(sd)
+        m = m.cuda()
+        st = FusedTrainStep(m, CustomDiffusion(T=1000, device="cuda"), B, L, compute_dtype="bf16", seed=5)
+        st.bwd.fuse_gn_bwd = fused
+        d = synthetic_chirps(B, L, seed=9)
+        cond = d["y_norm"] if cc == 1 else torch.cat([d["y_norm"], 0.2 * gaussian((B, 4, 1), 3).expand(B, 4, L)], 1)
+        st.load_batch(d["clean_norm"].cuda(), cond.contiguous().cuda(), None)
+        st.step(use_graph=False)
+        st.step(use_graph=False)           # second launch: the exchange epochs advance, no reset of the sync buffer
+        torch.cuda.synchronize()
+        return {k: v.clone() for k, v in st.layout.views(st.flat_g).items()}, float(st.loss)
+    finally:
+        if slice_bytes is not None:
+            lib.gw_set_option(b"gn_bwd_fused_slice", 45056)
+
+
+@pytest.mark.parametrize("in_ch,cc,B,L,slice_bytes", [(7, 5, 2, 4096, None), (3, 1, 3, 1024, None), (3, 1, 5, 192, None),
+                                                       (7, 5, 48, 512, 12000)])
+def test_one_pass_gn_backward_matches_two_pass(in_ch, cc, B, L, slice_bytes):
+    """gn_bwd_fused.cu (operands read once, group sums exchanged between the CTAs of a sample) against the two-pass streaming
+    kernels: same math, different summation order of the fp32 sums -> per-tensor rel-L2 <= 5e-3.  The last case forces 16 CTAs
+    per sample and more samples than CTA groups (every group loops over several samples)."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import _cabi
+    lib = _cabi.load()
+    if slice_bytes is not None:
+        lib.gw_set_option(b"gn_bwd_fused_slice", slice_bytes)
+    g0 = lib.gw_gn_bwd_fused_group(L, 64, cc, 1, 1)
+    if slice_bytes is not None:
+        lib.gw_set_option(b"gn_bwd_fused_slice", 45056)
+    assert g0 > 0, "the first block must take the one-pass kernel in this test"
+    ref, loss_ref = _run_gn(in_ch, cc, B, L, False)
+    got, loss_got = _run_gn(in_ch, cc, B, L, True, slice_bytes)
+    assert abs(loss_ref - loss_got) <= 1e-4 * abs(loss_ref)
+    tot = float(torch.cat([v.reshape(-1) for v in ref.values()]).norm())
+    for k in ref:
+        err = float((got[k].double() - ref[k].double()).norm())
+        assert err <= 5e-3 * max(float(ref[k].norm()), 1e-2 * tot), (k, err, float(ref[k].norm()))

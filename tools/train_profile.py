@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--wgrad-variant", type=int, default=-1)
+    ap.add_argument("--fuse-gn-bwd", type=int, default=-1, help="1/0: one-pass GroupNorm backward on/off (default: library default)")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for gw_set_option (repeatable)")
+    ap.add_argument("--only", default=None, help="print only launches whose name contains this")
     a = ap.parse_args()
     cc = 1 if a.cin == 3 else 5
     model = UNet1D(in_ch=a.cin, cond_in_ch=cc, use_selfcond=True, compute_dtype=a.dtype)
@@ -44,6 +47,11 @@ def main():
         cond = torch.cat([cond, torch.zeros(a.B, 4, a.L)], 1)
     if a.wgrad_variant >= 0:
         st.bwd.wgrad_variant = a.wgrad_variant
+    if a.fuse_gn_bwd >= 0:
+        st.bwd.fuse_gn_bwd = bool(a.fuse_gn_bwd)
+    for o in a.opt:
+        k, v = o.split("=")
+        assert st.lib.gw_set_option(k.encode(), int(v)) == 0, o
     st.load_batch(d["clean_norm"].cuda(), cond.cuda(), None)
     for _ in range(2):
         st.step(selfcond=bool(a.selfcond), use_graph=False)
@@ -66,7 +74,8 @@ def main():
         tot += m
         out.append({"launch": k, "us": m})
         by_name[k.split(" ", 1)[1]] = by_name.get(k.split(" ", 1)[1], 0.0) + m
-        print(f"{k:28s} {m:9.1f} us")
+        if a.only is None or a.only in k:
+            print(f"{k:28s} {m:9.1f} us")
     print("--- by entry point")
     for k, v in by_name.items():
         print(f"{k:28s} {v:9.1f} us  {100 * v / tot:5.1f} %")

@@ -52,6 +52,8 @@ _SIGS = {
     "gw_conv_gn_sync_bytes": ([_I], _L),
     "gw_conv_gn": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P,
                     _P], _I),
+    "gw_conv_gn2": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P,
+                     _P, _P, _P], _I),
 }
 # training step: backward.cu / optim.cu
 _SIGS.update({

@@ -45,6 +45,7 @@ typedef __nv_bfloat16 bf16;
 // dtype codes of the C-ABI
 #define GW_F32 0
 #define GW_BF16 1
+#define GW_DOTS 2     // gw_final_step only: h = head dot products [Bn, L, 4] fp32 (gw_conv_gn2)
 
 static inline int gw_cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -146,6 +147,31 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+// Sum V per-lane values over the 32 lanes with recursive halving (V-1 + 5-log2(V) shuffles instead of 5V): afterwards the
+// total of value j sits in every lane whose top log2(V) lane bits equal j.
+template <int V>
+__device__ __forceinline__ float warp_reduce_multi(float (&v)[V], int lane) {
+    static_assert(V == 4 || V == 8 || V == 16, "V");
+    int n = V;
+#pragma unroll
+    for (int m = 16; n > 1; m >>= 1) {
+        n >>= 1;
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+            if (i < n) {
+                const float send = up ? v[i] : v[i + n];
+                const float keep = up ? v[i + n] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+    }
+    float t = v[0];
+    constexpr int REST = V == 16 ? 1 : (V == 8 ? 2 : 4);      // lane bits not consumed by the halving
+#pragma unroll
+    for (int m = REST; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    return t;
 }
 
 // Philox4x32-10 counter RNG + Box-Muller; key = seed, counter = (sample, step, chunk, 0).

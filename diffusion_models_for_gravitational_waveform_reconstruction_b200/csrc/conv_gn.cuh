@@ -40,6 +40,9 @@ struct GnFuseArgs {
     unsigned int* ctrl;       // [0] epoch of the previous launch, [1] CTAs finished
     long film_b_stride, film_step_stride;
     int film_off, Cc, G, n_groups, B, Lpos, write_raw, pair;
+    const float* head_w;      // HEAD kernels: final.weight [C+1, 3] (models.py:230), else NULL
+    float* head_dots;         // HEAD kernels: [B, Lpos, 4] fp32: (sum_c out[l,c] w[c,0], .. w[c,1], .. w[c,2], 0)
+    int store_out;            // 0: the activated tensor itself is not needed (only the head dots leave the kernel)
     int dbg_mode;             // tools only (-DCGN_ABLATE builds): 1 no tanh, 2 no pack, 4 no stmatrix, 8 no TMA stores, 16 no pooling, 32 no TMEM load
     long long* dbg;           // tools only: [CTA][16 samples][8] clock64 stamps of CTA phases (NULL in production)
 };
@@ -63,10 +66,13 @@ static __device__ __noinline__ void xchg_timeout(int b, int src) {
 //   ab[pair] = {A.x, A.y, B.x, B.y}: h = A*acc + B is HALF the GroupNorm output (conv bias folded in), silu = h + h*tanh(h)
 //   ge[pair] = {G.x, G.y, E.x, E.y}: out = silu*G + E + sum_j W_j * cond_j,  G = 1+gamma_t, E = bc*G + beta_t, W_j = wc_j*G
 //   cd[m][j]: cond channel j at this thread's row of row-group m;  kb: which 16 columns of the chunk
-template <int NCA, bool HAS_COND, bool POOL>
+//   HEAD: hw[pair][tap] = head-conv weights of the column pair; hd[m][tap] += out * w (summed over the chunk's 64 channels by the
+//   caller); st_out = 0 skips the staging of the activated tile
+template <int NCA, bool HAS_COND, bool POOL, bool HEAD = false>
 __device__ __forceinline__ void gn_cols16(uint32_t taddr, int kb, const ulonglong2* __restrict__ ab, const ulonglong2* __restrict__ ge,
                                           const unsigned long long* __restrict__ w, const float (&cd)[4][NCA], uint32_t stg,
-                                          uint32_t stgp, int lane, int dm = 0) {
+                                          uint32_t stgp, int lane, int dm = 0, const unsigned long long* __restrict__ hw = nullptr,
+                                          unsigned long long (*hd)[3] = nullptr, bool st_out = true) {
     const unsigned long long half2 = pkf2(0.5f, 0.5f);
     const int tq = lane & 3, tr = lane >> 2;
     // coefficient loads first: the TMEM load below is an asm volatile with a memory clobber, nothing moves across it, and the
@@ -101,6 +107,11 @@ __device__ __forceinline__ void gn_cols16(uint32_t taddr, int kb, const ulonglon
         for (int jj = 0; jj < NCA; ++jj) wv[jj] = HAS_COND ? wv2[kk][jj] : 0ull;
         unsigned long long o[4];
         uint32_t r[4];
+        unsigned long long hwk[3] = {0ull, 0ull, 0ull};
+        if (HEAD) {
+            const int pi = 4 * k + tq;
+            hwk[0] = hw[pi * 3 + 0]; hwk[1] = hw[pi * 3 + 1]; hwk[2] = hw[pi * 3 + 2];
+        }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int i0 = 8 * (m >> 1) + 4 * kk + 2 * (m & 1);
@@ -119,6 +130,10 @@ __device__ __forceinline__ void gn_cols16(uint32_t taddr, int kb, const ulonglon
 #pragma unroll
                 for (int jj = 0; jj < NCA; ++jj) o[m] = ffma2(wv[jj], pkf2(cd[m][jj], cd[m][jj]), o[m]);
             }
+            if (HEAD) {
+#pragma unroll
+                for (int tp = 0; tp < 3; ++tp) hd[m][tp] = ffma2(o[m], hwk[tp], hd[m][tp]);
+            }
             float lo, hi;
             upk2(o[m], lo, hi);
 #ifdef CGN_ABLATE
@@ -129,6 +144,7 @@ __device__ __forceinline__ void gn_cols16(uint32_t taddr, int kb, const ulonglon
 #ifdef CGN_ABLATE
         if (!(dm & 4))
 #endif
+        if (!HEAD || st_out)
         stmatrix_x4(stg + (uint32_t)lane * 128 + (uint32_t)((k ^ (lane & 7)) * 16), r[0], r[1], r[2], r[3]);
 #ifdef CGN_ABLATE
         if (dm & 16) continue;
@@ -213,7 +229,10 @@ __device__ __forceinline__ void stat_reduce(float (&sv)[2 * (64 >> CG_LOG2)], fl
 
 // CG_LOG2 = log2(channels per group) (3, 4, 5 <=> C = 64, 128, 256); MT = row tiles per CTA (MT * bn = 256 TMEM columns);
 // CC = cond channels (1, 5, or -1: any Cc in [0, 8] with zero-padded weights); POOL: also write avg_pool1d(out, 2).
-template <int CG_LOG2, int MT, int CC, bool POOL>
+// HEAD (Cout = 64 decoder in pair space only): the head conv final(cat[h, x_t]) reads nothing but three dot products per position
+// of this block's output, so the epilogue forms them from the fp32 values it already holds (gw_final_step then runs on 16 B per
+// position instead of streaming the 128 B row back in).
+template <int CG_LOG2, int MT, int CC, bool POOL, bool HEAD = false>
 __global__ void __launch_bounds__(CGN_THREADS, 1)
 conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out,
@@ -237,6 +256,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     // per epilogue warpgroup: s_stat [8 warps][8 groups][2] | s_x [G][16] | s_abf, s_gef [128 column pairs][4] | s_wf [128][NCA][2]
     constexpr int GRP_FLOATS = 256 + CGN_MAX_G * 16 + 512 + 512 + 256 * NCA;
     float* s_grp0 = s_bias + 256;
+    unsigned long long* s_hw = reinterpret_cast<unsigned long long*>(s_grp0 + CGN_EPI_GROUPS * GRP_FLOATS);   // HEAD: [32 pairs][3 taps]
     auto a_full = [&](int i) { return smem_u32(bars + i); };
     auto a_empty = [&](int i) { return smem_u32(bars + SA + i); };
     auto b_full = [&](int i) { return smem_u32(bars + 2 * SA + i); };
@@ -267,6 +287,12 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
     for (int i = threadIdx.x; i < P.bn; i += blockDim.x) s_bias[i] = bias ? bias[(n_tile * P.bn + i) & (P.cout - 1)] : 0.0f;
+    if (HEAD) {
+        for (int i = threadIdx.x; i < 32 * 3; i += blockDim.x) {
+            const int pi = i / 3, tp = i % 3;
+            s_hw[i] = pkf2(F.head_w[(2 * pi) * 3 + tp], F.head_w[(2 * pi + 1) * 3 + tp]);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -518,12 +544,53 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 const ulonglong2* ab = reinterpret_cast<const ulonglong2*>(s_abf) + (c0 >> 1);
                 const ulonglong2* ge = reinterpret_cast<const ulonglong2*>(s_gef) + (c0 >> 1);
                 const unsigned long long* wv = reinterpret_cast<const unsigned long long*>(s_wf) + (c0 >> 1) * NCA;
+                unsigned long long hd[4][3];
+                if (HEAD) {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) hd[m][0] = hd[m][1] = hd[m][2] = 0ull;
+                }
+                const bool st_out = !HEAD || F.store_out != 0;
                 if (Cc > 0) {
 #pragma unroll 1
-                    for (int kb = 0; kb < 4; ++kb) gn_cols16<NCA, true, POOL>(acc, kb, ab, ge, wv, cd, stg, stgp, lane, F.dbg_mode);
+                    for (int kb = 0; kb < 4; ++kb)
+                        gn_cols16<NCA, true, POOL, HEAD>(acc, kb, ab, ge, wv, cd, stg, stgp, lane, F.dbg_mode, s_hw, hd, st_out);
                 } else {
 #pragma unroll 1
-                    for (int kb = 0; kb < 4; ++kb) gn_cols16<NCA, false, POOL>(acc, kb, ab, ge, wv, cd, stg, stgp, lane, F.dbg_mode);
+                    for (int kb = 0; kb < 4; ++kb)
+                        gn_cols16<NCA, false, POOL, HEAD>(acc, kb, ab, ge, wv, cd, stg, stgp, lane, F.dbg_mode, s_hw, hd, st_out);
+                }
+                if (HEAD) {
+                    // fold the channel pair, then the 4 lanes that share a row; lane (tr, tq) writes row-group m = tq
+                    const int tq = lane & 3, trow = lane >> 2;
+                    float dsel[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+#pragma unroll
+                        for (int tp = 0; tp < 3; ++tp) {
+                            float lo, hi;
+                            upk2(hd[m][tp], lo, hi);
+                            float v = lo + hi;
+                            v += __shfl_xor_sync(0xffffffffu, v, 1);
+                            v += __shfl_xor_sync(0xffffffffu, v, 2);
+                            if (tq == m) dsel[tp] = v;
+                        }
+                    }
+                    const int row = row_base + trow + 8 * tq;
+                    if (row < P.rows) {
+                        const int pos = F.pair ? 2 * row + my_par : row;
+                        *reinterpret_cast<float4*>(F.head_dots + ((size_t)b * F.Lpos + pos) * 4) =
+                            make_float4(dsel[0], dsel[1], dsel[2], 0.0f);
+                    }
+                    if (!st_out) {
+                        if (!ONE && MT == 2 && kc == 0) {
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+#pragma unroll
+                                for (int jj = 0; jj < NCA; ++jj) cd[m][jj] = cdn[m][jj];
+                            }
+                        }
+                        continue;
+                    }
                 }
                 fence_proxy_async();
                 __syncwarp();
@@ -606,7 +673,7 @@ static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
     pl->n_groups = sms / pl->G;
     if (pl->n_groups > s->B) pl->n_groups = s->B;
     const int nca = (Cc == 1 || Cc == 5) ? Cc : CGN_NCA_MAX;
-    const int misc = 256 + 1024 + CGN_EPI_GROUPS * (1024 + CGN_MAX_G * 64 + 2048 + 2048 + 1024 * nca) + 64;
+    const int misc = 256 + 1024 + CGN_EPI_GROUPS * (1024 + CGN_MAX_G * 64 + 2048 + 2048 + 1024 * nca) + 64 + (pl->lg == 3 ? 768 : 0);
     // ring / staging depths: prefer deep rings, shrink until the CTA fits
     const int ew = 8 * CGN_EPI_GROUPS;
     const int cand[6][3] = {{2, 4, 2}, {2, 3, 2}, {2, 4, 1}, {2, 3, 1}, {2, 2, 1}, {1, 2, 1}};
@@ -636,17 +703,23 @@ extern "C" void gw_conv_gn_debug(void* buf) { g_cgn_dbg = (long long*)buf; }
 extern "C" void gw_conv_gn_debug_mode(int m) { g_cgn_dbg_mode = m; }     // tools/cgn_timeline.py
 extern "C" long gw_conv_gn_sync_bytes(int B) { return 64 + (long)B * CGN_MAX_G * 16 * 8; }
 
-extern "C" int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
-                          const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
-                          const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
-                          void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, void* stream) {
+// gw_conv_gn2 = gw_conv_gn + the head conv's dot products (last decoder, Cout = 64 in pair space): head_w = final.weight
+// [C+1, 3], head_dots [B, L, 4] fp32 receive (sum_c out[l,c] w[c,k])_k for gw_final_step(dtype = GW_DOTS); out == NULL then
+// skips the activated tensor altogether.
+extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
+                           const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
+                           const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
+                           void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, const float* head_w,
+                           float* head_dots, void* stream) {
     CgnPlan pl;
     int rc = cgn_plan(s, Cc, pooled != nullptr, &pl);
     if (rc != GW_OK) return rc;
     TcParams& P = pl.P;
-    GW_REQUIRE(src0 != nullptr && packed != nullptr && out != nullptr && sync_buf != nullptr && gn_w != nullptr && gn_b != nullptr &&
-                   film != nullptr,
+    const bool head = head_dots != nullptr;
+    GW_REQUIRE(src0 != nullptr && packed != nullptr && (out != nullptr || head) && sync_buf != nullptr && gn_w != nullptr &&
+                   gn_b != nullptr && film != nullptr,
                "conv_gn: null pointer");
+    GW_REQUIRE(!head || (head_w != nullptr && pl.lg == 3 && pooled == nullptr), "conv_gn: the head dots need Cout = 64 in pair space");
     GW_REQUIRE((s->n_src == 2) == (src1 != nullptr), "conv_gn: src1 / n_src mismatch");
     GW_REQUIRE((cond != nullptr) == (Cc > 0) && (Cc == 0 || (wc != nullptr && bc != nullptr)), "conv_gn: cond/Cc mismatch");
     CUtensorMap ta0, ta1, tw, to, tr, tp;
@@ -657,7 +730,13 @@ extern "C" int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const voi
     } else {
         ta1 = ta0;
     }
-    if ((rc = make_map3(&to, out, oc, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
+    // (out == NULL with head dots: the map is never used; any valid bf16 tensor of the right extent will do -> src1 / src0)
+    const void* out_map = out != nullptr ? out : (raw != nullptr ? raw : nullptr);
+    if (out_map != nullptr) {
+        if ((rc = make_map3(&to, out_map, oc, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
+    } else {
+        to = ta0;
+    }
     tr = to;
     if (raw != nullptr && (rc = make_map3(&tr, raw, oc, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
     tp = to;
@@ -671,6 +750,7 @@ extern "C" int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const voi
     F.film_b_stride = film_b_stride; F.film_step_stride = film_step_stride; F.film_off = film_off;
     F.Cc = Cc; F.G = pl.G; F.n_groups = pl.n_groups; F.B = s->B; F.Lpos = s->L; F.write_raw = raw != nullptr ? 1 : 0;
     F.pair = s->pair == 1 ? 1 : 0;
+    F.head_w = head_w; F.head_dots = head_dots; F.store_out = out != nullptr ? 1 : 0;
     F.dbg = g_cgn_dbg;
     F.dbg_mode = g_cgn_dbg_mode;
     cudaStream_t st = (cudaStream_t)stream;
@@ -687,12 +767,29 @@ extern "C" int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const voi
         else if (Cc == 5) CGN_GO(LG, MTV, 5, PL);\
         else CGN_GO(LG, MTV, -1, PL);            \
     } while (0)
-    if (pl.lg == 3) CGN_CC(3, 2, false);
+#define CGN_GOH(CCV)                                                                                                      \
+    do {                                                                                                                  \
+        GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<3, 2, CCV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        conv_gn_kernel<3, 2, CCV, false, true><<<grid, CGN_THREADS, smem, st>>>(ta0, ta1, tw, to, tr, tp, P, F, bias);     \
+    } while (0)
+    if (pl.lg == 3 && head) {
+        if (Cc == 1) CGN_GOH(1);
+        else if (Cc == 5) CGN_GOH(5);
+        else CGN_GOH(-1);
+    } else if (pl.lg == 3) CGN_CC(3, 2, false);
     else if (pl.lg == 4 && pl.MT == 2) { if (pool) CGN_CC(4, 2, true); else CGN_CC(4, 2, false); }
     else if (pl.lg == 4) CGN_CC(4, 1, false);
     else { if (pool) CGN_CC(5, 1, true); else CGN_CC(5, 1, false); }
+#undef CGN_GOH
 #undef CGN_CC
 #undef CGN_GO
     GW_LAUNCH_CHECK();
     return GW_OK;
+}
+extern "C" int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
+                          const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
+                          const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
+                          void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, void* stream) {
+    return gw_conv_gn2(s, src0, src1, packed, bias, gn_w, gn_b, cond, Cc, wc, bc, film, film_off, film_b_stride, film_step_stride,
+                       step_ptr, out, pooled, raw, stats_out, sync_buf, nullptr, nullptr, stream);
 }

@@ -1,8 +1,10 @@
 // Fused FIRST block for inference (sm_100a): Conv1d(C_in -> 64, k=3) -> GroupNorm(8) -> SiLU -> + cond 1x1 conv -> FiLM ->
 // out [B, L, 64] bf16 and avg_pool1d(out, 2), in one kernel, without the raw conv tensor (models.py:160-173, 188-193, 204-208).
 //
-// K = 3*C_in <= 21 is not a tensor-core shape, so the conv stays on CUDA cores (as in conv_in_kernel, forward.cu); what this
-// kernel removes is the 134 MB raw write + read between gw_conv_in and gw_gn_apply.  Like conv_gn.cuh, a GROUP of G = L/256
+// K = 3*C_in <= 21 is far too small for a tcgen05 tile pipeline, but the conv was the issue-bound part of this kernel on CUDA
+// cores (576-1344 FMAs per row); for C_in <= 8 it now runs as warp-level tf32 MMAs (mma.sync.m16n8k8: a warp owns 16 rows x 64
+// channels, K = 3*C_in padded to 16 / 24, A fragments straight from the staged fp32 input, B fragments from shared memory),
+// fp32 accumulation.  What the kernel removes is the 134 MB raw write + read between gw_conv_in and gw_gn_apply.  Like conv_gn.cuh, a GROUP of G = L/256
 // (L/512 beyond L = 8192) persistent CTAs owns a sample: each CTA computes its rows ONCE into a bf16 slice in shared memory,
 // sums the GroupNorm statistics, and exchanges them with the group through {value, epoch} packets (xchg.cuh).  The exchange
 // latency is hidden by software pipelining: a CTA convolves sample s+1 into the second slice (and fetches the input of s+2
@@ -36,6 +38,23 @@ struct CigArgs {
     int film_off, B, Cx, L, Cc, G, n_groups;
 };
 
+// weight staging: [Cx*3][C] for the CUDA-core conv, or tf32 B fragments [KS][8 n-tiles][32 lanes][2] for the MMA conv
+__host__ __device__ inline int cig_ksteps(int Cx) { return Cx <= 8 ? (3 * Cx + 7) / 8 : 0; }     // 0: CUDA-core conv
+__host__ __device__ inline int cig_ws_floats(int Cx) {
+    const int a = Cx * 3 * CIG_C, b = cig_ksteps(Cx) * 8 * 32 * 2;
+    return a > b ? a : b;
+}
+__device__ __forceinline__ uint32_t cig_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void cig_mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 static __device__ __noinline__ void cig_timeout(int b, int src) {
     printf("gwb200 conv_in_gn kernel: statistics exchange timed out (block %d sample %d source %d)\n", blockIdx.x, b, src);
     __trap();
@@ -50,7 +69,7 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
     bf16* slice = reinterpret_cast<bf16*>(smem);                            // [2][ROWS][64 ch]
     float* xs = reinterpret_cast<float*>(smem + 2 * CIG_ROWS * C * 2);      // [2][Cx][XP]: xs[c][j] = x[c][l00 - 1 + j]
     float* ws = xs + 2 * A.Cx * CIG_XP;                                     // [Cx*3][C], split-octet layout
-    float* bs = ws + A.Cx * 3 * C;                                          // [C]
+    float* bs = ws + cig_ws_floats(A.Cx);                                   // [C]
     float* wst = bs + C;                                                    // [8 warps][8 octets][2]
     float* s_x = wst + 128;                                                 // [G][16]
     const int Cx = A.Cx, L = A.L, Cc = A.Cc, G = A.G;
@@ -66,10 +85,30 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
 
     // weights as [ck][half][octet][4]: the 8 octet lanes of a quarter-warp read 8 consecutive float4 (no bank conflicts)
     auto split = [](int co) { return ((co >> 2) & 1) * (C / 2) + (co >> 3) * 4 + (co & 3); };
-    for (int i = tid; i < Cx * 3 * C; i += 256) {
-        const int co = i % C, ck = i / C;
-        ws[ck * C + split(co)] = A.w[(size_t)co * Cx * 3 + ck];
+    const int KS = cig_ksteps(Cx);                       // > 0: tf32 MMA conv
+    if (KS > 0) {
+        // B fragment of (k-step ks, n-tile nt) for lane (g = lane>>2, t = lane&3): W[kk = 8 ks + t (+4)][co = 8 nt + g]
+        for (int i = tid; i < KS * 8 * 32 * 2; i += 256) {
+            const int j = i & 1, ln = (i >> 1) & 31, nt = (i >> 6) & 7, ks = i >> 9;
+            const int kk = ks * 8 + (ln & 3) + 4 * j, co = nt * 8 + (ln >> 2);
+            const float v = kk < 3 * Cx ? A.w[(size_t)co * Cx * 3 + kk] : 0.0f;
+            ws[i] = __uint_as_float(cig_tf32(v));
+        }
+    } else {
+        for (int i = tid; i < Cx * 3 * C; i += 256) {
+            const int co = i % C, ck = i / C;
+            ws[ck * C + split(co)] = A.w[(size_t)co * Cx * 3 + ck];
+        }
     }
+    // A fragment columns of this lane: kk = 8 ks + t (+4) -> (input channel, tap) -> offset into the staged input
+    int aoff[3][2];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int kk = ks * 8 + (lane & 3) + 4 * j;
+            aoff[ks][j] = kk < 3 * Cx ? (kk / 3) * CIG_XP + kk % 3 : -1;
+        }
     for (int i = tid; i < C; i += 256) bs[i] = A.bias[i];
     // apply phase: this thread always owns channels 8*ao .. 8*ao+7 (one GroupNorm group) of row pairs (tid>>3) + 32*jj
     const int ao = tid & 7;
@@ -102,61 +141,122 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
                     if (tid + k * 256 < Cx * CIG_XP) xsb[tid + k * 256] = pf[k];
             }
             __syncthreads();
-            float s1 = 0.0f, s2 = 0.0f;
+            if (KS > 0) {
+                // ---- tf32 MMA conv: warp = 16 rows x 64 channels per tile; n-tile nt = GroupNorm group nt ----
+                const int g = lane >> 2, t4 = lane & 3;
+                float s1v[8], s2v[8];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) s1v[nt] = s2v[nt] = 0.0f;
+                const float2* wsf = reinterpret_cast<const float2*>(ws);
+                uint32_t* sl32 = reinterpret_cast<uint32_t*>(sl);
 #pragma unroll 1
-            for (int blk = 0; blk < CIG_ROWS / 128; ++blk) {
-                const int r0 = blk * 128 + pg * 4;               // first of my 4 rows inside the CTA's slice
-                if (l00 + blk * 128 >= L) break;
-                float acc[4][8];
+                for (int rt = warp; rt < CIG_ROWS / 16; rt += 8) {
+                    const int rbase = rt * 16;
+                    if (l00 + rbase >= L) break;
+                    float acc[8][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[u][j] = bs[oct * 8 + j];
-                for (int ci = 0; ci < Cx; ++ci) {
-                    const float* xr = xsb + ci * CIG_XP + r0;
-                    const float4 xa4 = *reinterpret_cast<const float4*>(xr);
-                    const float2 xb2 = *reinterpret_cast<const float2*>(xr + 4);
-                    const float xv[6] = {xa4.x, xa4.y, xa4.z, xa4.w, xb2.x, xb2.y};
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const float* wp = ws + (ci * 3 + k) * C + oct * 4;
-                        const float4 wa = *reinterpret_cast<const float4*>(wp);
-                        const float4 wb = *reinterpret_cast<const float4*>(wp + C / 2);
-                        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(xv[u + k], wv[j], acc[u][j]);
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const float2 b2 = *reinterpret_cast<const float2*>(bs + nt * 8 + 2 * t4);
+                        acc[nt][0] = b2.x; acc[nt][1] = b2.y; acc[nt][2] = b2.x; acc[nt][3] = b2.y;
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    uint4 pk;
-                    pk.x = pack_bf16x2(acc[u][0], acc[u][1]);
-                    pk.y = pack_bf16x2(acc[u][2], acc[u][3]);
-                    pk.z = pack_bf16x2(acc[u][4], acc[u][5]);
-                    pk.w = pack_bf16x2(acc[u][6], acc[u][7]);
-                    *reinterpret_cast<uint4*>(sl + (size_t)(r0 + u) * C + oct * 8) = pk;
-                    if (l00 + r0 + u < L) {
-                        const uint32_t wds[4] = {pk.x, pk.y, pk.z, pk.w};
+                    for (int ks = 0; ks < 3; ++ks) {
+                        if (ks < KS) {
+                            uint32_t af[4];
+                            const float* x0 = xsb + rbase + g;
+                            af[0] = aoff[ks][0] >= 0 ? cig_tf32(x0[aoff[ks][0]]) : 0u;
+                            af[1] = aoff[ks][0] >= 0 ? cig_tf32(x0[aoff[ks][0] + 8]) : 0u;
+                            af[2] = aoff[ks][1] >= 0 ? cig_tf32(x0[aoff[ks][1]]) : 0u;
+                            af[3] = aoff[ks][1] >= 0 ? cig_tf32(x0[aoff[ks][1] + 8]) : 0u;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {           // statistics of the values as stored (bf16)
-                            const float lo = __uint_as_float(wds[q] << 16), hi = __uint_as_float(wds[q] & 0xffff0000u);
-                            s1 += lo + hi;
-                            s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                            for (int nt = 0; nt < 8; ++nt) {
+                                const float2 bf = wsf[(ks * 8 + nt) * 32 + lane];
+                                cig_mma_tf32(acc[nt], af, __float_as_uint(bf.x), __float_as_uint(bf.y));
+                            }
+                        }
+                    }
+                    // rows rbase + g and rbase + g + 8, channels 8 nt + 2 t4 (+1): bf16 into the swizzled slice, statistics
+                    const bool v0 = l00 + rbase + g < L, v1 = l00 + rbase + g + 8 < L;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const uint32_t w0 = pack_bf16x2(acc[nt][0], acc[nt][1]), w1 = pack_bf16x2(acc[nt][2], acc[nt][3]);
+                        const int col = ((nt ^ g) * 8 + 2 * t4) >> 1;
+                        sl32[(size_t)(rbase + g) * (C / 2) + col] = w0;
+                        sl32[(size_t)(rbase + g + 8) * (C / 2) + col] = w1;
+                        if (v0) {
+                            const float lo = __uint_as_float(w0 << 16), hi = __uint_as_float(w0 & 0xffff0000u);
+                            s1v[nt] += lo + hi;
+                            s2v[nt] = fmaf(lo, lo, fmaf(hi, hi, s2v[nt]));
+                        }
+                        if (v1) {
+                            const float lo = __uint_as_float(w1 << 16), hi = __uint_as_float(w1 & 0xffff0000u);
+                            s1v[nt] += lo + hi;
+                            s2v[nt] = fmaf(lo, lo, fmaf(hi, hi, s2v[nt]));
                         }
                     }
                 }
-            }
-            // fold the 4 position groups of the warp that share an octet (lanes differing in bits 3, 4), then the 8 warps
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-            if (lane < 8) {
-                wst[(warp * 8 + oct) * 2 + 0] = s1;
-                wst[(warp * 8 + oct) * 2 + 1] = s2;
-            }
+                float sv16[16];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) { sv16[nt] = s1v[nt]; sv16[8 + nt] = s2v[nt]; }
+                const float tot = warp_reduce_multi<16>(sv16, lane);      // value j lands in lanes 2j, 2j+1
+                if ((lane & 1) == 0) wst[(warp * 8 + ((lane >> 1) & 7)) * 2 + (lane >> 4)] = tot;
+            } else {
+                float s1 = 0.0f, s2 = 0.0f;
+    #pragma unroll 1
+                for (int blk = 0; blk < CIG_ROWS / 128; ++blk) {
+                    const int r0 = blk * 128 + pg * 4;               // first of my 4 rows inside the CTA's slice
+                    if (l00 + blk * 128 >= L) break;
+                    float acc[4][8];
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u)
+    #pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[u][j] = bs[oct * 8 + j];
+                    for (int ci = 0; ci < Cx; ++ci) {
+                        const float* xr = xsb + ci * CIG_XP + r0;
+                        const float4 xa4 = *reinterpret_cast<const float4*>(xr);
+                        const float2 xb2 = *reinterpret_cast<const float2*>(xr + 4);
+                        const float xv[6] = {xa4.x, xa4.y, xa4.z, xa4.w, xb2.x, xb2.y};
+    #pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float* wp = ws + (ci * 3 + k) * C + oct * 4;
+                            const float4 wa = *reinterpret_cast<const float4*>(wp);
+                            const float4 wb = *reinterpret_cast<const float4*>(wp + C / 2);
+                            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    #pragma unroll
+                            for (int u = 0; u < 4; ++u)
+    #pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(xv[u + k], wv[j], acc[u][j]);
+                        }
+                    }
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(acc[u][0], acc[u][1]);
+                        pk.y = pack_bf16x2(acc[u][2], acc[u][3]);
+                        pk.z = pack_bf16x2(acc[u][4], acc[u][5]);
+                        pk.w = pack_bf16x2(acc[u][6], acc[u][7]);
+                        *reinterpret_cast<uint4*>(sl + (size_t)(r0 + u) * C + ((oct ^ ((r0 + u) & 7)) * 8)) = pk;
+                        if (l00 + r0 + u < L) {
+                            const uint32_t wds[4] = {pk.x, pk.y, pk.z, pk.w};
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q) {           // statistics of the values as stored (bf16)
+                                const float lo = __uint_as_float(wds[q] << 16), hi = __uint_as_float(wds[q] & 0xffff0000u);
+                                s1 += lo + hi;
+                                s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                            }
+                        }
+                    }
+                }
+                // fold the 4 position groups of the warp that share an octet (lanes differing in bits 3, 4), then the 8 warps
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                if (lane < 8) {
+                    wst[(warp * 8 + oct) * 2 + 0] = s1;
+                    wst[(warp * 8 + oct) * 2 + 1] = s2;
+                }
+        }
             __syncthreads();
             if (tid < 16) {
                 float v = 0.0f;
@@ -246,7 +346,7 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int r = 2 * p + h;
-                    const uint4 xr = *reinterpret_cast<const uint4*>(sl + (size_t)r * C + ao * 8);
+                    const uint4 xr = *reinterpret_cast<const uint4*>(sl + (size_t)r * C + ((ao ^ (r & 7)) * 8));
                     const uint32_t wds[4] = {xr.x, xr.y, xr.z, xr.w};
                     float cv[NCA];
 #pragma unroll
@@ -324,7 +424,7 @@ extern "C" int gw_conv_in_gn(const float* x, const float* x_alt, const int* step
     A.film_b_stride = film_b_stride; A.film_step_stride = film_step_stride; A.film_off = film_off;
     A.B = B; A.Cx = Cx; A.L = L; A.Cc = Cc; A.G = G;
     const int rows = L <= 8192 ? 256 : 512;
-    const size_t smem = (size_t)2 * rows * CIG_C * 2 + (size_t)(2 * Cx * (rows + 8) + Cx * 3 * CIG_C + CIG_C + 128 + XCHG_MAX_G * 16) * 4;
+    const size_t smem = (size_t)2 * rows * CIG_C * 2 + (size_t)(2 * Cx * (rows + 8) + cig_ws_floats(Cx) + CIG_C + 128 + XCHG_MAX_G * 16) * 4;
     GW_REQUIRE(smem <= 232448, "gw_conv_in_gn: shared memory %zu too large", smem);
     cudaStream_t st = (cudaStream_t)stream;
     // every CTA of a group spins on its peers: the grid must be co-resident -> size it from the occupancy of this variant

@@ -55,31 +55,6 @@ struct TcParams {
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue
-// Sum V per-lane values over the 32 lanes with recursive halving (V-1 + 5-log2(V) shuffles instead of 5V): afterwards the
-// total of value j sits in every lane whose top log2(V) lane bits equal j.
-template <int V>
-__device__ __forceinline__ float warp_reduce_multi(float (&v)[V], int lane) {
-    static_assert(V == 4 || V == 8 || V == 16, "V");
-    int n = V;
-#pragma unroll
-    for (int m = 16; n > 1; m >>= 1) {
-        n >>= 1;
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < V / 2; ++i) {
-            if (i < n) {
-                const float send = up ? v[i] : v[i + n];
-                const float keep = up ? v[i + n] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-            }
-        }
-    }
-    float t = v[0];
-    constexpr int REST = V == 16 ? 1 : (V == 8 ? 2 : 4);      // lane bits not consumed by the halving
-#pragma unroll
-    for (int m = REST; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-    return t;
-}
 
 // One epilogue unit: 64 accumulator columns of this lane's row -> +bias -> bf16 -> 128-byte-swizzled staging rows, plus
 // (optionally) the GroupNorm partial sums of the fp32 values.  CG_LOG2 = log2(channels per group) in {3, 4, 5}.

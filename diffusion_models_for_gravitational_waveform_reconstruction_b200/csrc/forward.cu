@@ -1100,6 +1100,9 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
     if (x0_out != nullptr) x0_out[(size_t)b * L + l] = x0;
 }
 
+int final_step_dots(const void* dots, const float* net_a, const float* net_b, int B, int Cx, int L, int C, const float* wf,
+                    const float* bf, const gw_step_params* p, const float* coef, const int* step_ptr, const float* noise,
+                    float* eps_out, float* x0_out, cudaStream_t st);
 int final_step_stream(const void* h, const float* net_a, const float* net_b, int B, int Cx, int L, const float* wf, const float* bf,
                       const gw_step_params* p, const float* coef, const int* step_ptr, const float* noise, float* eps_out,
                       float* x0_out, cudaStream_t st);
@@ -1113,7 +1116,9 @@ extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const
     GW_REQUIRE(p->mode == 0 || (coef != nullptr && net_b != nullptr), "gw_final_step: step mode needs coef and net_b");
     GW_REQUIRE(p->mode == 1 || eps_out != nullptr, "gw_final_step: forward mode needs eps_out");
     GW_REQUIRE(!(p->dc_weight > 0.0f) || p->y_dc != nullptr, "gw_final_step: dc_weight needs y_dc");
-    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_final_step: dtype %d", dtype);
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16 || dtype == GW_DOTS, "gw_final_step: dtype %d", dtype);
+    if (dtype == GW_DOTS)                                    // h = the head dots left by gw_conv_gn2 (stream_gn.cu)
+        return final_step_dots(h, net_a, net_b, B, Cx, L, C, wf, bf, p, coef, step_ptr, noise, eps_out, x0_out, (cudaStream_t)stream);
     StepArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
     a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;

@@ -687,6 +687,139 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_stream_kernel(GnBwdArgs a
     }
 }
 
+// apply pass with compile-time strides (see gn_bwd_stats_fast_kernel)
+template <int C, bool POOL>
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, const float* __restrict__ gstat,
+                                                                bf16* __restrict__ d_raw, float* __restrict__ partial_bias,
+                                                                int depth) {
+    constexpr int S = SG_STAGE_BYTES / (C * 2);
+    constexpr int NQ = C / 4, NTR = 256 / NQ, RPT = S / NTR;
+    constexpr uint32_t OFF_DO = SG_STAGE_BYTES, OFF_POOL = 2 * SG_STAGE_BYTES;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int b = blockIdx.y, L = a.L;
+    SgBwdStream ps;
+    ps.a = &a; ps.b = b; ps.r0 = blockIdx.x * a.rows_per_cta; ps.rows_here = min(a.rows_per_cta, L - ps.r0); ps.S = S;
+    ps.depth = depth; ps.lay = sg_bwd_layout(C, 0, true, POOL); ps.base = smem;
+    const uint32_t stage_bytes = ps.lay.stage;
+    uint8_t* s_out = smem + (size_t)depth * stage_bytes;              // [2][8 KB] output staging
+    ps.bars = reinterpret_cast<uint64_t*>(s_out + 2 * SG_STAGE_BYTES);
+    const int n_sub = (ps.rows_here + S - 1) / S;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < depth; ++s) mbar_init(smem_u32(ps.bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < depth && i < n_sub; ++i) ps.issue(i, false);
+    }
+    const int quad = threadIdx.x % NQ, tr = threadIdx.x / NQ;
+    f32x2 hA[2], hB[2], G[2], GW2[2], rs2, xo2, nm1, nm2;
+    {
+        constexpr int cg = C / 8;
+        const int g = (quad * 4) / cg;
+        const float mean = a.stats[((size_t)b * 8 + g) * 2 + 0];
+        const float rstd = a.stats[((size_t)b * 8 + g) * 2 + 1];
+        const float m1 = gstat[((size_t)b * 8 + g) * 2 + 0], m2 = gstat[((size_t)b * 8 + g) * 2 + 1];
+        rs2 = pkf2(rstd, rstd);
+        xo2 = pkf2(-mean * rstd, -mean * rstd);
+        nm1 = pkf2(-m1, -m1);
+        nm2 = pkf2(-m2, -m2);
+        const float* fr = a.film + (size_t)b * a.film_b_stride + a.film_off;
+        float a_[4], b_[4], g_[4], w_[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = quad * 4 + i;
+            w_[i] = a.gn_w[c];
+            const float aa = rstd * w_[i];
+            a_[i] = 0.5f * aa;
+            b_[i] = 0.5f * (a.gn_b[c] - mean * aa);
+            g_[i] = 1.0f + fr[c];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hA[h] = pkf2(a_[2 * h], a_[2 * h + 1]);
+            hB[h] = pkf2(b_[2 * h], b_[2 * h + 1]);
+            G[h] = pkf2(g_[2 * h], g_[2 * h + 1]);
+            GW2[h] = pkf2(w_[2 * h], w_[2 * h + 1]);
+        }
+    }
+    f32x2 sbs[2] = {0ull, 0ull};
+    const f32x2 half2 = pkf2(0.5f, 0.5f);
+    auto row = [&](uint2 xr, uint2 dr, uint2 pl) -> uint2 {
+        const uint32_t xw[2] = {xr.x, xr.y}, dw[2] = {dr.x, dr.y}, pw[2] = {pl.x, pl.y};
+        uint32_t ow[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            f32x2 dv = bf2_lo(dw[h]);
+            if (POOL) dv = ffma2(bf2_lo(pw[h]), half2, dv);
+            const f32x2 x = bf2_lo(xw[h]);
+            f32x2 z, act, dact;
+            sg_silu_pair(x, hA[h], hB[h], z, act, dact);
+            const f32x2 dn = fmul2(fmul2(dv, G[h]), dact);
+            const f32x2 xh = ffma2(x, rs2, xo2);
+            const f32x2 dz = fmul2(ffma2(xh, nm2, ffma2(dn, GW2[h], nm1)), rs2);
+            sbs[h] = fadd2(sbs[h], dz);
+            float lo, hi;
+            upk2(dz, lo, hi);
+            ow[h] = pack_bf16x2(lo, hi);
+        }
+        return make_uint2(ow[0], ow[1]);
+    };
+    const uint32_t t_off = (uint32_t)(tr * C + quad * 4) * 2;
+    const uint32_t p_off = OFF_POOL + (uint32_t)((tr >> 1) * C + quad * 4) * 2;
+    bf16* obase = d_raw + ((size_t)b * L + ps.r0) * C;
+    __syncthreads();
+    for (int i = 0; i < n_sub; ++i) {
+        const int st = i % depth;
+        const int rows_i = min(S, ps.rows_here - i * S);
+        mbar_wait(smem_u32(ps.bars + st), (uint32_t)((i / depth) & 1));
+        const uint8_t* sb = smem + (size_t)st * stage_bytes;
+        uint8_t* so = s_out + (i & 1) * SG_STAGE_BYTES;
+        if (rows_i == S) {
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const uint2 xr = *reinterpret_cast<const uint2*>(sb + t_off + k * NTR * C * 2);
+                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + t_off + k * NTR * C * 2);
+                uint2 pl = make_uint2(0u, 0u);
+                if (POOL) pl = *reinterpret_cast<const uint2*>(sb + p_off + k * (NTR / 2) * C * 2);
+                *reinterpret_cast<uint2*>(so + t_off + k * NTR * C * 2) = row(xr, dr, pl);
+            }
+        } else {
+            for (int r = tr; r < rows_i; r += NTR) {
+                const uint2 xr = *reinterpret_cast<const uint2*>(sb + ((size_t)r * C + quad * 4) * 2);
+                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + ((size_t)r * C + quad * 4) * 2);
+                uint2 pl = make_uint2(0u, 0u);
+                if (POOL) pl = *reinterpret_cast<const uint2*>(sb + OFF_POOL + ((size_t)(r >> 1) * C + quad * 4) * 2);
+                *reinterpret_cast<uint2*>(so + ((size_t)r * C + quad * 4) * 2) = row(xr, dr, pl);
+            }
+        }
+        fence_proxy_async();
+        if (threadIdx.x == 0) tma_wait_read<0>();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store(obase + (size_t)i * S * C, smem_u32(so), (uint32_t)rows_i * C * 2);
+            tma_commit();
+            if (i + depth < n_sub) ps.issue(i + depth, false);
+        }
+    }
+    if (threadIdx.x == 0) tma_wait_read<0>();
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float lo, hi;
+        upk2(sbs[h], lo, hi);
+        red[(size_t)tr * C + quad * 4 + 2 * h] = lo;
+        red[(size_t)tr * C + quad * 4 + 2 * h + 1] = hi;
+    }
+    __syncthreads();
+    float* pt = partial_bias + ((size_t)b * gridDim.x + blockIdx.x) * C;
+    for (int i = threadIdx.x; i < C; i += 256) {
+        float sacc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < NTR; ++t) sacc += red[(size_t)t * C + i];
+        pt[i] = sacc;
+    }
+}
+
 int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t st) {
     const int C = a.C, Cc = a.Cc;
     const SgBwdLayout lay = sg_bwd_layout(C, Cc, a.do_a != nullptr, a.do_pool != nullptr);
@@ -744,6 +877,21 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
     const int depth = lay.stage > 20000 ? 2 : 3;        // + 16 KB of output staging: <= 75 KB per CTA, three CTAs per SM
     const size_t smem = (size_t)depth * lay.stage + 2 * SG_STAGE_BYTES + 64;
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
+    if (g_gn_bwd_stats_fast && a.do_eps == nullptr && a.do_a != nullptr) {
+        const bool pool = a.do_pool != nullptr;
+#define SGA_GO(CV, PL)                                                                                                      \
+    do {                                                                                                                    \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<CV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<CV, PL>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
+        gn_bwd_apply_fast_kernel<CV, PL><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);              \
+    } while (0)
+        if (C == 64) { if (pool) SGA_GO(64, true); else SGA_GO(64, false); }
+        else if (C == 128) { if (pool) SGA_GO(128, true); else SGA_GO(128, false); }
+        else { if (pool) SGA_GO(256, true); else SGA_GO(256, false); }
+#undef SGA_GO
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
     if (a.do_eps != nullptr) {
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -887,6 +1035,54 @@ struct FssArgs {
     long sample0;
 };
 
+struct FssCoef {
+    float c_s1mab, c_sab, c_sabp, c_dir, c_sig, c_w, c_s1mab_cl;
+    int use, last, draw;
+};
+// CFG combine + DDIM / DDPM update of one position (inference.py:455-506) given the head output of the conditional (outv0) and
+// unconditional (outv1) rows; writes x_{t-1} / x0_hat into the other ping-pong buffer
+__device__ __forceinline__ void fss_update(const FssArgs& p, const FssCoef& cf, float outv0, float outv1, float xt_c, float zu,
+                                           const float* __restrict__ noise, float* __restrict__ net_out, int n_half, int b, int B,
+                                           int Cx, int L, int l, float* __restrict__ eps_out, float* __restrict__ x0_out) {
+    const float c_s1mab = cf.c_s1mab, c_sab = cf.c_sab, c_sabp = cf.c_sabp, c_dir = cf.c_dir, c_sig = cf.c_sig, c_w = cf.c_w;
+    const float c_s1mab_cl = cf.c_s1mab_cl;
+    const int use = cf.use, last = cf.last, draw = cf.draw;
+    {
+        float o;
+        if (use == 0) o = outv0;
+        else if (use == 1) o = p.cfg_both ? outv1 : outv0;
+        else o = __fadd_rn(outv1, __fmul_rn(c_w, __fsub_rn(outv0, outv1)));
+        float eps, x0;
+        if (!p.pred_x0) {
+            eps = __fmul_rn(p.eps_scale, o);
+            x0 = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_s1mab, eps)), c_sab);
+        } else {
+            x0 = o;
+            eps = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_sab, x0)), c_s1mab_cl);
+        }
+        if (p.dc_weight > 0.0f)
+            x0 = __fadd_rn(__fmul_rn(1.0f - p.dc_weight, x0), __fmul_rn(p.dc_weight, p.y_dc[(size_t)b * L + l]));
+        float xn;
+        if (last) {
+            xn = x0;
+        } else {
+            float nz = 0.0f;
+            if (c_sig > 0.0f) {
+                const float z = noise != nullptr ? noise[((size_t)draw * B + b) * L + l] : zu;
+                nz = __fmul_rn(c_sig, z);
+            }
+            xn = __fadd_rn(__fadd_rn(__fmul_rn(c_sabp, x0), __fmul_rn(c_dir, eps)), nz);
+        }
+        for (int hf = 0; hf < n_half; ++hf) {
+            float* orow = net_out + (size_t)(b + hf * B) * Cx * L;
+            orow[l] = xn;
+            if (p.selfcond) orow[(size_t)(Cx - 1) * L + l] = x0;
+        }
+        if (eps_out != nullptr) eps_out[(size_t)b * L + l] = eps;
+        if (x0_out != nullptr) x0_out[(size_t)b * L + l] = x0;
+    }
+}
+
 __global__ void __launch_bounds__(256) final_step_stream_kernel(const bf16* __restrict__ h, const float* __restrict__ net_a,
                                                                 const float* __restrict__ net_b, int B, int Cx, int L,
                                                                 const float* __restrict__ wf, const float* __restrict__ bf,
@@ -984,10 +1180,10 @@ __global__ void __launch_bounds__(256) final_step_stream_kernel(const bf16* __re
 #pragma unroll
         for (int i = 0; i < 10; ++i) cfv[i] = cf[i];
     }
-    const float c_s1mab = cfv[0], c_sab = cfv[1], c_sabp = cfv[2], c_dir = cfv[3], c_sig = cfv[4], c_w = cfv[5];
-    const int use = (int)cfv[6], last = (int)cfv[7], draw = (int)cfv[8];
-    const float c_s1mab_cl = cfv[9];
-    const bool need_z = p.mode == 1 && !last && c_sig > 0.0f;
+    FssCoef cf;
+    cf.c_s1mab = cfv[0]; cf.c_sab = cfv[1]; cf.c_sabp = cfv[2]; cf.c_dir = cfv[3]; cf.c_sig = cfv[4]; cf.c_w = cfv[5];
+    cf.use = (int)cfv[6]; cf.last = (int)cfv[7]; cf.draw = (int)cfv[8]; cf.c_s1mab_cl = cfv[9];
+    const bool need_z = p.mode == 1 && !cf.last && cf.c_sig > 0.0f;
     float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (need_z && noise == nullptr)
         Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)((l0 + g * 4) >> 2), z4);
@@ -1009,39 +1205,85 @@ __global__ void __launch_bounds__(256) final_step_stream_kernel(const bf16* __re
             eps_out[(size_t)b * L + l] = outv0;
             continue;
         }
-        float o;
-        if (use == 0) o = outv0;
-        else if (use == 1) o = p.cfg_both ? outv1 : outv0;
-        else o = __fadd_rn(outv1, __fmul_rn(c_w, __fsub_rn(outv0, outv1)));
-        float eps, x0;
-        if (!p.pred_x0) {
-            eps = __fmul_rn(p.eps_scale, o);
-            x0 = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_s1mab, eps)), c_sab);
-        } else {
-            x0 = o;
-            eps = __fdiv_rn(__fsub_rn(xt_c, __fmul_rn(c_sab, x0)), c_s1mab_cl);
-        }
-        if (p.dc_weight > 0.0f)
-            x0 = __fadd_rn(__fmul_rn(1.0f - p.dc_weight, x0), __fmul_rn(p.dc_weight, p.y_dc[(size_t)b * L + l]));
-        float xn;
-        if (last) {
-            xn = x0;
-        } else {
-            float nz = 0.0f;
-            if (c_sig > 0.0f) {
-                const float z = noise != nullptr ? noise[((size_t)draw * B + b) * L + l] : z4[u];
-                nz = __fmul_rn(c_sig, z);
-            }
-            xn = __fadd_rn(__fadd_rn(__fmul_rn(c_sabp, x0), __fmul_rn(c_dir, eps)), nz);
-        }
-        for (int hf = 0; hf < n_half; ++hf) {
-            float* orow = net_out + (size_t)(b + hf * B) * Cx * L;
-            orow[l] = xn;
-            if (p.selfcond) orow[(size_t)(Cx - 1) * L + l] = x0;
-        }
-        if (eps_out != nullptr) eps_out[(size_t)b * L + l] = eps;
-        if (x0_out != nullptr) x0_out[(size_t)b * L + l] = x0;
+        fss_update(p, cf, outv0, outv1, xt_c, z4[u], noise, net_out, n_half, b, B, Cx, L, l, eps_out, x0_out);
     }
+}
+
+// The same head + update from the three dot products per position that the last decoder's fused kernel leaves behind
+// (gw_conv_gn2, dots [Bn, L, 4] fp32 = (sum_c h[l,c] w[c,0], .. w[c,1], .. w[c,2], 0)): eps_hat[l] = d0[l-1] + d1[l] + d2[l+1] + the x_t
+// taps + bias (models.py:230).  16 B per position instead of the 128 B row of h; a thread owns 4 positions (one Philox quad).
+__global__ void __launch_bounds__(256) final_step_dots_kernel(const float4* __restrict__ dots, const float* __restrict__ net_a,
+                                                              const float* __restrict__ net_b, int B, int Cx, int L,
+                                                              const float* __restrict__ wf, const float* __restrict__ bf, int C,
+                                                              FssArgs p, const float* __restrict__ coef,
+                                                              const int* __restrict__ step_ptr, const float* __restrict__ noise,
+                                                              float* __restrict__ eps_out, float* __restrict__ x0_out) {
+    const int b = blockIdx.y, l4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (l4 >= L) return;
+    const int step = step_ptr != nullptr ? *step_ptr : 0;
+    const float* net_in = (step & 1) ? net_b : net_a;
+    float* net_out = const_cast<float*>((step & 1) ? net_a : net_b);
+    const int n_half = (p.mode == 1 && p.cfg_both) ? 2 : 1;
+    const float wx0 = wf[C * 3 + 0], wx1 = wf[C * 3 + 1], wx2 = wf[C * 3 + 2], bias = bf[0];
+    float cfv[10] = {0.0f, 1.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+    if (p.mode == 1) {
+        const float* cfp = coef + (size_t)step * 16;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) cfv[i] = cfp[i];
+    }
+    FssCoef cf;
+    cf.c_s1mab = cfv[0]; cf.c_sab = cfv[1]; cf.c_sabp = cfv[2]; cf.c_dir = cfv[3]; cf.c_sig = cfv[4]; cf.c_w = cfv[5];
+    cf.use = (int)cfv[6]; cf.last = (int)cfv[7]; cf.draw = (int)cfv[8]; cf.c_s1mab_cl = cfv[9];
+    const bool need_z = p.mode == 1 && !cf.last && cf.c_sig > 0.0f;
+    float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (need_z && noise == nullptr) Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)(l4 >> 2), z4);
+    const int n = min(4, L - l4);
+    float ov[2][4], xc4[4];
+    for (int hf = 0; hf < n_half; ++hf) {
+        const float4* dr = dots + (size_t)(b + hf * B) * L;
+        const float* xr = net_in + (size_t)(b + hf * B) * Cx * L;
+        float dm = l4 > 0 ? dr[l4 - 1].x : 0.0f;                   // tap 0 of the previous position
+        float xm = l4 > 0 ? xr[l4 - 1] : 0.0f;
+        float4 dc = dr[l4];
+        float xc = xr[l4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < n) {
+                const int l = l4 + u;
+                const bool nx = l + 1 < L;
+                const float4 dn = nx ? dr[l + 1] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const float xp = nx ? xr[l + 1] : 0.0f;
+                float acc = dm + dc.y + dn.z;
+                acc += fmaf(xm, wx0, fmaf(xc, wx1, xp * wx2));
+                ov[hf][u] = acc + bias;
+                if (hf == 0) xc4[u] = xc;
+                dm = dc.x; dc = dn; xm = xc; xc = xp;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (u >= n) break;
+        const int l = l4 + u;
+        if (p.mode == 0) {
+            eps_out[(size_t)b * L + l] = ov[0][u];
+            continue;
+        }
+        fss_update(p, cf, ov[0][u], n_half == 2 ? ov[1][u] : 0.0f, xc4[u], z4[u], noise, net_out, n_half, b, B, Cx, L, l, eps_out, x0_out);
+    }
+}
+
+int final_step_dots(const void* dots, const float* net_a, const float* net_b, int B, int Cx, int L, int C, const float* wf,
+                    const float* bf, const gw_step_params* p, const float* coef, const int* step_ptr, const float* noise,
+                    float* eps_out, float* x0_out, cudaStream_t st) {
+    FssArgs a;
+    a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
+    a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    dim3 grid(gw_cdiv(L, 1024), B);
+    final_step_dots_kernel<<<grid, 256, 0, st>>>((const float4*)dots, net_a, net_b ? net_b : net_a, B, Cx, L, wf, bf, C, a, coef,
+                                                 step_ptr, noise, eps_out, x0_out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
 }
 
 // called by gw_final_step (forward.cu) for bf16, C = 64

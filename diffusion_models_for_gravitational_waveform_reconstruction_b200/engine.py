@@ -144,6 +144,8 @@ class _Workspace:
         self.cond = [torch.empty(B, Ls[j], max(spec.cond_in_ch, 1), device=device, dtype=torch.float32)
                      for j in range(d + 1)] if spec.cond_in_ch > 0 else None
         self.sync: Optional[Tensor] = None          # gw_conv_gn exchange buffer (zeroed once, see UNetEngine._block)
+        self.dots: Optional[Tensor] = None          # [B, L, 4] head dot products left by the last decoder's fused kernel
+        self.head_fused = False                     # set by UNetEngine.body(): ws.dots is current, ws.out[-1] was not written
 
 
 class UNetEngine:
@@ -188,6 +190,9 @@ class UNetEngine:
         # measured on B200 the fused kernel then loses its edge (962 us vs ~900 us of conv + GroupNorm launches per step at
         # B=256, L=4096, in_ch=7), so it stays an inference default; parity-tested for both
         self.fuse_gn_train = False
+        # inference: the last decoder's fused kernel also forms the three head-conv dot products per position (gw_conv_gn2), so
+        # gw_final_step runs on 16 B per position and the [B, L, 64] activation is neither written nor read back
+        self.fuse_head = True
         self._fuse_ok: Dict[tuple, bool] = {}
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
@@ -340,7 +345,7 @@ class UNetEngine:
         self.launches += 1
 
     def _block(self, li: int, ws: _Workspace, src0: Tensor, src1: Optional[Tensor], film: Tensor, film_b_stride: int,
-               film_step_stride: int, step_ptr: Optional[Tensor], pooled: Optional[Tensor], lvl: int) -> None:
+               film_step_stride: int, step_ptr: Optional[Tensor], pooled: Optional[Tensor], lvl: int, head: bool = False) -> bool:
         """One conv block (models.py:160-173 + cond bias + FiLM (+ pool)) of layer li >= 1 into ws.out[li]."""
         sp = self.spec
         raw = ws.raw[li]
@@ -359,7 +364,7 @@ class UNetEngine:
         if not fused:
             n_part = self._conv(li, src0, src1, raw, ws.part)
             self._gn(li, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, pooled, lvl)
-            return
+            return False
         if ws.sync is None:
             ws.sync = torch.zeros(self.lib.gw_conv_gn_sync_bytes(B), device=self.device, dtype=torch.uint8)
         key = (li, L, L0)
@@ -370,15 +375,20 @@ class UNetEngine:
         name, cname = sp.layer_names()[li], sp.cond_names()[li]
         shp = self._shape(li, B, L, L0)
         keep = ws.stats is not None
-        check(self.lib.gw_conv_gn(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),
-                                  ptr(self.p[name + ".1.weight"]), ptr(self.p[name + ".1.bias"]),
-                                  ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
-                                  ptr(self.p[cname + ".weight"]) if Cc > 0 else None,
-                                  ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film), sp.film_offsets()[li],
-                                  film_b_stride, film_step_stride, ptr(step_ptr), ptr(ws.out[li]), ptr(pooled),
-                                  ptr(raw) if keep else None, ptr(ws.stats[li]) if keep else None, ptr(ws.sync),
-                                  _cabi.stream_ptr()), f"conv_gn[{name}]")
+        head = head and not keep and Cout == 64 and src1 is not None and pooled is None
+        if head and ws.dots is None:
+            ws.dots = torch.empty(B, L, 4, device=self.device, dtype=torch.float32)
+        check(self.lib.gw_conv_gn2(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),
+                                   ptr(self.p[name + ".1.weight"]), ptr(self.p[name + ".1.bias"]),
+                                   ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                   ptr(self.p[cname + ".weight"]) if Cc > 0 else None,
+                                   ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film), sp.film_offsets()[li],
+                                   film_b_stride, film_step_stride, ptr(step_ptr), None if head else ptr(ws.out[li]), ptr(pooled),
+                                   ptr(raw) if keep else None, ptr(ws.stats[li]) if keep else None, ptr(ws.sync),
+                                   ptr(self.wf) if head else None, ptr(ws.dots) if head else None,
+                                   _cabi.stream_ptr()), f"conv_gn[{name}]")
         self.launches += 1
+        return head
 
     def body(self, ws: _Workspace, net_a: Tensor, net_b: Optional[Tensor], step_ptr: Optional[Tensor], film: Tensor,
              film_b_stride: int, film_step_stride: int) -> Tensor:
@@ -420,17 +430,24 @@ class UNetEngine:
             self._block(i, ws, ws.pooled[i - 1], None, film, film_b_stride, film_step_stride, step_ptr, ws.pooled[i], i)
         self._block(d, ws, ws.pooled[d - 1], None, film, film_b_stride, film_step_stride, step_ptr, None, d)
         h = ws.out[d]
+        ws.head_fused = False
         for i in range(d):
             li = d + 1 + i
-            self._block(li, ws, h, ws.out[d - 1 - i], film, film_b_stride, film_step_stride, step_ptr, None, d - 1 - i)
+            last = i == d - 1
+            hf = self._block(li, ws, h, ws.out[d - 1 - i], film, film_b_stride, film_step_stride, step_ptr, None, d - 1 - i,
+                             head=last and self.fuse_head)
             h = ws.out[li]
+            if last and hf:
+                ws.head_fused = True
+                h = ws.dots                                   # consumed by head() (gw_final_step with dtype = GW_DOTS)
         return h
 
     def head(self, h: Tensor, net_a: Tensor, net_b: Optional[Tensor], params: StepParams, coef: Optional[Tensor],
              step_ptr: Optional[Tensor], noise: Optional[Tensor], eps_out: Optional[Tensor], x0_out: Optional[Tensor],
              B: int) -> None:
         _, Cx, L = net_a.shape
-        check(self.lib.gw_final_step(ptr(h), self.gw_dtype, ptr(net_a), ptr(net_b), B, Cx, L, self.spec.base_ch,
+        dots = h.dtype == torch.float32 and h.dim() == 3 and h.shape[-1] == 4 and self.dtype == "bf16"
+        check(self.lib.gw_final_step(ptr(h), 2 if dots else self.gw_dtype, ptr(net_a), ptr(net_b), B, Cx, L, self.spec.base_ch,
                                      ptr(self.wf), ptr(self.p["final.bias"]), C.byref(params), ptr(coef), ptr(step_ptr),
                                      ptr(noise), ptr(eps_out), ptr(x0_out), _cabi.stream_ptr()), "final_step")
         self.launches += 1

@@ -85,8 +85,10 @@ class BackwardEngine:
         self.wgrad_impl = "tc" if eng.conv_impl == "tc" else "simt"
         self.wgrad_variant = 0
         self.fuse_head = False
-        # bf16: one-pass GroupNorm backward (gn_bwd_fused.cu) wherever a sample fits the shared memory of <= 32 CTAs
-        self.fuse_gn_bwd = True
+        # bf16: one-pass GroupNorm backward (gn_bwd_fused.cu).  Reads every operand once (3.5 instead of 5.5 tensor passes) but
+        # measured slower on B200 (1.90 vs 1.13 ms per step at B=256, L=4096): a slice stays in shared memory for load +
+        # sums + exchange + apply + store (~8 us), and 228 KB per SM cannot cover that latency at HBM rate.  Parity-tested option.
+        self.fuse_gn_bwd = False
 
     def grad_workspace(self, ws: _Workspace) -> _GradWorkspace:
         key = (ws.B, ws.L)

@@ -26,6 +26,7 @@ extern "C" {
 
 #define GW_F32 0
 #define GW_BF16 1
+#define GW_DOTS 2 /* gw_final_step only: `h` holds the head dot products [Bn, L, 4] fp32 written by gw_conv_gn2 */
 #define GW_MAX_LEVELS 8
 
 int gw_version(void);
@@ -172,6 +173,16 @@ int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const void* src1, co
                const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
                const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
                void* out, void* pooled, void* raw, float* stats_out, void* sync, void* stream);
+/* gw_conv_gn2 = gw_conv_gn that also leaves, for the LAST decoder (Cout = 64 over cat[upsample, skip]), the three dot products
+ * of the head conv final(cat[h, x_t]) (models.py:230) per position: head_w = final.weight [C+1, 3], head_dots [B, L, 4] fp32 =
+ * (sum_c out[l,c] w[c,0], sum_c out[l,c] w[c,1], sum_c out[l,c] w[c,2], 0), formed from the fp32 epilogue values.  gw_final_step
+ * (dtype = GW_DOTS, h = head_dots) finishes eps_hat and the DDIM / DDPM update from 16 B per position.  out may then be NULL
+ * (the activated tensor is not written).  head_w == head_dots == NULL: identical to gw_conv_gn. */
+int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
+                const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
+                const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
+                void* out, void* pooled, void* raw, float* stats_out, void* sync, const float* head_w, float* head_dots,
+                void* stream);
 
 /* ---- fused FIRST block for inference: Conv1d(C_in -> 64, k=3) -> GroupNorm -> SiLU -> + cond 1x1 conv -> FiLM (-> pool) in
  * one kernel (models.py:160-173, 188-193, 204-208; conv_in_gn.cu).  gw_conv_in + gw_gn_apply without the raw tensor: G = L/256

@@ -164,6 +164,7 @@ def test_fused_conv_gn_block(in_ch, cc, L, B, keep_raw):
     t = torch.tensor(([24, 999, 500, 3, 250] * B)[:B])
     fused, plain = _engine(sd, in_ch, cc, "bf16", "tc"), _engine(sd, in_ch, cc, "bf16", "tc")
     fused.fuse_gn_train = True
+    fused.fuse_head = False                      # this test reads the last decoder's activation (see test_fused_head_dots)
     plain.fuse_gn = False
     # three forwards through the same workspace: the exchange epoch must advance between launches
     for _ in range(3):
@@ -212,3 +213,26 @@ def test_fused_first_block_partial_tiles(in_ch, cc, L, B):
         with torch.no_grad():
             ref = oracle.unet_forward(sd, cfg, x, t)
         assert rel_l2(eps_f, ref) <= BF16_TOL
+
+
+@pytest.mark.parametrize("in_ch,cc,L,B", [(3, 1, 4096, 21), (7, 5, 4096, 5), (3, 1, 512, 5), (7, 5, 1536, 4), (3, 1, 16384, 2)])
+def test_fused_head_dots(in_ch, cc, L, B):
+    """gw_conv_gn2: the last decoder's fused kernel leaves the three head-conv dot products per position (formed from its fp32
+    epilogue values) and gw_final_step(dtype = GW_DOTS) finishes eps_hat from them -- against the path that writes the bf16
+    activation and streams it back, and against the oracle."""
+    sd = make_state_dict(in_ch, cc, seed=0)
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True)
+    x = gaussian((B, in_ch, L), seed=5 + L)
+    t = torch.tensor(([24, 999, 500, 3, 250] * B)[:B])
+    a, b = _engine(sd, in_ch, cc, "bf16", "tc"), _engine(sd, in_ch, cc, "bf16", "tc")
+    assert a.fuse_head
+    b.fuse_head = False
+    for _ in range(2):
+        eps_a = a.forward(x.cuda(), t.cuda())
+    eps_b = b.forward(x.cuda(), t.cuda())
+    assert a.workspace(B, L, False).head_fused and not b.workspace(B, L, False).head_fused
+    assert rel_l2(eps_a, eps_b) <= 5e-3          # fp32 vs bf16-rounded activations under the head conv
+    if B * L <= 5 * 4096:
+        with torch.no_grad():
+            eps_o = oracle.unet_forward(sd, cfg, x, t)
+        assert rel_l2(eps_a.cpu(), eps_o) <= BF16_TOL

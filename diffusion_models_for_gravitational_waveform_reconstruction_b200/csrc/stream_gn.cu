@@ -17,9 +17,10 @@
 // ------------------------------------------------------------------------------------------------
 // forward: GroupNorm-apply + SiLU + cond 1x1 conv + FiLM (+ avg_pool), see gn_apply_kernel in forward.cu
 // ------------------------------------------------------------------------------------------------
-template <int CC>
+// CV > 0: channel count known at compile time (every stride an immediate, full stages unrolled); CV = 0: generic
+template <int CC, int CV>
 __global__ void __launch_bounds__(256)
-gn_apply_stream_kernel(const bf16* __restrict__ raw, const float* __restrict__ part, int n_part, int L, int C,
+gn_apply_stream_kernel(const bf16* __restrict__ raw, const float* __restrict__ part, int n_part, int L, int C_rt,
                        const float* __restrict__ gn_w, const float* __restrict__ gn_b, const float* __restrict__ cond, int Cc_rt,
                        const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ film, int film_off,
                        long film_b_stride, long film_step_stride, const int* __restrict__ step_ptr, bf16* __restrict__ out,
@@ -27,6 +28,7 @@ gn_apply_stream_kernel(const bf16* __restrict__ raw, const float* __restrict__ p
     constexpr int NC = CC >= 0 ? CC : SG_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     const int Cc = CC >= 0 ? CC : Cc_rt;
+    const int C = CV > 0 ? CV : C_rt;
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: in[D][8 KB] | out[2][8 KB] | pool[2][4 KB] | cond[D][S*Cc*4 rounded to 128] | barriers
     const int S = SG_STAGE_BYTES / (C * 2);                       // rows per stage (64 / 32 / 16 for C = 64 / 128 / 256)
@@ -128,7 +130,7 @@ gn_apply_stream_kernel(const bf16* __restrict__ raw, const float* __restrict__ p
         const float* cd = reinterpret_cast<const float*>(s_cond + st * cond_stage);
         uint8_t* so = s_out + (i & 1) * SG_STAGE_BYTES;
         uint8_t* sp = s_pool + (i & 1) * (SG_STAGE_BYTES / 2);
-        for (int pr = pr0; 2 * pr < rows_i; pr += pr_stride) {
+        auto pair_rows = [&](int pr) {
             f32x2 o[2][2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -170,6 +172,13 @@ gn_apply_stream_kernel(const bf16* __restrict__ raw, const float* __restrict__ p
                 rr.y = pack_bf16x2(a2, a3);
                 *reinterpret_cast<uint2*>(sp + ((size_t)pr * C + quad * 4) * 2) = rr;
             }
+        };
+        if (CV > 0 && rows_i == S) {
+            constexpr int TRIPS = CV > 0 ? (SG_STAGE_BYTES / (CV * 2) / 2) / (256 / (CV / 4)) : 1;
+#pragma unroll
+            for (int kq = 0; kq < TRIPS; ++kq) pair_rows(pr0 + kq * pr_stride);
+        } else {
+            for (int pr = pr0; 2 * pr < rows_i; pr += pr_stride) pair_rows(pr);
         }
         fence_proxy_async();                                          // my smem writes -> visible to the bulk-store engine
         if (threadIdx.x == 0) tma_wait_read<0>();                     // stores of iteration i-1 have drained staging[(i+1)&1]
@@ -207,18 +216,25 @@ extern "C" int gw_gn_apply_stream(const void* raw, const float* part, int n_part
     const size_t smem = (size_t)SG_DEPTH * SG_STAGE_BYTES + 2 * SG_STAGE_BYTES + SG_STAGE_BYTES + SG_DEPTH * cond_stage + 64;
     dim3 grid(gw_cdiv(L, rows), B);
     cudaStream_t st = (cudaStream_t)stream;
-#define SGA_GO(CCV)                                                                                                        \
+#define SGA_GO(CCV, CV)                                                                                                    \
     do {                                                                                                                   \
-        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   \
-        gn_apply_stream_kernel<CCV><<<grid, 256, smem, st>>>((const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
+        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV, CV>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   \
+        gn_apply_stream_kernel<CCV, CV><<<grid, 256, smem, st>>>((const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
                                                              film, film_off, film_b_stride, film_step_stride, step_ptr,        \
                                                              (bf16*)out, (bf16*)pooled, stats_out, rows);                      \
     } while (0)
-    if (Cc == 0) SGA_GO(0);
-    else if (Cc == 1) SGA_GO(1);
-    else if (Cc == 5) SGA_GO(5);
-    else SGA_GO(-1);
+#define SGA_C(CCV)                          \
+    do {                                    \
+        if (C == 64) SGA_GO(CCV, 64);       \
+        else if (C == 128) SGA_GO(CCV, 128); \
+        else SGA_GO(CCV, 256);              \
+    } while (0)
+    if (Cc == 0) SGA_GO(0, 0);
+    else if (Cc == 1) SGA_C(1);
+    else if (Cc == 5) SGA_C(5);
+    else SGA_GO(-1, 0);
+#undef SGA_C
 #undef SGA_GO
     GW_LAUNCH_CHECK();
     return GW_OK;
@@ -1033,6 +1049,7 @@ struct FssArgs {
     const float* y_dc;
     unsigned long long seed;
     long sample0;
+    unsigned int* advance;      // final_step_dots_kernel: CTA counter; the last CTA out does *step_ptr += 1 (NULL: nobody does)
 };
 
 struct FssCoef {
@@ -1216,11 +1233,11 @@ __global__ void __launch_bounds__(256) final_step_dots_kernel(const float4* __re
                                                               const float* __restrict__ net_b, int B, int Cx, int L,
                                                               const float* __restrict__ wf, const float* __restrict__ bf, int C,
                                                               FssArgs p, const float* __restrict__ coef,
-                                                              const int* __restrict__ step_ptr, const float* __restrict__ noise,
+                                                              int* __restrict__ step_ptr, const float* __restrict__ noise,
                                                               float* __restrict__ eps_out, float* __restrict__ x0_out) {
     const int b = blockIdx.y, l4 = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (l4 >= L) return;
     const int step = step_ptr != nullptr ? *step_ptr : 0;
+    if (l4 < L) {
     const float* net_in = (step & 1) ? net_b : net_a;
     float* net_out = const_cast<float*>((step & 1) ? net_a : net_b);
     const int n_half = (p.mode == 1 && p.cfg_both) ? 2 : 1;
@@ -1271,6 +1288,19 @@ __global__ void __launch_bounds__(256) final_step_dots_kernel(const float4* __re
         }
         fss_update(p, cf, ov[0][u], n_half == 2 ? ov[1][u] : 0.0f, xc4[u], z4[u], noise, net_out, n_half, b, B, Cx, L, l, eps_out, x0_out);
     }
+    }
+    if (p.advance != nullptr) {
+        // every CTA has read *step_ptr before it arrives here: the last one out advances the step counter for the next launch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int done = atomicAdd(p.advance, 1u);
+            if (done == gridDim.x * gridDim.y - 1) {
+                *p.advance = 0u;
+                *step_ptr = step + 1;
+            }
+        }
+    }
 }
 
 int final_step_dots(const void* dots, const float* net_a, const float* net_b, int B, int Cx, int L, int C, const float* wf,
@@ -1279,9 +1309,10 @@ int final_step_dots(const void* dots, const float* net_a, const float* net_b, in
     FssArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
     a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    a.advance = (p->mode == 1 && step_ptr != nullptr) ? (unsigned int*)p->advance : nullptr;
     dim3 grid(gw_cdiv(L, 1024), B);
     final_step_dots_kernel<<<grid, 256, 0, st>>>((const float4*)dots, net_a, net_b ? net_b : net_a, B, Cx, L, wf, bf, C, a, coef,
-                                                 step_ptr, noise, eps_out, x0_out);
+                                                 const_cast<int*>(step_ptr), noise, eps_out, x0_out);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -1293,6 +1324,7 @@ int final_step_stream(const void* h, const float* net_a, const float* net_b, int
     FssArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
     a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    a.advance = nullptr;
     const size_t smem = (size_t)SG_DEPTH * SG_STAGE_BYTES + (size_t)2 * 3 * (FSS_TP + 2) * 4 + 64;
     GW_CUDA(cudaFuncSetAttribute(final_step_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(final_step_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));

@@ -564,8 +564,10 @@ class SamplerPlan:
         self.net = [torch.zeros(self.Bn, Cx, L, device=dev, dtype=torch.float32) for _ in range(2)]
         self.ws = eng.workspace(self.Bn, L)
         self.y_dc = torch.zeros(B, L, device=dev, dtype=torch.float32) if dc_weight > 0 else None
+        self.adv = torch.zeros(1, dtype=torch.int32, device=dev)      # CTA counter of the self-advancing head kernel
         self.params = StepParams(1, 1 if self.cfg_both else 0, 1 if sp.use_selfcond else 0, 1 if pred_type != "eps" else 0,
-                                 float(eps_scale), float(dc_weight), ptr(self.y_dc), int(seed) & (2 ** 64 - 1), int(sample0))
+                                 float(eps_scale), float(dc_weight), ptr(self.y_dc), int(seed) & (2 ** 64 - 1), int(sample0),
+                                 ptr(self.adv))
         self.noise: Optional[Tensor] = None
         self.trace_eps: Optional[Tensor] = None
         self.trace_x0: Optional[Tensor] = None
@@ -577,8 +579,9 @@ class SamplerPlan:
         eng = self.eng
         h = eng.body(self.ws, self.net[0], self.net[1], self.step, self.film, 0, eng.spec.film_dim)
         eng.head(h, self.net[0], self.net[1], self.params, self.coef, self.step, self.noise, self.trace_eps, self.trace_x0, self.B)
-        check(eng.lib.gw_step_advance(ptr(self.step), -1, _cabi.stream_ptr()), "step_advance")
-        eng.launches += 1
+        if not self.ws.head_fused:                     # the head kernel on the fused dots advances the counter itself
+            check(eng.lib.gw_step_advance(ptr(self.step), -1, _cabi.stream_ptr()), "step_advance")
+            eng.launches += 1
 
     def load_inputs(self, x_init: Tensor, cond_on: Tensor, cond_off: Optional[Tensor], y_dc: Optional[Tensor]) -> None:
         """x_init [B,1,L]; cond_on/off [B,Cc,L] (already cond-scaled / zeroed as inference.py:434-446)."""

@@ -114,6 +114,8 @@ typedef struct {
     const float* y_dc; /* device fp32 [B, L]: the unscaled y for the dc blend (inference.py:472); NULL if dc_weight == 0 */
     unsigned long long seed;
     long sample0;      /* global index of sample 0 (Philox stream id, world-size independent) */
+    void* advance;     /* dtype = GW_DOTS, mode 1: device uint32 (zeroed once): the last CTA of the launch does *step_ptr += 1, so
+                          no gw_step_advance launch is needed between reverse steps; NULL: the caller advances the counter */
 } gw_step_params;
 
 int gw_final_step(const void* h, int dtype, const float* net_a, const float* net_b, int B, int Cx, int L, int C,

@@ -414,7 +414,9 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(GnBwdArgs a, float
 }
 
 // grid B, block 1024: reduce the row-CTA partials of one sample, emit dfilm and the group means needed by the apply pass
-__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ partial, int n_rc, int C, int nvr, int L,
+// nvr = values per channel in `partial` / `redb` (4 + Cc, + 1 when the sums pass also delivers sum_l xhat for the analytic conv-bias
+// gradient, see gn_bwd_param_kernel)
+__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ partial, int n_rc, int C, int nvr, int Cc, int L,
                                                                const float* __restrict__ gn_w, const float* __restrict__ wc,
                                                                const float* __restrict__ bc, float* __restrict__ redb,
                                                                float* __restrict__ dfilm, long dfilm_b_stride, int film_off,
@@ -431,7 +433,6 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
     }
     __syncthreads();
     float* df = dfilm + (size_t)b * dfilm_b_stride + film_off;
-    const int Cc = nvr - 4;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float dg = sv[c * nvr + 1];                       // sum do*silu(n)
         if (Cc > 0) {                                     // + sum do*(bc + sum_j wc_j cond_j): h = silu(n) + cond bias
@@ -459,18 +460,24 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
 }
 
 // grid ceil(C/32), block 1024 = 32 channels x 32 batch lanes: parameter gradients that sum over the batch
-__global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restrict__ redb, int B, int C, int nvr,
+// SX (the sums pass delivered p[4+Cc] = sum_l xhat[l,c]): the conv-bias gradient sum_{b,l} d_raw[b,l,c] follows analytically,
+//   sum_l d_raw = rstd * (gn_w[c] * sum_l dn - L * m1 - m2 * sum_l xhat),  (m1, m2) = gstat of the sample's group,
+// so the apply pass needs no per-CTA bias partials and no reduce launches (and the sum is free of d_raw's bf16 rounding).
+__global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restrict__ redb, int B, int C, int nvr, int Cc,
                                                             const float* __restrict__ film, long film_b_stride, int film_off,
                                                             float* __restrict__ d_gn_w, float* __restrict__ d_gn_b,
-                                                            float* __restrict__ d_wc, float* __restrict__ d_bc) {
-    __shared__ float red[32][32][3 + BW_MAX_CC + 1];
+                                                            float* __restrict__ d_wc, float* __restrict__ d_bc, int sx,
+                                                            const float* __restrict__ stats, const float* __restrict__ gstat,
+                                                            const float* __restrict__ gn_w, int L, float* __restrict__ d_conv_bias) {
+    __shared__ float red[32][32][3 + BW_MAX_CC + 1];        // slot 3 + BW_MAX_CC: the conv-bias sum (SX)
     const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
-    const int Cc = nvr - 4;
-    float a[3 + BW_MAX_CC];
+    float a[4 + BW_MAX_CC];
 #pragma unroll
-    for (int v = 0; v < 3 + BW_MAX_CC; ++v) a[v] = 0.0f;
+    for (int v = 0; v < 4 + BW_MAX_CC; ++v) a[v] = 0.0f;
     if (c < C) {
+        const int g = c / (C / 8);
+        const float gw = sx ? gn_w[c] : 0.0f;
 #pragma unroll 4
         for (int b = bl; b < B; b += 32) {
             const float* p = redb + ((size_t)b * C + c) * nvr;
@@ -481,10 +488,15 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restr
 #pragma unroll
             for (int j = 0; j < BW_MAX_CC; ++j)
                 if (j < Cc) a[3 + j] = fmaf(G, p[4 + j], a[3 + j]);
+            if (sx) {
+                const float rstd = stats[((size_t)b * 8 + g) * 2 + 1];
+                const float m1 = gstat[((size_t)b * 8 + g) * 2 + 0], m2 = gstat[((size_t)b * 8 + g) * 2 + 1];
+                a[3 + BW_MAX_CC] += rstd * (fmaf(gw, p[2], -(float)L * m1) - m2 * p[4 + Cc]);
+            }
         }
     }
 #pragma unroll
-    for (int v = 0; v < 3 + BW_MAX_CC; ++v) red[bl][cl][v] = a[v];
+    for (int v = 0; v < 4 + BW_MAX_CC; ++v) red[bl][cl][v] = a[v];
     __syncthreads();
     // thread (v = bl, channel = cl) folds the 32 batch lanes of value v in fixed order
     if (bl < 3 + Cc && c < C) {
@@ -497,6 +509,11 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restr
             if (bl == 2) d_bc[c] += sv;
             else d_wc[c * Cc + (bl - 3)] += sv;
         }
+    } else if (sx && bl == 31 && c < C) {
+        float sv = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) sv += red[t][cl][3 + BW_MAX_CC];
+        d_conv_bias[c] += sv;
     }
 }
 
@@ -823,12 +840,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
 int g_gn_bwd_stream = 1;
 extern int g_final_stream;
 extern int g_gn_bwd_fused, g_gn_bwd_fused_slice;
-int g_gn_bwd_chunk = 0;
 extern int g_gn_bwd_stats_fast;
 extern "C" int gw_set_option(const char* name, int value) {
     if (strcmp(name, "gn_bwd_stream") == 0) { g_gn_bwd_stream = value; return GW_OK; }
     if (strcmp(name, "gn_bwd_stats_fast") == 0) { g_gn_bwd_stats_fast = value; return GW_OK; }
-    if (strcmp(name, "gn_bwd_chunk") == 0) { g_gn_bwd_chunk = value; return GW_OK; }
     if (strcmp(name, "gn_bwd_fused") == 0) { g_gn_bwd_fused = value; return GW_OK; }
     if (strcmp(name, "gn_bwd_fused_slice") == 0) { g_gn_bwd_fused_slice = value; return GW_OK; }
     if (strcmp(name, "final_stream") == 0) { g_final_stream = value; return GW_OK; }
@@ -844,7 +859,7 @@ static int gn_rows_per_cta(int L, int C) {
 }
 
 extern "C" long gw_gn_bwd_scratch_elems(int B, int L, int C, int Cc) {
-    const int rows = gn_rows_per_cta(L, C), n_rc = gw_cdiv(L, rows), nvr = 4 + Cc;
+    const int rows = gn_rows_per_cta(L, C), n_rc = gw_cdiv(L, rows), nvr = 5 + Cc;     // (+1: sum of xhat, fast sums kernel)
     // [partials | per-sample reduced | group means]
     const long two_pass = (long)B * n_rc * C * nvr + (long)B * C * nvr + (long)B * 16;
     // one-pass kernel (gn_bwd_fused.cu): up to XCHG_MAX_G row CTAs per sample, plus the conv-bias partials
@@ -871,11 +886,11 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
             float* biasp = gstat + (size_t)B * 16;
             const int rcf = gn_bwd_fused(a, B, partial, biasp, d_raw, sync, st);
             if (rcf == GW_OK) {
-                gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvr * sizeof(float), st>>>(partial, G, C, nvr, L, a.gn_w, a.wc, a.bc, redb,
-                                                                                        dfilm, dfilm_b_stride, a.film_off, gstat);
+                gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvr * sizeof(float), st>>>(partial, G, C, nvr, Cc, L, a.gn_w, a.wc, a.bc,
+                                                                                        redb, dfilm, dfilm_b_stride, a.film_off, gstat);
                 GW_LAUNCH_CHECK();
-                gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w,
-                                                                   d_gn_b, d_wc, d_bc);
+                gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w,
+                                                                   d_gn_b, d_wc, d_bc, 0, nullptr, nullptr, nullptr, L, nullptr);
                 GW_LAUNCH_CHECK();
                 return reduce_rows(biasp, B * G, C, C, 1.0f, d_conv_bias, 1, st);
             }
@@ -883,43 +898,18 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
         }
     }
     const int n_rc = gw_cdiv(L, a.rows_per_cta), n_tr = 256 / (C / 4);
-    float* partial = scratch;
-    float* redb = partial + (size_t)B * n_rc * C * nvr;
-    float* gstat = redb + (size_t)B * C * nvr;
-    dim3 grid(n_rc, B);
-    const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
     // bf16 with friendly shapes: HBM-streaming kernels (stream_gn.cu), same partial layouts
     const bool stream_ok = FAST && g_gn_bwd_stream && L % 4 == 0 && (C == 64 || C == 128 || C == 256) &&
                            a.rows_per_cta == gn_bwd_stream_rows(L, C);
-    if (FAST && stream_ok && g_gn_bwd_chunk > 0 && a.do_eps == nullptr && B > g_gn_bwd_chunk) {
-        // experiment: sub-batches small enough that the second pass finds its operands in the L2
-        const size_t esz = 2;
-        for (int b0 = 0; b0 < B; b0 += g_gn_bwd_chunk) {
-            const int Bc = B - b0 < g_gn_bwd_chunk ? B - b0 : g_gn_bwd_chunk;
-            GnBwdArgs c = a;
-            c.raw = (const char*)a.raw + (size_t)b0 * L * C * esz;
-            c.stats = a.stats + (size_t)b0 * 16;
-            if (a.cond) c.cond = a.cond + (size_t)b0 * L * Cc;
-            c.film = a.film + (size_t)b0 * a.film_b_stride;
-            if (a.do_a) c.do_a = (const char*)a.do_a + (size_t)b0 * L * C * esz;
-            if (a.do_pool) c.do_pool = (const char*)a.do_pool + (size_t)b0 * (L / 2) * C * esz;
-            float* pc = partial + (size_t)b0 * n_rc * C * nvr;
-            int rcs = gn_bwd_stats_stream(c, Bc, pc, st);
-            if (rcs != GW_OK) return rcs;
-            gn_bwd_finalize_kernel<<<Bc, 1024, (size_t)C * nvr * sizeof(float), st>>>(
-                pc, n_rc, C, nvr, L, a.gn_w, a.wc, a.bc, redb + (size_t)b0 * C * nvr, dfilm + (size_t)b0 * dfilm_b_stride,
-                dfilm_b_stride, a.film_off, gstat + (size_t)b0 * 16);
-            GW_LAUNCH_CHECK();
-            rcs = gn_bwd_apply_stream(c, Bc, gstat + (size_t)b0 * 16, (char*)d_raw + (size_t)b0 * L * C * esz, pc, st);
-            if (rcs != GW_OK) return rcs;
-            rcs = reduce_rows(pc, Bc * n_rc, C, C, 1.0f, d_conv_bias, 1, st);
-            if (rcs != GW_OK) return rcs;
-        }
-        gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
-                                                           d_wc, d_bc);
-        GW_LAUNCH_CHECK();
-        return GW_OK;
-    }
+    // compile-time-specialised streaming kernels: the sums pass also delivers sum_l xhat per channel (one more value per
+    // channel), from which gn_bwd_param_kernel forms the conv-bias gradient without partials from the apply pass
+    const bool sx = stream_ok && gn_bwd_stream_fast_ok(a);
+    const int nvs = nvr + (sx ? 1 : 0);
+    float* partial = scratch;
+    float* redb = partial + (size_t)B * n_rc * C * nvs;
+    float* gstat = redb + (size_t)B * C * nvs;
+    dim3 grid(n_rc, B);
+    const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
 #define GNB_GO(CCV)                                                                                                       \
     do {                                                                                                                  \
         if (FAST && stream_ok) {                                                                                          \
@@ -942,12 +932,14 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     else GNB_GO(-1);
 #undef GNB_GO
     GW_LAUNCH_CHECK();
-    gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvr * sizeof(float), st>>>(partial, n_rc, C, nvr, L, a.gn_w, a.wc, a.bc, redb, dfilm,
-                                                                            dfilm_b_stride, a.film_off, gstat);
+    gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvs * sizeof(float), st>>>(partial, n_rc, C, nvs, Cc, L, a.gn_w, a.wc, a.bc, redb,
+                                                                            dfilm, dfilm_b_stride, a.film_off, gstat);
     GW_LAUNCH_CHECK();
-    gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
-                                                       d_wc, d_bc);
+    gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+                                                       d_wc, d_bc, sx ? 1 : 0, a.stats, gstat, a.gn_w, L, d_conv_bias);
     GW_LAUNCH_CHECK();
+    if (sx)                                                  // no bias partials, no reduce launches
+        return gn_bwd_apply_stream(a, B, gstat, d_raw, nullptr, st);
     // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
 #define GNA_GO(CCV) gn_bwd_apply_kernel<T, FAST, CCV><<<grid, 256, sm2, st>>>(a, gstat, (T*)d_raw, partial)
     if (FAST && stream_ok) {

@@ -246,6 +246,9 @@ extern "C" int gw_gn_apply_stream(const void* raw, const float* part, int n_part
 #include "gn_bwd.cuh"
 
 int g_gn_bwd_stats_fast = 1;
+bool gn_bwd_stream_fast_ok(const GnBwdArgs& a) {
+    return g_gn_bwd_stats_fast && a.do_eps == nullptr && a.do_a != nullptr && (a.Cc == 1 || a.Cc == 5);
+}
 int gn_bwd_stream_rows(int L, int C) {
     const int S = SG_STAGE_BYTES / (C * 2);
     int rows = 8 * S;
@@ -441,7 +444,7 @@ template <int C, int CC, bool POOL>
 __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
     constexpr int S = SG_STAGE_BYTES / (C * 2);                       // rows per stage
     constexpr int NQ = C / 4, NTR = 256 / NQ, RPT = S / NTR;          // channel quads, row lanes, rows per thread and stage
-    constexpr int NV = 4 + CC;
+    constexpr int NV = 5 + CC;                                        // [sum do, sum do*act, sum dn, sum dn*xhat, cond.., sum xhat]
     constexpr uint32_t OFF_DO = SG_STAGE_BYTES, OFF_POOL = 2 * SG_STAGE_BYTES;
     constexpr uint32_t OFF_COND = OFF_POOL + (POOL ? SG_STAGE_BYTES / 2 : 0);
     static_assert(RPT * NTR == S && NTR % 2 == 0, "stage geometry");
@@ -512,6 +515,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, 
             acc[h][3] = ffma2(dn, xh, acc[h][3]);
 #pragma unroll
             for (int j = 0; j < CC; ++j) acc[h][4 + j] = ffma2(dv, pkf2(cv[j], cv[j]), acc[h][4 + j]);
+            acc[h][4 + CC] = fadd2(acc[h][4 + CC], xh);
         }
     };
     const uint32_t t_off = (uint32_t)(tr * C + quad * 4) * 2;          // my quad in row tr of a stage
@@ -817,6 +821,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, 
         }
     }
     if (threadIdx.x == 0) tma_wait_read<0>();
+    if (partial_bias == nullptr) return;                              // conv-bias gradient formed analytically (gn_bwd_param_kernel)
     __syncthreads();
     float* red = reinterpret_cast<float*>(smem);
 #pragma unroll
@@ -846,7 +851,9 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     if (smem < red_bytes) smem = red_bytes;
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
     const bool head = a.do_eps != nullptr;
-    if (g_gn_bwd_stats_fast && !head && a.do_a != nullptr && (Cc == 1 || Cc == 5)) {
+    if (gn_bwd_stream_fast_ok(a)) {
+        const size_t red_fast = (size_t)n_tr * C * (nvr + 1) * sizeof(float);
+        if (smem < red_fast) smem = red_fast;
         const bool pool = a.do_pool != nullptr;
 #define SGF_GO(CV, CCV, PL)                                                                                                 \
     do {                                                                                                                    \
@@ -893,7 +900,7 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
     const int depth = lay.stage > 20000 ? 2 : 3;        // + 16 KB of output staging: <= 75 KB per CTA, three CTAs per SM
     const size_t smem = (size_t)depth * lay.stage + 2 * SG_STAGE_BYTES + 64;
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
-    if (g_gn_bwd_stats_fast && a.do_eps == nullptr && a.do_a != nullptr) {
+    if ((g_gn_bwd_stats_fast && a.do_eps == nullptr && a.do_a != nullptr) || partial_bias == nullptr) {
         const bool pool = a.do_pool != nullptr;
 #define SGA_GO(CV, PL)                                                                                                      \
     do {                                                                                                                    \

@@ -50,7 +50,7 @@ class _GradWorkspace:
         cat_max = max(ws.lay_len[d + 1 + i] * (lc[d + i] + spec.chs[d - 1 - i]) for i in range(d))
         self.d_cat = e(cat_max) if simt else None
         n_scr = max(lib.gw_gn_bwd_scratch_elems(B, ws.lay_len[i], lc[i], spec.cond_in_ch) for i in range(2 * d + 1))
-        n_scr = max(n_scr, B * ((ws.L + 511) // 512) * ((lc[-1] + 1) * 3 + 1), B * spec.base_ch,
+        n_scr = max(n_scr, B * ((ws.L + 511) // 512) * ((lc[-1] + 1) * 3 + 1), B * spec.base_ch * (1 + (spec.film_dim + 95) // 96),
                     B * ((ws.L + 511) // 512) * lc[0] * spec.in_ch * 3)
         wmax = max(lc[i] * ((lc[i - 1] + (spec.chs[2 * d - i] if i > d else 0)) * 3) for i in range(1, 2 * d + 1))
         self.wg_elems = max(16 * wmax, 8 << 20)                           # split-K partials of the SIMT / tcgen05 wgrad
@@ -85,6 +85,7 @@ class BackwardEngine:
         self.wgrad_impl = "tc" if eng.conv_impl == "tc" else "simt"
         self.wgrad_variant = 0
         self.fuse_head = False
+        self._prepped = False                        # True while the caller has already run prepare_dgrad() for this step
         # bf16: one-pass GroupNorm backward (gn_bwd_fused.cu).  Reads every operand once (3.5 instead of 5.5 tensor passes) but
         # measured slower on B200 (1.90 vs 1.13 ms per step at B=256, L=4096): a slice stays in shared memory for load +
         # sums + exchange + apply + store (~8 us), and 228 KB per SM cannot cover that latency at HBM rate.  Parity-tested option.
@@ -114,6 +115,68 @@ class BackwardEngine:
         return eps_out
 
     # ------------------------------------------------------------------ backward
+    # ------------------------------------------------------------------ dgrad weights (depend on the parameters only)
+    def _layer_io(self, li: int, ws: _Workspace):
+        d = self.eng.spec.depth
+        if li <= d:
+            return ws.pooled[li - 1], None
+        return ws.out[li - 1], ws.out[2 * d - li]
+
+    def _dgrad_tc_ok(self, li: int, ws: _Workspace) -> bool:
+        src0, src1 = self._layer_io(li, ws)
+        _, L, Cout = ws.raw[li].shape
+        C0, L0 = src0.shape[2], src0.shape[1]
+        C1 = src1.shape[2] if src1 is not None else 0
+        return (self.eng.dtype == "bf16" and (src1 is None or (L % 2 == 0 and L0 * 2 == L)) and Cout <= 256 and C0 <= 256
+                and C1 <= 256)
+
+    def _dgrad_parts(self, li: int, ws: _Workspace):
+        """(conv shape, first row of the dgrad weight matrix) per dgrad GEMM of layer li: plain conv for pooled / skip inputs,
+        pair-sum mode through the nearest upsample."""
+        src0, src1 = self._layer_io(li, ws)
+        B, L, Cout = ws.raw[li].shape
+        C0 = src0.shape[2]
+
+        def plain(cout_):                     # 64 output channels: evaluate in pair space to fill a 128-column tile
+            return ConvTcShape(1, 3 if (cout_ == 64 and L % 2 == 0) else 0, B, L, Cout, L, 0, cout_)
+        if src1 is None:
+            return [(plain(C0), 0)]
+        return [(ConvTcShape(1, 2, B, L // 2, Cout, L, 0, C0), 0), (plain(src1.shape[2]), C0)]
+
+    def _prep_dgrad_layer(self, li: int, ws: _Workspace) -> None:
+        """w'[ci][co][k] = w[co][ci][2-k] (+ the bf16 GEMM packing for the tcgen05 dgrad) of conv li."""
+        eng, lib = self.eng, self.lib
+        st = _cabi.stream_ptr()
+        name = eng.spec.layer_names()[li]
+        src0, src1 = self._layer_io(li, ws)
+        _, L, Cout = ws.raw[li].shape
+        Cin = src0.shape[2] + (src1.shape[2] if src1 is not None else 0)
+        w = eng.p[name + ".0.weight"]
+        wt = self._wt.get(li)
+        if wt is None:
+            wt = torch.empty(w.numel(), device=eng.device, dtype=torch.float32)
+            self._wt[li] = wt
+        check(lib.gw_weight_dgrad(ptr(w), Cout, Cin, ptr(wt), st), "weight_dgrad")
+        eng.launches += 1
+        if self.dgrad_impl == "tc" and self._dgrad_tc_ok(li, ws):
+            for pi, (shp, row0) in enumerate(self._dgrad_parts(li, ws)):
+                key = (li, pi, L)
+                packed = self._dg_packed.get(key)
+                if packed is None:
+                    n = lib.gw_conv_tc_packed_elems(C.byref(shp))
+                    if n <= 0:
+                        raise RuntimeError("gw_conv_tc_packed_elems(dgrad): " + lib.gw_last_error().decode())
+                    packed = torch.empty(n, device=eng.device, dtype=torch.bfloat16)
+                    self._dg_packed[key] = packed
+                check(lib.gw_conv_tc_pack(C.byref(shp), wt.data_ptr() + 4 * row0 * Cout * 3, ptr(packed), st), "conv_tc_pack(dgrad)")
+                eng.launches += 1
+
+    def prepare_dgrad(self, ws: _Workspace) -> None:
+        """All layers' dgrad weights on the CURRENT stream.  They depend on the parameters only, so a caller may run this on a
+        side stream next to the forward pass and set `_prepped` around `backward` (FusedTrainStep._enqueue)."""
+        for li in range(1, 2 * self.eng.spec.depth + 1):
+            self._prep_dgrad_layer(li, ws)
+
     def _conv_bwd(self, li: int, ws: _Workspace, g: _GradWorkspace, grads: Dict[str, Tensor], d_in0: Tensor,
                   d_in1: Optional[Tensor]) -> None:
         """wgrad + dgrad of conv `li` (>= 1) given g.d_raw.  d_in0 receives the gradient wrt src0 (the pooled tensor, or h
@@ -147,36 +210,17 @@ class BackwardEngine:
                                      ptr(g.scratch), g.wg_elems, ptr(dW), st), f"wgrad3_simt[{name}]")
             eng.launches += 2
         # dgrad = the same conv with flipped / transposed weights (conv_transpose of a stride-1 'same' conv)
-        w = eng.p[name + ".0.weight"]
-        wt = self._wt.get(li)
-        if wt is None:
-            wt = torch.empty(w.numel(), device=eng.device, dtype=torch.float32)
-            self._wt[li] = wt
-        check(lib.gw_weight_dgrad(ptr(w), Cout, C0 + C1, ptr(wt), st), "weight_dgrad")
+        if not self._prepped:
+            self._prep_dgrad_layer(li, ws)
+        wt = self._wt[li]
         if self.dgrad_impl == "tc" and tc_ok:
-            # (shape, first row of the dgrad weight matrix, destination): plain conv for pooled / skip inputs, pair-sum
-            # mode through the nearest upsample
-            def plain(cout_):                 # 64 output channels: evaluate in pair space to fill a 128-column tile
-                return ConvTcShape(1, 3 if (cout_ == 64 and L % 2 == 0) else 0, B, L, Cout, L, 0, cout_)
-            if src1 is None:
-                parts = [(plain(C0), 0, d_in0)]
-            else:
-                parts = [(ConvTcShape(1, 2, B, L // 2, Cout, L, 0, C0), 0, d_in0), (plain(C1), C0, d_in1)]
-            for pi, (shp, row0, dst) in enumerate(parts):
-                key = (li, pi, L)
-                packed = self._dg_packed.get(key)
-                if packed is None:
-                    n = lib.gw_conv_tc_packed_elems(C.byref(shp))
-                    if n <= 0:
-                        raise RuntimeError("gw_conv_tc_packed_elems(dgrad): " + lib.gw_last_error().decode())
-                    packed = torch.empty(n, device=eng.device, dtype=torch.bfloat16)
-                    self._dg_packed[key] = packed
-                check(lib.gw_conv_tc_pack(C.byref(shp), wt.data_ptr() + 4 * row0 * Cout * 3, ptr(packed), st), "conv_tc_pack(dgrad)")
+            dsts = [d_in0] if src1 is None else [d_in0, d_in1]
+            for pi, (shp, row0) in enumerate(self._dgrad_parts(li, ws)):
+                packed = self._dg_packed[(li, pi, L)]
                 variant = eng.tc_variant if (shp.Cout >= 128 or shp.pair == 3) else 0
-                check(lib.gw_conv_tc(C.byref(shp), ptr(g.d_raw), None, ptr(packed), None, ptr(dst), None, variant, st),
+                check(lib.gw_conv_tc(C.byref(shp), ptr(g.d_raw), None, ptr(packed), None, ptr(dsts[pi]), None, variant, st),
                       f"dgrad_tc[{name}.{pi}]")
-                eng.launches += 2
-            eng.launches += 1
+                eng.launches += 1
             return
         dst = d_in0 if src1 is None else g.d_cat
         check(lib.gw_conv3_simt(ptr(g.d_raw), Cout, L, 0, None, 0, B, L, ptr(wt), None, C0 + C1, ptr(dst), eng.gw_dtype, None,
@@ -434,6 +478,8 @@ class FusedTrainStep:
         self.ab, self.sab, self.s1mab = ab, ab.sqrt().contiguous(), (1 - ab).sqrt().contiguous()
         self.steps_done = 0
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.overlap_prep = True                     # dgrad weight preparation on a forked stream / graph branch
+        self._side: Optional[torch.cuda.Stream] = None
 
     # ------------------------------------------------------------------ host -> device staging
     def prefetch(self, clean_norm: Tensor, cond_stack: Tensor, mask: Optional[Tensor] = None) -> None:
@@ -533,6 +579,15 @@ class FusedTrainStep:
             check(lib.gw_train_draws(self.seed, ptr(self.step_ctr), self.sample0, B, self.t_min, self.T, self.p_uncond,
                                      ptr(self.t), ptr(self.drop), st), "train_draws")
             eng.launches += 1
+        # fork: the dgrad weights depend on the parameters only -> a second stream (a parallel branch of the captured graph)
+        # prepares them while the forward pass runs; joined before the backward pass
+        cur = torch.cuda.current_stream()
+        if self.overlap_prep:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self.bwd.prepare_dgrad(eng.workspace(B, L, True))
         use_drop = self.p_uncond > 0.0
         y_only = self.dropout_y_only and Cc > 1
         check(lib.gw_train_pack(ptr(self.clean), ptr(self.cond) if Cc > 0 else None, Cc, ptr(self.t),
@@ -551,7 +606,13 @@ class FusedTrainStep:
                           self.huber_beta, 1.0, ptr(self.per_sample), ptr(self.loss), ptr(self.d_eps), st), "loss")
         eng.launches += 2
         self.flat_g.zero_()
-        self.bwd.backward(self.net, self.d_eps, self.flat_g)
+        if self.overlap_prep:
+            cur.wait_stream(self._side)
+        self.bwd._prepped = self.overlap_prep
+        try:
+            self.bwd.backward(self.net, self.d_eps, self.flat_g)
+        finally:
+            self.bwd._prepped = False
 
     def _enqueue_update(self) -> None:
         lib, st = self.lib, _cabi.stream_ptr()

@@ -31,6 +31,8 @@ extern "C" {
 
 int gw_version(void);
 /* runtime switches for A/B measurements: "gn_bwd_stream" (1 = HBM-streaming GroupNorm backward kernels, default),
+ * "gn_bwd_stats_fast" (1 = their compile-time-specialised versions + analytic conv-bias gradient, default),
+ * "gn_bwd_fused" / "gn_bwd_fused_slice" (one-pass GroupNorm backward of gw_gn_bwd2: enable, largest shared-memory slice in bytes),
  * "final_stream" (1 = HBM-streaming head + update kernel for bf16 / C = 64, default) */
 int gw_set_option(const char* name, int value);
 const char* gw_last_error(void);
@@ -264,7 +266,8 @@ int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, int L, int Co
                 float* scratch, long scratch_elems, float* dW, int variant, void* stream);
 
 /* time_mlp / tproj_* backward (models.py:105-109, 137-142): dfilm [B, F] (written by gw_gn_bwd), aux from
- * gw_film_vectors; accumulates dW1 [base, time_dim], db1 [base], dW2 [F, base], db2 [F]; scratch >= B*base floats. */
+ * gw_film_vectors; accumulates dW1 [base, time_dim], db1 [base], dW2 [F, base], db2 [F];
+ * scratch >= B*base*(1 + ceil(F/96)) floats (the split-K partials of dfilm x W2). */
 int gw_film_bwd(const float* dfilm, const float* aux, const float* w2, int B, int time_dim, int base, int F,
                 float* scratch, float* dW1, float* db1, float* dW2, float* db2, void* stream);
 

@@ -93,3 +93,22 @@ def test_one_pass_gn_backward_matches_two_pass(in_ch, cc, B, L, slice_bytes):
     for k in ref:
         err = float((got[k].double() - ref[k].double()).norm())
         assert err <= 5e-3 * max(float(ref[k].norm()), 1e-2 * tot), (k, err, float(ref[k].norm()))
+
+
+@pytest.mark.parametrize("in_ch,cc,B,L", [(7, 5, 2, 4096), (3, 1, 3, 1024), (3, 1, 5, 200)])
+def test_specialised_gn_backward_matches_generic(in_ch, cc, B, L):
+    """Compile-time-specialised streaming GroupNorm-backward kernels (+ the conv-bias gradient formed analytically from
+    sum_l xhat instead of summing the bf16-rounded d_raw) against the generic streaming kernels."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.gw_set_option(b"gn_bwd_stats_fast", 0) == 0
+    try:
+        ref, loss_ref = _run_gn(in_ch, cc, B, L, False)
+    finally:
+        lib.gw_set_option(b"gn_bwd_stats_fast", 1)
+    got, loss_got = _run_gn(in_ch, cc, B, L, False)
+    assert abs(loss_ref - loss_got) <= 1e-4 * abs(loss_ref)
+    tot = float(torch.cat([v.reshape(-1) for v in ref.values()]).norm())
+    for k in ref:
+        err = float((got[k].double() - ref[k].double()).norm())
+        assert err <= 5e-3 * max(float(ref[k].norm()), 1e-2 * tot), (k, err, float(ref[k].norm()))

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--wgrad-variant", type=int, default=-1)
     ap.add_argument("--fuse-gn-bwd", type=int, default=-1, help="1/0: one-pass GroupNorm backward on/off (default: library default)")
     ap.add_argument("--opt", action="append", default=[], help="name=value for gw_set_option (repeatable)")
+    ap.add_argument("--overlap-prep", type=int, default=-1, help="1/0: dgrad weight preparation on a forked stream")
     ap.add_argument("--only", default=None, help="print only launches whose name contains this")
     a = ap.parse_args()
     cc = 1 if a.cin == 3 else 5
@@ -49,6 +50,8 @@ def main():
         st.bwd.wgrad_variant = a.wgrad_variant
     if a.fuse_gn_bwd >= 0:
         st.bwd.fuse_gn_bwd = bool(a.fuse_gn_bwd)
+    if a.overlap_prep >= 0:
+        st.overlap_prep = bool(a.overlap_prep)
     for o in a.opt:
         k, v = o.split("=")
         assert st.lib.gw_set_option(k.encode(), int(v)) == 0, o

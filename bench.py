@@ -126,9 +126,9 @@ class TimedLib:
 
 
 def measured_traffic(step_kind, kernel, B, L):
-    """Per-launch DRAM traffic of `kernel` from the committed ncu capture (profiles/r01g_traffic.json); only valid for the
+    """Per-launch DRAM traffic of `kernel` from the committed ncu capture (profiles/r01j_traffic.json); only valid for the
     shape it was captured at (B=256, L=4096), otherwise None."""
-    p = os.path.join(ROOT, "profiles", "r01i_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r01j_traffic.json")
     if not os.path.exists(p) or (B, L) != (256, 4096):
         return None
     d = json.load(open(p)).get(step_kind, {}).get(kernel)
@@ -189,12 +189,12 @@ def family_rooflines(records, spec, B, L, pk, n_steps, train):
         add("conv fwd + dgrad (tcgen05 implicit GEMM)", ["gw_conv_tc"], "tensor", conv_fl * (n_fwd + 1.0),
             "2*Cin*Cout*3*L*B per conv, forward(s) + dgrad")
         add("wgrad (tcgen05 MN-major GEMM)", ["gw_wgrad_tc"], "tensor", conv_fl, "2*Cin*Cout*3*L*B per conv")
-        add("GroupNorm/SiLU/cond/FiLM backward", ["gw_gn_bwd"], "hbm", gn_bwd_bytes,
+        add("GroupNorm/SiLU/cond/FiLM backward", ["gw_gn_bwd", "gw_gn_bwd2"], "hbm", gn_bwd_bytes,
             "bf16: 2 passes over (raw, dout[, dpool/2]) + d_raw write per block")
     else:
         # inference: one kernel per block does the conv AND the GroupNorm/SiLU/cond/FiLM/pool epilogue (conv_gn.cuh); its
         # roofline counts the conv FLOPs only, against the time of the whole fused kernel
-        add("fused conv block (tcgen05 implicit GEMM + GroupNorm/SiLU/cond/FiLM/pool epilogue)", ["gw_conv_gn"], "tensor",
+        add("fused conv block (tcgen05 implicit GEMM + GroupNorm/SiLU/cond/FiLM/pool epilogue)", ["gw_conv_gn", "gw_conv_gn2"], "tensor",
             conv_fl, "2*Cin*Cout*3*L*B per conv (the fused elementwise work is not counted)")
         add("conv fwd (tcgen05 implicit GEMM)", ["gw_conv_tc"], "tensor", conv_fl, "2*Cin*Cout*3*L*B per conv")
     gn_keys = [k for k in ("gw_gn_apply", "gw_gn_apply_stream") if k in t_by]
@@ -426,11 +426,11 @@ def bench_sampling(args, workload, B, steps, warmup, world, rank, dev, barrier, 
                "roofline": {"bound": "tensor",
                             "kernel": "conv_gn_kernel (6 launches per reverse step: tcgen05+TMA implicit GEMM with the "
                                       "GroupNorm/SiLU/cond/FiLM/pool epilogue fused in)"
-                            if conv["entry_points"] == ["gw_conv_gn"] else "conv_tc2_kernel (tcgen05+TMA implicit GEMM)",
+                            if "gw_conv_gn" in conv["entry_points"] else "conv_tc2_kernel (tcgen05+TMA implicit GEMM)",
                             "achieved": conv["achieved"], "peak": pk["bf16"], "unit": "TFLOP/s", "frac": conv["frac"],
-                            "traffic": measured_traffic("reverse_step", "conv_gn_kernel" if conv["entry_points"] == ["gw_conv_gn"]
+                            "traffic": measured_traffic("reverse_step", "conv_gn_kernel" if "gw_conv_gn" in conv["entry_points"]
                                                         else "conv_tc2_kernel", plan.Bn, L),
-                            "traffic_note": "bytes per launch, ncu capture profiles/r01i_traffic.json (B=256, L=4096, in_ch=3)",
+                            "traffic_note": "bytes per launch, ncu capture profiles/r01j_traffic.json (B=256, L=4096, in_ch=3)",
                             "peak_source": pk["src"] + " burst (kernels timed one by one)",
                             "share_of_step": conv["share_of_step"]},
                "kernels": fams,
@@ -545,7 +545,7 @@ def bench_train(args, world, rank, dev, barrier, pk):
             "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel family (forward convs + dgrad, tcgen05+TMA implicit GEMM)",
                          "achieved": conv["achieved"], "peak": pk["bf16"], "unit": "TFLOP/s", "frac": conv["frac"],
                          "traffic": measured_traffic("train_step", "conv_tc2_kernel", B, L),
-                         "traffic_note": "bytes per launch, ncu capture profiles/r01g_traffic.json (B=256, L=4096, in_ch=7)",
+                         "traffic_note": "bytes per launch, ncu capture profiles/r01j_traffic.json (B=256, L=4096, in_ch=7)",
                          "peak_source": pk["src"] + " burst (kernels timed one by one, eager)",
                          "share_of_step": conv["share_of_step"]},
             "kernels": fams,

@@ -109,6 +109,11 @@ def load() -> C.CDLL:
         fn.argtypes = args
         fn.restype = res
     _lib = lib
+    # A/B switches for measurements, e.g. GWB200_OPTIONS="pdl=0,gn_bwd_stats_fast=0" (see gw_set_option in include/gwb200.h)
+    for kv in filter(None, os.environ.get("GWB200_OPTIONS", "").split(",")):
+        k, v = kv.split("=")
+        if lib.gw_set_option(k.strip().encode(), int(v)) != 0:
+            raise RuntimeError("GWB200_OPTIONS: " + lib.gw_last_error().decode())
     return lib
 
 

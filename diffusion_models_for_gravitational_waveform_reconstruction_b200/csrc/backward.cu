@@ -847,6 +847,7 @@ extern "C" int gw_set_option(const char* name, int value) {
     if (strcmp(name, "gn_bwd_fused") == 0) { g_gn_bwd_fused = value; return GW_OK; }
     if (strcmp(name, "gn_bwd_fused_slice") == 0) { g_gn_bwd_fused_slice = value; return GW_OK; }
     if (strcmp(name, "final_stream") == 0) { g_final_stream = value; return GW_OK; }
+    if (strcmp(name, "pdl") == 0) { g_pdl = value; return GW_OK; }
     gw_set_error("gw_set_option: unknown option %s", name);
     return GW_ERR_ARG;
 }

@@ -212,3 +212,29 @@ struct Philox {
         }
     }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): consecutive kernels of the sampler's reverse step are launched with the programmatic
+// stream-serialization attribute, so a kernel's CTAs may start (as SMs free up) and run their prologue -- barrier init, TMEM
+// allocation, weight staging -- while the previous kernel drains; pdl_wait() blocks until the previous grid has completed and its
+// writes are visible, and must precede the first access to anything the previous kernel wrote.  Both are no-ops in a kernel
+// launched without the attribute.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl;      // forward.cu; gw_set_option("pdl", 0/1)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gw_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

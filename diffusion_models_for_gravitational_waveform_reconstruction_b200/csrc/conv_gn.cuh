@@ -297,6 +297,10 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched parameters only; the activations, the exchange buffer and the step counter belong to the previous
+    // kernel of the stream (PDL, common.cuh)
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -759,7 +763,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
 #define CGN_GO(LG, MTV, CCV, PL)                                                                                          \
     do {                                                                                                                  \
         GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<LG, MTV, CCV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        conv_gn_kernel<LG, MTV, CCV, PL><<<grid, CGN_THREADS, smem, st>>>(ta0, ta1, tw, to, tr, tp, P, F, bias);                   \
+        GW_CUDA(gw_launch_pdl(conv_gn_kernel<LG, MTV, CCV, PL>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
     } while (0)
 #define CGN_CC(LG, MTV, PL)                      \
     do {                                         \
@@ -770,7 +774,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
 #define CGN_GOH(CCV)                                                                                                      \
     do {                                                                                                                  \
         GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<3, 2, CCV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        conv_gn_kernel<3, 2, CCV, false, true><<<grid, CGN_THREADS, smem, st>>>(ta0, ta1, tw, to, tr, tp, P, F, bias);     \
+        GW_CUDA(gw_launch_pdl(conv_gn_kernel<3, 2, CCV, false, true>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
     } while (0)
     if (pl.lg == 3 && head) {
         if (Cc == 1) CGN_GOH(1);

@@ -79,9 +79,6 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
     const int oct = lane & 7;                            // conv: my 8 output channels = GroupNorm group `oct`
     const int pg = warp * 4 + (lane >> 3);               // conv: position group (4 positions) inside a 128-position block
     unsigned int* ctrl = reinterpret_cast<unsigned int*>(A.sync);
-    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctrl) + 1u;
-    const int step = A.step_ptr != nullptr ? *A.step_ptr : 0;
-    const float* x = (step & 1) ? A.xb : A.xa;
 
     // weights as [ck][half][octet][4]: the 8 octet lanes of a quarter-warp read 8 consecutive float4 (no bank conflicts)
     auto split = [](int co) { return ((co >> 2) & 1) * (C / 2) + (co >> 3) * 4 + (co & 3); };
@@ -114,6 +111,12 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
     const int ao = tid & 7;
     const double inv_n = 1.0 / (8.0 * (double)L);
     __syncthreads();
+    // parameters only so far; the input, the exchange buffer and the step counter belong to the previous kernel (PDL, common.cuh)
+    pdl_wait();
+    pdl_launch_dependents();
+    const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(ctrl) + 1u;
+    const int step = A.step_ptr != nullptr ? *A.step_ptr : 0;
+    const float* x = (step & 1) ? A.xb : A.xa;
 
     // input staging: x[b, c, l00-1 .. l00+ROWS] -> xs; the NEXT sample's values are fetched into registers before phase 2 so
     // that their HBM latency is hidden behind it
@@ -438,7 +441,7 @@ extern "C" int gw_conv_in_gn(const float* x, const float* x_alt, const int* step
         A.n_groups = occ * cig_sm_count() / G;                                                                           \
         if (A.n_groups > B) A.n_groups = B;                                                                              \
         GW_REQUIRE(A.n_groups >= 1, "gw_conv_in_gn: a sample needs more CTAs than fit on the GPU");                      \
-        conv_in_gn_kernel<CCV, ROWSV><<<G * A.n_groups, 256, smem, st>>>(A);                                             \
+        GW_CUDA(gw_launch_pdl(conv_in_gn_kernel<CCV, ROWSV>, dim3(G * A.n_groups), dim3(256), smem, st, A));             \
     } while (0)
 #define CIG_ROWS_GO(CCV)                      \
     do {                                      \

@@ -1243,6 +1243,8 @@ __global__ void __launch_bounds__(256) final_step_dots_kernel(const float4* __re
                                                               int* __restrict__ step_ptr, const float* __restrict__ noise,
                                                               float* __restrict__ eps_out, float* __restrict__ x0_out) {
     const int b = blockIdx.y, l4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    pdl_wait();                                                       // the dots and the step counter come from the previous kernels
+    pdl_launch_dependents();
     const int step = step_ptr != nullptr ? *step_ptr : 0;
     if (l4 < L) {
     const float* net_in = (step & 1) ? net_b : net_a;
@@ -1318,8 +1320,8 @@ int final_step_dots(const void* dots, const float* net_a, const float* net_b, in
     a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
     a.advance = (p->mode == 1 && step_ptr != nullptr) ? (unsigned int*)p->advance : nullptr;
     dim3 grid(gw_cdiv(L, 1024), B);
-    final_step_dots_kernel<<<grid, 256, 0, st>>>((const float4*)dots, net_a, net_b ? net_b : net_a, B, Cx, L, wf, bf, C, a, coef,
-                                                 const_cast<int*>(step_ptr), noise, eps_out, x0_out);
+    GW_CUDA(gw_launch_pdl(final_step_dots_kernel, grid, dim3(256), (size_t)0, st, (const float4*)dots, net_a, net_b ? net_b : net_a, B,
+                          Cx, L, wf, bf, C, a, coef, const_cast<int*>(step_ptr), noise, eps_out, x0_out));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

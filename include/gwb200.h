@@ -33,7 +33,9 @@ int gw_version(void);
 /* runtime switches for A/B measurements: "gn_bwd_stream" (1 = HBM-streaming GroupNorm backward kernels, default),
  * "gn_bwd_stats_fast" (1 = their compile-time-specialised versions + analytic conv-bias gradient, default),
  * "gn_bwd_fused" / "gn_bwd_fused_slice" (one-pass GroupNorm backward of gw_gn_bwd2: enable, largest shared-memory slice in bytes),
- * "final_stream" (1 = HBM-streaming head + update kernel for bf16 / C = 64, default) */
+ * "final_stream" (1 = HBM-streaming head + update kernel for bf16 / C = 64, default),
+ * "pdl" (1 = the fused inference kernels are launched with programmatic stream serialization, default: a kernel's prologue
+ *  overlaps the previous kernel's tail; every such kernel executes griddepcontrol.wait before it touches activations) */
 int gw_set_option(const char* name, int value);
 const char* gw_last_error(void);
 int gw_device_info(int* sm_count, int* cc_major, int* cc_minor);

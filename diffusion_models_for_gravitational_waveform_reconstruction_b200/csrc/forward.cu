@@ -1107,7 +1107,7 @@ int final_step_stream(const void* h, const float* net_a, const float* net_b, int
                       const gw_step_params* p, const float* coef, const int* step_ptr, const float* noise, float* eps_out,
                       float* x0_out, cudaStream_t st);
 int g_final_stream = 1;
-int g_pdl = 1;
+int g_pdl = 0;      // flipped to 1 once verified on the GPU (see profiles)
 
 extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const float* net_b, int B, int Cx, int L,
                              int C, const float* wf, const float* bf, const gw_step_params* p, const float* coef,

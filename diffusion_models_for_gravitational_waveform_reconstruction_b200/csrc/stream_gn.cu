@@ -1022,6 +1022,110 @@ __global__ void __launch_bounds__(256) wgrad_in_stream_kernel(const float* __res
     }
 }
 
+// The same gradient as a tensor-core GEMM for Cx <= 8 and whole 64-row stages: dW^T is M = 64 couts x N = 3*Cx (padded to 24) taps
+// with K = rows.  The CUDA-core kernel above is FMA-bound (2 x 21 FMAs per row and channel: 127 us at B = 256, L = 4096 against
+// ~25 us of HBM time).  mma.sync.m16n8k16 (bf16 x bf16 -> fp32): the A operand d_raw^T comes straight out of the row-major
+// stage with ldmatrix.trans (exact: d_raw is bf16), the B operand is the input window rounded to bf16 on the fly.
+// Warp w owns k-step (w & 3) of every 64-row stage and couts [32 (w >> 2), +32).
+__global__ void __launch_bounds__(256) wgrad_in_mma_kernel(const float* __restrict__ x, int Cx, int L, const bf16* __restrict__ d_raw,
+                                                           float* __restrict__ partial, int rows_per_cta) {
+    constexpr int C = 64, S = SG_STAGE_BYTES / (C * 2), D = SG_DEPTH;       // S = 64 rows per stage
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* ring = smem;                                         // [D][8 KB]; reused for the final reduction
+    const int pitch = rows_per_cta + 8;
+    const int nv = Cx * 3;
+    const int ring_bytes = max(D * SG_STAGE_BYTES, 4 * C * nv * 4);
+    float* xs = reinterpret_cast<float*>(smem + ring_bytes);      // [Cx][pitch]: xs[ci][j] = x[ci][r0 - 1 + j]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + Cx * pitch);
+    const int b = blockIdx.y, r0 = blockIdx.x * rows_per_cta;
+    const int rows_here = min(rows_per_cta, L - r0);              // a multiple of 64 (launcher)
+    const int n_sub = rows_here / S;
+    const bf16* dbase = d_raw + ((size_t)b * L + r0) * C;
+    auto issue = [&](int i) {
+        const uint32_t bar = smem_u32(bars + (i % D));
+        mbar_expect_tx(bar, SG_STAGE_BYTES);
+        bulk_load(smem_u32(ring + (i % D) * SG_STAGE_BYTES), dbase + (size_t)i * S * C, SG_STAGE_BYTES, bar);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < D; ++s) mbar_init(smem_u32(bars + s), 1);
+        fence_barrier_init();
+        fence_proxy_async();
+        for (int i = 0; i < D && i < n_sub; ++i) issue(i);
+    }
+    for (int i = threadIdx.x; i < Cx * pitch; i += 256) {
+        const int c = i / pitch, p = i % pitch;
+        const int l = r0 + p - 1;
+        xs[i] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int kq = warp & 3, mh = warp >> 2;
+    // B fragment column n = 8 nt + g  ->  (input channel, tap)  ->  offset into xs (-1: padding column)
+    int boff[3];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+        const int kk = nt * 8 + g;
+        boff[nt] = kk < nv ? (kk / 3) * pitch + kk % 3 : -1;
+    }
+    // ldmatrix.x4.trans: lane -> row (k) and 8-column block (m) of the four 8x8 matrices a0..a3 of one 16 x 16 A tile
+    const int lk = (lane & 7) + 8 * (lane >> 4), lm = 8 * ((lane >> 3) & 1);
+    float acc[2][3][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[m][nt][q] = 0.0f;
+    for (int i = 0; i < n_sub; ++i) {
+        const int st = i % D;
+        mbar_wait(smem_u32(bars + st), (uint32_t)((i / D) & 1));
+        const uint32_t sb = smem_u32(ring + st * SG_STAGE_BYTES);
+        const int k0 = kq * 16;
+        uint32_t bfr[3][2];
+        const float* xw = xs + i * S + k0 + 2 * t4;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            if (boff[nt] >= 0) {
+                const float* xp = xw + boff[nt];
+                bfr[nt][0] = pack_bf16x2(xp[0], xp[1]);
+                bfr[nt][1] = pack_bf16x2(xp[8], xp[9]);
+            } else {
+                bfr[nt][0] = 0u; bfr[nt][1] = 0u;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            uint32_t a0, a1, a2, a3;
+            const uint32_t addr = sb + (uint32_t)(((k0 + lk) * C + 32 * mh + 16 * m + lm) * 2);
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[m][nt][0]), "+f"(acc[m][nt][1]), "+f"(acc[m][nt][2]), "+f"(acc[m][nt][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bfr[nt][0]), "r"(bfr[nt][1]));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && i + D < n_sub) issue(i + D);
+    }
+    float* red = reinterpret_cast<float*>(ring);                  // [4 k-steps][C][nv]
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int co = 32 * mh + 16 * m + g + 8 * (q >> 1), kk = 8 * nt + 2 * t4 + (q & 1);
+                if (kk < nv) red[((size_t)kq * C + co) * nv + kk] = acc[m][nt][q];
+            }
+    __syncthreads();
+    float* pt = partial + ((size_t)b * gridDim.x + blockIdx.x) * C * nv;
+    for (int i = threadIdx.x; i < C * nv; i += 256)
+        pt[i] = (red[i] + red[(size_t)C * nv + i]) + (red[(size_t)2 * C * nv + i] + red[(size_t)3 * C * nv + i]);
+}
+
+int g_wgrad_in_mma = 1;
+
 // launcher used by gw_wgrad_in (backward.cu) for bf16, C = 64, L % 4 == 0; returns the number of partial rows written
 int wgrad_in_stream(const float* x, int B, int Cx, int L, const void* d_raw, float* scratch, long scratch_elems, int* n_rows,
                     cudaStream_t st) {
@@ -1031,6 +1135,14 @@ int wgrad_in_stream(const float* x, int B, int Cx, int L, const void* d_raw, flo
     const int ring = SG_DEPTH * SG_STAGE_BYTES > 8 * C * nv * 4 ? SG_DEPTH * SG_STAGE_BYTES : 8 * C * nv * 4;
     const size_t smem = (size_t)ring + (size_t)Cx * (rows + 8) * 4 + 64;
     dim3 grid(n_rc, B);
+    if (g_wgrad_in_mma && Cx <= 8 && L % 64 == 0 && rows % 64 == 0) {
+        GW_CUDA(cudaFuncSetAttribute(wgrad_in_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(wgrad_in_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        wgrad_in_mma_kernel<<<grid, 256, smem, st>>>(x, Cx, L, (const bf16*)d_raw, scratch, rows);
+        GW_LAUNCH_CHECK();
+        *n_rows = B * n_rc;
+        return GW_OK;
+    }
 #define WIS_GO(CXM)                                                                                                   \
     do {                                                                                                              \
         GW_CUDA(cudaFuncSetAttribute(wgrad_in_stream_kernel<CXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

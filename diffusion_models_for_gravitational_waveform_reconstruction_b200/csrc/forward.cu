@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(256) conv_in_mma_kernel(const float* __restric
                                                           bf16* __restrict__ raw, float* __restrict__ part, int n_part) {
     constexpr int C = 64, TP = 128, XP = CIN_NPB * TP + 8;
     extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l00 - 1 + j]
+    float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l00 - 4 + j] (16-byte aligned body at j = 4)
     float* wsf = xs + Cx * XP;                   // [KS][8 n-tiles][32 lanes][2] tf32 B fragments
     const int KS = (3 * Cx + 7) / 8;
     float* bs = wsf + KS * 512;                  // [C]
@@ -451,10 +451,31 @@ __global__ void __launch_bounds__(256) conv_in_mma_kernel(const float* __restric
     const int step = step_ptr != nullptr ? *step_ptr : 0;
     const float* x = (step & 1) ? xb : xa;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
-    for (int i = threadIdx.x; i < Cx * XP; i += 256) {
-        const int c = i / XP, p = i % XP;
-        const int l = l00 + p - 1;
-        xs[i] = (p < CIN_NPB * TP + 2 && l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+    // input staging: vector loads, all of a thread's loads in flight before the first store (the scalar div/mod loop of the
+    // CUDA-core kernel cost more than the MMAs: profiles/r01j_ncu_full_in_mma.md)
+    {
+        constexpr int Q = CIN_NPB * TP / 4;      // float4 per channel
+        constexpr int UNR = 4;
+        for (int i0 = threadIdx.x; i0 < Cx * Q; i0 += 256 * UNR) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * 256;
+                const int c = i / Q, l = l00 + 4 * (i % Q);
+                v[u] = (i < Cx * Q && l < L) ? *reinterpret_cast<const float4*>(x + ((size_t)b * Cx + c) * L + l)
+                                             : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * 256;
+                if (i < Cx * Q) *reinterpret_cast<float4*>(xs + (i / Q) * XP + 4 + 4 * (i % Q)) = v[u];
+            }
+        }
+        if (threadIdx.x < 2 * Cx) {              // the two halo positions of every channel
+            const int c = threadIdx.x >> 1, side = threadIdx.x & 1;
+            const int l = side ? l00 + CIN_NPB * TP : l00 - 1;
+            xs[c * XP + (side ? 4 + CIN_NPB * TP : 3)] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+        }
     }
     for (int i = threadIdx.x; i < KS * 512; i += 256) {
         const int j = i & 1, ln = (i >> 1) & 31, nt = (i >> 6) & 7, ks = i >> 9;
@@ -469,7 +490,7 @@ __global__ void __launch_bounds__(256) conv_in_mma_kernel(const float* __restric
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int kk = ks * 8 + t4 + 4 * j;
-            aoff[ks][j] = kk < 3 * Cx ? (kk / 3) * XP + kk % 3 : -1;
+            aoff[ks][j] = kk < 3 * Cx ? (kk / 3) * XP + kk % 3 + 3 : -1;
         }
     __syncthreads();
     const float2* wf2 = reinterpret_cast<const float2*>(wsf);
@@ -574,7 +595,7 @@ extern "C" int gw_conv_in(const float* x, const float* x_alt, const int* step_pt
     GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_conv_in: C=%d must be a multiple of 64 and <= 256", C);
     GW_REQUIRE(Cx >= 1 && Cx <= 16, "gw_conv_in: Cx=%d", Cx);
     GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_conv_in: dtype %d", dtype);
-    if (dtype == GW_BF16 && C == 64 && Cx <= 8 && g_conv_in_mma) {
+    if (dtype == GW_BF16 && C == 64 && Cx <= 8 && L % 4 == 0 && g_conv_in_mma) {
         constexpr int TP = 128, XP = CIN_NPB * TP + 8;
         const int KS = (3 * Cx + 7) / 8, n_part = gw_cdiv(L, TP);
         const size_t smem = (size_t)(Cx * XP + KS * 512 + C + 128) * sizeof(float);

@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(256) wgrad_in_mma_kernel(const float* __restri
     const int pitch = rows_per_cta + 8;
     const int nv = Cx * 3;
     const int ring_bytes = max(D * SG_STAGE_BYTES, 4 * C * nv * 4);
-    float* xs = reinterpret_cast<float*>(smem + ring_bytes);      // [Cx][pitch]: xs[ci][j] = x[ci][r0 - 1 + j]
+    float* xs = reinterpret_cast<float*>(smem + ring_bytes);      // [Cx][pitch]: xs[ci][j] = x[ci][r0 - 4 + j] (aligned body at j = 4)
     uint64_t* bars = reinterpret_cast<uint64_t*>(xs + Cx * pitch);
     const int b = blockIdx.y, r0 = blockIdx.x * rows_per_cta;
     const int rows_here = min(rows_per_cta, L - r0);              // a multiple of 64 (launcher)
@@ -1052,10 +1052,29 @@ __global__ void __launch_bounds__(256) wgrad_in_mma_kernel(const float* __restri
         fence_proxy_async();
         for (int i = 0; i < D && i < n_sub; ++i) issue(i);
     }
-    for (int i = threadIdx.x; i < Cx * pitch; i += 256) {
-        const int c = i / pitch, p = i % pitch;
-        const int l = r0 + p - 1;
-        xs[i] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+    {   // input staging with vector loads, a thread's loads all in flight before its first store
+        const int Q = rows_per_cta / 4;
+        constexpr int UNR = 4;
+        for (int i0 = threadIdx.x; i0 < Cx * Q; i0 += 256 * UNR) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * 256;
+                const int c = i / Q, l = r0 + 4 * (i % Q);
+                v[u] = (i < Cx * Q && l < L) ? *reinterpret_cast<const float4*>(x + ((size_t)b * Cx + c) * L + l)
+                                             : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * 256;
+                if (i < Cx * Q) *reinterpret_cast<float4*>(xs + (i / Q) * pitch + 4 + 4 * (i % Q)) = v[u];
+            }
+        }
+        if (threadIdx.x < 2 * Cx) {
+            const int c = threadIdx.x >> 1, side = threadIdx.x & 1;
+            const int l = side ? r0 + rows_per_cta : r0 - 1;
+            xs[c * pitch + (side ? 4 + rows_per_cta : 3)] = (l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
@@ -1065,7 +1084,7 @@ __global__ void __launch_bounds__(256) wgrad_in_mma_kernel(const float* __restri
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) {
         const int kk = nt * 8 + g;
-        boff[nt] = kk < nv ? (kk / 3) * pitch + kk % 3 : -1;
+        boff[nt] = kk < nv ? (kk / 3) * pitch + kk % 3 + 3 : -1;
     }
     // ldmatrix.x4.trans: lane -> row (k) and 8-column block (m) of the four 8x8 matrices a0..a3 of one 16 x 16 A tile
     const int lk = (lane & 7) + 8 * (lane >> 4), lm = 8 * ((lane >> 3) & 1);

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t
             v = i < half ? sinf(a) : cosf(a);
         }
         emb[idx] = v;
-        if (aux != nullptr && n0 + s < n) aux[(size_t)(n0 + s) * na + i] = v;
+        if (aux != nullptr && blockIdx.y == 0 && n0 + s < n) aux[(size_t)(n0 + s) * na + i] = v;
     }
     __syncthreads();
     // time_mlp Linear: one warp per output row (coalesced weight reads), FILM_NB dot products at once
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t
             const float ctx = silu_f<false>(pre);     // time_mlp's SiLU
             const float a2 = silu_f<false>(ctx);      // tproj's leading SiLU
             act[lane * base + j] = a2;
-            if (aux != nullptr && n0 + lane < n) {    // saved for gw_film_bwd: [emb | pre | ctx | act]
+            if (aux != nullptr && blockIdx.y == 0 && n0 + lane < n) {    // saved for gw_film_bwd: [emb | pre | ctx | act]
                 float* ax = aux + (size_t)(n0 + lane) * na + time_dim;
                 ax[j] = pre;
                 ax[base + j] = ctx;
@@ -85,8 +85,10 @@ __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t
         }
     }
     __syncthreads();
-    // tproj Linears: one thread per output, its weight row streamed as float4
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    // tproj Linears: one thread per output, its weight row streamed as float4; blockIdx.y splits the F outputs so that the grid
+    // covers the GPU at small n (the time MLP above is recomputed per split: 8 K MACs per sample)
+    const int f_per = (F + gridDim.y - 1) / gridDim.y, f_end = min(F, (int)(blockIdx.y + 1) * f_per);
+    for (int f = blockIdx.y * f_per + threadIdx.x; f < f_end; f += blockDim.x) {
         float acc[FILM_NB];
 #pragma unroll
         for (int s = 0; s < FILM_NB; ++s) acc[s] = 0.0f;
@@ -113,7 +115,10 @@ extern "C" int gw_film_vectors(const int64_t* t, int n, int time_dim, float max_
     const float den = max_time > 1.0f ? max_time : 1.0f;                       // models.py:21
     const float coef = (float)(-(log(10000.0) / (double)(half - 1 > 1 ? half - 1 : 1)));   // models.py:25
     size_t smem = (size_t)FILM_NB * (time_dim + base) * sizeof(float);
-    film_kernel<<<gw_cdiv(n, FILM_NB), 256, smem, (cudaStream_t)stream>>>(t, n, time_dim, den, coef, w1, b1, w2, b2, base, F, out, aux);
+    const int nbx = gw_cdiv(n, FILM_NB);
+    int f_split = nbx >= 296 ? 1 : gw_cdiv(296, nbx);                          // ~2 CTAs per SM
+    if (f_split > gw_cdiv(F, 256)) f_split = gw_cdiv(F, 256);
+    film_kernel<<<dim3(nbx, f_split), 256, smem, (cudaStream_t)stream>>>(t, n, time_dim, den, coef, w1, b1, w2, b2, base, F, out, aux);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

@@ -247,7 +247,9 @@ extern "C" int gw_gn_apply_stream(const void* raw, const float* part, int n_part
 
 int g_gn_bwd_stats_fast = 1;
 bool gn_bwd_stream_fast_ok(const GnBwdArgs& a) {
-    return g_gn_bwd_stats_fast && a.do_eps == nullptr && a.do_a != nullptr && (a.Cc == 1 || a.Cc == 5);
+    if (!g_gn_bwd_stats_fast || !(a.Cc == 1 || a.Cc == 5)) return false;
+    if (a.do_eps != nullptr) return a.C == 64 && a.do_a == nullptr && a.do_pool == nullptr;    // head-gradient source (last decoder)
+    return a.do_a != nullptr;
 }
 int gn_bwd_stream_rows(int L, int C) {
     const int S = SG_STAGE_BYTES / (C * 2);
@@ -440,20 +442,23 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_stream_kernel(GnBwdArgs a
 // Same sums with every stride a compile-time constant (C, cond channels, which gradients come in): the generic kernel above
 // spends ~250 warp instructions per (row, 4 channels) of which ~85 are arithmetic and is ISSUE-bound at 61 % issue utilisation,
 // 2.8 TB/s (profiles/r01j_ncu_gn_bwd_stats.md).  Here a full stage is 4 rows per thread at immediate offsets.
-template <int C, int CC, bool POOL>
+// HEAD (last decoder, C = 64): the incoming gradient is the head conv's, dout[l,c] = sum_k do_w[c,k] * do_eps[l-k+1], formed on the fly
+// from the CTA's slice of d_eps in shared memory -- the [B, L, 64] d_h tensor is neither written by gw_final_bwd nor read here.
+template <int C, int CC, bool POOL, bool HEAD = false>
 __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
     constexpr int S = SG_STAGE_BYTES / (C * 2);                       // rows per stage
     constexpr int NQ = C / 4, NTR = 256 / NQ, RPT = S / NTR;          // channel quads, row lanes, rows per thread and stage
     constexpr int NV = 5 + CC;                                        // [sum do, sum do*act, sum dn, sum dn*xhat, cond.., sum xhat]
     constexpr uint32_t OFF_DO = SG_STAGE_BYTES, OFF_POOL = 2 * SG_STAGE_BYTES;
-    constexpr uint32_t OFF_COND = OFF_POOL + (POOL ? SG_STAGE_BYTES / 2 : 0);
-    static_assert(RPT * NTR == S && NTR % 2 == 0, "stage geometry");
+    constexpr uint32_t OFF_COND = HEAD ? SG_STAGE_BYTES : OFF_POOL + (POOL ? SG_STAGE_BYTES / 2 : 0);
+    static_assert(RPT * NTR == S && NTR % 2 == 0 && !(HEAD && POOL), "stage geometry");
     extern __shared__ __align__(128) uint8_t smem[];
     const int b = blockIdx.y, L = a.L;
     SgBwdStream ps;
     ps.a = &a; ps.b = b; ps.r0 = blockIdx.x * a.rows_per_cta; ps.rows_here = min(a.rows_per_cta, L - ps.r0); ps.S = S;
-    ps.depth = depth; ps.lay = sg_bwd_layout(C, CC, true, POOL); ps.base = smem;
+    ps.depth = depth; ps.lay = sg_bwd_layout(C, CC, !HEAD, POOL); ps.base = smem;
     ps.bars = reinterpret_cast<uint64_t*>(smem + (size_t)depth * ps.lay.stage);
+    float* s_de = reinterpret_cast<float*>(ps.bars + 8);              // HEAD: d_eps[r0 - 1 .. r0 + rows_here]
     const uint32_t stage_bytes = ps.lay.stage;
     const int n_sub = (ps.rows_here + S - 1) / S;
     if (threadIdx.x == 0) {
@@ -463,6 +468,19 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, 
         for (int i = 0; i < depth && i < n_sub; ++i) ps.issue(i, true);
     }
     const int quad = threadIdx.x % NQ, tr = threadIdx.x / NQ;
+    f32x2 wk[3][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+    if (HEAD) {
+        const float* de = a.do_eps + (size_t)b * L;
+        for (int i = threadIdx.x; i < ps.rows_here + 2; i += 256) {
+            const int l = ps.r0 - 1 + i;
+            s_de[i] = (l >= 0 && l < L) ? de[l] : 0.0f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                wk[kk][h] = pkf2(a.do_w[(quad * 4 + 2 * h) * 3 + kk], a.do_w[(quad * 4 + 2 * h + 1) * 3 + kk]);
+    }
     f32x2 hA[2], hB[2], G[2], rs2, xo2;
     {
         constexpr int cg = C / 8;
@@ -495,14 +513,20 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, 
         for (int v = 0; v < NV; ++v) acc[h][v] = 0ull;
     const f32x2 half2 = pkf2(0.5f, 0.5f);
     // one (row, channel quad): x, incoming gradient, cond values -> the 4 + CC running sums
-    auto row = [&](uint2 xr, uint2 dr, uint2 pl, const float* cdr) {
+    auto row = [&](uint2 xr, uint2 dr, uint2 pl, const float* cdr, const float* ep) {
         float cv[CC > 0 ? CC : 1];
 #pragma unroll
         for (int j = 0; j < CC; ++j) cv[j] = cdr[j];
         const uint32_t xw[2] = {xr.x, xr.y}, dw[2] = {dr.x, dr.y}, pw[2] = {pl.x, pl.y};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            f32x2 dv = bf2_lo(dw[h]);
+            f32x2 dv;
+            if (HEAD) {                                              // ep[0..2] = d_eps[l-1], d_eps[l], d_eps[l+1]
+                const float em = ep[0], ec = ep[1], en = ep[2];
+                dv = ffma2(wk[0][h], pkf2(en, en), ffma2(wk[1][h], pkf2(ec, ec), fmul2(wk[2][h], pkf2(em, em))));
+            } else {
+                dv = bf2_lo(dw[h]);
+            }
             if (POOL) dv = ffma2(bf2_lo(pw[h]), half2, dv);
             const f32x2 x = bf2_lo(xw[h]);
             f32x2 z, act, dact;
@@ -531,18 +555,20 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, 
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
                 const uint2 xr = *reinterpret_cast<const uint2*>(sb + t_off + k * NTR * C * 2);
-                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + t_off + k * NTR * C * 2);
+                uint2 dr = make_uint2(0u, 0u);
+                if (!HEAD) dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + t_off + k * NTR * C * 2);
                 uint2 pl = make_uint2(0u, 0u);
                 if (POOL) pl = *reinterpret_cast<const uint2*>(sb + p_off + k * (NTR / 2) * C * 2);
-                row(xr, dr, pl, cd + k * NTR * CC);
+                row(xr, dr, pl, cd + k * NTR * CC, s_de + i * S + tr + k * NTR);
             }
         } else {
             for (int r = tr; r < rows_i; r += NTR) {
                 const uint2 xr = *reinterpret_cast<const uint2*>(sb + ((size_t)r * C + quad * 4) * 2);
-                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + ((size_t)r * C + quad * 4) * 2);
+                uint2 dr = make_uint2(0u, 0u);
+                if (!HEAD) dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + ((size_t)r * C + quad * 4) * 2);
                 uint2 pl = make_uint2(0u, 0u);
                 if (POOL) pl = *reinterpret_cast<const uint2*>(sb + OFF_POOL + ((size_t)(r >> 1) * C + quad * 4) * 2);
-                row(xr, dr, pl, reinterpret_cast<const float*>(sb + OFF_COND) + r * CC);
+                row(xr, dr, pl, reinterpret_cast<const float*>(sb + OFF_COND) + r * CC, s_de + i * S + r);
             }
         }
         __syncthreads();                                              // every thread is done with stage st
@@ -708,7 +734,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_stream_kernel(GnBwdArgs a
 }
 
 // apply pass with compile-time strides (see gn_bwd_stats_fast_kernel)
-template <int C, bool POOL>
+template <int C, bool POOL, bool HEAD = false>
 __global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, const float* __restrict__ gstat,
                                                                 bf16* __restrict__ d_raw, float* __restrict__ partial_bias,
                                                                 int depth) {
@@ -719,10 +745,11 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, 
     const int b = blockIdx.y, L = a.L;
     SgBwdStream ps;
     ps.a = &a; ps.b = b; ps.r0 = blockIdx.x * a.rows_per_cta; ps.rows_here = min(a.rows_per_cta, L - ps.r0); ps.S = S;
-    ps.depth = depth; ps.lay = sg_bwd_layout(C, 0, true, POOL); ps.base = smem;
+    ps.depth = depth; ps.lay = sg_bwd_layout(C, 0, !HEAD, POOL); ps.base = smem;
     const uint32_t stage_bytes = ps.lay.stage;
     uint8_t* s_out = smem + (size_t)depth * stage_bytes;              // [2][8 KB] output staging
     ps.bars = reinterpret_cast<uint64_t*>(s_out + 2 * SG_STAGE_BYTES);
+    float* s_de = reinterpret_cast<float*>(ps.bars + 8);              // HEAD: d_eps[r0 - 1 .. r0 + rows_here]
     const int n_sub = (ps.rows_here + S - 1) / S;
     if (threadIdx.x == 0) {
         for (int s = 0; s < depth; ++s) mbar_init(smem_u32(ps.bars + s), 1);
@@ -731,6 +758,19 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, 
         for (int i = 0; i < depth && i < n_sub; ++i) ps.issue(i, false);
     }
     const int quad = threadIdx.x % NQ, tr = threadIdx.x / NQ;
+    f32x2 wk[3][2] = {{0ull, 0ull}, {0ull, 0ull}, {0ull, 0ull}};
+    if (HEAD) {
+        const float* de = a.do_eps + (size_t)b * L;
+        for (int i = threadIdx.x; i < ps.rows_here + 2; i += 256) {
+            const int l = ps.r0 - 1 + i;
+            s_de[i] = (l >= 0 && l < L) ? de[l] : 0.0f;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                wk[kk][h] = pkf2(a.do_w[(quad * 4 + 2 * h) * 3 + kk], a.do_w[(quad * 4 + 2 * h + 1) * 3 + kk]);
+    }
     f32x2 hA[2], hB[2], G[2], GW2[2], rs2, xo2, nm1, nm2;
     {
         constexpr int cg = C / 8;
@@ -763,12 +803,18 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, 
     }
     f32x2 sbs[2] = {0ull, 0ull};
     const f32x2 half2 = pkf2(0.5f, 0.5f);
-    auto row = [&](uint2 xr, uint2 dr, uint2 pl) -> uint2 {
+    auto row = [&](uint2 xr, uint2 dr, uint2 pl, const float* ep) -> uint2 {
         const uint32_t xw[2] = {xr.x, xr.y}, dw[2] = {dr.x, dr.y}, pw[2] = {pl.x, pl.y};
         uint32_t ow[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            f32x2 dv = bf2_lo(dw[h]);
+            f32x2 dv;
+            if (HEAD) {
+                const float em = ep[0], ec = ep[1], en = ep[2];
+                dv = ffma2(wk[0][h], pkf2(en, en), ffma2(wk[1][h], pkf2(ec, ec), fmul2(wk[2][h], pkf2(em, em))));
+            } else {
+                dv = bf2_lo(dw[h]);
+            }
             if (POOL) dv = ffma2(bf2_lo(pw[h]), half2, dv);
             const f32x2 x = bf2_lo(xw[h]);
             f32x2 z, act, dact;
@@ -797,18 +843,20 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, 
 #pragma unroll
             for (int k = 0; k < RPT; ++k) {
                 const uint2 xr = *reinterpret_cast<const uint2*>(sb + t_off + k * NTR * C * 2);
-                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + t_off + k * NTR * C * 2);
+                uint2 dr = make_uint2(0u, 0u);
+                if (!HEAD) dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + t_off + k * NTR * C * 2);
                 uint2 pl = make_uint2(0u, 0u);
                 if (POOL) pl = *reinterpret_cast<const uint2*>(sb + p_off + k * (NTR / 2) * C * 2);
-                *reinterpret_cast<uint2*>(so + t_off + k * NTR * C * 2) = row(xr, dr, pl);
+                *reinterpret_cast<uint2*>(so + t_off + k * NTR * C * 2) = row(xr, dr, pl, s_de + i * S + tr + k * NTR);
             }
         } else {
             for (int r = tr; r < rows_i; r += NTR) {
                 const uint2 xr = *reinterpret_cast<const uint2*>(sb + ((size_t)r * C + quad * 4) * 2);
-                const uint2 dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + ((size_t)r * C + quad * 4) * 2);
+                uint2 dr = make_uint2(0u, 0u);
+                if (!HEAD) dr = *reinterpret_cast<const uint2*>(sb + OFF_DO + ((size_t)r * C + quad * 4) * 2);
                 uint2 pl = make_uint2(0u, 0u);
                 if (POOL) pl = *reinterpret_cast<const uint2*>(sb + OFF_POOL + ((size_t)(r >> 1) * C + quad * 4) * 2);
-                *reinterpret_cast<uint2*>(so + ((size_t)r * C + quad * 4) * 2) = row(xr, dr, pl);
+                *reinterpret_cast<uint2*>(so + ((size_t)r * C + quad * 4) * 2) = row(xr, dr, pl, s_de + i * S + r);
             }
         }
         fence_proxy_async();
@@ -852,9 +900,22 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
     const bool head = a.do_eps != nullptr;
     if (gn_bwd_stream_fast_ok(a)) {
+        if (head) smem += (size_t)(a.rows_per_cta + 2) * sizeof(float) + 64;      // the CTA's slice of d_eps
         const size_t red_fast = (size_t)n_tr * C * (nvr + 1) * sizeof(float);
         if (smem < red_fast) smem = red_fast;
         const bool pool = a.do_pool != nullptr;
+        if (head) {                                          // last decoder: C = 64, no pooled gradient (gn_bwd_stream_fast_ok)
+#define SGH_GO(CCV)                                                                                                         \
+    do {                                                                                                                    \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<64, CCV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<64, CCV, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
+        gn_bwd_stats_fast_kernel<64, CCV, false, true><<<grid, 256, smem, st>>>(a, partial, depth);                          \
+    } while (0)
+            if (Cc == 1) SGH_GO(1); else SGH_GO(5);
+#undef SGH_GO
+            GW_LAUNCH_CHECK();
+            return GW_OK;
+        }
 #define SGF_GO(CV, CCV, PL)                                                                                                 \
     do {                                                                                                                    \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<CV, CCV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -898,8 +959,16 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
     const int C = a.C;
     const SgBwdLayout lay = sg_bwd_layout(C, 0, a.do_a != nullptr, a.do_pool != nullptr);
     const int depth = lay.stage > 20000 ? 2 : 3;        // + 16 KB of output staging: <= 75 KB per CTA, three CTAs per SM
-    const size_t smem = (size_t)depth * lay.stage + 2 * SG_STAGE_BYTES + 64;
+    size_t smem = (size_t)depth * lay.stage + 2 * SG_STAGE_BYTES + 64;
     dim3 grid(gw_cdiv(a.L, a.rows_per_cta), B);
+    if (a.do_eps != nullptr && gn_bwd_stream_fast_ok(a)) {   // head-gradient source (last decoder, C = 64)
+        smem += (size_t)(a.rows_per_cta + 2) * sizeof(float) + 64;
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<64, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        gn_bwd_apply_fast_kernel<64, false, true><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
     if ((g_gn_bwd_stats_fast && a.do_eps == nullptr && a.do_a != nullptr) || partial_bias == nullptr) {
         const bool pool = a.do_pool != nullptr;
 #define SGA_GO(CV, PL)                                                                                                      \

@@ -84,7 +84,7 @@ class BackwardEngine:
         self.dgrad_impl = "tc" if eng.conv_impl == "tc" else "simt"
         self.wgrad_impl = "tc" if eng.conv_impl == "tc" else "simt"
         self.wgrad_variant = 0
-        self.fuse_head = False
+        self.fuse_head = False                       # see backward(): measured a wash on B200, the materialised d_h stays the default
         self._prepped = False                        # True while the caller has already run prepare_dgrad() for this step
         # bf16: one-pass GroupNorm backward (gn_bwd_fused.cu).  Reads every operand once (3.5 instead of 5.5 tensor passes) but
         # measured slower on B200 (1.90 vs 1.13 ms per step at B=256, L=4096): a slice stays in shared memory for load +
@@ -261,9 +261,12 @@ class BackwardEngine:
                   f"gn_bwd[{n}]")
             eng.launches += 5
 
-        # The gradient wrt the last block's output is a 3-tap outer product of d_eps and final.weight.  gw_gn_bwd can form it on
-        # the fly (bf16, `fuse_head`), but with the streaming GroupNorm kernels the materialised d_h is faster on B200
-        # (205 + 128 us vs 296 + 75 us at B=256), so the fused source stays an option.
+        # The gradient wrt the last block's output is a 3-tap outer product of d_eps and final.weight.  With the specialised
+        # streaming GroupNorm-backward kernels (HEAD variants, stream_gn.cu) gw_gn_bwd forms it on the fly from d_eps in shared
+        # memory, so the [B, L, 64] d_h tensor is neither written by gw_final_bwd nor read back twice (bf16, `fuse_head`).
+        # Measured at B=256, L=4096: gw_final_bwd 130 -> 75 us, but the last block's two GroupNorm-backward passes 162 -> 226 us
+        # (they are issue-bound: 12 extra instructions per (row, 4 channels) cost more than the 268 MB of reads they save), so
+        # the step time is unchanged (3.68 vs 3.69 ms) and the option stays off.
         fuse_head = self.fuse_head and eng.dtype == "bf16"
         check(lib.gw_final_bwd(ptr(d_eps), ptr(ws.out[nl - 1]), eng.gw_dtype, ptr(net), B, Cx, L, lc[-1], ptr(eng.wf),
                                None if fuse_head else ptr(g.d_h[0]), ptr(g.scratch), ptr(grads["final.weight"]),

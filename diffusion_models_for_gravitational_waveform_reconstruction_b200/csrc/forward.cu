@@ -154,6 +154,34 @@ __global__ void __launch_bounds__(256) cond_pyramid_kernel(const float* __restri
     }
 }
 
+// Power-of-two pyramids (every level is L >> j, the reference's 4096 -> 2048 -> 1024 -> 512): the interpolation is the identity at
+// level 0 and the mean of the two central samples of each stride-2^j cell below it (src = 2^j (l + 1/2) - 1/2 lands exactly
+// between two samples, weights 1/2 and 1/2; same values as the generic kernel).  A CTA stages 1024 positions of all cond channels
+// once (vector loads) and writes every level's rows as one contiguous run: the generic kernel's strided reads and 20-byte row
+// stores took 52 us for 23 MB at B = 256.
+#define PYR_TILE 1024
+__global__ void __launch_bounds__(256) cond_pyramid_pow2_kernel(const float* __restrict__ x, int Cx, int L, int Cc, int n_levels,
+                                                                PyrArgs a) {
+    extern __shared__ __align__(16) float xs[];          // [Cc][PYR_TILE]
+    const int b = blockIdx.y, l0 = blockIdx.x * PYR_TILE;
+    const float* xp = x + ((size_t)b * Cx + 1) * L + l0;
+    for (int i = threadIdx.x; i < Cc * (PYR_TILE / 4); i += 256) {
+        const int c = i / (PYR_TILE / 4), q = i % (PYR_TILE / 4);
+        *reinterpret_cast<float4*>(xs + c * PYR_TILE + 4 * q) = *reinterpret_cast<const float4*>(xp + (size_t)c * L + 4 * q);
+    }
+    __syncthreads();
+    for (int lvl = 0; lvl < n_levels; ++lvl) {
+        const int n_out = PYR_TILE >> lvl, s = 1 << lvl;
+        float* op = (lvl == 0 ? a.out[0] : lvl == 1 ? a.out[1] : lvl == 2 ? a.out[2] : a.out[3]) +
+                    ((size_t)b * (L >> lvl) + (l0 >> lvl)) * Cc;
+        for (int idx = threadIdx.x; idx < n_out * Cc; idx += 256) {
+            const int i = idx / Cc, c = idx - i * Cc;
+            const float* xr = xs + c * PYR_TILE;
+            op[idx] = lvl == 0 ? xr[i] : 0.5f * xr[s * i + (s >> 1) - 1] + 0.5f * xr[s * i + (s >> 1)];
+        }
+    }
+}
+
 extern "C" int gw_cond_pyramid(const float* x, int B, int Cx, int L, int Cc, int n_levels, const int* level_len,
                                float* const* level_out, void* stream) {
     GW_REQUIRE(n_levels > 0 && n_levels <= GW_MAX_LEVELS, "gw_cond_pyramid: n_levels %d", n_levels);
@@ -162,6 +190,14 @@ extern "C" int gw_cond_pyramid(const float* x, int B, int Cx, int L, int Cc, int
     for (int i = 0; i < n_levels; ++i) {
         a.out[i] = level_out[i];
         a.len[i] = level_len[i];
+    }
+    bool pow2 = L % PYR_TILE == 0 && n_levels <= 4;
+    for (int i = 0; i < n_levels; ++i) pow2 = pow2 && level_len[i] == (L >> i);
+    if (pow2) {
+        const size_t smem = (size_t)Cc * PYR_TILE * sizeof(float);
+        cond_pyramid_pow2_kernel<<<dim3(L / PYR_TILE, B), 256, smem, (cudaStream_t)stream>>>(x, Cx, L, Cc, n_levels, a);
+        GW_LAUNCH_CHECK();
+        return GW_OK;
     }
     long total = (long)B * L;
     int gx = (int)((total + 255) / 256);

@@ -49,6 +49,45 @@ __global__ void __launch_bounds__(256) train_pack_kernel(const float* __restrict
     float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (philox) Philox::normal4(seed, (uint32_t)(sample0 + b), (uint32_t)(step_ptr ? *step_ptr : 0), (uint32_t)(l4 >> 2), z);
     float* nb = net + (size_t)b * Cx * L;
+    if ((L & 3) == 0) {
+        // whole quads: 16-byte loads / stores (the scalar path below touches every sector four times)
+        const size_t o = (size_t)b * L + l4;
+        float4 e4;
+        if (philox) {
+            e4 = make_float4(z[0], z[1], z[2], z[3]);
+            *reinterpret_cast<float4*>(eps + o) = e4;
+        } else {
+            e4 = *reinterpret_cast<const float4*>(eps + o);
+        }
+        const float4 c4 = *reinterpret_cast<const float4*>(clean + o);
+        const float ev[4] = {e4.x, e4.y, e4.z, e4.w}, xv[4] = {c4.x, c4.y, c4.z, c4.w};
+        float vv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float x0 = xv[i];
+            if (clampv > 0.0f) x0 = fminf(fmaxf(x0, -clampv), clampv);
+            float v = a * x0 + m * ev[i];
+            if (clampv > 0.0f) v = fminf(fmaxf(v, -clampv), clampv);
+            vv[i] = v;
+        }
+        *reinterpret_cast<float4*>(nb + l4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        for (int c = 0; c < Cc; ++c) {
+            const float4 q = *reinterpret_cast<const float4*>(cond + ((size_t)b * Cc + c) * L + l4);
+            float cv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (c == 0) {
+                    if (clampv > 0.0f && clamp_y) cv[i] = fminf(fmaxf(cv[i], -clampv), clampv);
+                    cv[i] *= keep;
+                } else if (drop_all) {
+                    cv[i] *= keep;
+                }
+            }
+            *reinterpret_cast<float4*>(nb + (size_t)(1 + c) * L + l4) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        }
+        for (int c = 1 + Cc; c < Cx; ++c) *reinterpret_cast<float4*>(nb + (size_t)c * L + l4) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int l = l4 + i;

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
     float* bs = ws + cig_ws_floats(A.Cx);                                   // [C]
     float* wst = bs + C;                                                    // [8 warps][8 octets][2]
     float* s_x = wst + 128;                                                 // [G][16]
+    float* s_mr = s_x + XCHG_MAX_G * 16;                                    // [8 groups][mean, rstd]
     const int Cx = A.Cx, L = A.L, Cc = A.Cc, G = A.G;
     const int grp = blockIdx.x / G, j_cta = blockIdx.x % G;
     const int l00 = j_cta * CIG_ROWS;
@@ -307,16 +308,21 @@ __global__ void __launch_bounds__(256, CIG_ROWS == 256 ? 2 : 1) conv_in_gn_kerne
                 s_x[i] = __uint_as_float((unsigned int)pk);
             }
             __syncthreads();
-            double a1 = 0.0, a2 = 0.0;
-            for (int s = 0; s < G; ++s) {
-                a1 += (double)s_x[s * 16 + ao * 2];
-                a2 += (double)s_x[s * 16 + ao * 2 + 1];
+            // one thread per GroupNorm group folds the G packets in fp64 (every thread doing it was ~5 % of the kernel's instructions)
+            if (tid < 8) {
+                double a1 = 0.0, a2 = 0.0;
+                for (int s = 0; s < G; ++s) {
+                    a1 += (double)s_x[s * 16 + tid * 2];
+                    a2 += (double)s_x[s * 16 + tid * 2 + 1];
+                }
+                const double mean = a1 * inv_n;
+                double var = a2 * inv_n - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_mr[tid * 2 + 0] = (float)mean;
+                s_mr[tid * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
             }
-            const double mean = a1 * inv_n;
-            double var = a2 * inv_n - mean * mean;
-            if (var < 0.0) var = 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-            const float meanf = (float)mean;
+            __syncthreads();
+            const float meanf = s_mr[ao * 2 + 0], rstd = s_mr[ao * 2 + 1];
             // coefficients of my 8 channels, packed in pairs: h = A x + B (half the GroupNorm output), out = silu G + E + sum W c
             f32x2 hA[4], hB[4], Gp[4], Ep[4], Wp[NCA][4];
 #pragma unroll
@@ -427,7 +433,7 @@ extern "C" int gw_conv_in_gn(const float* x, const float* x_alt, const int* step
     A.film_b_stride = film_b_stride; A.film_step_stride = film_step_stride; A.film_off = film_off;
     A.B = B; A.Cx = Cx; A.L = L; A.Cc = Cc; A.G = G;
     const int rows = L <= 8192 ? 256 : 512;
-    const size_t smem = (size_t)2 * rows * CIG_C * 2 + (size_t)(2 * Cx * (rows + 8) + cig_ws_floats(Cx) + CIG_C + 128 + XCHG_MAX_G * 16) * 4;
+    const size_t smem = (size_t)2 * rows * CIG_C * 2 + (size_t)(2 * Cx * (rows + 8) + cig_ws_floats(Cx) + CIG_C + 128 + XCHG_MAX_G * 16 + 16) * 4;
     GW_REQUIRE(smem <= 232448, "gw_conv_in_gn: shared memory %zu too large", smem);
     cudaStream_t st = (cudaStream_t)stream;
     // every CTA of a group spins on its peers: the grid must be co-resident -> size it from the occupancy of this variant

@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
     }
 }
 
+int final_bwd_stream(const float* d_eps, const void* h, const float* net, int B, int Cx, int L, const float* wf, void* d_h,
+                     float* partial, int* n_cta, cudaStream_t st);
+int g_final_bwd_stream = 1;
 extern "C" int gw_final_bwd(const float* d_eps, const void* h, int dtype, const float* net, int B, int Cx, int L, int C,
                             const float* wf, void* d_h, float* scratch, float* d_wf, float* d_bf, void* stream) {
     GW_REQUIRE(C % 64 == 0 && C <= 256, "gw_final_bwd: C=%d", C);
@@ -239,6 +242,15 @@ extern "C" int gw_final_bwd(const float* d_eps, const void* h, int dtype, const 
     const int n_tr = 256 / (C / 8);
     const size_t smem = (size_t)n_tr * C * 3 * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_BF16 && C == 64 && L % 4 == 0 && g_final_bwd_stream) {       // HBM-streaming kernel (stream_gn.cu)
+        int n_ctas = 0;
+        int rcs = final_bwd_stream(d_eps, h, net, B, Cx, L, wf, d_h, scratch, &n_ctas, st);
+        if (rcs != GW_OK) return rcs;
+        const int nvs = (C + 1) * 3 + 1;
+        rcs = reduce_rows(scratch, n_ctas, nvs - 1, nvs, 1.0f, d_wf, 1, st);
+        if (rcs != GW_OK) return rcs;
+        return reduce_rows(scratch + nvs - 1, n_ctas, 1, nvs, 1.0f, d_bf, 1, st);
+    }
 #define FB_GO(TT, WR)                                                                                                  \
     do {                                                                                                               \
         GW_CUDA(cudaFuncSetAttribute(final_bwd_kernel<TT, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -849,6 +861,7 @@ extern "C" int gw_set_option(const char* name, int value) {
     if (strcmp(name, "gn_bwd_fused_slice") == 0) { g_gn_bwd_fused_slice = value; return GW_OK; }
     if (strcmp(name, "final_stream") == 0) { g_final_stream = value; return GW_OK; }
     if (strcmp(name, "pdl") == 0) { g_pdl = value; return GW_OK; }
+    if (strcmp(name, "final_bwd_stream") == 0) { g_final_bwd_stream = value; return GW_OK; }
     if (strcmp(name, "conv_in_mma") == 0) { g_conv_in_mma = value; return GW_OK; }
     if (strcmp(name, "wgrad_in_mma") == 0) { g_wgrad_in_mma = value; return GW_OK; }
     gw_set_error("gw_set_option: unknown option %s", name);

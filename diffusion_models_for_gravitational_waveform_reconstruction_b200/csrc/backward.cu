@@ -426,8 +426,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(GnBwdArgs a, float
 }
 
 // grid B, block 1024: reduce the row-CTA partials of one sample, emit dfilm and the group means needed by the apply pass
-// nvr = values per channel in `partial` / `redb` (4 + Cc, + 1 when the sums pass also delivers sum_l xhat for the analytic conv-bias
-// gradient, see gn_bwd_param_kernel)
+// nvr = values per channel in `partial` / `redb` (4 + Cc)
 __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __restrict__ partial, int n_rc, int C, int nvr, int Cc, int L,
                                                                const float* __restrict__ gn_w, const float* __restrict__ wc,
                                                                const float* __restrict__ bc, float* __restrict__ redb,
@@ -472,15 +471,14 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
 }
 
 // grid ceil(C/32), block 1024 = 32 channels x 32 batch lanes: parameter gradients that sum over the batch
-// SX (the sums pass delivered p[4+Cc] = sum_l xhat[l,c]): the conv-bias gradient sum_{b,l} d_raw[b,l,c] follows analytically,
-//   sum_l d_raw = rstd * (gn_w[c] * sum_l dn - L * m1 - m2 * sum_l xhat),  (m1, m2) = gstat of the sample's group,
-// so the apply pass needs no per-CTA bias partials and no reduce launches (and the sum is free of d_raw's bf16 rounding).
+// bias_part != NULL: also folds the conv-bias partials of the apply pass, [B * n_rc, C] (sum over rows of d_raw per CTA), in fixed
+// order -- the two reduce launches per layer that used to do it are gone (the kernel then runs AFTER the apply pass).
 __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restrict__ redb, int B, int C, int nvr, int Cc,
                                                             const float* __restrict__ film, long film_b_stride, int film_off,
                                                             float* __restrict__ d_gn_w, float* __restrict__ d_gn_b,
-                                                            float* __restrict__ d_wc, float* __restrict__ d_bc, int sx,
-                                                            const float* __restrict__ stats, const float* __restrict__ gstat,
-                                                            const float* __restrict__ gn_w, int L, float* __restrict__ d_conv_bias) {
+                                                            float* __restrict__ d_wc, float* __restrict__ d_bc,
+                                                            const float* __restrict__ bias_part, int n_rc,
+                                                            float* __restrict__ d_conv_bias) {
     __shared__ float red[32][32][3 + BW_MAX_CC + 1];        // slot 3 + BW_MAX_CC: the conv-bias sum (SX)
     const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -488,8 +486,6 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restr
 #pragma unroll
     for (int v = 0; v < 4 + BW_MAX_CC; ++v) a[v] = 0.0f;
     if (c < C) {
-        const int g = c / (C / 8);
-        const float gw = sx ? gn_w[c] : 0.0f;
 #pragma unroll 4
         for (int b = bl; b < B; b += 32) {
             const float* p = redb + ((size_t)b * C + c) * nvr;
@@ -500,10 +496,11 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restr
 #pragma unroll
             for (int j = 0; j < BW_MAX_CC; ++j)
                 if (j < Cc) a[3 + j] = fmaf(G, p[4 + j], a[3 + j]);
-            if (sx) {
-                const float rstd = stats[((size_t)b * 8 + g) * 2 + 1];
-                const float m1 = gstat[((size_t)b * 8 + g) * 2 + 0], m2 = gstat[((size_t)b * 8 + g) * 2 + 1];
-                a[3 + BW_MAX_CC] += rstd * (fmaf(gw, p[2], -(float)L * m1) - m2 * p[4 + Cc]);
+            if (bias_part != nullptr) {
+                const float* bp = bias_part + (size_t)b * n_rc * C + c;
+                float sb = 0.0f;
+                for (int r = 0; r < n_rc; ++r) sb += bp[(size_t)r * C];
+                a[3 + BW_MAX_CC] += sb;
             }
         }
     }
@@ -521,7 +518,7 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restr
             if (bl == 2) d_bc[c] += sv;
             else d_wc[c * Cc + (bl - 3)] += sv;
         }
-    } else if (sx && bl == 31 && c < C) {
+    } else if (bias_part != nullptr && bl == 31 && c < C) {
         float sv = 0.0f;
 #pragma unroll
         for (int t = 0; t < 32; ++t) sv += red[t][cl][3 + BW_MAX_CC];
@@ -907,7 +904,7 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
                                                                                         redb, dfilm, dfilm_b_stride, a.film_off, gstat);
                 GW_LAUNCH_CHECK();
                 gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w,
-                                                                   d_gn_b, d_wc, d_bc, 0, nullptr, nullptr, nullptr, L, nullptr);
+                                                                   d_gn_b, d_wc, d_bc, nullptr, 0, nullptr);
                 GW_LAUNCH_CHECK();
                 return reduce_rows(biasp, B * G, C, C, 1.0f, d_conv_bias, 1, st);
             }
@@ -918,13 +915,14 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     // bf16 with friendly shapes: HBM-streaming kernels (stream_gn.cu), same partial layouts
     const bool stream_ok = FAST && g_gn_bwd_stream && L % 4 == 0 && (C == 64 || C == 128 || C == 256) &&
                            a.rows_per_cta == gn_bwd_stream_rows(L, C);
-    // compile-time-specialised streaming kernels: the sums pass also delivers sum_l xhat per channel (one more value per
-    // channel), from which gn_bwd_param_kernel forms the conv-bias gradient without partials from the apply pass
+    // compile-time-specialised streaming kernels: the parameter kernel runs after the apply pass and folds its conv-bias
+    // partials too (no reduce launches)
     const bool sx = stream_ok && gn_bwd_stream_fast_ok(a);
-    const int nvs = nvr + (sx ? 1 : 0);
+    const int nvs = nvr;
     float* partial = scratch;
     float* redb = partial + (size_t)B * n_rc * C * nvs;
     float* gstat = redb + (size_t)B * C * nvs;
+    float* biasp = gstat + (size_t)B * 16;                   // [B * n_rc, C] (sx)
     dim3 grid(n_rc, B);
     const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
 #define GNB_GO(CCV)                                                                                                       \
@@ -952,11 +950,17 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvs * sizeof(float), st>>>(partial, n_rc, C, nvs, Cc, L, a.gn_w, a.wc, a.bc, redb,
                                                                             dfilm, dfilm_b_stride, a.film_off, gstat);
     GW_LAUNCH_CHECK();
+    if (sx) {
+        int rcs = gn_bwd_apply_stream(a, B, gstat, d_raw, biasp, st);
+        if (rcs != GW_OK) return rcs;
+        gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+                                                           d_wc, d_bc, biasp, n_rc, d_conv_bias);
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
     gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
-                                                       d_wc, d_bc, sx ? 1 : 0, a.stats, gstat, a.gn_w, L, d_conv_bias);
+                                                       d_wc, d_bc, nullptr, 0, nullptr);
     GW_LAUNCH_CHECK();
-    if (sx)                                                  // no bias partials, no reduce launches
-        return gn_bwd_apply_stream(a, B, gstat, d_raw, nullptr, st);
     // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
 #define GNA_GO(CCV) gn_bwd_apply_kernel<T, FAST, CCV><<<grid, 256, sm2, st>>>(a, gstat, (T*)d_raw, partial)
     if (FAST && stream_ok) {

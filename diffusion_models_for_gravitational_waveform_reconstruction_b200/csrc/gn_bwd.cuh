@@ -41,7 +41,7 @@ __device__ __forceinline__ void sg_silu_pair(f32x2 x, f32x2 hA, f32x2 hB, f32x2&
 
 // HBM-streaming bf16 implementations (stream_gn.cu); same partial layouts as the register-streaming kernels
 int gn_bwd_stream_rows(int L, int C);
-bool gn_bwd_stream_fast_ok(const GnBwdArgs& a);   // the compile-time-specialised kernels run (partials carry 5 + Cc values)
+bool gn_bwd_stream_fast_ok(const GnBwdArgs& a);   // the compile-time-specialised kernels run
 int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t st);
 int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_raw, float* partial_bias, cudaStream_t st);
 

@@ -448,7 +448,7 @@ template <int C, int CC, bool POOL, bool HEAD = false>
 __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
     constexpr int S = SG_STAGE_BYTES / (C * 2);                       // rows per stage
     constexpr int NQ = C / 4, NTR = 256 / NQ, RPT = S / NTR;          // channel quads, row lanes, rows per thread and stage
-    constexpr int NV = 5 + CC;                                        // [sum do, sum do*act, sum dn, sum dn*xhat, cond.., sum xhat]
+    constexpr int NV = 4 + CC;                                        // [sum do, sum do*act, sum dn, sum dn*xhat, cond..]
     constexpr uint32_t OFF_DO = SG_STAGE_BYTES, OFF_POOL = 2 * SG_STAGE_BYTES;
     constexpr uint32_t OFF_COND = HEAD ? SG_STAGE_BYTES : OFF_POOL + (POOL ? SG_STAGE_BYTES / 2 : 0);
     static_assert(RPT * NTR == S && NTR % 2 == 0 && !(HEAD && POOL), "stage geometry");
@@ -539,7 +539,6 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, 
             acc[h][3] = ffma2(dn, xh, acc[h][3]);
 #pragma unroll
             for (int j = 0; j < CC; ++j) acc[h][4 + j] = ffma2(dv, pkf2(cv[j], cv[j]), acc[h][4 + j]);
-            acc[h][4 + CC] = fadd2(acc[h][4 + CC], xh);
         }
     };
     const uint32_t t_off = (uint32_t)(tr * C + quad * 4) * 2;          // my quad in row tr of a stage
@@ -901,8 +900,6 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     const bool head = a.do_eps != nullptr;
     if (gn_bwd_stream_fast_ok(a)) {
         if (head) smem += (size_t)(a.rows_per_cta + 2) * sizeof(float) + 64;      // the CTA's slice of d_eps
-        const size_t red_fast = (size_t)n_tr * C * (nvr + 1) * sizeof(float);
-        if (smem < red_fast) smem = red_fast;
         const bool pool = a.do_pool != nullptr;
         if (head) {                                          // last decoder: C = 64, no pooled gradient (gn_bwd_stream_fast_ok)
 #define SGH_GO(CCV)                                                                                                         \

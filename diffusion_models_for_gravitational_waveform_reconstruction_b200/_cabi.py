@@ -17,7 +17,7 @@ GW_F32, GW_BF16 = 0, 1
 class StepParams(C.Structure):
     _fields_ = [("mode", C.c_int), ("cfg_both", C.c_int), ("selfcond", C.c_int), ("pred_x0", C.c_int),
                 ("eps_scale", C.c_float), ("dc_weight", C.c_float), ("y_dc", C.c_void_p),
-                ("seed", C.c_ulonglong), ("sample0", C.c_long), ("advance", C.c_void_p)]
+                ("seed", C.c_ulonglong), ("sample0", C.c_long), ("advance", C.c_void_p), ("rng", C.c_void_p)]
 
 
 class ConvTcShape(C.Structure):

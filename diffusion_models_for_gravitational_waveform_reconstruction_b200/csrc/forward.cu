@@ -1157,6 +1157,7 @@ struct StepArgs {
     const float* y_dc;
     unsigned long long seed;
     long sample0;
+    const unsigned long long* rng;      // device {seed, sample0} (graph-replay safe) or NULL -> the by-value fields
 };
 
 // CTA = 256 rows of h (254 output positions + the two halo rows), 256 threads.  Phase 1: every thread first issues the
@@ -1288,7 +1289,9 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
             float z = zin;
             if (noise == nullptr) {
                 float z4[4];
-                Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)(l >> 2), z4);
+                const unsigned long long sd = p.rng != nullptr ? p.rng[0] : p.seed;
+                const long s0 = p.rng != nullptr ? (long)p.rng[1] : p.sample0;
+                Philox::normal4(sd, (uint32_t)(s0 + b), (uint32_t)step + 1u, (uint32_t)(l >> 2), z4);
                 z = z4[l & 3];
             }
             nz = __fmul_rn(c_sig, z);
@@ -1327,6 +1330,7 @@ extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const
     StepArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
     a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    a.rng = p->rng;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_BF16 && C == 64 && g_final_stream)       // HBM-streaming kernel (stream_gn.cu)
         return final_step_stream(h, net_a, net_b, B, Cx, L, wf, bf, p, coef, step_ptr, noise, eps_out, x0_out, st);

@@ -1404,6 +1404,7 @@ struct FssArgs {
     const float* y_dc;
     unsigned long long seed;
     long sample0;
+    const unsigned long long* rng;      // device {seed, sample0} (graph-replay safe) or NULL -> the by-value fields
     unsigned int* advance;      // final_step_dots_kernel: CTA counter; the last CTA out does *step_ptr += 1 (NULL: nobody does)
 };
 
@@ -1557,8 +1558,11 @@ __global__ void __launch_bounds__(256) final_step_stream_kernel(const bf16* __re
     cf.use = (int)cfv[6]; cf.last = (int)cfv[7]; cf.draw = (int)cfv[8]; cf.c_s1mab_cl = cfv[9];
     const bool need_z = p.mode == 1 && !cf.last && cf.c_sig > 0.0f;
     float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (need_z && noise == nullptr)
-        Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)((l0 + g * 4) >> 2), z4);
+    if (need_z && noise == nullptr) {
+        const unsigned long long sd = p.rng != nullptr ? p.rng[0] : p.seed;
+        const long s0 = p.rng != nullptr ? (long)p.rng[1] : p.sample0;
+        Philox::normal4(sd, (uint32_t)(s0 + b), (uint32_t)step + 1u, (uint32_t)((l0 + g * 4) >> 2), z4);
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int pi = g * 4 + u, l = l0 + pi;
@@ -1610,7 +1614,11 @@ __global__ void __launch_bounds__(256) final_step_dots_kernel(const float4* __re
     cf.use = (int)cfv[6]; cf.last = (int)cfv[7]; cf.draw = (int)cfv[8]; cf.c_s1mab_cl = cfv[9];
     const bool need_z = p.mode == 1 && !cf.last && cf.c_sig > 0.0f;
     float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (need_z && noise == nullptr) Philox::normal4(p.seed, (uint32_t)(p.sample0 + b), (uint32_t)step + 1u, (uint32_t)(l4 >> 2), z4);
+    if (need_z && noise == nullptr) {
+        const unsigned long long sd = p.rng != nullptr ? p.rng[0] : p.seed;
+        const long s0 = p.rng != nullptr ? (long)p.rng[1] : p.sample0;
+        Philox::normal4(sd, (uint32_t)(s0 + b), (uint32_t)step + 1u, (uint32_t)(l4 >> 2), z4);
+    }
     const int n = min(4, L - l4);
     float ov[2][4], xc4[4];
     for (int hf = 0; hf < n_half; ++hf) {
@@ -1665,7 +1673,7 @@ int final_step_dots(const void* dots, const float* net_a, const float* net_b, in
                     float* eps_out, float* x0_out, cudaStream_t st) {
     FssArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
-    a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0; a.rng = p->rng;
     a.advance = (p->mode == 1 && step_ptr != nullptr) ? (unsigned int*)p->advance : nullptr;
     dim3 grid(gw_cdiv(L, 1024), B);
     GW_CUDA(gw_launch_pdl(final_step_dots_kernel, grid, dim3(256), (size_t)0, st, (const float4*)dots, net_a, net_b ? net_b : net_a, B,
@@ -1680,7 +1688,7 @@ int final_step_stream(const void* h, const float* net_a, const float* net_b, int
                       float* x0_out, cudaStream_t st) {
     FssArgs a;
     a.mode = p->mode; a.cfg_both = p->cfg_both; a.selfcond = p->selfcond; a.pred_x0 = p->pred_x0;
-    a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0;
+    a.eps_scale = p->eps_scale; a.dc_weight = p->dc_weight; a.y_dc = p->y_dc; a.seed = p->seed; a.sample0 = p->sample0; a.rng = p->rng;
     a.advance = nullptr;
     const size_t smem = (size_t)SG_DEPTH * SG_STAGE_BYTES + (size_t)2 * 3 * (FSS_TP + 2) * 4 + 64;
     GW_CUDA(cudaFuncSetAttribute(final_step_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

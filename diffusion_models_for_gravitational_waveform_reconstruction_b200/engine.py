@@ -196,6 +196,7 @@ class UNetEngine:
         self._fuse_ok: Dict[tuple, bool] = {}
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
+        self.generation = 0                         # bumped by refresh(): weight-derived caches (SamplerPlan.film) follow it
         self.refresh()
 
     # ------------------------------------------------------------------ weights
@@ -212,6 +213,7 @@ class UNetEngine:
         self.wf = p["final.weight"].reshape(-1)                   # [(C+1)*3], index c*3+k
         for key in list(self._packed):
             self._pack_tc(key)
+        self.generation += 1
 
     def bind_flat(self, flat: Tensor, layout: ParamLayout) -> None:
         """Use `flat` (fp32, ParamLayout order) as the parameter storage: in-place optimiser updates of the flat buffer
@@ -558,23 +560,49 @@ class SamplerPlan:
         self.cfg_both = any(u != 0 for u in uses)       # an unconditional batch is needed at some step
         self.Bn = B * (2 if self.cfg_both else 1)
         self.coef = coef.to(dev)
-        self.film = eng.film_vectors(torch.tensor(sched, dtype=torch.int64, device=dev))
+        self.sched_dev = torch.tensor(sched, dtype=torch.int64, device=dev)
+        self.film = eng.film_vectors(self.sched_dev)
+        self._gen = eng.generation
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         Cx = sp.in_ch
         self.net = [torch.zeros(self.Bn, Cx, L, device=dev, dtype=torch.float32) for _ in range(2)]
         self.ws = eng.workspace(self.Bn, L)
         self.y_dc = torch.zeros(B, L, device=dev, dtype=torch.float32) if dc_weight > 0 else None
         self.adv = torch.zeros(1, dtype=torch.int32, device=dev)      # CTA counter of the self-advancing head kernel
+        # Philox key {seed, sample0} lives in device memory: the kernel arguments of a captured graph are frozen, the key of
+        # a cached plan is not (chunked sweeps, rank shards, repeated seed=None calls)
+        self.rng = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._rng_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        self._rng_ev: Optional[torch.cuda.Event] = None
         self.params = StepParams(1, 1 if self.cfg_both else 0, 1 if sp.use_selfcond else 0, 1 if pred_type != "eps" else 0,
                                  float(eps_scale), float(dc_weight), ptr(self.y_dc), int(seed) & (2 ** 64 - 1), int(sample0),
-                                 ptr(self.adv))
+                                 ptr(self.adv), ptr(self.rng))
+        self.set_rng(seed, sample0)
         self.noise: Optional[Tensor] = None
         self.trace_eps: Optional[Tensor] = None
         self.trace_x0: Optional[Tensor] = None
         self._graph = None
         self._graph_steps = 0
 
-    # one reverse step = 16 kernels
+    def set_rng(self, seed: int, sample0: int) -> None:
+        """Philox key of the stochastic steps (stream-ordered copy into the device key the kernels read)."""
+        seed = int(seed) & (2 ** 64 - 1)
+        if self._rng_ev is not None:
+            self._rng_ev.synchronize()                 # the previous copy out of the pinned pair has completed
+        self._rng_host[0] = seed - (1 << 64) if seed >= (1 << 63) else seed
+        self._rng_host[1] = int(sample0)
+        self.rng.copy_(self._rng_host, non_blocking=True)
+        self._rng_ev = torch.cuda.Event()
+        self._rng_ev.record()
+        self.params.seed, self.params.sample0 = seed, int(sample0)
+
+    def sync_weights(self) -> None:
+        """Recompute the FiLM table (in place: a captured graph stays valid) when the engine's weights were refreshed."""
+        if self._gen != self.eng.generation:
+            self.eng.film_vectors(self.sched_dev, out=self.film)
+            self._gen = self.eng.generation
+
+    # one reverse step = 8 kernels (bf16 fused path)
     def enqueue_step(self) -> None:
         eng = self.eng
         h = eng.body(self.ws, self.net[0], self.net[1], self.step, self.film, 0, eng.spec.film_dim)
@@ -586,6 +614,7 @@ class SamplerPlan:
     def load_inputs(self, x_init: Tensor, cond_on: Tensor, cond_off: Optional[Tensor], y_dc: Optional[Tensor]) -> None:
         """x_init [B,1,L]; cond_on/off [B,Cc,L] (already cond-scaled / zeroed as inference.py:434-446)."""
         sp, B = self.eng.spec, self.B
+        self.sync_weights()
         for net in self.net:
             net.zero_()
             net[:B, 0:1] = x_init

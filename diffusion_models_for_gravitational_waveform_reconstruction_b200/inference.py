@@ -79,8 +79,7 @@ def make_sampler_plan(model: UNet1D, diffusion: CustomDiffusion, B: int, L: int,
             if len(_PLANS) > 16:
                 _PLANS.clear()
             _PLANS[key] = plan
-    plan.params.seed = int(seed) & (2 ** 64 - 1)
-    plan.params.sample0 = int(sample0)
+    plan.set_rng(seed, sample0)
     return plan
 
 

@@ -523,6 +523,8 @@ class FusedTrainStep:
             self.cond.copy_(sset["cond"])
         if sset["has_mask"]:
             self.mask.copy_(sset["mask"])
+        else:
+            self.mask.fill_(1.0)
         self._free[slot].record(cur)
 
     # ------------------------------------------------------------------ pieces
@@ -551,6 +553,8 @@ class FusedTrainStep:
             self.cond.copy_(cond_stack.reshape(B, self.spec.cond_in_ch, L), non_blocking=True)
         if mask is not None:
             self.mask.copy_(mask.reshape(B, L), non_blocking=True)
+        else:
+            self.mask.fill_(1.0)                              # no mask = every sample valid (never the previous batch's mask)
 
     def _set_hyper(self) -> None:
         step = self.steps_done + 1
@@ -667,6 +671,9 @@ class FusedTrainStep:
             self._allreduce()
             gs[1].replay()
         self.steps_done += 1
+        # the flat buffer changed under the module's parameter views (no torch version bump): engines that UNet1D.engine()
+        # hands out (model(x, t), ddim_sample(model, ...)) must re-pack their bf16 weights / FiLM tables on next use
+        self.model._versions = None
 
     def _capture(self, key):
         """Two graphs per step flavour: [pack .. backward] and [norm .. AdamW/EMA .. re-pack]; the NCCL all-reduce of the

@@ -120,6 +120,8 @@ typedef struct {
     long sample0;      /* global index of sample 0 (Philox stream id, world-size independent) */
     void* advance;     /* dtype = GW_DOTS, mode 1: device uint32 (zeroed once): the last CTA of the launch does *step_ptr += 1, so
                           no gw_step_advance launch is needed between reverse steps; NULL: the caller advances the counter */
+    const unsigned long long* rng; /* device uint64[2] = {seed, sample0} read at run time (a captured CUDA graph then follows
+                          later changes of the Philox key); NULL: the by-value seed / sample0 above are used */
 } gw_step_params;
 
 int gw_final_step(const void* h, int dtype, const float* net_a, const float* net_b, int B, int Cx, int L, int C,

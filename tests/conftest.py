@@ -13,6 +13,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    config.addinivalue_line("markers", "slow: minutes of CPU oracle time (still part of -m gpu)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -79,7 +79,10 @@ _SIGS.update({
     "gw_selfcond_x0": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),
     "gw_opt_scratch_doubles": ([], _I),
     "gw_grad_sumsq": ([_P, _L, _P, _P], _I),
-    "gw_adamw_ema": ([_P, _P, _P, _P, _P, _L, _P, _P, _P, _F, _F, _F, _P, _P], _I),
+    "gw_adamw_ema": ([_P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _P, C.c_double, C.c_double, _F, _P, _P], _I),
+    "gw_bucket_reset": ([_P, _L, _P, _P], _I),
+    "gw_train_advance": ([_P, _P, _P, _P], _I),
+    "gw_loss_weight": ([_P, _P, _F, _P, _I, _P], _I),
 })
 _SIGS["gw_score_batch"] = ([_P, _P, _P, _I, _I, C.c_double, C.c_double, _I, C.c_double, _P, _P], _I)
 _SIGS["gw_set_option"] = ([C.c_char_p, _I], _I)

@@ -43,6 +43,9 @@ struct GnFuseArgs {
     const float* head_w;      // HEAD kernels: final.weight [C+1, 3] (models.py:230), else NULL
     float* head_dots;         // HEAD kernels: [B, Lpos, 4] fp32: (sum_c out[l,c] w[c,0], .. w[c,1], .. w[c,2], 0)
     int store_out;            // 0: the activated tensor itself is not needed (only the head dots leave the kernel)
+    int pair2;                // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2): ONE M = 256 MMA per pair, each CTA stages its own
+                              //    A rows and HALF of every weight tile -- halves the weight bytes an SM pulls through the L2
+    int wbox;                 // rows of the weight TMA box (64, or 32 when a pair splits a 64-row weight tile)
     int dbg_mode;             // tools only (-DCGN_ABLATE builds): 1 no tanh, 2 no pack, 4 no stmatrix, 8 no TMA stores, 16 no pooling, 32 no TMEM load
     long long* dbg;           // tools only: [CTA][16 samples][8] clock64 stamps of CTA phases (NULL in production)
 };
@@ -266,8 +269,13 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = F.G;
+    const bool PAIR2 = F.pair2 != 0;
+    const uint32_t cta_rank = PAIR2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0u;
     const int grp = blockIdx.x / G, j_cta = blockIdx.x % G;
-    const int n_tile = j_cta % P.n_tiles, ms = j_cta / P.n_tiles;
+    // pairs: CTAs (2c, 2c+1) of a group share the weights (same n_tile) and own adjacent row slices
+    const int n_tile = PAIR2 ? (j_cta >> 1) % P.n_tiles : j_cta % P.n_tiles;
+    const int ms = PAIR2 ? ((j_cta >> 1) / P.n_tiles) * 2 + (j_cta & 1) : j_cta / P.n_tiles;
     const int row0 = ms * (MT * TC_BLOCK_M);
     const int n_seg = P.n_seg[n_tile];
 
@@ -282,10 +290,14 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
         for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 1); }
+        // pairs: the leader's MMA thread waits until BOTH epilogues have drained an accumulator stage
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), PAIR2 ? 2 : 1); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 2) {
+        if (PAIR2) tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+        else tmem_alloc(smem_u32(tmem_slot), 512);
+    }
     for (int i = threadIdx.x; i < P.bn; i += blockDim.x) s_bias[i] = bias ? bias[(n_tile * P.bn + i) & (P.cout - 1)] : 0.0f;
     if (HEAD) {
         for (int i = threadIdx.x; i < 32 * 3; i += blockDim.x) {
@@ -295,6 +307,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR2) cluster_sync_all();          // the peer's barriers are initialised before any remote arrive / TMA completion
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // everything above touched parameters only; the activations, the exchange buffer and the step counter belong to the previous
@@ -306,30 +319,52 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t ia = 0, pa = 0, ib = 0, pb = 0;
+            const int wbox = F.wbox;
             for (int b = grp; b < F.B; b += F.n_groups) {
                 for (int s = 0; s < n_seg; ++s) {
                     const TcSeg sg = P.seg[n_tile][s];
                     if (sg.a_new) {
                         mbar_wait(a_empty(ia), pa ^ 1);
-                        mbar_expect_tx(a_full(ia), MT * TC2_A_BYTES);
+                        if (!PAIR2) {
+                            mbar_expect_tx(a_full(ia), MT * TC2_A_BYTES);
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt)
-                            tma_load_3d(sA + (ia * MT + mt) * TC2_A_SLOT, sg.src ? &tm_a1 : &tm_a0, a_full(ia), sg.col,
-                                        row0 + mt * TC_BLOCK_M + sg.load_shift, b);
+                            for (int mt = 0; mt < MT; ++mt)
+                                tma_load_3d(sA + (ia * MT + mt) * TC2_A_SLOT, sg.src ? &tm_a1 : &tm_a0, a_full(ia), sg.col,
+                                            row0 + mt * TC_BLOCK_M + sg.load_shift, b);
+                        } else {
+                            // both CTAs' boxes are counted on the LEADER's barrier (its own smem holds this CTA's rows)
+                            if (leader) mbar_expect_tx(a_full(ia), 2 * MT * TC2_A_BYTES);
+                            const uint32_t lbar = mapa_u32(a_full(ia), 0);
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt)
+                                tma_load_3d_2sm(sA + (ia * MT + mt) * TC2_A_SLOT, sg.src ? &tm_a1 : &tm_a0, lbar, sg.col,
+                                                row0 + mt * TC_BLOCK_M + sg.load_shift, b);
+                        }
                         if (++ia == (uint32_t)SA) { ia = 0; pa ^= 1; }
                     }
                     mbar_wait(b_empty(ib), pb ^ 1);
-                    mbar_expect_tx(b_full(ib), (uint32_t)sg.n_cnt * TC_BLOCK_K * 2);
                     const int wrow = n_tile * P.bn + sg.n_off;
-                    for (int j = 0; j < sg.n_cnt; j += 64)
-                        tma_load_2d(sB + ib * b_bytes + (uint32_t)j * 128, &tm_w, b_full(ib), sg.wk, wrow + j);
+                    if (!PAIR2) {
+                        mbar_expect_tx(b_full(ib), (uint32_t)sg.n_cnt * TC_BLOCK_K * 2);
+                        for (int j = 0; j < sg.n_cnt; j += 64)
+                            tma_load_2d(sB + ib * b_bytes + (uint32_t)j * 128, &tm_w, b_full(ib), sg.wk, wrow + j);
+                    } else {
+                        // this CTA stages weight rows [rank * n/2, (rank + 1) * n/2) at the start of its slot: the MMA reads B rows
+                        // [0, n/2) from the leader's shared memory and [n/2, n) from the peer's, at the same offset
+                        if (leader) mbar_expect_tx(b_full(ib), (uint32_t)sg.n_cnt * TC_BLOCK_K * 2);
+                        const uint32_t lbar = mapa_u32(b_full(ib), 0);
+                        const int half = sg.n_cnt >> 1;
+                        const int r0 = wrow + (int)cta_rank * half;
+                        for (int j = 0; j < half; j += wbox)
+                            tma_load_2d_2sm(sB + ib * b_bytes + (uint32_t)j * 128, &tm_w, lbar, sg.wk, r0 + j);
+                    }
                     if (++ib == (uint32_t)SB) { ib = 0; pb ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (pairs: the leader CTA only) =====================
+        if (lane == 0 && leader) {
             uint32_t ia = 0, pa = 0, ib = 0, pb = 0, cur_a = 0;
             const uint64_t desc_hi = make_sw128_desc(0, 0);
             int it = 0;
@@ -348,24 +383,37 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     }
                     mbar_wait(b_full(ib), pb);
                     tc_fence_after();
-                    const uint32_t idesc = make_idesc(TC_BLOCK_M, (uint32_t)sg.n_cnt);
-                    const uint64_t bd0 = desc_hi | (uint64_t)((sB + ib * b_bytes) >> 4);
+                    const uint32_t idesc = make_idesc(PAIR2 ? 2 * TC_BLOCK_M : TC_BLOCK_M, (uint32_t)sg.n_cnt);
+                    const uint64_t bd0 = desc_hi | (uint64_t)(((sB + ib * b_bytes) & 0x3FFFFu) >> 4);
                     const uint32_t acc_first = s > 0 ? 1u : 0u;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         const uint32_t a0 = sA + (cur_a * MT + mt) * TC2_A_SLOT + (uint32_t)sg.desc_row * 128u;
-                        const uint64_t ad0 = desc_hi | (uint64_t)(a0 >> 4);
+                        const uint64_t ad0 = desc_hi | (uint64_t)((a0 & 0x3FFFFu) >> 4);
                         const uint32_t d = acc0 + (uint32_t)(mt * P.bn + sg.n_off);
-                        umma_bf16(d, ad0, bd0, idesc, acc_first);
-                        umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u);
-                        umma_bf16(d, ad0 + 4, bd0 + 4, idesc, 1u);
-                        umma_bf16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+                        if (PAIR2) {
+                            umma_bf16_2sm(d, ad0, bd0, idesc, acc_first);
+                            umma_bf16_2sm(d, ad0 + 2, bd0 + 2, idesc, 1u);
+                            umma_bf16_2sm(d, ad0 + 4, bd0 + 4, idesc, 1u);
+                            umma_bf16_2sm(d, ad0 + 6, bd0 + 6, idesc, 1u);
+                        } else {
+                            umma_bf16(d, ad0, bd0, idesc, acc_first);
+                            umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+                            umma_bf16(d, ad0 + 4, bd0 + 4, idesc, 1u);
+                            umma_bf16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+                        }
                     }
-                    umma_commit(b_empty(ib));
-                    if (sg.a_last) umma_commit(a_empty(cur_a));
+                    if (PAIR2) {
+                        umma_commit_2sm(b_empty(ib));
+                        if (sg.a_last) umma_commit_2sm(a_empty(cur_a));
+                    } else {
+                        umma_commit(b_empty(ib));
+                        if (sg.a_last) umma_commit(a_empty(cur_a));
+                    }
                     if (++ib == (uint32_t)SB) { ib = 0; pb ^= 1; }
                 }
-                umma_commit(acc_full(as));
+                if (PAIR2) umma_commit_2sm(acc_full(as));
+                else umma_commit(acc_full(as));
                 CGN_STAMP(7);
             }
         }
@@ -625,7 +673,10 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
             tc_fence_before();
             named_bar_sync(bar_id, NT);
-            if (e == 0 && lane == 0) mbar_arrive(acc_empty(as));
+            if (e == 0 && lane == 0) {
+                if (leader) mbar_arrive(acc_empty(as));
+                else mbar_arrive_cluster(mapa_u32(acc_empty(as), 0));       // the leader issues this pair's MMAs
+            }
             if (tid == 0) CGN_STAMP(5);
         }
         if (lane == 0) tma_wait_all<0>();
@@ -633,9 +684,11 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR2) cluster_sync_all();          // neither CTA leaves (or frees its TMEM) while the pair's MMAs / remote arrives are in flight
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR2) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
     // last CTA out advances the epoch for the next launch (every CTA read it before it could finish)
     if (threadIdx.x == 0) {
@@ -653,7 +706,9 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
 struct CgnPlan {
     TcParams P;
     int MT, G, n_groups, smem, lg;
+    int pair2, wbox;          // CTA pairs (cta_group::2) and the weight TMA box rows they need
 };
+int g_cgn_pair2 = 1;          // gw_set_option("pair2", 0/1): A/B switch for measurements
 
 static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
     int rc = build_params(s, &pl->P, true);
@@ -676,6 +731,17 @@ static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
     GW_REQUIRE(pl->G <= sms, "conv_gn: group larger than the GPU");
     pl->n_groups = sms / pl->G;
     if (pl->n_groups > s->B) pl->n_groups = s->B;
+    // CTA pairs: the row slices of a sample must pair up, and half of every weight tile must be a whole number of 32-row boxes
+    const int m_slices = pl->G / P.n_tiles;
+    pl->pair2 = g_cgn_pair2 && (m_slices % 2 == 0);
+    pl->wbox = 64;
+    for (int t = 0; t < P.n_tiles && pl->pair2; ++t)
+        for (int i = 0; i < P.n_seg[t]; ++i) {
+            const int half = P.seg[t][i].n_cnt / 2;
+            if (half % 32 != 0) pl->pair2 = 0;
+            else if (half % 64 != 0) pl->wbox = 32;
+        }
+    if (!pl->pair2) pl->wbox = 64;
     const int nca = (Cc == 1 || Cc == 5) ? Cc : CGN_NCA_MAX;
     const int misc = 256 + 1024 + CGN_EPI_GROUPS * (1024 + CGN_MAX_G * 64 + 2048 + 2048 + 1024 * nca) + 64 + (pl->lg == 3 ? 768 : 0);
     // ring / staging depths: prefer deep rings, shrink until the CTA fits
@@ -745,7 +811,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
     if (raw != nullptr && (rc = make_map3(&tr, raw, oc, (uint64_t)P.rows, (uint64_t)s->B, 64, 32)) != GW_OK) return rc;
     tp = to;
     if (pooled != nullptr && (rc = make_map3(&tp, pooled, oc, (uint64_t)(P.rows / 2), (uint64_t)s->B, 64, 16)) != GW_OK) return rc;
-    if ((rc = make_map2(&tw, packed, (uint64_t)P.k_total, (uint64_t)P.n_tiles * P.bn, 64, 64)) != GW_OK) return rc;
+    if ((rc = make_map2(&tw, packed, (uint64_t)P.k_total, (uint64_t)P.n_tiles * P.bn, 64, (uint32_t)pl.wbox)) != GW_OK) return rc;
     GnFuseArgs F;
     F.gn_w = gn_w; F.gn_b = gn_b; F.cond = cond; F.wc = wc; F.bc = bc; F.film = film; F.step_ptr = step_ptr;
     F.stats_out = stats_out;
@@ -755,6 +821,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
     F.Cc = Cc; F.G = pl.G; F.n_groups = pl.n_groups; F.B = s->B; F.Lpos = s->L; F.write_raw = raw != nullptr ? 1 : 0;
     F.pair = s->pair == 1 ? 1 : 0;
     F.head_w = head_w; F.head_dots = head_dots; F.store_out = out != nullptr ? 1 : 0;
+    F.pair2 = pl.pair2; F.wbox = pl.wbox;
     F.dbg = g_cgn_dbg;
     F.dbg_mode = g_cgn_dbg_mode;
     cudaStream_t st = (cudaStream_t)stream;
@@ -763,7 +830,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
 #define CGN_GO(LG, MTV, CCV, PL)                                                                                          \
     do {                                                                                                                  \
         GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<LG, MTV, CCV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        GW_CUDA(gw_launch_pdl(conv_gn_kernel<LG, MTV, CCV, PL>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+        GW_CUDA(gw_launch_cluster(conv_gn_kernel<LG, MTV, CCV, PL>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, pl.pair2 ? 2 : 1, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
     } while (0)
 #define CGN_CC(LG, MTV, PL)                      \
     do {                                         \
@@ -774,7 +841,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
 #define CGN_GOH(CCV)                                                                                                      \
     do {                                                                                                                  \
         GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<3, 2, CCV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        GW_CUDA(gw_launch_pdl(conv_gn_kernel<3, 2, CCV, false, true>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+        GW_CUDA(gw_launch_cluster(conv_gn_kernel<3, 2, CCV, false, true>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, pl.pair2 ? 2 : 1, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
     } while (0)
     if (pl.lg == 3 && head) {
         if (Cc == 1) CGN_GOH(1);

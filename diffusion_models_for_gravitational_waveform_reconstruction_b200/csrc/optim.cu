@@ -385,15 +385,28 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     }
 }
 
-// hyper (device, fp32[8]): 0 lr, 1 bias_correction1, 2 sqrt(bias_correction2), 3 ema_decay (<0: no EMA), 4 weight_decay,
-//                          5 max_norm (<=0: no clipping), 6 grad_scale (1/world applied before the norm), 7 unused
-// info (device, fp32[4]) out: 0 total grad norm (after grad_scale), 1 clip coefficient, 2 1 if the step was applied
+// hyper (device, fp32[16]) -- constants of the run, uploaded once (nothing here changes per step):
+//   0 base lr, 3 ema_decay (<0: no EMA), 4 weight_decay, 5 max_norm (<=0: no clipping), 6 grad_scale (1/world, applied before the
+//   norm), 7 skip_loss_threshold (<=0: off; train.py:428-436), 8 warmup_steps, 9 total_steps, 10 min_lr_scale, 11 use_sched (0/1)
+// state (device, int32[4]): 0 = optimisation steps APPLIED so far (train.py: a skipped batch `continue`s before optimizer.step
+//   and scheduler.step, so neither the bias correction nor the LR schedule advances); advanced by gw_train_advance.
+// info (device, fp32[8]) out: 0 total grad norm (after grad_scale), 1 clip coefficient, 2 1 if the step was applied, 3 lr used,
+//   4 batch loss (mean over ranks when the bucket carries it)
+// lossv: the batch loss; with g_has_loss it is g[n] * grad_scale (the loss rides in the bucket's extra slot through the
+//   all-reduce, so every rank takes the same skip decision), else *loss (may be NULL).
+__device__ __forceinline__ double warmup_cosine_dev(double step, double warmup, double total, double min_scale) {   // train.py:85-90
+    if (step < warmup) return fmax(1e-8, (step + 1.0) / fmax(1.0, warmup));
+    double progress = (step - warmup) / fmax(1.0, total - warmup);
+    progress = fmin(fmax(progress, 0.0), 1.0);
+    return min_scale + 0.5 * (1.0 - min_scale) * (1.0 + cos(3.14159265358979323846 * progress));
+}
 __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, float* __restrict__ ema, long n,
                                                         const double* __restrict__ partial, int n_partial,
                                                         const float* __restrict__ hyper, const float* __restrict__ loss,
-                                                        float beta1, float beta2, float eps, float* __restrict__ info) {
-    __shared__ float s_coef;
+                                                        int g_has_loss, const int* __restrict__ state, double beta1d,
+                                                        double beta2d, float eps, float* __restrict__ info) {
+    __shared__ float s_coef, s_lr, s_bc1, s_bc2s;
     __shared__ int s_ok;
     if (threadIdx.x < 32) {
         double a = 0.0;
@@ -405,20 +418,36 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
             const float max_norm = hyper[5];
             float coef = 1.0f;
             if (max_norm > 0.0f) coef = fminf(max_norm / (norm + 1e-6f), 1.0f);    // torch clip_grad_norm_
-            const bool ok = isfinite(norm) && (loss == nullptr || isfinite(loss[0]));   // train.py:424-427 skips the batch
+            float lossv = 0.0f;
+            bool have_loss = false;
+            if (g_has_loss) { lossv = g[n] * gs; have_loss = true; }
+            else if (loss != nullptr) { lossv = loss[0]; have_loss = true; }
+            const float thr = hyper[7];
+            bool ok = isfinite(norm) && (!have_loss || isfinite(lossv));            // train.py:424-427 skips the batch
+            if (ok && have_loss && thr > 0.0f && lossv > thr) ok = false;           // train.py:428-436 (--skip_bad_batches)
+            const int applied = state != nullptr ? state[0] : 0;
+            const double lam = hyper[11] != 0.0f ? warmup_cosine_dev((double)applied, (double)hyper[8], (double)hyper[9], (double)hyper[10]) : 1.0;
+            const float lr = (float)((double)hyper[0] * lam);
+            const double stepd = (double)(applied + 1);
             s_coef = coef * gs;
             s_ok = ok ? 1 : 0;
+            s_lr = lr;
+            s_bc1 = (float)(1.0 - pow(beta1d, stepd));
+            s_bc2s = (float)sqrt(1.0 - pow(beta2d, stepd));
             if (blockIdx.x == 0) {
                 info[0] = norm;
                 info[1] = coef;
                 info[2] = ok ? 1.0f : 0.0f;
+                info[3] = lr;
+                info[4] = lossv;
             }
         }
     }
     __syncthreads();
     if (!s_ok) return;
     const float coef = s_coef;
-    const float lr = hyper[0], bc1 = hyper[1], bc2s = hyper[2], decay = hyper[3], wd = hyper[4];
+    const float lr = s_lr, bc1 = s_bc1, bc2s = s_bc2s, decay = hyper[3], wd = hyper[4];
+    const float beta1 = (float)beta1d, beta2 = (float)beta2d;
     const float step_size = lr / bc1;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const float gi = g[i] * coef;
@@ -443,12 +472,63 @@ extern "C" int gw_grad_sumsq(const float* g, long n, double* partial, void* stre
     return GW_OK;
 }
 extern "C" int gw_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, long n, const double* partial,
-                            const float* hyper, const float* loss, float beta1, float beta2, float eps, float* info,
-                            void* stream) {
+                            const float* hyper, const float* loss, int g_has_loss, const int* state, double beta1, double beta2,
+                            float eps, float* info, void* stream) {
     GW_REQUIRE(n > 0 && hyper != nullptr && info != nullptr && partial != nullptr, "gw_adamw_ema: arguments");
     int grid = (int)((n + 1023) / 1024);
     if (grid > 148 * 4) grid = 148 * 4;
-    adamw_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, partial, OPT_PARTIALS, hyper, loss, beta1, beta2, eps, info);
+    adamw_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, partial, OPT_PARTIALS, hyper, loss, g_has_loss, state,
+                                                             beta1, beta2, eps, info);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// gradient bucket reset before the backward pass: g[0, n) = 0 and (loss != NULL) g[n] = *loss, the extra slot that carries the
+// batch loss through the all-reduce
+__global__ void __launch_bounds__(256) bucket_reset_kernel(float4* __restrict__ g4, long n4, float* __restrict__ g, long n,
+                                                           const float* __restrict__ loss) {
+    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) g4[i] = z;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (long i = n4 * 4; i < n; ++i) g[i] = 0.0f;
+        if (loss != nullptr) g[n] = loss[0];
+    }
+}
+extern "C" int gw_bucket_reset(float* g, long n, const float* loss, void* stream) {
+    GW_REQUIRE(g != nullptr && n > 0 && ((uintptr_t)g & 15) == 0, "gw_bucket_reset: g must be 16-byte aligned");
+    int grid = (int)((n / 4 + 255) / 256);
+    if (grid > 148 * 2) grid = 148 * 2;
+    if (grid < 1) grid = 1;
+    bucket_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(g), n / 4, g, n, loss);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// end of an optimisation step: the Philox draw counter always advances (the reference consumes its RNG on skipped batches
+// too), the applied-step counter only when gw_adamw_ema applied the update (info[2])
+__global__ void train_advance_kernel(int* step_ctr, int* state, const float* info) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (step_ctr != nullptr) *step_ctr += 1;
+        if (state != nullptr) {
+            if (info == nullptr || info[2] != 0.0f) state[0] += 1;
+            else state[1] += 1;                                 // skipped batches (train.py: skipped_batches)
+        }
+    }
+}
+extern "C" int gw_train_advance(int* step_ctr, int* state, const float* info, void* stream) {
+    train_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_ctr, state, info);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// loss weight (train.py:414-417): wt[b] = (1 - alpha_bar[t_b])^power
+__global__ void loss_weight_kernel(const long long* __restrict__ t, const float* __restrict__ ab, float power, float* __restrict__ wt, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) wt[b] = powf(1.0f - ab[t[b]], power);
+}
+extern "C" int gw_loss_weight(const int64_t* t, const float* alpha_bar, float power, float* wt, int B, void* stream) {
+    GW_REQUIRE(t != nullptr && alpha_bar != nullptr && wt != nullptr && B > 0, "gw_loss_weight: arguments");
+    loss_weight_kernel<<<gw_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>((const long long*)t, alpha_bar, power, wt, B);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

@@ -308,12 +308,20 @@ class _UNetFunction(torch.autograd.Function):
         net = x.detach().contiguous().float()
         eps = bwd.forward(net, t.reshape(-1).expand(net.shape[0]) if t.numel() == 1 else t)
         ctx.bwd, ctx.net, ctx.n_params = bwd, net, len(params)
+        # the saved activations live in the engine workspace shared per (B, L): stamp it, so a second grad-enabled forward of
+        # the same shape before this one's backward is an error instead of silently wrong gradients
+        ws = bwd.eng.workspace(net.shape[0], net.shape[2], True)
+        ws.fwd_gen = getattr(ws, "fwd_gen", 0) + 1
+        ctx.ws, ctx.gen = ws, ws.fwd_gen
         ctx.names = [k for k, _ in model.named_parameters()]
         return eps
 
     @staticmethod
     def backward(ctx, d_eps):
         bwd = ctx.bwd
+        if ctx.ws.fwd_gen != ctx.gen:
+            raise RuntimeError("gwb200 UNet1D: another grad-enabled forward of the same (batch, length) ran before this backward; "
+                               "the saved activations were overwritten (call backward() first, or use torch.no_grad())")
         flat = torch.zeros(bwd.layout.total, device=d_eps.device, dtype=torch.float32)
         B, _, L = ctx.net.shape
         bwd.backward(ctx.net, d_eps.contiguous().float().reshape(B, L), flat)
@@ -414,7 +422,14 @@ class FusedTrainStep:
                  loss: str = "huber", huber_beta: float = 0.5, loss_weight_power: float = 0.0, clamp_inputs: float = 10.0,
                  p_uncond: float = 0.2, dropout_y_only: bool = True, t_min: int = 500, warmup_steps: int = 0,
                  total_steps: int = 0, min_lr_scale: float = 0.1, cosine_decay: bool = False, seed: int = 0,
-                 compute_dtype: Optional[str] = None, conv_impl: str = "auto", process_group=None, sample0: int = 0):
+                 compute_dtype: Optional[str] = None, conv_impl: str = "auto", process_group=None, sample0: int = 0,
+                 skip_loss_threshold: float = 0.0, clamp_cond_y: bool = False, world: Optional[int] = None,
+                 share: Optional["FusedTrainStep"] = None):
+        """`skip_loss_threshold` > 0 is `--skip_bad_batches --skip_loss_threshold` (train.py:428-436), decided on the device.
+        `clamp_cond_y`: the y channel of the conditioning stack is the clamped one (what train.py:360-369 builds for t_multi > 1).
+        `share`: another stepper of the same model (a different batch size / length): parameters, gradients, AdamW moments,
+        EMA, the Philox step counter and the applied-step counter are SHARED, so alternating between shapes continues one
+        optimisation run (train_diffusion on ragged batches)."""
         import torch.distributed as dist
         self.model, self.diffusion = model, diffusion
         self.B, self.L = B, L
@@ -430,16 +445,25 @@ class FusedTrainStep:
         shapes = {k: tuple(p.shape) for k, p in model.named_parameters()}
         self.layout = ParamLayout(sp, shapes)
         n = self.layout.total
-        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
-        views = self.layout.views(self.flat_p)
-        with torch.no_grad():
-            for k, p in model.named_parameters():
-                views[k].copy_(p.data)
-                p.data = views[k]
-        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.flat_ema = self.flat_p.clone() if ema_decay is not None else None
+        if share is not None:
+            if share.model is not model:
+                raise ValueError("FusedTrainStep(share=...): the steppers must train the same model")
+            self.flat_p, self.bucket, self.flat_g = share.flat_p, share.bucket, share.flat_g
+            self.flat_m, self.flat_v, self.flat_ema = share.flat_m, share.flat_v, share.flat_ema
+            views = self.layout.views(self.flat_p)
+        else:
+            self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+            views = self.layout.views(self.flat_p)
+            with torch.no_grad():
+                for k, p in model.named_parameters():
+                    views[k].copy_(p.data)
+                    p.data = views[k]
+            # gradient bucket: n gradients + one slot that carries the batch loss through the all-reduce (see gw_bucket_reset)
+            self.bucket = torch.zeros(n + 4, device=dev, dtype=torch.float32)
+            self.flat_g = self.bucket[:n]
+            self.flat_m = torch.zeros(n, device=dev, dtype=torch.float32)
+            self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
+            self.flat_ema = self.flat_p.clone() if ema_decay is not None else None
         self.eng = UNetEngine(views, sp, dtype=cd, conv_impl=conv_impl)
         self.eng.bind_flat(self.flat_p, self.layout)
         self.bwd = BackwardEngine(self.eng, self.layout)
@@ -454,8 +478,12 @@ class FusedTrainStep:
         self.warmup_steps, self.total_steps, self.min_lr_scale = int(warmup_steps), int(total_steps), float(min_lr_scale)
         self.use_sched = warmup_steps > 0 or cosine_decay
         self.seed, self.sample0 = int(seed) & (2 ** 64 - 1), int(sample0)
+        self.skip_loss_threshold, self.clamp_cond_y = float(skip_loss_threshold), bool(clamp_cond_y)
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world is not None:
+            self.world = int(world)
+        else:
+            self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         # ---- step state
         Cx, Cc = sp.in_ch, sp.cond_in_ch
         f32 = dict(device=dev, dtype=torch.float32)
@@ -471,15 +499,18 @@ class FusedTrainStep:
         self.wt = torch.ones(B, **f32) if self.lwp != 0.0 else None
         self.per_sample = torch.zeros(B, **f32)
         self.loss = torch.zeros(1, **f32)
-        self.info = torch.zeros(4, **f32)
-        self.hyper = torch.zeros(8, **f32)
-        self.hyper_host = torch.zeros(64, 8, dtype=torch.float32).pin_memory()     # ring: the host may run ahead of the stream
-        self._hyper_ev: List[Optional[torch.cuda.Event]] = [None] * 64
+        self.info = torch.zeros(8, **f32)
+        self.hyper = torch.zeros(16, **f32)           # run constants; LR schedule / bias corrections are evaluated on the device
+        self._hyper_sent = None
         self.partial = torch.zeros(self.lib.gw_opt_scratch_doubles(), device=dev, dtype=torch.float64)
-        self.step_ctr = torch.zeros(1, device=dev, dtype=torch.int32)
+        if share is not None:
+            self.step_ctr, self.opt_state, self._shared = share.step_ctr, share.opt_state, share._shared
+        else:
+            self.step_ctr = torch.zeros(1, device=dev, dtype=torch.int32)     # Philox draw counter (every attempted step)
+            self.opt_state = torch.zeros(4, device=dev, dtype=torch.int32)    # [0] steps applied, [1] batches skipped
+            self._shared = {"steps_done": 0}
         ab = diffusion.alpha_bar.to(dev).float().contiguous()
         self.ab, self.sab, self.s1mab = ab, ab.sqrt().contiguous(), (1 - ab).sqrt().contiguous()
-        self.steps_done = 0
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.overlap_prep = True                     # dgrad weight preparation on a forked stream / graph branch
         self._side: Optional[torch.cuda.Stream] = None
@@ -536,9 +567,10 @@ class FusedTrainStep:
         which is what the reference stores under 'optimizer_state' (train.py:610)."""
         m, v = self.layout.views(self.flat_m), self.layout.views(self.flat_v)
         names = [k for k, _ in self.model.named_parameters()]
-        state = {i: {"step": torch.tensor(float(self.steps_done)), "exp_avg": m[k].clone(), "exp_avg_sq": v[k].clone()}
+        applied = self.applied_steps()
+        state = {i: {"step": torch.tensor(float(applied)), "exp_avg": m[k].clone(), "exp_avg_sq": v[k].clone()}
                  for i, k in enumerate(names)}
-        group = {"lr": getattr(self, "last_lr", self.lr), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+        group = {"lr": self.last_lr if applied > 0 else self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
                  "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
                  "fused": None, "params": list(range(len(names)))}
         if self.use_sched:
@@ -556,26 +588,35 @@ class FusedTrainStep:
         else:
             self.mask.fill_(1.0)                              # no mask = every sample valid (never the previous batch's mask)
 
+    # steps attempted (host count, shared between steppers of one run); the APPLIED count lives on the device
+    @property
+    def steps_done(self) -> int:
+        return self._shared["steps_done"]
+
+    @steps_done.setter
+    def steps_done(self, v: int) -> None:
+        self._shared["steps_done"] = int(v)
+
+    def applied_steps(self) -> int:
+        """Optimisation steps actually applied (skipped batches excluded); one device read."""
+        return int(self.opt_state[0])
+
+    def skipped_batches(self) -> int:
+        return int(self.opt_state[1])
+
+    @property
+    def last_lr(self) -> float:
+        """Learning rate of the last step (device read)."""
+        return float(self.info[3])
+
     def _set_hyper(self) -> None:
-        step = self.steps_done + 1
-        lr = self.lr * (warmup_cosine_lambda(self.steps_done, self.warmup_steps, self.total_steps, self.min_lr_scale)
-                        if self.use_sched else 1.0)
-        slot = self.steps_done % self.hyper_host.shape[0]
-        if self._hyper_ev[slot] is not None:
-            self._hyper_ev[slot].synchronize()                # the copy that last used this pinned row has completed
-        h = self.hyper_host[slot]
-        h[0] = lr
-        h[1] = 1.0 - self.betas[0] ** step
-        h[2] = math.sqrt(1.0 - self.betas[1] ** step)
-        h[3] = self.ema_decay if self.ema_decay is not None else -1.0
-        h[4] = self.wd
-        h[5] = self.clip_grad
-        h[6] = 1.0 / self.world
-        self.hyper.copy_(h, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self._hyper_ev[slot] = ev
-        self.last_lr = lr
+        """Upload the run constants when they changed (normally once): nothing here depends on the step number."""
+        h = (self.lr, 0.0, 0.0, self.ema_decay if self.ema_decay is not None else -1.0, self.wd, self.clip_grad,
+             1.0 / self.world, self.skip_loss_threshold, float(self.warmup_steps), float(self.total_steps), self.min_lr_scale,
+             1.0 if self.use_sched else 0.0, 0.0, 0.0, 0.0, 0.0)
+        if h != self._hyper_sent:
+            self.hyper.copy_(torch.tensor(h, dtype=torch.float32))
+            self._hyper_sent = h
 
     def _enqueue(self, selfcond: bool, draws: bool, philox: bool) -> None:
         """All kernels of one step on the current stream (capturable: no host reads, no allocation)."""
@@ -600,7 +641,8 @@ class FusedTrainStep:
         check(lib.gw_train_pack(ptr(self.clean), ptr(self.cond) if Cc > 0 else None, Cc, ptr(self.t),
                                 ptr(self.drop) if use_drop else None, ptr(self.sab), ptr(self.s1mab), ptr(self.eps_buf),
                                 1 if philox else 0, self.seed, self.sample0, ptr(self.step_ctr), self.clamp,
-                                1 if (use_drop and y_only) else 0, 0 if y_only else 1, ptr(self.net), B, Cx, L, st), "train_pack")
+                                1 if ((use_drop and y_only) or self.clamp_cond_y) else 0, 0 if y_only else 1, ptr(self.net), B,
+                                Cx, L, st), "train_pack")
         eng.launches += 1
         if selfcond and sp.use_selfcond:                      # train.py:401-403: extra no-grad forward, zero self-cond
             self.bwd.forward(self.net, self.t, self.eps_hat)
@@ -608,11 +650,13 @@ class FusedTrainStep:
             eng.launches += 1
         self.bwd.forward(self.net, self.t, self.eps_hat)
         if self.wt is not None:
-            torch.pow(1.0 - self.ab[self.t], self.lwp, out=self.wt)
+            check(lib.gw_loss_weight(ptr(self.t), ptr(self.ab), self.lwp, ptr(self.wt), B, st), "loss_weight")
+            eng.launches += 1
         check(lib.gw_loss(ptr(self.eps_hat), ptr(self.eps_buf), ptr(self.mask), ptr(self.wt), B, L, self.loss_type,
                           self.huber_beta, 1.0, ptr(self.per_sample), ptr(self.loss), ptr(self.d_eps), st), "loss")
         eng.launches += 2
-        self.flat_g.zero_()
+        check(lib.gw_bucket_reset(ptr(self.bucket), self.layout.total, ptr(self.loss), st), "bucket_reset")
+        eng.launches += 1
         if self.overlap_prep:
             cur.wait_stream(self._side)
         self.bwd._prepped = self.overlap_prep
@@ -626,16 +670,18 @@ class FusedTrainStep:
         n = self.layout.total
         check(lib.gw_grad_sumsq(ptr(self.flat_g), n, ptr(self.partial), st), "grad_sumsq")
         check(lib.gw_adamw_ema(ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v), ptr(self.flat_ema), n,
-                               ptr(self.partial), ptr(self.hyper), ptr(self.loss), self.betas[0], self.betas[1], self.eps,
-                               ptr(self.info), st), "adamw_ema")
+                               ptr(self.partial), ptr(self.hyper), None, 1, ptr(self.opt_state), float(self.betas[0]),
+                               float(self.betas[1]), self.eps, ptr(self.info), st), "adamw_ema")
         self.eng.refresh()                                    # re-pack the bf16 conv weights from the updated fp32 master
-        check(lib.gw_step_advance(ptr(self.step_ctr), -1, st), "step_advance")
+        check(lib.gw_train_advance(ptr(self.step_ctr), ptr(self.opt_state), ptr(self.info), st), "train_advance")
         self.eng.launches += 3
 
     def _allreduce(self) -> None:
+        """Sum of the gradient bucket (+ the loss slot) over the ranks; the 1/world scale is applied in gw_adamw_ema.  NCCL
+        collectives are capturable, so inside `_capture` this becomes a node of the step's CUDA graph."""
         if self.world > 1:
             from .parallel import allreduce_flat_
-            allreduce_flat_(self.flat_g, self.pg)             # the 1/world scale is applied in gw_adamw_ema
+            allreduce_flat_(self.bucket[: self.layout.total + 1], self.pg)
 
     # ------------------------------------------------------------------ public
     def step(self, *, selfcond: bool = False, t: Optional[Tensor] = None, eps: Optional[Tensor] = None,
@@ -658,48 +704,52 @@ class FusedTrainStep:
         elif not draws:
             self.drop.zero_()
         self._set_hyper()
+        if self._shared.get("owner") is not self:             # another stepper of this run updated the shared parameters:
+            if self._shared.get("owner") is not None:         # my packed bf16 conv weights are stale
+                self.eng.refresh()
+            self._shared["owner"] = self
         if not use_graph:
             self._enqueue(selfcond, draws, philox)
             self._allreduce()
             self._enqueue_update()
         else:
             key = (bool(selfcond), draws, philox, self.p_uncond, self.t_min)
-            gs = self._graphs.get(key)
-            if gs is None:
-                gs = self._capture(key)
-            gs[0].replay()
-            self._allreduce()
-            gs[1].replay()
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._capture(key)
+            g.replay()
         self.steps_done += 1
         # the flat buffer changed under the module's parameter views (no torch version bump): engines that UNet1D.engine()
         # hands out (model(x, t), ddim_sample(model, ...)) must re-pack their bf16 weights / FiLM tables on next use
         self.model._versions = None
 
     def _capture(self, key):
-        """Two graphs per step flavour: [pack .. backward] and [norm .. AdamW/EMA .. re-pack]; the NCCL all-reduce of the
-        flat gradient bucket runs between them on the same stream."""
+        """ONE graph per step flavour: [draws, pack, (self-cond fwd), fwd, loss, backward, all-reduce, norm, clip+AdamW+EMA,
+        re-pack, advance].  The NCCL all-reduce of the gradient bucket is captured with the kernels, so a step is a single
+        graph launch with no host work between the backward pass and the optimiser."""
         selfcond, draws, philox = key[:3]
-        saved = [b.clone() for b in (self.flat_p, self.flat_m, self.flat_v, self.step_ctr)]
+        saved = [b.clone() for b in (self.flat_p, self.flat_m, self.flat_v, self.step_ctr, self.opt_state)]
         saved_ema = self.flat_ema.clone() if self.flat_ema is not None else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):                            # warm-up: lazy packing, cudaFuncSetAttribute
+        with torch.cuda.stream(s):                            # warm-up: lazy packing, cudaFuncSetAttribute, NCCL channels
             self._enqueue(selfcond, draws, philox)
+            self._allreduce()
             self._enqueue_update()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        for b, sv in zip((self.flat_p, self.flat_m, self.flat_v, self.step_ctr), saved):
+        for b, sv in zip((self.flat_p, self.flat_m, self.flat_v, self.step_ctr, self.opt_state), saved):
             b.copy_(sv)
         if saved_ema is not None:
             self.flat_ema.copy_(saved_ema)
         self.eng.refresh()
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             self._enqueue(selfcond, draws, philox)
-        with torch.cuda.graph(g2):
+            self._allreduce()
             self._enqueue_update()
-        self._graphs[key] = (g1, g2)
-        return self._graphs[key]
+        self._graphs[key] = g
+        return g
 
 
 # ======================================================================================================
@@ -732,7 +782,9 @@ def train_diffusion(args, loader=None):
         ckpt = torch.load(args.init_from, map_location=device)
         model.load_state_dict(ckpt.get("model_ema_state", ckpt.get("model_state")), strict=True)
     total_steps = len(loader) * args.epochs
-    stepper = None
+    stepper, first = None, None
+    steppers: Dict[tuple, FusedTrainStep] = {}
+    max_shapes = int(getattr(args, "max_cached_shapes", 4))
     rng = random.Random(getattr(args, "seed", 0) or 0)
     history = []
     for epoch in range(1, args.epochs + 1):
@@ -752,21 +804,27 @@ def train_diffusion(args, loader=None):
             mask = mask.to(device).float()
             if K > 1:
                 clean_norm, cond_stack, mask = (a.repeat_interleave(K, dim=0) for a in (clean_norm, cond_stack, mask))
-            if stepper is None or stepper.B != clean_norm.shape[0] or stepper.L != clean_norm.shape[-1]:
-                prev = stepper
-                stepper = FusedTrainStep(model, diffusion, clean_norm.shape[0], clean_norm.shape[-1], lr=args.lr,
+            key = (int(clean_norm.shape[0]), int(clean_norm.shape[-1]))
+            stepper = steppers.get(key)
+            if stepper is None:
+                # pad_collate pads to the per-batch maximum (dataloader.py:248-268), so (B, L) may change from batch to batch:
+                # one stepper (workspace + captured graphs) per shape, all SHARING parameters, gradient bucket, AdamW moments,
+                # EMA, the Philox draw counter and the applied-step counter -- the run continues, it does not restart
+                if len(steppers) >= max_shapes:
+                    steppers.pop(next(iter(steppers)))          # oldest shape: its workspace / graphs are released
+                thr = float(getattr(args, "skip_loss_threshold", 0.0)) if getattr(args, "skip_bad_batches", False) else 0.0
+                stepper = FusedTrainStep(model, diffusion, key[0], key[1], lr=args.lr,
                                          weight_decay=args.weight_decay, clip_grad=args.clip_grad,
                                          ema_decay=args.ema_decay if args.ema else None, loss=args.loss,
                                          huber_beta=args.huber_beta, loss_weight_power=args.loss_weight_power,
                                          clamp_inputs=args.clamp_inputs, p_uncond=p_uncond,
                                          dropout_y_only=args.dropout_y_only, t_min=t_min, warmup_steps=args.warmup_steps,
                                          total_steps=total_steps, min_lr_scale=args.min_lr_scale,
-                                         cosine_decay=args.cosine_decay, seed=getattr(args, "seed", 0) or 0)
-                if prev is not None:                           # ragged last batch: carry the optimiser state over
-                    for a, b in ((stepper.flat_m, prev.flat_m), (stepper.flat_v, prev.flat_v), (stepper.flat_ema, prev.flat_ema)):
-                        if a is not None and b is not None:
-                            a.copy_(b)
-                    stepper.steps_done = prev.steps_done
+                                         cosine_decay=args.cosine_decay, seed=getattr(args, "seed", 0) or 0,
+                                         skip_loss_threshold=thr, clamp_cond_y=(K > 1 and args.clamp_inputs > 0), share=first)
+                steppers[key] = stepper
+                if first is None:
+                    first = stepper
             stepper.p_uncond, stepper.t_min = p_uncond, t_min
             stepper.load_batch(clean_norm, cond_stack, mask)
             t_inj = None

@@ -292,13 +292,26 @@ int gw_selfcond_x0(float* net, const float* eps_hat, const int64_t* t, const flo
 
 /* clip_grad_norm_ + AdamW + EMA (train.py:445-455, 73-81) over flat fp32 buffers of n elements.
  * gw_grad_sumsq writes gw_opt_scratch_doubles() partial sums; gw_adamw_ema finishes the norm, clips, updates.
- * hyper (device fp32[8]): lr, 1-beta1^t, sqrt(1-beta2^t), ema_decay (<0 none), weight_decay, max_norm (<=0 none),
- * grad_scale (1/world), unused.  info (device fp32[4]) out: grad norm, clip coefficient, applied flag.
- * The update is skipped when the norm or *loss is not finite (train.py:424-427). */
+ * hyper (device fp32[16], constants of the run): 0 base lr, 3 ema_decay (<0 none), 4 weight_decay, 5 max_norm (<=0 none),
+ *   6 grad_scale (1/world), 7 skip_loss_threshold (<=0 off; train.py:428-436), 8 warmup_steps, 9 total_steps, 10 min_lr_scale,
+ *   11 use_sched.  The LR schedule (train.py:84-91) and Adam's bias corrections are evaluated ON THE DEVICE from
+ * state (device int32[4]): [0] optimisation steps applied so far, [1] batches skipped -- a skipped batch (non-finite loss or
+ *   gradient norm, train.py:424-427; loss above the threshold, :428-436) leaves parameters, moments, EMA, schedule and bias
+ *   correction untouched, exactly like the reference's `continue`, and no host read is needed.
+ * loss: device scalar or NULL; g_has_loss != 0: the batch loss is g[n] * grad_scale instead (written by gw_bucket_reset, so it
+ *   went through the same all-reduce as the gradients and every rank decides alike).
+ * info (device fp32[8]) out: grad norm, clip coefficient, applied flag, lr used, loss seen. */
 int gw_opt_scratch_doubles(void);
 int gw_grad_sumsq(const float* g, long n, double* partial, void* stream);
 int gw_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, long n, const double* partial,
-                 const float* hyper, const float* loss, float beta1, float beta2, float eps, float* info, void* stream);
+                 const float* hyper, const float* loss, int g_has_loss, const int* state, double beta1, double beta2,
+                 float eps, float* info, void* stream);
+/* g[0, n) = 0 (16-byte aligned), and g[n] = *loss when loss != NULL (the bucket's extra slot). */
+int gw_bucket_reset(float* g, long n, const float* loss, void* stream);
+/* *step_ctr += 1 (Philox draw counter); state[0] += 1 if info[2] (step applied) else state[1] += 1. */
+int gw_train_advance(int* step_ctr, int* state, const float* info, void* stream);
+/* wt[b] = (1 - alpha_bar[t_b])^power (train.py:414-417) */
+int gw_loss_weight(const int64_t* t, const float* alpha_bar, float power, float* wt, int B, void* stream);
 
 /* =====================================================================================================
  * On-device scoring of reconstructions (inference.py:11-27, 247-279, 303-314; sweep_infer.py:8-13, 225-241).

@@ -236,3 +236,26 @@ def test_fused_head_dots(in_ch, cc, L, B):
         with torch.no_grad():
             eps_o = oracle.unet_forward(sd, cfg, x, t)
         assert rel_l2(eps_a.cpu(), eps_o) <= BF16_TOL
+
+
+@pytest.mark.parametrize("in_ch,cc,L,B", [(3, 1, 4096, 21), (7, 5, 4096, 5), (3, 1, 16384, 2), (7, 5, 512, 3)])
+def test_cta_pair_mma_equals_single_cta(in_ch, cc, L, B):
+    """conv_gn_kernel with tcgen05 CTA pairs (cta_group::2: one M = 256 MMA per pair, each CTA staging half of every weight
+    tile) accumulates every output row in the same K order as the single-CTA kernel: results are bit-identical."""
+    sd = make_state_dict(in_ch, cc, seed=0)
+    x = gaussian((B, in_ch, L), seed=9 + L)
+    t = torch.tensor(([24, 999, 500, 3, 250] * B)[:B])
+    eng = _engine(sd, in_ch, cc, "bf16", "tc")
+    outs = []
+    try:
+        for pair2 in (0, 1):
+            assert eng.lib.gw_set_option(b"pair2", pair2) == 0
+            for _ in range(2):
+                eps = eng.forward(x.cuda(), t.cuda())
+            ws = eng.workspace(B, L, False)
+            outs.append((eps.clone(), [o.clone() for o in ws.out[:6]], [p.clone() for p in ws.pooled]))
+    finally:
+        eng.lib.gw_set_option(b"pair2", 1)
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
+        assert torch.equal(a, b)

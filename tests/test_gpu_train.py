@@ -70,7 +70,7 @@ def test_fused_step_fp32_vs_oracle_and_reference_golden(golden_dir, in_ch, cc, s
         torch.cuda.synchronize()
         assert abs(float(st.loss) - float(g[f"loss{step}"])) <= 2e-6 * max(1.0, abs(float(g[f"loss{step}"]))), step
         assert abs(float(st.info[0]) - float(g[f"grad_norm{step}"])) <= 2e-5 * float(g[f"grad_norm{step}"]), step
-        assert abs(st.last_lr - float(g[f"lr{step}"])) <= 1e-12
+        assert abs(st.last_lr - float(g[f"lr{step}"])) <= 1e-7 * float(g[f"lr{step}"])      # fp32 device scalar
         if step == 0:
             assert rel_l2(st.eps_hat, eps_hat_o) <= 1e-5
             assert rel_l2(st.eps_hat, torch.from_numpy(g["eps_hat"])) <= 1e-5
@@ -319,3 +319,71 @@ def test_non_default_architectures(base_ch, depth, time_dim, cd, tol):
     for k, go in grads_o.items():
         err = float((grads[k].cpu().double() - go.double()).norm())
         assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))
+
+
+def test_skip_bad_batches_decided_on_device():
+    """--skip_bad_batches / --skip_loss_threshold (train.py:428-436): a batch whose loss exceeds the threshold leaves parameters,
+    AdamW moments, EMA, the LR schedule and the bias-correction step untouched -- with no host read in the step."""
+    in_ch, cc, B, L = 3, 1, 4, 256
+    sd, clean, cond, mask, t, eps, drop = _case(in_ch, cc, B, L)
+    m, st = _stepper(sd, in_ch, cc, B, L, "fp32", skip_loss_threshold=1e-6)
+    st.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+    p0, m0, e0 = st.flat_p.clone(), st.flat_m.clone(), st.flat_ema.clone()
+    for use_graph in (False, True):
+        st.step(t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=use_graph)
+    torch.cuda.synchronize()
+    assert float(st.info[2]) == 0.0 and st.applied_steps() == 0 and st.skipped_batches() == 2 and st.steps_done == 2
+    assert torch.equal(st.flat_p, p0) and torch.equal(st.flat_m, m0) and torch.equal(st.flat_ema, e0)
+    assert int(st.step_ctr) == 2                              # the Philox draw counter advances like the reference's RNG
+    st.skip_loss_threshold = 1e6
+    st.step(t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=True)
+    torch.cuda.synchronize()
+    assert float(st.info[2]) == 1.0 and st.applied_steps() == 1
+    assert not torch.equal(st.flat_p, p0)
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import warmup_cosine_lambda
+    assert abs(st.last_lr - 2e-4 * warmup_cosine_lambda(0, 10, 100, 0.1)) <= 1e-10      # first APPLIED step: schedule step 0
+    # and the applied step equals the very first step of a run that never skipped
+    m2, st2 = _stepper(sd, in_ch, cc, B, L, "fp32")
+    st2.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+    st2.step(t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=False)
+    torch.cuda.synchronize()
+    assert torch.allclose(st.flat_p, st2.flat_p, rtol=0, atol=1e-8)
+
+
+def test_steppers_of_different_shapes_share_one_run():
+    """train_diffusion on ragged batches (pad_collate pads to the per-batch maximum): steppers of different (B, L) share
+    parameters, optimiser state and the Philox step counter, so the draws continue instead of restarting."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import FusedTrainStep
+    in_ch, cc, B = 3, 1, 4
+    sd, clean, cond, mask, t, eps, drop = _case(in_ch, cc, B, 512)
+    m = _model(sd, in_ch, cc, "fp32")
+    d = CustomDiffusion(T=1000, device="cuda")
+    kw = dict(lr=1e-3, p_uncond=0.2, seed=5, warmup_steps=0)
+    a = FusedTrainStep(m, d, B, 256, **kw)
+    b = FusedTrainStep(m, d, B, 512, share=a, **kw)
+    assert b.flat_p.data_ptr() == a.flat_p.data_ptr() and b.step_ctr.data_ptr() == a.step_ctr.data_ptr()
+    a.load_batch(clean[..., :256].cuda(), cond[..., :256].cuda(), None)
+    a.step(use_graph=True)                                   # step 0, on-device draws
+    torch.cuda.synchronize()
+    t_a = a.t.clone()
+    sd1 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    assert float((sd1["mid.0.weight"] - sd["mid.0.weight"]).abs().max()) > 1e-5
+    b.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+    b.step(use_graph=False)                                  # step 1 of the SAME run: new draws, updated weights
+    torch.cuda.synchronize()
+    assert int(a.step_ctr) == 2 and a.steps_done == 2 and b.applied_steps() == 2
+    assert not torch.equal(b.t, t_a)
+    # a single-shape run draws the same t at its second step (Philox keyed on seed, sample index, step)
+    m2 = _model(sd, in_ch, cc, "fp32")
+    c = FusedTrainStep(m2, d, B, 512, **kw)
+    c.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+    c.step(use_graph=False)
+    c.step(use_graph=False)
+    torch.cuda.synchronize()
+    assert torch.equal(c.t, b.t) and torch.equal(c.eps_buf, b.eps_buf)
+    # b's forward ran on the weights a's step produced (its packed copies were refreshed)
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True)
+    with torch.no_grad():
+        ref = oracle.unet_forward(sd1, cfg, b.net.cpu(), b.t.cpu())
+    assert rel_l2(b.eps_hat, ref) <= 1e-5

@@ -235,7 +235,9 @@ __device__ __forceinline__ void stat_reduce(float (&sv)[2 * (64 >> CG_LOG2)], fl
 // HEAD (Cout = 64 decoder in pair space only): the head conv final(cat[h, x_t]) reads nothing but three dot products per position
 // of this block's output, so the epilogue forms them from the fp32 values it already holds (gw_final_step then runs on 16 B per
 // position instead of streaming the 128 B row back in).
-template <int CG_LOG2, int MT, int CC, bool POOL, bool HEAD = false>
+// PAIR2: CTA pairs (cluster of 2, tcgen05 cta_group::2), a compile-time flavour: a kernel that contains .2CTA instructions can
+// only be launched with an even cluster size.
+template <int CG_LOG2, int MT, int CC, bool POOL, bool HEAD = false, bool PAIR2 = false>
 __global__ void __launch_bounds__(CGN_THREADS, 1)
 conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out,
@@ -245,7 +247,9 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int SA = P.sa, SB = P.sb, NBUF = P.nbuf;
-    const uint32_t b_bytes = (uint32_t)P.bn * TC_BLOCK_K * 2;
+    // B ring slot: the whole weight tile of a segment, or (pairs) the half this CTA stages -- half the bytes per slot buys a
+    // ring twice as deep, i.e. twice as many segments in flight against the L2 -> shared-memory latency
+    const uint32_t b_bytes = (uint32_t)P.bn * TC_BLOCK_K * (PAIR2 ? 1 : 2);
     const uint32_t sA = base;                                           // [SA][MT][A_SLOT]
     const uint32_t sB = sA + (uint32_t)SA * MT * TC2_A_SLOT;            // [SB][b_bytes]
     constexpr uint32_t EW = 8u * CGN_EPI_GROUPS;                        // epilogue warps
@@ -269,7 +273,6 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = F.G;
-    const bool PAIR2 = F.pair2 != 0;
     const uint32_t cta_rank = PAIR2 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0u;
     const int grp = blockIdx.x / G, j_cta = blockIdx.x % G;
@@ -731,6 +734,8 @@ static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
     GW_REQUIRE(pl->G <= sms, "conv_gn: group larger than the GPU");
     pl->n_groups = sms / pl->G;
     if (pl->n_groups > s->B) pl->n_groups = s->B;
+    const int nca = (Cc == 1 || Cc == 5) ? Cc : CGN_NCA_MAX;
+    const int misc = 256 + 1024 + CGN_EPI_GROUPS * (1024 + CGN_MAX_G * 64 + 2048 + 2048 + 1024 * nca) + 64 + (pl->lg == 3 ? 768 : 0);
     // CTA pairs: the row slices of a sample must pair up, and half of every weight tile must be a whole number of 32-row boxes
     const int m_slices = pl->G / P.n_tiles;
     pl->pair2 = g_cgn_pair2 && (m_slices % 2 == 0);
@@ -742,15 +747,18 @@ static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
             else if (half % 64 != 0) pl->wbox = 32;
         }
     if (!pl->pair2) pl->wbox = 64;
-    const int nca = (Cc == 1 || Cc == 5) ? Cc : CGN_NCA_MAX;
-    const int misc = 256 + 1024 + CGN_EPI_GROUPS * (1024 + CGN_MAX_G * 64 + 2048 + 2048 + 1024 * nca) + 64 + (pl->lg == 3 ? 768 : 0);
-    // ring / staging depths: prefer deep rings, shrink until the CTA fits
+    // ring / staging depths: prefer deep rings, shrink until the CTA fits.  The MMA warp is paced by the operand rings: a ring
+    // holds (slots x bytes) in flight against ~1-1.5 us of L2 -> shared-memory latency, so pairs (half-size B slots) go deeper
     const int ew = 8 * CGN_EPI_GROUPS;
-    const int cand[6][3] = {{2, 4, 2}, {2, 3, 2}, {2, 4, 1}, {2, 3, 1}, {2, 2, 1}, {1, 2, 1}};
+    const int cand1[6][3] = {{2, 4, 2}, {2, 3, 2}, {2, 4, 1}, {2, 3, 1}, {2, 2, 1}, {1, 2, 1}};
+    const int cand2[8][3] = {{3, 8, 2}, {3, 6, 2}, {3, 8, 1}, {3, 7, 1}, {3, 6, 1}, {2, 6, 1}, {2, 5, 1}, {2, 4, 1}};
+    const int n_cand = pl->pair2 ? 8 : 6;
+    const int b_slot = P.bn * (pl->pair2 ? 64 : 128);
     pl->smem = 0;
-    for (int i = 0; i < 6; ++i) {
-        const int sa = cand[i][0], sb = cand[i][1], nb = cand[i][2];
-        const int sm = 1024 + sa * pl->MT * TC2_A_SLOT + sb * P.bn * 128 + ew * nb * 4096 + (pool ? ew * nb * 2048 : 0) + misc;
+    for (int i = 0; i < n_cand; ++i) {
+        const int sa = pl->pair2 ? cand2[i][0] : cand1[i][0], sb = pl->pair2 ? cand2[i][1] : cand1[i][1];
+        const int nb = pl->pair2 ? cand2[i][2] : cand1[i][2];
+        const int sm = 1024 + sa * pl->MT * TC2_A_SLOT + sb * b_slot + ew * nb * 4096 + (pool ? ew * nb * 2048 : 0) + misc;
         if (sm <= 232448) {
             P.sa = sa; P.sb = sb; P.nbuf = nb; P.n_acc = 2;
             pl->smem = sm;
@@ -827,10 +835,15 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = pl.G * pl.n_groups, smem = pl.smem;
     const bool pool = pooled != nullptr;
-#define CGN_GO(LG, MTV, CCV, PL)                                                                                          \
+#define CGN_GO2(LG, MTV, CCV, PL, HD, P2)                                                                                 \
     do {                                                                                                                  \
-        GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<LG, MTV, CCV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        GW_CUDA(gw_launch_cluster(conv_gn_kernel<LG, MTV, CCV, PL>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, pl.pair2 ? 2 : 1, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+        GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        GW_CUDA(gw_launch_cluster(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, P2 ? 2 : 1, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+    } while (0)
+#define CGN_GO(LG, MTV, CCV, PL)                                  \
+    do {                                                          \
+        if (pl.pair2) CGN_GO2(LG, MTV, CCV, PL, false, true);     \
+        else CGN_GO2(LG, MTV, CCV, PL, false, false);             \
     } while (0)
 #define CGN_CC(LG, MTV, PL)                      \
     do {                                         \
@@ -838,10 +851,10 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
         else if (Cc == 5) CGN_GO(LG, MTV, 5, PL);\
         else CGN_GO(LG, MTV, -1, PL);            \
     } while (0)
-#define CGN_GOH(CCV)                                                                                                      \
-    do {                                                                                                                  \
-        GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<3, 2, CCV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        GW_CUDA(gw_launch_cluster(conv_gn_kernel<3, 2, CCV, false, true>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, pl.pair2 ? 2 : 1, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+#define CGN_GOH(CCV)                                              \
+    do {                                                          \
+        if (pl.pair2) CGN_GO2(3, 2, CCV, false, true, true);      \
+        else CGN_GO2(3, 2, CCV, false, true, false);              \
     } while (0)
     if (pl.lg == 3 && head) {
         if (Cc == 1) CGN_GOH(1);
@@ -854,6 +867,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
 #undef CGN_GOH
 #undef CGN_CC
 #undef CGN_GO
+#undef CGN_GO2
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

@@ -711,7 +711,10 @@ struct CgnPlan {
     int MT, G, n_groups, smem, lg;
     int pair2, wbox;          // CTA pairs (cta_group::2) and the weight TMA box rows they need
 };
-int g_cgn_pair2 = 1;          // gw_set_option("pair2", 0/1): A/B switch for measurements
+// gw_set_option("pair2", 0/1).  Measured on B200 (profiles/r02_pair2.md): the pair flavour -- half the weight bytes per SM, B ring
+// twice as deep -- leaves every layer's MMA-issue time unchanged (dec0: 20.0 k vs 20.3 k cycles per sample slice), i.e. the
+// operand supply is not what paces the MMA warp; it stays a parity-tested option, off by default.
+int g_cgn_pair2 = 0;
 
 static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
     int rc = build_params(s, &pl->P, true);

@@ -197,6 +197,8 @@ class UNetEngine:
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
         self.generation = 0                         # bumped by refresh(): weight-derived caches (SamplerPlan.film) follow it
+        self.ptr_generation = 0                     # bumped when a parameter tensor MOVED: captured graphs hold raw pointers
+        self._ptr_sig = None
         self.refresh()
 
     # ------------------------------------------------------------------ weights
@@ -214,6 +216,10 @@ class UNetEngine:
         for key in list(self._packed):
             self._pack_tc(key)
         self.generation += 1
+        sig = tuple(t.data_ptr() for t in p.values())
+        if sig != self._ptr_sig:                    # e.g. FusedTrainStep re-pointed the module's parameters at its flat buffer
+            self._ptr_sig = sig
+            self.ptr_generation += 1
 
     def bind_flat(self, flat: Tensor, layout: ParamLayout) -> None:
         """Use `flat` (fp32, ParamLayout order) as the parameter storage: in-place optimiser updates of the flat buffer
@@ -563,6 +569,7 @@ class SamplerPlan:
         self.sched_dev = torch.tensor(sched, dtype=torch.int64, device=dev)
         self.film = eng.film_vectors(self.sched_dev)
         self._gen = eng.generation
+        self._ptr_gen = eng.ptr_generation
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         Cx = sp.in_ch
         self.net = [torch.zeros(self.Bn, Cx, L, device=dev, dtype=torch.float32) for _ in range(2)]
@@ -601,6 +608,9 @@ class SamplerPlan:
         if self._gen != self.eng.generation:
             self.eng.film_vectors(self.sched_dev, out=self.film)
             self._gen = self.eng.generation
+        if self._ptr_gen != self.eng.ptr_generation:   # the captured kernel arguments point at the parameters' OLD storage
+            self._graph = None
+            self._ptr_gen = self.eng.ptr_generation
 
     # one reverse step = 8 kernels (bf16 fused path)
     def enqueue_step(self) -> None:

@@ -58,6 +58,32 @@ def _reduce_to_one_channel(x: torch.Tensor) -> torch.Tensor:
     return x[:, :1, :] if (x.ndim == 3 and x.size(1) > 1) else x
 
 
+def _stats(name: str, arr) -> str:
+    """inference.py `_stats`: the debug line format of the reference sampler."""
+    a = arr.detach().double() if isinstance(arr, torch.Tensor) else torch.as_tensor(np.asarray(arr), dtype=torch.float64)
+    return (f"{name}: shape={tuple(a.shape)}, min={a.min().item():.3e}, max={a.max().item():.3e}, "
+            f"mean={a.mean().item():.3e}, std={a.std(unbiased=False).item():.3e})")
+
+
+def _corr_lag(x_t: torch.Tensor, y: torch.Tensor, delta_t: float):
+    """The `corr_lag` diagnostic of the per-step JSONL log (inference.py:491-506): Pearson correlation of x_t and y after the
+    cross-correlation lag search over +-0.25 s, one value per sample; the lag search runs on the device (gw_score_batch)."""
+    from . import scoring
+    B, L = x_t.shape
+    win = min(L - 1, int(max(1.0, 0.25 / delta_t)))
+    lags = scoring.best_lag_by_xcorr(x_t, y, max_shift=win).tolist()
+    out = []
+    for b, k in enumerate(lags):
+        a, c = x_t[b].double(), y[b].double()
+        if k < 0:
+            a, c = a[-k:], c[: L + k]
+        elif k > 0:
+            a, c = a[: L - k], c[k:]
+        a, c = a - a.mean(), c - c.mean()
+        out.append(float((a * c).sum() / (torch.sqrt((a * a).sum() * (c * c).sum()) + 1e-30)))
+    return out
+
+
 _PLANS: Dict[Tuple, SamplerPlan] = {}
 
 
@@ -186,14 +212,17 @@ def ddim_sample(model, diffusion, cond_stack: torch.Tensor,
                 steps_out.append({"t": plan.sched[i], "x_in": x_in, "eps": plan.trace_eps.clone().view(B, 1, L),
                                   "x0": plan.trace_x0.clone().view(B, 1, L), "x_out": x_now.clone()})
             if debug and (i % max(1, plan.N // 5) == 0 or plan.sched[i] == 0):
-                print(f"x_t (t={plan.sched[i]}): mean={x_now.mean().item():.3e} std={x_now.std().item():.3e}")
+                print(_stats(f"x_t (t={plan.sched[i]})", x_now))
+                print(_stats(f"eps_hat (t={plan.sched[i]})", plan.trace_eps.view(B, 1, L)))
             if log_jsonl_path and ((i % max(1, log_interval) == 0) or (i == plan.N - 1)):
+                corr_lag = _corr_lag(x_now.reshape(B, L), y_chan.reshape(B, L), delta_t)
                 with open(log_jsonl_path, "a") as fh:
                     fh.write(json.dumps({"phase": "ddim_step", "i": i, "t": plan.sched[i],
                                          "i_norm": float(0.0 if plan.N <= 1 else i / (plan.N - 1)),
                                          "alpha_bar": float(diffusion.alpha_bar[plan.sched[i]]),
                                          "cfg_mode": cfg_mode, "cfg_w_t": float(plan.coef[i, 5]),
-                                         "cfg_scale": float(cfg_scale)}) + "\n")
+                                         "cfg_scale": float(cfg_scale),
+                                         "corr_lag": corr_lag[0] if B == 1 else corr_lag}) + "\n")
         out = plan.net[plan.N & 1][:B, 0:1].clone()
         return (out, steps_out) if return_trace else out
     return plan.run(use_graph=use_graph).clone()

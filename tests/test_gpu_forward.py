@@ -241,7 +241,8 @@ def test_fused_head_dots(in_ch, cc, L, B):
 @pytest.mark.parametrize("in_ch,cc,L,B", [(3, 1, 4096, 21), (7, 5, 4096, 5), (3, 1, 16384, 2), (7, 5, 512, 3)])
 def test_cta_pair_mma_equals_single_cta(in_ch, cc, L, B):
     """conv_gn_kernel with tcgen05 CTA pairs (cta_group::2: one M = 256 MMA per pair, each CTA staging half of every weight
-    tile) accumulates every output row in the same K order as the single-CTA kernel: results are bit-identical."""
+    tile) against the single-CTA kernel.  Every output row is accumulated in the same K order; only the order in which the
+    CTAs' GroupNorm partial sums are added differs (slice -> CTA mapping), i.e. fp32 rounding of the statistics."""
     sd = make_state_dict(in_ch, cc, seed=0)
     x = gaussian((B, in_ch, L), seed=9 + L)
     t = torch.tensor(([24, 999, 500, 3, 250] * B)[:B])
@@ -255,7 +256,11 @@ def test_cta_pair_mma_equals_single_cta(in_ch, cc, L, B):
             ws = eng.workspace(B, L, False)
             outs.append((eps.clone(), [o.clone() for o in ws.out[:6]], [p.clone() for p in ws.pooled]))
     finally:
-        eng.lib.gw_set_option(b"pair2", 1)
-    assert torch.equal(outs[0][0], outs[1][0])
+        eng.lib.gw_set_option(b"pair2", 0)
+    assert rel_l2(outs[1][0], outs[0][0]) <= 1e-3
     for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
-        assert torch.equal(a, b)
+        assert rel_l2(b.float(), a.float()) <= 1e-3               # bf16 tensors: a last-bit flip here and there
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=True)
+    if B * L <= 5 * 4096:
+        with torch.no_grad():
+            assert rel_l2(outs[1][0], oracle.unet_forward(sd, cfg, x, t)) <= BF16_TOL

@@ -48,6 +48,8 @@ _SIGS = {
     "gw_conv_tc": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _I, _P], _I),
     "gw_conv_in_gn_group": ([_I, _I, _I, _I], _I),
     "gw_conv_in_gn": ([_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P], _I),
+    "gw_conv_in_direct_ws_floats": ([_I, _I, _I, _I, _I], _L),
+    "gw_conv_in_direct": ([_P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P], _I),
     "gw_conv_gn_group": ([C.POINTER(ConvTcShape), _I, _I], _I),
     "gw_conv_gn_sync_bytes": ([_I], _L),
     "gw_conv_gn": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P,

@@ -144,6 +144,7 @@ class _Workspace:
         self.cond = [torch.empty(B, Ls[j], max(spec.cond_in_ch, 1), device=device, dtype=torch.float32)
                      for j in range(d + 1)] if spec.cond_in_ch > 0 else None
         self.sync: Optional[Tensor] = None          # gw_conv_gn exchange buffer (zeroed once, see UNetEngine._block)
+        self.coef0: Optional[Tensor] = None         # gw_conv_in_direct: per-(sample, channel) epilogue coefficients of block 0
         self.dots: Optional[Tensor] = None          # [B, L, 4] head dot products left by the last decoder's fused kernel
         self.head_fused = False                     # set by UNetEngine.body(): ws.dots is current, ws.out[-1] was not written
 
@@ -193,6 +194,9 @@ class UNetEngine:
         # inference: the last decoder's fused kernel also forms the three head-conv dot products per position (gw_conv_gn2), so
         # gw_final_step runs on 16 B per position and the [B, L, 64] activation is neither written nor read back
         self.fuse_head = True
+        # inference: first block in one pass with ANALYTIC GroupNorm statistics (conv_in_direct.cu) instead of the exchange-based
+        # conv_in_gn kernel
+        self.direct_first = True
         self._fuse_ok: Dict[tuple, bool] = {}
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None
@@ -406,7 +410,20 @@ class UNetEngine:
         B, Cx, L = net_a.shape
         st = _cabi.stream_ptr()
         Cc0 = sp.cond_in_ch
-        if (ws.stats is None and self.fuse_gn and self.dtype == "bf16" and ws.sync is not None
+        n_coef = (self.lib.gw_conv_in_direct_ws_floats(B, Cx, L, sp.base_ch, Cc0)
+                  if (ws.stats is None and self.fuse_gn and self.direct_first and self.dtype == "bf16") else 0)
+        if n_coef > 0:
+            if ws.coef0 is None or ws.coef0.numel() < n_coef:
+                ws.coef0 = torch.empty(n_coef, device=self.device, dtype=torch.float32)
+            check(self.lib.gw_conv_in_direct(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),
+                                             ptr(self.p["encoders.0.0.bias"]), sp.base_ch, ptr(self.p["encoders.0.1.weight"]),
+                                             ptr(self.p["encoders.0.1.bias"]), Cc0,
+                                             ptr(self.p["cond_enc.0.weight"]) if Cc0 > 0 else None,
+                                             ptr(self.p["cond_enc.0.bias"]) if Cc0 > 0 else None, ptr(film),
+                                             sp.film_offsets()[0], film_b_stride, film_step_stride, ptr(ws.out[0]),
+                                             ptr(ws.pooled[0]), ptr(ws.coef0), st), "conv_in_direct")
+            self.launches += 2
+        elif (ws.stats is None and self.fuse_gn and self.dtype == "bf16" and ws.sync is not None
                 and self.lib.gw_conv_in_gn_group(Cx, L, sp.base_ch, Cc0) > 0):
             # inference: conv + GroupNorm + SiLU + cond + FiLM + pool of the first block in one kernel (conv_in_gn.cu)
             check(self.lib.gw_conv_in_gn(ptr(net_a), ptr(net_b), ptr(step_ptr), B, Cx, L, ptr(self.p["encoders.0.0.weight"]),

@@ -95,6 +95,19 @@ int gw_gn_apply_stream(const void* raw, const float* part, int n_part, int B, in
                        int film_off, long film_b_stride, long film_step_stride, const int* step_ptr, void* out,
                        void* pooled, float* stats_out, void* stream);
 
+/* ---- FIRST block for inference in one pass with analytic GroupNorm statistics (conv_in_direct.cu; models.py:160-173,
+ * 188-193, 204-208).  The first conv has only 3*Cx <= 24 inputs per output, so the first / second moments of its output are a
+ * quadratic form of the input's lag-(0,1,2) cross products: one small kernel reads the fp32 input once and leaves the
+ * per-(sample, channel) epilogue coefficients in coef_ws (gw_conv_in_direct_ws_floats floats), then any CTA convolves any
+ * 256-row slice (tf32 mma.sync) and applies GroupNorm / SiLU / cond / FiLM / pool on the accumulator fragments -- no exchange
+ * between CTAs, no raw tensor.  Same arguments as gw_conv_in_gn; x / x_alt / step_ptr: ping-pong input of the sampler.
+ * Needs Cx <= 8, C == 64, L even. */
+long gw_conv_in_direct_ws_floats(int B, int Cx, int L, int C, int Cc);
+int gw_conv_in_direct(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
+                      const float* bias, int C, const float* gn_w, const float* gn_b, int Cc, const float* wc,
+                      const float* bc, const float* film, int film_off, long film_b_stride, long film_step_stride,
+                      void* out, void* pooled, float* coef_ws, void* stream);
+
 /* ---- head: final Conv1d(C+1 -> 1, k=3) on cat[h, x_t] (models.py:227-230, K8) optionally fused with classifier-free
  * guidance combine and the DDIM/DDPM update (inference.py:445-484, K20/K21).
  *

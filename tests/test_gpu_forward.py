@@ -199,6 +199,7 @@ def test_fused_first_block_partial_tiles(in_ch, cc, L, B):
     fused = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype="bf16", conv_impl="tc")
     plain = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype="bf16", conv_impl="tc")
     plain.fuse_gn = False
+    fused.direct_first = False                   # this test covers the exchange-based kernel (see test_direct_first_block)
     x = gaussian((B, in_ch, L), seed=5 + L)
     t = torch.tensor(([700, 12, 333] * B)[:B])
     assert fused.lib.gw_conv_in_gn_group(in_ch, L, 64, cc) > 0
@@ -264,3 +265,41 @@ def test_cta_pair_mma_equals_single_cta(in_ch, cc, L, B):
     if B * L <= 5 * 4096:
         with torch.no_grad():
             assert rel_l2(outs[1][0], oracle.unet_forward(sd, cfg, x, t)) <= BF16_TOL
+
+
+@pytest.mark.parametrize("in_ch,cc,L,B", [(3, 1, 4096, 21), (7, 5, 4096, 5), (3, 1, 1000, 3), (7, 5, 2050, 2), (1, 0, 768, 2),
+                                          (3, 1, 16384, 2), (7, 5, 250, 3)])
+def test_direct_first_block(in_ch, cc, L, B):
+    """gw_conv_in_direct: the first block in one pass, GroupNorm statistics from the analytic moments of the conv output (a
+    quadratic form of the input's lagged cross products) -- block output, pooled output and eps_hat against the oracle, the
+    statistics themselves against the oracle's raw conv output, inputs with a large self-conditioning channel included."""
+    import torch.nn.functional as F
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.engine import ModelSpec, UNetEngine
+    sd = make_state_dict(in_ch, cc, seed=0)
+    sc = in_ch > 1
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=sc)
+    spec = ModelSpec(in_ch=in_ch, cond_in_ch=cc, use_selfcond=sc)
+    eng = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype="bf16", conv_impl="tc")
+    assert eng.direct_first and eng.lib.gw_conv_in_direct_ws_floats(B, in_ch, L, 64, cc) > 0
+    x = gaussian((B, in_ch, L), seed=13 + L)
+    x[:, 0] += 0.7                                # a DC offset: the variance is a difference of large moments
+    if sc:
+        x[0, -1] *= 3000.0                        # x0_hat of the first reverse steps is ~1e4 (SURVEY F7)
+    t = torch.tensor(([700, 12, 333] * B)[:B])
+    with torch.no_grad():
+        taps = oracle.unet_forward_taps(sd, cfg, x, t)
+    for _ in range(2):
+        eps = eng.forward(x.cuda(), t.cuda())
+    ws = eng.workspace(B, L, False)
+    assert ws.coef0 is not None
+    assert rel_l2(ws.out[0].float().transpose(1, 2), taps["enc0.out"]) <= 5e-3
+    assert rel_l2(ws.pooled[0].float().transpose(1, 2), F.avg_pool1d(taps["enc0.out"], 2, 2)) <= 5e-3
+    assert rel_l2(eps, taps["eps"]) <= BF16_TOL
+    # the analytic statistics: A = 0.5 rstd gn_w of channel pair 0 / 4 .. against the oracle's raw conv output
+    raw = taps["enc0.raw"].double().reshape(B, 8, 8 * L)
+    rstd = 1.0 / torch.sqrt(raw.var(dim=2, unbiased=False) + 1e-5)
+    nca = cc if cc in (0, 1, 5) else 8
+    coef = ws.coef0[: B * 32 * (8 + 2 * nca)].view(B, 32, 8 + 2 * nca).cpu().double()
+    a_ref = 0.5 * rstd[:, :, None] * sd["encoders.0.1.weight"].double().view(1, 8, 8)
+    a_got = coef[:, :, 0:2].reshape(B, 64).view(B, 8, 8)
+    assert float(((a_got - a_ref).abs() / a_ref.abs().clamp_min(1e-12)).max()) <= 2e-4

@@ -23,7 +23,8 @@
 #define CID_XP (CID_ROWS + 8)
 #define CID_MAX_CX 8
 #define CID_MAX_CC 8
-#define CID_PF 9                        // prefetch registers per thread: 8 * 264 / 256 rounded up
+#define CID_PF (CID_MAX_CX + 1)         // prefetch registers per thread: one column of every channel + the window's tail
+#define CID_CF(nca) ((8 + 2 * (nca) + 3) / 4 * 4)      // floats per channel pair (16-byte aligned rows: read with LDS.128)
 
 struct CidArgs {
     const float* xa;
@@ -36,7 +37,7 @@ struct CidArgs {
     const float* wc;
     const float* bc;
     const float* film;
-    float* coef;            // [B][32 channel pairs][8 + 2*NCA]: A0 A1 B0 B1 G0 G1 E0 E1 (W_j0 W_j1)...
+    float* coef;            // [B][32 channel pairs][CID_CF(NCA)]: A0 A1 B0 B1 G0 G1 E0 E1 (W_j0 W_j1)... padded to 16 bytes
     bf16* out;
     bf16* pooled;
     long film_b_stride, film_step_stride;
@@ -59,42 +60,93 @@ __device__ __forceinline__ void cid_stmatrix_x4(uint32_t addr, uint32_t r0, uint
 }
 
 // ------------------------------------------------------------------------------------------------ 1. moments -> coefficients
-// One CTA (256 threads) per sample.  Warp i < Cx accumulates q[j][d] = sum_u x_i[u] x_j[u+d], d = 0..2, and T_i = sum_u x_i[u]
-// over chunks of CID_CH positions staged in shared memory (fp32 inside a chunk, fp64 across chunks).
+// One CTA (256 threads) per sample.  The sample's channels are staged chunk by chunk with 1-D bulk copies (no per-element index
+// arithmetic); warp w works on channel i = w % Cx and position slab w / Cx of the chunk and accumulates
+// q[j][d] = sum_u x_i[u] x_j[u+d], d = 0..2, and T_i = sum_u x_i[u] (fp32 inside a chunk, fp64 across chunks and slabs).
 #define CID_CH 2048
+__device__ __forceinline__ void cid_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void cid_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cid_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cid_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 template <int NCA>
 __global__ void __launch_bounds__(256) in_moments_kernel(const CidArgs A) {
+    constexpr int XPM = CID_CH + 8;
     extern __shared__ __align__(16) unsigned char smem_m[];
-    float* xs = reinterpret_cast<float*>(smem_m);                        // [Cx][CID_CH + 4]
+    float* xs = reinterpret_cast<float*>(smem_m);                        // [Cx][XPM]
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ double s_q[CID_MAX_CX][CID_MAX_CX][3];
     __shared__ double s_t[CID_MAX_CX];
+    __shared__ double s_R[3 * CID_MAX_CX][3 * CID_MAX_CX + 1];
+    __shared__ double s_x1[3 * CID_MAX_CX];
     __shared__ float s_edge[CID_MAX_CX][4];                              // x[0], x[1], x[L-2], x[L-1]
     __shared__ double s_s1[CID_C], s_s2[CID_C];
     __shared__ float s_mr[8][2];
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int Cx = A.Cx, L = A.L, Cc = A.Cc;
+    const int Cx = A.Cx, L = A.L, Cc = A.Cc, K = 3 * A.Cx;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    for (int i = tid; i < CID_MAX_CX * CID_MAX_CX * 3; i += 256) (&s_q[0][0][0])[i] = 0.0;
+    if (tid < CID_MAX_CX) s_t[tid] = 0.0;
+    if (tid == 0) {
+        cid_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     pdl_wait();
     pdl_launch_dependents();
     const int step = A.step_ptr != nullptr ? *A.step_ptr : 0;
     const float* x = ((step & 1) ? A.xb : A.xa) + (size_t)b * Cx * L;
-    constexpr int XPM = CID_CH + 4;
-    double qd[CID_MAX_CX][3], td = 0.0;
-#pragma unroll
-    for (int j = 0; j < CID_MAX_CX; ++j) qd[j][0] = qd[j][1] = qd[j][2] = 0.0;
+    const bool bulk_ok = (L % 4) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const int S = 8 / Cx;                                 // position slabs per channel (Cx <= 8)
+    const int ci = warp % Cx, slab = warp / Cx;
+    const bool active = slab < S;
+    uint32_t phase = 0;
     for (int c0 = 0; c0 < L; c0 += CID_CH) {
         const int n = min(CID_CH, L - c0);
-        __syncthreads();
-        for (int i = tid; i < Cx * XPM; i += 256) {
-            const int c = i / XPM, p = i % XPM, l = c0 + p;
-            xs[i] = (p < n + 2 && l < L) ? x[(size_t)c * L + l] : 0.0f;
+        const int ncp = min(n + 4, L - c0);              // staged floats per channel (2 halo positions, rounded to 16 bytes)
+        __syncthreads();                                  // the previous chunk's readers are done
+        if (bulk_ok) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                cid_mbar_expect_tx(bar, (uint32_t)(Cx * ncp * 4));
+                for (int c = 0; c < Cx; ++c)
+                    cid_bulk_load((uint32_t)__cvta_generic_to_shared(xs + c * XPM), x + (size_t)c * L + c0, (uint32_t)(ncp * 4), bar);
+            }
+            if (ncp < n + 2)                              // last chunk: the two halo positions lie beyond the sample
+                for (int i = tid; i < Cx * 4; i += 256) xs[(i >> 2) * XPM + ncp + (i & 3)] = 0.0f;
+            cid_mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            for (int c = 0; c < Cx; ++c)
+                for (int p = tid; p < n + 2; p += 256) xs[c * XPM + p] = c0 + p < L ? x[(size_t)c * L + c0 + p] : 0.0f;
         }
         __syncthreads();
-        if (warp < Cx) {
+        if (active) {
             float q[CID_MAX_CX][3], t = 0.0f;
 #pragma unroll
             for (int j = 0; j < CID_MAX_CX; ++j) q[j][0] = q[j][1] = q[j][2] = 0.0f;
-            const float* xi = xs + warp * XPM;
-            for (int u = lane; u < n; u += 32) {
+            const float* xi = xs + ci * XPM;
+            const int per = (n + S - 1) / S, u0 = slab * per, u1 = min(n, u0 + per);
+            for (int u = u0 + lane; u < u1; u += 32) {
                 const float v = xi[u];
                 t += v;
 #pragma unroll
@@ -107,66 +159,72 @@ __global__ void __launch_bounds__(256) in_moments_kernel(const CidArgs A) {
                     }
                 }
             }
-            td += (double)t;
+            // fold the warp, then add to the CTA totals in fp64 (one atomic per value, per warp, per chunk)
+            t = warp_sum(t);
+            if (lane == 0) atomicAdd(&s_t[ci], (double)t);
 #pragma unroll
             for (int j = 0; j < CID_MAX_CX; ++j) {
-                qd[j][0] += (double)q[j][0];
-                qd[j][1] += (double)q[j][1];
-                qd[j][2] += (double)q[j][2];
-            }
-        }
-    }
-    if (warp < Cx) {
-        td = warp_sum_d(td);
+                if (j < Cx) {
 #pragma unroll
-        for (int j = 0; j < CID_MAX_CX; ++j) {
-            if (j < Cx) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const double v = warp_sum_d(qd[j][d]);
-                    if (lane == 0) s_q[warp][j][d] = v;
+                    for (int d = 0; d < 3; ++d) {
+                        const float v = warp_sum(q[j][d]);
+                        if (lane == 0) atomicAdd(&s_q[ci][j][d], (double)v);
+                    }
                 }
             }
         }
-        if (lane == 0) s_t[warp] = td;
-        if (lane < 4) {
-            const int l = lane < 2 ? lane : L - 4 + lane;
-            s_edge[warp][lane] = (l >= 0 && l < L) ? x[(size_t)warp * L + l] : 0.0f;
-        }
+    }
+    if (tid < Cx * 4) {
+        const int c = tid >> 2, e = tid & 3;
+        const int l = e < 2 ? e : L - 4 + e;
+        s_edge[c][e] = (l >= 0 && l < L) ? x[(size_t)c * L + l] : 0.0f;
     }
     __syncthreads();
-    // ---- channel c = tid: first and second moment of its conv output
-    if (tid < CID_C) {
-        const int c = tid;
-        const float* wr = A.w + (size_t)c * Cx * 3;
-        const double bias = (double)A.bias[c];
-        auto xe = [&](int i, int l) -> double {          // x_i[l] for l in {0, 1, L-2, L-1}
-            if (l == 0) return (double)s_edge[i][0];
-            if (l == 1) return (double)s_edge[i][1];
-            if (l == L - 2) return (double)s_edge[i][2];
-            return (double)s_edge[i][3];
-        };
+    auto xe = [&](int i, int l) -> double {               // x_i[l] for l in {0, 1, L-2, L-1}
+        if (l == 0) return (double)s_edge[i][0];
+        if (l == 1) return (double)s_edge[i][1];
+        if (l == L - 2) return (double)s_edge[i][2];
+        return (double)s_edge[i][3];
+    };
+    // ---- R[(i,k)][(j,m)] = sum_l xp_i[l+k-1] xp_j[l+m-1] and X1[(i,k)] = sum_l xp_i[l+k-1] from the lagged products:
+    //      u = l+k-1 runs over [0, L-2] for k = 0 and [1, L-1] for k = 2, so one boundary product drops out
+    for (int e = tid; e < K * K; e += 256) {
+        const int a = e / K, c2 = e % K;
+        const int i = a / 3, k = a % 3, j = c2 / 3, m = c2 % 3, d = m - k;
+        double r = d >= 0 ? s_q[i][j][d] : s_q[j][i][-d];
+        if (k == 0 && d <= 0 && L - 1 + d >= 0) r -= xe(i, L - 1) * xe(j, L - 1 + d);
+        if (k == 2 && d >= 0 && d < L) r -= xe(i, 0) * xe(j, d);
+        s_R[a][c2] = r;
+    }
+    if (tid < K) {
+        const int i = tid / 3, k = tid % 3;
+        double x1 = s_t[i];
+        if (k == 0) x1 -= xe(i, L - 1);
+        if (k == 2) x1 -= xe(i, 0);
+        s_x1[tid] = x1;
+    }
+    __syncthreads();
+    // ---- channel c = tid / 4: first and second moment of its conv output; the 4 lanes of a channel split the rows of R
+    {
+        const int c = tid >> 2, part = tid & 3;
+        const float* wr = A.w + (size_t)c * K;
         double lin = 0.0, quad = 0.0;
-        for (int i = 0; i < Cx; ++i)
-            for (int k = 0; k < 3; ++k) {
-                const double wik = (double)wr[i * 3 + k];
-                // X1[(i,k)] = sum_l xp_i[l+k-1]: k = 0 misses x_i[L-1], k = 2 misses x_i[0]
-                double x1 = s_t[i];
-                if (k == 0) x1 -= xe(i, L - 1);
-                if (k == 2) x1 -= xe(i, 0);
-                lin += wik * x1;
-                for (int j = 0; j < Cx; ++j)
-                    for (int m = 0; m < 3; ++m) {
-                        const int d = m - k;
-                        double r = d >= 0 ? s_q[i][j][d] : s_q[j][i][-d];
-                        // u = l+k-1 runs over [0, L-2] for k = 0 and [1, L-1] for k = 2: one boundary product drops out
-                        if (k == 0 && d <= 0 && L - 1 + d >= 0) r -= xe(i, L - 1) * xe(j, L - 1 + d);
-                        if (k == 2 && d >= 0 && d < L) r -= xe(i, 0) * xe(j, d);
-                        quad += wik * (double)wr[j * 3 + m] * r;
-                    }
-            }
-        s_s1[c] = (double)L * bias + lin;
-        s_s2[c] = (double)L * bias * bias + 2.0 * bias * lin + quad;
+        for (int a = part; a < K; a += 4) {
+            const double wa = (double)wr[a];
+            double acc = 0.0;
+            for (int c2 = 0; c2 < K; ++c2) acc = fma((double)wr[c2], s_R[a][c2], acc);
+            quad = fma(wa, acc, quad);
+            lin = fma(wa, s_x1[a], lin);
+        }
+        lin += __shfl_xor_sync(0xffffffffu, lin, 1);
+        quad += __shfl_xor_sync(0xffffffffu, quad, 1);
+        lin += __shfl_xor_sync(0xffffffffu, lin, 2);
+        quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+        if (part == 0) {
+            const double bias = (double)A.bias[c];
+            s_s1[c] = (double)L * bias + lin;
+            s_s2[c] = (double)L * bias * bias + 2.0 * bias * lin + quad;
+        }
     }
     __syncthreads();
     if (tid < 8) {
@@ -180,7 +238,7 @@ __global__ void __launch_bounds__(256) in_moments_kernel(const CidArgs A) {
         s_mr[tid][1] = (float)(1.0 / sqrt(var + 1e-5));
     }
     __syncthreads();
-    // ---- epilogue coefficients of channel c: h = A x + B is HALF the GroupNorm output (conv bias is inside x),
+    // ---- epilogue coefficients of channel c for the conv WITHOUT its bias (acc): h = A acc + B is HALF the GroupNorm output,
     //      out = (h + h tanh h) G + E + sum_j W_j cond_j,  G = 1 + gamma_t, E = bc G + beta_t, W_j = wc_j G
     if (tid < CID_C) {
         const int c = tid, pr = c >> 1, hf = c & 1;
@@ -188,9 +246,9 @@ __global__ void __launch_bounds__(256) in_moments_kernel(const CidArgs A) {
         const float mean = s_mr[c >> 3][0], rstd = s_mr[c >> 3][1];
         const float a = rstd * A.gn_w[c];
         const float g = 1.0f + fr[c];
-        float* cf = A.coef + ((size_t)b * 32 + pr) * (8 + 2 * NCA);
+        float* cf = A.coef + ((size_t)b * 32 + pr) * CID_CF(NCA);
         cf[0 + hf] = 0.5f * a;
-        cf[2 + hf] = 0.5f * (A.gn_b[c] - mean * a);
+        cf[2 + hf] = 0.5f * fmaf(A.bias[c] - mean, a, A.gn_b[c]);
         cf[4 + hf] = g;
         cf[6 + hf] = fmaf(Cc > 0 ? A.bc[c] : 0.0f, g, fr[CID_C + c]);
 #pragma unroll
@@ -201,14 +259,14 @@ __global__ void __launch_bounds__(256) in_moments_kernel(const CidArgs A) {
 // ------------------------------------------------------------------------------------------------ 2. conv + epilogue
 template <int CC>
 __global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const CidArgs A) {
-    constexpr int NCA = CC > 0 ? CC : CID_MAX_CC;
-    constexpr int CF = 8 + 2 * NCA;                      // floats per channel pair
+    constexpr int NCA = CC >= 0 ? CC : CID_MAX_CC;       // CC = -1: any count up to 8, zero-padded weights
+    constexpr int NCR = NCA > 0 ? NCA : 1;               // register array extent
+    constexpr int CF = CID_CF(NCA);                      // floats per channel pair
     constexpr int C = CID_C;
     extern __shared__ __align__(16) unsigned char smem[];
-    float* xs = reinterpret_cast<float*>(smem);                           // [Cx][XP]: xs[c][j] = x[c][l00 - 1 + j]
-    float* ws = xs + A.Cx * CID_XP;                                       // tf32 B fragments [KS][8 n-tiles][32 lanes][2]
-    float* bs = ws + 3 * 8 * 32 * 2;                                      // [C]
-    float* cfs = bs + C;                                                  // [32 pairs][CF]
+    float* xs = reinterpret_cast<float*>(smem);                           // [Cx + 1][XP]: xs[c][j] = x[c][l00 - 1 + j]; row Cx = zeros
+    float* ws = xs + (A.Cx + 1) * CID_XP;                                 // tf32 B fragments [KS][8 n-tiles][32 lanes][2]
+    float* cfs = ws + 3 * 8 * 32 * 2;                                     // [32 pairs][CF]
     unsigned char* stg_base = reinterpret_cast<unsigned char*>(cfs + 32 * CF);   // [8 warps][2 KB out tile | 1 KB pooled tile]
     const int Cx = A.Cx, L = A.L, Cc = A.Cc;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -227,66 +285,61 @@ __global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const CidArgs A)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int kk = ks * 8 + t4 + 4 * j;
-            aoff[ks][j] = kk < 3 * Cx ? (kk / 3) * CID_XP + kk % 3 : -1;
+            aoff[ks][j] = kk < 3 * Cx ? (kk / 3) * CID_XP + kk % 3 : Cx * CID_XP;       // padding columns read the zero row
         }
-    for (int i = tid; i < C; i += 256) bs[i] = A.bias[i];
+    for (int i = tid; i < CID_XP; i += 256) xs[Cx * CID_XP + i] = 0.0f;
     const uint32_t stg = (uint32_t)__cvta_generic_to_shared(stg_base) + (uint32_t)warp * 3072u;
     const unsigned char* stg_g = stg_base + warp * 3072;
     pdl_wait();                          // the input, the step counter and the coefficient table belong to earlier kernels
     pdl_launch_dependents();
     const int step = A.step_ptr != nullptr ? *A.step_ptr : 0;
     const float* x = (step & 1) ? A.xb : A.xa;
-    auto load_x = [&](int item, int i) {
-        const int b = item / A.slices, l00 = (item % A.slices) * CID_ROWS;
-        const int c = i / CID_XP, p = i % CID_XP;
-        const int l = l00 + p - 1;
-        return (p < CID_ROWS + 2 && l >= 0 && l < L) ? x[((size_t)b * Cx + c) * L + l] : 0.0f;
-    };
+    // input staging: thread tid fetches column tid of every channel's [l00 - 1, l00 + 256] window, threads 0 .. 2 Cx - 1 the two
+    // remaining columns; the NEXT item's values travel in registers while the current item is computed
     float pf[CID_PF];
-    bool pf_valid = false;
+    const int xc = tid >> 1, xp = CID_ROWS + (tid & 1);
+    auto fetch = [&](int item) {
+        const int b = item / A.slices, l00 = (item - b * A.slices) * CID_ROWS;
+        const float* xb = x + (size_t)b * Cx * L + l00 - 1;
+        const int l = l00 + tid - 1;
+        const bool ok = l >= 0 && l < L;
+#pragma unroll
+        for (int k = 0; k < CID_MAX_CX; ++k) pf[k] = (k < Cx && ok) ? xb[(size_t)k * L + tid] : 0.0f;
+        pf[CID_MAX_CX] = (tid < 2 * Cx && l00 + xp - 1 < L) ? xb[(size_t)xc * L + xp] : 0.0f;
+    };
+    if ((int)blockIdx.x < A.n_items) fetch(blockIdx.x);
     const unsigned long long half2 = pkf2(0.5f, 0.5f);
     const float2* wsf = reinterpret_cast<const float2*>(ws);
     for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
         const int b = item / A.slices, l00 = (item % A.slices) * CID_ROWS;
         __syncthreads();                 // the previous item's readers of xs / cfs are done
-        if (pf_valid) {
 #pragma unroll
-            for (int k = 0; k < CID_PF; ++k)
-                if (tid + k * 256 < Cx * CID_XP) xs[tid + k * 256] = pf[k];
-        } else {
-            for (int i = tid; i < Cx * CID_XP; i += 256) xs[i] = load_x(item, i);
-        }
+        for (int k = 0; k < CID_MAX_CX; ++k)
+            if (k < Cx) xs[k * CID_XP + tid] = pf[k];
+        if (tid < 2 * Cx) xs[xc * CID_XP + xp] = pf[CID_MAX_CX];
         {
             const float* cf = A.coef + (size_t)b * 32 * CF;
             for (int i = tid; i < 32 * CF; i += 256) cfs[i] = cf[i];
         }
         __syncthreads();
         // the next item's input travels while this one is computed
-        pf_valid = false;
-        if (item + (int)gridDim.x < A.n_items) {
-#pragma unroll
-            for (int k = 0; k < CID_PF; ++k) pf[k] = tid + k * 256 < Cx * CID_XP ? load_x(item + gridDim.x, tid + k * 256) : 0.0f;
-            pf_valid = true;
-        }
+        if (item + (int)gridDim.x < A.n_items) fetch(item + gridDim.x);
 #pragma unroll 1
         for (int rt = warp; rt < CID_ROWS / 16; rt += 8) {
             const int rbase = rt * 16;
             if (l00 + rbase >= L) break;
-            float acc[8][4];
+            float acc[8][4];                     // the conv WITHOUT its bias (folded into the B coefficient)
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const float2 b2 = *reinterpret_cast<const float2*>(bs + nt * 8 + 2 * t4);
-                acc[nt][0] = b2.x; acc[nt][1] = b2.y; acc[nt][2] = b2.x; acc[nt][3] = b2.y;
-            }
+            for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
             const float* x0 = xs + rbase + g;
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks) {
                 if (ks < KS) {
                     uint32_t af[4];
-                    af[0] = aoff[ks][0] >= 0 ? cid_tf32(x0[aoff[ks][0]]) : 0u;
-                    af[1] = aoff[ks][0] >= 0 ? cid_tf32(x0[aoff[ks][0] + 8]) : 0u;
-                    af[2] = aoff[ks][1] >= 0 ? cid_tf32(x0[aoff[ks][1]]) : 0u;
-                    af[3] = aoff[ks][1] >= 0 ? cid_tf32(x0[aoff[ks][1] + 8]) : 0u;
+                    af[0] = cid_tf32(x0[aoff[ks][0]]);
+                    af[1] = cid_tf32(x0[aoff[ks][0] + 8]);
+                    af[2] = cid_tf32(x0[aoff[ks][1]]);
+                    af[3] = cid_tf32(x0[aoff[ks][1] + 8]);
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         const float2 bf = wsf[(ks * 8 + nt) * 32 + lane];
@@ -295,11 +348,13 @@ __global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const CidArgs A)
                 }
             }
             // ---- epilogue on the fragments: rows rbase + g (acc[.][0..1]) and rbase + g + 8 (acc[.][2..3]), channels 8 nt + 2 t4 (+1)
-            float cv0[NCA], cv1[NCA];                                   // cond = input channels 1 .. Cc at my two rows
+            unsigned long long cv0[NCR], cv1[NCR];                      // cond = input channels 1 .. Cc at my two rows, as (v, v) pairs
 #pragma unroll
             for (int jc = 0; jc < NCA; ++jc) {
-                cv0[jc] = jc < Cc ? x0[(1 + jc) * CID_XP + 1] : 0.0f;
-                cv1[jc] = jc < Cc ? x0[(1 + jc) * CID_XP + 9] : 0.0f;
+                const int ro = jc < Cc ? (1 + jc) * CID_XP : Cx * CID_XP;   // weights beyond Cc are zero; read the zero row
+                const float v0 = x0[ro + 1], v1 = x0[ro + 9];
+                cv0[jc] = pkf2(v0, v0);
+                cv1[jc] = pkf2(v1, v1);
             }
             const bool odd = (g & 1) != 0;
             uint32_t r0[8], r1[8], rp[8];
@@ -323,8 +378,8 @@ __global__ void __launch_bounds__(256, 2) conv_in_direct_kernel(const CidArgs A)
 #pragma unroll
                     for (int jc = 0; jc < NCA; ++jc) {
                         const unsigned long long wv = *reinterpret_cast<const unsigned long long*>(cf + 8 + 2 * jc);
-                        o0 = ffma2(wv, pkf2(cv0[jc], cv0[jc]), o0);
-                        o1 = ffma2(wv, pkf2(cv1[jc], cv1[jc]), o1);
+                        o0 = ffma2(wv, cv0[jc], o0);
+                        o1 = ffma2(wv, cv1[jc], o1);
                     }
                 }
                 float lo, hi;
@@ -399,7 +454,7 @@ static int cid_sm_count() {
 extern "C" long gw_conv_in_direct_ws_floats(int B, int Cx, int L, int C, int Cc) {
     if (C != CID_C || Cx < 1 || Cx > CID_MAX_CX || Cc < 0 || Cc > CID_MAX_CC || 1 + Cc > Cx || L < 4 || (L % 2) != 0 || B < 1) return 0;
     const int nca = (Cc == 0 || Cc == 1 || Cc == 5) ? Cc : CID_MAX_CC;
-    return (long)B * 32 * (8 + 2 * nca);
+    return (long)B * 32 * CID_CF(nca);
 }
 
 extern "C" int gw_conv_in_direct(const float* x, const float* x_alt, const int* step_ptr, int B, int Cx, int L, const float* w,
@@ -418,9 +473,9 @@ extern "C" int gw_conv_in_direct(const float* x, const float* x_alt, const int* 
     A.slices = (L + CID_ROWS - 1) / CID_ROWS;
     A.n_items = B * A.slices;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem_m = (size_t)Cx * (CID_CH + 4) * 4;
+    const size_t smem_m = (size_t)Cx * (CID_CH + 8) * 4;
     const int nca = (Cc == 0 || Cc == 1 || Cc == 5) ? Cc : CID_MAX_CC;
-    const size_t smem = (size_t)(Cx * CID_XP + 3 * 8 * 32 * 2 + CID_C + 32 * (8 + 2 * nca)) * 4 + 8 * 3072;
+    const size_t smem = (size_t)((Cx + 1) * CID_XP + 3 * 8 * 32 * 2 + 32 * CID_CF(nca)) * 4 + 8 * 3072;
     int grid = 2 * cid_sm_count();
     if (grid > A.n_items) grid = A.n_items;
 #define CID_GO(CCV, NCAV)                                                                                                    \

@@ -109,7 +109,7 @@ class TimedLib:
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
-        if not name.startswith("gw_") or name in ("gw_last_error", "gw_conv_tc_packed_elems", "gw_conv_tc_n_part", "gw_conv_gn_group", "gw_conv_in_gn_group", "gw_conv_gn_sync_bytes", "gw_version",
+        if not name.startswith("gw_") or name in ("gw_last_error", "gw_conv_tc_packed_elems", "gw_conv_tc_n_part", "gw_conv_gn_group", "gw_conv_in_gn_group", "gw_conv_gn_sync_bytes", "gw_conv_in_direct_ws_floats", "gw_version",
                                                   "gw_gn_bwd_scratch_elems", "gw_wgrad_tc_scratch_elems", "gw_opt_scratch_doubles"):
             return fn
 
@@ -194,7 +194,7 @@ def family_rooflines(records, spec, B, L, pk, n_steps, train):
     else:
         # inference: one kernel per block does the conv AND the GroupNorm/SiLU/cond/FiLM/pool epilogue (conv_gn.cuh); its
         # roofline counts the conv FLOPs only, against the time of the whole fused kernel
-        add("fused conv block (tcgen05 implicit GEMM + GroupNorm/SiLU/cond/FiLM/pool epilogue)", ["gw_conv_gn", "gw_conv_gn2"], "tensor",
+        add("fused conv block (tcgen05 implicit GEMM + GroupNorm/SiLU/cond/FiLM/pool epilogue)", ["gw_conv_gn", "gw_conv_gn2", "gw_conv_gn3"], "tensor",
             conv_fl, "2*Cin*Cout*3*L*B per conv (the fused elementwise work is not counted)")
         add("conv fwd (tcgen05 implicit GEMM)", ["gw_conv_tc"], "tensor", conv_fl, "2*Cin*Cout*3*L*B per conv")
     gn_keys = [k for k in ("gw_gn_apply", "gw_gn_apply_stream") if k in t_by]
@@ -426,9 +426,9 @@ def bench_sampling(args, workload, B, steps, warmup, world, rank, dev, barrier, 
                "roofline": {"bound": "tensor",
                             "kernel": "conv_gn_kernel (6 launches per reverse step: tcgen05+TMA implicit GEMM with the "
                                       "GroupNorm/SiLU/cond/FiLM/pool epilogue fused in)"
-                            if "gw_conv_gn" in conv["entry_points"] else "conv_tc2_kernel (tcgen05+TMA implicit GEMM)",
+                            if "gw_conv_gn3" in conv["entry_points"] else "conv_tc2_kernel (tcgen05+TMA implicit GEMM)",
                             "achieved": conv["achieved"], "peak": pk["bf16"], "unit": "TFLOP/s", "frac": conv["frac"],
-                            "traffic": measured_traffic("reverse_step", "conv_gn_kernel" if "gw_conv_gn" in conv["entry_points"]
+                            "traffic": measured_traffic("reverse_step", "conv_gn_kernel" if "gw_conv_gn3" in conv["entry_points"]
                                                         else "conv_tc2_kernel", plan.Bn, L),
                             "traffic_note": "bytes per launch, ncu capture profiles/r01j_traffic.json (B=256, L=4096, in_ch=3)",
                             "peak_source": pk["src"] + " burst (kernels timed one by one)",

@@ -241,7 +241,7 @@ static inline cudaError_t gw_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim
 // the same with thread-block clusters of `cluster` consecutive CTAs (1 = none); cluster = 2 is a tcgen05 CTA pair
 template <typename... KArgs, typename... Args>
 static inline cudaError_t gw_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
-                                            Args&&... args) {
+                                            bool force_pdl, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -249,7 +249,7 @@ static inline cudaError_t gw_launch_cluster(void (*kernel)(KArgs...), dim3 grid,
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     int n = 0;
-    if (g_pdl) {
+    if (g_pdl || force_pdl) {
         at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[n].val.programmaticStreamSerializationAllowed = 1;
         ++n;

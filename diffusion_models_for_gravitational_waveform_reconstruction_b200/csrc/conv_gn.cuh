@@ -46,6 +46,13 @@ struct GnFuseArgs {
     int pair2;                // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2): ONE M = 256 MMA per pair, each CTA stages its own
                               //    A rows and HALF of every weight tile -- halves the weight bytes an SM pulls through the L2
     int wbox;                 // rows of the weight TMA box (64, or 32 when a pair splits a 64-row weight tile)
+    // ---- layer chaining (sampler): the NEXT layer's kernel is launched with programmatic stream serialization and starts on
+    // the SMs this kernel's early-finishing groups free; it orders itself per SAMPLE through these flags instead of waiting for
+    // the whole grid: no fill / drain bubble between layers and the last, partly filled round overlaps the next layer's work
+    unsigned int* done_cnt;   // [B] arrivals of this layer's epilogue warps (monotonic, never reset) or NULL: no signalling
+    unsigned int* done_flag;  // [B] = chain value V once every store of sample b has completed
+    const unsigned int* prev_flag;   // the producing layer's done_flag, or NULL: plain griddepcontrol.wait ordering
+    const int* serial_ptr;    // device chain serial; V = serial * 4096 + step + 1 is unique per (chain, reverse step)
     int dbg_mode;             // tools only (-DCGN_ABLATE builds): 1 no tanh, 2 no pack, 4 no stmatrix, 8 no TMA stores, 16 no pooling, 32 no TMEM load
     long long* dbg;           // tools only: [CTA][16 samples][8] clock64 stamps of CTA phases (NULL in production)
 };
@@ -314,9 +321,13 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // everything above touched parameters only; the activations, the exchange buffer and the step counter belong to the previous
-    // kernel of the stream (PDL, common.cuh)
-    pdl_wait();
+    // kernel of the stream (PDL, common.cuh).  Chained launches order themselves per sample (producer warp below): everything
+    // else this kernel reads was written before the previous non-chained kernel of the stream completed.
+    if (F.prev_flag == nullptr) pdl_wait();
     pdl_launch_dependents();
+    const unsigned int chain_v = F.serial_ptr != nullptr
+                                     ? (unsigned int)(*F.serial_ptr) * 4096u + (unsigned int)(F.step_ptr != nullptr ? *F.step_ptr : 0) + 1u
+                                     : 0u;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -324,6 +335,17 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             uint32_t ia = 0, pa = 0, ib = 0, pb = 0;
             const int wbox = F.wbox;
             for (int b = grp; b < F.B; b += F.n_groups) {
+                if (F.prev_flag != nullptr) {
+                    // chained launch: sample b of the producing layer (and, transitively, of every layer before it) is complete
+                    unsigned int f;
+                    const long long t0 = clock64();
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(F.prev_flag + b) : "memory");
+                        if (f == chain_v) break;
+                        if (clock64() - t0 > 4000000000LL) xchg_timeout(b, -1);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");       // the TMA loads below must not pass the acquire
+                }
                 for (int s = 0; s < n_seg; ++s) {
                     const TcSeg sg = P.seg[n_tile][s];
                     if (sg.a_new) {
@@ -456,6 +478,21 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         // output phase (pair space) of this warp's columns: the CTA's n_tile, or the column half when a tile spans both
         const int my_par = !F.pair ? 0 : (P.n_tiles == 2 ? n_tile : ((ch * cols_per_warp) >= P.cout ? 1 : 0));
         int buf = 0, stores = 0;
+        int b_sig = -1, k_groups = 0;                         // chaining: my previous sample (not yet signalled), store groups of the current one
+        constexpr unsigned int SIG_PER_CTA = ONE ? 16u : 8u;  // epilogue warps that signal each sample
+        // every store group of sample b_sig has completed (at most `keep` newer groups pending) -> count this warp in; the last
+        // warp of the last CTA of the group publishes the flag (fence cumulativity carries every CTA's stores)
+        auto signal_done = [&](int bs, int keep) {
+            if (lane == 0) {
+                if (keep >= 2) tma_wait_all<2>(); else if (keep == 1) tma_wait_all<1>(); else tma_wait_all<0>();
+                __threadfence();
+                const unsigned int old = atomicAdd(F.done_cnt + bs, 1u);
+                if ((old + 1u) % (SIG_PER_CTA * (unsigned int)G) == 0u) {
+                    __threadfence();
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.done_flag + bs), "r"(chain_v) : "memory");
+                }
+            }
+        };
         float f_gam = 0.0f, f_bet = 0.0f;                     // FiLM (gamma, beta) of my column for the current sample
         auto load_film = [&](int b) {
             const float* fr = F.film + (size_t)step * F.film_step_stride + (size_t)b * F.film_b_stride + F.film_off;
@@ -526,6 +563,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                         tma_commit();
                     }
                     ++stores;
+                    ++k_groups;
                     if (NBUF == 2) buf ^= 1;
                 }
                 stat_reduce<CG_LOG2>(sv, my_stat, ((n_tile * P.bn + c0) & (P.cout - 1)) >> CG_LOG2, lane);
@@ -664,6 +702,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     tma_commit();
                 }
                 ++stores;
+                ++k_groups;
                 if (NBUF == 2) buf ^= 1;
                 if (!ONE && MT == 2 && kc == 0) {
 #pragma unroll
@@ -680,8 +719,16 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 if (leader) mbar_arrive(acc_empty(as));
                 else mbar_arrive_cluster(mapa_u32(acc_empty(as), 0));       // the leader issues this pair's MMAs
             }
+            if (F.done_flag != nullptr) {
+                // deferred by one sample: the stores of my previous sample are a whole sample period old, so waiting for all but
+                // the current sample's groups does not stall
+                if (b_sig >= 0) signal_done(b_sig, k_groups);
+                b_sig = b;
+                k_groups = 0;
+            }
             if (tid == 0) CGN_STAMP(5);
         }
+        if (F.done_flag != nullptr && b_sig >= 0) signal_done(b_sig, 0);
         if (lane == 0) tma_wait_all<0>();
         __syncwarp();
     }
@@ -782,16 +829,20 @@ static long long* g_cgn_dbg = nullptr;
 static int g_cgn_dbg_mode = 0;
 extern "C" void gw_conv_gn_debug(void* buf) { g_cgn_dbg = (long long*)buf; }
 extern "C" void gw_conv_gn_debug_mode(int m) { g_cgn_dbg_mode = m; }     // tools/cgn_timeline.py
-extern "C" long gw_conv_gn_sync_bytes(int B) { return 64 + (long)B * CGN_MAX_G * 16 * 8; }
+// [0, 64): epoch / finished counter; packets [B][CGN_MAX_G][16] x 8 bytes; done counters [B] and done flags [B] (uint32)
+extern "C" long gw_conv_gn_sync_bytes(int B) { return 64 + (long)B * CGN_MAX_G * 16 * 8 + (long)B * 8 + 64; }
 
 // gw_conv_gn2 = gw_conv_gn + the head conv's dot products (last decoder, Cout = 64 in pair space): head_w = final.weight
 // [C+1, 3], head_dots [B, L, 4] fp32 receive (sum_c out[l,c] w[c,k])_k for gw_final_step(dtype = GW_DOTS); out == NULL then
 // skips the activated tensor altogether.
-extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
+// gw_conv_gn3 = gw_conv_gn2 + layer chaining for the sampler: serial_ptr != NULL (with step_ptr) makes this launch signal per-sample
+// completion in its sync buffer; prev_sync = the sync buffer of the layer that produced src0 in the SAME reverse step (launched
+// with a non-NULL serial_ptr): this launch then overlaps the tail of that kernel and orders itself per sample.
+extern "C" int gw_conv_gn3(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
                            const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
                            const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
                            void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, const float* head_w,
-                           float* head_dots, void* stream) {
+                           float* head_dots, const void* prev_sync, const int* serial_ptr, void* stream) {
     CgnPlan pl;
     int rc = cgn_plan(s, Cc, pooled != nullptr, &pl);
     if (rc != GW_OK) return rc;
@@ -833,6 +884,18 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
     F.pair = s->pair == 1 ? 1 : 0;
     F.head_w = head_w; F.head_dots = head_dots; F.store_out = out != nullptr ? 1 : 0;
     F.pair2 = pl.pair2; F.wbox = pl.wbox;
+    {
+        const size_t flags_off = 64 + (size_t)s->B * CGN_MAX_G * 16 * 8;
+        const bool sig = serial_ptr != nullptr && step_ptr != nullptr;
+        GW_REQUIRE(prev_sync == nullptr || sig, "conv_gn: chaining needs serial_ptr and step_ptr");
+        F.serial_ptr = sig ? serial_ptr : nullptr;
+        F.done_cnt = sig ? reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(sync_buf) + flags_off) : nullptr;
+        F.done_flag = sig ? F.done_cnt + s->B : nullptr;
+        F.prev_flag = prev_sync != nullptr
+                          ? reinterpret_cast<const unsigned int*>(reinterpret_cast<const uint8_t*>(prev_sync) + flags_off) + s->B
+                          : nullptr;
+    }
+    const bool chained = F.prev_flag != nullptr;
     F.dbg = g_cgn_dbg;
     F.dbg_mode = g_cgn_dbg_mode;
     cudaStream_t st = (cudaStream_t)stream;
@@ -841,7 +904,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
 #define CGN_GO2(LG, MTV, CCV, PL, HD, P2)                                                                                 \
     do {                                                                                                                  \
         GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        GW_CUDA(gw_launch_cluster(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, P2 ? 2 : 1, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+        GW_CUDA(gw_launch_cluster(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, P2 ? 2 : 1, chained, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
     } while (0)
 #define CGN_GO(LG, MTV, CCV, PL)                                  \
     do {                                                          \
@@ -873,6 +936,14 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
 #undef CGN_GO2
     GW_LAUNCH_CHECK();
     return GW_OK;
+}
+extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
+                           const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
+                           const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
+                           void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, const float* head_w,
+                           float* head_dots, void* stream) {
+    return gw_conv_gn3(s, src0, src1, packed, bias, gn_w, gn_b, cond, Cc, wc, bc, film, film_off, film_b_stride, film_step_stride,
+                       step_ptr, out, pooled, raw, stats_out, sync_buf, head_w, head_dots, nullptr, nullptr, stream);
 }
 extern "C" int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
                           const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,

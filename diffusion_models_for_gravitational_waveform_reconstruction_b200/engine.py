@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -143,7 +144,9 @@ class _Workspace:
         self.stats = [torch.empty(B, 8, 2, device=device, dtype=torch.float32) for _ in range(2 * d + 1)] if keep_raw else None
         self.cond = [torch.empty(B, Ls[j], max(spec.cond_in_ch, 1), device=device, dtype=torch.float32)
                      for j in range(d + 1)] if spec.cond_in_ch > 0 else None
-        self.sync: Optional[Tensor] = None          # gw_conv_gn exchange buffer (zeroed once, see UNetEngine._block)
+        self.sync: Optional[Tensor] = None          # exchange buffer of the first block (zeroed once, see UNetEngine.workspace)
+        self.syncs: List[Optional[Tensor]] = [None] * (2 * d + 1)   # gw_conv_gn: one buffer per layer (packets, epochs, chain flags)
+        self.chain_prev: Optional[Tensor] = None    # sync buffer of the layer that just ran with chain signalling (body())
         self.coef0: Optional[Tensor] = None         # gw_conv_in_direct: per-(sample, channel) epilogue coefficients of block 0
         self.dots: Optional[Tensor] = None          # [B, L, 4] head dot products left by the last decoder's fused kernel
         self.head_fused = False                     # set by UNetEngine.body(): ws.dots is current, ws.out[-1] was not written
@@ -179,6 +182,7 @@ class UNetEngine:
         self._ws: Dict[tuple, _Workspace] = {}
         self._packed: Dict[tuple, Tensor] = {}
         self.launches = 0
+        self._chain_serial: Optional[Tensor] = None
         # inference option: gw_conv_in_block (stats pass + recompute/apply pass, no raw tensor) instead of gw_conv_in +
         # gw_gn_apply.  Measured on B200 at B=256, L=4096: 166 us vs 70 + 72 us -- the CUDA-core conv is issue-bound, so
         # recomputing it costs more than the 268 MB of HBM traffic it saves; kept (parity-tested) but off by default.
@@ -194,6 +198,9 @@ class UNetEngine:
         # inference: the last decoder's fused kernel also forms the three head-conv dot products per position (gw_conv_gn2), so
         # gw_final_step runs on 16 B per position and the [B, L, 64] activation is neither written nor read back
         self.fuse_head = True
+        # sampler: chain the fused layer kernels (gw_conv_gn3): each layer's launch overlaps the tail of the previous one and
+        # orders itself per sample through completion flags instead of a grid-wide dependency
+        self.chain_layers = os.environ.get("GWB200_CHAIN", "1") != "0"
         # inference: first block in one pass with ANALYTIC GroupNorm statistics (conv_in_direct.cu) instead of the exchange-based
         # conv_in_gn kernel.  Measured on B200 (B=256, L=4096, in_ch=3; profiles/r02_first_block.md): moments 25 us + one-pass
         # kernel 79 us vs 107 us for conv_in_gn -- a wash so far, so the parity-tested kernel stays an option
@@ -276,7 +283,10 @@ class UNetEngine:
         if ws is None:
             ws = _Workspace(self.spec, B, L, self.tdtype, self.device, keep_raw)
             if self.dtype == "bf16":
-                ws.sync = torch.zeros(self.lib.gw_conv_gn_sync_bytes(B), device=self.device, dtype=torch.uint8)
+                # exchange buffers are zeroed ONCE, outside any graph capture: epochs / chain counters only ever advance
+                nb = self.lib.gw_conv_gn_sync_bytes(B)
+                ws.sync = torch.zeros(nb, device=self.device, dtype=torch.uint8)
+                ws.syncs = [torch.zeros(nb, device=self.device, dtype=torch.uint8) for _ in range(2 * self.spec.depth + 1)]
             self._ws[key] = ws
         return ws
 
@@ -375,11 +385,12 @@ class UNetEngine:
                 fused = self.lib.gw_conv_gn_group(C.byref(shp1), Cc, 1 if pooled is not None else 0) > 0
                 self._fuse_ok[fkey] = fused
         if not fused:
+            ws.chain_prev = None
             n_part = self._conv(li, src0, src1, raw, ws.part)
             self._gn(li, ws, n_part, film, film_b_stride, film_step_stride, step_ptr, pooled, lvl)
             return False
-        if ws.sync is None:
-            ws.sync = torch.zeros(self.lib.gw_conv_gn_sync_bytes(B), device=self.device, dtype=torch.uint8)
+        if ws.syncs[li] is None:
+            ws.syncs[li] = torch.zeros(self.lib.gw_conv_gn_sync_bytes(B), device=self.device, dtype=torch.uint8)
         key = (li, L, L0)
         packed = self._packed.get(key)
         if packed is None:
@@ -391,22 +402,29 @@ class UNetEngine:
         head = head and not keep and Cout == 64 and src1 is not None and pooled is None
         if head and ws.dots is None:
             ws.dots = torch.empty(B, L, 4, device=self.device, dtype=torch.float32)
-        check(self.lib.gw_conv_gn2(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),
+        serial = self._chain_serial if (self.chain_layers and not keep and step_ptr is not None) else None
+        prev = ws.chain_prev if serial is not None else None
+        check(self.lib.gw_conv_gn3(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),
                                    ptr(self.p[name + ".1.weight"]), ptr(self.p[name + ".1.bias"]),
                                    ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
                                    ptr(self.p[cname + ".weight"]) if Cc > 0 else None,
                                    ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film), sp.film_offsets()[li],
                                    film_b_stride, film_step_stride, ptr(step_ptr), None if head else ptr(ws.out[li]), ptr(pooled),
-                                   ptr(raw) if keep else None, ptr(ws.stats[li]) if keep else None, ptr(ws.sync),
-                                   ptr(self.wf) if head else None, ptr(ws.dots) if head else None,
+                                   ptr(raw) if keep else None, ptr(ws.stats[li]) if keep else None, ptr(ws.syncs[li]),
+                                   ptr(self.wf) if head else None, ptr(ws.dots) if head else None, ptr(prev), ptr(serial),
                                    _cabi.stream_ptr()), f"conv_gn[{name}]")
         self.launches += 1
+        # the next layer may chain to this launch (the head flavour writes its dots with plain stores: no flags)
+        ws.chain_prev = ws.syncs[li] if (serial is not None and not head) else None
         return head
 
     def body(self, ws: _Workspace, net_a: Tensor, net_b: Optional[Tensor], step_ptr: Optional[Tensor], film: Tensor,
-             film_b_stride: int, film_step_stride: int) -> Tensor:
-        """conv_in .. decoders[-1] FiLM; returns the last activation [B, L, base_ch].  The cond pyramid must be current."""
+             film_b_stride: int, film_step_stride: int, chain_serial: Optional[Tensor] = None) -> Tensor:
+        """conv_in .. decoders[-1] FiLM; returns the last activation [B, L, base_ch].  The cond pyramid must be current.
+        `chain_serial` (device int32, bumped once per chain by the sampler) enables layer chaining (gw_conv_gn3)."""
         sp = self.spec
+        self._chain_serial = chain_serial
+        ws.chain_prev = None                        # the first block is not a chained producer
         d = sp.depth
         B, Cx, L = net_a.shape
         st = _cabi.stream_ptr()
@@ -594,6 +612,9 @@ class SamplerPlan:
         self.ws = eng.workspace(self.Bn, L)
         self.y_dc = torch.zeros(B, L, device=dev, dtype=torch.float32) if dc_weight > 0 else None
         self.adv = torch.zeros(1, dtype=torch.int32, device=dev)      # CTA counter of the self-advancing head kernel
+        self.serial = torch.zeros(1, dtype=torch.int32, device=dev)   # chain serial: (serial, step) tags the layer-chaining flags
+        if N >= 4096:
+            raise ValueError("SamplerPlan: at most 4095 reverse steps per chain")
         # Philox key {seed, sample0} lives in device memory: the kernel arguments of a captured graph are frozen, the key of
         # a cached plan is not (chunked sweeps, rank shards, repeated seed=None calls)
         self.rng = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -633,7 +654,7 @@ class SamplerPlan:
     # one reverse step = 8 kernels (bf16 fused path)
     def enqueue_step(self) -> None:
         eng = self.eng
-        h = eng.body(self.ws, self.net[0], self.net[1], self.step, self.film, 0, eng.spec.film_dim)
+        h = eng.body(self.ws, self.net[0], self.net[1], self.step, self.film, 0, eng.spec.film_dim, chain_serial=self.serial)
         eng.head(h, self.net[0], self.net[1], self.params, self.coef, self.step, self.noise, self.trace_eps, self.trace_x0, self.B)
         if not self.ws.head_fused:                     # the head kernel on the fused dots advances the counter itself
             check(eng.lib.gw_step_advance(ptr(self.step), -1, _cabi.stream_ptr()), "step_advance")
@@ -655,6 +676,7 @@ class SamplerPlan:
         if self.y_dc is not None:
             self.y_dc.copy_(y_dc.reshape(B, self.L))
         self.step.zero_()
+        self.serial.add_(1)                            # a new chain: its (serial, step) tags differ from every earlier chain's
         self.eng.cond_pyramid(self.ws, self.net[0])
 
     def capture(self, steps_per_graph: int) -> None:
@@ -672,6 +694,7 @@ class SamplerPlan:
         for n, sv in zip(self.net, saved):
             n.copy_(sv)
         self.step.zero_()
+        self.serial.add_(1)                            # the warm-up step used (serial, step 0): its chain flags must not match again
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for _ in range(steps_per_graph):

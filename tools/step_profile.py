@@ -29,7 +29,7 @@ class TimedLib:
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
-        if not name.startswith("gw_") or name in ("gw_last_error", "gw_conv_tc_packed_elems", "gw_conv_tc_n_part", "gw_conv_gn_group", "gw_conv_in_gn_group", "gw_conv_gn_sync_bytes", "gw_version"):
+        if not name.startswith("gw_") or name in ("gw_last_error", "gw_conv_tc_packed_elems", "gw_conv_tc_n_part", "gw_conv_gn_group", "gw_conv_in_gn_group", "gw_conv_gn_sync_bytes", "gw_conv_in_direct_ws_floats", "gw_version"):
             return fn
 
         def wrapped(*a):

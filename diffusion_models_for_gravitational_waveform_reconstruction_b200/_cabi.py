@@ -57,7 +57,7 @@ _SIGS = {
     "gw_conv_gn2": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P,
                      _P, _P, _P], _I),
     "gw_conv_gn3": ([C.POINTER(ConvTcShape), _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P, _P,
-                     _P, _P, _P, _P, _P], _I),
+                     _P, _P, _P, _I, _P, _P], _I),
 }
 # training step: backward.cu / optim.cu
 _SIGS.update({

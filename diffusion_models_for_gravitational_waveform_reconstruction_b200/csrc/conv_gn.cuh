@@ -20,7 +20,7 @@
 #define CGN_MAX_G 32
 #define CGN_NCA_MAX 8
 #define CGN_EPI_GROUPS 2       // epilogue warpgroups (8 warps each) working on alternate samples
-#define CGN_THREADS (64 + CGN_EPI_GROUPS * 256)
+#define CGN_THREADS (64 + CGN_EPI_GROUPS * 256 + 32)     // TMA warp, MMA warp, epilogue warpgroups, chain-signalling warp
 // 1: the 16 epilogue warps form ONE group (every warp owns one 32x64 chunk of every sample); 0: two groups of 8 warps on
 // alternate samples (two chunks per warp)
 #ifndef CGN_ONE_GROUP
@@ -49,12 +49,13 @@ struct GnFuseArgs {
     // ---- layer chaining (sampler): the NEXT layer's kernel is launched with programmatic stream serialization and starts on
     // the SMs this kernel's early-finishing groups free; it orders itself per SAMPLE through these flags instead of waiting for
     // the whole grid: no fill / drain bubble between layers and the last, partly filled round overlaps the next layer's work
-    unsigned int* done_cnt;   // [B] arrivals of this layer's epilogue warps (monotonic, never reset) or NULL: no signalling
-    unsigned int* done_flag;  // [B] = chain value V once every store of sample b has completed
+    unsigned int* done_flag;  // [B][CGN_MAX_G]: CTA j of a sample's group writes V once all ITS stores of sample b have completed; NULL: off
     const unsigned int* prev_flag;   // the producing layer's done_flag, or NULL: plain griddepcontrol.wait ordering
+    int prev_G;               // CTAs per sample of the producing layer
     const int* serial_ptr;    // device chain serial; V = serial * 4096 + step + 1 is unique per (chain, reverse step)
     int dbg_mode;             // tools only (-DCGN_ABLATE builds): 1 no tanh, 2 no pack, 4 no stmatrix, 8 no TMA stores, 16 no pooling, 32 no TMEM load
     long long* dbg;           // tools only: [CTA][16 samples][8] clock64 stamps of CTA phases (NULL in production)
+    unsigned long long* tdbg; // tools only: [CTA][2] %globaltimer at CTA start / end of this launch (NULL in production)
 };
 #define CGN_STAMP(k)                                                                                     \
     do {                                                                                                 \
@@ -264,7 +265,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     const uint32_t sPool = sStage + EW * NBUF * 4096u;                  // [EW warps][NBUF][2048] (POOL)
     const uint32_t sMisc = sPool + (POOL ? EW * NBUF * 2048u : 0u);
     uint8_t* misc = smem_raw + (sMisc - smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(misc);                 // a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(misc);                 // a_full[SA] a_empty[SA] b_full[SB] b_empty[SB] acc_full[2] acc_empty[2] sig[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * 28);
     float* s_bias = reinterpret_cast<float*>(misc + 256);               // [256]
     // per epilogue warpgroup: s_stat [8 warps][8 groups][2] | s_x [G][16] | s_abf, s_gef [128 column pairs][4] | s_wf [128][NCA][2]
@@ -277,6 +278,10 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     auto b_empty = [&](int i) { return smem_u32(bars + 2 * SA + SB + i); };
     auto acc_full = [&](int i) { return smem_u32(bars + 2 * SA + 2 * SB + i); };
     auto acc_empty = [&](int i) { return smem_u32(bars + 2 * SA + 2 * SB + 2 + i); };
+    // chaining: monotonic per-warpgroup arrival counters "my stores of a sample completed" (an mbarrier's phase parity would alias:
+    // nothing stops the epilogue from completing two samples before the signalling thread has looked)
+    auto sig_cnt = [&](int i) { return smem_u32(bars + 2 * SA + 2 * SB + 4 + i); };
+    static_assert(CGN_ONE_GROUP == 0, "the chain-signalling barriers count the 8 warps of one epilogue warpgroup");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = F.G;
@@ -302,6 +307,8 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         // pairs: the leader's MMA thread waits until BOTH epilogues have drained an accumulator stage
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), PAIR2 ? 2 : 1); }
+        bars[2 * SA + 2 * SB + 4] = 0ull;
+        bars[2 * SA + 2 * SB + 5] = 0ull;
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -325,6 +332,11 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     // else this kernel reads was written before the previous non-chained kernel of the stream completed.
     if (F.prev_flag == nullptr) pdl_wait();
     pdl_launch_dependents();
+    if (F.tdbg != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        F.tdbg[blockIdx.x * 2] = t;
+    }
     const unsigned int chain_v = F.serial_ptr != nullptr
                                      ? (unsigned int)(*F.serial_ptr) * 4096u + (unsigned int)(F.step_ptr != nullptr ? *F.step_ptr : 0) + 1u
                                      : 0u;
@@ -334,17 +346,35 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         if (lane == 0) {
             uint32_t ia = 0, pa = 0, ib = 0, pb = 0;
             const int wbox = F.wbox;
+            unsigned int pfl[8];                          // chain flags of the sample about to be loaded (prev_G <= 8 used)
+            auto load_flags = [&](int bb) {
+                const unsigned int* fp = F.prev_flag + (size_t)bb * CGN_MAX_G;
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(pfl[0]), "=r"(pfl[1]), "=r"(pfl[2]), "=r"(pfl[3]) : "l"(fp) : "memory");
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(pfl[4]), "=r"(pfl[5]), "=r"(pfl[6]), "=r"(pfl[7]) : "l"(fp + 4) : "memory");
+            };
+            if (F.prev_flag != nullptr && grp < F.B) load_flags(grp);
             for (int b = grp; b < F.B; b += F.n_groups) {
                 if (F.prev_flag != nullptr) {
                     // chained launch: sample b of the producing layer (and, transitively, of every layer before it) is complete
-                    unsigned int f;
+                    // (every CTA of its group has published V for b).  Relaxed accesses, as for the statistics packets (xchg.cuh): a
+                    // flag is stored only after the bulk stores it covers have COMPLETED (performed at the L2), the loads below are
+                    // issued only after the flag was read from the L2, and the tensor data never passes through an L1.
+                    // The flags of a sample are read with two 16-byte loads; those of the NEXT sample are requested right away, so
+                    // in steady state the check costs no L2 round trip.
                     const long long t0 = clock64();
                     for (;;) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(F.prev_flag + b) : "memory");
-                        if (f == chain_v) break;
+                        bool ok = true;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) ok = ok && (j >= F.prev_G || pfl[j] == chain_v);
+                        if (ok) break;
+                        __nanosleep(64);
+                        load_flags(b);
                         if (clock64() - t0 > 4000000000LL) xchg_timeout(b, -1);
                     }
-                    asm volatile("fence.proxy.async;" ::: "memory");       // the TMA loads below must not pass the acquire
+                    if (b + F.n_groups < F.B) load_flags(b + F.n_groups);
+                    asm volatile("fence.proxy.async;" ::: "memory");       // the TMA loads below must not pass the polls
                 }
                 for (int s = 0; s < n_seg; ++s) {
                     const TcSeg sg = P.seg[n_tile][s];
@@ -442,8 +472,28 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 CGN_STAMP(7);
             }
         }
+    } else if (warp >= 2 + 8 * CGN_EPI_GROUPS) {
+        // ===================== chain signalling (one thread) =====================
+        // The epilogue warps only count themselves in (shared memory) once their stores of a sample have completed; this otherwise
+        // idle thread then publishes the CTA's flag.  No gpu-scope release / atomic: a MEMBAR.GPU per sample cost 3 % of every
+        // layer (it stalls behind all of the SM's stores in flight), and the flag is safe without it (see the producer warp).
+        if (lane == 0 && F.done_flag != nullptr) {
+            int it = 0;
+            for (int b = grp; b < F.B; b += F.n_groups, ++it) {
+                const uint32_t need = 8u * (uint32_t)((it >> 1) + 1), sc = sig_cnt(it & 1);
+                const long long t0 = clock64();
+                for (;;) {
+                    uint32_t v;
+                    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(sc) : "memory");
+                    if (v >= need) break;
+                    __nanosleep(128);
+                    if (clock64() - t0 > 4000000000LL) xchg_timeout(b, -2);
+                }
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(F.done_flag + (size_t)b * CGN_MAX_G + j_cta), "r"(chain_v) : "memory");
+            }
+        }
     } else {
-        // ===================== epilogue (warps 2..9) =====================
+        // ===================== epilogue (warps 2..17) =====================
         constexpr bool ONE = CGN_ONE_GROUP != 0;
         constexpr int NT = ONE ? 512 : 256;           // threads of one epilogue group
         const int eg = ONE ? 0 : (warp - 2) >> 3;     // epilogue warpgroup: samples it = eg, eg + GROUPS, ... of this CTA
@@ -479,18 +529,13 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         const int my_par = !F.pair ? 0 : (P.n_tiles == 2 ? n_tile : ((ch * cols_per_warp) >= P.cout ? 1 : 0));
         int buf = 0, stores = 0;
         int b_sig = -1, k_groups = 0;                         // chaining: my previous sample (not yet signalled), store groups of the current one
-        constexpr unsigned int SIG_PER_CTA = ONE ? 16u : 8u;  // epilogue warps that signal each sample
-        // every store group of sample b_sig has completed (at most `keep` newer groups pending) -> count this warp in; the last
-        // warp of the last CTA of the group publishes the flag (fence cumulativity carries every CTA's stores)
-        auto signal_done = [&](int bs, int keep) {
+        // Completion of a sample for the next layer: a warp whose store groups of its PREVIOUS sample have completed (deferred by
+        // one sample, `keep` = groups of the newer sample still allowed in flight: no stall) arrives on the warpgroup's sig barrier;
+        // the signalling warp publishes it (see above).
+        auto stores_done = [&](int keep) {
             if (lane == 0) {
                 if (keep >= 2) tma_wait_all<2>(); else if (keep == 1) tma_wait_all<1>(); else tma_wait_all<0>();
-                __threadfence();
-                const unsigned int old = atomicAdd(F.done_cnt + bs, 1u);
-                if ((old + 1u) % (SIG_PER_CTA * (unsigned int)G) == 0u) {
-                    __threadfence();
-                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.done_flag + bs), "r"(chain_v) : "memory");
-                }
+                asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(sig_cnt(eg)) : "memory");
             }
         };
         float f_gam = 0.0f, f_bet = 0.0f;                     // FiLM (gamma, beta) of my column for the current sample
@@ -588,6 +633,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 if ((unsigned int)(pk >> 32) != epoch) {
                     const long long t0 = clock64();
                     do {
+                        __nanosleep(64);                  // the chain is power-capped: do not burn issue slots and L2 requests while waiting
                         pk = ld_relaxed_u64(src);
                         if (clock64() - t0 > 4000000000LL) xchg_timeout(b, i >> 4);
                     } while ((unsigned int)(pk >> 32) != epoch);
@@ -720,15 +766,14 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 else mbar_arrive_cluster(mapa_u32(acc_empty(as), 0));       // the leader issues this pair's MMAs
             }
             if (F.done_flag != nullptr) {
-                // deferred by one sample: the stores of my previous sample are a whole sample period old, so waiting for all but
-                // the current sample's groups does not stall
-                if (b_sig >= 0) signal_done(b_sig, k_groups);
+                // after the accumulator stage went back to the MMA warp (off its critical path): my stores of the PREVIOUS sample
+                if (b_sig >= 0) stores_done(k_groups);
                 b_sig = b;
                 k_groups = 0;
             }
             if (tid == 0) CGN_STAMP(5);
         }
-        if (F.done_flag != nullptr && b_sig >= 0) signal_done(b_sig, 0);
+        if (F.done_flag != nullptr && b_sig >= 0) stores_done(0);
         if (lane == 0) tma_wait_all<0>();
         __syncwarp();
     }
@@ -742,6 +787,11 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     }
     // last CTA out advances the epoch for the next launch (every CTA read it before it could finish)
     if (threadIdx.x == 0) {
+        if (F.tdbg != nullptr) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            F.tdbg[blockIdx.x * 2 + 1] = t;
+        }
         __threadfence();
         const unsigned int done = atomicAdd(F.ctrl + 1, 1u);
         if (done == gridDim.x - 1) {
@@ -826,11 +876,14 @@ extern "C" int gw_conv_gn_group(const gw_conv_tc_shape* s, int Cc, int pool) {
     return pl.G;
 }
 static long long* g_cgn_dbg = nullptr;
+static unsigned long long* g_cgn_tdbg = nullptr;      // tools/chain_overlap.py: [launch][160 CTAs][2] globaltimer stamps
+static int g_cgn_tdbg_launch = 0;
+extern "C" void gw_conv_gn_tdebug(void* buf) { g_cgn_tdbg = (unsigned long long*)buf; g_cgn_tdbg_launch = 0; }
 static int g_cgn_dbg_mode = 0;
 extern "C" void gw_conv_gn_debug(void* buf) { g_cgn_dbg = (long long*)buf; }
 extern "C" void gw_conv_gn_debug_mode(int m) { g_cgn_dbg_mode = m; }     // tools/cgn_timeline.py
-// [0, 64): epoch / finished counter; packets [B][CGN_MAX_G][16] x 8 bytes; done counters [B] and done flags [B] (uint32)
-extern "C" long gw_conv_gn_sync_bytes(int B) { return 64 + (long)B * CGN_MAX_G * 16 * 8 + (long)B * 8 + 64; }
+// [0, 64): epoch / finished counter; packets [B][CGN_MAX_G][16] x 8 bytes; chain flags [B][CGN_MAX_G] (uint32)
+extern "C" long gw_conv_gn_sync_bytes(int B) { return 64 + (long)B * CGN_MAX_G * 16 * 8 + (long)B * CGN_MAX_G * 4 + 64; }
 
 // gw_conv_gn2 = gw_conv_gn + the head conv's dot products (last decoder, Cout = 64 in pair space): head_w = final.weight
 // [C+1, 3], head_dots [B, L, 4] fp32 receive (sum_c out[l,c] w[c,k])_k for gw_final_step(dtype = GW_DOTS); out == NULL then
@@ -842,7 +895,7 @@ extern "C" int gw_conv_gn3(const gw_conv_tc_shape* s, const void* src0, const vo
                            const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
                            const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
                            void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, const float* head_w,
-                           float* head_dots, const void* prev_sync, const int* serial_ptr, void* stream) {
+                           float* head_dots, const void* prev_sync, int prev_G, const int* serial_ptr, void* stream) {
     CgnPlan pl;
     int rc = cgn_plan(s, Cc, pooled != nullptr, &pl);
     if (rc != GW_OK) return rc;
@@ -887,16 +940,16 @@ extern "C" int gw_conv_gn3(const gw_conv_tc_shape* s, const void* src0, const vo
     {
         const size_t flags_off = 64 + (size_t)s->B * CGN_MAX_G * 16 * 8;
         const bool sig = serial_ptr != nullptr && step_ptr != nullptr;
-        GW_REQUIRE(prev_sync == nullptr || sig, "conv_gn: chaining needs serial_ptr and step_ptr");
+        GW_REQUIRE(prev_sync == nullptr || (sig && prev_G >= 1 && prev_G <= 8), "conv_gn: chaining needs serial_ptr, step_ptr and a producer group of <= 8 CTAs");
         F.serial_ptr = sig ? serial_ptr : nullptr;
-        F.done_cnt = sig ? reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(sync_buf) + flags_off) : nullptr;
-        F.done_flag = sig ? F.done_cnt + s->B : nullptr;
-        F.prev_flag = prev_sync != nullptr
-                          ? reinterpret_cast<const unsigned int*>(reinterpret_cast<const uint8_t*>(prev_sync) + flags_off) + s->B
-                          : nullptr;
+        F.done_flag = sig ? reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(sync_buf) + flags_off) : nullptr;
+        F.prev_flag = prev_sync != nullptr ? reinterpret_cast<const unsigned int*>(reinterpret_cast<const uint8_t*>(prev_sync) + flags_off)
+                                           : nullptr;
+        F.prev_G = prev_G;
     }
     const bool chained = F.prev_flag != nullptr;
     F.dbg = g_cgn_dbg;
+    F.tdbg = g_cgn_tdbg != nullptr ? g_cgn_tdbg + (size_t)(g_cgn_tdbg_launch++) * 160 * 2 : nullptr;
     F.dbg_mode = g_cgn_dbg_mode;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = pl.G * pl.n_groups, smem = pl.smem;
@@ -943,7 +996,7 @@ extern "C" int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const vo
                            void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, const float* head_w,
                            float* head_dots, void* stream) {
     return gw_conv_gn3(s, src0, src1, packed, bias, gn_w, gn_b, cond, Cc, wc, bc, film, film_off, film_b_stride, film_step_stride,
-                       step_ptr, out, pooled, raw, stats_out, sync_buf, head_w, head_dots, nullptr, nullptr, stream);
+                       step_ptr, out, pooled, raw, stats_out, sync_buf, head_w, head_dots, nullptr, 0, nullptr, stream);
 }
 extern "C" int gw_conv_gn(const gw_conv_tc_shape* s, const void* src0, const void* src1, const void* packed, const float* bias,
                           const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,

@@ -146,7 +146,7 @@ class _Workspace:
                      for j in range(d + 1)] if spec.cond_in_ch > 0 else None
         self.sync: Optional[Tensor] = None          # exchange buffer of the first block (zeroed once, see UNetEngine.workspace)
         self.syncs: List[Optional[Tensor]] = [None] * (2 * d + 1)   # gw_conv_gn: one buffer per layer (packets, epochs, chain flags)
-        self.chain_prev: Optional[Tensor] = None    # sync buffer of the layer that just ran with chain signalling (body())
+        self.chain_prev = None                      # (sync buffer, CTAs per sample) of the layer that just ran with chain signalling
         self.coef0: Optional[Tensor] = None         # gw_conv_in_direct: per-(sample, channel) epilogue coefficients of block 0
         self.dots: Optional[Tensor] = None          # [B, L, 4] head dot products left by the last decoder's fused kernel
         self.head_fused = False                     # set by UNetEngine.body(): ws.dots is current, ws.out[-1] was not written
@@ -199,8 +199,12 @@ class UNetEngine:
         # gw_final_step runs on 16 B per position and the [B, L, 64] activation is neither written nor read back
         self.fuse_head = True
         # sampler: chain the fused layer kernels (gw_conv_gn3): each layer's launch overlaps the tail of the previous one and
-        # orders itself per sample through completion flags instead of a grid-wide dependency
-        self.chain_layers = os.environ.get("GWB200_CHAIN", "1") != "0"
+        # orders itself per sample through completion flags instead of a grid-wide dependency.  Measured on B200 (B=256, L=4096;
+        # profiles/r02_chain_overlap.md): the six layer kernels of an eager reverse step finish 19 us earlier (706 vs 725 us: the
+        # 6 us launch gaps disappear, the overlap is real), but inside the CUDA graph the chain is power-capped -- the SM clock
+        # drops from 1837 to 1788 MHz and the throughput is unchanged (287.7 vs 289.3 waveforms/s) -- so it stays an option
+        # (GWB200_CHAIN=1), parity-tested in both modes.
+        self.chain_layers = os.environ.get("GWB200_CHAIN", "0") not in ("0", "")
         # inference: first block in one pass with ANALYTIC GroupNorm statistics (conv_in_direct.cu) instead of the exchange-based
         # conv_in_gn kernel.  Measured on B200 (B=256, L=4096, in_ch=3; profiles/r02_first_block.md): moments 25 us + one-pass
         # kernel 79 us vs 107 us for conv_in_gn -- a wash so far, so the parity-tested kernel stays an option
@@ -382,7 +386,7 @@ class UNetEngine:
             fused = self._fuse_ok.get(fkey)
             if fused is None:
                 shp1 = self._shape(li, 1, L, L0)
-                fused = self.lib.gw_conv_gn_group(C.byref(shp1), Cc, 1 if pooled is not None else 0) > 0
+                fused = self.lib.gw_conv_gn_group(C.byref(shp1), Cc, 1 if pooled is not None else 0)
                 self._fuse_ok[fkey] = fused
         if not fused:
             ws.chain_prev = None
@@ -403,7 +407,8 @@ class UNetEngine:
         if head and ws.dots is None:
             ws.dots = torch.empty(B, L, 4, device=self.device, dtype=torch.float32)
         serial = self._chain_serial if (self.chain_layers and not keep and step_ptr is not None) else None
-        prev = ws.chain_prev if serial is not None else None
+        prev, prev_g = ws.chain_prev if (serial is not None and ws.chain_prev is not None and ws.chain_prev[1] <= 8
+                                         and os.environ.get("GWB200_CHAIN", "0") != "2") else (None, 0)
         check(self.lib.gw_conv_gn3(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),
                                    ptr(self.p[name + ".1.weight"]), ptr(self.p[name + ".1.bias"]),
                                    ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
@@ -411,11 +416,11 @@ class UNetEngine:
                                    ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film), sp.film_offsets()[li],
                                    film_b_stride, film_step_stride, ptr(step_ptr), None if head else ptr(ws.out[li]), ptr(pooled),
                                    ptr(raw) if keep else None, ptr(ws.stats[li]) if keep else None, ptr(ws.syncs[li]),
-                                   ptr(self.wf) if head else None, ptr(ws.dots) if head else None, ptr(prev), ptr(serial),
+                                   ptr(self.wf) if head else None, ptr(ws.dots) if head else None, ptr(prev), prev_g, ptr(serial),
                                    _cabi.stream_ptr()), f"conv_gn[{name}]")
         self.launches += 1
         # the next layer may chain to this launch (the head flavour writes its dots with plain stores: no flags)
-        ws.chain_prev = ws.syncs[li] if (serial is not None and not head) else None
+        ws.chain_prev = (ws.syncs[li], int(fused)) if (serial is not None and not head) else None
         return head
 
     def body(self, ws: _Workspace, net_a: Tensor, net_b: Optional[Tensor], step_ptr: Optional[Tensor], film: Tensor,

@@ -207,7 +207,7 @@ int gw_conv_gn2(const gw_conv_tc_shape* s, const void* src0, const void* src1, c
 /* gw_conv_gn3 = gw_conv_gn2 + LAYER CHAINING for the sampler.  serial_ptr (device int32, bumped once per chain by the caller)
  * together with step_ptr gives every (chain, reverse step) a unique value V; a launch with serial_ptr != NULL publishes, per
  * sample, flag[b] = V in its sync buffer once all of the sample's stores have completed.  prev_sync = the sync buffer of the
- * layer that produced src0 in the same reverse step (itself launched with serial_ptr): this launch is then issued with
+ * layer that produced src0 in the same reverse step (itself launched with serial_ptr; prev_G = its gw_conv_gn_group): this launch is then issued with
  * programmatic stream serialization, starts on the SMs the producer's early-finishing CTA groups free, and orders itself per
  * SAMPLE through the producer's flags instead of waiting for the producer's whole grid -- no fill / drain bubble between
  * layers, and a partly filled last round overlaps the next layer's work.  Every layer needs its OWN sync buffer. */
@@ -215,7 +215,7 @@ int gw_conv_gn3(const gw_conv_tc_shape* s, const void* src0, const void* src1, c
                 const float* gn_w, const float* gn_b, const float* cond, int Cc, const float* wc, const float* bc,
                 const float* film, int film_off, long film_b_stride, long film_step_stride, const int* step_ptr,
                 void* out, void* pooled, void* raw, float* stats_out, void* sync_buf, const float* head_w,
-                float* head_dots, const void* prev_sync, const int* serial_ptr, void* stream);
+                float* head_dots, const void* prev_sync, int prev_G, const int* serial_ptr, void* stream);
 
 
 /* ---- fused FIRST block for inference: Conv1d(C_in -> 64, k=3) -> GroupNorm -> SiLU -> + cond 1x1 conv -> FiLM (-> pool) in

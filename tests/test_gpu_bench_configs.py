@@ -238,3 +238,26 @@ def test_backward_bf16_selfcond_c7_L4096_vs_oracle():
     for k, go in grads_o.items():
         err = float((grads[k].cpu().double() - go.double()).norm())
         assert err <= 5e-2 * max(float(go.norm()), 2e-2 * tot), (k, err, float(go.norm()))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_layer_chaining_is_bit_identical(use_graph):
+    """gw_conv_gn3: the fused layer kernels launched with programmatic stream serialization, each ordering itself per SAMPLE
+    through the producer's completion flags instead of a grid-wide dependency (option GWB200_CHAIN=1).  Same arithmetic, so the
+    chain result is bit-identical to the plain launch order -- with more samples than CTA groups, twice through the same plan
+    (the second chain must not be satisfied by the first chain's flags)."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion
+    L, B = 4096, 40
+    diff = CustomDiffusion(T=1000, device="cuda")
+    y = synthetic_chirps(B, L, snr=10.0, seed=80)["y_norm"]
+    noise = torch.stack([gaussian((B, 1, L), seed=700 + k) for k in range(14)], 0)
+    kw = dict(steps=12, eta=1.0, start_t=529)
+    outs = {}
+    for chain in (False, True):
+        model = _model(3, 1, seed=1, dtype="bf16")
+        model.engine("bf16").chain_layers = chain
+        a = _sample(model, diff, y, kw, noise=noise, use_graph=use_graph)
+        b = _sample(model, diff, y, kw, noise=noise, use_graph=use_graph)
+        assert torch.equal(a, b)
+        outs[chain] = a
+    assert torch.equal(outs[False], outs[True])

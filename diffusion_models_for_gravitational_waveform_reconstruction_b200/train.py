@@ -513,6 +513,8 @@ class FusedTrainStep:
         self.ab, self.sab, self.s1mab = ab, ab.sqrt().contiguous(), (1 - ab).sqrt().contiguous()
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.overlap_prep = True                     # dgrad weight preparation on a forked stream / graph branch
+        import os as _os
+        self.capture_allreduce = _os.environ.get("GWB200_GRAPH_ALLREDUCE", "0") == "1"     # world > 1: collective inside the graph
         self._side: Optional[torch.cuda.Stream] = None
 
     # ------------------------------------------------------------------ host -> device staging
@@ -714,20 +716,27 @@ class FusedTrainStep:
             self._enqueue_update()
         else:
             key = (bool(selfcond), draws, philox, self.p_uncond, self.t_min)
-            g = self._graphs.get(key)
-            if g is None:
-                g = self._capture(key)
-            g.replay()
+            gs = self._graphs.get(key)
+            if gs is None:
+                gs = self._capture(key)
+            if len(gs) == 1:
+                gs[0].replay()
+            else:                                             # world > 1 (default): the collective runs between two graphs
+                gs[0].replay()
+                self._allreduce()
+                gs[1].replay()
         self.steps_done += 1
         # the flat buffer changed under the module's parameter views (no torch version bump): engines that UNet1D.engine()
         # hands out (model(x, t), ddim_sample(model, ...)) must re-pack their bf16 weights / FiLM tables on next use
         self.model._versions = None
 
     def _capture(self, key):
-        """ONE graph per step flavour: [draws, pack, (self-cond fwd), fwd, loss, backward, all-reduce, norm, clip+AdamW+EMA,
-        re-pack, advance].  The NCCL all-reduce of the gradient bucket is captured with the kernels, so a step is a single
-        graph launch with no host work between the backward pass and the optimiser."""
+        """world == 1: ONE graph per step flavour: [draws, pack, (self-cond fwd), fwd, loss, backward, norm, clip+AdamW+EMA,
+        re-pack, advance] -- a step is a single graph launch.  world > 1: two graphs with the NCCL all-reduce of the gradient
+        bucket between them on the same stream (the configuration measured at 2 / 8 GPUs); `capture_allreduce = True` captures
+        the collective into the single graph as well (NCCL is capturable; opt-in)."""
         selfcond, draws, philox = key[:3]
+        one = self.world == 1 or self.capture_allreduce
         saved = [b.clone() for b in (self.flat_p, self.flat_m, self.flat_v, self.step_ctr, self.opt_state)]
         saved_ema = self.flat_ema.clone() if self.flat_ema is not None else None
         s = torch.cuda.Stream()
@@ -743,13 +752,21 @@ class FusedTrainStep:
         if saved_ema is not None:
             self.flat_ema.copy_(saved_ema)
         self.eng.refresh()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._enqueue(selfcond, draws, philox)
-            self._allreduce()
-            self._enqueue_update()
-        self._graphs[key] = g
-        return g
+        if one:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(selfcond, draws, philox)
+                self._allreduce()
+                self._enqueue_update()
+            self._graphs[key] = (g,)
+        else:
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._enqueue(selfcond, draws, philox)
+            with torch.cuda.graph(g2):
+                self._enqueue_update()
+            self._graphs[key] = (g1, g2)
+        return self._graphs[key]
 
 
 # ======================================================================================================

@@ -54,10 +54,18 @@ def main():
     ap.add_argument("--dtype", default="fp32")
     ap.add_argument("--Bg", type=int, default=8)
     ap.add_argument("--L", type=int, default=1024)
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"],
+                    help="gloo + --same-device: both ranks share cuda:0 (host-staged all-reduce): the DP logic on a one-GPU box")
+    ap.add_argument("--same-device", action="store_true")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    if a.same_device:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if a.backend == "nccl":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
     from diffusion_models_for_gravitational_waveform_reconstruction_b200.parallel import current_shard
     sh = current_shard(a.Bg)
     clean, cond, mask = batch(a.Bg, a.L)

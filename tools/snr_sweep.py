@@ -103,6 +103,17 @@ def run(a):
                "tail_corr_vs_clean_mean": float(corr_dev.mean()),
                "overlap_vs_clean_by_snr": {f"{lo}-{lo + 5}": float(ov_clean[(snr >= lo) & (snr < lo + 5)].mean())
                                            for lo in range(5, 30, 5) if ((snr >= lo) & (snr < lo + 5)).any()}}
+        if getattr(a, "save_first", None):
+            # the first injections of rank 0's shard: re-done on one GPU with the CPU oracle (`--check K --compare-first file`),
+            # since the result of an injection does not depend on the world size or on the chunking
+            k = min(a.save_first_k, recon.shape[0])
+            torch.save({"recon": recon[:k].clone(), "n": a.n, "world": world, "steps": a.steps, "seed": a.seed}, a.save_first)
+        if getattr(a, "compare_first", None):
+            ref8 = torch.load(a.compare_first)
+            k = min(ref8["recon"].shape[0], recon.shape[0])
+            res["same_as_saved_run"] = {"k": k, "saved_world": ref8["world"], "saved_n": ref8["n"],
+                                        "bit_equal": bool(torch.equal(ref8["recon"][:k], recon[:k])),
+                                        "max_abs_diff": float((ref8["recon"][:k] - recon[:k]).abs().max())}
         if a.check > 0:
             import oracle
             k = min(a.check, recon.shape[0])
@@ -135,6 +146,9 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--check", type=int, default=0, help="injections re-done with the CPU oracle on rank 0")
+    ap.add_argument("--save-first", default=None, help="file: keep rank 0's first --save-first-k reconstructions")
+    ap.add_argument("--save-first-k", type=int, default=256)
+    ap.add_argument("--compare-first", default=None, help="file written by --save-first of another run (e.g. the 8-GPU one)")
     run(ap.parse_args())
 
 

@@ -107,7 +107,10 @@ def run(a):
             # the first injections of rank 0's shard: re-done on one GPU with the CPU oracle (`--check K --compare-first file`),
             # since the result of an injection does not depend on the world size or on the chunking
             k = min(a.save_first_k, recon.shape[0])
-            torch.save({"recon": recon[:k].clone(), "n": a.n, "world": world, "steps": a.steps, "seed": a.seed}, a.save_first)
+            # x_T of these injections (step 0 of each one's Philox stream), so that tools/sweep_oracle_check.py can redo them on a CPU
+            xT = inf.philox_normal(k, a.length, a.seed, 0, 0, dev).cpu()
+            torch.save({"recon": recon[:k].clone(), "xT": xT, "n": a.n, "world": world, "steps": a.steps, "seed": a.seed,
+                        "eta": a.eta, "start_t": a.start_t, "length": a.length, "dtype": a.dtype}, a.save_first)
         if getattr(a, "compare_first", None):
             ref8 = torch.load(a.compare_first)
             k = min(ref8["recon"].shape[0], recon.shape[0])
@@ -137,7 +140,7 @@ def run(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--n", "--count", dest="n", type=int, default=65536)
     ap.add_argument("--chunk", type=int, default=1024)
     ap.add_argument("--length", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=50)

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) periodogram_kernel(const cufftDoubleCompl
     P[(size_t)b * F + f] = fmax(acc, 1e-20);
 }
 
-// Z = Y * g(P):  mode 0: 1/sqrt(P)   mode 1: 1/sqrt(P + 1e-12)   mode 2: sqrt(P + 1e-12)
+// Z = Y * g(P):  mode 0: 1/sqrt(P)   mode 1: 1/sqrt(P + 1e-12)   mode 2: sqrt(P + 1e-12)   mode 3: 1/sqrt(P + 1e-20)
 __global__ void __launch_bounds__(256) spectral_scale_kernel(const cufftDoubleComplex* __restrict__ Y, const double* __restrict__ P,
                                                              long p_b_stride, int F, int mode, cufftDoubleComplex* __restrict__ Z) {
     const int b = blockIdx.y;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) spectral_scale_kernel(const cufftDoubleCo
         const double g = sqrt(p + 1e-12);
         z.x = y.x * g; z.y = y.y * g;
     } else {
-        const double g = sqrt(mode == 0 ? p : p + 1e-12);
+        const double g = sqrt(mode == 0 ? p : (mode == 3 ? p + 1e-20 : p + 1e-12));
         z.x = y.x / g; z.y = y.y / g;
     }
     Z[(size_t)b * F + f] = z;
@@ -174,11 +174,12 @@ extern "C" int gwf_whiten_train_like(const float* y, const float* x, int B, int 
 }
 
 // spectral multiply / divide by a given PSD: mode 1 = whiten with 1/sqrt(P + 1e-12) (_whiten_pair_model, inference.py:190-199, no
-// mean removal), mode 2 = de-whiten with sqrt(P + 1e-12) (_dewhiten_train_like / _dewhiten_model, inference.py:155-159, 201-203).
+// mean removal), mode 2 = de-whiten with sqrt(P + 1e-12) (_dewhiten_train_like / _dewhiten_model, inference.py:155-159, 201-203),
+// mode 3 = whiten with 1/sqrt(P + 1e-20) (the data loader's model / Welch whitening, dataloader.py:127-143).
 // P fp64 [B, L/2+1] or one shared row (p_shared != 0).  Output fp32 (o32) and / or fp64 (o64).
 extern "C" int gwf_apply_psd(const float* sig, int B, int L, const double* P, int p_shared, int mode, float* o32, double* o64,
                              void* work, void* stream) {
-    GW_REQUIRE(B > 0 && L >= 2 && sig && P && work && (o32 || o64) && (mode == 1 || mode == 2), "gwf_apply_psd: arguments");
+    GW_REQUIRE(B > 0 && L >= 2 && sig && P && work && (o32 || o64) && (mode >= 1 && mode <= 3), "gwf_apply_psd: arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int F = L / 2 + 1;
     double* tbuf = (double*)work;
@@ -216,6 +217,130 @@ __global__ void interp_psd_kernel(const double* __restrict__ Ps, int n_src, int 
 extern "C" int gwf_interp_psd(const double* P_src, int n_src, int L, double fs, double* out, void* stream) {
     GW_REQUIRE(P_src && out && n_src >= 2 && L >= 2 && fs > 0.0, "gwf_interp_psd: arguments");
     interp_psd_kernel<<<gw_cdiv(L / 2 + 1, 256), 256, 0, (cudaStream_t)stream>>>(P_src, n_src, L, fs, out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// batched form: P_src fp64 [B, n_src] -> out [B, L/2+1]
+__global__ void interp_psd_batch_kernel(const double* __restrict__ Ps, int n_src, int L, double fs, double* __restrict__ out) {
+    const int F = L / 2 + 1;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const double* ps = Ps + (size_t)blockIdx.y * n_src;
+    double* o = out + (size_t)blockIdx.y * F;
+    if (n_src == F) { o[f] = ps[f]; return; }
+    const int Ls = n_src * 2 - 2;
+    const double df_s = 1.0 / ((double)Ls * (1.0 / fs)), df_t = 1.0 / ((double)L * (1.0 / fs));
+    const double x = (double)f * df_t;
+    if (x <= 0.0) { o[f] = ps[0]; return; }
+    const double xmax = (double)(n_src - 1) * df_s;
+    if (x >= xmax) { o[f] = ps[n_src - 1]; return; }
+    int k = (int)(x / df_s);
+    if (k > n_src - 2) k = n_src - 2;
+    while (k > 0 && (double)k * df_s > x) --k;
+    while (k < n_src - 2 && (double)(k + 1) * df_s <= x) ++k;
+    const double x0 = (double)k * df_s, x1 = (double)(k + 1) * df_s;
+    o[f] = (ps[k + 1] - ps[k]) / (x1 - x0) * (x - x0) + ps[k];
+}
+extern "C" int gwf_interp_psd_batch(const double* P_src, int B, int n_src, int L, double fs, double* out, void* stream) {
+    GW_REQUIRE(P_src && out && B > 0 && n_src >= 2 && L >= 2 && fs > 0.0, "gwf_interp_psd_batch: arguments");
+    interp_psd_batch_kernel<<<dim3(gw_cdiv(L / 2 + 1, 256), B), 256, 0, (cudaStream_t)stream>>>(P_src, n_src, L, fs, out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// np.interp(rfftfreq(L, 1/fs), xp, fp, left = fp[0], right = fp[-1]) for an arbitrary increasing grid xp (a saved Welch PSD with
+// its own frequency array, dataloader.py:136-139): xp, fp fp64 [B, n_src] -> out [B, L/2+1]
+__global__ void interp_grid_kernel(const double* __restrict__ xp, const double* __restrict__ fp, int n_src, int L, double fs,
+                                   double* __restrict__ out) {
+    const int F = L / 2 + 1;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const double* xs = xp + (size_t)blockIdx.y * n_src;
+    const double* ps = fp + (size_t)blockIdx.y * n_src;
+    const double x = (double)f / ((double)L * (1.0 / fs));
+    double v;
+    if (x <= xs[0]) v = ps[0];
+    else if (x >= xs[n_src - 1]) v = ps[n_src - 1];
+    else {
+        int lo = 0, hi = n_src - 1;                 // xs[lo] <= x < xs[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (xs[mid] <= x) lo = mid; else hi = mid;
+        }
+        v = (ps[lo + 1] - ps[lo]) / (xs[lo + 1] - xs[lo]) * (x - xs[lo]) + ps[lo];
+    }
+    out[(size_t)blockIdx.y * F + f] = v;
+}
+extern "C" int gwf_interp_grid(const double* xp, const double* fp, int B, int n_src, int L, double fs, double* out, void* stream) {
+    GW_REQUIRE(xp && fp && out && B > 0 && n_src >= 2 && L >= 2 && fs > 0.0, "gwf_interp_grid: arguments");
+    interp_grid_kernel<<<dim3(gw_cdiv(L / 2 + 1, 256), B), 256, 0, (cudaStream_t)stream>>>(xp, fp, n_src, L, fs, out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- Welch PSD (scipy.signal.welch)
+// inference._whiten_pair_welch (inference.py:161-173): welch(y, fs, nperseg = min(4096, L)) with scipy's defaults -- periodic Hann
+// window, noverlap = nperseg // 2, constant detrend per segment, one-sided density scaling, mean over the segments.
+// segment (b, s): (y[s*step + n] - mean_n) * w[n] -> fp64 [B * n_seg, nperseg]
+__global__ void __launch_bounds__(256) welch_segment_kernel(const float* __restrict__ y, int L, int nperseg, int step, int n_seg,
+                                                            double* __restrict__ out) {
+    __shared__ double red[8];
+    const int b = blockIdx.x / n_seg, sgm = blockIdx.x % n_seg;
+    const float* ys = y + (size_t)b * L + (size_t)sgm * step;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nperseg; i += 256) s += (double)ys[i];
+    const double mean = blk_sum_d(s, red) / (double)nperseg;
+    double* o = out + (size_t)blockIdx.x * nperseg;
+    for (int i = threadIdx.x; i < nperseg; i += 256) {
+        const double w = 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)i / (double)nperseg);
+        o[i] = ((double)ys[i] - mean) * w;
+    }
+}
+// Pxx[b, f] = mean_s |Y[b, s, f]|^2 * scale * (2 for the bins that have a mirror image)
+__global__ void __launch_bounds__(256) welch_average_kernel(const cufftDoubleComplex* __restrict__ Y, int n_seg, int nperseg, double scale,
+                                                            double* __restrict__ Pxx) {
+    const int F = nperseg / 2 + 1;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int b = blockIdx.y;
+    double acc = 0.0;
+    for (int sgm = 0; sgm < n_seg; ++sgm) {
+        const cufftDoubleComplex v = Y[((size_t)b * n_seg + sgm) * F + f];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    const bool mirrored = f > 0 && ((nperseg & 1) || f < F - 1);
+    Pxx[(size_t)b * F + f] = acc / (double)n_seg * scale * (mirrored ? 2.0 : 1.0);
+}
+static int welch_nseg(int L, int nperseg) {
+    const int nov = nperseg / 2, step = nperseg - nov;
+    return (L - nov) / step;
+}
+extern "C" long gwf_welch_workspace_bytes(int B, int L, int nperseg) {
+    if (nperseg < 2 || nperseg > L) return 0;
+    const long ns = welch_nseg(L, nperseg);
+    return (long)B * ns * nperseg * 8 + (long)B * ns * (nperseg / 2 + 1) * 16;
+}
+extern "C" int gwf_welch_psd(const float* y, int B, int L, double fs, int nperseg, double* Pxx, void* work, void* stream) {
+    GW_REQUIRE(y && Pxx && work && B > 0 && nperseg >= 2 && nperseg <= L && fs > 0.0, "gwf_welch_psd: arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_seg = welch_nseg(L, nperseg), step = nperseg - nperseg / 2, F = nperseg / 2 + 1;
+    GW_REQUIRE(n_seg >= 1, "gwf_welch_psd: no complete segment");
+    double* tbuf = (double*)work;
+    cufftDoubleComplex* Y = (cufftDoubleComplex*)(tbuf + (size_t)B * n_seg * nperseg);
+    welch_segment_kernel<<<B * n_seg, 256, 0, st>>>(y, L, nperseg, step, n_seg, tbuf);
+    GW_LAUNCH_CHECK();
+    cufftHandle h;
+    int rc = get_plan(0, nperseg, B * n_seg, &h);
+    if (rc != GW_OK) return rc;
+    GW_CUFFT(cufftSetStream(h, st));
+    GW_CUFFT(cufftExecD2Z(h, tbuf, Y));
+    double w2 = 0.0;                                        // sum of the squared window (host: nperseg <= a few thousand terms)
+    for (int i = 0; i < nperseg; ++i) {
+        const double w = 0.5 - 0.5 * cos(2.0 * 3.14159265358979323846 * (double)i / (double)nperseg);
+        w2 += w * w;
+    }
+    welch_average_kernel<<<dim3(gw_cdiv(F, 256), B), 256, 0, st>>>(Y, n_seg, nperseg, 1.0 / (fs * w2), Pxx);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

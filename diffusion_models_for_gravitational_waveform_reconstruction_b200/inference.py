@@ -20,8 +20,8 @@ import torch
 from .engine import SamplerPlan, build_t_schedule, cfg_weight
 from .models import CustomDiffusion, UNet1D
 # CPU pre/post-processing of the reference CLI, on the GPU here; same names as inference.py:36-38, 125-205
-from .whitening import (_dewhiten_model, _dewhiten_train_like, _interp_psd_for_length, _mad_std, _pick_sigma,  # noqa: F401
-                        _whiten_pair_model, _whiten_pair_train_like)
+from .whitening import (_dewhiten_model, _dewhiten_train_like, _dewhiten_welch, _interp_psd_for_length, _mad_std,  # noqa: F401
+                        _pick_sigma, _whiten_pair_model, _whiten_pair_train_like, _whiten_pair_welch)
 
 __all__ = ["philox_normal", "snr_from_alpha_bar", "t_for_target_snr", "_build_t_schedule", "_cfg_weight", "_reduce_to_one_channel",
            "one_step_proxy_like_test_infer", "ddim_sample", "make_sampler_plan"]

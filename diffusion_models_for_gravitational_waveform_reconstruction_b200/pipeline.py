@@ -36,16 +36,17 @@ def reconstruct_batch(model, diffusion, y_raw: torch.Tensor, *, fs: float, clean
     B, L = y_raw.shape[0], y_raw.shape[-1]
     y_raw = y_raw.reshape(B, L).float()
     clean = clean_raw.to(dev).reshape(B, L).float() if clean_raw is not None else None
-    # ---- whitening (inference.py:655-700); 'auto' resolves model -> train, the Welch variant is not implemented
+    # ---- whitening (inference.py:655-700); 'auto' resolves model -> train (a saved Welch PSD is the data loader's business)
     P = None
     kind = "raw"
     if whiten:
         mode = whiten_mode
         if mode == "auto":
             mode = "model" if P_model is not None else "train"
-        if mode == "welch":
-            raise NotImplementedError("gwb200: the Welch whitening variant (scipy.signal.welch) is not implemented")
-        if mode == "model" and P_model is not None:
+        if mode == "welch":                                   # inference.py:676-679: Welch PSD estimated from y itself
+            y_c, c_c, P = whitening.whiten_welch(y_raw, clean, fs)
+            kind = "welch"
+        elif mode == "model" and P_model is not None:
             P = whitening.interp_psd_for_length(P_model, L, fs)
             y_c = whitening.apply_psd(y_raw, P, dewhiten=False, out_dtype=torch.float32)
             c_c = whitening.apply_psd(clean, P, dewhiten=False, out_dtype=torch.float32) if clean is not None else None

@@ -4,7 +4,7 @@ Batched fp64 equivalents of the reference's per-sample numpy helpers (inference.
 uses the same train-like recipe, dataloader.py:110-151), bound from libgwb200_fft.so (include/gwb200_fft.h).  The functions
 with the reference's names at the bottom take / return numpy arrays exactly like the reference (one sample), so
 `inference.main`-style code can call them unchanged; the batched functions keep everything on the device.
-The Welch variant (`_whiten_pair_welch`, scipy.signal.welch) is not implemented.
+`welch_psd` is scipy.signal.welch (defaults) on the device, `whiten_welch` the reference's Welch variant around it.
 """
 from __future__ import annotations
 
@@ -25,6 +25,10 @@ _SIGS = {
     "gwf_whiten_train_like": ([_P, _P, _I, _I, _P, _P, _P, _P, _P], _I),
     "gwf_apply_psd": ([_P, _I, _I, _P, _I, _I, _P, _P, _P, _P], _I),
     "gwf_interp_psd": ([_P, _I, _I, _D, _P, _P], _I),
+    "gwf_interp_psd_batch": ([_P, _I, _I, _I, _D, _P, _P], _I),
+    "gwf_interp_grid": ([_P, _P, _I, _I, _I, _D, _P, _P], _I),
+    "gwf_welch_workspace_bytes": ([_I, _I, _I], _L),
+    "gwf_welch_psd": ([_P, _I, _I, _D, _I, _P, _P, _P], _I),
     "gwf_sigma": ([_P, _I, _I, _I, _P, _P], _I),
 }
 
@@ -84,9 +88,9 @@ def whiten_train_like(y: torch.Tensor, x: Optional[torch.Tensor] = None):
     return y_w, x_w, P
 
 
-def apply_psd(sig: torch.Tensor, P: torch.Tensor, dewhiten: bool, out_dtype=torch.float64) -> torch.Tensor:
+def apply_psd(sig: torch.Tensor, P: torch.Tensor, dewhiten: bool, out_dtype=torch.float64, loader_floor: bool = False) -> torch.Tensor:
     """rfft(sig) * sqrt(P + 1e-12) (dewhiten; `_dewhiten_train_like` / `_dewhiten_model`) or / sqrt(P + 1e-12) (`_whiten_pair_model`),
-    then irfft.  P: [B, F] or one shared row [F]."""
+    then irfft.  P: [B, F] or one shared row [F].  `loader_floor`: whiten with the data loader's 1e-20 floor (dataloader.py:127-143)."""
     s = _prep(sig)
     B, L = s.shape
     P = P.to(s.device, torch.float64).contiguous()
@@ -94,7 +98,8 @@ def apply_psd(sig: torch.Tensor, P: torch.Tensor, dewhiten: bool, out_dtype=torc
     o32 = torch.empty_like(s) if out_dtype == torch.float32 else None
     o64 = torch.empty(B, L, device=s.device, dtype=torch.float64) if out_dtype == torch.float64 else None
     w = _work(B, L, s.device)
-    _check(load().gwf_apply_psd(_ptr(s), B, L, _ptr(P), shared, 2 if dewhiten else 1, _ptr(o32), _ptr(o64), _ptr(w), _stream()), "apply_psd")
+    mode = 2 if dewhiten else (3 if loader_floor else 1)
+    _check(load().gwf_apply_psd(_ptr(s), B, L, _ptr(P), shared, mode, _ptr(o32), _ptr(o64), _ptr(w), _stream()), "apply_psd")
     return o32 if o32 is not None else o64
 
 
@@ -104,6 +109,52 @@ def interp_psd_for_length(P_model: torch.Tensor, L_tgt: int, fs: float) -> torch
     out = torch.empty(L_tgt // 2 + 1, device=Ps.device, dtype=torch.float64)
     _check(load().gwf_interp_psd(_ptr(Ps), Ps.numel(), L_tgt, float(fs), _ptr(out), _stream()), "interp_psd")
     return out
+
+
+def interp_psd_batch(P_src: torch.Tensor, L_tgt: int, fs: float) -> torch.Tensor:
+    """Per-sample `_interp_psd_for_length`: P_src fp64 [B, n_src] -> [B, L_tgt//2+1]."""
+    Ps = P_src.to("cuda", torch.float64).contiguous()
+    B, n_src = Ps.shape
+    out = torch.empty(B, L_tgt // 2 + 1, device=Ps.device, dtype=torch.float64)
+    _check(load().gwf_interp_psd_batch(_ptr(Ps), B, n_src, L_tgt, float(fs), _ptr(out), _stream()), "interp_psd_batch")
+    return out
+
+
+def interp_grid(xp: torch.Tensor, fp: torch.Tensor, L_tgt: int, fs: float) -> torch.Tensor:
+    """np.interp(rfftfreq(L_tgt, 1/fs), xp, fp, left=fp[0], right=fp[-1]) per row (dataloader.py:136-139): [B, n] -> [B, L_tgt//2+1]."""
+    xs = xp.to("cuda", torch.float64).contiguous()
+    fs_ = fp.to("cuda", torch.float64).contiguous()
+    if xs.ndim == 1:
+        xs, fs_ = xs[None], fs_[None]
+    B, n = xs.shape
+    out = torch.empty(B, L_tgt // 2 + 1, device=xs.device, dtype=torch.float64)
+    _check(load().gwf_interp_grid(_ptr(xs), _ptr(fs_), B, n, L_tgt, float(fs), _ptr(out), _stream()), "interp_grid")
+    return out
+
+
+def welch_psd(y: torch.Tensor, fs: float, nperseg: int) -> torch.Tensor:
+    """scipy.signal.welch(y, fs=fs, nperseg=nperseg) with scipy's defaults, batched: y [B, L] CUDA -> Pxx fp64 [B, nperseg//2+1]
+    (frequencies: rfftfreq(nperseg, 1/fs))."""
+    yy = _prep(y)
+    B, L = yy.shape
+    nb = load().gwf_welch_workspace_bytes(B, L, int(nperseg))
+    if nb <= 0:
+        raise ValueError(f"welch_psd: nperseg={nperseg} for L={L}")
+    w = torch.empty(nb, device=yy.device, dtype=torch.uint8)
+    out = torch.empty(B, nperseg // 2 + 1, device=yy.device, dtype=torch.float64)
+    _check(load().gwf_welch_psd(_ptr(yy), B, L, float(fs), int(nperseg), _ptr(out), _ptr(w), _stream()), "welch_psd")
+    return out
+
+
+def whiten_welch(y: torch.Tensor, x: Optional[torch.Tensor], fs: float):
+    """Batched `_whiten_pair_welch` (inference.py:161-173): Welch PSD of y (nperseg = min(4096, L)), interpolated onto the rfft
+    grid, divide by sqrt(P + 1e-12), no mean removal.  -> (y_w fp32, x_w fp32 or None, P fp64 [B, L//2+1])."""
+    yy = _prep(y)
+    L = yy.shape[1]
+    P = interp_psd_batch(welch_psd(yy, fs, min(4096, L)), L, fs)
+    y_w = apply_psd(yy, P, False, torch.float32)
+    x_w = apply_psd(_prep(x), P, False, torch.float32) if x is not None else None
+    return y_w, x_w, P
 
 
 def sigma(y: torch.Tensor, mode: str = "std", fixed: float = 1.0) -> torch.Tensor:
@@ -145,6 +196,18 @@ def _whiten_pair_model(y: np.ndarray, x: Optional[np.ndarray], P_model: np.ndarr
 
 def _dewhiten_model(sig: np.ndarray, P: np.ndarray) -> np.ndarray:
     return _dewhiten_train_like(sig, P)
+
+
+def _whiten_pair_welch(y: np.ndarray, x: Optional[np.ndarray], fs: float):
+    """inference.py:161-173: -> (y_w, x_w, (freqs, P))."""
+    y_w, x_w, P = whiten_welch(_dev(y), _dev(x) if x is not None else None, fs)
+    freqs = np.fft.rfftfreq(len(y), 1 / fs)
+    return y_w[0].cpu().numpy(), (x_w[0].cpu().numpy() if x_w is not None else None), (freqs, P[0].cpu().numpy())
+
+
+def _dewhiten_welch(sig: np.ndarray, freqs_P, fs: float) -> np.ndarray:
+    """inference.py:175-179."""
+    return _dewhiten_train_like(sig, freqs_P[1])
 
 
 def _mad_std(x: np.ndarray) -> float:

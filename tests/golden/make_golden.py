@@ -355,10 +355,36 @@ def gen_whitening(I, out):
     np.savez_compressed(os.path.join(out, "whitening.npz"), **rec)
 
 
+def gen_whitening_welch(I, out):
+    """The Welch variant (inference.py:161-179: scipy.signal.welch inside `_whiten_pair_welch`, `_dewhiten_welch`) of the
+    unmodified reference on the inputs of gen_whitening, plus a multi-segment length; and scipy's welch itself on a batch."""
+    from scipy.signal import welch
+    rng = np.random.default_rng(22)
+    fs = 4096.0
+    rec = {}
+    for L in (2048, 1000, 10000):
+        n = rng.standard_normal(L + 64)
+        col = np.convolve(n, np.hanning(33) / np.hanning(33).sum(), mode="valid")[:L]
+        clean = synthetic_chirps(1, L, snr=8.0, seed=70 + L)["clean_norm"][0, 0].numpy().astype(np.float64) * 0.3
+        y = (col * 3.0 + clean + 0.7).astype(np.float32)
+        x = clean.astype(np.float32)
+        y_w, x_w, (freqs, P) = I._whiten_pair_welch(y, x, fs)
+        back = I._dewhiten_welch(y_w, (freqs, P), fs)
+        f, Pxx = welch(y, fs=fs, nperseg=min(4096, L))
+        rec.update({f"y_{L}": y, f"x_{L}": x, f"yw_{L}": y_w, f"xw_{L}": x_w, f"P_{L}": P, f"freqs_{L}": freqs, f"back_{L}": back,
+                    f"Pxx_{L}": Pxx.astype(np.float64), f"f_{L}": f})
+    np.savez_compressed(os.path.join(out, "whitening_welch.npz"), **rec)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
+    ap.add_argument("--only", default=None, help="run one generator only (e.g. whitening_welch)")
     args = ap.parse_args()
+    if args.only == "whitening_welch":
+        M, I, TR = import_reference()
+        gen_whitening_welch(I, args.out)
+        return
     torch.set_num_threads(8)
     M, I, TR = import_reference()
     gen_schedule(M, I, args.out)
@@ -368,6 +394,7 @@ def main():
     gen_proxy_and_helpers(M, I, TR, args.out)
     gen_scores(I, args.out)
     gen_whitening(I, args.out)
+    gen_whitening_welch(I, args.out)
     tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
     print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
 

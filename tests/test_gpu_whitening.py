@@ -92,3 +92,28 @@ def test_reconstruct_batch_pipeline_equals_its_stages_and_the_oracle():
     # raw (un-whitened) flavour and the bf16 engine
     r2 = pipeline.reconstruct_batch(m, diff, y_raw, fs=fs, whiten=False, steps=4, start_t=200, seed=5, compute_dtype="bf16")
     assert r2["whiten_kind"] == "raw" and r2["x0_hat_strain"].shape == (B, L) and torch.isfinite(r2["x0_hat_strain"]).all()
+
+
+@pytest.mark.parametrize("L", [2048, 1000, 10000])
+def test_welch_whitening_matches_reference_golden(golden_dir, L):
+    """The Welch variant (inference.py:161-179): scipy.signal.welch on the device (one segment at L <= 4096, four at L = 10000),
+    interpolation onto the rfft grid, whitening and de-whitening -- against outputs of the unmodified reference helper.  scipy
+    transforms the float32 input in single precision; cuFFT here runs in fp64: PSD rel-L2 <= 2e-6."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening as W
+    g = np.load(os.path.join(golden_dir, "whitening_welch.npz"))
+    y, x = g[f"y_{L}"], g[f"x_{L}"]
+    nper = min(4096, L)
+    Pxx = W.welch_psd(torch.from_numpy(np.stack([y, 2.0 * y])).cuda(), 4096.0, nper).cpu().numpy()
+    assert Pxx.shape == (2, nper // 2 + 1)
+    assert rel(Pxx[0], g[f"Pxx_{L}"]) <= 2e-6 and rel(Pxx[1], 4.0 * g[f"Pxx_{L}"]) <= 2e-6
+    y_w, x_w, (freqs, P) = W._whiten_pair_welch(y, x, 4096.0)
+    assert np.array_equal(freqs, g[f"freqs_{L}"])
+    assert rel(P, g[f"P_{L}"]) <= 2e-6
+    assert rel(y_w, g[f"yw_{L}"]) <= 5e-6 and rel(x_w, g[f"xw_{L}"]) <= 5e-6
+    assert rel(W._dewhiten_welch(g[f"yw_{L}"], (freqs, g[f"P_{L}"]), 4096.0), g[f"back_{L}"]) <= 1e-5
+    # np.interp on an arbitrary grid (a saved Welch PSD with its own frequency array, dataloader.py:136-139)
+    fw = np.sort(np.random.default_rng(1).uniform(0.0, 2100.0, size=97))
+    Pw = np.random.default_rng(2).uniform(0.5, 2.0, size=97)
+    got = W.interp_grid(torch.from_numpy(fw), torch.from_numpy(Pw), L, 4096.0)[0].cpu().numpy()
+    ref = np.interp(np.fft.rfftfreq(L, 1 / 4096.0), fw, Pw, left=Pw[0], right=Pw[-1])
+    assert rel(got, ref) <= 1e-13

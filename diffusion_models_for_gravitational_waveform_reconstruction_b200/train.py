@@ -772,14 +772,52 @@ class FusedTrainStep:
 # ======================================================================================================
 # train_diffusion (train.py:174-630): host loop around FusedTrainStep
 # ======================================================================================================
+def _compute_meta_scale(h5_file: str) -> dict:
+    """train.py:105-130: dataset-adaptive label scales (95th percentile of the masses / mass ratio)."""
+    import numpy as np
+    from .dataloader import open_h5
+    scale = {"M": 80.0, "q": 10.0}
+    try:
+        f = open_h5(h5_file)
+        try:
+            def p95(name):
+                if name in f:
+                    arr = np.array(f[name][...], dtype=np.float64)
+                    if arr.size:
+                        return float(np.nanpercentile(arr, 95))
+                return None
+            Ms = [x for x in (p95("mass1"), p95("mass2"), p95("chirp_mass")) if (x is not None and np.isfinite(x) and x > 0)]
+            if Ms:
+                scale["M"] = float(max(Ms))
+            q_p = p95("q")
+            if (q_p is not None) and np.isfinite(q_p) and q_p > 0:
+                scale["q"] = float(q_p)
+        finally:
+            f.close()
+    except Exception as e:
+        print(f"[train] meta_scale computation failed; using defaults {scale} ({e})")
+    return scale
+
+
 def train_diffusion(args, loader=None):
-    """Reference entry point.  `loader` yields (clean, noisy, sigma, mask[, meta]) batches as `dataloader.pad_collate`
-    does (dataloader.py:248-268); the HDF5 reader itself is outside this path, so a loader must be supplied."""
+    """Reference entry point `train_diffusion(args)` (train.py:174-630).  With `loader=None` the data loader is built from
+    `args.data` exactly as the reference does (train.py:178-198: meta scale, then `make_dataloader`), through
+    `dataloader.BatchLoader` (pinned double-buffered staging, whitening / sigma on the GPU).  `loader` may instead be any
+    iterable of (clean, noisy, sigma, mask[, meta]) batches shaped like `dataloader.pad_collate` output."""
     import random
-    from copy import deepcopy
     from .models import CustomDiffusion, UNet1D
+    meta_scale = None
     if loader is None:
-        raise RuntimeError("gwb200 train_diffusion: pass a batch iterable (the HDF5 dataloader is outside the hot path)")
+        from .dataloader import make_dataloader, resolve_h5_path
+        h5_path = resolve_h5_path(args.data)
+        meta_scale = _compute_meta_scale(h5_path)
+        loader = make_dataloader(h5_path=args.data, batch_size=args.batch_size, shuffle=True,
+                                 num_workers=getattr(args, "num_workers", 0), pin_memory=True,
+                                 whiten=getattr(args, "whiten", False), whiten_mode=getattr(args, "whiten_mode", "auto"),
+                                 sigma_mode=getattr(args, "sigma_mode", "std"), sigma_fixed=getattr(args, "sigma_fixed", 1.0),
+                                 include_metadata=True, mass_scale=float(meta_scale.get("M", 80.0)), device=args.device)
+        if len(loader.dataset) == 0:
+            raise RuntimeError("Empty dataset")
     if getattr(args, "seed", None) is not None:
         random.seed(args.seed)
         torch.manual_seed(args.seed)
@@ -859,7 +897,7 @@ def train_diffusion(args, loader=None):
                         "conditioning": "concat[y + meta]+selfcond" if C_meta > 0 else "concat[y]+selfcond",
                         "whiten": getattr(args, "whiten", False), "whiten_mode": getattr(args, "whiten_mode", "auto"),
                         "sigma_mode": getattr(args, "sigma_mode", "std"), "dropout_y_only": bool(args.dropout_y_only),
-                        "meta_scale": getattr(args, "meta_scale", {"M": 80.0, "q": 10.0})},
+                        "meta_scale": meta_scale if meta_scale is not None else getattr(args, "meta_scale", {"M": 80.0, "q": 10.0})},
                "epoch": args.epochs}
     if getattr(args, "ema", False) and stepper is not None:
         payload["model_ema_state"] = stepper.state_dict_ema()

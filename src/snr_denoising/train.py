@@ -8,5 +8,5 @@ if _ROOT not in _sys.path:
 
 from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import (  # noqa: E402,F401
     FusedTrainStep, _element_loss, _match_batch, _predict_x0_norm, _sample_timesteps_stratified,
-    make_warmup_cosine_scheduler, train_diffusion, update_ema, warmup_cosine_lambda)
+    _compute_meta_scale, make_warmup_cosine_scheduler, train_diffusion, update_ema, warmup_cosine_lambda)
 from diffusion_models_for_gravitational_waveform_reconstruction_b200.models import CustomDiffusion, UNet1D  # noqa: E402,F401

@@ -376,14 +376,62 @@ def gen_whitening_welch(I, out):
     np.savez_compressed(os.path.join(out, "whitening_welch.npz"), **rec)
 
 
+def gen_ingest(out):
+    """The unmodified reference ingest path (dataloader.NoisyWaveDataset + pad_collate, dataloader.py:26-268) on a small HDF5
+    file with gen.py's layout (variable-length float32 rows of ragged lengths, per-sample masses / spins, model PSD rows, root
+    attributes).  This image has no h5py: the fixture is written by the package's `_hdf5.write_file`, and the reference reads
+    it through the package's minimal reader registered as `h5py` (only `h5py.File(path, 'r')` indexing is used by the
+    reference); everything after the read -- NaN scrub, whitening, sigma, metadata broadcast, left-pad collate -- is the
+    reference's own code."""
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import _hdf5
+    rng = np.random.default_rng(33)
+    lens = [1024, 768, 1024, 512, 1000, 768]
+    sig, noisy = [], []
+    for i, L in enumerate(lens):
+        c = synthetic_chirps(1, L, snr=9.0, seed=300 + i)["clean_norm"][0, 0].numpy().astype(np.float64) * 2e-21
+        n = np.convolve(rng.standard_normal(L + 32), np.hanning(33) / np.hanning(33).sum(), mode="valid")[:L] * 1e-21
+        sig.append(c.astype(np.float32))
+        noisy.append((c + n).astype(np.float32))
+    noisy[3][5] = np.nan                                          # exercised by the NaN scrub (dataloader.py:160-164)
+    psd_model = [1e-42 * (1.0 + np.abs(np.sin(np.linspace(0, 3, 513))) ** 2 + np.linspace(0, 1, 513) * (1 + 0.1 * i)) for i in range(6)]
+    fixture = os.path.join(out, "ingest_fixture.h5")
+    _hdf5.write_file(fixture, {"signal": sig, "noisy": noisy, "noise": [b - a for a, b in zip(sig, noisy)],
+                               "lengths": np.array(lens, dtype=np.int64), "mass1": rng.uniform(20, 70, 6), "mass2": rng.uniform(10, 40, 6),
+                               "spin1z": rng.uniform(-0.5, 0.5, 6), "spin2z": rng.uniform(-0.5, 0.5, 6),
+                               "psd_model": np.stack(psd_model)},
+                     {"sampling_rate": 4096.0, "delta_t": 1.0 / 4096.0, "time_axis": "seconds-rel-peak", "padding": "none"})
+    h5stub = types.ModuleType("h5py")
+    h5stub.File = _hdf5.File
+    sys.modules["h5py"] = h5stub
+    sys.path.insert(0, REF)
+    import importlib
+    D = importlib.import_module("dataloader")
+    rec = {}
+    for tag, kw in {"raw_std": dict(whiten=False, sigma_mode="std"), "train_std": dict(whiten=True, whiten_mode="train", sigma_mode="std"),
+                    "model_mad": dict(whiten=True, whiten_mode="auto", sigma_mode="mad")}.items():
+        ds = D.NoisyWaveDataset(fixture, include_metadata=True, mass_scale=65.0, **kw)
+        batch = D.pad_collate([ds[i] for i in range(6)])
+        for name, t in zip(("clean", "noisy", "sigma", "mask", "meta"), batch):
+            rec[f"{tag}/{name}"] = t.numpy()
+        one = ds[3]
+        rec[f"{tag}/item3_noisy"] = one[1].numpy()
+        ds.close()
+    np.savez_compressed(os.path.join(out, "ingest.npz"), **rec)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
-    ap.add_argument("--only", default=None, help="run one generator only (e.g. whitening_welch)")
+    ap.add_argument("--only", default=None, help="run one generator only (whitening_welch | ingest)")
     args = ap.parse_args()
     if args.only == "whitening_welch":
         M, I, TR = import_reference()
         gen_whitening_welch(I, args.out)
+        return
+    if args.only == "ingest":
+        gen_ingest(args.out)
         return
     torch.set_num_threads(8)
     M, I, TR = import_reference()
@@ -395,6 +443,7 @@ def main():
     gen_scores(I, args.out)
     gen_whitening(I, args.out)
     gen_whitening_welch(I, args.out)
+    gen_ingest(args.out)
     tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
     print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
 

@@ -98,7 +98,7 @@ def test_reconstruct_batch_pipeline_equals_its_stages_and_the_oracle():
 def test_welch_whitening_matches_reference_golden(golden_dir, L):
     """The Welch variant (inference.py:161-179): scipy.signal.welch on the device (one segment at L <= 4096, four at L = 10000),
     interpolation onto the rfft grid, whitening and de-whitening -- against outputs of the unmodified reference helper.  scipy
-    transforms the float32 input in single precision; cuFFT here runs in fp64: PSD rel-L2 <= 2e-6."""
+    transforms the float32 input in single precision; cuFFT here runs in fp64: PSD rel-L2 <= 2e-6, whitened signals <= 1e-4."""
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening as W
     g = np.load(os.path.join(golden_dir, "whitening_welch.npz"))
     y, x = g[f"y_{L}"], g[f"x_{L}"]
@@ -109,7 +109,8 @@ def test_welch_whitening_matches_reference_golden(golden_dir, L):
     y_w, x_w, (freqs, P) = W._whiten_pair_welch(y, x, 4096.0)
     assert np.array_equal(freqs, g[f"freqs_{L}"])
     assert rel(P, g[f"P_{L}"]) <= 2e-6
-    assert rel(y_w, g[f"yw_{L}"]) <= 5e-6 and rel(x_w, g[f"xw_{L}"]) <= 5e-6
+    # the reference's rfft(y) runs in single precision here (float32 input, numpy >= 2; no float64 cast at inference.py:168-171)
+    assert rel(y_w, g[f"yw_{L}"]) <= 1e-4 and rel(x_w, g[f"xw_{L}"]) <= 1e-4
     assert rel(W._dewhiten_welch(g[f"yw_{L}"], (freqs, g[f"P_{L}"]), 4096.0), g[f"back_{L}"]) <= 1e-5
     # np.interp on an arbitrary grid (a saved Welch PSD with its own frequency array, dataloader.py:136-139)
     fw = np.sort(np.random.default_rng(1).uniform(0.0, 2100.0, size=97))

@@ -80,7 +80,7 @@ def reconstruct_batch(model, diffusion, y_raw: torch.Tensor, *, fs: float, clean
                       cfg_width, cfg_u_only_thresh, drop_y_only=drop_y_only, seed=seed, sample0=sample0, noise=noise,
                       compute_dtype=compute_dtype)
     x0_white = (x0n * sig32).view(B, L)                                     # inference.py:815
-    if kind in ("train", "model"):                                          # inference.py:818-826
+    if kind in ("train", "model", "welch"):                                 # inference.py:818-826
         x0_strain = whitening.apply_psd(x0_white, P, dewhiten=True)
     else:
         x0_strain = x0_white.double()

@@ -607,6 +607,75 @@ def bench_train(args, world, rank, dev, barrier, pk):
     return line
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm: whitening / scoring
+def bench_aux(args, dev, pk):
+    """`--workload whiten`: batched train-like whitening of (y, clean) + sigma (inference.py:125-153 / dataloader.py:110-200);
+    `--workload score`: the batched scoring kernel (inference.py:11-27, 247-314).  HBM-bound by intent: algorithmic bytes =
+    every input read once + every output written once."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import scoring, whitening
+    B, L = args.batch, args.length
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    y = torch.randn(B, L, device=dev, generator=g) * 3e-3 + 1e-3
+    x = torch.randn(B, L, device=dev, generator=g) * 1e-3
+    y_host, x_host = y.cpu().pin_memory(), x.cpu().pin_memory()
+    if args.workload == "whiten":
+        def step_resident():
+            y_w, x_w, P = whitening.whiten_train_like(y, x)
+            return whitening.sigma(y_w, "std")
+        alg_bytes = B * (2 * L * 4 + 2 * L * 4 + (L // 2 + 1) * 8 + L * 4 + 8)      # y, x in; y_w, x_w, P out; sigma pass
+        def step_e2e():
+            yd, xd = y_host.to(dev, non_blocking=True), x_host.to(dev, non_blocking=True)
+            y_w, x_w, P = whitening.whiten_train_like(yd, xd)
+            return whitening.sigma(y_w, "std").cpu()
+        metric, unit, kernel = "whitened segments/sec", "segments/s", "cuFFT D2Z/Z2D (fp64) + periodogram / spectral-scale / finish / sigma kernels"
+        h2d, d2h = 2 * B * L * 4, B * 8
+    else:
+        sig = torch.full((B,), 1e-3, device=dev)
+        def step_resident():
+            return scoring.score_batch(y, x, 4096.0, sigma=sig, secs=0.8, max_shift=82)["corr_last"]
+        alg_bytes = B * (2 * L * 4 + 12 * 8)
+        def step_e2e():
+            yd, xd = y_host.to(dev, non_blocking=True), x_host.to(dev, non_blocking=True)
+            return scoring.score_batch(yd, xd, 4096.0, sigma=sig, secs=0.8, max_shift=82)["corr_last"].cpu()
+        metric, unit, kernel = "scored reconstructions/sec", "reconstructions/s", "score_batch_kernel (one CTA per sample, fp64 accumulation, +-82 lag search)"
+        h2d, d2h = 2 * B * L * 4, B * 8
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(dev.index)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1)
+    per = ms / args.steps
+    ach = alg_bytes / (per * 1e-3) / 1e9
+    return {"metric": metric, "value": B * args.steps / (ms / 1e3), "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.workload == "whiten" else "f32/f64",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: batch {B} x {L}", "l2": "inputs + workspace >> 126 MB L2" if B * L * 40 > 126e6 else "fits L2 partly"},
+            "e2e": {"value": B * args.steps / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": None, "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                         "traffic": None, "algorithmic_bytes_per_step": alg_bytes, "peak_source": pk["src"],
+                         "note": "whole step (several kernels + cuFFT) against the bytes that must move once; the fp64 FFT workspace "
+                                 "passes are not algorithmic bytes" if args.workload == "whiten" else "one kernel"}}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import _cabi
@@ -625,7 +694,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.workload == "train":
+    if args.workload in ("whiten", "score"):
+        if rank == 0:
+            emit(bench_aux(args, dev, pk))
+    elif args.workload == "train":
         line = bench_train(args, world, rank, dev, barrier, pk)
         samp = None
         if not args.no_sampling:
@@ -676,7 +748,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train"] + list(WORKLOADS))
+    ap.add_argument("--workload", default="train", choices=["train"] + list(WORKLOADS) + ["whiten", "score"])
     ap.add_argument("--batch", type=int, default=256, help="samples / waveforms per GPU")
     ap.add_argument("--length", type=int, default=4096)
     ap.add_argument("--cin", type=int, default=3, choices=[3, 7], help="input channels of the sampling workloads")

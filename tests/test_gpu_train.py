@@ -313,9 +313,13 @@ def test_non_default_architectures(base_ch, depth, time_dim, cd, tol):
     st.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
     st.step(t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=False)
     torch.cuda.synchronize()
-    assert rel_l2(st.eps_hat, eps_o) <= (1e-5 if cd == "fp32" else 1.5e-2)
+    e_eps = rel_l2(st.eps_hat, eps_o)
     grads = st.layout.views(st.flat_g)
     tot = float(torch.cat([g.reshape(-1) for g in grads_o.values()]).norm())
+    worst = max(float((grads[k].cpu().double() - go.double()).norm()) / max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot)
+                for k, go in grads_o.items())
+    print(f"non-default arch base_ch={base_ch} depth={depth} {cd}: eps_hat rel-L2 {e_eps:.3e}, worst gradient tensor {worst:.3e}")
+    assert e_eps <= (1e-5 if cd == "fp32" else 1.5e-2)
     for k, go in grads_o.items():
         err = float((grads[k].cpu().double() - go.double()).norm())
         assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))

@@ -295,7 +295,7 @@ def test_backward_odd_lengths(L, cd, tol):
         assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))
 
 
-@pytest.mark.parametrize("base_ch,depth,time_dim,cd,tol", [(128, 2, 64, "fp32", 5e-5), (128, 3, 128, "bf16", 6e-2), (64, 4, 128, "fp32", 5e-5)])
+@pytest.mark.parametrize("base_ch,depth,time_dim,cd,tol", [(128, 2, 64, "fp32", 5e-5), (128, 3, 128, "bf16", 5e-2), (64, 4, 128, "fp32", 5e-5)])
 def test_non_default_architectures(base_ch, depth, time_dim, cd, tol):
     """UNet1D(base_ch, depth, time_dim) other than the CLI defaults (models.py:78-88): forward and one training step."""
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
@@ -319,7 +319,7 @@ def test_non_default_architectures(base_ch, depth, time_dim, cd, tol):
     worst = max(float((grads[k].cpu().double() - go.double()).norm()) / max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot)
                 for k, go in grads_o.items())
     print(f"non-default arch base_ch={base_ch} depth={depth} {cd}: eps_hat rel-L2 {e_eps:.3e}, worst gradient tensor {worst:.3e}")
-    assert e_eps <= (1e-5 if cd == "fp32" else 1.5e-2)
+    assert e_eps <= (1e-5 if cd == "fp32" else 1e-2)
     for k, go in grads_o.items():
         err = float((grads[k].cpu().double() - go.double()).norm())
         assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))

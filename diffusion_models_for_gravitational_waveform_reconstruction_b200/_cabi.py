@@ -71,6 +71,17 @@ _SIGS.update({
                     _P, _P, _P, _P], _I),
     "gw_gn_bwd_sync_bytes": ([_I], _L),
     "gw_gn_bwd_fused_group": ([_I, _I, _I, _I, _I], _I),
+    "gw_gen_conv": ([_P, _I, _I, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P], _I),
+    "gw_gen_weight_dgrad": ([_P, _I, _I, _I, _P, _P], _I),
+    "gw_gen_gn_stats": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "gw_gen_gn_apply": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _I, _P], _I),
+    "gw_gen_final": ([_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P, C.POINTER(StepParams), _P, _P, _P, _P, _P, _P], _I),
+    "gw_gen_final_bwd": ([_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P], _I),
+    "gw_gen_gn_bwd_scratch_floats": ([_I, _I], _L),
+    "gw_gen_gn_bwd": ([_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P, _P,
+                       _P, _P], _I),
+    "gw_gen_wgrad": ([_P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "gw_gen_split_cat": ([_P, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     "gw_weight_dgrad": ([_P, _I, _I, _P, _P], _I),
     "gw_split_cat_grad": ([_P, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     "gw_wgrad3_simt": ([_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _L, _P, _P], _I),

@@ -10,7 +10,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libgwb200.so")
 LIB_FFT = os.path.join(PKG, "libgwb200_fft.so")
 SOURCES = ["forward.cu", "conv_tc.cu", "backward.cu", "optim.cu", "wgrad_tc.cu", "stream_gn.cu", "score.cu", "conv_in_gn.cu",
-           "gn_bwd_fused.cu", "conv_in_direct.cu"]
+           "gn_bwd_fused.cu", "conv_in_direct.cu", "generic.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

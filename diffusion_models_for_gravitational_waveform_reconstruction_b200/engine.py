@@ -170,10 +170,20 @@ class UNetEngine:
             raise ValueError("the tcgen05 conv path stores bf16 activations; use dtype='bf16'")
         self.conv_impl = conv_impl
         self.tc_variant = tc_variant
-        if spec.base_ch % 64 != 0:
-            raise NotImplementedError("gwb200 kernels need base_ch % 64 == 0 (reference default is 64)")
-        if spec.kernel != 3:
-            raise NotImplementedError("gwb200 kernels implement the reference default kernel=3")
+        # Non-default architectures (train.py:609-612 exposes --base-ch and --kernel): every layer runs the shape-generic
+        # CUDA-core kernels of csrc/generic.cu (fp32 math, fp32 or bf16 storage) instead of the tcgen05 / streaming kernels,
+        # which are laid out for 64-channel rows and three taps.
+        self.generic = spec.base_ch % 64 != 0 or spec.kernel != 3
+        if self.generic:
+            b = spec.base_ch
+            if b < 4 or (b & (b - 1)) != 0 or b > 1024:
+                raise ValueError(f"base_ch={b}: the time-MLP kernels need a power of two in [4, 1024] (or a multiple of 64 with "
+                                 "kernel=3)")
+            if spec.kernel not in (1, 3, 5, 7):
+                raise ValueError(f"kernel={spec.kernel}: odd kernel sizes up to 7 ('same' padding needs an odd size)")
+            if spec.cond_in_ch > 8:
+                raise ValueError("cond_in_ch > 8")
+            self.conv_impl = "simt"
         self.p = params
         dev = params["final.weight"].device
         if dev.type != "cuda":
@@ -291,6 +301,9 @@ class UNetEngine:
                 nb = self.lib.gw_conv_gn_sync_bytes(B)
                 ws.sync = torch.zeros(nb, device=self.device, dtype=torch.uint8)
                 ws.syncs = [torch.zeros(nb, device=self.device, dtype=torch.uint8) for _ in range(2 * self.spec.depth + 1)]
+            if self.generic and ws.stats is None:
+                ws.stats = [torch.empty(B, 8, 2, device=self.device, dtype=torch.float32)
+                            for _ in range(2 * self.spec.depth + 1)]
             self._ws[key] = ws
         return ws
 
@@ -428,6 +441,8 @@ class UNetEngine:
         """conv_in .. decoders[-1] FiLM; returns the last activation [B, L, base_ch].  The cond pyramid must be current.
         `chain_serial` (device int32, bumped once per chain by the sampler) enables layer chaining (gw_conv_gn3)."""
         sp = self.spec
+        if self.generic:
+            return self._body_generic(ws, net_a, net_b, step_ptr, film, film_b_stride, film_step_stride)
         self._chain_serial = chain_serial
         ws.chain_prev = None                        # the first block is not a chained producer
         d = sp.depth
@@ -491,10 +506,62 @@ class UNetEngine:
                 h = ws.dots                                   # consumed by head() (gw_final_step with dtype = GW_DOTS)
         return h
 
+    # ------------------------------------------------------------------ shape-generic path (csrc/generic.cu)
+    def _block_generic(self, li: int, ws: _Workspace, src0: Optional[Tensor], src1: Optional[Tensor], net_a: Optional[Tensor],
+                       net_b: Optional[Tensor], step_ptr: Optional[Tensor], film: Tensor, film_b_stride: int,
+                       film_step_stride: int, pooled: Optional[Tensor], lvl: int) -> None:
+        """Conv1d(K) + GroupNorm(gcd(8, C)) + SiLU + cond bias + FiLM (+ avg-pool) of layer li (models.py:160-173, 203-208)."""
+        sp, lib = self.spec, self.lib
+        name, cname = sp.layer_names()[li], sp.cond_names()[li]
+        raw, out = ws.raw[li], ws.out[li]
+        B, L, Cout = raw.shape
+        st = _cabi.stream_ptr()
+        Cc = sp.cond_in_ch
+        if src0 is None:
+            Cx = net_a.shape[1]
+            check(lib.gw_gen_conv(None, 0, 0, 0, None, 0, ptr(net_a), ptr(net_b), ptr(step_ptr), Cx, B, L,
+                                  ptr(self.p[name + ".0.weight"]), ptr(self.p[name + ".0.bias"]), Cout, sp.kernel, ptr(raw),
+                                  self.gw_dtype, st), f"gen_conv[{name}]")
+        else:
+            C1 = src1.shape[2] if src1 is not None else 0
+            check(lib.gw_gen_conv(ptr(src0), src0.shape[2], src0.shape[1], 1 if src1 is not None else 0, ptr(src1), C1, None, None,
+                                  None, 0, B, L, ptr(self.p[name + ".0.weight"]), ptr(self.p[name + ".0.bias"]), Cout, sp.kernel,
+                                  ptr(raw), self.gw_dtype, st), f"gen_conv[{name}]")
+        groups = math.gcd(8, Cout)
+        check(lib.gw_gen_gn_stats(ptr(raw), B, L, Cout, groups, self.gw_dtype, ptr(ws.stats[li]), st), f"gen_gn_stats[{name}]")
+        check(lib.gw_gen_gn_apply(ptr(raw), ptr(ws.stats[li]), B, L, Cout, groups, ptr(self.p[name + ".1.weight"]),
+                                  ptr(self.p[name + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                  ptr(self.p[cname + ".weight"]) if Cc > 0 else None,
+                                  ptr(self.p[cname + ".bias"]) if Cc > 0 else None, ptr(film), sp.film_offsets()[li],
+                                  film_b_stride, film_step_stride, ptr(step_ptr), ptr(out), ptr(pooled), self.gw_dtype, st),
+              f"gen_gn_apply[{name}]")
+        self.launches += 3
+
+    def _body_generic(self, ws: _Workspace, net_a: Tensor, net_b: Optional[Tensor], step_ptr: Optional[Tensor], film: Tensor,
+                      film_b_stride: int, film_step_stride: int) -> Tensor:
+        d = self.spec.depth
+        ws.head_fused = False
+        self._block_generic(0, ws, None, None, net_a, net_b, step_ptr, film, film_b_stride, film_step_stride, ws.pooled[0], 0)
+        for i in range(1, d):
+            self._block_generic(i, ws, ws.pooled[i - 1], None, None, None, step_ptr, film, film_b_stride, film_step_stride,
+                                ws.pooled[i], i)
+        self._block_generic(d, ws, ws.pooled[d - 1], None, None, None, step_ptr, film, film_b_stride, film_step_stride, None, d)
+        for i in range(d):
+            li = d + 1 + i
+            self._block_generic(li, ws, ws.out[li - 1], ws.out[d - 1 - i], None, None, step_ptr, film, film_b_stride,
+                                film_step_stride, None, d - 1 - i)
+        return ws.out[2 * d]
+
     def head(self, h: Tensor, net_a: Tensor, net_b: Optional[Tensor], params: StepParams, coef: Optional[Tensor],
              step_ptr: Optional[Tensor], noise: Optional[Tensor], eps_out: Optional[Tensor], x0_out: Optional[Tensor],
              B: int) -> None:
         _, Cx, L = net_a.shape
+        if self.generic:
+            check(self.lib.gw_gen_final(ptr(h), self.gw_dtype, ptr(net_a), ptr(net_b), B, Cx, L, self.spec.base_ch, self.spec.kernel,
+                                        ptr(self.wf), ptr(self.p["final.bias"]), C.byref(params), ptr(coef), ptr(step_ptr),
+                                        ptr(noise), ptr(eps_out), ptr(x0_out), _cabi.stream_ptr()), "gen_final")
+            self.launches += 1
+            return
         dots = h.dtype == torch.float32 and h.dim() == 3 and h.shape[-1] == 4 and self.dtype == "bf16"
         check(self.lib.gw_final_step(ptr(h), 2 if dots else self.gw_dtype, ptr(net_a), ptr(net_b), B, Cx, L, self.spec.base_ch,
                                      ptr(self.wf), ptr(self.p["final.bias"]), C.byref(params), ptr(coef), ptr(step_ptr),

@@ -60,6 +60,7 @@ class _GradWorkspace:
                 if mode == 1 and ws.lay_len[i] % 2:
                     continue
                 self.wg_elems = max(self.wg_elems, lib.gw_wgrad_tc_scratch_elems(mode, B, ws.lay_len[i], lc[i], cx))
+        n_scr = max(n_scr, lib.gw_gen_gn_bwd_scratch_floats(B, max(lc)))   # generic path: per-(sample, channel) sums
         self.scratch = torch.empty(max(n_scr, self.wg_elems), device=device, dtype=torch.float32)
         self.dfilm = torch.zeros(B, spec.film_dim, device=device, dtype=torch.float32)
         self.aux = torch.empty(B, spec.time_dim + 3 * spec.base_ch, device=device, dtype=torch.float32)
@@ -156,6 +157,10 @@ class BackwardEngine:
         if wt is None:
             wt = torch.empty(w.numel(), device=eng.device, dtype=torch.float32)
             self._wt[li] = wt
+        if eng.generic:
+            check(lib.gw_gen_weight_dgrad(ptr(w), Cout, Cin, eng.spec.kernel, ptr(wt), st), "gen_weight_dgrad")
+            eng.launches += 1
+            return
         check(lib.gw_weight_dgrad(ptr(w), Cout, Cin, ptr(wt), st), "weight_dgrad")
         eng.launches += 1
         if self.dgrad_impl == "tc" and self._dgrad_tc_ok(li, ws):
@@ -194,6 +199,20 @@ class BackwardEngine:
         C1 = src1.shape[2] if src1 is not None else 0
         tc_ok = eng.dtype == "bf16" and (src1 is None or (L % 2 == 0 and L0 * 2 == L)) and Cout <= 256 and C0 <= 256 and C1 <= 256
         dW = grads[name + ".0.weight"]
+        if eng.generic:
+            K = sp.kernel
+            check(lib.gw_gen_wgrad(ptr(src0), C0, L0, up, ptr(src1), C1, None, 0, ptr(g.d_raw), B, L, Cout, K, eng.gw_dtype,
+                                   ptr(dW), st), f"gen_wgrad[{name}]")
+            if not self._prepped:
+                self._prep_dgrad_layer(li, ws)
+            dst = d_in0 if src1 is None else g.d_cat
+            check(lib.gw_gen_conv(ptr(g.d_raw), Cout, L, 0, None, 0, None, None, None, 0, B, L, ptr(self._wt[li]), None, C0 + C1, K,
+                                  ptr(dst), eng.gw_dtype, st), f"gen_dgrad[{name}]")
+            eng.launches += 2
+            if src1 is not None:
+                check(lib.gw_gen_split_cat(ptr(g.d_cat), B, L, C0, L0, C1, ptr(d_in0), ptr(d_in1), eng.gw_dtype, st), "gen_split_cat")
+                eng.launches += 1
+            return
         if self.wgrad_impl == "tc" and tc_ok:
             if src1 is None:
                 check(lib.gw_wgrad_tc(0, ptr(g.d_raw), ptr(src0), B, L, Cout, C0, C0, 0, ptr(g.scratch), g.scratch.numel(), ptr(dW),
@@ -248,6 +267,18 @@ class BackwardEngine:
             n = names[li]
             lvl = li if li <= d else 2 * d - li
             _, Ll, Cl = ws.raw[li].shape
+            if eng.generic:
+                check(lib.gw_gen_gn_bwd(ptr(ws.raw[li]), ptr(ws.stats[li]), B, Ll, Cl, math.gcd(8, Cl), ptr(eng.p[n + ".1.weight"]),
+                                        ptr(eng.p[n + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                        ptr(eng.p[cnames[li] + ".weight"]) if Cc > 0 else None,
+                                        ptr(eng.p[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(g.film), foffs[li], sp.film_dim,
+                                        ptr(do_a), ptr(do_pool), eng.gw_dtype, ptr(g.scratch), ptr(g.dfilm), sp.film_dim,
+                                        ptr(g.d_raw), ptr(grads[n + ".1.weight"]), ptr(grads[n + ".1.bias"]),
+                                        ptr(grads[cnames[li] + ".weight"]) if Cc > 0 else None,
+                                        ptr(grads[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(grads[n + ".0.bias"]), st),
+                      f"gen_gn_bwd[{n}]")
+                eng.launches += 3
+                return
             check(lib.gw_gn_bwd2(ptr(ws.raw[li]), ptr(ws.stats[li]), B, Ll, Cl, ptr(eng.p[n + ".1.weight"]),
                                 ptr(eng.p[n + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
                                 ptr(eng.p[cnames[li] + ".weight"]) if Cc > 0 else None,
@@ -267,11 +298,17 @@ class BackwardEngine:
         # Measured at B=256, L=4096: gw_final_bwd 130 -> 75 us, but the last block's two GroupNorm-backward passes 162 -> 226 us
         # (they are issue-bound: 12 extra instructions per (row, 4 channels) cost more than the 268 MB of reads they save), so
         # the step time is unchanged (3.68 vs 3.69 ms) and the option stays off.
-        fuse_head = self.fuse_head and eng.dtype == "bf16"
-        check(lib.gw_final_bwd(ptr(d_eps), ptr(ws.out[nl - 1]), eng.gw_dtype, ptr(net), B, Cx, L, lc[-1], ptr(eng.wf),
-                               None if fuse_head else ptr(g.d_h[0]), ptr(g.scratch), ptr(grads["final.weight"]),
-                               ptr(grads["final.bias"]), st), "final_bwd")
-        eng.launches += 3
+        fuse_head = self.fuse_head and eng.dtype == "bf16" and not eng.generic
+        if eng.generic:
+            check(lib.gw_gen_final_bwd(ptr(d_eps), ptr(ws.out[nl - 1]), eng.gw_dtype, ptr(net), B, Cx, L, lc[-1], sp.kernel,
+                                       ptr(eng.wf), ptr(g.d_h[0]), ptr(grads["final.weight"]), ptr(grads["final.bias"]), st),
+                  "gen_final_bwd")
+            eng.launches += 2
+        else:
+            check(lib.gw_final_bwd(ptr(d_eps), ptr(ws.out[nl - 1]), eng.gw_dtype, ptr(net), B, Cx, L, lc[-1], ptr(eng.wf),
+                                   None if fuse_head else ptr(g.d_h[0]), ptr(g.scratch), ptr(grads["final.weight"]),
+                                   ptr(grads["final.bias"]), st), "final_bwd")
+            eng.launches += 3
         cur = 0
         for li in range(nl - 1, d, -1):                       # decoders, last first
             if li == nl - 1 and fuse_head:
@@ -288,9 +325,14 @@ class BackwardEngine:
             self._conv_bwd(li, ws, g, grads, g.d_pool[pc ^ 1], None)
             pc ^= 1
         gn_bwd(0, g.d_skip[0], g.d_pool[pc])
-        check(lib.gw_wgrad_in(ptr(net), B, Cx, L, ptr(g.d_raw), lc[0], eng.gw_dtype, ptr(g.scratch), g.scratch.numel(),
-                              ptr(grads["encoders.0.0.weight"]), st), "wgrad_in")
-        eng.launches += 2
+        if eng.generic:
+            check(lib.gw_gen_wgrad(None, 0, 0, 0, None, 0, ptr(net), Cx, ptr(g.d_raw), B, L, lc[0], sp.kernel, eng.gw_dtype,
+                                   ptr(grads["encoders.0.0.weight"]), st), "gen_wgrad[encoders.0]")
+            eng.launches += 1
+        else:
+            check(lib.gw_wgrad_in(ptr(net), B, Cx, L, ptr(g.d_raw), lc[0], eng.gw_dtype, ptr(g.scratch), g.scratch.numel(),
+                                  ptr(grads["encoders.0.0.weight"]), st), "wgrad_in")
+            eng.launches += 2
         lo = self.layout
         check(lib.gw_film_bwd(ptr(g.dfilm), ptr(g.aux), ptr(eng.film_w2), B, sp.time_dim, sp.base_ch, sp.film_dim, ptr(g.scratch),
                               ptr(grads["time_mlp.1.weight"]), ptr(grads["time_mlp.1.bias"]),

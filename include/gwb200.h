@@ -349,6 +349,44 @@ int gw_loss_weight(const int64_t* t, const float* alpha_bar, float power, float*
 int gw_score_batch(const float* xhat, const float* clean, const float* sigma, int B, int L, double fs, double secs,
                    int max_shift, double delta_t, double* out, void* stream);
 
+/* =====================================================================================================
+ * Shape-generic CUDA-core path (csrc/generic.cu) for the UNet1D configurations the specialised kernels do not cover:
+ * base_ch not a multiple of 64 and / or kernel in {1, 3, 5, 7} (models.py:78-88 takes both from the CLI, train.py:609-612).
+ * Any channel count; GroupNorm with `groups` = gcd(8, C) groups (models.py:160-164); stats fp32 [B, 8, 2] = (mean, rstd).
+ * Same operand conventions as the specialised entry points: activations channels-last [B, L, C] in `dtype`, weights in the
+ * reference layout [Cout, Cin, K], the network input fp32 [B, Cx, L] (ping-pong pair selected by *step_ptr & 1).
+ *   gw_gen_conv        replaces nn.Conv1d(Cin, Cout, K, padding=K/2) of _conv_block (models.py:166-173) on
+ *                      cat[nearest-upsample x2 (src0), src1] (models.py:217-222; zero rows beyond 2 L0), or on x when src0 == NULL
+ *   gw_gen_gn_stats    GroupNorm statistics of the stored conv output (biased variance, eps 1e-5)
+ *   gw_gen_gn_apply    GroupNorm affine + SiLU + cond 1x1 conv + FiLM (+ avg_pool1d(2, 2)) (models.py:188-193, 205-208)
+ *   gw_gen_final       final Conv1d(C + 1, 1, K) on cat[h, x_t] (models.py:227-230) (+ the gw_final_step update when mode = 1)
+ *   gw_gen_final_bwd, gw_gen_gn_bwd, gw_gen_wgrad, gw_gen_weight_dgrad, gw_gen_split_cat: their backward passes; parameter
+ *                      gradients are ACCUMULATED (+=), dfilm rows are written.
+ * ===================================================================================================== */
+int gw_gen_conv(const void* src0, int C0, int L0, int up0, const void* src1, int C1, const float* x, const float* x_alt,
+                const int* step_ptr, int Cx, int B, int L, const float* w, const float* bias, int Cout, int K, void* out,
+                int dtype, void* stream);
+int gw_gen_weight_dgrad(const float* w, int Cout, int Cin, int K, float* wt, void* stream);
+int gw_gen_gn_stats(const void* raw, int B, int L, int C, int groups, int dtype, float* stats, void* stream);
+int gw_gen_gn_apply(const void* raw, const float* stats, int B, int L, int C, int groups, const float* gn_w, const float* gn_b,
+                    const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+                    long film_b_stride, long film_step_stride, const int* step_ptr, void* out, void* pooled, int dtype,
+                    void* stream);
+int gw_gen_final(const void* h, int dtype, const float* net_a, const float* net_b, int B, int Cx, int L, int C, int K,
+                 const float* wf, const float* bf, const gw_step_params* p, const float* coef, const int* step_ptr,
+                 const float* noise, float* eps_out, float* x0_out, void* stream);
+int gw_gen_final_bwd(const float* d_eps, const void* h, int dtype, const float* net, int B, int Cx, int L, int C, int K,
+                     const float* wf, void* d_h, float* dWf, float* dbf, void* stream);
+long gw_gen_gn_bwd_scratch_floats(int B, int C);
+int gw_gen_gn_bwd(const void* raw, const float* stats, int B, int L, int C, int groups, const float* gn_w, const float* gn_b,
+                  const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+                  long film_b_stride, const void* d_out, const void* d_pool, int dtype, float* scratch, float* dfilm,
+                  long dfilm_stride, void* d_raw, float* d_gn_w, float* d_gn_b, float* d_wc, float* d_bc, float* d_bias,
+                  void* stream);
+int gw_gen_wgrad(const void* src0, int C0, int L0, int up0, const void* src1, int C1, const float* x, int Cx,
+                 const void* d_raw, int B, int L, int Cout, int K, int dtype, float* dW, void* stream);
+int gw_gen_split_cat(const void* d_cat, int B, int L, int C0, int L0, int C1, void* d_h, void* d_skip, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,126 @@
+"""GPU parity of the shape-generic kernels (csrc/generic.cu): UNet1D configurations outside the CLI defaults --
+base_ch in {16, 32} and / or kernel in {5, 7} (models.py:78-88; train.py:609-612 exposes both) -- forward per layer, one
+training step (loss + every parameter gradient), the reverse chain (CFG, self-conditioning, DDIM / DDPM noise).
+
+Tolerances as for the default architecture: fp32 mode rel-L2 <= 1e-5 per layer, gradients <= 5e-5; bf16 storage <= 1e-2 / 5e-2;
+fp32 chain rel-L2 <= 1e-4.
+"""
+import pytest
+import torch
+
+import oracle
+from weights import make_state_dict, synthetic_chirps, gaussian
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+ARCHS = [(16, 3, 3), (32, 5, 3), (64, 7, 2), (8, 1, 3), (128, 5, 2)]
+
+
+@pytest.mark.parametrize("base_ch,kernel,depth", ARCHS)
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+@pytest.mark.parametrize("in_ch,cc,L,B", [(3, 1, 512, 2), (7, 5, 250, 3), (1, 0, 256, 2)])
+def test_generic_forward_per_layer_vs_oracle(base_ch, kernel, depth, dtype, tol, in_ch, cc, L, B):
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.engine import ModelSpec, UNetEngine
+    sc = in_ch > 1
+    sd = make_state_dict(in_ch, cc, base_ch=base_ch, depth=depth, kernel=kernel, seed=5)
+    cfg = oracle.ModelCfg(in_ch=in_ch, base_ch=base_ch, depth=depth, kernel=kernel, cond_in_ch=cc, use_selfcond=sc)
+    x = gaussian((B, in_ch, L), seed=17 + L)
+    t = torch.tensor(([24, 999, 500] * B)[:B])
+    with torch.no_grad():
+        taps = oracle.unet_forward_taps(sd, cfg, x, t)
+    spec = ModelSpec(in_ch=in_ch, base_ch=base_ch, depth=depth, kernel=kernel, cond_in_ch=cc, use_selfcond=sc)
+    eng = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype=dtype)
+    assert eng.generic
+    eps = eng.forward(x.cuda(), t.cuda(), keep_raw=True)
+    ws = eng.workspace(B, L, True)
+    names = [f"enc{i}" for i in range(depth)] + ["mid"] + [f"dec{i}" for i in range(depth)]
+    for li, n in enumerate(names):
+        assert rel_l2(ws.raw[li].float().transpose(1, 2), taps[n + ".raw"]) <= tol, (n, "raw")
+        assert rel_l2(ws.out[li].float().transpose(1, 2), taps[n + ".out"]) <= tol, (n, "out")
+    assert rel_l2(eps, taps["eps"]) <= tol
+
+
+@pytest.mark.parametrize("base_ch,kernel,depth,cd,tol", [(16, 3, 3, "fp32", 5e-5), (32, 5, 3, "fp32", 5e-5), (64, 7, 2, "fp32", 5e-5),
+                                                         (32, 5, 3, "bf16", 5e-2), (16, 7, 3, "bf16", 5e-2)])
+@pytest.mark.parametrize("in_ch,cc,L", [(3, 1, 512), (7, 5, 250)])
+def test_generic_train_step_vs_oracle(base_ch, kernel, depth, cd, tol, in_ch, cc, L):
+    """One training step (q_sample, CFG dropout, self-conditioning pass, Huber loss, backward): loss, eps_hat and every
+    parameter gradient against the oracle's autograd; odd length 250 exercises pad / trim and the unpaired last row."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import FusedTrainStep
+    B = 3
+    sd = make_state_dict(in_ch, cc, base_ch=base_ch, depth=depth, kernel=kernel, seed=3)
+    cfg = oracle.ModelCfg(in_ch=in_ch, base_ch=base_ch, depth=depth, kernel=kernel, cond_in_ch=cc, use_selfcond=True)
+    data = synthetic_chirps(B, L, snr=12.0, seed=31)
+    clean, y = data["clean_norm"], data["y_norm"]
+    mask = torch.ones(B, 1, L)
+    mask[1, :, :37] = 0.0
+    cond = y if cc == 1 else torch.cat([y, gaussian((B, 4, 1), seed=6).expand(B, 4, L).contiguous() * 0.3], dim=1)
+    t = torch.tensor([500, 731, 999])
+    eps = gaussian((B, 1, L), seed=41)
+    drop = torch.tensor([0.0, 1.0, 0.0]).view(B, 1, 1)
+    ab = oracle.alpha_bar_from_betas(oracle.cosine_beta_schedule(1000))
+    loss_o, grads_o, eps_o = oracle.train_step(sd, cfg, ab, clean_norm=clean, cond_stack=cond, mask=mask, t=t, eps=eps, drop=drop,
+                                               selfcond=True)
+    m = UNet1D(in_ch=in_ch, base_ch=base_ch, depth=depth, kernel=kernel, cond_in_ch=cc, use_selfcond=True, compute_dtype=cd)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    st = FusedTrainStep(m, CustomDiffusion(T=1000, device="cuda"), B, L, compute_dtype=cd, p_uncond=0.2, warmup_steps=10,
+                        total_steps=100)
+    st.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+    st.step(selfcond=True, t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=False)
+    torch.cuda.synchronize()
+    assert rel_l2(st.eps_hat, eps_o) <= (1e-5 if cd == "fp32" else 1e-2)
+    assert abs(float(st.loss) - float(loss_o)) <= max(tol, 2e-6) * abs(float(loss_o))
+    grads = st.layout.views(st.flat_g)
+    tot = float(torch.cat([g.reshape(-1) for g in grads_o.values()]).norm())
+    for k, go in grads_o.items():
+        err = float((grads[k].cpu().double() - go.double()).norm())
+        assert err <= tol * max(float(go.norm()), (1e-3 if cd == "fp32" else 2e-2) * tot), (k, err, float(go.norm()))
+    # the captured graph replays the same step
+    p0 = st.flat_p.clone()
+    st.step(selfcond=True, t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(st.flat_p).all() and not torch.equal(p0, st.flat_p)
+
+
+@pytest.mark.parametrize("base_ch,kernel", [(16, 3), (32, 5)])
+def test_generic_chain_vs_oracle(base_ch, kernel):
+    """Reverse chain on a non-default model: CFG two-pass batch, self-conditioning, DDIM (eta 0) and stochastic (eta 1, start_t)
+    steps with injected noise, eager and CUDA-graph replay."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    L, B = 512, 3
+    sd = make_state_dict(3, 1, base_ch=base_ch, kernel=kernel, seed=1)
+    cfg = oracle.ModelCfg(in_ch=3, base_ch=base_ch, kernel=kernel, cond_in_ch=1, use_selfcond=True)
+    ab = oracle.alpha_bar_from_betas(oracle.cosine_beta_schedule(1000))
+    y = synthetic_chirps(B, L, snr=10.0, seed=78)["y_norm"]
+    noise = torch.stack([gaussian((B, 1, L), seed=300 + k) for k in range(30)], 0)
+    m = UNet1D(in_ch=3, base_ch=base_ch, kernel=kernel, cond_in_ch=1, use_selfcond=True, compute_dtype="fp32")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    diff = CustomDiffusion(T=1000, device="cuda")
+    base = dict(T=1000, device="cuda", length=L, debug=False, x0_std_est=0.14, cond_scale=1.0, eps_scale=1.0, pred_type="eps",
+                in_ch=3, cond_in_ch=1, use_selfcond=True, cfg_mode="const", cfg_center=0.5, cfg_width=0.3, cfg_u_only_thresh=0.0,
+                dc_weight=0.0, init_mode="noise")
+    for kw in [dict(steps=20, eta=0.0, start_t=None, cfg_scale=1.0), dict(steps=20, eta=1.0, start_t=289, cfg_scale=2.0)]:
+        ref = oracle.ddim_sample(sd, cfg, ab, y, T=1000, noise=list(noise), **kw)
+        out = inf.ddim_sample(m, diff, y.cuda(), noise=noise, **base, **kw)
+        assert rel_l2(out, ref) <= 1e-4, (kw, rel_l2(out, ref))
+        out_b = inf.ddim_sample(m, diff, y.cuda(), noise=noise, compute_dtype="bf16", **base, **kw)
+        assert rel_l2(out_b, ref) <= 3e-2, (kw, rel_l2(out_b, ref))
+
+
+def test_unsupported_architectures_fail_loudly():
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.engine import ModelSpec, UNetEngine
+    for base_ch, kernel in [(24, 3), (16, 4), (16, 9)]:
+        sd = make_state_dict(3, 1, base_ch=base_ch, kernel=kernel, seed=0)
+        with pytest.raises(ValueError):
+            UNetEngine({k: v.cuda() for k, v in sd.items()}, ModelSpec(in_ch=3, base_ch=base_ch, kernel=kernel, cond_in_ch=1,
+                                                                       use_selfcond=True), dtype="fp32")

@@ -42,3 +42,30 @@ def test_element_loss_matches_reference_formula():
     m = (torch.rand(2, 1, 33) > 0.3).float()
     for lt in ("huber", "mse"):
         assert torch.equal(TR._element_loss(a, b, m, lt, 0.5), oracle.element_loss(a, b, m, lt, 0.5))
+
+
+def test_stratified_timesteps_cover_every_stratum():
+    """`_sample_timesteps_stratified` (train.py:147-172): every stratum [edge_i, edge_{i+1}) of [t_min, t_max] receives q or q + 1
+    of the bsz draws, all draws lie in range, and the result is a permutation of the per-stratum draws."""
+    import torch
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200.train import _sample_timesteps_stratified
+    torch.manual_seed(0)
+    for bsz, t_min, t_max, bins in [(256, 500, 999, 0), (37, 500, 999, 8), (16, 0, 999, 64), (5, 990, 999, 0), (12, 7, 7, 4)]:
+        t = _sample_timesteps_stratified(bsz, t_min, t_max, "cpu", bins=bins)
+        assert t.dtype == torch.int64 and t.shape == (bsz,)
+        assert int(t.min()) >= t_min and int(t.max()) <= t_max
+        b = max(1, min(bins if bins > 0 else bsz, bsz))
+        edges = torch.linspace(t_min, t_max + 1, b + 1).long().tolist()
+        q, r = divmod(bsz, b)
+        left = sorted(t.tolist())
+        for i in range(b):
+            lo, hi = edges[i], max(edges[i + 1] - 1, edges[i])
+            want = q + 1 if i < r else q
+            got = [v for v in left if lo <= v <= hi]
+            assert len(got) >= want, (bsz, bins, i, lo, hi, want, len(got))      # >=: a degenerate stratum may overlap its neighbour
+        # different calls give different draws (it is random), same seed gives the same
+        torch.manual_seed(3)
+        a1 = _sample_timesteps_stratified(bsz, t_min, t_max, "cpu", bins=bins)
+        torch.manual_seed(3)
+        a2 = _sample_timesteps_stratified(bsz, t_min, t_max, "cpu", bins=bins)
+        assert torch.equal(a1, a2)

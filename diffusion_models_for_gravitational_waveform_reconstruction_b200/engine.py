@@ -170,7 +170,7 @@ class UNetEngine:
             raise ValueError("the tcgen05 conv path stores bf16 activations; use dtype='bf16'")
         self.conv_impl = conv_impl
         self.tc_variant = tc_variant
-        # Non-default architectures (train.py:609-612 exposes --base-ch and --kernel): every layer runs the shape-generic
+        # Non-default architectures (models.py:78-88 takes base_ch and kernel; the training CLI exposes --base_ch, train.py:641): every layer runs the shape-generic
         # CUDA-core kernels of csrc/generic.cu (fp32 math, fp32 or bf16 storage) instead of the tcgen05 / streaming kernels,
         # which are laid out for 64-channel rows and three taps.
         self.generic = spec.base_ch % 64 != 0 or spec.kernel != 3

@@ -5,8 +5,9 @@
   * `noise=` injects the draws the reference would take from the global RNG ([n_draws, B, 1, L], draw 0 = x_T,
     draw k = k-th stochastic step), `seed=`/`sample0=` select the on-device Philox stream instead;
   * `use_graph=` runs the whole chain as one CUDA graph, `compute_dtype=` picks fp32-exact or bf16/tcgen05 kernels.
-Deployment-CLI pieces of the reference file (HDF5 IO, whitening, plotting; inference.py:59-205, 247-314, 517-903) are
-outside the hot path and are not re-implemented here.
+The data / checkpoint loaders either side of the chain are mirrored too: `load_checkpoint` (inference.py:614-650,
+sweep_infer.py:170-190), `_load_measurement_from_h5` / `_load_measurement_from_npy` (inference.py:59-93), `_meta_to_stack`
+(inference.py:96-122).  Plotting and the argparse `main` (inference.py:517-903) are outside the hot path and not re-implemented.
 """
 from __future__ import annotations
 
@@ -24,7 +25,91 @@ from .whitening import (_dewhiten_model, _dewhiten_train_like, _dewhiten_welch, 
                         _pick_sigma, _whiten_pair_model, _whiten_pair_train_like, _whiten_pair_welch)
 
 __all__ = ["philox_normal", "snr_from_alpha_bar", "t_for_target_snr", "_build_t_schedule", "_cfg_weight", "_reduce_to_one_channel",
-           "one_step_proxy_like_test_infer", "ddim_sample", "make_sampler_plan"]
+           "one_step_proxy_like_test_infer", "ddim_sample", "make_sampler_plan", "load_checkpoint", "_load_measurement_from_h5",
+           "_load_measurement_from_npy", "_meta_to_stack"]
+
+
+# ------------------------------------------------------------------------------------------------ loaders around the chain
+def load_checkpoint(path: str, device="cuda", use_ema: bool = True, compute_dtype: Optional[str] = None):
+    """Model + diffusion from a reference-format checkpoint (payload of train.py:606-630), the way every reference entry point
+    does it (inference.py:614-650, sweep_infer.py:170-190, grid_infer.py:288-307): architecture from `ckpt['args']` with the
+    reference's fallbacks, self-conditioning inferred from the channel count, EMA weights when present and wanted,
+    `load_state_dict(strict=True)`.  Returns (model.eval() on `device`, CustomDiffusion, ck_args)."""
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    ck_args = ckpt.get("args", {}) or {}
+    in_ch = int(ck_args.get("in_ch", 3))
+    cond_in_ch = int(ck_args.get("cond_in_ch", 1))
+    T = int(ck_args.get("T", 1000))
+    kw = {} if compute_dtype is None else {"compute_dtype": compute_dtype}
+    model = UNet1D(in_ch=in_ch, base_ch=int(ck_args.get("base_ch", 64)), time_dim=int(ck_args.get("time_dim", 128)),
+                   depth=int(ck_args.get("depth", 3)), t_embed_max_time=max(0, T - 1), cond_in_ch=cond_in_ch,
+                   use_selfcond=(in_ch == (1 + cond_in_ch + 1)), **kw)
+    loaded = False
+    if use_ema and "model_ema_state" in ckpt:
+        try:
+            model.load_state_dict(ckpt["model_ema_state"], strict=True)
+            loaded = True
+        except Exception as e:                                    # inference.py:645-646: fall back to the raw weights
+            print(f"[warn] EMA load failed ({e}); falling back to raw weights]")
+    if not loaded:
+        model.load_state_dict(ckpt["model_state"], strict=True)
+    model = model.to(device).eval()
+    return model, CustomDiffusion(T=T, device=device), ck_args
+
+
+def _load_measurement_from_h5(h5_path: str, index: int):
+    """inference.py:59-89: (y, clean, fs, P_model, (fw, Pw), meta_dict) of one HDF5 row (`gen.py:406-413` layout), read with
+    h5py when installed and with the bundled reader otherwise."""
+    from .dataloader import open_h5
+    meta: Dict[str, float] = {}
+    f = open_h5(h5_path)
+    try:
+        y = np.array(f["noisy"][index], dtype=np.float32)
+        clean = np.array(f["signal"][index], dtype=np.float32) if "signal" in f else None
+        fs = float(f.attrs.get("sampling_rate", 0.0)) or float(1.0 / f.attrs.get("delta_t", 1.0 / 4096.0))
+        P_model = None
+        if "psd_model" in f:
+            P_model = np.array(f["psd_model"][index], dtype=np.float64)
+        elif "psd" in f:                                          # legacy name
+            P_model = np.array(f["psd"][index], dtype=np.float64)
+        fw = Pw = None
+        if ("psd_welch" in f) and ("psd_welch_freqs" in f):
+            Pw = np.array(f["psd_welch"][index], dtype=np.float64)
+            fw = np.array(f["psd_welch_freqs"][index], dtype=np.float64)
+        for k in ["mass1", "mass2", "spin1z", "spin2z", "q", "chirp_mass", "snr", "epoch", "label_m1", "label_m2", "label_s1",
+                  "label_s2"]:
+            if k in f:
+                try:
+                    meta[k] = float(np.array(f[k][index]).reshape(()))
+                except Exception:
+                    pass
+    finally:
+        if hasattr(f, "close"):
+            f.close()
+    return y, clean, fs, P_model, (fw, Pw), meta
+
+
+def _load_measurement_from_npy(npy_path: str, fs: float):
+    """inference.py:91-93."""
+    y = np.load(npy_path).astype(np.float32).ravel()
+    return y, None, fs, None, (None, None), {}
+
+
+def _meta_to_stack(meta: dict, L: int, cond_in_ch: int, M_SCALE: float, Q_SCALE: float) -> Optional[np.ndarray]:
+    """inference.py:96-122: [cond_in_ch - 1, L] constant channels in the order m1, m2, s1, s2, q, chirp_mass (masses / M_SCALE,
+    q clipped to [0, Q_SCALE] / Q_SCALE, spins as they are), zero rows beyond the sixth."""
+    need = max(0, cond_in_ch - 1)
+    if need <= 0:
+        return None
+    qv = meta.get("q", 0.0)
+    if not np.isfinite(qv):
+        qv = 0.0
+    vals = [meta.get("mass1", 0.0) / max(M_SCALE, 1e-9), meta.get("mass2", 0.0) / max(M_SCALE, 1e-9), meta.get("spin1z", 0.0),
+            meta.get("spin2z", 0.0), min(max(qv, 0.0), Q_SCALE) / max(Q_SCALE, 1e-9), meta.get("chirp_mass", 0.0) / max(M_SCALE, 1e-9)]
+    arr = np.zeros((need, L), dtype=np.float32)
+    for i, v in enumerate(vals[:need]):
+        arr[i, :] = np.float32(float(v))
+    return arr
 
 
 def philox_normal(B: int, L: int, seed: int, sample0: int = 0, step: int = 0, device="cuda") -> torch.Tensor:

@@ -351,7 +351,7 @@ int gw_score_batch(const float* xhat, const float* clean, const float* sigma, in
 
 /* =====================================================================================================
  * Shape-generic CUDA-core path (csrc/generic.cu) for the UNet1D configurations the specialised kernels do not cover:
- * base_ch not a multiple of 64 and / or kernel in {1, 3, 5, 7} (models.py:78-88 takes both from the CLI, train.py:609-612).
+ * base_ch not a multiple of 64 and / or kernel in {1, 3, 5, 7} (UNet1D arguments, models.py:78-88; --base_ch on the training CLI, train.py:641).
  * Any channel count; GroupNorm with `groups` = gcd(8, C) groups (models.py:160-164); stats fp32 [B, 8, 2] = (mean, rstd).
  * Same operand conventions as the specialised entry points: activations channels-last [B, L, C] in `dtype`, weights in the
  * reference layout [Cout, Cin, K], the network input fp32 [B, Cx, L] (ping-pong pair selected by *step_ptr & 1).

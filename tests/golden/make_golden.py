@@ -421,10 +421,71 @@ def gen_ingest(out):
     np.savez_compressed(os.path.join(out, "ingest.npz"), **rec)
 
 
+def gen_checkpoint(M, I, TR, out):
+    """A reference-format checkpoint (payload of train.py:606-630) written from the unmodified reference classes: a small
+    non-default UNet1D (base_ch=16, depth=2, time_dim=32, 7 input channels) after two AdamW steps on the reference loss with an
+    EMA copy (train.py:73-81), plus what the reference computes from it -- eps_hat of the raw and of the EMA weights -- and the
+    outputs of the reference's measurement loaders (`_load_measurement_from_h5`, `_meta_to_stack`, inference.py:59-122) on the
+    ingest fixture."""
+    import copy
+    import types
+    torch.manual_seed(11)
+    in_ch, cc, L = 7, 5, 256
+    model = M.UNet1D(in_ch=in_ch, base_ch=16, time_dim=32, depth=2, t_embed_max_time=999, cond_in_ch=cc, use_selfcond=True)
+    with torch.no_grad():
+        model.final.weight.normal_(0.0, 0.05)
+        model.final.bias.normal_(0.0, 0.05)
+    ema = copy.deepcopy(model)
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-3, weight_decay=1e-4)
+    diff = M.CustomDiffusion(T=1000, device="cpu")
+    data = synthetic_chirps(3, L, snr=10.0, seed=90)
+    cond = torch.cat([data["y_norm"], 0.3 * gaussian((3, 4, 1), seed=91).expand(3, 4, L)], dim=1)
+    for it in range(2):
+        t = torch.tensor([600, 800, 999]) - it
+        x_t, eps = diff.q_sample(data["clean_norm"], t)
+        net = torch.cat([x_t, cond, torch.zeros_like(x_t)], dim=1)
+        loss = TR._element_loss(model(net, t), eps, torch.ones_like(eps), "huber", 0.5).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        TR.update_ema(ema, model, 0.9)
+    args = dict(data="train.h5", model_dir="model", epochs=2, batch_size=3, lr=2e-3, weight_decay=1e-4, T=1000, base_ch=16, time_dim=32,
+                depth=2, ema=True, ema_decay=0.9, p_uncond=0.2, p_selfcond=0.5, loss="huber", huber_beta=0.5)
+    payload = {"model_state": model.state_dict(), "optimizer_state": opt.state_dict(),
+               "args": {**args, "conditional": True, "in_ch": in_ch, "cond_in_ch": cc, "meta_enabled": True, "meta_channels": 4,
+                        "conditioning": "concat[y + meta]+selfcond", "whiten": True, "whiten_mode": "auto", "sigma_mode": "std",
+                        "dropout_y_only": True, "meta_scale": {"M": 65.0, "q": 10.0}},
+               "epoch": 2, "model_ema_state": ema.state_dict()}
+    torch.save(payload, os.path.join(out, "ref_checkpoint.pth"))
+    rec = {}
+    x = gaussian((2, in_ch, L), seed=92)
+    tt = torch.tensor([24, 731])
+    with torch.no_grad():
+        rec["x"], rec["t"] = x.numpy(), tt.numpy()
+        rec["eps_raw"] = model.eval()(x, tt).numpy()
+        rec["eps_ema"] = ema.eval()(x, tt).numpy()
+    # measurement loaders on the ingest fixture (read through the package's reader registered as h5py, see gen_ingest)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import _hdf5
+    h5stub = types.ModuleType("h5py")
+    h5stub.File = _hdf5.File
+    I.h5py = h5stub
+    y, clean, fs, P_model, (fw, Pw), meta = I._load_measurement_from_h5(os.path.join(out, "ingest_fixture.h5"), 4)
+    rec["meas/y"], rec["meas/clean"], rec["meas/fs"], rec["meas/P_model"] = y, clean, np.float64(fs), P_model
+    rec["meas/meta_keys"] = np.array(sorted(meta))
+    rec["meas/meta_vals"] = np.array([meta[k] for k in sorted(meta)], dtype=np.float64)
+    meta["q"] = meta["mass1"] / meta["mass2"]
+    meta["chirp_mass"] = 21.5
+    for need in (1, 3, 5, 7, 9):
+        st = I._meta_to_stack(meta, 64, need, 65.0, 10.0)
+        rec[f"meta_stack/{need}"] = np.zeros((0, 64), np.float32) if st is None else st
+    np.savez_compressed(os.path.join(out, "checkpoint.npz"), **rec)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
-    ap.add_argument("--only", default=None, help="run one generator only (whitening_welch | ingest)")
+    ap.add_argument("--only", default=None, help="run one generator only (whitening_welch | ingest | checkpoint)")
     args = ap.parse_args()
     if args.only == "whitening_welch":
         M, I, TR = import_reference()
@@ -432,6 +493,10 @@ def main():
         return
     if args.only == "ingest":
         gen_ingest(args.out)
+        return
+    if args.only == "checkpoint":
+        M, I, TR = import_reference()
+        gen_checkpoint(M, I, TR, args.out)
         return
     torch.set_num_threads(8)
     M, I, TR = import_reference()
@@ -444,6 +509,7 @@ def main():
     gen_whitening(I, args.out)
     gen_whitening_welch(I, args.out)
     gen_ingest(args.out)
+    gen_checkpoint(M, I, TR, args.out)
     tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
     print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
 

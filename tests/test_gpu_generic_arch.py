@@ -1,5 +1,5 @@
 """GPU parity of the shape-generic kernels (csrc/generic.cu): UNet1D configurations outside the CLI defaults --
-base_ch in {16, 32} and / or kernel in {5, 7} (models.py:78-88; train.py:609-612 exposes both) -- forward per layer, one
+base_ch in {16, 32} and / or kernel in {5, 7} (UNet1D arguments, models.py:78-88; --base_ch on the training CLI, train.py:641) -- forward per layer, one
 training step (loss + every parameter gradient), the reverse chain (CFG, self-conditioning, DDIM / DDPM noise).
 
 Tolerances as for the default architecture: fp32 mode rel-L2 <= 1e-5 per layer, gradients <= 5e-5; bf16 storage <= 1e-2 / 5e-2;
@@ -126,3 +126,32 @@ def test_unsupported_architectures_fail_loudly():
         with pytest.raises(ValueError):
             UNetEngine({k: v.cuda() for k, v in sd.items()}, ModelSpec(in_ch=3, base_ch=base_ch, kernel=kernel, cond_in_ch=1,
                                                                        use_selfcond=True), dtype="fp32")
+
+
+def test_reference_checkpoint_runs_on_the_gpu(golden_dir):
+    """tests/golden/ref_checkpoint.pth was written by the unmodified reference classes (base_ch=16, depth=2, time_dim=32, 7 input
+    channels; payload of train.py:606-630).  `load_checkpoint` (inference.py:614-650) + forward on the GPU must reproduce the
+    reference's own eps_hat for the EMA and for the raw weights."""
+    import os
+    import numpy as np
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    g = np.load(os.path.join(golden_dir, "checkpoint.npz"))
+    x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    path = os.path.join(golden_dir, "ref_checkpoint.pth")
+    for use_ema, key in [(True, "eps_ema"), (False, "eps_raw")]:
+        model, diff, ck_args = inf.load_checkpoint(path, device="cuda", use_ema=use_ema, compute_dtype="fp32")
+        with torch.no_grad():
+            eps = model(x, t)
+        assert rel_l2(eps, torch.from_numpy(g[key])) <= 1e-5, (key, rel_l2(eps, torch.from_numpy(g[key])))
+        model_b, _, _ = inf.load_checkpoint(path, device="cuda", use_ema=use_ema, compute_dtype="bf16")
+        with torch.no_grad():
+            eps_b = model_b(x, t)
+        assert rel_l2(eps_b, torch.from_numpy(g[key])) <= 1e-2, (key, "bf16")
+    # ... and a short chain through the reference-facing sampler entry point on the loaded model
+    y = synthetic_chirps(2, 256, snr=10.0, seed=5)["y_norm"]
+    cond = torch.cat([y, torch.zeros(2, 4, 256)], dim=1).cuda()
+    out = inf.ddim_sample(model, diff, cond, T=1000, steps=8, eta=0.0, device="cuda", length=256, debug=False, start_t=289,
+                          init_mode="y-blend", x0_std_est=0.14, dc_weight=0.0, cond_scale=1.0, eps_scale=1.0, pred_type="eps",
+                          in_ch=7, cond_in_ch=5, use_selfcond=True, cfg_scale=1.5, cfg_mode="const", cfg_center=0.5, cfg_width=0.3,
+                          cfg_u_only_thresh=0.0)
+    assert out.shape == (2, 1, 256) and torch.isfinite(out).all()

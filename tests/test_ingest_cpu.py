@@ -73,3 +73,48 @@ def test_resolve_path_and_pad_collate(tmp_path, golden_dir):
     assert clean[1, 0].tolist() == [0, 0, 0, 1, 2] and mask[1, 0].tolist() == [0, 0, 1, 1, 1] and meta[2, :, 0].sum() == 0
     with pytest.raises(ValueError):
         D.NoisyWaveDataset(os.path.join(golden_dir, "ingest_fixture.h5"), sigma_mode="bogus")
+
+
+def test_measurement_loaders_match_reference(golden_dir):
+    """`_load_measurement_from_h5` / `_meta_to_stack` (inference.py:59-122) against the outputs of the reference's own functions on
+    the ingest fixture (tests/golden/make_golden.py::gen_checkpoint)."""
+    import os
+    import numpy as np
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    g = np.load(os.path.join(golden_dir, "checkpoint.npz"))
+    y, clean, fs, P_model, (fw, Pw), meta = inf._load_measurement_from_h5(os.path.join(golden_dir, "ingest_fixture.h5"), 4)
+    assert y.dtype == np.float32 and np.array_equal(y, g["meas/y"]) and np.array_equal(clean, g["meas/clean"])
+    assert fs == float(g["meas/fs"]) and np.array_equal(P_model, g["meas/P_model"]) and fw is None and Pw is None
+    assert sorted(meta) == list(g["meas/meta_keys"])
+    assert np.array_equal(np.array([meta[k] for k in sorted(meta)]), g["meas/meta_vals"])
+    meta["q"] = meta["mass1"] / meta["mass2"]
+    meta["chirp_mass"] = 21.5
+    for need in (1, 3, 5, 7, 9):
+        st = inf._meta_to_stack(meta, 64, need, 65.0, 10.0)
+        ref = g[f"meta_stack/{need}"]
+        if need == 1:
+            assert st is None and ref.shape[0] == 0
+        else:
+            assert st.dtype == np.float32 and st.shape == ref.shape and np.array_equal(st, ref), need
+    assert inf._meta_to_stack({"q": float("nan")}, 8, 6, 80.0, 10.0)[4].max() == 0.0      # inference.py:113
+
+
+def test_load_checkpoint_reads_reference_format(golden_dir):
+    """A checkpoint written by the reference classes (payload keys of train.py:606-630) loads with strict=True; the architecture
+    comes from ckpt['args'] with the reference's fallbacks and EMA weights win when present (inference.py:614-650)."""
+    import os
+    import torch
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    path = os.path.join(golden_dir, "ref_checkpoint.pth")
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model_state", "optimizer_state", "args", "epoch", "model_ema_state"}
+    model, diff, ck_args = inf.load_checkpoint(path, device="cpu", use_ema=True)
+    assert (model.in_ch, model.cond_in_ch, model.use_selfcond) == (7, 5, True)
+    assert model.spec.base_ch == 16 and model.spec.depth == 2 and model.spec.time_dim == 32 and model.spec.max_time == 999.0
+    assert diff.T == 1000 and ck_args["meta_scale"] == {"M": 65.0, "q": 10.0}
+    sd = model.state_dict()
+    assert list(sd) == list(ck["model_ema_state"])
+    assert all(torch.equal(sd[k], ck["model_ema_state"][k]) for k in sd)
+    raw, _, _ = inf.load_checkpoint(path, device="cpu", use_ema=False)
+    assert all(torch.equal(raw.state_dict()[k], ck["model_state"][k]) for k in sd)
+    assert not torch.equal(raw.state_dict()["final.weight"], sd["final.weight"])

@@ -213,8 +213,13 @@ class UNetEngine:
         # profiles/r02_chain_overlap.md): the six layer kernels of an eager reverse step finish 19 us earlier (706 vs 725 us: the
         # 6 us launch gaps disappear, the overlap is real), but inside the CUDA graph the chain is power-capped -- the SM clock
         # drops from 1837 to 1788 MHz and the throughput is unchanged (287.7 vs 289.3 waveforms/s) -- so it stays an option
-        # (GWB200_CHAIN=1), parity-tested in both modes.
-        self.chain_layers = os.environ.get("GWB200_CHAIN", "0") not in ("0", "")
+        # (GWB200_CHAIN=1), parity-tested in both modes.  Small batches are a different regime: at B=8 the chain is latency-bound
+        # at full clock (64 of 148 SMs busy, ~14 us per layer kernel) and chaining is worth +14 % (80.4 vs 70.5 waveforms/s,
+        # profiles/r02_bench_ddpm1000_B8_chain.json), so `None` = automatic: on when a layer's samples fit in two rounds of CTA
+        # groups (batch <= 36), off above.  GWB200_CHAIN=0 / 1 or setting the attribute forces it.
+        env = os.environ.get("GWB200_CHAIN", "")
+        self.chain_layers: Optional[bool] = None if env == "" else (env != "0")
+        self.chain_auto_batch = 36
         # inference: first block in one pass with ANALYTIC GroupNorm statistics (conv_in_direct.cu) instead of the exchange-based
         # conv_in_gn kernel.  Measured on B200 (B=256, L=4096, in_ch=3; profiles/r02_first_block.md): moments 25 us + one-pass
         # kernel 79 us vs 107 us for conv_in_gn -- a wash so far, so the parity-tested kernel stays an option
@@ -419,7 +424,8 @@ class UNetEngine:
         head = head and not keep and Cout == 64 and src1 is not None and pooled is None
         if head and ws.dots is None:
             ws.dots = torch.empty(B, L, 4, device=self.device, dtype=torch.float32)
-        serial = self._chain_serial if (self.chain_layers and not keep and step_ptr is not None) else None
+        chain = self.chain_layers if self.chain_layers is not None else B <= self.chain_auto_batch
+        serial = self._chain_serial if (chain and not keep and step_ptr is not None) else None
         prev, prev_g = ws.chain_prev if (serial is not None and ws.chain_prev is not None and ws.chain_prev[1] <= 8
                                          and os.environ.get("GWB200_CHAIN", "0") != "2") else (None, 0)
         check(self.lib.gw_conv_gn3(C.byref(shp), ptr(src0), ptr(src1), ptr(packed), ptr(self.p[name + ".0.bias"]),

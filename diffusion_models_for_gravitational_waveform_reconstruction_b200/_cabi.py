@@ -89,6 +89,7 @@ _SIGS.update({
     "gw_wgrad_tc_scratch_elems": ([_I, _I, _I, _I, _I], _L),
     "gw_wgrad_tc": ([_I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P, _I, _P], _I),
     "gw_film_bwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
+    "gw_batch_prepare": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "gw_train_draws": ([_U64, _P, _L, _I, _I, _I, _F, _P, _P, _P], _I),
     "gw_train_pack": ([_P, _P, _I, _P, _P, _P, _P, _P, _I, _U64, _L, _P, _F, _I, _I, _P, _I, _I, _I, _P], _I),
     "gw_selfcond_x0": ([_P, _P, _P, _P, _I, _I, _I, _P], _I),

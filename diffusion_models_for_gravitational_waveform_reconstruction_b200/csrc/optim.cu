@@ -129,6 +129,39 @@ extern "C" int gw_train_pack(const float* clean, const float* cond, int Cc, cons
     return GW_OK;
 }
 
+// collated batch -> stepper inputs in one pass (train.py:336-347 + the --t_multi repeat_interleave, :355-360): division by the
+// per-sample sigma, y and the metadata channels stacked, every sample repeated K times.  out row b*K + r <- in row b.
+__global__ void __launch_bounds__(256) batch_prepare_kernel(const float* __restrict__ clean_raw, const float* __restrict__ noisy_raw,
+                                                            const float* __restrict__ sigma, const float* __restrict__ mask,
+                                                            const float* __restrict__ meta, int Cm, int L, int K,
+                                                            float* __restrict__ clean_out, float* __restrict__ cond_out,
+                                                            float* __restrict__ mask_out) {
+    const int b = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const float sg = sigma[b];
+    const float c = __fdiv_rn(clean_raw[(size_t)b * L + l], sg), y = __fdiv_rn(noisy_raw[(size_t)b * L + l], sg);
+    const float m = mask != nullptr ? mask[(size_t)b * L + l] : 1.0f;
+    const int Cc = 1 + Cm;
+    for (int r = 0; r < K; ++r) {
+        const size_t o = (size_t)b * K + r;
+        clean_out[o * L + l] = c;
+        mask_out[o * L + l] = m;
+        cond_out[o * Cc * L + l] = y;
+        for (int j = 0; j < Cm; ++j) cond_out[(o * Cc + 1 + j) * L + l] = meta[((size_t)b * Cm + j) * L + l];
+    }
+}
+extern "C" int gw_batch_prepare(const float* clean_raw, const float* noisy_raw, const float* sigma, const float* mask,
+                                const float* meta, int Cm, int B0, int L, int K, float* clean_out, float* cond_out, float* mask_out,
+                                void* stream) {
+    GW_REQUIRE(clean_raw && noisy_raw && sigma && clean_out && cond_out && mask_out, "gw_batch_prepare: null pointer");
+    GW_REQUIRE(B0 > 0 && L > 0 && K >= 1 && Cm >= 0 && (Cm == 0 || meta != nullptr), "gw_batch_prepare: sizes");
+    batch_prepare_kernel<<<dim3(gw_cdiv(L, 256), B0), 256, 0, (cudaStream_t)stream>>>(clean_raw, noisy_raw, sigma, mask, meta, Cm, L, K,
+                                                                                  clean_out, cond_out, mask_out);
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
 // self-conditioning estimate x0_hat = (x_t - sqrt(1-ab_t) eps_hat) / sqrt(ab_t) written to the last input channel
 // (train.py:40-51, 404-407).  ab = alpha_bar table (NOT clamped, as in train.py:49).
 __global__ void __launch_bounds__(256) selfcond_kernel(float* __restrict__ net, const float* __restrict__ eps_hat,

@@ -632,6 +632,32 @@ class FusedTrainStep:
         else:
             self.mask.fill_(1.0)                              # no mask = every sample valid (never the previous batch's mask)
 
+    def load_collated(self, clean_raw: Tensor, noisy_raw: Tensor, sigma: Tensor, mask: Optional[Tensor] = None,
+                      meta: Optional[Tensor] = None, repeat: int = 1) -> None:
+        """A collated loader batch (dataloader.py:248-268) straight into the step's input buffers: sigma-normalisation, the
+        [y | metadata] stack and the --t_multi repeat (train.py:336-347, 355-360) in ONE kernel (gw_batch_prepare) instead of
+        six eager ops and three staging copies.  clean_raw, noisy_raw, mask [B0, 1, L]; sigma [B0]; meta [B0, Cm, L]; B0 * repeat
+        must equal this stepper's batch."""
+        dev = self.clean.device
+        f = lambda a: a.to(dev, non_blocking=True).float().contiguous()
+        clean_raw, noisy_raw, sigma = f(clean_raw), f(noisy_raw), f(sigma).reshape(-1)
+        B0, L = int(sigma.numel()), self.L
+        Cm = self.spec.cond_in_ch - 1
+        if B0 * repeat != self.B or clean_raw.numel() != B0 * L or noisy_raw.numel() != B0 * L:
+            raise ValueError(f"load_collated: batch {B0} x repeat {repeat}, length {clean_raw.shape[-1]} vs stepper ({self.B}, {L})")
+        if Cm > 0:
+            if meta is None or meta.shape[1] != Cm:
+                raise ValueError(f"load_collated: the model expects {Cm} metadata channels")
+            meta = f(meta)
+            if meta.size(-1) != L:                            # train.py:341-343
+                meta = torch.nn.functional.interpolate(meta, size=L, mode="linear", align_corners=False).contiguous()
+        elif Cm < 0:
+            raise ValueError("load_collated needs a conditional model (cond_in_ch >= 1)")
+        mask = f(mask) if mask is not None else None
+        check(self.lib.gw_batch_prepare(ptr(clean_raw), ptr(noisy_raw), ptr(sigma), ptr(mask), ptr(meta) if Cm > 0 else None, Cm, B0,
+                                        L, repeat, ptr(self.clean), ptr(self.cond), ptr(self.mask), _cabi.stream_ptr()),
+              "batch_prepare")
+
     # steps attempted (host count, shared between steppers of one run); the APPLIED count lives on the device
     @property
     def steps_done(self) -> int:
@@ -891,17 +917,8 @@ def train_diffusion(args, loader=None):
         t_min = int(max(0, min(args.T - 1, int(args.t_min_frac * args.T))))
         for batch in loader:
             clean_raw, noisy_raw, sigma, mask = batch[:4]
-            meta = batch[4].to(device).float() if len(batch) == 5 else None
-            sig = sigma.to(device).view(-1, 1, 1).float()
-            clean_norm = clean_raw.to(device).float() / sig
-            y_norm = noisy_raw.to(device).float() / sig
-            if meta is not None and meta.size(-1) != y_norm.size(-1):
-                meta = torch.nn.functional.interpolate(meta, size=y_norm.size(-1), mode="linear", align_corners=False)
-            cond_stack = torch.cat([y_norm, meta], dim=1) if meta is not None else y_norm
-            mask = mask.to(device).float()
-            if K > 1:
-                clean_norm, cond_stack, mask = (a.repeat_interleave(K, dim=0) for a in (clean_norm, cond_stack, mask))
-            key = (int(clean_norm.shape[0]), int(clean_norm.shape[-1]))
+            meta = batch[4] if (len(batch) == 5 and C_meta > 0) else None
+            key = (int(clean_raw.shape[0]) * K, int(clean_raw.shape[-1]))
             stepper = steppers.get(key)
             if stepper is None:
                 # pad_collate pads to the per-batch maximum (dataloader.py:248-268), so (B, L) may change from batch to batch:
@@ -923,7 +940,7 @@ def train_diffusion(args, loader=None):
                 if first is None:
                     first = stepper
             stepper.p_uncond, stepper.t_min = p_uncond, t_min
-            stepper.load_batch(clean_norm, cond_stack, mask)
+            stepper.load_collated(clean_raw, noisy_raw, sigma, mask, meta, repeat=K)   # sigma-normalise + stack + repeat: one kernel
             t_inj = None
             if getattr(args, "t_cover", "rand") == "strat":
                 t_inj = _sample_timesteps_stratified(stepper.B, t_min, args.T - 1, device, bins=getattr(args, "t_bins", 0))

@@ -305,6 +305,11 @@ int gw_film_bwd(const float* dfilm, const float* aux, const float* w2, int B, in
  * CFG-dropout coin (train.py:386).  step_ptr: device step counter (NULL = 0). */
 int gw_train_draws(unsigned long long seed, const int* step_ptr, long sample0, int B, int t_min, int T,
                    float p_uncond, int64_t* t_out, float* drop_out, void* stream);
+/* collated batch -> stepper inputs (train.py:336-347, 355-360): clean_out [B0*K, L] = clean_raw / sigma, cond_out [B0*K, 1+Cm, L] =
+ * [noisy_raw / sigma | meta], mask_out [B0*K, L] (ones when mask == NULL); row b*K + r <- row b (repeat_interleave of --t_multi).
+ * clean_raw, noisy_raw, mask [B0, L]; sigma [B0]; meta [B0, Cm, L] or NULL. */
+int gw_batch_prepare(const float* clean_raw, const float* noisy_raw, const float* sigma, const float* mask, const float* meta,
+                     int Cm, int B0, int L, int K, float* clean_out, float* cond_out, float* mask_out, void* stream);
 /* network-input packing (train.py:350-352, 379-398, 404-407): q_sample with clamp into channel 0, conditioning
  * channels with CFG dropout, zero self-conditioning channel.  clean [B, L]; cond [B, Cc, L]; eps [B, L] read
  * (philox == 0) or generated; drop [B] or NULL. */

@@ -391,3 +391,30 @@ def test_steppers_of_different_shapes_share_one_run():
     with torch.no_grad():
         ref = oracle.unet_forward(sd1, cfg, b.net.cpu(), b.t.cpu())
     assert rel_l2(b.eps_hat, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("in_ch,cc,K", [(3, 1, 1), (7, 5, 3)])
+def test_load_collated_equals_reference_batch_preparation(in_ch, cc, K):
+    """gw_batch_prepare: sigma-normalisation, [y | metadata] stack and the --t_multi repeat_interleave of train.py:336-347,
+    355-360 in one kernel, written straight into the step's input buffers -- bit-equal to the reference's torch ops."""
+    B0, L = 4, 384
+    sd = make_state_dict(in_ch=in_ch, cond_in_ch=cc, seed=2)
+    m, st = _stepper(sd, in_ch, cc, B0 * K, L, "fp32")
+    clean = gaussian((B0, 1, L), seed=1) * 3e-21
+    noisy = clean + gaussian((B0, 1, L), seed=2) * 1e-21
+    sigma = noisy.reshape(B0, -1).std(dim=1)
+    mask = torch.ones(B0, 1, L)
+    mask[2, :, :100] = 0.0
+    meta = (gaussian((B0, cc - 1, 1), seed=3).expand(B0, cc - 1, L) * mask).contiguous() if cc > 1 else None
+    st.load_collated(clean.cuda(), noisy.cuda(), sigma.cuda(), mask.cuda(), meta.cuda() if meta is not None else None, repeat=K)
+    torch.cuda.synchronize()
+    sg = sigma.view(-1, 1, 1)
+    cond_ref = torch.cat([noisy / sg, meta], dim=1) if meta is not None else noisy / sg
+    ref = [a.repeat_interleave(K, dim=0) for a in (clean / sg, cond_ref, mask)]
+    assert torch.equal(st.clean.cpu().view(B0 * K, 1, L), ref[0])
+    assert torch.equal(st.cond.cpu().view(B0 * K, cc, L), ref[1])
+    assert torch.equal(st.mask.cpu().view(B0 * K, 1, L), ref[2])
+    st.load_collated(clean.cuda(), noisy.cuda(), sigma.cuda(), None, meta.cuda() if meta is not None else None, repeat=K)
+    assert float(st.mask.min()) == 1.0
+    with pytest.raises(ValueError):
+        st.load_collated(clean[:2].cuda(), noisy[:2].cuda(), sigma[:2].cuda(), None, None, repeat=K)

@@ -27,6 +27,8 @@
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) reduce_rows_kernel(float* __restrict__ src, int n_rows, long n_cols, long pitch, int chunk,
                                                            float scale, float* __restrict__ dst, int accumulate, int final_stage) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long c = (long)blockIdx.x * 32 + tx;
@@ -53,16 +55,16 @@ static int reduce_rows(const float* src_c, int n_rows, long n_cols, long pitch, 
     float* src = const_cast<float*>(src_c);
     const unsigned gx = (unsigned)((n_cols + 31) / 32);
     if (n_rows <= 256) {
-        reduce_rows_kernel<<<dim3(gx, 1), 1024, 0, st>>>(src, n_rows, n_cols, pitch, n_rows, scale, dst, accumulate, 1);
+        GW_CUDA(gw_launch_pdl(reduce_rows_kernel, dim3(gx, 1), dim3(1024), (size_t)(0), st, src, n_rows, n_cols, pitch, n_rows, scale, dst, accumulate, 1));
         GW_LAUNCH_CHECK();
         return GW_OK;
     }
     const int chunk = 128;
     const int n_chunks = gw_cdiv(n_rows, chunk);
-    reduce_rows_kernel<<<dim3(gx, n_chunks), 1024, 0, st>>>(src, n_rows, n_cols, pitch, chunk, 1.0f, nullptr, 0, 0);
+    GW_CUDA(gw_launch_pdl(reduce_rows_kernel, dim3(gx, n_chunks), dim3(1024), (size_t)(0), st, src, n_rows, n_cols, pitch, chunk, 1.0f, nullptr, 0, 0));
     GW_LAUNCH_CHECK();
     if (n_chunks <= 256) {
-        reduce_rows_kernel<<<dim3(gx, 1), 1024, 0, st>>>(src, n_chunks, n_cols, pitch * chunk, n_chunks, scale, dst, accumulate, 1);
+        GW_CUDA(gw_launch_pdl(reduce_rows_kernel, dim3(gx, 1), dim3(1024), (size_t)(0), st, src, n_chunks, n_cols, pitch * chunk, n_chunks, scale, dst, accumulate, 1));
         GW_LAUNCH_CHECK();
         return GW_OK;
     }
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ eps
                                                    const float* __restrict__ mask, const float* __restrict__ wt, int B, int L,
                                                    int loss_type, float beta, float grad_scale, float* __restrict__ per_sample,
                                                    float* __restrict__ d_eps) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[8];
     const int b = blockIdx.x;
     const float* eh = eps_hat + (size_t)b * L;
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ eps
 }
 
 __global__ void __launch_bounds__(256) mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[8];
     float a = 0.0f;
     for (int i = threadIdx.x; i < n; i += 256) a += v[i];
@@ -140,9 +146,9 @@ extern "C" int gw_loss(const float* eps_hat, const float* eps, const float* mask
                        float beta, float grad_scale, float* per_sample, float* loss, float* d_eps, void* stream) {
     GW_REQUIRE(B > 0 && L > 0 && (loss_type == 0 || loss_type == 1), "gw_loss: arguments");
     GW_REQUIRE(loss_type == 1 || beta > 0.0f, "gw_loss: huber beta must be > 0");
-    loss_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(eps_hat, eps, mask, wt, B, L, loss_type, beta, grad_scale, per_sample, d_eps);
+    GW_CUDA(gw_launch_pdl(loss_kernel, dim3(B), dim3(256), (size_t)(0), (cudaStream_t)stream, eps_hat, eps, mask, wt, B, L, loss_type, beta, grad_scale, per_sample, d_eps));
     GW_LAUNCH_CHECK();
-    mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(per_sample, B, loss);
+    GW_CUDA(gw_launch_pdl(mean_kernel, dim3(1), dim3(256), (size_t)(0), (cudaStream_t)stream, per_sample, B, loss));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -157,6 +163,8 @@ __global__ void __launch_bounds__(256) final_bwd_kernel(const float* __restrict_
                                                         const float* __restrict__ net, int Cx, int L, int C,
                                                         const float* __restrict__ wf, T* __restrict__ d_h,
                                                         float* __restrict__ partial, int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float sm[];
     const int n_oct = C / 8;
     const int n_tr = 256 / n_oct;                 // thread rows
@@ -254,7 +262,7 @@ extern "C" int gw_final_bwd(const float* d_eps, const void* h, int dtype, const 
 #define FB_GO(TT, WR)                                                                                                  \
     do {                                                                                                               \
         GW_CUDA(cudaFuncSetAttribute(final_bwd_kernel<TT, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        final_bwd_kernel<TT, WR><<<grid, 256, smem, st>>>(d_eps, (const TT*)h, net, Cx, L, C, wf, (TT*)d_h, scratch, rows); \
+        GW_CUDA(gw_launch_pdl(final_bwd_kernel<TT, WR>, grid, dim3(256), (size_t)(smem), st, d_eps, (const TT*)h, net, Cx, L, C, wf, (TT*)d_h, scratch, rows)); \
     } while (0)
     if (dtype == GW_F32) {
         if (d_h) FB_GO(float, true); else FB_GO(float, false);
@@ -338,6 +346,8 @@ __device__ __forceinline__ void load_quad(const GnBwdArgs& a, int b, int quad, i
 
 template <typename T, bool FAST, int CC>
 __global__ void __launch_bounds__(256, 2) gn_bwd_stats_kernel(GnBwdArgs a, float* __restrict__ partial) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     constexpr int NV = 4 + NC;
@@ -432,6 +442,8 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* __re
                                                                const float* __restrict__ bc, float* __restrict__ redb,
                                                                float* __restrict__ dfilm, long dfilm_b_stride, int film_off,
                                                                float* __restrict__ gstat) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float sv[];                        // [C][nvr]
     const int b = blockIdx.x;
     const float* pb = partial + (size_t)b * n_rc * C * nvr;
@@ -479,6 +491,8 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restr
                                                             float* __restrict__ d_wc, float* __restrict__ d_bc,
                                                             const float* __restrict__ bias_part, int n_rc,
                                                             float* __restrict__ d_conv_bias) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[32][32][3 + BW_MAX_CC + 1];        // slot 3 + BW_MAX_CC: the conv-bias sum (SX)
     const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -529,6 +543,8 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const float* __restr
 template <typename T, bool FAST, int CC>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs a, const float* __restrict__ gstat, T* __restrict__ d_raw,
                                                            float* __restrict__ partial_bias) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     extern __shared__ float red[];                      // [n_tr][C]
@@ -613,6 +629,8 @@ __device__ __forceinline__ void silu_pair(f32x2 x, f32x2 hA, f32x2 hB, f32x2& z,
 
 template <int CC, bool HEAD>
 __global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, float* __restrict__ partial) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : BW_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     constexpr int NV = 4 + NC;
@@ -735,6 +753,8 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_stats_bf16_kernel(GnBwdArgs a, 
 template <bool HEAD>
 __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, const float* __restrict__ gstat,
                                                                    bf16* __restrict__ d_raw, float* __restrict__ partial_bias) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float red[];                      // [n_tr][C]
     const int b = blockIdx.y, C = a.C, L = a.L;
     const int n_quad = C / 4, n_tr = 256 / n_quad;
@@ -901,11 +921,11 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
             float* biasp = gstat + (size_t)B * 16;
             const int rcf = gn_bwd_fused(a, B, partial, biasp, d_raw, sync, st);
             if (rcf == GW_OK) {
-                gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvr * sizeof(float), st>>>(partial, G, C, nvr, Cc, L, a.gn_w, a.wc, a.bc,
-                                                                                        redb, dfilm, dfilm_b_stride, a.film_off, gstat);
+                GW_CUDA(gw_launch_pdl(gn_bwd_finalize_kernel, dim3(B), dim3(1024), (size_t)((size_t)C * nvr * sizeof(float)), st, partial, G, C, nvr, Cc, L, a.gn_w, a.wc, a.bc,
+                                                                                        redb, dfilm, dfilm_b_stride, a.film_off, gstat));
                 GW_LAUNCH_CHECK();
-                gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvr, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w,
-                                                                   d_gn_b, d_wc, d_bc, nullptr, 0, nullptr);
+                GW_CUDA(gw_launch_pdl(gn_bwd_param_kernel, dim3(gw_cdiv(C, 32)), dim3(1024), (size_t)(0), st, redb, B, C, nvr, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w,
+                                                                   d_gn_b, d_wc, d_bc, nullptr, 0, nullptr));
                 GW_LAUNCH_CHECK();
                 return reduce_rows(biasp, B * G, C, C, 1.0f, d_conv_bias, 1, st);
             }
@@ -933,13 +953,13 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
             if (rcs != GW_OK) return rcs;                                                                                 \
         } else if (FAST && a.do_eps != nullptr) {                                                                         \
             GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_bf16_kernel<CCV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
-            gn_bwd_stats_bf16_kernel<CCV, true><<<grid, 256, sm1, st>>>(a, partial);                                      \
+            GW_CUDA(gw_launch_pdl(gn_bwd_stats_bf16_kernel<CCV, true>, grid, dim3(256), (size_t)(sm1), st, a, partial));                                      \
         } else if (FAST) {                                                                                                \
             GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_bf16_kernel<CCV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
-            gn_bwd_stats_bf16_kernel<CCV, false><<<grid, 256, sm1, st>>>(a, partial);                                     \
+            GW_CUDA(gw_launch_pdl(gn_bwd_stats_bf16_kernel<CCV, false>, grid, dim3(256), (size_t)(sm1), st, a, partial));                                     \
         } else {                                                                                                          \
             GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_kernel<T, FAST, CCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); \
-            gn_bwd_stats_kernel<T, FAST, CCV><<<grid, 256, sm1, st>>>(a, partial);                                        \
+            GW_CUDA(gw_launch_pdl(gn_bwd_stats_kernel<T, FAST, CCV>, grid, dim3(256), (size_t)(sm1), st, a, partial));                                        \
         }                                                                                                                 \
     } while (0)
     if (Cc == 0) GNB_GO(0);
@@ -948,27 +968,27 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     else GNB_GO(-1);
 #undef GNB_GO
     GW_LAUNCH_CHECK();
-    gn_bwd_finalize_kernel<<<B, 1024, (size_t)C * nvs * sizeof(float), st>>>(partial, n_rc, C, nvs, Cc, L, a.gn_w, a.wc, a.bc, redb,
-                                                                            dfilm, dfilm_b_stride, a.film_off, gstat);
+    GW_CUDA(gw_launch_pdl(gn_bwd_finalize_kernel, dim3(B), dim3(1024), (size_t)((size_t)C * nvs * sizeof(float)), st, partial, n_rc, C, nvs, Cc, L, a.gn_w, a.wc, a.bc, redb,
+                                                                            dfilm, dfilm_b_stride, a.film_off, gstat));
     GW_LAUNCH_CHECK();
     if (sx) {
         int rcs = gn_bwd_apply_stream(a, B, gstat, d_raw, biasp, st);
         if (rcs != GW_OK) return rcs;
-        gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
-                                                           d_wc, d_bc, biasp, n_rc, d_conv_bias);
+        GW_CUDA(gw_launch_pdl(gn_bwd_param_kernel, dim3(gw_cdiv(C, 32)), dim3(1024), (size_t)(0), st, redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+                                                           d_wc, d_bc, biasp, n_rc, d_conv_bias));
         GW_LAUNCH_CHECK();
         return GW_OK;
     }
-    gn_bwd_param_kernel<<<gw_cdiv(C, 32), 1024, 0, st>>>(redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
-                                                       d_wc, d_bc, nullptr, 0, nullptr);
+    GW_CUDA(gw_launch_pdl(gn_bwd_param_kernel, dim3(gw_cdiv(C, 32)), dim3(1024), (size_t)(0), st, redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+                                                       d_wc, d_bc, nullptr, 0, nullptr));
     GW_LAUNCH_CHECK();
     // the apply pass reuses the partial region for the conv-bias partials ([B*n_rc, C] <= [B*n_rc, C*nvr])
-#define GNA_GO(CCV) gn_bwd_apply_kernel<T, FAST, CCV><<<grid, 256, sm2, st>>>(a, gstat, (T*)d_raw, partial)
+#define GNA_GO(CCV) GW_CUDA(gw_launch_pdl(gn_bwd_apply_kernel<T, FAST, CCV>, grid, dim3(256), (size_t)(sm2), st, a, gstat, (T*)d_raw, partial))
     if (FAST && stream_ok) {
         int rcs = gn_bwd_apply_stream(a, B, gstat, d_raw, partial, st);
         if (rcs != GW_OK) return rcs;
-    } else if (FAST && a.do_eps != nullptr) gn_bwd_apply_bf16_kernel<true><<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
-    else if (FAST) gn_bwd_apply_bf16_kernel<false><<<grid, 256, sm2, st>>>(a, gstat, (bf16*)d_raw, partial);
+    } else if (FAST && a.do_eps != nullptr) GW_CUDA(gw_launch_pdl(gn_bwd_apply_bf16_kernel<true>, grid, dim3(256), (size_t)(sm2), st, a, gstat, (bf16*)d_raw, partial));
+    else if (FAST) GW_CUDA(gw_launch_pdl(gn_bwd_apply_bf16_kernel<false>, grid, dim3(256), (size_t)(sm2), st, a, gstat, (bf16*)d_raw, partial));
     else if (Cc == 0) GNA_GO(0);
     else if (Cc == 1) GNA_GO(1);
     else if (Cc == 5) GNA_GO(5);
@@ -1017,6 +1037,8 @@ extern "C" int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int 
 // ------------------------------------------------------------------------------------------------
 // dgrad of Conv1d(k=3, pad=1) is the same conv with w'[ci][co][k] = w[co][ci][2-k]  (run through gw_conv3_simt)
 __global__ void __launch_bounds__(256) weight_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ wt) {
+    pdl_wait();
+    pdl_launch_dependents();
     const long n = (long)Cout * Cin * 3;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const int k = (int)(i % 3);
@@ -1030,7 +1052,7 @@ extern "C" int gw_weight_dgrad(const float* w, int Cout, int Cin, float* wt, voi
     const long n = (long)Cout * Cin * 3;
     int grid = (int)((n + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    weight_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, wt);
+    GW_CUDA(gw_launch_pdl(weight_dgrad_kernel, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, w, Cout, Cin, wt));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -1040,6 +1062,8 @@ extern "C" int gw_weight_dgrad(const float* w, int Cout, int Cin, float* wt, voi
 template <typename T>
 __global__ void __launch_bounds__(256) split_cat_grad_kernel(const T* __restrict__ d_cat, int L, int C0, int L0, int C1,
                                                              T* __restrict__ d_h, T* __restrict__ d_skip) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int Ct = C0 + C1;
     const int q0 = C0 / 4, q1 = C1 / 4;
@@ -1073,9 +1097,9 @@ extern "C" int gw_split_cat_grad(const void* d_cat, int B, int L, int C0, int L0
     if (gx > 1024) gx = 1024;
     dim3 grid(gx, B);
     if (dtype == GW_F32)
-        split_cat_grad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)d_cat, L, C0, L0, C1, (float*)d_h, (float*)d_skip);
+        GW_CUDA(gw_launch_pdl(split_cat_grad_kernel<float>, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, (const float*)d_cat, L, C0, L0, C1, (float*)d_h, (float*)d_skip));
     else
-        split_cat_grad_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)d_cat, L, C0, L0, C1, (bf16*)d_h, (bf16*)d_skip);
+        GW_CUDA(gw_launch_pdl(split_cat_grad_kernel<bf16>, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)d_cat, L, C0, L0, C1, (bf16*)d_h, (bf16*)d_skip));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -1088,6 +1112,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) wgrad3_simt_kernel(const T* __restrict__ src0, int C0, int L0, int up0,
                                                           const T* __restrict__ src1, int C1, const T* __restrict__ d_raw, int B,
                                                           int L, int Cout, float* __restrict__ partial) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int KP = 32;
     __shared__ __align__(16) float dy[KP][64];
     __shared__ __align__(16) float xs[KP + 2][64];
@@ -1173,9 +1199,9 @@ extern "C" int gw_wgrad3_simt(const void* src0, int C0, int L0, int up0, const v
     dim3 grid(Cin / 64, Cout / 64, (unsigned)n_split);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32)
-        wgrad3_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)src0, C0, L0, up0, (const float*)src1, C1, (const float*)d_raw, B, L, Cout, scratch);
+        GW_CUDA(gw_launch_pdl(wgrad3_simt_kernel<float>, grid, dim3(256), (size_t)(0), st, (const float*)src0, C0, L0, up0, (const float*)src1, C1, (const float*)d_raw, B, L, Cout, scratch));
     else
-        wgrad3_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src0, C0, L0, up0, (const bf16*)src1, C1, (const bf16*)d_raw, B, L, Cout, scratch);
+        GW_CUDA(gw_launch_pdl(wgrad3_simt_kernel<bf16>, grid, dim3(256), (size_t)(0), st, (const bf16*)src0, C0, L0, up0, (const bf16*)src1, C1, (const bf16*)d_raw, B, L, Cout, scratch));
     GW_LAUNCH_CHECK();
     return reduce_rows(scratch, (int)n_split, per, per, 1.0f, dW, 1, st);
 }
@@ -1198,6 +1224,8 @@ __device__ __forceinline__ void ld2f(const bf16* p, float (&v)[2]) {
 template <typename T, int CXM>
 __global__ void __launch_bounds__(256) wgrad_in_kernel(const float* __restrict__ x, int Cx, int L, const T* __restrict__ d_raw,
                                                        int C, float* __restrict__ partial, int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float sm[];
     const int pitch = rows_per_cta + 8;           // multiple of 4: xs[ci][j] = x[r0 - 1 + j], float4-aligned at j % 4 == 0
     float* xs = sm;                               // [Cx][pitch]
@@ -1277,7 +1305,7 @@ extern "C" int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_r
 #define WIN_GO(TT, CXM)                                                                                               \
     do {                                                                                                              \
         GW_CUDA(cudaFuncSetAttribute(wgrad_in_kernel<TT, CXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        wgrad_in_kernel<TT, CXM><<<grid, 256, smem, st>>>(x, Cx, L, (const TT*)d_raw, C, scratch, rows);                \
+        GW_CUDA(gw_launch_pdl(wgrad_in_kernel<TT, CXM>, grid, dim3(256), (size_t)(smem), st, x, Cx, L, (const TT*)d_raw, C, scratch, rows));                \
     } while (0)
     if (dtype == GW_F32) {
         if (Cx <= 4) WIN_GO(float, 4); else if (Cx <= 8) WIN_GO(float, 8); else WIN_GO(float, 16);

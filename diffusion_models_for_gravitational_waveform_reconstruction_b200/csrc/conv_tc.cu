@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out,
                const __grid_constant__ TcParams P, const float* __restrict__ bias, float* __restrict__ part) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = P.stages;
@@ -271,6 +273,8 @@ __global__ void __launch_bounds__(320, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out,
                 const __grid_constant__ TcParams P, const float* __restrict__ bias, float* __restrict__ part) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int SA = P.sa, SB = P.sb, NBUF = P.nbuf, NACC = P.n_acc;
@@ -614,6 +618,8 @@ extern "C" int gw_conv_tc_n_part(const gw_conv_tc_shape* s) {
 // packed[(t*bn + n)][seg*64 + kk] = sum over taps in mask of w[co][ci0 + kk][tap]
 __global__ void conv_tc_pack_kernel(const __grid_constant__ TcParams P, const float* __restrict__ w, int cin,
                                     bf16* __restrict__ packed) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int t = blockIdx.z, s = blockIdx.y;
     const TcSeg sg = P.seg[t][s];
     const bool active = s < P.n_seg[t];
@@ -639,7 +645,7 @@ extern "C" int gw_conv_tc_pack(const gw_conv_tc_shape* s, const float* w, void* 
     int rc = build_params(s, &P);
     if (rc != GW_OK) return rc;
     dim3 grid(gw_cdiv(P.bn * 64, 256), P.k_total / 64, P.n_tiles);
-    conv_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P, w, s->C0 + s->C1, (bf16*)packed);
+    GW_CUDA(gw_launch_pdl(conv_tc_pack_kernel, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, P, w, s->C0 + s->C1, (bf16*)packed));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -737,7 +743,7 @@ extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const voi
 #define TC2_GO(LG)                                                                                                  \
     do {                                                                                                            \
         GW_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));       \
-        conv_tc2_kernel<LG><<<grid, 320, smem, st>>>(ta0, ta1, tw, to, P, bias, part);                               \
+        GW_CUDA(gw_launch_pdl(conv_tc2_kernel<LG>, grid, dim3(320), (size_t)(smem), st, ta0, ta1, tw, to, P, bias, part));                               \
     } while (0)
         if (cg == 8) TC2_GO(3);
         else if (cg == 16) TC2_GO(4);
@@ -761,7 +767,7 @@ extern "C" int gw_conv_tc(const gw_conv_tc_shape* s, const void* src0, const voi
 #define TC_GO(LG)                                                                                                   \
     do {                                                                                                            \
         GW_CUDA(cudaFuncSetAttribute(conv_tc_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));        \
-        conv_tc_kernel<LG><<<grid, 192, smem, st>>>(ta0, ta1, tw, to, P, bias, part);                                \
+        GW_CUDA(gw_launch_pdl(conv_tc_kernel<LG>, grid, dim3(192), (size_t)(smem), st, ta0, ta1, tw, to, P, bias, part));                                \
     } while (0)
     if (cg == 8) TC_GO(3);
     else if (cg == 16) TC_GO(4);

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256) film_kernel(const int64_t* __restrict__ t
                                                    const float* __restrict__ b1, const float* __restrict__ w2,
                                                    const float* __restrict__ b2, int base, int F, float* __restrict__ out,
                                                    float* __restrict__ aux) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float sm[];
     float* emb = sm;                         // [NB][time_dim]
     float* act = sm + FILM_NB * time_dim;    // [NB][base]
@@ -118,7 +120,7 @@ extern "C" int gw_film_vectors(const int64_t* t, int n, int time_dim, float max_
     const int nbx = gw_cdiv(n, FILM_NB);
     int f_split = nbx >= 296 ? 1 : gw_cdiv(296, nbx);                          // ~2 CTAs per SM
     if (f_split > gw_cdiv(F, 256)) f_split = gw_cdiv(F, 256);
-    film_kernel<<<dim3(nbx, f_split), 256, smem, (cudaStream_t)stream>>>(t, n, time_dim, den, coef, w1, b1, w2, b2, base, F, out, aux);
+    GW_CUDA(gw_launch_pdl(film_kernel, dim3(nbx, f_split), dim3(256), (size_t)(smem), (cudaStream_t)stream, t, n, time_dim, den, coef, w1, b1, w2, b2, base, F, out, aux));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -133,6 +135,8 @@ struct PyrArgs {
 
 __global__ void __launch_bounds__(256) cond_pyramid_kernel(const float* __restrict__ x, int B, int Cx, int L, int Cc,
                                                            PyrArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lvl = blockIdx.y;
     const int Lo = a.len[lvl];
     const long total = (long)B * Lo;
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(256) cond_pyramid_kernel(const float* __restri
 #define PYR_TILE 1024
 __global__ void __launch_bounds__(256) cond_pyramid_pow2_kernel(const float* __restrict__ x, int Cx, int L, int Cc, int n_levels,
                                                                 PyrArgs a) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) float xs[];          // [Cc][PYR_TILE]
     const int b = blockIdx.y, l0 = blockIdx.x * PYR_TILE;
     const float* xp = x + ((size_t)b * Cx + 1) * L + l0;
@@ -195,14 +201,14 @@ extern "C" int gw_cond_pyramid(const float* x, int B, int Cx, int L, int Cc, int
     for (int i = 0; i < n_levels; ++i) pow2 = pow2 && level_len[i] == (L >> i);
     if (pow2) {
         const size_t smem = (size_t)Cc * PYR_TILE * sizeof(float);
-        cond_pyramid_pow2_kernel<<<dim3(L / PYR_TILE, B), 256, smem, (cudaStream_t)stream>>>(x, Cx, L, Cc, n_levels, a);
+        GW_CUDA(gw_launch_pdl(cond_pyramid_pow2_kernel, dim3(L / PYR_TILE, B), dim3(256), (size_t)(smem), (cudaStream_t)stream, x, Cx, L, Cc, n_levels, a));
         GW_LAUNCH_CHECK();
         return GW_OK;
     }
     long total = (long)B * L;
     int gx = (int)((total + 255) / 256);
     if (gx > 148 * 16) gx = 148 * 16;
-    cond_pyramid_kernel<<<dim3(gx, n_levels), 256, 0, (cudaStream_t)stream>>>(x, B, Cx, L, Cc, a);
+    GW_CUDA(gw_launch_pdl(cond_pyramid_kernel, dim3(gx, n_levels), dim3(256), (size_t)(0), (cudaStream_t)stream, x, B, Cx, L, Cc, a));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -266,6 +272,8 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                                                       const int* __restrict__ step_ptr, int Cx, int L,
                                                       const float* __restrict__ w, const float* __restrict__ bias, int C,
                                                       T* __restrict__ raw, float* __restrict__ part, int n_part, ConvInApply ap) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int TP = 128, XP = CIN_NPB * TP + 8;   // XP: row pitch of xs (multiple of 4 -> float4-aligned groups)
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l00 - 1 + j]
@@ -481,6 +489,8 @@ __global__ void __launch_bounds__(256) conv_in_mma_kernel(const float* __restric
                                                           const int* __restrict__ step_ptr, int Cx, int L,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           bf16* __restrict__ raw, float* __restrict__ part, int n_part) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int C = 64, TP = 128, XP = CIN_NPB * TP + 8;
     extern __shared__ __align__(16) float sm[];
     float* xs = sm;                              // [Cx][XP]: xs[c][j] = x[c][l00 - 4 + j] (16-byte aligned body at j = 4)
@@ -626,7 +636,7 @@ static int conv_in_launch(const float* x, const float* x_alt, const int* step_pt
     size_t smem = (size_t)(Cx * XP + Cx * 3 * C + C + (C / 8) * 8 * 2 + (MODE == 2 ? (4 + CIN_MAX_CC) * C : 0)) * sizeof(float);
     dim3 grid(gw_cdiv(L, CIN_NPB * TP), B);
     GW_CUDA(cudaFuncSetAttribute(conv_in_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_in_kernel<T, MODE><<<grid, 256, smem, st>>>(x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, C, (T*)raw, part, n_part, ap);
+    GW_CUDA(gw_launch_pdl(conv_in_kernel<T, MODE>, grid, dim3(256), (size_t)(smem), st, x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, C, (T*)raw, part, n_part, ap));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -642,8 +652,8 @@ extern "C" int gw_conv_in(const float* x, const float* x_alt, const int* step_pt
         const size_t smem = (size_t)(Cx * XP + KS * 512 + C + 128) * sizeof(float);
         dim3 grid(gw_cdiv(L, CIN_NPB * TP), B);
         GW_CUDA(cudaFuncSetAttribute(conv_in_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_in_mma_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, (bf16*)raw, part,
-                                                                     n_part);
+        GW_CUDA(gw_launch_pdl(conv_in_mma_kernel, grid, dim3(256), (size_t)(smem), (cudaStream_t)stream, x, x_alt ? x_alt : x, step_ptr, Cx, L, w, bias, (bf16*)raw, part,
+                                                                     n_part));
         GW_LAUNCH_CHECK();
         return GW_OK;
     }
@@ -686,6 +696,8 @@ __global__ void __launch_bounds__(256) conv3_simt_kernel(const T* __restrict__ s
                                                          const float* __restrict__ w3, const float* __restrict__ bias,
                                                          int Cout, T* __restrict__ raw, float* __restrict__ part,
                                                          int n_part) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int TP = 64, TN = 64, KC = 16;
     __shared__ __align__(16) float xs[(TP + 2) * KC];
     __shared__ __align__(16) float ws[3 * KC * TN];
@@ -790,11 +802,11 @@ extern "C" int gw_conv3_simt(const void* src0, int C0, int L0, int up0, const vo
     dim3 grid(n_part, Cout / 64, B);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == GW_F32)
-        conv3_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)src0, C0, L0, up0, (const float*)src1, C1, L, w3, bias,
-                                                        Cout, (float*)raw, part, n_part);
+        GW_CUDA(gw_launch_pdl(conv3_simt_kernel<float>, grid, dim3(256), (size_t)(0), st, (const float*)src0, C0, L0, up0, (const float*)src1, C1, L, w3, bias,
+                                                        Cout, (float*)raw, part, n_part));
     else
-        conv3_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src0, C0, L0, up0, (const bf16*)src1, C1, L, w3, bias,
-                                                       Cout, (bf16*)raw, part, n_part);
+        GW_CUDA(gw_launch_pdl(conv3_simt_kernel<bf16>, grid, dim3(256), (size_t)(0), st, (const bf16*)src0, C0, L0, up0, (const bf16*)src1, C1, L, w3, bias,
+                                                       Cout, (bf16*)raw, part, n_part));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -833,6 +845,8 @@ gn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ part, int n
                 const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ film, int film_off,
                 long film_b_stride, long film_step_stride, const int* __restrict__ step_ptr, T* __restrict__ out,
                 T* __restrict__ pooled, float* __restrict__ stats_out, int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : GN_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     constexpr int UN = (FAST && (CC == 0 || CC == 1)) ? 4 : 2;
@@ -966,6 +980,8 @@ gn_apply_bf16_kernel(const bf16* __restrict__ raw, const float* __restrict__ par
                      const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ film, int film_off,
                      long film_b_stride, long film_step_stride, const int* __restrict__ step_ptr, bf16* __restrict__ out,
                      bf16* __restrict__ pooled, float* __restrict__ stats_out, int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : GN_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     constexpr int UN = (CC == 0 || CC == 1) ? 4 : 2;
@@ -1106,9 +1122,9 @@ static int gn_apply_launch(dim3 grid, cudaStream_t st, const void* raw, const fl
                            const float* bc, const float* film, int film_off, long fbs, long fss, const int* step_ptr,
                            void* out, void* pooled, float* stats_out, int rows) {
 #define GN_GO(CCV)                                                                                                     \
-    gn_apply_kernel<T, FAST, CCV><<<grid, 256, 0, st>>>((const T*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
+    GW_CUDA(gw_launch_pdl(gn_apply_kernel<T, FAST, CCV>, grid, dim3(256), (size_t)(0), st, (const T*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
                                                         film, film_off, fbs, fss, step_ptr, (T*)out, (T*)pooled,        \
-                                                        stats_out, rows)
+                                                        stats_out, rows))
     if (Cc == 0) GN_GO(0);
     else if (Cc == 1) GN_GO(1);
     else if (Cc == 5) GN_GO(5);
@@ -1136,9 +1152,9 @@ extern "C" int gw_gn_apply(const void* raw, const float* part, int n_part, int B
         return gn_apply_launch<float, false>(grid, st, raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film, film_off,
                                              film_b_stride, film_step_stride, step_ptr, out, pooled, stats_out, rows);
 #define GNB_GO(CCV)                                                                                                         \
-    gn_apply_bf16_kernel<CCV><<<grid, 256, 0, st>>>((const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film,   \
+    GW_CUDA(gw_launch_pdl(gn_apply_bf16_kernel<CCV>, grid, dim3(256), (size_t)(0), st, (const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, film,   \
                                                     film_off, film_b_stride, film_step_stride, step_ptr, (bf16*)out,            \
-                                                    (bf16*)pooled, stats_out, rows)
+                                                    (bf16*)pooled, stats_out, rows))
     if (Cc == 0) GNB_GO(0);
     else if (Cc == 1) GNB_GO(1);
     else if (Cc == 5) GNB_GO(5);
@@ -1172,6 +1188,8 @@ __global__ void __launch_bounds__(256) final_step_kernel(const T* __restrict__ h
                                                          StepArgs p, const float* __restrict__ coef,
                                                          const int* __restrict__ step_ptr, const float* __restrict__ noise,
                                                          float* __restrict__ eps_out, float* __restrict__ x0_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float pd[2][3][FS_ROWS];           // [half][tap][row] partial dots
     const int b = blockIdx.y, l0 = blockIdx.x * FS_TP;
     const int step = step_ptr != nullptr ? *step_ptr : 0;
@@ -1336,20 +1354,22 @@ extern "C" int gw_final_step(const void* h, int dtype, const float* net_a, const
         return final_step_stream(h, net_a, net_b, B, Cx, L, wf, bf, p, coef, step_ptr, noise, eps_out, x0_out, st);
     dim3 grid(gw_cdiv(L, FS_TP), B);
     if (dtype == GW_F32)
-        final_step_kernel<float><<<grid, 256, 0, st>>>((const float*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
-                                                       coef, step_ptr, noise, eps_out, x0_out);
+        GW_CUDA(gw_launch_pdl(final_step_kernel<float>, grid, dim3(256), (size_t)(0), st, (const float*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
+                                                       coef, step_ptr, noise, eps_out, x0_out));
     else
-        final_step_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
-                                                      coef, step_ptr, noise, eps_out, x0_out);
+        GW_CUDA(gw_launch_pdl(final_step_kernel<bf16>, grid, dim3(256), (size_t)(0), st, (const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, C, wf, bf, a,
+                                                      coef, step_ptr, noise, eps_out, x0_out));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
 
 __global__ void step_advance_kernel(int* p, int set_value) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x == 0 && blockIdx.x == 0) *p = set_value >= 0 ? set_value : *p + 1;
 }
 extern "C" int gw_step_advance(int* step_ptr, int set_value, void* stream) {
-    step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_ptr, set_value);
+    GW_CUDA(gw_launch_pdl(step_advance_kernel, dim3(1), dim3(32), (size_t)(0), (cudaStream_t)stream, step_ptr, set_value));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -1359,6 +1379,8 @@ extern "C" int gw_step_advance(int* step_ptr, int set_value, void* stream) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) philox_normal_kernel(unsigned long long seed, long sample0, unsigned step, int L,
                                                             float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (l4 >= L) return;
@@ -1370,7 +1392,7 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(unsigned long long s
 }
 extern "C" int gw_philox_normal(unsigned long long seed, long sample0, unsigned step, int B, int L, float* out, void* stream) {
     GW_REQUIRE(B > 0 && L > 0 && out != nullptr, "gw_philox_normal: sizes");
-    philox_normal_kernel<<<dim3(gw_cdiv(gw_cdiv(L, 4), 256), B), 256, 0, (cudaStream_t)stream>>>(seed, sample0, step, L, out);
+    GW_CUDA(gw_launch_pdl(philox_normal_kernel, dim3(gw_cdiv(gw_cdiv(L, 4), 256), B), dim3(256), (size_t)(0), (cudaStream_t)stream, seed, sample0, step, L, out));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -1383,6 +1405,8 @@ __global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__
                                                        float* __restrict__ eps, int philox, unsigned long long seed,
                                                        long sample0, unsigned step, float clampv, float* __restrict__ net,
                                                        int Cx, int L) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (l4 >= L) return;
@@ -1414,8 +1438,8 @@ extern "C" int gw_q_sample(const float* x0, const int64_t* t, const float* sqrt_
                            int B, int Cx, int L, void* stream) {
     GW_REQUIRE(B > 0 && L > 0 && Cx > 0, "gw_q_sample: sizes");
     dim3 grid(gw_cdiv(gw_cdiv(L, 4), 256), B);
-    q_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, t, sqrt_ab, sqrt_1mab, eps, philox, seed, sample0, step, clampv,
-                                                            net, Cx, L);
+    GW_CUDA(gw_launch_pdl(q_sample_kernel, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, x0, t, sqrt_ab, sqrt_1mab, eps, philox, seed, sample0, step, clampv,
+                                                            net, Cx, L));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

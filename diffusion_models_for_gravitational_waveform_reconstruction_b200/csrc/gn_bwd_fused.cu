@@ -60,6 +60,8 @@ template <int CC>      // cond channels: 0, 1, 5, or -1 (any <= 8)
 __global__ void __launch_bounds__(256, 4) gn_bwd_fused_kernel(const GnBwdArgs a, const GbfPlan pl, int B, int n_groups,
                                                               float* __restrict__ partial, float* __restrict__ partial_bias,
                                                               bf16* __restrict__ d_raw, void* sync) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : GBF_MAX_CC;
     constexpr int NV = 4 + NC;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -310,8 +312,8 @@ int gn_bwd_fused(const GnBwdArgs& a, int B, float* partial, float* partial_bias,
         int n_groups = occ * gbf_sm_count() / pl.G;                                                                       \
         if (n_groups > B) n_groups = B;                                                                                   \
         if (n_groups < 1) return GW_ERR_UNSUPPORTED;                                                                      \
-        gn_bwd_fused_kernel<CCV><<<pl.G * n_groups, 256, pl.smem, st>>>(a, pl, B, n_groups, partial, partial_bias,        \
-                                                                         (bf16*)d_raw, sync);                             \
+        GW_CUDA(gw_launch_pdl(gn_bwd_fused_kernel<CCV>, pl.G * n_groups, dim3(256), (size_t)(pl.smem), st, a, pl, B, n_groups, partial, partial_bias,        \
+                                                                         (bf16*)d_raw, sync));                             \
     } while (0)
     if (Cc == 0) GBF_GO(0);
     else if (Cc == 1) GBF_GO(1);

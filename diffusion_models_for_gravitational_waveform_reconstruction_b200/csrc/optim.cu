@@ -10,6 +10,8 @@
 // ------------------------------------------------------------------------------------------------
 __global__ void train_draws_kernel(unsigned long long seed, const int* __restrict__ step_ptr, long sample0, int B, int t_min,
                                    int T, float p_uncond, int64_t* __restrict__ t_out, float* __restrict__ drop_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const uint32_t step = (uint32_t)(step_ptr ? *step_ptr : 0);
@@ -23,7 +25,7 @@ __global__ void train_draws_kernel(unsigned long long seed, const int* __restric
 extern "C" int gw_train_draws(unsigned long long seed, const int* step_ptr, long sample0, int B, int t_min, int T,
                               float p_uncond, int64_t* t_out, float* drop_out, void* stream) {
     GW_REQUIRE(B > 0 && T > t_min && t_min >= 0, "gw_train_draws: B=%d t_min=%d T=%d", B, t_min, T);
-    train_draws_kernel<<<gw_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(seed, step_ptr, sample0, B, t_min, T, p_uncond, t_out, drop_out);
+    GW_CUDA(gw_launch_pdl(train_draws_kernel, dim3(gw_cdiv(B, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, seed, step_ptr, sample0, B, t_min, T, p_uncond, t_out, drop_out));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) train_pack_kernel(const float* __restrict
                                                          float* __restrict__ eps, int philox, unsigned long long seed,
                                                          long sample0, const int* __restrict__ step_ptr, float clampv,
                                                          int clamp_y, int drop_all, float* __restrict__ net, int Cx, int L) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (l4 >= L) return;
@@ -123,8 +127,8 @@ extern "C" int gw_train_pack(const float* clean, const float* cond, int Cc, cons
                              int L, void* stream) {
     GW_REQUIRE(B > 0 && L > 0 && Cx >= 1 + Cc && Cc >= 0, "gw_train_pack: sizes B=%d L=%d Cx=%d Cc=%d", B, L, Cx, Cc);
     dim3 grid(gw_cdiv(gw_cdiv(L, 4), 256), B);
-    train_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(clean, cond, Cc, t, drop, sqrt_ab, sqrt_1mab, eps, philox, seed, sample0,
-                                                              step_ptr, clampv, clamp_y, drop_all, net, Cx, L);
+    GW_CUDA(gw_launch_pdl(train_pack_kernel, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, clean, cond, Cc, t, drop, sqrt_ab, sqrt_1mab, eps, philox, seed, sample0,
+                                                              step_ptr, clampv, clamp_y, drop_all, net, Cx, L));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -136,6 +140,8 @@ __global__ void __launch_bounds__(256) batch_prepare_kernel(const float* __restr
                                                             const float* __restrict__ meta, int Cm, int L, int K,
                                                             float* __restrict__ clean_out, float* __restrict__ cond_out,
                                                             float* __restrict__ mask_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
@@ -156,8 +162,8 @@ extern "C" int gw_batch_prepare(const float* clean_raw, const float* noisy_raw, 
                                 void* stream) {
     GW_REQUIRE(clean_raw && noisy_raw && sigma && clean_out && cond_out && mask_out, "gw_batch_prepare: null pointer");
     GW_REQUIRE(B0 > 0 && L > 0 && K >= 1 && Cm >= 0 && (Cm == 0 || meta != nullptr), "gw_batch_prepare: sizes");
-    batch_prepare_kernel<<<dim3(gw_cdiv(L, 256), B0), 256, 0, (cudaStream_t)stream>>>(clean_raw, noisy_raw, sigma, mask, meta, Cm, L, K,
-                                                                                  clean_out, cond_out, mask_out);
+    GW_CUDA(gw_launch_pdl(batch_prepare_kernel, dim3(gw_cdiv(L, 256), B0), dim3(256), (size_t)(0), (cudaStream_t)stream, clean_raw, noisy_raw, sigma, mask, meta, Cm, L, K,
+                                                                                  clean_out, cond_out, mask_out));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -166,6 +172,8 @@ extern "C" int gw_batch_prepare(const float* clean_raw, const float* noisy_raw, 
 // (train.py:40-51, 404-407).  ab = alpha_bar table (NOT clamped, as in train.py:49).
 __global__ void __launch_bounds__(256) selfcond_kernel(float* __restrict__ net, const float* __restrict__ eps_hat,
                                                        const int64_t* __restrict__ t, const float* __restrict__ ab, int Cx, int L) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y;
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(256) selfcond_kernel(float* __restrict__ net, 
 extern "C" int gw_selfcond_x0(float* net, const float* eps_hat, const int64_t* t, const float* alpha_bar, int B, int Cx, int L,
                               void* stream) {
     GW_REQUIRE(B > 0 && L > 0 && Cx >= 2, "gw_selfcond_x0: sizes");
-    selfcond_kernel<<<dim3(gw_cdiv(L, 256), B), 256, 0, (cudaStream_t)stream>>>(net, eps_hat, t, alpha_bar, Cx, L);
+    GW_CUDA(gw_launch_pdl(selfcond_kernel, dim3(gw_cdiv(L, 256), B), dim3(256), (size_t)(0), (cudaStream_t)stream, net, eps_hat, t, alpha_bar, Cx, L));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -195,6 +203,8 @@ __device__ __forceinline__ float dsilu(float x) {
 __global__ void __launch_bounds__(1024) film_bwd_w2_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux, int B,
                                                            int td, int base, int F, float* __restrict__ dW2,
                                                            float* __restrict__ db2) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float red[];                   // [BL][4][base]
     __shared__ float redb[FILM_BL][4];
     const int jl = threadIdx.x, fl = threadIdx.y, bl = threadIdx.z;
@@ -234,6 +244,8 @@ __global__ void __launch_bounds__(1024) film_bwd_w2_kernel(const float* __restri
 __global__ void __launch_bounds__(1024) film_bwd_act_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux,
                                                             const float* __restrict__ w2, int td, int base, int F,
                                                             float* __restrict__ dpre) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float sm[];           // [n_part][base]
     const int b = blockIdx.x;
     const int j = threadIdx.x % base, part = threadIdx.x / base, n_part = blockDim.x / base;
@@ -252,6 +264,8 @@ __global__ void __launch_bounds__(1024) film_bwd_act_kernel(const float* __restr
 // grid base, block (128, 8): dW1[j, i] += sum_b dpre[b,j] emb[b,i] (i = il, il+128, ...); db1[j] += sum_b dpre[b,j]
 __global__ void __launch_bounds__(1024) film_bwd_w1_kernel(const float* __restrict__ dpre, const float* __restrict__ aux, int B,
                                                            int td, int base, float* __restrict__ dW1, float* __restrict__ db1) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ float sm[];           // [8][td] + [8]
     const int j = blockIdx.x, il = threadIdx.x, bl = threadIdx.y;
     const int na = td + 3 * base;
@@ -287,6 +301,8 @@ __global__ void __launch_bounds__(1024) film_bwd_w1_kernel(const float* __restri
 template <int BASE>
 __global__ void __launch_bounds__(256) film_bwd_w2_tiled_kernel(const float* __restrict__ dfilm, const float* __restrict__ aux, int B,
                                                                 int td, int F, float* __restrict__ dW2, float* __restrict__ db2) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int FG = 256 / BASE, NF = 32 / FG;
     __shared__ float df_s[32][33];
     __shared__ float act_s[32][BASE];
@@ -331,6 +347,8 @@ __global__ void __launch_bounds__(256) film_bwd_w2_tiled_kernel(const float* __r
 template <int BASE>
 __global__ void __launch_bounds__(256) film_bwd_act_split_kernel(const float* __restrict__ dfilm, const float* __restrict__ w2, int B,
                                                                  int F, float* __restrict__ partial) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int SG = 256 / BASE, NS = 8 / SG;          // sample groups, samples per thread
     __shared__ float df_s[8][FILM_FS];
     const int b0 = blockIdx.x * 8, ks = blockIdx.y, fs0 = ks * FILM_FS, tid = threadIdx.x;
@@ -357,6 +375,8 @@ __global__ void __launch_bounds__(256) film_bwd_act_split_kernel(const float* __
 // dpre[b, j] = (sum_ks partial[ks, b, j]) * silu'(ctx) * silu'(pre)
 __global__ void film_bwd_act_fold_kernel(const float* __restrict__ partial, int n_split, int B, const float* __restrict__ aux,
                                          int td, int base, float* __restrict__ dpre) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * base) return;
     const int b = i / base, j = i % base;
@@ -375,25 +395,25 @@ extern "C" int gw_film_bwd(const float* dfilm, const float* aux, const float* w2
     if (base == 64 || base == 128) {
         float* partial = scratch + (size_t)B * base;               // [n_split, B, base] behind dpre [B, base]
         if (base == 64) {
-            film_bwd_w2_tiled_kernel<64><<<gw_cdiv(F, 32), 256, 0, st>>>(dfilm, aux, B, time_dim, F, dW2, db2);
-            film_bwd_act_split_kernel<64><<<dim3(gw_cdiv(B, 8), n_split), 256, 0, st>>>(dfilm, w2, B, F, partial);
+            GW_CUDA(gw_launch_pdl(film_bwd_w2_tiled_kernel<64>, dim3(gw_cdiv(F, 32)), dim3(256), (size_t)(0), st, dfilm, aux, B, time_dim, F, dW2, db2));
+            GW_CUDA(gw_launch_pdl(film_bwd_act_split_kernel<64>, dim3(gw_cdiv(B, 8), n_split), dim3(256), (size_t)(0), st, dfilm, w2, B, F, partial));
         } else {
-            film_bwd_w2_tiled_kernel<128><<<gw_cdiv(F, 32), 256, 0, st>>>(dfilm, aux, B, time_dim, F, dW2, db2);
-            film_bwd_act_split_kernel<128><<<dim3(gw_cdiv(B, 8), n_split), 256, 0, st>>>(dfilm, w2, B, F, partial);
+            GW_CUDA(gw_launch_pdl(film_bwd_w2_tiled_kernel<128>, dim3(gw_cdiv(F, 32)), dim3(256), (size_t)(0), st, dfilm, aux, B, time_dim, F, dW2, db2));
+            GW_CUDA(gw_launch_pdl(film_bwd_act_split_kernel<128>, dim3(gw_cdiv(B, 8), n_split), dim3(256), (size_t)(0), st, dfilm, w2, B, F, partial));
         }
         GW_LAUNCH_CHECK();
-        film_bwd_act_fold_kernel<<<gw_cdiv(B * base, 256), 256, 0, st>>>(partial, n_split, B, aux, time_dim, base, scratch);
+        GW_CUDA(gw_launch_pdl(film_bwd_act_fold_kernel, dim3(gw_cdiv(B * base, 256)), dim3(256), (size_t)(0), st, partial, n_split, B, aux, time_dim, base, scratch));
         GW_LAUNCH_CHECK();
-        film_bwd_w1_kernel<<<base, dim3(128, 8), (size_t)(8 * time_dim + 8) * sizeof(float), st>>>(scratch, aux, B, time_dim, base, dW1, db1);
+        GW_CUDA(gw_launch_pdl(film_bwd_w1_kernel, dim3(base), dim3(128, 8), (size_t)((size_t)(8 * time_dim + 8) * sizeof(float)), st, scratch, aux, B, time_dim, base, dW1, db1));
         GW_LAUNCH_CHECK();
         return GW_OK;
     }
-    film_bwd_w2_kernel<<<gw_cdiv(F, 4), dim3(64, 4, FILM_BL), (size_t)FILM_BL * 4 * base * sizeof(float), st>>>(dfilm, aux, B, time_dim,
-                                                                                                          base, F, dW2, db2);
+    GW_CUDA(gw_launch_pdl(film_bwd_w2_kernel, dim3(gw_cdiv(F, 4)), dim3(64, 4, FILM_BL), (size_t)((size_t)FILM_BL * 4 * base * sizeof(float)), st, dfilm, aux, B, time_dim,
+                                                                                                          base, F, dW2, db2));
     GW_LAUNCH_CHECK();
-    film_bwd_act_kernel<<<B, 1024, (size_t)1024 * sizeof(float), st>>>(dfilm, aux, w2, time_dim, base, F, scratch);
+    GW_CUDA(gw_launch_pdl(film_bwd_act_kernel, dim3(B), dim3(1024), (size_t)((size_t)1024 * sizeof(float)), st, dfilm, aux, w2, time_dim, base, F, scratch));
     GW_LAUNCH_CHECK();
-    film_bwd_w1_kernel<<<base, dim3(128, 8), (size_t)(8 * time_dim + 8) * sizeof(float), st>>>(scratch, aux, B, time_dim, base, dW1, db1);
+    GW_CUDA(gw_launch_pdl(film_bwd_w1_kernel, dim3(base), dim3(128, 8), (size_t)((size_t)(8 * time_dim + 8) * sizeof(float)), st, scratch, aux, B, time_dim, base, dW1, db1));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -402,6 +422,8 @@ extern "C" int gw_film_bwd(const float* dfilm, const float* aux, const float* w2
 // clip_grad_norm_ + AdamW + EMA over flat buffers
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, double* __restrict__ partial) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ double red[8];
     double a = 0.0;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -439,6 +461,8 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
                                                         const float* __restrict__ hyper, const float* __restrict__ loss,
                                                         int g_has_loss, const int* __restrict__ state, double beta1d,
                                                         double beta2d, float eps, float* __restrict__ info) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float s_coef, s_lr, s_bc1, s_bc2s;
     __shared__ int s_ok;
     if (threadIdx.x < 32) {
@@ -500,7 +524,7 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
 extern "C" int gw_opt_scratch_doubles(void) { return OPT_PARTIALS; }
 extern "C" int gw_grad_sumsq(const float* g, long n, double* partial, void* stream) {
     GW_REQUIRE(n > 0, "gw_grad_sumsq: n");
-    sumsq_kernel<<<OPT_PARTIALS, 256, 0, (cudaStream_t)stream>>>(g, n, partial);
+    GW_CUDA(gw_launch_pdl(sumsq_kernel, dim3(OPT_PARTIALS), dim3(256), (size_t)(0), (cudaStream_t)stream, g, n, partial));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -510,8 +534,8 @@ extern "C" int gw_adamw_ema(float* p, const float* g, float* m, float* v, float*
     GW_REQUIRE(n > 0 && hyper != nullptr && info != nullptr && partial != nullptr, "gw_adamw_ema: arguments");
     int grid = (int)((n + 1023) / 1024);
     if (grid > 148 * 4) grid = 148 * 4;
-    adamw_ema_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, partial, OPT_PARTIALS, hyper, loss, g_has_loss, state,
-                                                             beta1, beta2, eps, info);
+    GW_CUDA(gw_launch_pdl(adamw_ema_kernel, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, p, g, m, v, ema, n, partial, OPT_PARTIALS, hyper, loss, g_has_loss, state,
+                                                             beta1, beta2, eps, info));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -520,6 +544,8 @@ extern "C" int gw_adamw_ema(float* p, const float* g, float* m, float* v, float*
 // batch loss through the all-reduce
 __global__ void __launch_bounds__(256) bucket_reset_kernel(float4* __restrict__ g4, long n4, float* __restrict__ g, long n,
                                                            const float* __restrict__ loss) {
+    pdl_wait();
+    pdl_launch_dependents();
     const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) g4[i] = z;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -532,7 +558,7 @@ extern "C" int gw_bucket_reset(float* g, long n, const float* loss, void* stream
     int grid = (int)((n / 4 + 255) / 256);
     if (grid > 148 * 2) grid = 148 * 2;
     if (grid < 1) grid = 1;
-    bucket_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(g), n / 4, g, n, loss);
+    GW_CUDA(gw_launch_pdl(bucket_reset_kernel, grid, dim3(256), (size_t)(0), (cudaStream_t)stream, reinterpret_cast<float4*>(g), n / 4, g, n, loss));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
@@ -540,6 +566,8 @@ extern "C" int gw_bucket_reset(float* g, long n, const float* loss, void* stream
 // end of an optimisation step: the Philox draw counter always advances (the reference consumes its RNG on skipped batches
 // too), the applied-step counter only when gw_adamw_ema applied the update (info[2])
 __global__ void train_advance_kernel(int* step_ctr, int* state, const float* info) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (step_ctr != nullptr) *step_ctr += 1;
         if (state != nullptr) {
@@ -549,19 +577,21 @@ __global__ void train_advance_kernel(int* step_ctr, int* state, const float* inf
     }
 }
 extern "C" int gw_train_advance(int* step_ctr, int* state, const float* info, void* stream) {
-    train_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_ctr, state, info);
+    GW_CUDA(gw_launch_pdl(train_advance_kernel, dim3(1), dim3(32), (size_t)(0), (cudaStream_t)stream, step_ctr, state, info));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }
 
 // loss weight (train.py:414-417): wt[b] = (1 - alpha_bar[t_b])^power
 __global__ void loss_weight_kernel(const long long* __restrict__ t, const float* __restrict__ ab, float power, float* __restrict__ wt, int B) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) wt[b] = powf(1.0f - ab[t[b]], power);
 }
 extern "C" int gw_loss_weight(const int64_t* t, const float* alpha_bar, float power, float* wt, int B, void* stream) {
     GW_REQUIRE(t != nullptr && alpha_bar != nullptr && wt != nullptr && B > 0, "gw_loss_weight: arguments");
-    loss_weight_kernel<<<gw_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>((const long long*)t, alpha_bar, power, wt, B);
+    GW_CUDA(gw_launch_pdl(loss_weight_kernel, dim3(gw_cdiv(B, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, (const long long*)t, alpha_bar, power, wt, B));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

@@ -25,6 +25,8 @@ gn_apply_stream_kernel(const bf16* __restrict__ raw, const float* __restrict__ p
                        const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ film, int film_off,
                        long film_b_stride, long film_step_stride, const int* __restrict__ step_ptr, bf16* __restrict__ out,
                        bf16* __restrict__ pooled, float* __restrict__ stats_out, int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : SG_MAX_CC;
     constexpr int NCA = NC > 0 ? NC : 1;
     const int Cc = CC >= 0 ? CC : Cc_rt;
@@ -220,9 +222,9 @@ extern "C" int gw_gn_apply_stream(const void* raw, const float* part, int n_part
     do {                                                                                                                   \
         GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         GW_CUDA(cudaFuncSetAttribute(gn_apply_stream_kernel<CCV, CV>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));   \
-        gn_apply_stream_kernel<CCV, CV><<<grid, 256, smem, st>>>((const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
+        GW_CUDA(gw_launch_pdl(gn_apply_stream_kernel<CCV, CV>, grid, dim3(256), (size_t)(smem), st, (const bf16*)raw, part, n_part, L, C, gn_w, gn_b, cond, Cc, wc, bc, \
                                                              film, film_off, film_b_stride, film_step_stride, step_ptr,        \
-                                                             (bf16*)out, (bf16*)pooled, stats_out, rows);                      \
+                                                             (bf16*)out, (bf16*)pooled, stats_out, rows));                      \
     } while (0)
 #define SGA_C(CCV)                          \
     do {                                    \
@@ -306,6 +308,8 @@ struct SgBwdStream {
 
 template <int CC, bool HEAD>
 __global__ void __launch_bounds__(256, 3) gn_bwd_stats_stream_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int NC = CC >= 0 ? CC : SG_MAX_CC;
     constexpr int NV = 4 + NC;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -446,6 +450,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_stats_stream_kernel(GnBwdArgs a
 // from the CTA's slice of d_eps in shared memory -- the [B, L, 64] d_h tensor is neither written by gw_final_bwd nor read here.
 template <int C, int CC, bool POOL, bool HEAD = false>
 __global__ void __launch_bounds__(256, 3) gn_bwd_stats_fast_kernel(GnBwdArgs a, float* __restrict__ partial, int depth) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int S = SG_STAGE_BYTES / (C * 2);                       // rows per stage
     constexpr int NQ = C / 4, NTR = 256 / NQ, RPT = S / NTR;          // channel quads, row lanes, rows per thread and stage
     constexpr int NV = 4 + CC;                                        // [sum do, sum do*act, sum dn, sum dn*xhat, cond..]
@@ -598,6 +604,8 @@ template <bool HEAD>
 __global__ void __launch_bounds__(256, 3) gn_bwd_apply_stream_kernel(GnBwdArgs a, const float* __restrict__ gstat,
                                                                   bf16* __restrict__ d_raw, float* __restrict__ partial_bias,
                                                                   int depth) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(128) uint8_t smem[];
     const int b = blockIdx.y, C = a.C, L = a.L;
     const int S = SG_STAGE_BYTES / (C * 2);
@@ -737,6 +745,8 @@ template <int C, bool POOL, bool HEAD = false>
 __global__ void __launch_bounds__(256, 3) gn_bwd_apply_fast_kernel(GnBwdArgs a, const float* __restrict__ gstat,
                                                                 bf16* __restrict__ d_raw, float* __restrict__ partial_bias,
                                                                 int depth) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int S = SG_STAGE_BYTES / (C * 2);
     constexpr int NQ = C / 4, NTR = 256 / NQ, RPT = S / NTR;
     constexpr uint32_t OFF_DO = SG_STAGE_BYTES, OFF_POOL = 2 * SG_STAGE_BYTES;
@@ -906,7 +916,7 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     do {                                                                                                                    \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<64, CCV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<64, CCV, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
-        gn_bwd_stats_fast_kernel<64, CCV, false, true><<<grid, 256, smem, st>>>(a, partial, depth);                          \
+        GW_CUDA(gw_launch_pdl(gn_bwd_stats_fast_kernel<64, CCV, false, true>, grid, dim3(256), (size_t)(smem), st, a, partial, depth));                          \
     } while (0)
             if (Cc == 1) SGH_GO(1); else SGH_GO(5);
 #undef SGH_GO
@@ -917,7 +927,7 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     do {                                                                                                                    \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<CV, CCV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_fast_kernel<CV, CCV, PL>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
-        gn_bwd_stats_fast_kernel<CV, CCV, PL><<<grid, 256, smem, st>>>(a, partial, depth);                                   \
+        GW_CUDA(gw_launch_pdl(gn_bwd_stats_fast_kernel<CV, CCV, PL>, grid, dim3(256), (size_t)(smem), st, a, partial, depth));                                   \
     } while (0)
 #define SGF_C(CCV, PL)                        \
     do {                                      \
@@ -936,7 +946,7 @@ int gn_bwd_stats_stream(const GnBwdArgs& a, int B, float* partial, cudaStream_t 
     do {                                                                                                                    \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_stream_kernel<CCV, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_stats_stream_kernel<CCV, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
-        gn_bwd_stats_stream_kernel<CCV, HD><<<grid, 256, smem, st>>>(a, partial, depth);                                     \
+        GW_CUDA(gw_launch_pdl(gn_bwd_stats_stream_kernel<CCV, HD>, grid, dim3(256), (size_t)(smem), st, a, partial, depth));                                     \
     } while (0)
 #define SGS_CC(HD)                      \
     do {                                \
@@ -962,7 +972,7 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
         smem += (size_t)(a.rows_per_cta + 2) * sizeof(float) + 64;
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<64, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        gn_bwd_apply_fast_kernel<64, false, true><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
+        GW_CUDA(gw_launch_pdl(gn_bwd_apply_fast_kernel<64, false, true>, grid, dim3(256), (size_t)(smem), st, a, gstat, (bf16*)d_raw, partial_bias, depth));
         GW_LAUNCH_CHECK();
         return GW_OK;
     }
@@ -972,7 +982,7 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
     do {                                                                                                                    \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<CV, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_fast_kernel<CV, PL>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
-        gn_bwd_apply_fast_kernel<CV, PL><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);              \
+        GW_CUDA(gw_launch_pdl(gn_bwd_apply_fast_kernel<CV, PL>, grid, dim3(256), (size_t)(smem), st, a, gstat, (bf16*)d_raw, partial_bias, depth));              \
     } while (0)
         if (C == 64) { if (pool) SGA_GO(64, true); else SGA_GO(64, false); }
         else if (C == 128) { if (pool) SGA_GO(128, true); else SGA_GO(128, false); }
@@ -984,11 +994,11 @@ int gn_bwd_apply_stream(const GnBwdArgs& a, int B, const float* gstat, void* d_r
     if (a.do_eps != nullptr) {
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        gn_bwd_apply_stream_kernel<true><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
+        GW_CUDA(gw_launch_pdl(gn_bwd_apply_stream_kernel<true>, grid, dim3(256), (size_t)(smem), st, a, gstat, (bf16*)d_raw, partial_bias, depth));
     } else {
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(gn_bwd_apply_stream_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        gn_bwd_apply_stream_kernel<false><<<grid, 256, smem, st>>>(a, gstat, (bf16*)d_raw, partial_bias, depth);
+        GW_CUDA(gw_launch_pdl(gn_bwd_apply_stream_kernel<false>, grid, dim3(256), (size_t)(smem), st, a, gstat, (bf16*)d_raw, partial_bias, depth));
     }
     GW_LAUNCH_CHECK();
     return GW_OK;
@@ -1007,6 +1017,8 @@ __global__ void __launch_bounds__(256, 3) final_bwd_stream_kernel(const float* _
                                                                const float* __restrict__ net, int Cx, int L,
                                                                const float* __restrict__ wf, bf16* __restrict__ d_h,
                                                                float* __restrict__ partial, int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int C = 64, S = SG_STAGE_BYTES / (C * 2), D = 3, NQ = 16, NTR = 16, RPT = S / NTR, NV = C * 3 + 4;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;                                             // [D][8 KB]
@@ -1134,11 +1146,11 @@ int final_bwd_stream(const float* d_eps, const void* h, const float* net, int B,
     if (d_h != nullptr) {
         GW_CUDA(cudaFuncSetAttribute(final_bwd_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(final_bwd_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        final_bwd_stream_kernel<true><<<grid, 256, smem, st>>>(d_eps, (const bf16*)h, net, Cx, L, wf, (bf16*)d_h, partial, rows);
+        GW_CUDA(gw_launch_pdl(final_bwd_stream_kernel<true>, grid, dim3(256), (size_t)(smem), st, d_eps, (const bf16*)h, net, Cx, L, wf, (bf16*)d_h, partial, rows));
     } else {
         GW_CUDA(cudaFuncSetAttribute(final_bwd_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(final_bwd_stream_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        final_bwd_stream_kernel<false><<<grid, 256, smem, st>>>(d_eps, (const bf16*)h, net, Cx, L, wf, (bf16*)d_h, partial, rows);
+        GW_CUDA(gw_launch_pdl(final_bwd_stream_kernel<false>, grid, dim3(256), (size_t)(smem), st, d_eps, (const bf16*)h, net, Cx, L, wf, (bf16*)d_h, partial, rows));
     }
     GW_LAUNCH_CHECK();
     *n_cta = grid.x * grid.y;
@@ -1154,6 +1166,8 @@ template <int CXM>
 __global__ void __launch_bounds__(256) wgrad_in_stream_kernel(const float* __restrict__ x, int Cx, int L,
                                                               const bf16* __restrict__ d_raw, float* __restrict__ partial,
                                                               int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int C = 64, S = SG_STAGE_BYTES / (C * 2), D = SG_DEPTH;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;                                         // [D][8 KB]; reused for the final reduction
@@ -1246,6 +1260,8 @@ __global__ void __launch_bounds__(256) wgrad_in_stream_kernel(const float* __res
 // Warp w owns k-step (w & 3) of every 64-row stage and couts [32 (w >> 2), +32).
 __global__ void __launch_bounds__(256) wgrad_in_mma_kernel(const float* __restrict__ x, int Cx, int L, const bf16* __restrict__ d_raw,
                                                            float* __restrict__ partial, int rows_per_cta) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int C = 64, S = SG_STAGE_BYTES / (C * 2), D = SG_DEPTH;       // S = 64 rows per stage
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;                                         // [D][8 KB]; reused for the final reduction
@@ -1374,7 +1390,7 @@ int wgrad_in_stream(const float* x, int B, int Cx, int L, const void* d_raw, flo
     if (g_wgrad_in_mma && Cx <= 8 && L % 64 == 0 && rows % 64 == 0) {
         GW_CUDA(cudaFuncSetAttribute(wgrad_in_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(wgrad_in_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        wgrad_in_mma_kernel<<<grid, 256, smem, st>>>(x, Cx, L, (const bf16*)d_raw, scratch, rows);
+        GW_CUDA(gw_launch_pdl(wgrad_in_mma_kernel, grid, dim3(256), (size_t)(smem), st, x, Cx, L, (const bf16*)d_raw, scratch, rows));
         GW_LAUNCH_CHECK();
         *n_rows = B * n_rc;
         return GW_OK;
@@ -1383,7 +1399,7 @@ int wgrad_in_stream(const float* x, int B, int Cx, int L, const void* d_raw, flo
     do {                                                                                                              \
         GW_CUDA(cudaFuncSetAttribute(wgrad_in_stream_kernel<CXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         GW_CUDA(cudaFuncSetAttribute(wgrad_in_stream_kernel<CXM>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
-        wgrad_in_stream_kernel<CXM><<<grid, 256, smem, st>>>(x, Cx, L, (const bf16*)d_raw, scratch, rows);               \
+        GW_CUDA(gw_launch_pdl(wgrad_in_stream_kernel<CXM>, grid, dim3(256), (size_t)(smem), st, x, Cx, L, (const bf16*)d_raw, scratch, rows));               \
     } while (0)
     if (Cx <= 4) WIS_GO(4); else if (Cx <= 8) WIS_GO(8); else WIS_GO(16);
 #undef WIS_GO
@@ -1405,6 +1421,8 @@ __global__ void __launch_bounds__(256) final_step_stream_kernel(const bf16* __re
                                                                 FssArgs p, const float* __restrict__ coef,
                                                                 const int* __restrict__ step_ptr, const float* __restrict__ noise,
                                                                 float* __restrict__ eps_out, float* __restrict__ x0_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int C = 64, S = 64, D = SG_DEPTH, ROWS = FSS_TP + 2;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;                                           // [D][8 KB]
@@ -1537,6 +1555,8 @@ __global__ void __launch_bounds__(256) final_step_dots_kernel(const float4* __re
                                                               FssArgs p, const float* __restrict__ coef,
                                                               int* __restrict__ step_ptr, const float* __restrict__ noise,
                                                               float* __restrict__ eps_out, float* __restrict__ x0_out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.y, l4 = (blockIdx.x * 256 + threadIdx.x) * 4;
     pdl_wait();                                                       // the dots and the step counter come from the previous kernels
     pdl_launch_dependents();
@@ -1637,8 +1657,8 @@ int final_step_stream(const void* h, const float* net_a, const float* net_b, int
     GW_CUDA(cudaFuncSetAttribute(final_step_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GW_CUDA(cudaFuncSetAttribute(final_step_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     dim3 grid(gw_cdiv(L, FSS_TP), B);
-    final_step_stream_kernel<<<grid, 256, smem, st>>>((const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, wf, bf, a, coef, step_ptr,
-                                                      noise, eps_out, x0_out);
+    GW_CUDA(gw_launch_pdl(final_step_stream_kernel, grid, dim3(256), (size_t)(smem), st, (const bf16*)h, net_a, net_b ? net_b : net_a, B, Cx, L, wf, bf, a, coef, step_ptr,
+                                                      noise, eps_out, x0_out));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

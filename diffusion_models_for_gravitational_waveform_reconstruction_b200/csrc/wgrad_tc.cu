@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_x,
                 const __grid_constant__ WgParams P, float* __restrict__ partial, int shifted_desc, float* __restrict__ dW_atomic,
                 int mode, int Cout, int Cin_total, int ci_off) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int stages = P.stages;
@@ -214,6 +216,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 //   mode 1 (up/pair): A is the pair view [rows = L/2][2*Cout] of d_raw (lo = position 2r, hi = 2r+1) and X = h:
 //     dW[co][ci_off + n][0] += G_-1[lo] + G_0[hi];  [1] += G_0[lo] + G_0[hi];  [2] += G_0[lo] + G_+1[hi]
 __global__ void __launch_bounds__(256) wgrad_fold_kernel(float* __restrict__ partial, int n_split, long cols) {
+    pdl_wait();
+    pdl_launch_dependents();
     // block = 32 float4 columns x 8 split lanes; each lane streams its splits with 4 loads in flight
     __shared__ float4 red[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -243,6 +247,8 @@ __global__ void __launch_bounds__(256) wgrad_fold_kernel(float* __restrict__ par
 
 __global__ void __launch_bounds__(256) wgrad_scatter_kernel(const float* __restrict__ folded, WgParams P, int mode, int Cout,
                                                             int Cx, int Cin_total, int ci_off, float* __restrict__ dW) {
+    pdl_wait();
+    pdl_launch_dependents();
     const long n = (long)Cout * Cx;
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -352,15 +358,15 @@ extern "C" int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, in
     GW_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaStream_t st = (cudaStream_t)stream;
     const bool atomic = (variant & 2) != 0;
-    wgrad_tc_kernel<<<P.mt * P.nt * P.n_split, 192, smem, st>>>(ta, tx, P, scratch, shifted, atomic ? dW : nullptr, mode, Cout,
-                                                                 Cin_total, ci_off);
+    GW_CUDA(gw_launch_pdl(wgrad_tc_kernel, P.mt * P.nt * P.n_split, dim3(192), (size_t)(smem), st, ta, tx, P, scratch, shifted, atomic ? dW : nullptr, mode, Cout,
+                                                                 Cin_total, ci_off));
     GW_LAUNCH_CHECK();
     if (atomic) return GW_OK;
     const long cols = (long)P.mt * P.nt * 3 * 128 * P.bn;
-    wgrad_fold_kernel<<<(unsigned)((cols / 4 + 31) / 32), 256, 0, st>>>(scratch, P.n_split, cols);
+    GW_CUDA(gw_launch_pdl(wgrad_fold_kernel, dim3((unsigned)((cols / 4 + 31) / 32)), dim3(256), (size_t)(0), st, scratch, P.n_split, cols));
     GW_LAUNCH_CHECK();
     const long n = (long)Cout * Cx;
-    wgrad_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, P, mode, Cout, Cx, Cin_total, ci_off, dW);
+    GW_CUDA(gw_launch_pdl(wgrad_scatter_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, scratch, P, mode, Cout, Cx, Cin_total, ci_off, dW));
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

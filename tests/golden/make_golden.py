@@ -421,6 +421,30 @@ def gen_ingest(out):
     np.savez_compressed(os.path.join(out, "ingest.npz"), **rec)
 
 
+ARCH_CASES = [("b16_k5_d3", 16, 5, 3, 3, 1, 256), ("b8_k7_d2", 8, 7, 2, 7, 5, 250), ("b32_k1_d3", 32, 1, 3, 3, 1, 256)]
+
+
+def gen_arch(M, TR, out):
+    """Non-default UNet1D(base_ch, kernel, depth) (models.py:78-88) through the unmodified reference: eps_hat and every parameter
+    gradient of the reference loss (train.py:53-58), for pinning the oracle (and through it the generic CUDA kernels) there."""
+    rec = {}
+    for tag, base_ch, kernel, depth, in_ch, cc, L in ARCH_CASES:
+        model = M.UNet1D(in_ch=in_ch, base_ch=base_ch, depth=depth, kernel=kernel, cond_in_ch=cc, use_selfcond=True)
+        model.load_state_dict(make_state_dict(in_ch=in_ch, cond_in_ch=cc, base_ch=base_ch, depth=depth, kernel=kernel, seed=21),
+                              strict=True)
+        x = gaussian((2, in_ch, L), seed=200 + L + base_ch)
+        t = torch.tensor([24, 731])
+        target = gaussian((2, 1, L), seed=300 + base_ch)
+        eps = model(x, t)
+        loss = TR._element_loss(eps, target, torch.ones_like(target), "huber", 0.5).mean()
+        loss.backward()
+        rec[f"{tag}/eps"] = eps.detach().numpy()
+        rec[f"{tag}/loss"] = np.float64(loss.item())
+        for k, p_ in model.named_parameters():
+            rec[f"{tag}/grad/{k}"] = p_.grad.numpy()
+    np.savez_compressed(os.path.join(out, "arch.npz"), **rec)
+
+
 def gen_checkpoint(M, I, TR, out):
     """A reference-format checkpoint (payload of train.py:606-630) written from the unmodified reference classes: a small
     non-default UNet1D (base_ch=16, depth=2, time_dim=32, 7 input channels) after two AdamW steps on the reference loss with an
@@ -485,7 +509,7 @@ def gen_checkpoint(M, I, TR, out):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=HERE)
-    ap.add_argument("--only", default=None, help="run one generator only (whitening_welch | ingest | checkpoint)")
+    ap.add_argument("--only", default=None, help="run one generator only (whitening_welch | ingest | checkpoint | arch)")
     args = ap.parse_args()
     if args.only == "whitening_welch":
         M, I, TR = import_reference()
@@ -493,6 +517,10 @@ def main():
         return
     if args.only == "ingest":
         gen_ingest(args.out)
+        return
+    if args.only == "arch":
+        M, I, TR = import_reference()
+        gen_arch(M, TR, args.out)
         return
     if args.only == "checkpoint":
         M, I, TR = import_reference()
@@ -510,6 +538,7 @@ def main():
     gen_whitening_welch(I, args.out)
     gen_ingest(args.out)
     gen_checkpoint(M, I, TR, args.out)
+    gen_arch(M, TR, args.out)
     tot = sum(os.path.getsize(os.path.join(args.out, f)) for f in os.listdir(args.out) if f.endswith(".npz"))
     print(f"golden fixtures written to {args.out}: {tot / 1e6:.2f} MB")
 

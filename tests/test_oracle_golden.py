@@ -138,3 +138,25 @@ def test_train_step_matches_reference(golden_dir, in_ch, cc, sc):
     lam = np.load(os.path.join(golden_dir, "lr_lambda.npz"))["lam"]
     mine = [oracle.warmup_cosine_lambda(s, 10, 100, 0.1) for s in [0, 5, 9, 10, 50, 99, 100, 150]]
     assert np.allclose(mine, lam, rtol=0, atol=1e-15)
+
+
+def test_non_default_architectures_match_reference(golden_dir):
+    """UNet1D(base_ch, kernel, depth) outside the CLI defaults (models.py:78-88): the oracle's eps_hat and autograd gradients
+    against the unmodified reference's (tests/golden/make_golden.py::gen_arch) -- this pins the oracle where the shape-generic
+    CUDA kernels are compared with it (tests/test_gpu_generic_arch.py)."""
+    from make_golden import ARCH_CASES
+    g = _load(golden_dir, "arch.npz")
+    for tag, base_ch, kernel, depth, in_ch, cc, L in ARCH_CASES:
+        sd = {k: v.clone().requires_grad_(True) for k, v in
+              make_state_dict(in_ch=in_ch, cond_in_ch=cc, base_ch=base_ch, depth=depth, kernel=kernel, seed=21).items()}
+        cfg = ModelCfg(in_ch=in_ch, base_ch=base_ch, depth=depth, kernel=kernel, cond_in_ch=cc, use_selfcond=True)
+        x = gaussian((2, in_ch, L), seed=200 + L + base_ch)
+        target = gaussian((2, 1, L), seed=300 + base_ch)
+        eps = oracle.unet_forward(sd, cfg, x, torch.tensor([24, 731]))
+        assert float((eps.detach() - torch.from_numpy(g[f"{tag}/eps"])).norm() / torch.from_numpy(g[f"{tag}/eps"]).norm()) <= 2e-6, tag
+        loss = torch.nn.functional.smooth_l1_loss(eps, target, beta=0.5, reduction="none").mean()
+        assert abs(float(loss) - float(g[f"{tag}/loss"])) <= 2e-6 * abs(float(g[f"{tag}/loss"]))
+        loss.backward()
+        for k, v in sd.items():
+            ref = torch.from_numpy(g[f"{tag}/grad/{k}"])
+            assert float((v.grad - ref).norm()) <= 5e-6 * max(float(ref.norm()), 1e-6), (tag, k)

@@ -437,7 +437,10 @@ def bench_sampling(args, workload, B, steps, warmup, world, rank, dev, barrier, 
                             "share_of_step": conv["share_of_step"]},
                "kernels": fams,
                "chain": {"tflops_per_gpu": chain_tflops, "frac_of_sustained_bf16_peak": chain_tflops / pk["bf16_sustained"],
-                         "ms_per_reverse_step": step_ms, "flops_per_waveform": flops_wf}}
+                         "ms_per_reverse_step": step_ms, "flops_per_waveform": flops_wf,
+                         "graph_capture_ms": getattr(plan, "graph_capture_ms", None),
+                         "graph_capture_note": "stream capture + instantiate of the whole chain as one CUDA graph, host wall clock, "
+                                               "once per (batch, length, schedule)"}}
         if with_cpu and world == 1:
             cpu_v, per_step, k, n = cpu_chain_rate(args, 6, 8, workload)
             res["cpu_baseline"] = {"value": cpu_v, "unit": "waveforms/s", "cores": os.cpu_count(), "kind": "port",

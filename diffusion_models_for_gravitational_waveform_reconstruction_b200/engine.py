@@ -706,6 +706,7 @@ class SamplerPlan:
         self.trace_eps: Optional[Tensor] = None
         self.trace_x0: Optional[Tensor] = None
         self._graph = None
+        self.graph_capture_ms: Optional[float] = None
         self._graph_steps = 0
 
     def set_rng(self, seed: int, sample0: int) -> None:
@@ -773,10 +774,14 @@ class SamplerPlan:
             n.copy_(sv)
         self.step.zero_()
         self.serial.add_(1)                            # the warm-up step used (serial, step 0): its chain flags must not match again
+        import time
+        t0 = time.perf_counter()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for _ in range(steps_per_graph):
                 self.enqueue_step()
+        torch.cuda.synchronize()
+        self.graph_capture_ms = (time.perf_counter() - t0) * 1e3     # stream capture + cudaGraphInstantiate (host wall clock)
         self._graph, self._graph_steps = g, steps_per_graph
         self.step.zero_()
 

@@ -21,6 +21,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 echo "ncu traffic list exit $?" >> $S
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name regex:conv_gn_kernel --launch-skip 9 --launch-count 3 -o gpurun_out/prof_cgn_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full exit $?" >> $S
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?" >> $S
+BCMD="python bench.py --steps 2 --warmup 3 --no-sampling"
+timeout 300 $BCMD > gpurun_out/plain_bench_$TAG.log 2>&1 &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_bench_train_$TAG.csv $BCMD > gpurun_out/ncu_bench_list_$TAG.log 2>&1
+echo "ncu bench launch list exit $?" >> $S
 cat $S
 grep -E "^(FAILED|ERROR)|passed|failed|non-default arch|ddpm1000 |L16384 ddpm" gpurun_out/pytest_$TAG.log | tail -12
 for f in bench_train bench_ddpm1000_B8 bench_ddim50 bench_L16384 bench_whiten bench_score; do echo "== $f"; cut -c1-260 gpurun_out/${f}_$TAG.json; done

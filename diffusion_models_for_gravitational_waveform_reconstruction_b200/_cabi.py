@@ -67,6 +67,8 @@ _SIGS.update({
     "gw_gn_bwd_scratch_elems": ([_I, _I, _I, _I], _L),
     "gw_gn_bwd": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P,
                    _P, _P, _P], _I),
+    "gw_gn_bwd_phase": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P,
+                         _P, _P, _I, _P], _I),
     "gw_gn_bwd2": ([_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _L, _P, _P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _P,
                     _P, _P, _P, _P], _I),
     "gw_gn_bwd_sync_bytes": ([_I], _L),
@@ -87,6 +89,7 @@ _SIGS.update({
     "gw_wgrad3_simt": ([_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _L, _P, _P], _I),
     "gw_wgrad_in": ([_P, _I, _I, _I, _P, _I, _I, _P, _L, _P, _P], _I),
     "gw_wgrad_tc_scratch_elems": ([_I, _I, _I, _I, _I], _L),
+    "gw_wgrad_tc_finish": ([_I, _I, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "gw_wgrad_tc": ([_I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P, _I, _P], _I),
     "gw_film_bwd": ([_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     "gw_batch_prepare": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),

@@ -909,8 +909,12 @@ extern "C" int gw_gn_bwd_fused_group(int L, int C, int Cc, int has_do, int has_p
 
 template <typename T, bool FAST>
 static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
-                      float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* sync, cudaStream_t st) {
+                      float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* sync, cudaStream_t st, int phase = 0) {
+    // phase (gw_gn_bwd_phase): 0 = everything; 1 = everything but the parameter-gradient kernel where that kernel is the LAST launch
+    // (the specialised streaming path), 2 = only that kernel (a no-op on the other paths, where phase 1 already ran it): lets the
+    // caller take the small parameter reduction off the critical path (a second stream) -- d_raw is complete after phase 1
     const int C = a.C, L = a.L, Cc = a.Cc, nvr = 4 + Cc;
+    if (phase != 0) sync = nullptr;
     if (FAST && sync != nullptr && a.do_eps == nullptr) {
         // one-pass kernel: operands read once, d_raw formed out of shared memory (gn_bwd_fused.cu)
         const int G = gn_bwd_fused_group(L, C, Cc, a.do_a != nullptr, a.do_pool != nullptr);
@@ -944,6 +948,13 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     float* redb = partial + (size_t)B * n_rc * C * nvs;
     float* gstat = redb + (size_t)B * C * nvs;
     float* biasp = gstat + (size_t)B * 16;                   // [B * n_rc, C] (sx)
+    if (phase == 2) {
+        if (!sx) return GW_OK;
+        GW_CUDA(gw_launch_pdl(gn_bwd_param_kernel, dim3(gw_cdiv(C, 32)), dim3(1024), (size_t)(0), st, redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
+                              d_wc, d_bc, biasp, n_rc, d_conv_bias));
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
     dim3 grid(n_rc, B);
     const size_t sm1 = (size_t)n_tr * C * nvr * sizeof(float), sm2 = (size_t)n_tr * C * sizeof(float);
 #define GNB_GO(CCV)                                                                                                       \
@@ -974,6 +985,7 @@ static int gn_bwd_run(const GnBwdArgs& a, int B, float* scratch, float* dfilm, l
     if (sx) {
         int rcs = gn_bwd_apply_stream(a, B, gstat, d_raw, biasp, st);
         if (rcs != GW_OK) return rcs;
+        if (phase == 1) return GW_OK;
         GW_CUDA(gw_launch_pdl(gn_bwd_param_kernel, dim3(gw_cdiv(C, 32)), dim3(1024), (size_t)(0), st, redb, B, C, nvs, Cc, a.film, a.film_b_stride, a.film_off, d_gn_w, d_gn_b,
                                                            d_wc, d_bc, biasp, n_rc, d_conv_bias));
         GW_LAUNCH_CHECK();
@@ -1022,6 +1034,28 @@ extern "C" int gw_gn_bwd2(const void* raw, const float* stats, int B, int L, int
     if (dtype == GW_F32)
         return gn_bwd_run<float, false>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, nullptr, st);
     return gn_bwd_run<bf16, true>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, sync_buf, st);
+}
+extern "C" int gw_gn_bwd_phase(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
+                               const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+                               long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
+                               int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+                               float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, int phase, void* stream) {
+    GW_REQUIRE(C % 64 == 0 && C <= 1024 && 256 % (C / 4) == 0, "gw_gn_bwd: C=%d", C);
+    GW_REQUIRE(Cc >= 0 && Cc <= BW_MAX_CC, "gw_gn_bwd: Cc=%d", Cc);
+    GW_REQUIRE((cond != nullptr) == (Cc > 0), "gw_gn_bwd: cond/Cc mismatch");
+    GW_REQUIRE(do_a != nullptr || do_pool != nullptr || do_eps != nullptr, "gw_gn_bwd: no incoming gradient");
+    GW_REQUIRE(do_eps == nullptr || (dtype == GW_BF16 && do_w != nullptr), "gw_gn_bwd: the head-gradient source needs bf16 and do_w");
+    GW_REQUIRE(dtype == GW_F32 || dtype == GW_BF16, "gw_gn_bwd: dtype %d", dtype);
+    GW_REQUIRE(phase >= 0 && phase <= 2, "gw_gn_bwd_phase: phase %d", phase);
+    GnBwdArgs a;
+    a.raw = raw; a.stats = stats; a.gn_w = gn_w; a.gn_b = gn_b; a.cond = cond; a.wc = wc; a.bc = bc; a.film = film;
+    a.film_b_stride = film_b_stride; a.film_off = film_off; a.do_a = do_a; a.do_pool = do_pool; a.do_eps = do_eps; a.do_w = do_w;
+    a.L = L; a.C = C; a.Cc = Cc;
+    a.rows_per_cta = gn_rows_per_cta(L, C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GW_F32)
+        return gn_bwd_run<float, false>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, nullptr, st, phase);
+    return gn_bwd_run<bf16, true>(a, B, scratch, dfilm, dfilm_b_stride, d_raw, d_gn_w, d_gn_b, d_wc, d_bc, d_conv_bias, nullptr, st, phase);
 }
 extern "C" int gw_gn_bwd(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
                          const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,

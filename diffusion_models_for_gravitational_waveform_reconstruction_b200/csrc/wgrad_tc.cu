@@ -361,7 +361,25 @@ extern "C" int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, in
     GW_CUDA(gw_launch_pdl(wgrad_tc_kernel, P.mt * P.nt * P.n_split, dim3(192), (size_t)(smem), st, ta, tx, P, scratch, shifted, atomic ? dW : nullptr, mode, Cout,
                                                                  Cin_total, ci_off));
     GW_LAUNCH_CHECK();
-    if (atomic) return GW_OK;
+    if (atomic || (variant & 4)) return GW_OK;               // bit 2: the caller runs gw_wgrad_tc_finish (e.g. on another stream)
+    const long cols = (long)P.mt * P.nt * 3 * 128 * P.bn;
+    GW_CUDA(gw_launch_pdl(wgrad_fold_kernel, dim3((unsigned)((cols / 4 + 31) / 32)), dim3(256), (size_t)(0), st, scratch, P.n_split, cols));
+    GW_LAUNCH_CHECK();
+    const long n = (long)Cout * Cx;
+    GW_CUDA(gw_launch_pdl(wgrad_scatter_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, scratch, P, mode, Cout, Cx, Cin_total, ci_off, dW));
+    GW_LAUNCH_CHECK();
+    return GW_OK;
+}
+
+// the deterministic split-K epilogue of gw_wgrad_tc(variant | 4): fold the partial buffer, then scatter-accumulate into dW.  Same
+// shape arguments as the GEMM call that filled `scratch`; may run on any stream ordered after that call.
+extern "C" int gw_wgrad_tc_finish(int mode, int B, int L, int Cout, int Cx, int Cin_total, int ci_off, float* scratch, float* dW,
+                                  void* stream) {
+    WgParams P;
+    int rc = wg_params(mode, B, L, Cout, Cx, &P);
+    if (rc != GW_OK) return rc;
+    GW_REQUIRE(scratch != nullptr && dW != nullptr, "wgrad_tc_finish: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
     const long cols = (long)P.mt * P.nt * 3 * 128 * P.bn;
     GW_CUDA(gw_launch_pdl(wgrad_fold_kernel, dim3((unsigned)((cols / 4 + 31) / 32)), dim3(256), (size_t)(0), st, scratch, P.n_split, cols));
     GW_LAUNCH_CHECK();

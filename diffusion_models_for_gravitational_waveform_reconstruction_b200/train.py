@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -67,6 +68,21 @@ class _GradWorkspace:
         self.film = torch.empty(B, spec.film_dim, device=device, dtype=torch.float32)
         # exchange buffer of the one-pass GroupNorm backward (gn_bwd_fused.cu): zeroed once, epochs advance per launch
         self.sync = torch.zeros(lib.gw_gn_bwd_sync_bytes(B), device=device, dtype=torch.uint8)
+        # deferred small reductions (BackwardEngine.defer_small): the parameter-gradient kernel of a GroupNorm block and the
+        # fold / scatter passes of a weight gradient run on a second stream, so what they read must outlive the next launches on
+        # the main stream: one scratch buffer per layer / per wgrad call instead of the shared one (a few hundred MB of 180 GB)
+        self.gn_scr = [torch.empty(lib.gw_gn_bwd_scratch_elems(B, ws.lay_len[i], lc[i], spec.cond_in_ch), device=device,
+                                   dtype=torch.float32) if lc[i] % 64 == 0 else None for i in range(2 * d + 1)]
+        self.wg_scr: Dict[tuple, Tensor] = {}
+        self.film_scr = torch.empty(B * spec.base_ch * (2 + (spec.film_dim + 95) // 96), device=device, dtype=torch.float32)
+        self._dev = device
+
+    def wgrad_scratch(self, key: tuple, n: int) -> Tensor:
+        buf = self.wg_scr.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(n, device=self._dev, dtype=torch.float32)
+            self.wg_scr[key] = buf
+        return buf
 
 
 class BackwardEngine:
@@ -91,6 +107,13 @@ class BackwardEngine:
         # measured slower on B200 (1.90 vs 1.13 ms per step at B=256, L=4096): a slice stays in shared memory for load +
         # sums + exchange + apply + store (~8 us), and 228 KB per SM cannot cover that latency at HBM rate.  Parity-tested option.
         self.fuse_gn_bwd = False
+        # bf16 / tcgen05: the small latency-bound reductions of the backward pass -- the per-block parameter-gradient kernel
+        # (gn_bwd_param_kernel, 2 - 8 CTAs, ~15 us), the split-K fold + scatter of every weight gradient (~12 us per call) and the
+        # time-MLP backward (4 launches, ~80 us) -- run on a second stream (a parallel branch of the step's CUDA graph) next to
+        # the big kernels instead of between them; joined before the gradient norm.  GWB200_DEFER=0 turns it off.
+        self.defer_small = os.environ.get("GWB200_DEFER", "1") != "0"
+        self._side2: Optional[torch.cuda.Stream] = None
+        self._deferring = False
 
     def grad_workspace(self, ws: _Workspace) -> _GradWorkspace:
         key = (ws.B, ws.L)
@@ -214,16 +237,22 @@ class BackwardEngine:
                 eng.launches += 1
             return
         if self.wgrad_impl == "tc" and tc_ok:
-            if src1 is None:
-                check(lib.gw_wgrad_tc(0, ptr(g.d_raw), ptr(src0), B, L, Cout, C0, C0, 0, ptr(g.scratch), g.scratch.numel(), ptr(dW),
-                                      self.wgrad_variant, st), f"wgrad_tc[{name}]")
+            defer = self._deferring and (self.wgrad_variant & 2) == 0
+            parts = [(0, src0, C0, C0, 0)] if src1 is None else [(1, src0, C0, C0 + C1, 0), (0, src1, C1, C0 + C1, C0)]
+            for pi, (mode, src, cx, ctot, off) in enumerate(parts):
+                if not defer:
+                    check(lib.gw_wgrad_tc(mode, ptr(g.d_raw), ptr(src), B, L, Cout, cx, ctot, off, ptr(g.scratch), g.scratch.numel(),
+                                          ptr(dW), self.wgrad_variant, st), f"wgrad_tc[{name}.{pi}]")
+                else:
+                    # GEMM on the main stream into this call's own partial buffer; fold + scatter-accumulate on the side stream
+                    scr = g.wgrad_scratch((li, pi), lib.gw_wgrad_tc_scratch_elems(mode, B, L, Cout, cx))
+                    check(lib.gw_wgrad_tc(mode, ptr(g.d_raw), ptr(src), B, L, Cout, cx, ctot, off, ptr(scr), scr.numel(), ptr(dW),
+                                          self.wgrad_variant | 4, st), f"wgrad_tc[{name}.{pi}]")
+                    self._side2.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(self._side2):
+                        check(lib.gw_wgrad_tc_finish(mode, B, L, Cout, cx, ctot, off, ptr(scr), ptr(dW), _cabi.stream_ptr()),
+                              f"wgrad_tc_finish[{name}.{pi}]")
                 eng.launches += 2
-            else:
-                check(lib.gw_wgrad_tc(1, ptr(g.d_raw), ptr(src0), B, L, Cout, C0, C0 + C1, 0, ptr(g.scratch), g.scratch.numel(),
-                                      ptr(dW), self.wgrad_variant, st), f"wgrad_tc[{name}.up]")
-                check(lib.gw_wgrad_tc(0, ptr(g.d_raw), ptr(src1), B, L, Cout, C1, C0 + C1, C0, ptr(g.scratch), g.scratch.numel(),
-                                      ptr(dW), self.wgrad_variant, st), f"wgrad_tc[{name}.skip]")
-                eng.launches += 4
         else:
             check(lib.gw_wgrad3_simt(ptr(src0), C0, L0, up, ptr(src1), C1, ptr(g.d_raw), B, L, Cout, eng.gw_dtype,
                                      ptr(g.scratch), g.wg_elems, ptr(dW), st), f"wgrad3_simt[{name}]")
@@ -262,6 +291,9 @@ class BackwardEngine:
         names, cnames, foffs = sp.layer_names(), sp.cond_names(), sp.film_offsets()
         Cc = sp.cond_in_ch
         nl = 2 * d + 1
+        self._deferring = self.defer_small and eng.dtype == "bf16" and not eng.generic and not self.fuse_gn_bwd
+        if self._deferring and self._side2 is None:
+            self._side2 = torch.cuda.Stream()
 
         def gn_bwd(li: int, do_a: Optional[Tensor], do_pool: Optional[Tensor], do_eps: Optional[Tensor] = None) -> None:
             n = names[li]
@@ -278,6 +310,23 @@ class BackwardEngine:
                                         ptr(grads[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(grads[n + ".0.bias"]), st),
                       f"gen_gn_bwd[{n}]")
                 eng.launches += 3
+                return
+            if self._deferring and do_eps is None and g.gn_scr[li] is not None:
+                def call(phase):
+                    check(lib.gw_gn_bwd_phase(ptr(ws.raw[li]), ptr(ws.stats[li]), B, Ll, Cl, ptr(eng.p[n + ".1.weight"]),
+                                              ptr(eng.p[n + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
+                                              ptr(eng.p[cnames[li] + ".weight"]) if Cc > 0 else None,
+                                              ptr(eng.p[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(g.film), foffs[li],
+                                              sp.film_dim, ptr(do_a), ptr(do_pool), None, None, eng.gw_dtype, ptr(g.gn_scr[li]),
+                                              ptr(g.dfilm), sp.film_dim, ptr(g.d_raw), ptr(grads[n + ".1.weight"]),
+                                              ptr(grads[n + ".1.bias"]), ptr(grads[cnames[li] + ".weight"]) if Cc > 0 else None,
+                                              ptr(grads[cnames[li] + ".bias"]) if Cc > 0 else None, ptr(grads[n + ".0.bias"]),
+                                              phase, _cabi.stream_ptr()), f"gn_bwd[{n}].{phase}")
+                call(1)                                       # statistics, fold, apply: d_raw and the FiLM gradient rows
+                self._side2.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side2):
+                    call(2)                                   # parameter / conv-bias gradients of this block
+                eng.launches += 5
                 return
             check(lib.gw_gn_bwd2(ptr(ws.raw[li]), ptr(ws.stats[li]), B, Ll, Cl, ptr(eng.p[n + ".1.weight"]),
                                 ptr(eng.p[n + ".1.bias"]), ptr(ws.cond[lvl]) if Cc > 0 else None, Cc,
@@ -325,6 +374,20 @@ class BackwardEngine:
             self._conv_bwd(li, ws, g, grads, g.d_pool[pc ^ 1], None)
             pc ^= 1
         gn_bwd(0, g.d_skip[0], g.d_pool[pc])
+        lo = self.layout
+        cur_s = torch.cuda.current_stream()
+
+        def film_bwd(scr):
+            check(lib.gw_film_bwd(ptr(g.dfilm), ptr(g.aux), ptr(eng.film_w2), B, sp.time_dim, sp.base_ch, sp.film_dim, ptr(scr),
+                                  ptr(grads["time_mlp.1.weight"]), ptr(grads["time_mlp.1.bias"]),
+                                  flat_grad.data_ptr() + 4 * lo.w2[0], flat_grad.data_ptr() + 4 * lo.b2[0], _cabi.stream_ptr()),
+                  "film_bwd")
+        if self._deferring:
+            # dfilm is complete once the first block's GroupNorm backward (phase 1) has run: the time-MLP backward runs on the
+            # side stream next to the first conv's weight gradient
+            self._side2.wait_stream(cur_s)
+            with torch.cuda.stream(self._side2):
+                film_bwd(g.film_scr)
         if eng.generic:
             check(lib.gw_gen_wgrad(None, 0, 0, 0, None, 0, ptr(net), Cx, ptr(g.d_raw), B, L, lc[0], sp.kernel, eng.gw_dtype,
                                    ptr(grads["encoders.0.0.weight"]), st), "gen_wgrad[encoders.0]")
@@ -333,10 +396,10 @@ class BackwardEngine:
             check(lib.gw_wgrad_in(ptr(net), B, Cx, L, ptr(g.d_raw), lc[0], eng.gw_dtype, ptr(g.scratch), g.scratch.numel(),
                                   ptr(grads["encoders.0.0.weight"]), st), "wgrad_in")
             eng.launches += 2
-        lo = self.layout
-        check(lib.gw_film_bwd(ptr(g.dfilm), ptr(g.aux), ptr(eng.film_w2), B, sp.time_dim, sp.base_ch, sp.film_dim, ptr(g.scratch),
-                              ptr(grads["time_mlp.1.weight"]), ptr(grads["time_mlp.1.bias"]),
-                              flat_grad.data_ptr() + 4 * lo.w2[0], flat_grad.data_ptr() + 4 * lo.b2[0], st), "film_bwd")
+        if self._deferring:
+            cur_s.wait_stream(self._side2)                    # join: every deferred reduction precedes the gradient norm
+        else:
+            film_bwd(g.scratch)
         eng.launches += 3
 
 

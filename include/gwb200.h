@@ -274,6 +274,15 @@ int gw_gn_bwd2(const void* raw, const float* stats, int B, int L, int C, const f
                int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
                float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, void* sync, void* stream);
 
+/* gw_gn_bwd in phases, for callers that take the small parameter-gradient reduction off the critical path: phase 0 = gw_gn_bwd;
+ * phase 1 = everything d_raw / dfilm need (and, where the parameter kernel is not the last launch, that kernel too); phase 2 = the
+ * parameter-gradient kernel alone (same arguments, same scratch, any stream ordered after phase 1; a no-op where phase 1 ran it). */
+int gw_gn_bwd_phase(const void* raw, const float* stats, int B, int L, int C, const float* gn_w, const float* gn_b,
+                    const float* cond, int Cc, const float* wc, const float* bc, const float* film, int film_off,
+                    long film_b_stride, const void* do_a, const void* do_pool, const float* do_eps, const float* do_w,
+                    int dtype, float* scratch, float* dfilm, long dfilm_b_stride, void* d_raw, float* d_gn_w,
+                    float* d_gn_b, float* d_wc, float* d_bc, float* d_conv_bias, int phase, void* stream);
+
 /* exact-mode conv backward.  gw_weight_dgrad: wt[ci][co][k] = w[co][ci][2-k], so that dgrad = gw_conv3_simt(d_raw, wt).
  * gw_split_cat_grad: gradient of cat[nearest-upsample x2 (h), skip]: d_h [B, L0, C0] (pair sums), d_skip [B, L, C1].
  * gw_wgrad3_simt: dW[co][ci][k] += sum_{b,l} d_raw[b,l,co] * cat[up(src0), src1][b, l+k-1, ci] (split-K partials in scratch).
@@ -290,10 +299,14 @@ int gw_wgrad_in(const float* x, int B, int Cx, int L, const void* d_raw, int C, 
  * mode 1: x [B, L/2, Cx] is h before the nearest upsample.  d_raw [B, L, Cout] bf16.  ACCUMULATES into the input-channel
  * block [ci_off, ci_off+Cx) of dW fp32 [Cout][Cin_total][3].  scratch >= gw_wgrad_tc_scratch_elems(...) floats.
  * variant bit 0: one TMA box per tap instead of row-shifted descriptors; bit 1: split-K by fp32 atomics straight into dW
- * (no fold / scatter passes; summation order, hence the last bits, not reproducible run to run). */
+ * (no fold / scatter passes; summation order, hence the last bits, not reproducible run to run); bit 2: GEMM only -- the
+ * deterministic fold + scatter-accumulate into dW is run by gw_wgrad_tc_finish (same shape arguments and scratch), which may be
+ * issued on another stream ordered after the GEMM so that the two small kernels leave the critical path. */
 long gw_wgrad_tc_scratch_elems(int mode, int B, int L, int Cout, int Cx);
 int gw_wgrad_tc(int mode, const void* d_raw, const void* x, int B, int L, int Cout, int Cx, int Cin_total, int ci_off,
                 float* scratch, long scratch_elems, float* dW, int variant, void* stream);
+int gw_wgrad_tc_finish(int mode, int B, int L, int Cout, int Cx, int Cin_total, int ci_off, float* scratch, float* dW,
+                       void* stream);
 
 /* time_mlp / tproj_* backward (models.py:105-109, 137-142): dfilm [B, F] (written by gw_gn_bwd), aux from
  * gw_film_vectors; accumulates dW1 [base, time_dim], db1 [base], dW2 [F, base], db2 [F];

@@ -418,3 +418,24 @@ def test_load_collated_equals_reference_batch_preparation(in_ch, cc, K):
     assert float(st.mask.min()) == 1.0
     with pytest.raises(ValueError):
         st.load_collated(clean[:2].cuda(), noisy[:2].cuda(), sigma[:2].cuda(), None, None, repeat=K)
+
+
+def test_deferred_reductions_are_bit_identical():
+    """BackwardEngine.defer_small: the parameter-gradient kernels, the wgrad fold / scatter passes and the time-MLP backward on a
+    second stream (gw_gn_bwd_phase, gw_wgrad_tc_finish) -- same kernels, same summation orders, so every gradient, the loss and the
+    updated parameters are bit-identical to the single-stream order, eager and graph-replayed."""
+    in_ch, cc, B, L = 7, 5, 6, 1024
+    sd, clean, cond, mask, t, eps, drop = _case(in_ch, cc, B, L)
+    res = {}
+    for defer in (False, True):
+        for use_graph in (False, True):
+            m, st = _stepper(sd, in_ch, cc, B, L, "bf16")
+            st.bwd.defer_small = defer
+            st.load_batch(clean.cuda(), cond.cuda(), mask.cuda())
+            for _ in range(2):
+                st.step(selfcond=True, t=t.cuda(), eps=eps.cuda(), drop=drop.cuda(), use_graph=use_graph)
+            torch.cuda.synchronize()
+            res[(defer, use_graph)] = (st.flat_g.clone(), st.flat_p.clone(), float(st.loss))
+    ref = res[(False, False)]
+    for k, v in res.items():
+        assert torch.equal(v[0], ref[0]) and torch.equal(v[1], ref[1]) and v[2] == ref[2], k

@@ -178,3 +178,30 @@ def test_long_segment_forward_L16384():
         eng = UNetEngine({k: v.cuda() for k, v in sd.items()}, spec, dtype=dtype, conv_impl=impl)
         out = eng.forward(x.cuda(), t.cuda()).cpu()
         assert float((out - ref).norm() / ref.norm()) <= tol, dtype
+
+
+@pytest.mark.parametrize("in_ch,cc,sc", [(2, 1, False), (6, 5, False), (3, 1, True)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+def test_chain_without_selfcond_channel(in_ch, cc, sc, dtype, tol):
+    """Channel layouts the reference constructor allows besides the trained ones (models.py:89-98, 175-186): conditional models
+    WITHOUT a self-conditioning channel ([x_t | y] and [x_t | y | 4 metadata]) -- CFG two-pass batch, stochastic steps with
+    injected noise, graph replay -- against the oracle chain."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, UNet1D
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import inference as inf
+    L, B = 512, 3
+    sd = make_state_dict(in_ch, cc, seed=4)
+    cfg = oracle.ModelCfg(in_ch=in_ch, cond_in_ch=cc, use_selfcond=sc)
+    ab = oracle.alpha_bar_from_betas(oracle.cosine_beta_schedule(1000))
+    y = synthetic_chirps(B, L, snr=10.0, seed=78)["y_norm"]
+    cond = y if cc == 1 else torch.cat([y, gaussian((B, 4, 1), seed=6).expand(B, 4, L).contiguous() * 0.3], dim=1)
+    noise = torch.stack([gaussian((B, 1, L), seed=300 + k) for k in range(20)], 0)
+    m = UNet1D(in_ch=in_ch, cond_in_ch=cc, use_selfcond=sc, compute_dtype=dtype)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    diff = CustomDiffusion(T=1000, device="cuda")
+    kw = dict(steps=12, eta=1.0, start_t=289, cfg_scale=1.5)
+    ref = oracle.ddim_sample(sd, cfg, ab, cond, T=1000, noise=list(noise), **kw)
+    out = inf.ddim_sample(m, diff, cond.cuda(), T=1000, device="cuda", length=L, debug=False, x0_std_est=0.14, cond_scale=1.0,
+                          eps_scale=1.0, pred_type="eps", in_ch=in_ch, cond_in_ch=cc, use_selfcond=sc, cfg_mode="const", cfg_center=0.5,
+                          cfg_width=0.3, cfg_u_only_thresh=0.0, dc_weight=0.0, init_mode="noise", noise=noise, **kw)
+    assert rel_l2(out, ref) <= tol, rel_l2(out, ref)

@@ -676,7 +676,10 @@ def bench_aux(args, dev, pk):
             "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                          "traffic": None, "algorithmic_bytes_per_step": alg_bytes, "peak_source": pk["src"],
                          "note": "whole step (several kernels + cuFFT) against the bytes that must move once; the fp64 FFT workspace "
-                                 "passes are not algorithmic bytes" if args.workload == "whiten" else "one kernel"}}
+                                 "passes are not algorithmic bytes" if args.workload == "whiten" else
+                                 f"one kernel; its time is the fp64 lag search (2 x 165 lags x L FLOP per sample = "
+                                 f"{2 * 165 * L * B / (per * 1e-3) / 1e12:.1f} TFLOP/s fp64, register-tiled out of shared memory), "
+                                 "not the 33 KB per sample it reads"}}
 
 
 def run_ours(args):

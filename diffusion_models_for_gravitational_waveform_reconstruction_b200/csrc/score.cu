@@ -29,9 +29,49 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return t;
 }
 
+// Lag search out of shared memory, register-tiled: c and x staged ONCE as fp64 (x zero-padded by `pad` on both sides, so every
+// (i, k) pair is in range and out-of-range products are exact zeros), a warp takes 8 consecutive lags, a lane 4 consecutive
+// positions per iteration: 32 DFMA on 4 + 11 shared-memory loads instead of 2 loads (and 2 conversions) per DFMA.  Both series
+// are stored in four planes (element e -> plane e & 3, slot e >> 2), so that lanes reading elements 4 apart touch consecutive
+// 8-byte words: every load is bank-conflict free.
+#define SC_LAGS 8
+__device__ __forceinline__ void lag_search_tiled(const double* __restrict__ cs, const double* __restrict__ xs, int pad, int Lp, int nx,
+                                                 int ms, int warp, int lane, double& bestv, int& bestk) {
+    const int cq = Lp >> 2, xq = nx >> 2;
+    for (int k0 = -ms + warp * SC_LAGS; k0 <= ms; k0 += 8 * SC_LAGS) {
+        double acc[SC_LAGS];
+#pragma unroll
+        for (int j = 0; j < SC_LAGS; ++j) acc[j] = 0.0;
+        const double* xp[SC_LAGS + 3];
+#pragma unroll
+        for (int j = 0; j < SC_LAGS + 3; ++j) {
+            const int e = pad + k0 + j;                        // element of lane 0 at i = 0
+            xp[j] = xs + (e & 3) * xq + (e >> 2) + lane;
+        }
+        for (int t = 0; t < cq; t += 32) {                    // positions i = 4 (lane + t) .. + 3
+            double cv[4], xw[SC_LAGS + 3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cv[q] = cs[q * cq + lane + t];
+#pragma unroll
+            for (int j = 0; j < SC_LAGS + 3; ++j) xw[j] = xp[j][t];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < SC_LAGS; ++j) acc[j] = fma(cv[q], xw[q + j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < SC_LAGS; ++j) {
+            const double v = warp_sum_d(acc[j]);
+            const int k = k0 + j;
+            if (k <= ms && v > bestv) { bestv = v; bestk = k; }      // ascending k per warp: first maximum wins
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ xhat, const float* __restrict__ clean,
                                                     const float* __restrict__ sigma, int L, double fs, double secs, int max_shift,
-                                                    double delta_t, double* __restrict__ out) {
+                                                    double delta_t, double* __restrict__ out, int tiled_pad) {
+    extern __shared__ __align__(16) double sc_dyn[];          // tiled lag search: cs [Lp] | xs [pad + Lp + pad + 16]
     __shared__ double red[8];
     __shared__ double s_best[8];
     __shared__ int s_bestk[8];
@@ -97,6 +137,19 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ xh
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double bestv = -1.0e300;
     int bestk = 0;
+    if (tiled_pad > 0) {
+        const int Lp = (L + 127) / 128 * 128;
+        double* cs = sc_dyn;
+        double* xs = sc_dyn + Lp;
+        const int nx = tiled_pad + Lp + tiled_pad + 16;
+        for (int i = threadIdx.x; i < Lp; i += 256) cs[(i & 3) * (Lp >> 2) + (i >> 2)] = i < L ? (double)c[i] : 0.0;
+        for (int i = threadIdx.x; i < nx; i += 256) {
+            const int j = i - tiled_pad;
+            xs[(i & 3) * (nx >> 2) + (i >> 2)] = (j >= 0 && j < L) ? (double)x[j] : 0.0;
+        }
+        __syncthreads();
+        lag_search_tiled(cs, xs, tiled_pad, Lp, nx, ms, warp, lane, bestv, bestk);
+    } else
     for (int k = -ms + warp; k <= ms; k += 8) {
         const int lo = k < 0 ? -k : 0, hi = k > 0 ? L - k : L;       // i range with 0 <= i + k < L
         double v = 0.0;
@@ -180,7 +233,15 @@ extern "C" int gw_score_batch(const float* xhat, const float* clean, const float
                               int max_shift, double delta_t, double* out, void* stream) {
     GW_REQUIRE(B > 0 && L > 1 && fs > 0.0 && secs > 0.0 && xhat != nullptr && clean != nullptr && out != nullptr,
                "gw_score_batch: arguments");
-    score_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(xhat, clean, sigma, L, fs, secs, max_shift, delta_t, out);
+    // shared-memory lag search when the fp64 copies of both series fit (L = 4096, |k| <= 82: 68 KB); else straight from L1 / L2
+    int ms = max_shift <= 0 ? L - 1 : max_shift;
+    if (ms > L - 1) ms = L - 1;
+    const int Lp = (L + 127) / 128 * 128;
+    int pad = (ms + SC_LAGS * 8 + 15) / 16 * 16;              // k0 + j may run SC_LAGS * 8 - 1 past ms in the last pass of a warp
+    size_t smem = (size_t)(Lp + pad + Lp + pad + 16) * sizeof(double);
+    if (smem > 200 * 1024) { pad = 0; smem = 0; }
+    if (smem > 48 * 1024) GW_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(xhat, clean, sigma, L, fs, secs, max_shift, delta_t, out, pad);
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

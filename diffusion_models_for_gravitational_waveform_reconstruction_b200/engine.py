@@ -204,7 +204,7 @@ class UNetEngine:
         # training (keep_raw) forwards also have to write the conv output for the backward pass and carry five cond channels;
         # measured on B200 the fused kernel then loses its edge (962 us vs ~900 us of conv + GroupNorm launches per step at
         # B=256, L=4096, in_ch=7), so it stays an inference default; parity-tested for both
-        self.fuse_gn_train = False
+        self.fuse_gn_train = os.environ.get("GWB200_FUSE_GN_TRAIN", "0") not in ("0", "")
         # inference: the last decoder's fused kernel also forms the three head-conv dot products per position (gw_conv_gn2), so
         # gw_final_step runs on 16 B per position and the [B, L, 64] activation is neither written nor read back
         self.fuse_head = True

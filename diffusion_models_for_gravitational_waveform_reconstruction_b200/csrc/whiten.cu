@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "../../include/gwb200_fft.h"
 #include <cufft.h>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -146,6 +147,260 @@ static int fft_inverse(cufftDoubleComplex* Z, int B, int L, double* tbuf, float*
     return GW_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- fused train-like whitening
+// One CTA per sample, everything between the fp32 input and the fp32 output in shared memory (power-of-two L up to 8192):
+// mean removal, the real FFT as an L/2-point complex fp64 FFT of the packed samples (radix-2 decimation in frequency in place,
+// bit-reversal permutation, even / odd split), the 9-tap smoothed periodogram, division by sqrt(P), the inverse transform the same
+// way back, for y and then for x with the same P.  HBM traffic = the algorithmic bytes (inputs read once, outputs written once);
+// the cuFFT path above moves ~8x that through fp64 workspaces.
+static std::map<int, double2*> g_twiddles;                  // L -> W_L^k = exp(-2 pi i k / L), k = 0 .. L/2 (device)
+__global__ void twiddle_kernel(int L, double2* __restrict__ tab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > L / 2) return;
+    double s, c;
+    sincospi(2.0 * (double)k / (double)L, &s, &c);
+    tab[k] = make_double2(c, -s);
+}
+static int get_twiddles(int L, cudaStream_t st, const double2** out) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_twiddles.find(L);
+    if (it == g_twiddles.end()) {
+        double2* tab = nullptr;
+        GW_CUDA(cudaMalloc(&tab, (size_t)(L / 2 + 1) * sizeof(double2)));
+        twiddle_kernel<<<gw_cdiv(L / 2 + 1, 256), 256, 0, st>>>(L, tab);
+        GW_LAUNCH_CHECK();
+        it = g_twiddles.emplace(L, tab).first;
+    }
+    *out = it->second;
+    return GW_OK;
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+
+// Shared-memory layouts.  z (N complex fp64) and the twiddle table W_N^e (e < N/2) are stored skewed (one extra element per 8, per 64
+// and per 512): the power-of-two strides of the late passes, of the twiddle exponents and of the bit-reversal permutation then still
+// spread over the 8 sixteen-byte bank groups instead of piling onto one (measured: the unskewed permutation alone cost 4x the FFT).
+__device__ __forceinline__ int zp(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+__device__ __forceinline__ int tw_skew(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }             // a * (-i)
+template <int N>
+__device__ __forceinline__ double2 tw_get(const double2* __restrict__ tws, int e) {                  // W_N^e, 0 <= e < N
+    const double2 w = tws[tw_skew(e & (N / 2 - 1))];
+    return (e & (N / 2)) ? make_double2(-w.x, -w.y) : w;
+}
+// forward 4-point DFT, outputs in natural order
+__device__ __forceinline__ void dft4(double2 c0, double2 c1, double2 c2, double2 c3, double2& y0, double2& y1, double2& y2, double2& y3) {
+    const double2 d0 = cadd(c0, c2), d1 = csub(c0, c2), d2 = cadd(c1, c3), d3 = mul_mi(csub(c1, c3));
+    y0 = cadd(d0, d2); y2 = csub(d0, d2); y1 = cadd(d1, d3); y3 = csub(d1, d3);
+}
+
+// in-place forward N-point complex FFT of z (shared memory, zp-padded), N = 2^LGN, natural order in and out: decimation in
+// frequency in radix-8 passes (a thread holds the 8 points of a butterfly in registers: N = 2048 is 8 x 8 x 8 x 4, four
+// shared-memory round trips instead of eleven), one radix-4 or radix-2 pass for the leftover bits, then the bit-reversal
+// permutation (every butterfly stores output q in sub-block bitrev(q), so the radix-2 ordering is kept).  The inverse transform is
+// conj(forward(conj(.))), applied by the callers.  All 256 threads must call.
+template <int LGN>
+__device__ __forceinline__ void smem_fft(double2* z, const double2* __restrict__ tws) {
+    constexpr int N = 1 << LGN;
+    constexpr double RH = 0.70710678118654752440;
+    int lgn = LGN;                                           // log2 of the current block size
+#pragma unroll 1
+    for (int pass = 0; pass < LGN / 3; ++pass) {
+        const int m = 1 << (lgn - 3), sh = LGN - lgn;
+#pragma unroll 1
+        for (int t = threadIdx.x; t < N / 8; t += 256) {
+            const int j = t & (m - 1), base = ((t - j) << 3) + j;
+            double2 x[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) x[r] = z[zp(base + r * m)];
+            // first layer: pairs (r, r + 4); the differences take W_8^r
+            const double2 a0 = cadd(x[0], x[4]), a1 = cadd(x[1], x[5]), a2 = cadd(x[2], x[6]), a3 = cadd(x[3], x[7]);
+            const double2 b0 = csub(x[0], x[4]);
+            double2 b1 = csub(x[1], x[5]), b2 = csub(x[2], x[6]), b3 = csub(x[3], x[7]);
+            b1 = make_double2(RH * (b1.x + b1.y), RH * (b1.y - b1.x));           // * (1 - i) / sqrt 2
+            b2 = mul_mi(b2);
+            b3 = make_double2(RH * (b3.y - b3.x), -RH * (b3.x + b3.y));          // * (-1 - i) / sqrt 2
+            double2 y[8];
+            dft4(a0, a1, a2, a3, y[0], y[2], y[4], y[6]);
+            dft4(b0, b1, b2, b3, y[1], y[3], y[5], y[7]);
+            // output q -> sub-block bitrev3(q), times W_n^(j q) = W_N^((j q) << sh): one table load (j << sh < N / 8), the other six
+            // powers by multiplication (depth 3; the fp64 pipe has room, the shared-memory pipe is what this kernel runs into)
+            double2 w[8];
+            w[1] = tws[tw_skew(j << sh)];
+            w[2] = cmul(w[1], w[1]);
+            w[3] = cmul(w[2], w[1]);
+            w[4] = cmul(w[2], w[2]);
+            w[5] = cmul(w[4], w[1]);
+            w[6] = cmul(w[4], w[2]);
+            w[7] = cmul(w[4], w[3]);
+            z[zp(base)] = y[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                const int slot = ((q & 1) << 2) | (q & 2) | (q >> 2);
+                z[zp(base + slot * m)] = cmul(y[q], w[q]);
+            }
+        }
+        __syncthreads();
+        lgn -= 3;
+    }
+    if (LGN % 3 == 2) {                                      // blocks of 4 are left: j = 0, no twiddles
+#pragma unroll 1
+        for (int t = threadIdx.x; t < N / 4; t += 256) {
+            const int base = t << 2;
+            double2 y0, y1, y2, y3;
+            dft4(z[zp(base)], z[zp(base + 1)], z[zp(base + 2)], z[zp(base + 3)], y0, y1, y2, y3);
+            z[zp(base)] = y0; z[zp(base + 2)] = y1; z[zp(base + 1)] = y2; z[zp(base + 3)] = y3;
+        }
+        __syncthreads();
+    } else if (LGN % 3 == 1) {
+#pragma unroll 1
+        for (int t = threadIdx.x; t < N / 2; t += 256) {
+            const double2 a = z[zp(2 * t)], b = z[zp(2 * t + 1)];
+            z[zp(2 * t)] = cadd(a, b);
+            z[zp(2 * t + 1)] = csub(a, b);
+        }
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int i = threadIdx.x; i < N; i += 256) {
+        const int r = (int)(__brev((unsigned)i) >> (32 - LGN));
+        if (i < r) {
+            const double2 a = z[zp(i)];
+            z[zp(i)] = z[zp(r)];
+            z[zp(r)] = a;
+        }
+    }
+    __syncthreads();
+}
+
+// z [N] (the packed-sample FFT) -> the real-input spectrum Y[0 .. N]: Y[k] (k < N) in place, Y[N] (real) to *yN
+__device__ __forceinline__ void rfft_split(double2* z, int N, const double2* __restrict__ tw, double* yN) {
+    for (int k = threadIdx.x; k <= N / 2; k += 256) {
+        if (k == 0) {
+            const double2 a = z[0];
+            *yN = a.x - a.y;
+            z[0] = make_double2(a.x + a.y, 0.0);
+        } else if (2 * k == N) {
+            z[zp(k)] = cconj(z[zp(k)]);
+        } else {
+            const double2 a = z[zp(k)], bc = cconj(z[zp(N - k)]);
+            const double2 e = make_double2(0.5 * (a.x + bc.x), 0.5 * (a.y + bc.y));
+            const double2 d = make_double2(0.5 * (a.x - bc.x), 0.5 * (a.y - bc.y));
+            const double2 t = cmul(__ldg(tw + k), mul_mi(d));                    // W_L^k * (-i d)
+            z[zp(k)] = make_double2(e.x + t.x, e.y + t.y);
+            z[zp(N - k)] = make_double2(e.x - t.x, -(e.y - t.y));
+        }
+    }
+    __syncthreads();
+}
+// inverse of rfft_split after the spectrum was multiplied by the real gains g[0 .. N]: Y -> the CONJUGATE of the packed-sample
+// spectrum, in place (the forward FFT of it, conjugated again by the caller, is the inverse transform)
+__device__ __forceinline__ void irfft_merge_conj(double2* z, int N, const double2* __restrict__ tw, const double* __restrict__ g,
+                                                 double yN) {
+    for (int k = threadIdx.x; k <= N / 2; k += 256) {
+        if (k == 0) {
+            const double y0 = z[0].x * g[0], yn = yN * g[N];                     // imaginary parts of Y[0], Y[N] are ignored (irfft)
+            z[0] = make_double2(0.5 * (y0 + yn), -0.5 * (y0 - yn));
+        } else if (2 * k == N) {
+            const double2 a = z[zp(k)];
+            z[zp(k)] = make_double2(a.x * g[k], a.y * g[k]);                     // conj(conj(Y[N/2]))
+        } else {
+            const double2 zk = z[zp(k)], zn = z[zp(N - k)];
+            const double2 a = make_double2(zk.x * g[k], zk.y * g[k]);
+            const double2 bc = make_double2(zn.x * g[N - k], -zn.y * g[N - k]);
+            const double2 e = make_double2(0.5 * (a.x + bc.x), 0.5 * (a.y + bc.y));
+            const double2 t = make_double2(0.5 * (a.x - bc.x), 0.5 * (a.y - bc.y));
+            const double2 o = cmul(cconj(__ldg(tw + k)), t);
+            z[zp(k)] = make_double2(e.x - o.y, -(e.y + o.x));                    // conj(E + i O)
+            z[zp(N - k)] = make_double2(e.x + o.y, -(-e.y + o.x));               // conj(conj(E) + i conj(O))
+        }
+    }
+    __syncthreads();
+}
+
+template <int LGN>
+__global__ void __launch_bounds__(256, 2) whiten_fused_kernel(const float* __restrict__ y, const float* __restrict__ x,
+                                                              const double2* __restrict__ tw, float* __restrict__ y_w,
+                                                              float* __restrict__ x_w, double* __restrict__ P) {
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    __shared__ double red[8];
+    __shared__ double s_yN;
+    constexpr int N = 1 << LGN, L = 2 * N, F = N + 1;
+    constexpr int MPT = (F + 255) / 256;                      // spectrum bins per thread
+    const int b = blockIdx.x;
+    double2* z = reinterpret_cast<double2*>(wf_smem);        // [N] skewed (x 1.143)
+    double2* tws = z + (N + N / 6 + 8);                       // [N/2] skewed (x 1.143): W_N^e = tw[2e]
+    double* g = reinterpret_cast<double*>(tws + (N / 2 + N / 12 + 8));   // [F]: |Y|^2, then 1 / sqrt(P)
+    for (int j = threadIdx.x; j < N / 2; j += 256) tws[tw_skew(j)] = tw[2 * j];
+#pragma unroll 1
+    for (int pass = 0; pass < (x != nullptr ? 2 : 1); ++pass) {
+        const float* src = (pass == 0 ? y : x) + (size_t)b * L;
+        float* dst = (pass == 0 ? y_w : x_w) + (size_t)b * L;
+        double s = 0.0;
+        for (int i = threadIdx.x; i < L; i += 256) s += (double)src[i];
+        s = blk_sum_d(s, red) / (double)L;
+        for (int n = threadIdx.x; n < N; n += 256) {
+            const float2 v = *reinterpret_cast<const float2*>(src + 2 * n);
+            z[zp(n)] = make_double2((double)v.x - s, (double)v.y - s);
+        }
+        __syncthreads();
+        smem_fft<LGN>(z, tws);
+        rfft_split(z, N, tw, &s_yN);
+        if (pass == 0) {
+            for (int k = threadIdx.x; k < F; k += 256) {
+                const double2 v = z[zp(k < N ? k : 0)];
+                g[k] = k < N ? v.x * v.x + v.y * v.y : s_yN * s_yN;
+            }
+            __syncthreads();
+            // P = max(conv_same(|Y|^2, ones(9) / 9), 1e-20), the products summed in numpy's order (see periodogram_kernel)
+            double pv[MPT];
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) {
+                const int k = (int)threadIdx.x + 256 * m;
+                double acc = 0.0;
+                if (k < F) {
+                    if (F > 9) {
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            const int i = k + 4 - j;
+                            if (i >= 0 && i < F) acc += g[i] * (1.0 / 9.0);
+                        }
+                    } else acc = g[k];
+                }
+                pv[m] = fmax(acc, 1e-20);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) {
+                const int k = (int)threadIdx.x + 256 * m;
+                if (k < F) {
+                    P[(size_t)b * F + k] = pv[m];
+                    g[k] = 1.0 / sqrt(pv[m]);
+                }
+            }
+            __syncthreads();
+        }
+        irfft_merge_conj(z, N, tw, g, s_yN);
+        smem_fft<LGN>(z, tws);
+        const double sc = 1.0 / (double)N;
+        for (int n = threadIdx.x; n < N; n += 256) {
+            const double2 v = z[zp(n)];
+            *reinterpret_cast<float2*>(dst + 2 * n) = make_float2((float)(v.x * sc), (float)(-v.y * sc));
+        }
+        __syncthreads();
+    }
+}
+
+int g_whiten_fused = 1;       // gwf_set_option("fused", 0): always take the cuFFT path
+extern "C" int gwf_set_option(const char* name, int value) {
+    if (strcmp(name, "fused") == 0) { g_whiten_fused = value; return GW_OK; }
+    gw_set_error("gwf_set_option: unknown option %s", name);
+    return GW_ERR_ARG;
+}
+
 // _whiten_pair_train_like (inference.py:137-153): y, x fp32 [B, L] (x may be NULL) -> y_w, x_w fp32 [B, L], P fp64 [B, L/2+1]
 extern "C" int gwf_whiten_train_like(const float* y, const float* x, int B, int L, float* y_w, float* x_w, double* P, void* work,
                                      void* stream) {
@@ -153,6 +408,27 @@ extern "C" int gwf_whiten_train_like(const float* y, const float* x, int B, int 
     GW_REQUIRE((x == nullptr) == (x_w == nullptr), "gwf_whiten_train_like: x / x_w mismatch");
     cudaStream_t st = (cudaStream_t)stream;
     const int F = L / 2 + 1;
+    if (g_whiten_fused && L >= 64 && L <= 8192 && (L & (L - 1)) == 0) {
+        int lgN = 0;
+        while ((2 << lgN) < L) ++lgN;
+        const double2* tw = nullptr;
+        int rct = get_twiddles(L, st, &tw);
+        if (rct != GW_OK) return rct;
+        const size_t smem = (size_t)(L / 2 + L / 12 + 8 + L / 4 + L / 24 + 8) * sizeof(double2) + (size_t)F * sizeof(double) + 16;
+#define WF_GO(LG)                                                                                                              \
+    case LG:                                                                                                                   \
+        if (smem > 48 * 1024)                                                                                                  \
+            GW_CUDA(cudaFuncSetAttribute(whiten_fused_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        whiten_fused_kernel<LG><<<B, 256, smem, st>>>(y, x, tw, y_w, x_w, P);                                                  \
+        break;
+        switch (lgN) {
+            WF_GO(5) WF_GO(6) WF_GO(7) WF_GO(8) WF_GO(9) WF_GO(10) WF_GO(11) WF_GO(12)
+            default: GW_REQUIRE(false, "gwf_whiten_train_like: fused length %d", L);
+        }
+#undef WF_GO
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
     double* tbuf = (double*)work;
     cufftDoubleComplex* Y = (cufftDoubleComplex*)(tbuf + (size_t)B * L);
     cufftDoubleComplex* Z = Y + (size_t)B * F;

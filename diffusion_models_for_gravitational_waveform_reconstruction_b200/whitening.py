@@ -21,6 +21,7 @@ _lib = None
 _P, _I, _L, _D = C.c_void_p, C.c_int, C.c_long, C.c_double
 _SIGS = {
     "gwf_last_error": ([], C.c_char_p),
+    "gwf_set_option": ([C.c_char_p, _I], _I),
     "gwf_workspace_bytes": ([_I, _I], _L),
     "gwf_whiten_train_like": ([_P, _P, _I, _I, _P, _P, _P, _P, _P], _I),
     "gwf_apply_psd": ([_P, _I, _I, _P, _I, _I, _P, _P, _P, _P], _I),

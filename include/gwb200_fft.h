@@ -18,6 +18,8 @@
 extern "C" {
 #endif
 const char* gwf_last_error(void);
+/* A/B switches: "fused" (default 1): power-of-two L <= 8192 whitens in ONE kernel per call (shared-memory fp64 FFT); 0 = cuFFT path */
+int gwf_set_option(const char* name, int value);
 long gwf_workspace_bytes(int B, int L);
 int gwf_whiten_train_like(const float* y, const float* x, int B, int L, float* y_w, float* x_w, double* P, void* work,
                           void* stream);

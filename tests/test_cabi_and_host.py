@@ -34,7 +34,7 @@ def test_fft_library_exports_every_declared_symbol(lib):
     from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening
     hdr = open(os.path.join(ROOT, "include", "gwb200_fft.h")).read()
     names = set(re.findall(r"^\s*(?:int|long|const char\*)\s+(gwf_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
-    assert names == set(whitening.exported_symbols()) and len(names) == 10
+    assert names == set(whitening.exported_symbols()) and len(names) == 11
     flib = whitening.load()
     for n in names:
         assert hasattr(flib, n)

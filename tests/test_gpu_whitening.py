@@ -118,3 +118,41 @@ def test_welch_whitening_matches_reference_golden(golden_dir, L):
     got = W.interp_grid(torch.from_numpy(fw), torch.from_numpy(Pw), L, 4096.0)[0].cpu().numpy()
     ref = np.interp(np.fft.rfftfreq(L, 1 / 4096.0), fw, Pw, left=Pw[0], right=Pw[-1])
     assert rel(got, ref) <= 1e-13
+
+
+@pytest.mark.parametrize("L", [64, 512, 2048, 4096, 16384])
+def test_fused_whitening_kernel_equals_cufft_path(L):
+    """gwf_whiten_train_like for power-of-two lengths runs in ONE kernel (shared-memory fp64 FFT, whiten.cu::whiten_fused_kernel);
+    against the cuFFT + spectral-kernel path (option fused = 0) and against numpy's float64 recipe (inference.py:137-153)."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening as W
+    rng = np.random.default_rng(L)
+    B = 5
+    t = np.arange(L) / 4096.0
+    y = (rng.standard_normal((B, L)) * 3e-3 + 1e-3 + 2e-3 * np.sin(2 * np.pi * 60.0 * t)).astype(np.float32)
+    x = (rng.standard_normal((B, L)) * 1e-3).astype(np.float32)
+    lib = W.load()
+    outs = {}
+    for fused in (1, 0):
+        assert lib.gwf_set_option(b"fused", fused) == 0
+        try:
+            y_w, x_w, P = W.whiten_train_like(torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda())
+            only_y = W.whiten_train_like(torch.from_numpy(y).cuda())
+        finally:
+            lib.gwf_set_option(b"fused", 1)
+        assert only_y[1] is None and torch.equal(only_y[0], y_w)
+        outs[fused] = (y_w.cpu().numpy(), x_w.cpu().numpy(), P.cpu().numpy())
+    # numpy float64 recipe
+    for b in range(B):
+        y64 = y[b].astype(np.float64) - y[b].astype(np.float64).mean()
+        Y = np.fft.rfft(y64)
+        Pn = np.abs(Y) ** 2
+        if Pn.size > 9:
+            Pn = np.convolve(Pn, np.ones(9) / 9.0, mode="same")
+        Pn = np.maximum(Pn, 1e-20)
+        yw = np.fft.irfft(Y / np.sqrt(Pn), n=L).astype(np.float32)
+        x64 = x[b].astype(np.float64) - x[b].astype(np.float64).mean()
+        xw = np.fft.irfft(np.fft.rfft(x64) / np.sqrt(Pn), n=L).astype(np.float32)
+        for fused in (1, 0):
+            assert rel(outs[fused][2][b], Pn) <= 1e-10, (fused, b, "P")
+            assert rel(outs[fused][0][b], yw) <= 1e-6 and rel(outs[fused][1][b], xw) <= 1e-6, (fused, b)
+    assert rel(outs[1][2], outs[0][2]) <= 1e-12 and rel(outs[1][0], outs[0][0]) <= 1e-6

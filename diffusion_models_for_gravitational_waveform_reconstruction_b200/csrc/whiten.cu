@@ -169,6 +169,7 @@ static int get_twiddles(int L, cudaStream_t st, const double2** out) {
         GW_CUDA(cudaMalloc(&tab, (size_t)(L / 2 + 1) * sizeof(double2)));
         twiddle_kernel<<<gw_cdiv(L / 2 + 1, 256), 256, 0, st>>>(L, tab);
         GW_LAUNCH_CHECK();
+        GW_CUDA(cudaStreamSynchronize(st));                  // one-time: the cached table may be used from any stream afterwards
         it = g_twiddles.emplace(L, tab).first;
     }
     *out = it->second;
@@ -394,6 +395,42 @@ __global__ void __launch_bounds__(256, 2) whiten_fused_kernel(const float* __res
     }
 }
 
+// gwf_apply_psd in one kernel: rfft(sig) * gain(P) -> irfft, gain per `mode` as in spectral_scale_kernel (no mean removal)
+template <int LGN>
+__global__ void __launch_bounds__(256, 2) apply_psd_fused_kernel(const float* __restrict__ sig, const double* __restrict__ P,
+                                                                 long p_b_stride, int mode, const double2* __restrict__ tw,
+                                                                 float* __restrict__ o32, double* __restrict__ o64) {
+    extern __shared__ __align__(16) unsigned char wf_smem[];
+    __shared__ double s_yN;
+    constexpr int N = 1 << LGN, L = 2 * N, F = N + 1;
+    const int b = blockIdx.x;
+    double2* z = reinterpret_cast<double2*>(wf_smem);
+    double2* tws = z + (N + N / 6 + 8);
+    double* g = reinterpret_cast<double*>(tws + (N / 2 + N / 12 + 8));
+    for (int j = threadIdx.x; j < N / 2; j += 256) tws[tw_skew(j)] = tw[2 * j];
+    const float* src = sig + (size_t)b * L;
+    for (int n = threadIdx.x; n < N; n += 256) {
+        const float2 v = *reinterpret_cast<const float2*>(src + 2 * n);
+        z[zp(n)] = make_double2((double)v.x, (double)v.y);
+    }
+    for (int k = threadIdx.x; k < F; k += 256) {
+        const double p = P[(size_t)b * p_b_stride + k];
+        g[k] = mode == 2 ? sqrt(p + 1e-12) : 1.0 / sqrt(mode == 3 ? p + 1e-20 : p + 1e-12);
+    }
+    __syncthreads();
+    smem_fft<LGN>(z, tws);
+    rfft_split(z, N, tw, &s_yN);
+    irfft_merge_conj(z, N, tw, g, s_yN);
+    smem_fft<LGN>(z, tws);
+    const double sc = 1.0 / (double)N;
+    for (int n = threadIdx.x; n < N; n += 256) {
+        const double2 v = z[zp(n)];
+        const double a = v.x * sc, c = -v.y * sc;
+        if (o32 != nullptr) *reinterpret_cast<float2*>(o32 + (size_t)b * L + 2 * n) = make_float2((float)a, (float)c);
+        if (o64 != nullptr) *reinterpret_cast<double2*>(o64 + (size_t)b * L + 2 * n) = make_double2(a, c);
+    }
+}
+
 int g_whiten_fused = 1;       // gwf_set_option("fused", 0): always take the cuFFT path
 extern "C" int gwf_set_option(const char* name, int value) {
     if (strcmp(name, "fused") == 0) { g_whiten_fused = value; return GW_OK; }
@@ -458,6 +495,28 @@ extern "C" int gwf_apply_psd(const float* sig, int B, int L, const double* P, in
     GW_REQUIRE(B > 0 && L >= 2 && sig && P && work && (o32 || o64) && (mode >= 1 && mode <= 3), "gwf_apply_psd: arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int F = L / 2 + 1;
+    if (g_whiten_fused && L >= 64 && L <= 8192 && (L & (L - 1)) == 0) {
+        int lgN = 0;
+        while ((2 << lgN) < L) ++lgN;
+        const double2* tw = nullptr;
+        int rct = get_twiddles(L, st, &tw);
+        if (rct != GW_OK) return rct;
+        const size_t smem = (size_t)(L / 2 + L / 12 + 8 + L / 4 + L / 24 + 8) * sizeof(double2) + (size_t)F * sizeof(double) + 16;
+        const long pbs = p_shared ? 0 : F;
+#define AP_GO(LG)                                                                                                              \
+    case LG:                                                                                                                   \
+        if (smem > 48 * 1024)                                                                                                  \
+            GW_CUDA(cudaFuncSetAttribute(apply_psd_fused_kernel<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        apply_psd_fused_kernel<LG><<<B, 256, smem, st>>>(sig, P, pbs, mode, tw, o32, o64);                                     \
+        break;
+        switch (lgN) {
+            AP_GO(5) AP_GO(6) AP_GO(7) AP_GO(8) AP_GO(9) AP_GO(10) AP_GO(11) AP_GO(12)
+            default: GW_REQUIRE(false, "gwf_apply_psd: fused length %d", L);
+        }
+#undef AP_GO
+        GW_LAUNCH_CHECK();
+        return GW_OK;
+    }
     double* tbuf = (double*)work;
     cufftDoubleComplex* Y = (cufftDoubleComplex*)(tbuf + (size_t)B * L);
     cufftDoubleComplex* Z = Y + (size_t)B * F;

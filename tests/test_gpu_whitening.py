@@ -156,3 +156,32 @@ def test_fused_whitening_kernel_equals_cufft_path(L):
             assert rel(outs[fused][2][b], Pn) <= 1e-10, (fused, b, "P")
             assert rel(outs[fused][0][b], yw) <= 1e-6 and rel(outs[fused][1][b], xw) <= 1e-6, (fused, b)
     assert rel(outs[1][2], outs[0][2]) <= 1e-12 and rel(outs[1][0], outs[0][0]) <= 1e-6
+
+
+@pytest.mark.parametrize("L", [256, 4096, 8192])
+@pytest.mark.parametrize("shared", [False, True])
+def test_fused_apply_psd_equals_cufft_path(L, shared):
+    """gwf_apply_psd (model-PSD whitening, the loader's 1e-20-floor variant, de-whitening; inference.py:155-159, 190-203,
+    dataloader.py:127-143) in one kernel for power-of-two lengths, against the cuFFT path and numpy."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import whitening as W
+    rng = np.random.default_rng(L + shared)
+    B = 4
+    sig = (rng.standard_normal((B, L)) * 2e-3 + 5e-4).astype(np.float32)
+    P = np.abs(rng.standard_normal((L // 2 + 1,) if shared else (B, L // 2 + 1))) * 1e-6 + 1e-9
+    lib = W.load()
+    for dewhiten, floor in [(False, False), (False, True), (True, False)]:
+        outs = {}
+        for fused in (1, 0):
+            assert lib.gwf_set_option(b"fused", fused) == 0
+            try:
+                o64 = W.apply_psd(torch.from_numpy(sig).cuda(), torch.from_numpy(P).cuda(), dewhiten, torch.float64, loader_floor=floor)
+                o32 = W.apply_psd(torch.from_numpy(sig).cuda(), torch.from_numpy(P).cuda(), dewhiten, torch.float32, loader_floor=floor)
+            finally:
+                lib.gwf_set_option(b"fused", 1)
+            outs[fused] = (o64.cpu().numpy(), o32.cpu().numpy())
+        Y = np.fft.rfft(sig.astype(np.float64), axis=1)
+        gain = np.sqrt(P + 1e-12) if dewhiten else 1.0 / np.sqrt(P + (1e-20 if floor else 1e-12))
+        ref = np.fft.irfft(Y * gain, n=L, axis=1)
+        for fused in (1, 0):
+            assert rel(outs[fused][0], ref) <= 1e-12, (fused, dewhiten, floor)
+            assert rel(outs[fused][1], ref) <= 1e-6

@@ -188,7 +188,10 @@ class File:
                 bt, heap = struct.unpack_from("<QQ", d, 0)
                 self._walk_group(bt, self._local_heap(heap))
             elif t == 0xC:
-                k, v = self._parse_attr(d)
+                try:
+                    k, v = self._parse_attr(d)
+                except (NotImplementedError, struct.error, ValueError, KeyError):
+                    continue                                   # an attribute of a type outside the subset must not make the file unreadable
                 self.attrs[k] = v
         self._cache: Dict[str, Dataset] = {}
 

@@ -382,7 +382,6 @@ __global__ void __launch_bounds__(256) gen_gn_bwd_sums_kernel(const T* __restric
         const float d_y = d_u * gen_dsilu(y);
         s[0] += d_o; s[1] += (double)d_o * u; s[2] += d_y; s[3] += (double)d_y * xh; s[4] += xh;
         for (int j = 0; j < A.Cc; ++j) s[5 + j] += (double)d_u * cr[j];
-        if (A.Cc == 0) s[5] += 0.0;
     }
     // sum of d_u itself (d_bc) = S[0] (1 + gamma): no extra slot needed
     for (int j = 0; j < 5 + A.Cc; ++j) {

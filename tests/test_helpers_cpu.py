@@ -69,3 +69,36 @@ def test_stratified_timesteps_cover_every_stratum():
         torch.manual_seed(3)
         a2 = _sample_timesteps_stratified(bsz, t_min, t_max, "cpu", bins=bins)
         assert torch.equal(a1, a2)
+
+
+def test_sweep_sample_combo_consumes_the_rngs_in_reference_order():
+    """sweep.sample_combo mirrors the nested `sample_combo` of sweep_infer.py:291-303, which draws from the GLOBAL `random` and
+    `np.random` streams in a fixed order (cfg-mode coin, start_snr, cfg_scale, cfg_center, cfg_width from numpy; dc_weight,
+    init_mode, eta choices from `random`): with the same seeds a reference run and this one must visit the same combinations."""
+    import math
+    import random
+    import types
+    import numpy as np
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import sweep as S
+    a = types.SimpleNamespace(cfg_mode="auto", start_snr_min=5.0, start_snr_max=40.0, cfg_min=1.0, cfg_max=3.0, cfg_center_min=0.5,
+                              cfg_center_max=0.9, cfg_width_min=0.05, cfg_width_max=0.3, dc_choices=[0.0, 0.05, 0.1],
+                              init_choices=["noise", "y-blend"], eta_choices=[0.0, 0.5, 1.0])
+    random.seed(7)
+    np.random.seed(7)
+    got = [S.sample_combo(a) for _ in range(5)]
+    random.seed(7)
+    np.random.seed(7)
+    for c in got:
+        coin = random.random()
+        u = [np.random.uniform(lo, hi) for lo, hi in [(math.log10(5.0), math.log10(40.0)), (1.0, 3.0), (0.5, 0.9), (0.05, 0.3)]]
+        dc, init, eta = random.choice(a.dc_choices), random.choice(a.init_choices), random.choice(a.eta_choices)
+        assert c["cfg_mode"] == ("gauss" if coin < 0.7 else "const")
+        assert c["start_snr"] == 10 ** u[0] and c["cfg_scale"] == u[1] and c["cfg_center"] == u[2] and c["cfg_width"] == u[3]
+        assert (c["dc_weight"], c["init_mode"], c["eta"]) == (float(dc), init, float(eta))
+    a.cfg_mode = "const"                                       # a fixed mode draws no coin
+    random.seed(1)
+    S.sample_combo(a)
+    r_after = random.random()
+    random.seed(1)
+    random.choice(a.dc_choices), random.choice(a.init_choices), random.choice(a.eta_choices)
+    assert random.random() == r_after

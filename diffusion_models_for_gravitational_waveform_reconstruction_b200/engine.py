@@ -223,7 +223,7 @@ class UNetEngine:
         # inference: first block in one pass with ANALYTIC GroupNorm statistics (conv_in_direct.cu) instead of the exchange-based
         # conv_in_gn kernel.  Measured on B200 (B=256, L=4096, in_ch=3; profiles/r02_first_block.md): moments 25 us + one-pass
         # kernel 79 us vs 107 us for conv_in_gn -- a wash so far, so the parity-tested kernel stays an option
-        self.direct_first = False
+        self.direct_first = os.environ.get("GWB200_DIRECT_FIRST", "0") not in ("0", "")
         self._fuse_ok: Dict[tuple, bool] = {}
         self.flat: Optional[Tensor] = None          # set by bind_flat(): params are views of one ParamLayout buffer
         self.layout: Optional[ParamLayout] = None

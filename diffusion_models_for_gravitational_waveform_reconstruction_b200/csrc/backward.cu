@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_bf16_kernel(GnBwdArgs a, 
 
 int g_gn_bwd_stream = 1;
 extern int g_final_stream;
-extern int g_pdl, g_conv_in_mma, g_wgrad_in_mma, g_cgn_pair2;
+extern int g_pdl, g_conv_in_mma, g_wgrad_in_mma, g_cgn_pair2, g_cgn_one_group;
 extern int g_gn_bwd_fused, g_gn_bwd_fused_slice;
 extern int g_gn_bwd_stats_fast;
 extern "C" int gw_set_option(const char* name, int value) {
@@ -878,6 +878,7 @@ extern "C" int gw_set_option(const char* name, int value) {
     if (strcmp(name, "gn_bwd_fused_slice") == 0) { g_gn_bwd_fused_slice = value; return GW_OK; }
     if (strcmp(name, "final_stream") == 0) { g_final_stream = value; return GW_OK; }
     if (strcmp(name, "pdl") == 0) { g_pdl = value; return GW_OK; }
+    if (strcmp(name, "one_group") == 0) { g_cgn_one_group = value; return GW_OK; }
     if (strcmp(name, "pair2") == 0) { g_cgn_pair2 = value; return GW_OK; }
     if (strcmp(name, "final_bwd_stream") == 0) { g_final_bwd_stream = value; return GW_OK; }
     if (strcmp(name, "conv_in_mma") == 0) { g_conv_in_mma = value; return GW_OK; }

@@ -245,7 +245,10 @@ __device__ __forceinline__ void stat_reduce(float (&sv)[2 * (64 >> CG_LOG2)], fl
 // position instead of streaming the 128 B row back in).
 // PAIR2: CTA pairs (cluster of 2, tcgen05 cta_group::2), a compile-time flavour: a kernel that contains .2CTA instructions can
 // only be launched with an even cluster size.
-template <int CG_LOG2, int MT, int CC, bool POOL, bool HEAD = false, bool PAIR2 = false>
+// ONE_T: the 16 epilogue warps form ONE group that works on every sample (one 32 x 64 chunk per warp) instead of two warpgroups on
+// alternate samples -- the flavour for launches in which a CTA sees a single sample (batch <= number of CTA groups: the second
+// warpgroup would otherwise idle); +6 % on the B = 8 chain, -2 % at B = 256 (profiles/r02_one_group.md).
+template <int CG_LOG2, int MT, int CC, bool POOL, bool HEAD = false, bool PAIR2 = false, bool ONE_T = (CGN_ONE_GROUP != 0)>
 __global__ void __launch_bounds__(CGN_THREADS, 1)
 conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out,
@@ -281,7 +284,6 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
     // chaining: monotonic per-warpgroup arrival counters "my stores of a sample completed" (an mbarrier's phase parity would alias:
     // nothing stops the epilogue from completing two samples before the signalling thread has looked)
     auto sig_cnt = [&](int i) { return smem_u32(bars + 2 * SA + 2 * SB + 4 + i); };
-    static_assert(CGN_ONE_GROUP == 0, "the chain-signalling barriers count the 8 warps of one epilogue warpgroup");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = F.G;
@@ -480,7 +482,9 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         if (lane == 0 && F.done_flag != nullptr) {
             int it = 0;
             for (int b = grp; b < F.B; b += F.n_groups, ++it) {
-                const uint32_t need = 8u * (uint32_t)((it >> 1) + 1), sc = sig_cnt(it & 1);
+                // two warpgroups on alternate samples: 8 warps arrive per sample of a group; ONE group: all 16 warps, every sample
+                const uint32_t need = ONE_T ? 16u * (uint32_t)(it + 1) : 8u * (uint32_t)((it >> 1) + 1);
+                const uint32_t sc = sig_cnt(ONE_T ? 0 : (it & 1));
                 const long long t0 = clock64();
                 for (;;) {
                     uint32_t v;
@@ -494,7 +498,7 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         }
     } else {
         // ===================== epilogue (warps 2..17) =====================
-        constexpr bool ONE = CGN_ONE_GROUP != 0;
+        constexpr bool ONE = ONE_T;
         constexpr int NT = ONE ? 512 : 256;           // threads of one epilogue group
         const int eg = ONE ? 0 : (warp - 2) >> 3;     // epilogue warpgroup: samples it = eg, eg + GROUPS, ... of this CTA
         const int e = ONE ? (warp - 2) : ((warp - 2) & 7);
@@ -621,9 +625,12 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             load_cond(b, (ONE && MT == 2) ? kc_lo : 0, cd);
             // ---- exchange: publish this CTA's 16 sums, collect the G x 16 sums of the group
             if (tid < 16) {
+                // fixed summation order, the same in both epilogue flavours (a sample's result must not depend on how many samples
+                // the launch carries): per warp slot the two chunks first -- one warp adds them in the two-group flavour, warps w
+                // and w + 8 hold them in the single-group flavour -- then the eight slots in order
                 float v = 0.0f;
 #pragma unroll
-                for (int w = 0; w < NT / 32; ++w) v += s_stat[w * 16 + tid];
+                for (int w = 0; w < 8; ++w) v += ONE ? s_stat[w * 16 + tid] + s_stat[(w + 8) * 16 + tid] : s_stat[w * 16 + tid];
                 st_relaxed_u64(F.xchg + ((size_t)b * CGN_MAX_G + j_cta) * 16 + tid,
                                ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v));
             }
@@ -812,6 +819,8 @@ struct CgnPlan {
 // twice as deep -- leaves every layer's MMA-issue time unchanged (dec0: 20.0 k vs 20.3 k cycles per sample slice), i.e. the
 // operand supply is not what paces the MMA warp; it stays a parity-tested option, off by default.
 int g_cgn_pair2 = 0;
+// gw_set_option("one_group", 0/1): allow the single-group epilogue flavour for launches with at most one sample per CTA group
+int g_cgn_one_group = 1;
 
 static int cgn_plan(const gw_conv_tc_shape* s, int Cc, bool pool, CgnPlan* pl) {
     int rc = build_params(s, &pl->P, true);
@@ -954,10 +963,17 @@ extern "C" int gw_conv_gn3(const gw_conv_tc_shape* s, const void* src0, const vo
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = pl.G * pl.n_groups, smem = pl.smem;
     const bool pool = pooled != nullptr;
+    // one sample per CTA group at most: the single-group epilogue flavour (all 16 warps on that sample)
+    const bool one = !pl.pair2 && g_cgn_one_group != 0 && s->B <= pl.n_groups;
+#define CGN_GO3(LG, MTV, CCV, PL, HD, P2, ON)                                                                             \
+    do {                                                                                                                  \
+        GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2, ON>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        GW_CUDA(gw_launch_cluster(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2, ON>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, P2 ? 2 : 1, chained, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+    } while (0)
 #define CGN_GO2(LG, MTV, CCV, PL, HD, P2)                                                                                 \
     do {                                                                                                                  \
-        GW_CUDA(cudaFuncSetAttribute(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        GW_CUDA(gw_launch_cluster(conv_gn_kernel<LG, MTV, CCV, PL, HD, P2>, dim3(grid), dim3(CGN_THREADS), (size_t)smem, st, P2 ? 2 : 1, chained, ta0, ta1, tw, to, tr, tp, P, F, bias)); \
+        if (!(P2) && one) CGN_GO3(LG, MTV, CCV, PL, HD, false, true);                                                     \
+        else CGN_GO3(LG, MTV, CCV, PL, HD, P2, (CGN_ONE_GROUP != 0));                                                     \
     } while (0)
 #define CGN_GO(LG, MTV, CCV, PL)                                  \
     do {                                                          \
@@ -987,6 +1003,7 @@ extern "C" int gw_conv_gn3(const gw_conv_tc_shape* s, const void* src0, const vo
 #undef CGN_CC
 #undef CGN_GO
 #undef CGN_GO2
+#undef CGN_GO3
     GW_LAUNCH_CHECK();
     return GW_OK;
 }

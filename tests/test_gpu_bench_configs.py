@@ -261,3 +261,27 @@ def test_layer_chaining_is_bit_identical(use_graph):
         assert torch.equal(a, b)
         outs[chain] = a
     assert torch.equal(outs[False], outs[True])
+
+
+@pytest.mark.parametrize("in_ch,cc", [(3, 1), (7, 5)])
+def test_single_group_epilogue_flavour_is_bit_identical(in_ch, cc):
+    """conv_gn_kernel<..., ONE_T>: launches that carry at most one sample per CTA group let all 16 epilogue warps work on that sample
+    (the second warpgroup would idle).  The statistics are summed in the same order in both flavours, so a sample's result does
+    not depend on the batch it travels in: small batch (single-group flavour) == the same samples inside a large batch (two
+    warpgroups) == the small batch with the flavour switched off."""
+    from diffusion_models_for_gravitational_waveform_reconstruction_b200 import CustomDiffusion, _cabi
+    L, B = 4096, 40
+    lib = _cabi.load()
+    diff = CustomDiffusion(T=1000, device="cuda")
+    data = synthetic_chirps(B, L, snr=10.0, seed=81)["y_norm"]
+    y = data if cc == 1 else torch.cat([data, gaussian((B, 4, 1), seed=6).expand(B, 4, L).contiguous() * 0.3], dim=1)
+    kw = dict(steps=6, eta=1.0, start_t=289)
+    big = _sample(_model(in_ch, cc, seed=1, dtype="bf16"), diff, y, kw, seed=5, sample0=0)
+    small = _sample(_model(in_ch, cc, seed=1, dtype="bf16"), diff, y[:6], kw, seed=5, sample0=0)
+    assert lib.gw_set_option(b"one_group", 0) == 0
+    try:
+        small_two = _sample(_model(in_ch, cc, seed=1, dtype="bf16"), diff, y[:6], kw, seed=5, sample0=0)
+    finally:
+        lib.gw_set_option(b"one_group", 1)
+    assert torch.equal(small, small_two)
+    assert torch.equal(small, big[:6])

@@ -34,8 +34,12 @@ int gw_version(void);
  * "gn_bwd_stats_fast" (1 = their compile-time-specialised versions + analytic conv-bias gradient, default),
  * "gn_bwd_fused" / "gn_bwd_fused_slice" (one-pass GroupNorm backward of gw_gn_bwd2: enable, largest shared-memory slice in bytes),
  * "final_stream" (1 = HBM-streaming head + update kernel for bf16 / C = 64, default),
- * "pdl" (1 = the fused inference kernels are launched with programmatic stream serialization, default: a kernel's prologue
- *  overlaps the previous kernel's tail; every such kernel executes griddepcontrol.wait before it touches activations) */
+ * "pdl" (1 = kernels are launched with programmatic stream serialization: a kernel's launch overlaps the previous kernel's tail,
+ *  every kernel executes griddepcontrol.wait before it touches memory; default 0 -- measured without gain inside CUDA graphs),
+ * "pair2" (1 = CTA-pair flavour of the fused conv block kernel, tcgen05 cta_group::2; default 0),
+ * "one_group" (1 = launches with at most one sample per CTA group use the single-group epilogue flavour; default 1; results are
+ *  bit-identical either way), "conv_in_mma" / "wgrad_in_mma" / "final_bwd_stream" (first-layer and head kernels: tensor-core /
+ *  streaming versions, default 1) */
 int gw_set_option(const char* name, int value);
 const char* gw_last_error(void);
 int gw_device_info(int* sm_count, int* cc_major, int* cc_minor);
